@@ -1,0 +1,268 @@
+"""ctypes bindings for the parity oracle (TEST INFRASTRUCTURE ONLY).
+
+Two libraries, both built by oracle/Makefile:
+  * libngt_oracle.so  -- the C restatement (oracle/ngt_oracle.c), kind "port"
+  * _ref/libngt_ref.so -- the unmodified reference compiled from /root/reference plus
+                          oracle/ref_shim.cpp, kind "reference"
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import
+this module. The product package ngt_b200 never does.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PORT_SO = os.path.join(HERE, "libngt_oracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libngt_ref.so")
+
+# ObjectSpace.h:166-186
+L1, L2, HAMMING, ANGLE, COSINE, NORMALIZED_ANGLE, NORMALIZED_COSINE, JACCARD = range(8)
+NORMALIZED_L2 = 9
+UINT8, FLOAT = 1, 2
+
+_u32p = np.ctypeslib.ndpointer(np.uint32, flags="C")
+_u64p = np.ctypeslib.ndpointer(np.uint64, flags="C")
+_f32p = np.ctypeslib.ndpointer(np.float32, flags="C")
+
+
+def build(ref=True):
+    """Compile the restatement and, when /root/reference is present, the reference itself."""
+    subprocess.check_call(["make", "-s", "-C", HERE, "oracle"])
+    if ref and os.path.isdir("/root/reference"):
+        subprocess.check_call(["make", "-s", "-j8", "-C", HERE, "ref"])
+
+
+def padded_dimension(dim):
+    return ((dim - 1) // 16 + 1) * 16
+
+
+def pad_objects(x, otype):
+    """[n, dim] -> [(n+1), padded] with the dummy row 0 (1-based ids), zero padded (ObjectSpace.h:357-400)."""
+    x = np.asarray(x)
+    n, dim = x.shape
+    dt = np.uint8 if otype == UINT8 else np.float32
+    out = np.zeros((n + 1, padded_dimension(dim)), dtype=dt)
+    out[1:, :dim] = x.astype(dt)
+    return out
+
+
+def pad_queries(q, otype):
+    q = np.asarray(q)
+    dt = np.uint8 if otype == UINT8 else np.float32
+    out = np.zeros((q.shape[0], padded_dimension(q.shape[1])), dtype=dt)
+    out[:, : q.shape[1]] = q.astype(dt)
+    return out
+
+
+class Port:
+    """The C restatement."""
+
+    def __init__(self):
+        if not os.path.exists(PORT_SO):
+            build(ref=False)
+        self.lib = lib = C.CDLL(PORT_SO)
+        lib.ngto_distance.restype = C.c_double
+        lib.ngto_distance.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
+        lib.ngto_set_simd.argtypes = [C.c_int, C.c_int]
+        lib.ngto_normalize.argtypes = [_f32p, C.c_size_t]
+        lib.ngto_edge_size.restype = C.c_int64
+        lib.ngto_edge_size.argtypes = [C.c_int64, C.c_int64, C.c_float, C.c_int64, C.c_int64]
+        lib.ngto_recall.restype = C.c_double
+        lib.ngto_recall.argtypes = [_u32p, _f32p, C.c_size_t, _u32p, _f32p, C.c_size_t]
+        lib.ngto_batch_linear_search.argtypes = [
+            C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p,
+            C.c_size_t, C.c_size_t, C.c_double, C.c_size_t, _u32p, _f32p, _u32p]
+        lib.ngto_batch_graph_search.argtypes = [
+            C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, _u64p, _u32p, C.c_void_p,
+            C.c_size_t, C.c_size_t, _u32p, C.c_size_t, C.c_size_t, C.c_float, C.c_float, C.c_int64,
+            _u32p, _f32p, _u32p, C.c_void_p]
+
+    def set_simd(self, lanes, fma):
+        self.lib.ngto_set_simd(lanes, int(fma))
+
+    def distance(self, dtype, otype, a, b):
+        a = np.ascontiguousarray(a)
+        b = np.ascontiguousarray(b)
+        return self.lib.ngto_distance(dtype, otype, a.ctypes.data, b.ctypes.data, a.shape[-1])
+
+    def normalize(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float32).copy()
+        for i in range(x.shape[0]):
+            row = x[i]
+            if self.lib.ngto_normalize(row, row.shape[0]) != 0:
+                raise ValueError("zero vector")
+        return x
+
+    def edge_size(self, sc_edge_size, prop_edge_size_for_search, exploration_coefficient, dyn_base, dyn_rate):
+        return self.lib.ngto_edge_size(sc_edge_size, prop_edge_size_for_search, exploration_coefficient,
+                                       dyn_base, dyn_rate)
+
+    def recall(self, ids, dists, gt_ids, gt_dists):
+        ids = np.ascontiguousarray(ids, np.uint32)
+        dists = np.ascontiguousarray(dists, np.float32)
+        gt_ids = np.ascontiguousarray(gt_ids, np.uint32)
+        gt_dists = np.ascontiguousarray(gt_dists, np.float32)
+        return self.lib.ngto_recall(ids, dists, ids.size, gt_ids, gt_dists, gt_ids.size)
+
+    def mean_recall(self, ids, dists, counts, gt_ids, gt_dists):
+        tot = 0.0
+        for q in range(ids.shape[0]):
+            c = int(counts[q])
+            tot += self.recall(ids[q, :c], dists[q, :c], gt_ids[q], gt_dists[q])
+        return tot / ids.shape[0]
+
+    def linear_search(self, dtype, otype, objects, queries, k, radius=-1.0, valid=None):
+        """objects: padded [(n+1), pad]; queries: padded [nq, pad]."""
+        objects = np.ascontiguousarray(objects)
+        queries = np.ascontiguousarray(queries)
+        n = objects.shape[0] - 1
+        nq = queries.shape[0]
+        ids = np.zeros((nq, k), np.uint32)
+        dists = np.zeros((nq, k), np.float32)
+        counts = np.zeros(nq, np.uint32)
+        vp = None
+        if valid is not None:
+            valid = np.ascontiguousarray(valid, np.uint8)
+            vp = valid.ctypes.data
+        self.lib.ngto_batch_linear_search(dtype, otype, objects.ctypes.data, objects.strides[0], n, vp,
+                                          objects.shape[1], queries.ctypes.data, queries.strides[0], nq,
+                                          float(radius), k, ids, dists, counts)
+        return ids, dists, counts
+
+    def graph_search(self, dtype, otype, objects, row_ptr, col, queries, seeds, k, epsilon, radius=-1.0,
+                     edge_size=2 ** 31 - 1):
+        objects = np.ascontiguousarray(objects)
+        queries = np.ascontiguousarray(queries)
+        row_ptr = np.ascontiguousarray(row_ptr, np.uint64)
+        col = np.ascontiguousarray(col, np.uint32)
+        seeds = np.ascontiguousarray(seeds, np.uint32)
+        n = objects.shape[0] - 1
+        nq = queries.shape[0]
+        ids = np.zeros((nq, k), np.uint32)
+        dists = np.zeros((nq, k), np.float32)
+        counts = np.zeros(nq, np.uint32)
+        stats = np.zeros((nq, 3), np.uint64)
+        self.lib.ngto_batch_graph_search(dtype, otype, objects.ctypes.data, objects.strides[0], n,
+                                         objects.shape[1], row_ptr, col, queries.ctypes.data,
+                                         queries.strides[0], nq, seeds, seeds.shape[1], k, epsilon, radius,
+                                         edge_size, ids, dists, counts, stats.ctypes.data)
+        return ids, dists, counts, stats
+
+
+class Ref:
+    """The unmodified reference behind oracle/ref_shim.cpp."""
+
+    def __init__(self):
+        if not os.path.exists(REF_SO):
+            raise FileNotFoundError(REF_SO + " (build it with `make -C oracle ref` where /root/reference exists)")
+        self.lib = lib = C.CDLL(REF_SO)
+        lib.ref_last_error.restype = C.c_char_p
+        lib.ref_build_index.argtypes = [C.c_char_p, _f32p, C.c_size_t, C.c_int, C.c_char, C.c_int, C.c_int,
+                                        C.c_int, C.c_char, C.c_int]
+        lib.ref_build_onng.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int]
+        lib.ref_open.restype = C.c_void_p
+        lib.ref_open.argtypes = [C.c_char_p, C.c_int]
+        lib.ref_close.argtypes = [C.c_void_p]
+        lib.ref_info.argtypes = [C.c_void_p, np.ctypeslib.ndpointer(np.int64, flags="C")]
+        lib.ref_get_object.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
+        lib.ref_export_graph.restype = C.c_int64
+        lib.ref_export_graph.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.ref_search.argtypes = [C.c_void_p, _f32p, C.c_size_t, C.c_int, C.c_size_t, C.c_float, C.c_float,
+                                   C.c_int, C.c_void_p, C.c_size_t, _u32p, _f32p, _u32p, C.c_void_p, C.c_int,
+                                   C.POINTER(C.c_double)]
+        lib.ref_linear_search.argtypes = [C.c_void_p, _f32p, C.c_size_t, C.c_int, C.c_size_t, C.c_float, _u32p,
+                                          _f32p, _u32p, C.c_int, C.POINTER(C.c_double)]
+        lib.ref_max_threads.restype = C.c_int
+        lib.ref_tree_seeds.argtypes = [C.c_void_p, _f32p, C.c_size_t, C.c_int, C.c_size_t, _u32p, C.c_size_t, _u32p]
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError(self.lib.ref_last_error().decode())
+
+    def max_threads(self):
+        return self.lib.ref_max_threads()
+
+    def build_index(self, path, data, objtype="f", disttype=L2, edge_creation=10, edge_search=40,
+                    indextype="t", threads=8):
+        data = np.ascontiguousarray(data, np.float32)
+        self._check(self.lib.ref_build_index(path.encode(), data, data.shape[0], data.shape[1],
+                                             objtype.encode(), disttype, edge_creation, edge_search,
+                                             indextype.encode(), threads))
+
+    def build_onng(self, anng, onng, outgoing=10, incoming=120, shortcut=True):
+        self._check(self.lib.ref_build_onng(anng.encode(), onng.encode(), outgoing, incoming, int(shortcut)))
+
+    def open(self, path, readonly=False):
+        h = self.lib.ref_open(path.encode(), int(readonly))
+        if not h:
+            raise RuntimeError(self.lib.ref_last_error().decode())
+        return h
+
+    def close(self, h):
+        self.lib.ref_close(h)
+
+    def info(self, h):
+        a = np.zeros(10, np.int64)
+        self._check(self.lib.ref_info(h, a))
+        keys = ["repo_size", "dim", "padded", "object_type", "distance_type", "edge_size_for_search",
+                "dyn_base", "dyn_rate", "seed_size", "byte_size"]
+        return dict(zip(keys, [int(v) for v in a]))
+
+    def objects(self, h):
+        """Stored object bytes as [n, dim] array of the object type (unpadded; normalised if applicable)."""
+        inf = self.info(h)
+        n = inf["repo_size"] - 1
+        dt = np.uint8 if inf["object_type"] == UINT8 else np.float32
+        out = np.zeros((n, inf["byte_size"] // np.dtype(dt).itemsize), dt)
+        for i in range(n):
+            self._check(self.lib.ref_get_object(h, i + 1, out[i].ctypes.data))
+        return out
+
+    def graph(self, h):
+        nnz = self.lib.ref_export_graph(h, None, None, None)
+        if nnz < 0:
+            raise RuntimeError(self.lib.ref_last_error().decode())
+        rs = self.info(h)["repo_size"]
+        row_ptr = np.zeros(rs + 1, np.uint64)
+        col = np.zeros(max(nnz, 1), np.uint32)
+        dist = np.zeros(max(nnz, 1), np.float32)
+        self.lib.ref_export_graph(h, row_ptr.ctypes.data, col.ctypes.data, dist.ctypes.data)
+        return row_ptr, col[:nnz], dist[:nnz]
+
+    def search(self, h, queries, k, epsilon=0.1, radius=-1.0, edge_size=-1, seeds=None, threads=1, stats=True):
+        queries = np.ascontiguousarray(queries, np.float32)
+        nq, dim = queries.shape
+        ids = np.zeros((nq, k), np.uint32)
+        dists = np.zeros((nq, k), np.float32)
+        counts = np.zeros(nq, np.uint32)
+        st = np.zeros((nq, 2), np.uint64)
+        sec = C.c_double(0)
+        sp, ns = None, 0
+        if seeds is not None:
+            seeds = np.ascontiguousarray(seeds, np.uint32)
+            sp, ns = seeds.ctypes.data, seeds.shape[1]
+        self._check(self.lib.ref_search(h, queries, nq, dim, k, epsilon, radius, edge_size, sp, ns, ids, dists,
+                                        counts, st.ctypes.data if stats else None, threads, C.byref(sec)))
+        return ids, dists, counts, st, sec.value
+
+    def tree_seeds(self, h, queries, k, max_seeds=128):
+        queries = np.ascontiguousarray(queries, np.float32)
+        nq, dim = queries.shape
+        seeds = np.zeros((nq, max_seeds), np.uint32)
+        ns = np.zeros(nq, np.uint32)
+        self._check(self.lib.ref_tree_seeds(h, queries, nq, dim, k, seeds, max_seeds, ns))
+        return seeds, ns
+
+    def linear_search(self, h, queries, k, radius=-1.0, threads=1):
+        queries = np.ascontiguousarray(queries, np.float32)
+        nq, dim = queries.shape
+        ids = np.zeros((nq, k), np.uint32)
+        dists = np.zeros((nq, k), np.float32)
+        counts = np.zeros(nq, np.uint32)
+        sec = C.c_double(0)
+        self._check(self.lib.ref_linear_search(h, queries, nq, dim, k, radius, ids, dists, counts, threads,
+                                               C.byref(sec)))
+        return ids, dists, counts, sec.value
