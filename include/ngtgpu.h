@@ -1,0 +1,129 @@
+/*
+ * ngtgpu.h -- C ABI of the B200 (sm_100a) engine for NGT's data-parallel hot path.
+ *
+ * This is the whole drop-in boundary: plain pointers and sizes, integer status codes, no
+ * exceptions, no torch/C++ types. The reference (NGT v1.13.8, /root/reference) would bind these
+ * symbols from the seams listed next to each function; INTEGRATION.md shows the few lines a
+ * maintainer adds on the reference side. There is no CPU fallback: without a CUDA device every
+ * call fails with NGTGPU_ERR_NO_DEVICE.
+ *
+ * Conventions shared with the reference
+ *   - object ids are 1-based, id 0 is the dummy slot          (lib/NGT/Common.h:1704-1720)
+ *   - results are ascending by (distance, id)                  (lib/NGT/Common.h:1946-1959)
+ *   - distances are float, the id type is uint32               (lib/NGT/Common.h:46-47)
+ *   - object/distance type codes are the reference's enums     (lib/NGT/ObjectSpace.h:166-186)
+ *   - rows are zero padded to 16 elements                      (lib/NGT/ObjectSpace.h:249)
+ *
+ * Every function returns NGTGPU_OK (0) or an NGTGPU_ERR_* code; ngtgpu_last_error() returns the
+ * message of the calling thread's last failure (the `Capi : f() : Error: what` string the C API
+ * layer of the reference puts into NGTError, lib/NGT/Capi.cpp:25-38, is built from it).
+ */
+#ifndef NGTGPU_H
+#define NGTGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NGTGPU_OK 0
+#define NGTGPU_ERR_INVALID 1    /* bad argument / unsupported type combination            */
+#define NGTGPU_ERR_CUDA 2       /* a CUDA runtime call failed                              */
+#define NGTGPU_ERR_NO_DEVICE 3  /* no usable sm_100 device: there is no CPU fallback       */
+#define NGTGPU_ERR_STATE 4      /* call order (e.g. search before objects/graph are set)   */
+#define NGTGPU_ERR_ZERO_VECTOR 5 /* zero vector given to a normalised space (ObjectSpace.h:256-260) */
+
+/* lib/NGT/ObjectSpace.h:182-186 */
+#define NGTGPU_OBJECT_UINT8 1
+#define NGTGPU_OBJECT_FLOAT 2
+/* lib/NGT/ObjectSpace.h:166-180 */
+#define NGTGPU_DISTANCE_L2 1
+#define NGTGPU_DISTANCE_HAMMING 2
+#define NGTGPU_DISTANCE_ANGLE 3
+#define NGTGPU_DISTANCE_COSINE 4
+#define NGTGPU_DISTANCE_NORMALIZED_ANGLE 5
+#define NGTGPU_DISTANCE_NORMALIZED_COSINE 6
+#define NGTGPU_DISTANCE_NORMALIZED_L2 9
+
+typedef struct ngtgpu_index ngtgpu_index; /* opaque; one per (index, device) */
+
+/* Per-call search settings == the fields of NGT::SearchContainer a caller can set
+ * (lib/NGT/Common.h:2029-2046) == NGTQuery (lib/NGT/Capi.h:40-47). */
+typedef struct {
+  uint32_t size;      /* k; 0 returns no results (Index.h:1141-1144)                          */
+  float epsilon;      /* explorationCoefficient = (float)(epsilon + 1.0) (Common.h:2041)      */
+  float radius;       /* < 0 means unbounded (FLT_MAX), as Capi.cpp:384-386                   */
+  int64_t edge_size;  /* -1 index property, 0 all edges, >0 cap, -2 dynamic (Graph.h:675-692) */
+} ngtgpu_search_params;
+
+const char *ngtgpu_last_error(void);
+int ngtgpu_device_count(int *count);
+
+/* ---- index life cycle: replaces GraphIndex construction + loadIndex
+ *      (lib/NGT/Index.cpp:587-606, Index.h:665-695) for the device-resident copy ---------------- */
+int ngtgpu_index_create(ngtgpu_index **out, int device, int object_type, int distance_type, uint32_t dimension);
+int ngtgpu_index_destroy(ngtgpu_index *index);
+
+/* Objects 1..n, row-major, `dimension` elements of the object type each (the payload of `obj`,
+ * lib/NGT/Common.h:1776-1793). Rows are padded on the device; for Normalized* distance types they
+ * are stored as given unless `normalize` != 0, in which case each row is divided by its L2 norm as
+ * ObjectSpace::normalize does (lib/NGT/ObjectSpace.h:251-266). `on_device`: pointer is in HBM. */
+int ngtgpu_index_set_objects(ngtgpu_index *index, const void *objects, uint64_t n, int normalize, int on_device);
+/* ids whose slots are empty ('-' records): skipped by linearSearch (ObjectSpaceRepository.h:485). */
+int ngtgpu_index_set_removed(ngtgpu_index *index, const uint32_t *ids, uint64_t count);
+/* Adjacency lists in CSR over ids 0..n: row_ptr has n+2 entries, list of id is
+ * col[row_ptr[id] .. row_ptr[id+1]) in `grp` order, i.e. ascending (distance,id)
+ * (lib/NGT/Graph.h:62-183, ObjectSpace.h:29). */
+int ngtgpu_index_set_graph(ngtgpu_index *index, const uint64_t *row_ptr, const uint32_t *col, int on_device);
+/* NeighborhoodGraph::Property fields the search path reads (lib/NGT/Graph.h:383-454). */
+int ngtgpu_index_set_search_property(ngtgpu_index *index, int64_t edge_size_for_search,
+                                     int64_t dynamic_edge_size_base, int64_t dynamic_edge_size_rate);
+/* Batched on-device seed selection that stands in for the DVP-tree leaf lookup
+ * (lib/NGT/Index.h:1524-1567, Tree.cpp:400-563): `n_pivots` sampled objects form a table; each query's
+ * seeds are its nearest `seed_size` pivots. */
+int ngtgpu_index_build_seed_table(ngtgpu_index *index, uint32_t n_pivots, uint64_t rng_seed);
+
+uint64_t ngtgpu_index_size(const ngtgpu_index *index);          /* n */
+uint32_t ngtgpu_index_padded_dimension(const ngtgpu_index *index);
+/* Copies the stored (possibly normalised) object `id` back: ngt_get_object_as_float/_as_integer
+ * (lib/NGT/Capi.cpp:750-782). `out` holds `dimension` elements of the object type. */
+int ngtgpu_index_get_object(const ngtgpu_index *index, uint32_t id, void *out);
+
+/* ---- graph beam search: replaces NeighborhoodGraph::search / searchReadOnlyGraph
+ *      (lib/NGT/Graph.cpp:398-495, 499-638) behind GraphIndex::search(sc, seeds)
+ *      (lib/NGT/Index.h:1140-1179), for a batch of queries -------------------------------------
+ * queries: nq rows of `dimension` elements; query_type says whether they are float (as every
+ *   ngt_search_index* entry point passes them, Capi.cpp:377-406) or already uint8. They are cast to
+ *   the object type / normalised on the device exactly as Index::allocateObject does
+ *   (ObjectRepository.h:222-258, ObjectSpaceRepository.h:560-594).
+ * seeds: nq x n_seeds explicit seed ids (what GraphIndex::search(sc, seeds) takes), or NULL to use the
+ *   device seed table (n_seeds = number of pivots to take per query).
+ * ids/dists: nq x size, ascending (distance,id); counts: results per query.
+ * stats (nullable): nq x 3 = {distance computations incl. seeds, adjacency entries examined,
+ *   nodes expanded} -- the reference's distanceComputationCount / visitCount (Graph.cpp:592,604). */
+int ngtgpu_search(ngtgpu_index *index, const void *queries, int query_type, uint32_t nq,
+                  const ngtgpu_search_params *params, const uint32_t *seeds, uint32_t n_seeds,
+                  uint32_t *ids, float *dists, uint32_t *counts, uint32_t *stats);
+/* Same with every buffer already in HBM, enqueued on `stream` (a cudaStream_t); returns without
+ * synchronising unless a query overflowed the on-chip working set and had to be re-run. */
+int ngtgpu_search_device(ngtgpu_index *index, const void *queries, int query_type, uint32_t nq,
+                         const ngtgpu_search_params *params, const uint32_t *seeds, uint32_t n_seeds,
+                         uint32_t *ids, float *dists, uint32_t *counts, uint32_t *stats, void *stream);
+
+/* ---- exhaustive scan: replaces ObjectSpaceRepository::linearSearch
+ *      (lib/NGT/ObjectSpaceRepository.h:466-502) behind GraphIndex::linearSearch (Index.h:729-749) */
+int ngtgpu_linear_search(ngtgpu_index *index, const void *queries, int query_type, uint32_t nq, uint32_t size,
+                         float radius, uint32_t *ids, float *dists, uint32_t *counts);
+int ngtgpu_linear_search_device(ngtgpu_index *index, const void *queries, int query_type, uint32_t nq,
+                                uint32_t size, float radius, uint32_t *ids, float *dists, uint32_t *counts,
+                                void *stream);
+
+/* Number of kernels this library launched since the index was created (bench.py's gpu_launches). */
+uint64_t ngtgpu_index_launch_count(const ngtgpu_index *index);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NGTGPU_H */

@@ -1,0 +1,295 @@
+"""Parity of the CUDA path (through the C ABI) with the reference: golden vectors produced by the
+unmodified reference (tests/golden/*.npz) and the C restatement (oracle/) on seeded inputs.
+
+Bars (tests/parity.py): bit-exact ids + float bits for uint8 L2, Hamming and integer-valued float data;
+1e-6 relative on distances and near-tie id swaps only for general float data.
+"""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from parity import (EDGE_GRID, EPS_GRID, FLOAT_CASES, INTEGER_EXACT, NORMALIZED, assert_bit_exact,
+                    assert_float_parity, grid_key)
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from ngt_b200 import engine
+    return engine
+
+
+def _gpu_index(eng, otype, dtype, objects, row_ptr=None, col=None, prop=None, normalize=False):
+    ix = eng.GpuIndex(otype, dtype, objects.shape[1])
+    ix.set_objects(objects, normalize=normalize)
+    if row_ptr is not None:
+        ix.set_graph(np.asarray(row_ptr, np.uint64), col)
+    if prop is not None:
+        ix.set_search_property(*[int(v) for v in prop])
+    return ix
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference golden vectors
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,otype", [("u8", po.UINT8), ("f32", po.FLOAT)])
+def test_sift5k_golden(eng, sift5k, tag, otype):
+    data = sift5k["data"]
+    qs = sift5k["queries"].astype(np.float32)   # every ngt_search_index* entry point takes numbers, Capi.cpp:377-406
+    ix = _gpu_index(eng, otype, po.L2, data, sift5k["row_ptr"], sift5k["col"], sift5k["prop"])
+    ids, dists, counts = ix.linear_search(qs, 20)
+    assert_bit_exact(ids, dists, counts, sift5k[tag + "_lin_ids"], sift5k[tag + "_lin_dists"], what="linear")
+    for eps in EPS_GRID:
+        for e in EDGE_GRID:
+            key = grid_key(tag, eps, e)
+            ids, dists, counts, stats = ix.search(qs, 20, eps, edge_size=e, seeds=sift5k["seeds"], with_stats=True)
+            assert_bit_exact(ids, dists, counts, sift5k[key + "_ids"], sift5k[key + "_dists"],
+                             sift5k[key + "_counts"], what=key)
+            ref = sift5k[key + "_stats"]   # writable path: counts after the seeds, Graph.cpp:592,604
+            assert (stats[:, 0].astype(np.int64) - sift5k["seeds"].shape[1] == ref[:, 0]).all(), key
+            assert (stats[:, 1] == ref[:, 1]).all(), key
+    ix.close()
+
+
+def test_readme_known_answer(eng, sift5k):
+    """bin/ngt/README.md:254-323 with the seeds the reference's DVP-tree produced."""
+    import json
+    import os
+    from conftest import GOLDEN
+    kat = json.load(open(os.path.join(GOLDEN, "readme_kat.json")))
+    ix = _gpu_index(eng, po.UINT8, po.L2, sift5k["data"], sift5k["row_ptr"], sift5k["col"], sift5k["prop"])
+    ids, dists, counts = ix.search(sift5k["queries"], 20, 0.1, seeds=sift5k["tree_seeds"])
+    for q in range(3):
+        assert [[int(ids[q, i]), "%g" % float(dists[q, i])] for i in range(20)] == kat[q]
+    ix.close()
+
+
+def _case(z, tag):
+    data_tag = "f32l2" if tag == "onng" else tag
+    ot, dt, dim, es, base, rate = [int(v) for v in z[tag + "_meta"]]
+    return dict(otype=ot, dtype=dt, prop=(es, base, rate), objects=z[data_tag + "_objects"],
+                queries=z[data_tag + "_queries"], row_ptr=z[tag + "_row_ptr"], col=z[tag + "_col"], seeds=z[tag + "_seeds"])
+
+
+@pytest.mark.parametrize("tag", INTEGER_EXACT + FLOAT_CASES)
+def test_synth_golden(eng, synth_golden, tag):
+    z = synth_golden
+    c = _case(z, tag)
+    exact = tag in INTEGER_EXACT
+    check = assert_bit_exact if exact else assert_float_parity
+    # stored rows are what the reference holds (already normalised for Normalized* types)
+    ix = _gpu_index(eng, c["otype"], c["dtype"], c["objects"], c["row_ptr"], c["col"], c["prop"], normalize=False)
+    qs = c["queries"].astype(np.float32)
+    if tag != "onng":
+        ids, dists, counts = ix.linear_search(qs, 10)
+        check(ids, dists, counts, z[tag + "_lin_ids"], z[tag + "_lin_dists"], what=tag + " linear")
+        rad = float(z[tag + "_linr_radius"][0])
+        ids, dists, counts = ix.linear_search(qs, 10, radius=rad)
+        if exact:
+            assert_bit_exact(ids, dists, counts, z[tag + "_linr_ids"], z[tag + "_linr_dists"], z[tag + "_linr_counts"],
+                             what=tag + " linear radius")
+    for eps in EPS_GRID:
+        for e in EDGE_GRID:
+            key = grid_key(tag, eps, e)
+            ids, dists, counts, stats = ix.search(qs, 10, eps, edge_size=e, seeds=c["seeds"], with_stats=True)
+            check(ids, dists, counts, z[key + "_ids"], z[key + "_dists"], z[key + "_counts"], what=key)
+            if exact:
+                assert (stats[:, 1] == z[key + "_stats"][:, 1]).all(), key
+    ix.close()
+
+
+def test_normalization_matches_reference(eng, synth_golden):
+    """ObjectSpace.h:251-266 on the device: raw rows in, the reference's stored rows out (1e-6)."""
+    raw = synth_golden["glove_l2_objects"]
+    stored = synth_golden["glove_ncos_objects"]
+    ix = eng.GpuIndex(po.FLOAT, po.NORMALIZED_COSINE, raw.shape[1])
+    ix.set_objects(raw)          # normalises by default for Normalized* types
+    got = np.stack([ix.get_object(i + 1) for i in range(0, raw.shape[0], 97)])
+    assert np.abs(got - stored[::97]).max() <= 1e-6
+    with pytest.raises(eng.NgtGpuError):
+        ix.linear_search(np.zeros((1, raw.shape[1]), np.float32), 5)     # zero query vector: the reference throws
+    ix.close()
+    ix2 = eng.GpuIndex(po.FLOAT, po.NORMALIZED_COSINE, raw.shape[1])
+    bad = raw.copy()
+    bad[3] = 0
+    with pytest.raises(eng.NgtGpuError):
+        ix2.set_objects(bad)
+    ix2.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# seeded inputs against the C restatement
+# ---------------------------------------------------------------------------------------------------
+def _knn_csr(ids, counts):
+    """adjacency lists from exhaustive results (already ascending by (distance,id))."""
+    n = ids.shape[0]
+    row_ptr = np.zeros(n + 2, np.uint64)
+    row_ptr[2:] = np.cumsum(counts.astype(np.uint64))
+    col = np.concatenate([ids[i, :counts[i]] for i in range(n)]).astype(np.uint32)
+    return row_ptr, col
+
+
+@pytest.mark.parametrize("kind", ["u8l2", "ham", "f32int", "f32cos"])
+def test_seeded_against_port(eng, port, kind):
+    from ngt_b200 import synth
+    rng = np.random.default_rng(7)
+    n, nq, k = 6000, 64, 10
+    base = synth.make("sift", n, 1)
+    qs = synth.make("sift", nq, 2)
+    if kind == "u8l2":
+        otype, dtype, objs, q = po.UINT8, po.L2, base.astype(np.uint8), qs
+    elif kind == "ham":
+        otype, dtype = po.UINT8, po.HAMMING
+        objs = synth.hamming_from(base, 64.0)
+        q = synth.hamming_from(qs, 64.0).astype(np.float32)
+    elif kind == "f32int":
+        otype, dtype, objs, q = po.FLOAT, po.L2, base, qs
+    else:
+        otype, dtype = po.FLOAT, po.COSINE
+        objs = (base - 64.0).astype(np.float32) / 40.0
+        q = (qs - 64.0).astype(np.float32) / 40.0
+    ix = eng.GpuIndex(otype, dtype, objs.shape[1])
+    ix.set_objects(objs)
+    pobj = po.pad_objects(objs, otype)
+    pq = po.pad_queries(q, otype)
+    check = assert_float_parity if kind == "f32cos" else assert_bit_exact
+    # exhaustive search, with and without a radius, k beyond one warp, k > n handled below
+    for kk in (1, k, 40):
+        ids, dists, counts = ix.linear_search(q, kk)
+        rids, rdists, rcounts = port.linear_search(dtype, otype, pobj, pq, kk)
+        check(ids, dists, counts, rids, rdists, rcounts, what="%s linear k=%d" % (kind, kk))
+    rad = float(rdists[0, 20])
+    ids, dists, counts = ix.linear_search(q, k, radius=rad)
+    rids, rdists2, rcounts = port.linear_search(dtype, otype, pobj, pq, k, radius=rad)
+    check(ids, dists, counts, rids, rdists2, rcounts, what=kind + " linear radius")
+    # a kNN graph made by the engine itself (self included: harmless), searched by both
+    gids, _, gcounts = ix.linear_search(objs.astype(np.float32), 12)
+    row_ptr, col = _knn_csr(gids, gcounts)
+    ix.set_graph(row_ptr, col)
+    seeds = np.stack([rng.choice(n, 8, replace=False) + 1 for _ in range(nq)]).astype(np.uint32)
+    for eps, cap, kk in ((0.1, 2 ** 31 - 1, k), (0.25, 7, k), (0.0, 2 ** 31 - 1, 40), (-0.05, 2 ** 31 - 1, k)):
+        es = 0 if cap == 2 ** 31 - 1 else cap
+        ids, dists, counts, stats = ix.search(q, kk, eps, edge_size=es, seeds=seeds, with_stats=True)
+        rids, rdists, rcounts, rstats = port.graph_search(dtype, otype, pobj, row_ptr, col, pq, seeds, kk, eps,
+                                                          edge_size=cap)
+        what = "%s graph eps=%g cap=%d k=%d" % (kind, eps, cap, kk)
+        check(ids, dists, counts, rids, rdists, rcounts, what=what)
+        if kind != "f32cos":
+            assert (stats.astype(np.uint64) == rstats).all(), what
+    # the HBM tier (tiny on-chip working set forces every query to overflow) gives the same answers
+    ix.set_search_workspace(hash_bits=8, queue_cap=64)
+    ids, dists, counts = ix.search(q, k, 0.1, edge_size=0, seeds=seeds)
+    assert ix.last_overflows > 0
+    rids, rdists, rcounts, _ = port.graph_search(dtype, otype, pobj, row_ptr, col, pq, seeds, k, 0.1)
+    check(ids, dists, counts, rids, rdists, rcounts, what=kind + " overflow tier")
+    ix.close()
+
+
+def test_edge_cases(eng, port):
+    rng = np.random.default_rng(3)
+    objs = rng.integers(0, 256, (50, 24)).astype(np.uint8)       # ragged dimension: padded to 32
+    q = rng.integers(0, 256, (5, 24)).astype(np.uint8)
+    ix = eng.GpuIndex(po.UINT8, po.L2, 24)
+    ix.set_objects(objs)
+    assert ix.padded_dimension == 32 and ix.size == 50
+    pobj, pq = po.pad_objects(objs, po.UINT8), po.pad_queries(q, po.UINT8)
+    # k larger than the repository: everything comes back, ascending
+    ids, dists, counts = ix.linear_search(q, 64)
+    rids, rdists, rcounts = port.linear_search(po.L2, po.UINT8, pobj, pq, 64)
+    assert (counts == 50).all()
+    assert_bit_exact(ids, dists, counts, rids, rdists, rcounts, what="k > n")
+    # size 0 returns nothing (Index.h:1141-1144); an empty batch is a no-op
+    ids, dists, counts = ix.linear_search(q, 0)
+    assert ids.shape == (5, 0) and (counts == 0).all()
+    ids, dists, counts = ix.linear_search(np.zeros((0, 24), np.uint8), 3)
+    assert ids.shape[0] == 0
+    # removed objects are skipped (ObjectSpaceRepository.h:485)
+    removed = np.array([1, 7, 50], np.uint32)
+    ix.set_removed(removed)
+    valid = np.ones(51, np.uint8)
+    valid[0] = 0
+    valid[removed] = 0
+    ids, dists, counts = ix.linear_search(q, 10)
+    rids, rdists, rcounts = port.linear_search(po.L2, po.UINT8, pobj, pq, 10, valid=valid)
+    assert_bit_exact(ids, dists, counts, rids, rdists, rcounts, what="removed")
+    assert not np.isin(ids, removed).any()
+    # graph search without a graph / without seeds fails loudly
+    with pytest.raises(eng.NgtGpuError):
+        ix.search(q, 5, 0.1, seeds=np.ones((5, 2), np.uint32))
+    # bad edge-size mode: the reference's message (Graph.h:687-689)
+    ix.set_removed(np.zeros(0, np.uint32))
+    row_ptr = np.zeros(52, np.uint64)
+    ix.set_graph(row_ptr, np.zeros(0, np.uint32))
+    with pytest.raises(eng.NgtGpuError, match="Invalid edge size parameters"):
+        ix.search(q, 5, 0.1, edge_size=-3, seeds=np.ones((5, 2), np.uint32))
+    # a graph with no edges returns the seeds that fit
+    ids, dists, counts = ix.search(q, 5, 0.1, seeds=np.tile(np.array([[3, 9]], np.uint32), (5, 1)))
+    rids, rdists, rcounts, _ = port.graph_search(po.L2, po.UINT8, pobj, row_ptr, np.zeros(1, np.uint32), pq,
+                                                 np.tile(np.array([[3, 9]], np.uint32), (5, 1)), 5, 0.1)
+    assert_bit_exact(ids, dists, counts, rids, rdists, rcounts, what="edgeless graph")
+    # dimension mismatch
+    with pytest.raises(eng.NgtGpuError):
+        ix.linear_search(np.zeros((1, 25), np.uint8), 3)
+    ix.close()
+    with pytest.raises(eng.NgtGpuError):
+        eng.GpuIndex(po.UINT8, po.COSINE, 16)                    # unsupported pair
+
+
+def test_long_rows_and_wide_results(eng, port):
+    """dimension > 1024 floats takes the shared-memory-query instantiation; k = 300 the smem result list."""
+    rng = np.random.default_rng(11)
+    n, d = 700, 1100
+    objs = rng.integers(0, 16, (n, d)).astype(np.float32)
+    q = rng.integers(0, 16, (6, d)).astype(np.float32)
+    ix = eng.GpuIndex(po.FLOAT, po.L2, d)
+    ix.set_objects(objs)
+    pobj, pq = po.pad_objects(objs, po.FLOAT), po.pad_queries(q, po.FLOAT)
+    ids, dists, counts = ix.linear_search(q, 300)
+    rids, rdists, rcounts = port.linear_search(po.L2, po.FLOAT, pobj, pq, 300)
+    assert_bit_exact(ids, dists, counts, rids, rdists, rcounts, what="long rows linear")
+    gids, _, gcounts = ix.linear_search(objs, 10)
+    row_ptr, col = _knn_csr(gids, gcounts)
+    ix.set_graph(row_ptr, col)
+    seeds = np.tile(np.arange(1, 11, dtype=np.uint32), (6, 1))
+    ids, dists, counts = ix.search(q, 100, 0.2, edge_size=0, seeds=seeds)
+    rids, rdists, rcounts, _ = port.graph_search(po.L2, po.FLOAT, pobj, row_ptr, col, pq, seeds, 100, 0.2)
+    assert_bit_exact(ids, dists, counts, rids, rdists, rcounts, what="long rows graph")
+    ix.close()
+
+
+def test_device_seed_table_recall(eng, port):
+    """Seeds from the device pivot table (stand-in for the DVP-tree leaf): recall at the reference's epsilon
+    is at least what the restated search reaches from the same seeds, and >= 0.9 on this set."""
+    from ngt_b200 import synth
+    n, nq, k = 20000, 200, 10
+    base, qs = synth.make("sift", n, 1), synth.make("sift", nq, 2)
+    ix = eng.GpuIndex(po.FLOAT, po.L2, 128)
+    ix.set_objects(base)
+    gids, _, gcounts = ix.linear_search(base, 17)
+    # symmetrised kNN graph (what ANNG construction approximates), lists ordered by (distance,id)
+    pobj, pq = po.pad_objects(base, po.FLOAT), po.pad_queries(qs, po.FLOAT)
+    src = np.repeat(np.arange(1, n + 1, dtype=np.uint32), 16)
+    dst = gids[:, 1:17].reshape(-1)
+    e = np.unique(np.concatenate([np.stack([src, dst], 1), np.stack([dst, src], 1)]), axis=0)
+    d = np.linalg.norm(base[e[:, 0] - 1] - base[e[:, 1] - 1], axis=1)
+    order = np.lexsort((e[:, 1], d, e[:, 0]))
+    e = e[order]
+    row_ptr = np.zeros(n + 2, np.uint64)
+    np.add.at(row_ptr, e[:, 0].astype(np.int64) + 1, 1)
+    row_ptr = np.cumsum(row_ptr).astype(np.uint64)
+    col = e[:, 1].astype(np.uint32)
+    ix.set_graph(row_ptr, col)
+    ix.build_seed_table(1024, 5)
+    gt_ids, gt_d, _ = ix.linear_search(qs, k)
+    ids, dists, counts = ix.search(qs, k, 0.1, edge_size=0, n_seeds=10)
+    rec = port.mean_recall(ids, dists, counts, gt_ids, gt_d)
+    assert rec >= 0.9, rec
+    # torch (already-in-HBM) entry point returns the same thing
+    import torch
+    tq = torch.from_numpy(qs).cuda()
+    tids, tdists, tcounts = ix.search(tq, k, 0.1, edge_size=0, n_seeds=10)
+    torch.cuda.synchronize()
+    assert (tids.cpu().numpy().astype(np.uint32) == ids).all()
+    assert (tdists.cpu().numpy().view(np.uint32) == dists.view(np.uint32)).all()
+    ix.close()
