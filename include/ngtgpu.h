@@ -120,8 +120,53 @@ int ngtgpu_linear_search_device(ngtgpu_index *index, const void *queries, int qu
                                 uint32_t size, float radius, uint32_t *ids, float *dists, uint32_t *counts,
                                 void *stream);
 
+/* ---- exhaustive kNN of stored objects: the brute-force pass behind graph construction,
+ *      GraphIndex::searchForKNNGInsertion (lib/NGT/Index.h:839-856: linearSearch with size k+1 for object
+ *      `id`, the object itself dropped, ObjectSpace.h:70-88). Queries are the stored rows
+ *      first_id..first_id+count-1; outputs are DEVICE buffers [count x k], enqueued on `stream`. */
+int ngtgpu_index_knn_graph(ngtgpu_index *index, uint32_t k, uint32_t first_id, uint32_t count, uint32_t *ids,
+                           float *dists, uint32_t *counts, void *stream);
+
+/* The seeds the engine would start these (host) queries from -- the nearest `n_seeds` pivots of the seed
+ * table -- so a caller can run the reference's GraphIndex::search(sc, seeds) (Index.h:1140) from the same
+ * starting points. seeds_out: nq x n_seeds. */
+int ngtgpu_select_seeds(ngtgpu_index *index, const void *queries, int query_type, uint32_t nq, uint32_t n_seeds,
+                        uint32_t *seeds_out);
+
+/* Working set of the traversal kernel per query: visited-hash slots = 2^hash_bits (8..17; an exact
+ * open-addressing table in a per-CTA slab that stays in L2), unchecked-queue entries in shared memory
+ * (64..8192). A query that outgrows it is re-run with a 2^17-slot slab and finally with an exact bitmap +
+ * queue in HBM (the reference's own structures, lib/NGT/Graph.h:751-799); ngtgpu_index_last_overflows()
+ * says how many queries of the last host-pointer call left the first tier. */
+int ngtgpu_index_set_search_workspace(ngtgpu_index *index, uint32_t hash_bits, uint32_t queue_cap);
+/* Number of shared-memory tiers tried before the HBM tier: 2 (default: the configured one, then the largest
+ * that fits an SM) or 1. */
+int ngtgpu_index_set_onchip_tiers(ngtgpu_index *index, int tiers);
+/* Shared-memory staging area (bytes per CTA) that neighbour rows are copied into with cp.async. */
+int ngtgpu_index_set_stage_bytes(ngtgpu_index *index, uint32_t bytes);
+uint64_t ngtgpu_index_last_overflows(const ngtgpu_index *index);
+
 /* Number of kernels this library launched since the index was created (bench.py's gpu_launches). */
 uint64_t ngtgpu_index_launch_count(const ngtgpu_index *index);
+/* Device timing of the traversal kernel with CUDA events on the launching stream (bench.py's roofline leg):
+ * enable, run searches, then pop the summed milliseconds and the number of traversal launches. */
+int ngtgpu_index_set_timing(ngtgpu_index *index, int enabled);
+int ngtgpu_index_pop_timing(ngtgpu_index *index, double *total_ms, uint64_t *launches);
+
+/* Development aid: when a device buffer of nq x 8 words is set, the traversal kernel's control warp writes the
+ * cycles it spent per phase (merge, pop, adjacency load, visited filter, TMA issue, row wait, distances, other). */
+int ngtgpu_index_set_phase_profile(ngtgpu_index *index, uint32_t *device_buffer);
+
+/* ---- NGT index files (host only): `obj` and `grp` as Repository::serialize writes them
+ *      (lib/NGT/Common.h:1776-1837, ObjectSpace.h:293-301, Graph.h:151-158). record_bytes =
+ *      dimension * sizeof(object element). Slots = repository size = n + 1 (slot 0 is the dummy). */
+int ngtgpu_io_obj_info(const char *path, uint32_t record_bytes, uint64_t *slots, uint64_t *present);
+int ngtgpu_io_read_obj(const char *path, uint32_t record_bytes, void *rows, uint8_t *present);
+int ngtgpu_io_write_obj(const char *path, uint32_t record_bytes, const void *rows, uint64_t n, const uint8_t *present);
+int ngtgpu_io_grp_info(const char *path, uint64_t *slots, uint64_t *nnz);
+int ngtgpu_io_read_grp(const char *path, uint64_t *row_ptr, uint32_t *col, float *dist, uint8_t *present);
+int ngtgpu_io_write_grp(const char *path, uint64_t n, const uint64_t *row_ptr, const uint32_t *col, const float *dist,
+                        const uint8_t *present);
 
 #ifdef __cplusplus
 }

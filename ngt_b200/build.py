@@ -1,0 +1,109 @@
+"""Index construction on the device.
+
+The distance work -- the brute-force kNN pass that GraphIndex::searchForKNNGInsertion
+(lib/NGT/Index.h:839-856) does one object at a time -- runs in libngtgpu.so (ngtgpu_index_knn_graph).
+What is left is adjacency-list surgery with no arithmetic in it (concatenate, sort by (node, distance, id),
+drop duplicates); it is done with torch sort/unique primitives on the device, following
+GraphReconstructor::reconstructGraph (lib/NGT/GraphReconstructor.h:425-561): keep the first `outgoing`
+edges of every node, add the reverse of the first `incoming` edges, sort, dedupe.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+_ready = False
+
+
+def _fn():
+    global _ready
+    lib = _lib.load()
+    if not _ready:
+        P = C.c_void_p
+        lib.ngtgpu_index_knn_graph.argtypes = [P, C.c_uint32, C.c_uint32, C.c_uint32, P, P, P, P]
+        lib.ngtgpu_index_knn_graph.restype = C.c_int
+        _ready = True
+    return lib
+
+
+def knn_graph(ix, k, batch=1 << 17):
+    """Exact k nearest OTHER objects of every stored object. -> (ids [n,k] int32, dists [n,k] float32,
+    counts [n] int32) as torch CUDA tensors; lists ascending by (distance,id)."""
+    import torch
+    lib = _fn()
+    n = ix.size
+    dev = torch.device("cuda", ix.device)
+    ids = torch.zeros((n, k), dtype=torch.int32, device=dev)
+    dists = torch.zeros((n, k), dtype=torch.float32, device=dev)
+    counts = torch.zeros((n,), dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    for s in range(0, n, batch):
+        m = min(batch, n - s)
+        _lib.check(lib.ngtgpu_index_knn_graph(ix._h, int(k), s + 1, m, ids[s:].data_ptr(), dists[s:].data_ptr(),
+                                              counts[s:].data_ptr(), stream))
+    return ids, dists, counts
+
+
+def _dist_sort_key(dists):
+    """float32 -> int64 that sorts like the float (handles negative zero and tiny negative cosines)."""
+    import torch
+    b = (dists + 0.0).view(torch.int32).to(torch.int64)
+    return torch.where(b < 0, -(b & 0x7fffffff) - 1, b)
+
+
+def reconstruct_graph(ids, dists, counts, outgoing, incoming):
+    """GraphReconstructor::reconstructGraph on a [n,k] neighbour table (1-based ids, ascending lists).
+    -> (row_ptr [n+2] int64 over ids 0..n, col int32, dist float32), lists ascending by (distance,id)."""
+    import torch
+    n, k = ids.shape
+    dev = ids.device
+    outgoing, incoming = min(outgoing, k), min(incoming, k)
+    node = torch.arange(1, n + 1, device=dev, dtype=torch.int64)[:, None]
+    rank = torch.arange(k, device=dev)[None, :]
+    have = rank < counts[:, None]
+    # outgoing part: node -> its first `outgoing` neighbours
+    mo = have & (rank < outgoing)
+    src_o = node.expand(n, k)[mo]
+    dst_o = ids.to(torch.int64)[mo]
+    d_o = dists[mo]
+    # incoming part: the reverse of the first `incoming` edges
+    mi = have & (rank < incoming)
+    src_i = ids.to(torch.int64)[mi]
+    dst_i = node.expand(n, k)[mi]
+    d_i = dists[mi]
+    src = torch.cat([src_o, src_i])
+    dst = torch.cat([dst_o, dst_i])
+    d = torch.cat([d_o, d_i])
+    del src_o, src_i, dst_o, dst_i, d_o, d_i, mo, mi, have
+    # sort by (src, distance, dst): stable sort by src after a sort by (distance, dst)
+    key = (_dist_sort_key(d) << 32) | dst
+    order = torch.argsort(key, stable=True)
+    src, dst, d = src[order], dst[order], d[order]
+    order = torch.argsort(src, stable=True)
+    src, dst, d = src[order], dst[order], d[order]
+    del key, order
+    keep = torch.ones_like(src, dtype=torch.bool)
+    keep[1:] = (src[1:] != src[:-1]) | (dst[1:] != dst[:-1])
+    src, dst, d = src[keep], dst[keep], d[keep]
+    deg = torch.bincount(src, minlength=n + 1)
+    row_ptr = torch.zeros(n + 2, dtype=torch.int64, device=dev)
+    row_ptr[1:] = torch.cumsum(deg, 0)
+    return row_ptr, dst.to(torch.int32), d
+
+
+def graph_statistics(row_ptr):
+    deg = (row_ptr[2:] - row_ptr[1:-1]).float()
+    return {"edges": int(row_ptr[-1]), "mean_degree": float(deg.mean()), "min_degree": int(deg.min()),
+            "max_degree": int(deg.max())}
+
+
+def csr_from_table(ids, counts):
+    """[n,k] table -> CSR numpy (row_ptr over ids 0..n)."""
+    ids = np.asarray(ids)
+    counts = np.asarray(counts).astype(np.int64)
+    n, k = ids.shape
+    row_ptr = np.zeros(n + 2, np.uint64)
+    row_ptr[2:] = np.cumsum(counts)
+    mask = np.arange(k)[None, :] < counts[:, None]
+    return row_ptr, ids[mask].astype(np.uint32)

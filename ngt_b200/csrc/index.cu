@@ -121,6 +121,8 @@ extern "C" int ngtgpu_index_create(ngtgpu_index **out, int device, int object_ty
 static void free_graph(ngtgpu_index *ix) {
   if (ix->d_row_ptr) cudaFree(ix->d_row_ptr);
   if (ix->d_col) cudaFree(ix->d_col);
+  if (ix->d_head) cudaFree(ix->d_head);
+  ix->d_head = nullptr;
   ix->d_row_ptr = nullptr;
   ix->d_col = nullptr;
   ix->nnz = 0;
@@ -345,6 +347,19 @@ extern "C" int ngtgpu_index_set_removed(ngtgpu_index *ix, const uint32_t *ids, u
   return NGTGPU_OK;
 }
 
+// fixed-stride copy of the first 64 edges of every node (zero padded): the traversal kernel reads one node's
+// edges with a single coalesced access instead of row_ptr -> col (two dependent ones)
+__global__ void build_head_kernel(const uint64_t *__restrict__ row_ptr, const uint32_t *__restrict__ col, uint64_t n,
+                                  uint32_t *__restrict__ head) {
+  const uint64_t total = (n + 1) * 64;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t id = i >> 6;
+    const uint32_t e = (uint32_t)(i & 63);
+    const uint64_t b = row_ptr[id], deg = row_ptr[id + 1] - b;
+    head[i] = e < deg ? col[b + e] : 0u;
+  }
+}
+
 extern "C" int ngtgpu_index_set_graph(ngtgpu_index *ix, const uint64_t *row_ptr, const uint32_t *col, int on_device) {
   NGTGPU_TRY(ngtgpu_check_device(ix));
   if (!ix->d_objects) NGTGPU_FAIL(NGTGPU_ERR_STATE, "ngtgpu_index_set_graph: objects are not set");
@@ -368,6 +383,11 @@ extern "C" int ngtgpu_index_set_graph(ngtgpu_index *ix, const uint64_t *row_ptr,
   CUDA_TRY(cudaMemcpy(ix->d_row_ptr, row_ptr, (ix->n + 2) * sizeof(uint64_t), kind));
   if (nnz) CUDA_TRY(cudaMemcpy(ix->d_col, col, nnz * sizeof(uint32_t), kind));
   ix->nnz = nnz;
+  CUDA_TRY(cudaMalloc(&ix->d_head, (ix->n + 1) * 64 * sizeof(uint32_t)));
+  build_head_kernel<<<ix->sm_count * 8, 256, 0, ix->stream>>>(ix->d_row_ptr, ix->d_col, ix->n, ix->d_head);
+  ix->launches++;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(ix->stream));
   return NGTGPU_OK;
 }
 
@@ -382,10 +402,24 @@ extern "C" int ngtgpu_index_set_search_property(ngtgpu_index *ix, int64_t edge_s
 
 extern "C" int ngtgpu_index_set_search_workspace(ngtgpu_index *ix, uint32_t hash_bits, uint32_t queue_cap) {
   if (!ix) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "null index handle");
-  if (hash_bits < 8 || hash_bits > 15) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "hash_bits must be in [8, 15]");
+  if (hash_bits < 8 || hash_bits > 17) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "hash_bits must be in [8, 17]");
   if (queue_cap < 64 || queue_cap > 8192) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "queue_cap must be in [64, 8192]");
   ix->hash_bits = hash_bits;
   ix->queue_cap = queue_cap;
+  return NGTGPU_OK;
+}
+
+extern "C" int ngtgpu_index_set_stage_bytes(ngtgpu_index *ix, uint32_t bytes) {
+  if (!ix) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "null index handle");
+  if (bytes < 2048 || bytes > 131072) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "stage bytes must be in [2048, 131072]");
+  ix->stage_bytes = bytes;
+  return NGTGPU_OK;
+}
+
+extern "C" int ngtgpu_index_set_onchip_tiers(ngtgpu_index *ix, int tiers) {
+  if (!ix) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "null index handle");
+  if (tiers < 1 || tiers > 2) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "tiers must be 1 or 2");
+  ix->onchip_tiers = tiers;
   return NGTGPU_OK;
 }
 

@@ -46,7 +46,9 @@ enum ScratchSlot {
   SCR_RAW_QUERIES = 5, // host queries as given, before preparation
   SCR_SEARCH_WS = 6,   // counters + overflow list of the traversal kernel
   SCR_SEARCH_BIG = 7,  // global-memory working sets of the overflow tier
-  SCR_COUNT = 8
+  SCR_HASH0 = 8,       // visited-hash slabs of the first traversal tier (one per resident CTA)
+  SCR_HASH1 = 9,       // ... of the second tier
+  SCR_COUNT = 10
 };
 
 struct ngtgpu_index {
@@ -66,6 +68,7 @@ struct ngtgpu_index {
   uint8_t *d_valid = nullptr;     // (n+1) bytes, 0 = empty slot; nullptr when nothing was removed
   uint64_t *d_row_ptr = nullptr;  // n+2
   uint32_t *d_col = nullptr;
+  uint32_t *d_head = nullptr;     // (n+1) x 64: the first 64 edges of every node, zero padded (one coalesced read)
   uint64_t nnz = 0;
   int64_t edge_size_for_search = 40;   // Graph.h:401 defaults
   int64_t dyn_base = 30;
@@ -75,8 +78,10 @@ struct ngtgpu_index {
   uint8_t *d_pivot_rows = nullptr;     // n_pivots x row_bytes
   uint32_t *d_pivot_ids = nullptr;
   // traversal working-set sizing (on-chip tier)
-  uint32_t hash_bits = 13;             // visited hash slots = 1 << hash_bits (4 B each, shared memory)
+  uint32_t hash_bits = 14;             // visited hash slots = 1 << hash_bits (4 B each, per-CTA slab in L2)
   uint32_t queue_cap = 1024;           // unchecked queue entries (8 B each, shared memory)
+  uint32_t stage_bytes = 16384;        // shared-memory staging area the TMA engine fills with neighbour rows
+  int onchip_tiers = 2;                // 1: overflow goes straight to the HBM tier (tests)
   uint64_t last_overflows = 0;         // queries of the last call that fell to the global-memory tier
   // scratch
   void *d_scratch[SCR_COUNT] = {nullptr};
@@ -84,6 +89,10 @@ struct ngtgpu_index {
   cudaStream_t stream = nullptr;       // owned; host-pointer entry points run here
   int sm_count = 0;
   uint64_t launches = 0;
+  // optional device timing of the traversal kernel (bench.py's roofline leg)
+  uint32_t *d_prof = nullptr;          // development aid: per-phase cycle counters of the traversal kernel
+  bool timing = false;
+  std::vector<cudaEvent_t> timing_events;   // start, stop, start, stop ...
 };
 
 int ngtgpu_scratch(ngtgpu_index *ix, int slot, size_t bytes, void **out);

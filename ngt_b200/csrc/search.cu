@@ -6,6 +6,7 @@
 // run the traversal kernel, hand back ascending (distance,id) lists.
 #include <cfloat>
 #include <cmath>
+#include <cstring>
 
 #include "search.cuh"
 
@@ -28,8 +29,7 @@ static cudaError_t dispatch(int acc, const SearchArgs &a, const SearchLaunch &l,
   return cudaErrorInvalidValue;
 }
 
-#define BIG_TIER_CTAS 32u
-#define BIG_TIER_QUEUE (1u << 20)
+#define BIG_TIER_QUEUE (1u << 18)
 
 int ngtgpu_traverse(ngtgpu_index *ix, const uint8_t *d_queries, uint32_t nq, const ngtgpu_search_params *params,
                     const uint32_t *d_seeds, uint32_t n_seeds, uint32_t *d_ids, float *d_dists, uint32_t *d_counts,
@@ -53,6 +53,7 @@ int ngtgpu_traverse(ngtgpu_index *ix, const uint8_t *d_queries, uint32_t nq, con
   a.n = ix->n;
   a.row_ptr = ix->d_row_ptr;
   a.col = ix->d_col;
+  a.head = ix->d_head;
   a.queries = d_queries;
   a.seeds = d_seeds;
   a.n_seeds = n_seeds;
@@ -69,17 +70,19 @@ int ngtgpu_traverse(ngtgpu_index *ix, const uint8_t *d_queries, uint32_t nq, con
   a.dists = d_dists;
   a.counts = d_counts;
   a.stats = d_stats;
+  a.prof = ix->d_prof;
 
-  // counters: [0] work counter tier 0, [1] overflow count, [2] work counter tier 1, [3] failed count, [4..] list
+  // counters (16 words): [2t] work counter of tier t, [2t+1] overflow count of tier t (t = 0, 1), [4] work counter
+  // of the HBM tier, [5] failed count; then two overflow lists of nq entries each
   uint32_t *ws = nullptr;
-  NGTGPU_TRY(ngtgpu_scratch(ix, SCR_SEARCH_WS, (size_t)(nq + 8) * sizeof(uint32_t), (void **)&ws));
-  CUDA_TRY(cudaMemsetAsync(ws, 0, 8 * sizeof(uint32_t), stream));
-  a.work_counter = ws + 0;
-  a.overflow_count = ws + 1;
-  a.overflow_list = ws + 8;
-  a.failed_count = ws + 3;
+  NGTGPU_TRY(ngtgpu_scratch(ix, SCR_SEARCH_WS, ((size_t)2 * nq + 16) * sizeof(uint32_t), (void **)&ws));
+  CUDA_TRY(cudaMemsetAsync(ws, 0, 16 * sizeof(uint32_t), stream));
+  uint32_t *lists[2] = {ws + 16, ws + 16 + nq};
+  a.failed_count = ws + 5;
 
-  // ---- tier 0: shared-memory working set
+  // ---- on-chip tiers: the configured working set, then (for the queries that outgrew it) the largest one
+  // that still fits one CTA per SM. Later tiers read the previous tier's overflow list and exit at once
+  // when it is empty, so no host synchronisation is needed in between.
   SearchLaunch l;
   l.group = (int)ix->group;
   if (ix->group < 32) l.cpl = 1;
@@ -89,43 +92,86 @@ int ngtgpu_traverse(ngtgpu_index *ix, const uint8_t *d_queries, uint32_t nq, con
   }
   l.ws = 0;
   l.stream = stream;
-  size_t smem = (k > 32 ? (((size_t)k * 8 + 15) & ~(size_t)15) : 0) + (size_t)a.queue_cap * 8 + ((size_t)4 << a.hash_bits);
-  if (l.cpl == 0) smem += ix->row_bytes;
-  if (smem > 200 * 1024) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "search: working set does not fit shared memory; lower hash_bits/queue_cap");
-  l.smem = smem;
-  int blocks = 0;
-  cudaError_t e = dispatch(ix->acc_kind, a, l, 1, &blocks);
-  if (e != cudaSuccess) NGTGPU_FAIL(NGTGPU_ERR_CUDA, std::string("search occupancy query: ") + cudaGetErrorString(e));
-  if (blocks < 1) blocks = 1;
-  uint64_t grid = (uint64_t)blocks * ix->sm_count;
-  if (grid > nq) grid = nq;
-  if (grid == 0) return NGTGPU_OK;
-  l.grid = (unsigned)grid;
-  e = dispatch(ix->acc_kind, a, l, 0, nullptr);
-  if (e != cudaSuccess) NGTGPU_FAIL(NGTGPU_ERR_CUDA, std::string("search kernel launch: ") + cudaGetErrorString(e));
-  ix->launches++;
+  const size_t res_bytes = k > 32 ? (((size_t)k * 8 + 15) & ~(size_t)15) : 0;
+  // staging area of the TMA row gather: as many rows as fit the budget, 4..64
+  // (split evenly between the 4 warps: a multiple of 4, and of 4 x rows-per-instruction for short rows)
+  uint32_t stage_rows = ix->stage_bytes / ix->row_bytes;
+  const uint32_t unit = 4 * (32 / ix->group);
+  if (stage_rows > 128) stage_rows = 128;
+  stage_rows = stage_rows / unit * unit;
+  if (stage_rows < unit) stage_rows = unit;
+  a.stage_rows = stage_rows;
+  const size_t stage_bytes = ((size_t)stage_rows * ix->row_bytes + 127) & ~(size_t)127;
+  const size_t extra = stage_bytes + res_bytes + (l.cpl == 0 ? ix->row_bytes : 0);
+  uint32_t tier_bits[2] = {ix->hash_bits, 17};
+  uint32_t tier_queue[2] = {ix->queue_cap, 4096};
+  int n_tiers = ix->onchip_tiers >= 2 ? 2 : 1;
+  if (tier_bits[0] >= 17) n_tiers = 1;
+  for (int t = 0; t < n_tiers; t++) {
+    a.hash_bits = tier_bits[t];
+    a.hash_limit = (uint32_t)((3ull << a.hash_bits) / 4);
+    a.queue_cap = tier_queue[t];
+    a.work_counter = ws + 2 * t;
+    a.overflow_count = ws + 2 * t + 1;
+    a.overflow_list = lists[t & 1];
+    a.query_list = t == 0 ? nullptr : lists[(t - 1) & 1];
+    a.query_list_count = t == 0 ? nullptr : ws + 2 * (t - 1) + 1;
+    size_t smem = extra + (size_t)a.queue_cap * 8;
+    if (smem > 200 * 1024)
+      NGTGPU_FAIL(NGTGPU_ERR_INVALID, "search: working set does not fit shared memory; lower queue_cap/size");
+    l.smem = smem;
+    int blocks = 0;
+    cudaError_t e = dispatch(ix->acc_kind, a, l, 1, &blocks);
+    if (e != cudaSuccess) NGTGPU_FAIL(NGTGPU_ERR_CUDA, std::string("search occupancy query: ") + cudaGetErrorString(e));
+    if (blocks < 1) blocks = 1;
+    if (t > 0 && blocks > 2) blocks = 2;   // the overflow tier serves few queries: keep its slabs small
+    uint64_t grid = (uint64_t)blocks * ix->sm_count;
+    if (grid > nq) grid = nq;
+    if (grid == 0) return NGTGPU_OK;
+    l.grid = (unsigned)grid;
+    // visited-hash slabs of this tier: one per CTA, in global memory (they live in L2)
+    uint32_t *slabs = nullptr;
+    NGTGPU_TRY(ngtgpu_scratch(ix, t == 0 ? SCR_HASH0 : SCR_HASH1, (size_t)grid * ((size_t)4 << a.hash_bits), (void **)&slabs));
+    a.hash_slabs = slabs;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (ix->timing && t == 0) {
+      CUDA_TRY(cudaEventCreate(&ev0));
+      CUDA_TRY(cudaEventCreate(&ev1));
+      CUDA_TRY(cudaEventRecord(ev0, stream));
+    }
+    e = dispatch(ix->acc_kind, a, l, 0, nullptr);
+    if (e != cudaSuccess) NGTGPU_FAIL(NGTGPU_ERR_CUDA, std::string("search kernel launch: ") + cudaGetErrorString(e));
+    ix->launches++;
+    if (ix->timing && t == 0) {
+      CUDA_TRY(cudaEventRecord(ev1, stream));
+      ix->timing_events.push_back(ev0);
+      ix->timing_events.push_back(ev1);
+    }
+  }
 
-  // ---- tier 1: HBM working set for the queries that overflowed (exits at once when there are none)
+  // ---- HBM tier: exact bitmap + large queue in global memory for whatever is still left
+  const int last = n_tiers - 1;
   const uint64_t bitmap_words = ((ix->n + 1 + 31) / 32 + 3) & ~(uint64_t)3;
+  const uint32_t big_ctas = (uint32_t)ix->sm_count;
   uint32_t big_queue = BIG_TIER_QUEUE;
-  size_t big_bytes = (size_t)BIG_TIER_CTAS * (bitmap_words * 4 + (size_t)big_queue * 8);
+  size_t big_bytes = (size_t)big_ctas * (bitmap_words * 4 + (size_t)big_queue * 8);
   uint8_t *big = nullptr;
   NGTGPU_TRY(ngtgpu_scratch(ix, SCR_SEARCH_BIG, big_bytes, (void **)&big));
   SearchArgs b = a;
-  b.work_counter = ws + 2;
-  b.query_list = ws + 8;
-  b.query_list_count = ws + 1;
+  b.work_counter = ws + 4;
+  b.query_list = lists[last & 1];
+  b.query_list_count = ws + 2 * last + 1;
+  b.overflow_list = nullptr;
+  b.overflow_count = nullptr;
   b.queue_cap = big_queue;
   b.big_queues = reinterpret_cast<uint64_t *>(big);
-  b.big_bitmaps = reinterpret_cast<uint32_t *>(big + (size_t)BIG_TIER_CTAS * big_queue * 8);
+  b.big_bitmaps = reinterpret_cast<uint32_t *>(big + (size_t)big_ctas * big_queue * 8);
   b.bitmap_words = bitmap_words;
   SearchLaunch lb = l;
-  lb.group = 32;
-  lb.cpl = 0;
   lb.ws = 1;
-  lb.grid = BIG_TIER_CTAS;
-  lb.smem = (k > 32 ? (((size_t)k * 8 + 15) & ~(size_t)15) : 0) + ix->row_bytes;
-  e = dispatch(ix->acc_kind, b, lb, 0, nullptr);
+  lb.grid = big_ctas;
+  lb.smem = extra;
+  cudaError_t e = dispatch(ix->acc_kind, b, lb, 0, nullptr);
   if (e != cudaSuccess) NGTGPU_FAIL(NGTGPU_ERR_CUDA, std::string("search overflow-tier launch: ") + cudaGetErrorString(e));
   ix->launches++;
   return NGTGPU_OK;
@@ -205,7 +251,7 @@ static int search_common(ngtgpu_index *ix, const void *queries, int query_type, 
   NGTGPU_TRY(ngtgpu_traverse(ix, d_q, nq, params, d_seeds, ns, d_ids, d_dists, d_counts, d_stats, stream));
   if (!on_device) {
     uint32_t *ws = (uint32_t *)ix->d_scratch[SCR_SEARCH_WS];
-    uint32_t h_ws[4] = {0, 0, 0, 0};
+    uint32_t h_ws[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     CUDA_TRY(cudaMemcpyAsync(ids, d_ids, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaMemcpyAsync(dists, d_dists, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaMemcpyAsync(counts, d_counts, (size_t)nq * 4, cudaMemcpyDeviceToHost, stream));
@@ -213,9 +259,9 @@ static int search_common(ngtgpu_index *ix, const void *queries, int query_type, 
     CUDA_TRY(cudaMemcpyAsync(h_ws, ws, sizeof(h_ws), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
     ix->last_overflows = h_ws[1];
-    if (h_ws[3])
-      NGTGPU_FAIL(NGTGPU_ERR_STATE, "search: " + std::to_string(h_ws[3]) +
-                                        " queries outgrew the HBM working set (unchecked queue > 2^20 entries)");
+    if (h_ws[5])
+      NGTGPU_FAIL(NGTGPU_ERR_STATE, "search: " + std::to_string(h_ws[5]) +
+                                        " queries outgrew the HBM working set (unchecked queue > 2^18 entries)");
   }
   return NGTGPU_OK;
 }
@@ -233,4 +279,58 @@ extern "C" int ngtgpu_search_device(ngtgpu_index *ix, const void *queries, int q
   if (!ix) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "null index handle");
   return search_common(ix, queries, query_type, nq, params, seeds, n_seeds, ids, dists, counts, stats, true,
                        (cudaStream_t)stream);
+}
+
+// ---- device timing of the traversal kernel (CUDA events on the launching stream) -----------------------
+extern "C" int ngtgpu_index_set_timing(ngtgpu_index *ix, int enabled) {
+  if (!ix) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "null index handle");
+  ix->timing = enabled != 0;
+  return NGTGPU_OK;
+}
+
+// Sums and clears the recorded (start, stop) pairs: total milliseconds and number of traversal launches.
+extern "C" int ngtgpu_index_pop_timing(ngtgpu_index *ix, double *total_ms, uint64_t *launches) {
+  if (!ix || !total_ms || !launches) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "ngtgpu_index_pop_timing: null argument");
+  NGTGPU_TRY(ngtgpu_check_device(ix));
+  double sum = 0.0;
+  uint64_t cnt = 0;
+  for (size_t i = 0; i + 1 < ix->timing_events.size(); i += 2) {
+    CUDA_TRY(cudaEventSynchronize(ix->timing_events[i + 1]));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, ix->timing_events[i], ix->timing_events[i + 1]));
+    sum += ms;
+    cnt++;
+    cudaEventDestroy(ix->timing_events[i]);
+    cudaEventDestroy(ix->timing_events[i + 1]);
+  }
+  ix->timing_events.clear();
+  *total_ms = sum;
+  *launches = cnt;
+  return NGTGPU_OK;
+}
+
+// The seeds the engine would use for these queries (nearest pivots of the seed table): lets a caller run
+// the reference's GraphIndex::search(sc, seeds) from identical starting points.
+extern "C" int ngtgpu_select_seeds(ngtgpu_index *ix, const void *queries, int query_type, uint32_t nq, uint32_t n_seeds,
+                                   uint32_t *seeds_out) {
+  if (!ix) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "null index handle");
+  NGTGPU_TRY(ngtgpu_check_device(ix));
+  if (!queries || !seeds_out) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "ngtgpu_select_seeds: null buffer");
+  if (nq == 0) return NGTGPU_OK;
+  uint8_t *d_q = nullptr;
+  NGTGPU_TRY(ngtgpu_scratch(ix, SCR_QUERIES, (size_t)nq * ix->row_bytes, (void **)&d_q));
+  NGTGPU_TRY(ngtgpu_prepare_queries(ix, queries, query_type, nq, false, d_q, ix->stream));
+  uint32_t *s = nullptr;
+  if (n_seeds > ix->n_pivots) n_seeds = ix->n_pivots;
+  NGTGPU_TRY(select_seeds(ix, d_q, nq, n_seeds, &s, ix->stream));
+  CUDA_TRY(cudaMemcpyAsync(seeds_out, s, (size_t)nq * n_seeds * 4, cudaMemcpyDeviceToHost, ix->stream));
+  CUDA_TRY(cudaStreamSynchronize(ix->stream));
+  return NGTGPU_OK;
+}
+
+// development aid: per-phase cycle counters of warp 0 (nq x 8 words, device buffer owned by the caller)
+extern "C" int ngtgpu_index_set_phase_profile(ngtgpu_index *ix, uint32_t *d_buffer) {
+  if (!ix) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "null index handle");
+  ix->d_prof = d_buffer;
+  return NGTGPU_OK;
 }

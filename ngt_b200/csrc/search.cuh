@@ -16,22 +16,34 @@
 // exceeds the current explorationRadius can never be expanded (the radius only shrinks). That lets the
 // neighbours of one node be evaluated in parallel and merged afterwards with results identical to the
 // sequential loop whenever coef >= 1. For coef < 1 (negative epsilon) the order inside one adjacency
-// list matters (results are gated by the shrinking explorationRadius), so the merge falls back to the
-// reference's element-by-element order.
+// list matters (results are gated by the shrinking explorationRadius), so filter and merge fall back to
+// the reference's element-by-element order.
 //
-// Work split inside the CTA (4 warps): warp 0 is the control warp (queue pop, adjacency read, visited
-// filter, merge); all warps gather the surviving neighbours' rows from HBM with 128-bit loads, G lanes
-// per row (G = min(32, pow2ceil(row_bytes/16))), several rows in flight per lane.
+// One round of the loop inside the CTA (4 warps):
+//   control   warp 0 merges the previous round's keys into results/unchecked, pops the next node.
+//   filter    all threads: thread e reads edge e of the node -- one coalesced access to a fixed-stride
+//             table of the first 64 edges of every node (the CSR only when edgeSize > 64) -- and
+//             test-and-sets it in the visited set (shared-memory hash, atomicCAS).
+//   gather    every warp copies the rows of its share of the surviving neighbours from HBM into a
+//             shared-memory staging area with cp.async (16 B per lane: one warp instruction moves a whole
+//             512-byte row, no registers held while the copies are in flight -- the GPU counterpart of the
+//             reference's _mm_prefetch pipeline, Graph.cpp:446-456), waits for its own copies only, and
+//             evaluates the distances from shared memory, G lanes per row.
 //
-// Tiers: WS == 0 keeps the visited set (open-addressing hash) and the queue in shared memory; a query
-// that outgrows them is appended to an overflow list and re-run by the WS == 1 instantiation, which
-// keeps an exact bitmap and a large queue in HBM (the reference's own choice, Graph.h:751-799).
+// Where the state lives. Results and the unchecked queue are in shared memory (registers for k <= 32). The
+// visited set of WS == 0 is an exact open-addressing hash in a per-CTA slab of GLOBAL memory: the slabs of
+// all resident CTAs (8 per SM x 32 KB) stay in the 126 MB L2, whose capacity is of little use to the
+// 512 MB of randomly gathered rows anyway, and taking the hash out of shared memory is what lets 8 CTAs
+// share an SM instead of 3. A query that outgrows its slab or queue is appended to an overflow list and
+// re-run by a later launch with a larger slab or, finally (WS == 1), with an exact bitmap and a large
+// queue in HBM (the reference's own structures, Graph.h:751-799).
 #pragma once
 #include "ngtgpu_internal.cuh"
 
 #define SEARCH_WARPS 4
 #define SEARCH_THREADS (SEARCH_WARPS * 32)
-#define SEARCH_CMAX 128  // adjacency entries filtered per round
+#define SEARCH_CMAX 128       // upper bound of edges filtered / rows staged per round (== SEARCH_THREADS)
+#define SEARCH_HEAD 64        // edges per node in the fixed-stride adjacency table
 
 struct SearchArgs {
   const uint8_t *objects;
@@ -40,6 +52,7 @@ struct SearchArgs {
   uint64_t n;
   const uint64_t *row_ptr;
   const uint32_t *col;
+  const uint32_t *head;    // (n+1) x SEARCH_HEAD, zero padded
   const uint8_t *queries;  // prepared rows, nq x row_bytes
   const uint32_t *seeds;   // nq x n_seeds
   uint32_t n_seeds;
@@ -52,25 +65,37 @@ struct SearchArgs {
   uint32_t hash_bits;   // WS == 0
   uint32_t hash_limit;  // max visited entries before overflow (WS == 0)
   uint32_t queue_cap;
+  uint32_t stage_rows;  // rows the staging area holds (<= SEARCH_CMAX)
   uint32_t *ids;
   float *dists;
   uint32_t *counts;
   uint32_t *stats;  // nullable, nq x 3
   uint32_t *work_counter;
-  const uint32_t *query_list;        // WS == 1: the overflow list of the first tier
-  const uint32_t *query_list_count;  // WS == 1
+  const uint32_t *query_list;        // nullable: run only these queries (the overflow list of the previous tier)
+  const uint32_t *query_list_count;
   uint32_t *overflow_list;           // WS == 0: where overflowing queries go
   uint32_t *overflow_count;
   uint32_t *failed_count;            // WS == 1: queries that outgrew even the HBM tier
+  uint32_t *hash_slabs;              // WS == 0: gridDim.x x 2^hash_bits words, L2-resident
   uint32_t *big_bitmaps;             // WS == 1: gridDim.x x bitmap_words
   uint64_t *big_queues;              // WS == 1: gridDim.x x queue_cap
   uint64_t bitmap_words;
+  uint32_t *prof;                    // nullable, nq x 8: cycles of warp 0 per phase (development aid)
 };
 
 __device__ __forceinline__ uint32_t lanemask_lt() {
   uint32_t m;
   asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
   return m;
+}
+
+// ---- cp.async: 16 bytes global -> shared without a register round trip (LDGSTS) -----------------------
+__device__ __forceinline__ void cp_async_row16(void *smem_dst, const void *gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
 // ---- result list: k smallest keys ---------------------------------------------------------------------
@@ -121,17 +146,110 @@ __device__ __forceinline__ uint64_t result_kth(const ResultList &R) {  // valid 
   return R.smem[R.k - 1];
 }
 
+// Fold eight per-lane partial sums (eight rows) over the 32 lanes with 9 shuffles instead of 40: at each
+// of the first three butterfly levels a lane keeps half of its rows and hands the other half to its
+// partner. Every row is still summed over the pairs (lane, lane ^ 16), (.., ^ 8), (.., ^ 4), (.., ^ 2),
+// (.., ^ 1) in that order, i.e. exactly group_fold<ACC, 32>, so the float bits are the same. On return
+// the total of row ((lane >> 2) & 7) is in v[0] of every lane.
+template <typename T>
+__device__ __forceinline__ void fold8(T (&v)[8], int lane) {
+  {
+    const bool up = (lane & 16) != 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      T send = up ? v[i] : v[i + 4];
+      T keep = up ? v[i + 4] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool up = (lane & 8) != 0;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      T send = up ? v[i] : v[i + 2];
+      T keep = up ? v[i + 2] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool up = (lane & 4) != 0;
+    T send = up ? v[0] : v[1];
+    T keep = up ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 2);
+  v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+// ---- visited set of WS == 0: exact hash in a per-CTA slab of global memory (L2 resident) ----------------
+// The slab is an array of 32-byte buckets of eight ids. A lookup is ONE 32-byte read of the home bucket
+// (ld.global.cg: served by L2, never a stale L1 line): the id is there, or the bucket has a free slot and
+// the id is new (moving on to the next bucket only when all eight slots are taken by other ids). The
+// insertion -- atomicCAS on the free slot -- does not gate anything and is issued later, while the row
+// copies of the round are in flight.
+struct BucketProbe {
+  uint32_t bucket;   // where the id belongs (first bucket with a free slot)
+  uint32_t slot;     // first free slot seen there
+};
+
+__device__ __forceinline__ bool hash_lookup(const uint32_t *hash, uint32_t bucket_bits, uint32_t nid, BucketProbe &bp) {
+  const uint32_t bmask = (1u << bucket_bits) - 1u;
+  uint32_t b = (nid * 2654435761u) >> (32 - bucket_bits);
+  for (;;) {
+    const uint4 lo = __ldcg(reinterpret_cast<const uint4 *>(hash + (size_t)b * 8));
+    const uint4 hi = __ldcg(reinterpret_cast<const uint4 *>(hash + (size_t)b * 8) + 1);
+    const uint32_t v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    uint32_t free_slot = 8;
+#pragma unroll
+    for (int i = 7; i >= 0; i--) {
+      if (v[i] == nid) return true;   // visited
+      if (v[i] == 0u) free_slot = i;
+    }
+    if (free_slot < 8) {
+      bp.bucket = b;
+      bp.slot = free_slot;
+      return false;
+    }
+    b = (b + 1) & bmask;
+  }
+}
+
+// returns false when the id turned out to be in the table already (a duplicate inside one round)
+__device__ __forceinline__ bool hash_insert(uint32_t *hash, uint32_t bucket_bits, uint32_t nid, BucketProbe bp) {
+  const uint32_t bmask = (1u << bucket_bits) - 1u;
+  uint32_t b = bp.bucket, s0 = bp.slot;
+  for (;;) {
+    for (uint32_t i = s0; i < 8; i++) {
+      uint32_t old = atomicCAS(&hash[(size_t)b * 8 + i], 0u, nid);
+      if (old == 0u) return true;
+      if (old == nid) return false;
+    }
+    b = (b + 1) & bmask;
+    s0 = 0;
+  }
+}
+
+// WS == 1: exact bitmap in HBM, test-and-set in one atomic
+__device__ __forceinline__ bool bitmap_visit(uint32_t *bitmap, uint32_t nid) {
+  uint32_t bit = 1u << (nid & 31);
+  uint32_t old = atomicOr(&bitmap[nid >> 5], bit);
+  return (old & bit) == 0;
+}
+
 template <int ACC, int G, int CPL, int WS>
 __global__ void __launch_bounds__(SEARCH_THREADS) search_kernel(const SearchArgs a) {
-  constexpr int R = 32 / G;                                  // rows per warp instruction
-  constexpr int NCH = CPL > 0 ? CPL : 1;                      // register-resident query chunks per lane
-  constexpr int U = CPL == 0 ? 2 : (CPL >= 8 ? 2 : (CPL >= 4 ? 2 : (CPL == 2 ? 4 : 8)));  // row groups in flight per warp
-  extern __shared__ __align__(16) uint8_t smem_raw[];
+  constexpr int R = 32 / G;                 // rows per warp instruction (G < 32)
+  constexpr int NCH = CPL > 0 ? CPL : 1;    // register-resident query chunks per lane
+  extern __shared__ __align__(128) uint8_t smem_raw[];
   __shared__ uint32_t s_cand_ids[SEARCH_CMAX];
   __shared__ uint64_t s_cand_keys[SEARCH_CMAX];
   __shared__ uint32_t s_cand_n;
-  __shared__ int s_state;  // 0 run, 1 finished, 2 overflow
+  __shared__ uint32_t s_edge_n;   // non-empty edges seen by the filter (head-table mode)
+  __shared__ int s_state;         // 0 run, 1 finished, 2 overflow
   __shared__ uint32_t s_query;
+  __shared__ int s_seeding;       // the round reads a seed list
+  __shared__ uint32_t s_take;     // edges to filter this round
+  __shared__ const uint32_t *s_src;  // where they are (head row, CSR slice or seed list)
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -139,8 +257,10 @@ __global__ void __launch_bounds__(SEARCH_THREADS) search_kernel(const SearchArgs
   const int gl = lane % G;   // lane inside its row group
   const int grp = lane / G;  // row group inside the warp
 
-  // ---- carve dynamic shared memory: [results k>32][queue][hash][query copy (CPL==0)]
+  // ---- carve dynamic shared memory: [staging][results k>32][queue][query copy (CPL==0)]
   uint8_t *sp = smem_raw;
+  uint8_t *stage = sp;
+  sp += ((size_t)a.stage_rows * a.row_bytes + 127) & ~(size_t)127;
   uint64_t *s_results = reinterpret_cast<uint64_t *>(sp);
   sp += a.k > 32 ? (((size_t)a.k * 8 + 15) & ~(size_t)15) : 0;
   uint64_t *queue;
@@ -149,23 +269,25 @@ __global__ void __launch_bounds__(SEARCH_THREADS) search_kernel(const SearchArgs
   if (WS == 0) {
     queue = reinterpret_cast<uint64_t *>(sp);
     sp += (size_t)a.queue_cap * 8;
-    hash = reinterpret_cast<uint32_t *>(sp);
-    sp += (size_t)4 << a.hash_bits;
+    hash = a.hash_slabs + ((size_t)blockIdx.x << a.hash_bits);
   } else {
     queue = a.big_queues + (size_t)blockIdx.x * a.queue_cap;
     bitmap = a.big_bitmaps + (size_t)blockIdx.x * a.bitmap_words;
   }
   const uint4 *s_query_row = reinterpret_cast<const uint4 *>(sp);  // CPL == 0 only
-  const uint32_t hash_mask = (1u << a.hash_bits) - 1u;
+  const uint32_t round_cap = SEARCH_CMAX;
+  const bool ordered = a.coef < 1.0f;           // negative epsilon: keep the reference's element order
+  const bool use_head = a.edge_cap <= SEARCH_HEAD;
 
   for (;;) {
     // ---- next query (dynamic scheduling over a persistent grid)
     if (tid == 0) {
       uint32_t w = atomicAdd(a.work_counter, 1u);
-      uint32_t total = WS == 0 ? a.nq : *a.query_list_count;
-      s_query = w < total ? (WS == 0 ? w : a.query_list[w]) : 0xffffffffu;
+      uint32_t total = a.query_list ? *a.query_list_count : a.nq;
+      s_query = w < total ? (a.query_list ? a.query_list[w] : w) : 0xffffffffu;
       s_state = 0;
       s_cand_n = 0;
+      s_edge_n = 0;
     }
     __syncthreads();
     const uint32_t q = s_query;
@@ -235,18 +357,31 @@ __global__ void __launch_bounds__(SEARCH_THREADS) search_kernel(const SearchArgs
     const uint32_t *cur = a.seeds + (size_t)q * a.n_seeds;
     uint32_t cur_deg = a.n_seeds, cur_pos = 0;
     bool seeding = true;
+    bool head_round = false;      // the round in flight read a head-table row (its edge count comes from s_edge_n)
     uint32_t cand_n = 0;
+    uint32_t pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tp = a.prof ? clock64() : 0;
+#define PROF_MARK(i)                     \
+  if (a.prof) {                          \
+    long long _t = clock64();            \
+    pf[i] += (uint32_t)(_t - tp);        \
+    tp = _t;                             \
+  }
 
     for (;;) {
+      // ================= control (warp 0): merge the previous round, choose the next edges =================
       if (warp == 0) {
-        // ======== merge the keys evaluated in the previous round ========
+        bool overflow = false;
+        PROF_MARK(7)
+        if (head_round) st_edge += s_edge_n;
+        visited_n += cand_n;
+        st_dist += cand_n;
         if (cand_n) {
-          if (a.coef >= 1.0f && !seeding) {
+          if (!ordered && !seeding) {
             // set semantics: results first, then everything within the final explorationRadius
             for (uint32_t j0 = 0; j0 < cand_n; j0 += 32) {
               uint64_t key = j0 + lane < cand_n ? s_cand_keys[j0 + lane] : KEY_NONE;
-              float d = key_dist(key);
-              uint32_t m = __ballot_sync(0xffffffffu, key != KEY_NONE && d <= radius);
+              uint32_t m = __ballot_sync(0xffffffffu, key != KEY_NONE && key_dist(key) <= radius);
               while (m) {
                 int src = __ffs(m) - 1;
                 m &= m - 1;
@@ -257,7 +392,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS) search_kernel(const SearchArgs
               }
             }
             er = a.coef * radius;
-            for (uint32_t j0 = 0; j0 < cand_n; j0 += 32) {
+            for (uint32_t j0 = 0; j0 < cand_n && !overflow; j0 += 32) {
               uint64_t key = j0 + lane < cand_n ? s_cand_keys[j0 + lane] : KEY_NONE;
               bool acc = key != KEY_NONE && key_dist(key) <= er;
               uint32_t m = __ballot_sync(0xffffffffu, acc);
@@ -277,17 +412,24 @@ __global__ void __launch_bounds__(SEARCH_THREADS) search_kernel(const SearchArgs
                 qsize = w;
               }
               if (qsize + cnt > a.queue_cap) {
-                if (lane == 0) s_state = 2;
+                overflow = true;
                 break;
               }
-              if (acc) queue[qsize + __popc(m & lanemask_lt())] = key;
+              if (acc) {
+                queue[qsize + __popc(m & lanemask_lt())] = key;
+                if (use_head) {
+                  // its edges will be wanted when it is popped: pull that row of the head table towards L2 now
+                  const uint32_t *hp = a.head + (size_t)key_id(key) * SEARCH_HEAD;
+                  asm volatile("prefetch.global.L2 [%0];" ::"l"(hp));
+                  asm volatile("prefetch.global.L2 [%0];" ::"l"(hp + 32));
+                }
+              }
               qsize += cnt;
             }
             __syncwarp();
           } else {
             // the reference's order: seeds (all go to unchecked, Graph.cpp:352-366) and coef < 1
-            bool full = false;
-            for (uint32_t j0 = 0; j0 < cand_n && !full; j0 += 32) {
+            for (uint32_t j0 = 0; j0 < cand_n && !overflow; j0 += 32) {
               uint64_t key = j0 + lane < cand_n ? s_cand_keys[j0 + lane] : KEY_NONE;
               uint32_t m = __ballot_sync(0xffffffffu, key != KEY_NONE);
               while (m) {
@@ -297,8 +439,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS) search_kernel(const SearchArgs
                 float d = key_dist(kk);
                 if (!seeding && d > er) continue;
                 if (qsize >= a.queue_cap) {
-                  if (lane == 0) s_state = 2;
-                  full = true;
+                  overflow = true;
                   break;
                 }
                 if (lane == 0) queue[qsize] = kk;
@@ -316,161 +457,279 @@ __global__ void __launch_bounds__(SEARCH_THREADS) search_kernel(const SearchArgs
           }
         }
         cand_n = 0;
-        // ======== pop / filter until some unvisited neighbours are found ========
-        bool overflow = false;
-        __syncwarp();
-        if (*(volatile int *)&s_state == 2) overflow = true;
-        while (!overflow && cand_n == 0) {
-          if (cur_pos >= cur_deg) {
-            if (seeding) {
-              // setupSeeds: radius from the seeds once k of them are within it (Graph.cpp:349-351)
-              seeding = false;
-              if (res.n >= res.k) radius = key_dist(result_kth(res));
-              er = a.coef * radius;
+        head_round = false;
+        PROF_MARK(0)
+        // ---- next edges: the rest of the current list, or pop the smallest unchecked node
+        bool finished = false;
+        uint32_t take = 0;
+        const uint32_t *src_ptr = nullptr;
+        while (!overflow && !finished && take == 0) {
+          if (cur_pos < cur_deg) {
+            take = cur_deg - cur_pos;
+            if (take > round_cap) take = round_cap;
+            src_ptr = cur + cur_pos;
+            cur_pos += take;
+            break;
+          }
+          if (seeding) {
+            // setupSeeds: radius from the seeds once k of them are within it (Graph.cpp:349-351)
+            seeding = false;
+            if (res.n >= res.k) radius = key_dist(result_kth(res));
+            er = a.coef * radius;
+          }
+          uint64_t best = KEY_NONE;
+          uint32_t bi = 0;
+          for (uint32_t i = lane; i < qsize; i += 32) {
+            uint64_t v = queue[i];
+            if (v < best) {
+              best = v;
+              bi = i;
             }
-            // pop the smallest unchecked key
-            uint64_t best = KEY_NONE;
-            uint32_t bi = 0;
-            for (uint32_t i = lane; i < qsize; i += 32) {
-              uint64_t v = queue[i];
-              if (v < best) {
-                best = v;
-                bi = i;
-              }
-            }
+          }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-              uint64_t ob = shfl_xor_u64(best, o);
-              uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
-              if (ob < best) {
-                best = ob;
-                bi = oi;
-              }
+          for (int o = 16; o > 0; o >>= 1) {
+            uint64_t ob = shfl_xor_u64(best, o);
+            uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob < best) {
+              best = ob;
+              bi = oi;
             }
-            if (best == KEY_NONE || key_dist(best) > er) {  // Graph.cpp:430-435
-              if (lane == 0) s_state = 1;
-              break;
-            }
-            if (lane == 0) queue[bi] = queue[qsize - 1];
-            qsize--;
-            __syncwarp();
-            uint32_t t = key_id(best);
+          }
+          if (best == KEY_NONE || key_dist(best) > er) {  // Graph.cpp:430-435
+            finished = true;
+            break;
+          }
+          if (lane == 0) queue[bi] = queue[qsize - 1];
+          qsize--;
+          __syncwarp();
+          const uint32_t t = key_id(best);
+          st_exp++;
+          PROF_MARK(1)
+          if (use_head) {
+            // the whole (capped) list is one row of the head table; empty slots are zero
+            take = a.edge_cap < SEARCH_HEAD ? a.edge_cap : SEARCH_HEAD;
+            src_ptr = a.head + (size_t)t * SEARCH_HEAD;
+            head_round = true;
+            cur_deg = 0;
+            cur_pos = 0;
+          } else {
+            // longer lists (edgeSize > 64): walk the CSR slice (Graph.cpp:438 caps it)
             uint64_t b = 0, e = 0;
             if (lane < 2) b = a.row_ptr[(size_t)t + lane];
             e = shfl_u64(b, 1);
             b = shfl_u64(b, 0);
             uint64_t deg = e - b;
-            if (deg > a.edge_cap) deg = a.edge_cap;  // Graph.cpp:438
+            if (deg > a.edge_cap) deg = a.edge_cap;
             cur = a.col + b;
             cur_deg = (uint32_t)deg;
             cur_pos = 0;
             st_edge += cur_deg;
-            st_exp++;
-            if (cur_deg == 0) continue;
           }
-          uint32_t take = cur_deg - cur_pos;
-          if (take > SEARCH_CMAX) take = SEARCH_CMAX;
-          if (WS == 0 && visited_n + take > a.hash_limit) {
-            if (lane == 0) s_state = 2;
-            overflow = true;
-            break;
-          }
-          for (uint32_t e0 = 0; e0 < take; e0 += 32) {
-            uint32_t ei = e0 + lane;
-            uint32_t nid = ei < take ? __ldg(cur + cur_pos + ei) : 0u;
-            bool isnew = false;
-            if (nid != 0u && nid <= a.n) {
-              if (WS == 0) {
-                uint32_t slot = (nid * 2654435761u) >> (32 - a.hash_bits);
-                for (;;) {
-                  uint32_t old = atomicCAS(&hash[slot], 0u, nid);
-                  if (old == 0u) {
-                    isnew = true;
-                    break;
-                  }
-                  if (old == nid) break;
-                  slot = (slot + 1) & hash_mask;
-                }
-              } else {
-                uint32_t bit = 1u << (nid & 31);
-                uint32_t old = atomicOr(&bitmap[nid >> 5], bit);
-                isnew = (old & bit) == 0;
-              }
-            }
-            uint32_t m = __ballot_sync(0xffffffffu, isnew);
-            if (isnew) s_cand_ids[cand_n + __popc(m & lanemask_lt())] = nid;
-            cand_n += __popc(m);
-          }
-          cur_pos += take;
-          visited_n += cand_n;
+          PROF_MARK(2)
         }
-        st_dist += cand_n;
-        if (lane == 0) s_cand_n = cand_n;
+        if (WS == 0 && !overflow && !finished && visited_n + take > a.hash_limit) overflow = true;
+        if (lane == 0) {
+          s_cand_n = 0;
+          s_edge_n = 0;
+          s_take = take;
+          s_src = src_ptr;
+          s_seeding = seeding ? 1 : 0;
+          if (overflow) s_state = 2;
+          else if (finished) s_state = 1;
+        }
       }
-      __syncthreads();  // candidate list (or the final state) is published
+      __syncthreads();  // (A) the round is published
       if (s_state != 0) break;
-      const uint32_t cn = s_cand_n;
+      const bool seeding_round = s_seeding != 0;
 
-      // ======== gather: all warps evaluate the candidates' distances ========
+      // ================= filter: one edge per thread, looked up in the visited set =================
+      bool pending_insert = false;   // this thread found a new id whose insertion is still to be issued
+      uint32_t pending_id = 0;
+      BucketProbe bp;
+      bp.bucket = 0;
+      bp.slot = 0;
       {
-        const uint32_t rounds = (cn + SEARCH_WARPS * R * U - 1) / (SEARCH_WARPS * R * U);
-        for (uint32_t it = 0; it < rounds; it++) {
-          if (CPL > 0) {
-            uint4 rows[U][NCH];
-            uint32_t cid[U];
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-              uint32_t j = (it * U + u) * (SEARCH_WARPS * R) + warp * R + grp;
-              cid[u] = j < cn ? s_cand_ids[j] : 0u;
-              const uint8_t *rp = a.objects + (size_t)cid[u] * a.row_bytes;
-#pragma unroll
-              for (int i = 0; i < NCH; i++) {
-                uint32_t c = gl + i * G;
-                rows[u][i] = (j < cn && c < a.chunks) ? ldg16_stream(rp + (size_t)c * 16) : zero16();
+        const uint32_t take = s_take;
+        const uint32_t *src = s_src;
+        const bool immediate = seeding_round;   // seed lists may repeat an id: insert at once so the second copy is seen
+        if (!ordered) {
+          uint32_t nid = (uint32_t)tid < take ? __ldg(src + tid) : 0u;
+          const bool valid = nid != 0u && nid <= a.n;
+          bool isnew = false;
+          if (valid) {
+            if (WS == 0) {
+              isnew = !hash_lookup(hash, a.hash_bits - 3, nid, bp);
+              if (isnew && immediate) isnew = hash_insert(hash, a.hash_bits - 3, nid, bp);
+              else if (isnew) {
+                pending_insert = true;
+                pending_id = nid;
+              }
+            } else {
+              isnew = bitmap_visit(bitmap, nid);
+            }
+          }
+          const uint32_t m = __ballot_sync(0xffffffffu, isnew);
+          const uint32_t mv = __ballot_sync(0xffffffffu, valid);
+          uint32_t base = 0;
+          if (lane == 0) {
+            if (m) base = atomicAdd(&s_cand_n, __popc(m));
+            if (mv) atomicAdd(&s_edge_n, __popc(mv));
+          }
+          base = __shfl_sync(0xffffffffu, base, 0);
+          if (isnew) s_cand_ids[base + __popc(m & lanemask_lt())] = nid;
+        } else if (warp == 0) {
+          // element order kept: warp 0 walks the edges 32 at a time
+          uint32_t cn = 0, en = 0;
+          for (uint32_t e0 = 0; e0 < take; e0 += 32) {
+            uint32_t nid = e0 + lane < take ? __ldg(src + e0 + lane) : 0u;
+            const bool valid = nid != 0u && nid <= a.n;
+            bool isnew = false;
+            if (valid) {
+              if (WS == 0) {
+                isnew = !hash_lookup(hash, a.hash_bits - 3, nid, bp);
+                if (isnew) isnew = hash_insert(hash, a.hash_bits - 3, nid, bp);
+              } else {
+                isnew = bitmap_visit(bitmap, nid);
               }
             }
+            const uint32_t m = __ballot_sync(0xffffffffu, isnew);
+            en += __popc(__ballot_sync(0xffffffffu, valid));
+            if (isnew) s_cand_ids[cn + __popc(m & lanemask_lt())] = nid;
+            cn += __popc(m);
+            __syncwarp();
+          }
+          if (lane == 0) {
+            s_cand_n = cn;
+            s_edge_n = en;
+          }
+        }
+      }
+      __syncthreads();  // (B) the candidate list is complete
+      const uint32_t cn = s_cand_n;
+      if (warp == 0) {
+        cand_n = cn;
+        PROF_MARK(3)
+      }
+
+      // ================= gather: each warp stages and evaluates its own slice of the rows =================
+      // The staging area is split evenly between the warps (wrows rows each); candidates are taken in passes
+      // of 4 * wrows, warp w owning the w-th slice of every pass, so no CTA-wide synchronisation is needed
+      // between copying a row and reading it.
+      {
+        const uint32_t wrows = a.stage_rows / SEARCH_WARPS;
+        uint8_t *wstage = stage + (size_t)warp * wrows * a.row_bytes;
+        for (uint32_t j0 = warp * wrows; j0 < cn; j0 += SEARCH_WARPS * wrows) {
+          const uint32_t nr = cn - j0 < wrows ? cn - j0 : wrows;
+          if (G == 32) {
+            for (uint32_t r = 0; r < nr; r++) {
+              const uint8_t *srow = a.objects + (size_t)s_cand_ids[j0 + r] * a.row_bytes + (size_t)lane * 16;
+              uint8_t *drow = wstage + (size_t)r * a.row_bytes + (size_t)lane * 16;
+              if (CPL > 0) {
 #pragma unroll
-            for (int u = 0; u < U; u++) {
-              uint32_t j = (it * U + u) * (SEARCH_WARPS * R) + warp * R + grp;
-              Sums s = zero_sums();
-#pragma unroll
-              for (int i = 0; i < NCH; i++) acc_chunk<ACC>(s, qreg[i], rows[u][i]);
-              group_fold<ACC, G>(s);
-              if (gl == 0 && j < cn) s_cand_keys[j] = make_key(finish_distance<ACC>(a.dtype, s, qn), cid[u]);
+                for (int c = 0; c < NCH; c++)
+                  if ((uint32_t)lane + c * 32 < a.chunks) cp_async_row16(drow + c * 512, srow + c * 512);
+              } else {
+                for (uint32_t c = lane; c < a.chunks; c += 32) cp_async_row16(drow + (size_t)(c - lane) * 16, srow + (size_t)(c - lane) * 16);
+              }
             }
           } else {
-            // long rows: the query sits in shared memory, G == 32, one row per warp at a time
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-              uint32_t j = (it * U + u) * (SEARCH_WARPS * R) + warp * R + grp;
-              uint32_t id = j < cn ? s_cand_ids[j] : 0u;
-              const uint8_t *rp = a.objects + (size_t)id * a.row_bytes;
-              Sums s = zero_sums();
-              if (j < cn) {
-                uint32_t c = gl;
-                for (; c + 3 * G < a.chunks; c += 4 * G) {
-                  uint4 r0 = ldg16_stream(rp + (size_t)c * 16);
-                  uint4 r1 = ldg16_stream(rp + (size_t)(c + G) * 16);
-                  uint4 r2 = ldg16_stream(rp + (size_t)(c + 2 * G) * 16);
-                  uint4 r3 = ldg16_stream(rp + (size_t)(c + 3 * G) * 16);
-                  acc_chunk<ACC>(s, s_query_row[c], r0);
-                  acc_chunk<ACC>(s, s_query_row[c + G], r1);
-                  acc_chunk<ACC>(s, s_query_row[c + 2 * G], r2);
-                  acc_chunk<ACC>(s, s_query_row[c + 3 * G], r3);
-                }
-                for (; c < a.chunks; c += G) acc_chunk<ACC>(s, s_query_row[c], ldg16_stream(rp + (size_t)c * 16));
-              }
-              group_fold<ACC, G>(s);
-              if (gl == 0 && j < cn) s_cand_keys[j] = make_key(finish_distance<ACC>(a.dtype, s, qn), id);
+            // short rows: the slice is one flat run of nr * chunks 16-byte pieces
+            const uint32_t total = nr * a.chunks;
+            for (uint32_t x = lane; x < total; x += 32) {
+              const uint32_t r = x / a.chunks, c = x - r * a.chunks;
+              cp_async_row16(wstage + (size_t)r * a.row_bytes + (size_t)c * 16,
+                             a.objects + (size_t)s_cand_ids[j0 + r] * a.row_bytes + (size_t)c * 16);
             }
           }
+          if (WS == 0 && pending_insert) {
+            // the insertion of this thread's new id, overlapped with the row copies in flight
+            hash_insert(hash, a.hash_bits - 3, pending_id, bp);
+            pending_insert = false;
+          }
+          cp_async_commit_wait_all();
+          __syncwarp();
+          if (CPL > 0 && CPL <= 2 && G == 32) {
+            // eight rows at a time, folded together (fold8)
+            for (uint32_t r0 = 0; r0 < nr; r0 += 8) {
+              Sums s[8];
+#pragma unroll
+              for (int i = 0; i < 8; i++) {
+                s[i] = zero_sums();
+                if (r0 + i < nr) {
+                  const uint4 *rp = reinterpret_cast<const uint4 *>(wstage + (size_t)(r0 + i) * a.row_bytes);
+#pragma unroll
+                  for (int c = 0; c < NCH; c++) {
+                    const uint32_t ch = lane + c * 32;
+                    if (ch < a.chunks) acc_chunk<ACC>(s[i], qreg[c], rp[ch]);
+                  }
+                }
+              }
+              Sums tot = zero_sums();
+              if (ACC == ACC_U8_L2 || ACC == ACC_U8_HAM) {
+                uint32_t v[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) v[i] = s[i].u;
+                fold8<uint32_t>(v, lane);
+                tot.u = v[0];
+              } else {
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) v[i] = s[i].f0;
+                fold8<float>(v, lane);
+                tot.f0 = v[0];
+                if (ACC == ACC_F_COS) {
+#pragma unroll
+                  for (int i = 0; i < 8; i++) v[i] = s[i].f1;
+                  fold8<float>(v, lane);
+                  tot.f1 = v[0];
+                }
+              }
+              const uint32_t r = r0 + ((lane >> 2) & 7);
+              if ((lane & 3) == 0 && r < nr)
+                s_cand_keys[j0 + r] = make_key(finish_distance<ACC>(a.dtype, tot, qn), s_cand_ids[j0 + r]);
+            }
+          } else if (G == 32) {
+            // long rows: one row at a time (query chunks in registers, or in shared memory when CPL == 0)
+            for (uint32_t r = 0; r < nr; r++) {
+              const uint4 *rp = reinterpret_cast<const uint4 *>(wstage + (size_t)r * a.row_bytes);
+              Sums s = zero_sums();
+              if (CPL > 0) {
+#pragma unroll
+                for (int c = 0; c < NCH; c++) {
+                  const uint32_t ch = lane + c * 32;
+                  if (ch < a.chunks) acc_chunk<ACC>(s, qreg[c], rp[ch]);
+                }
+              } else {
+                for (uint32_t c = lane; c < a.chunks; c += 32) acc_chunk<ACC>(s, s_query_row[c], rp[c]);
+              }
+              group_fold<ACC, 32>(s);
+              if (lane == 0) s_cand_keys[j0 + r] = make_key(finish_distance<ACC>(a.dtype, s, qn), s_cand_ids[j0 + r]);
+            }
+          } else {
+            // short rows: R rows per warp instruction, G lanes each
+            for (uint32_t r0 = 0; r0 < nr; r0 += R) {
+              const uint32_t r = r0 + grp;
+              Sums s = zero_sums();
+              if (r < nr && (uint32_t)gl < a.chunks)
+                acc_chunk<ACC>(s, qreg[0], reinterpret_cast<const uint4 *>(wstage + (size_t)r * a.row_bytes)[gl]);
+              group_fold<ACC, G>(s);
+              if (gl == 0 && r < nr) s_cand_keys[j0 + r] = make_key(finish_distance<ACC>(a.dtype, s, qn), s_cand_ids[j0 + r]);
+            }
+          }
+          __syncwarp();
         }
+        if (WS == 0 && pending_insert) hash_insert(hash, a.hash_bits - 3, pending_id, bp);   // warps without rows this round
+        if (warp == 0) { PROF_MARK(5) }
       }
-      __syncthreads();  // keys are published
+      __syncthreads();  // (C) keys are published; the staging area may be overwritten
+      if (warp == 0) { PROF_MARK(6) }
     }
 
     // ---- write the outcome
     const int state = s_state;
+    if (a.prof && tid == 0 && state == 1) {
+      for (int i = 0; i < 8; i++) a.prof[(size_t)q * 8 + i] = pf[i];
+    }
     if (warp == 0) {
       if (state == 1) {
         for (uint32_t i = lane; i < a.k; i += 32) {
@@ -536,17 +795,20 @@ cudaError_t search_dispatch(const SearchArgs &a, const SearchLaunch &l, int op, 
 #define SEARCH_CASE(GG, CC, WW)                                   \
   if (l.group == GG && l.cpl == CC && l.ws == WW)                 \
     return op == 0 ? launch_one<ACC, GG, CC, WW>(a, l) : occupancy_one<ACC, GG, CC, WW>(l.smem, blocks);
-  SEARCH_CASE(1, 1, 0)
-  SEARCH_CASE(2, 1, 0)
-  SEARCH_CASE(4, 1, 0)
-  SEARCH_CASE(8, 1, 0)
-  SEARCH_CASE(16, 1, 0)
-  SEARCH_CASE(32, 1, 0)
-  SEARCH_CASE(32, 2, 0)
-  SEARCH_CASE(32, 4, 0)
-  SEARCH_CASE(32, 8, 0)
-  SEARCH_CASE(32, 0, 0)
-  SEARCH_CASE(32, 0, 1)
+#define SEARCH_CASES(WW) \
+  SEARCH_CASE(1, 1, WW)  \
+  SEARCH_CASE(2, 1, WW)  \
+  SEARCH_CASE(4, 1, WW)  \
+  SEARCH_CASE(8, 1, WW)  \
+  SEARCH_CASE(16, 1, WW) \
+  SEARCH_CASE(32, 1, WW) \
+  SEARCH_CASE(32, 2, WW) \
+  SEARCH_CASE(32, 4, WW) \
+  SEARCH_CASE(32, 8, WW) \
+  SEARCH_CASE(32, 0, WW)
+  SEARCH_CASES(0)
+  SEARCH_CASES(1)
+#undef SEARCH_CASES
 #undef SEARCH_CASE
   return cudaErrorInvalidValue;
 }

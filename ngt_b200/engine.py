@@ -135,8 +135,11 @@ class GpuIndex:
         _lib.check(self._lib.ngtgpu_index_set_search_property(self._h, int(edge_size_for_search),
                                                               int(dynamic_edge_size_base), int(dynamic_edge_size_rate)))
 
-    def set_search_workspace(self, hash_bits=13, queue_cap=1024):
+    def set_search_workspace(self, hash_bits=14, queue_cap=1024, onchip_tiers=2, stage_bytes=None):
         _lib.check(self._lib.ngtgpu_index_set_search_workspace(self._h, int(hash_bits), int(queue_cap)))
+        _lib.check(self._lib.ngtgpu_index_set_onchip_tiers(self._h, int(onchip_tiers)))
+        if stage_bytes is not None:
+            _lib.check(self._lib.ngtgpu_index_set_stage_bytes(self._h, int(stage_bytes)))
 
     def build_seed_table(self, n_pivots=4096, rng_seed=1):
         _lib.check(self._lib.ngtgpu_index_build_seed_table(self._h, int(n_pivots), int(rng_seed)))

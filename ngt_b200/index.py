@@ -1,0 +1,286 @@
+"""ngt_b200.Index -- the host-side mirror of ngtpy.Index (python/src/ngtpy.cpp:28-360, bindings :500-560)
+over the B200 engine: same method names, argument meaning, defaults and id numbering, plus the batch entry
+points a GPU needs (batch_search / batch_linear_search). Index directories are NGT's own (`prf`, `obj`,
+`grp`; see index_io.py), so an index built by the reference's `ngt create` opens here and vice versa.
+
+What differs, on purpose: seeds come from the device seed table instead of the DVP-tree,
+`build_index` builds the graph from an exact kNN pass on the device instead of incremental insertion, and
+a single-query `search` is a batch of one.
+"""
+import os
+
+import numpy as np
+
+from . import _lib, build, index_io
+from .engine import NORMALIZED, GpuIndex
+from ._lib import NgtGpuError
+
+FLT_MAX = 3.4028234663852886e38
+INT_MIN = -2 ** 31
+
+# python/src/ngtpy.cpp:59-99
+_DISTANCE_ARG = {
+    "L2": "L2", "Normalized L2": "NormalizedL2", "Hamming": "Hamming", "Angle": "Angle",
+    "Normalized Angle": "NormalizedAngle", "Cosine": "Cosine", "Normalized Cosine": "NormalizedCosine",
+}
+_OBJECT_ARG = {"Float": "Float-4", "float": "Float-4", "Byte": "Integer-1", "byte": "Integer-1"}
+
+
+def create(path, dimension, edge_size_for_creation=10, edge_size_for_search=40, distance_type="L2",
+           object_type="Float"):
+    """ngtpy.create: an empty index directory."""
+    if object_type not in _OBJECT_ARG:
+        raise NgtGpuError(_lib.ERR_INVALID, "ngtpy::create: invalid object type. %s" % object_type)
+    if distance_type not in _DISTANCE_ARG:
+        raise NgtGpuError(_lib.ERR_INVALID, "ngtpy::create: invalid distance type. %s" % distance_type)
+    prop = dict(index_io.DEFAULT_PRF)
+    prop.update({"Dimension": str(int(dimension)), "EdgeSizeForCreation": str(int(edge_size_for_creation)),
+                 "EdgeSizeForSearch": str(int(edge_size_for_search)), "DistanceType": _DISTANCE_ARG[distance_type],
+                 "ObjectType": _OBJECT_ARG[object_type]})
+    os.makedirs(path, exist_ok=True)
+    dt = index_io.object_dtype(prop)
+    index_io.write_prf(path, prop)
+    index_io.write_objects(path, np.zeros((0, int(dimension)), dt))
+    index_io.write_graph(path, np.zeros(2, np.uint64), np.zeros(0, np.uint32), np.zeros(0, np.float32))
+
+
+class Index:
+    def __init__(self, path, read_only=False, zero_based_numbering=True, tree_disabled=False, log_disabled=False,
+                 device=0, n_pivots=4096):
+        self.path = path
+        self.read_only = read_only
+        self.zero_numbering = zero_based_numbering
+        self.device = device
+        self.n_pivots = n_pivots
+        self.prop = index_io.read_prf(path)
+        self.object_type = index_io.OBJECT_TYPE_NAMES[self.prop["ObjectType"]]
+        self.distance_type = index_io.DISTANCE_TYPE_NAMES[self.prop["DistanceType"]]
+        self.dimension = int(self.prop["Dimension"])
+        self._dtype = index_io.object_dtype(self.prop)
+        rows, present = index_io.read_objects(path, self.prop)
+        self._objects = rows                      # ids 1..n, as stored (normalised when the space normalises)
+        self._present = present
+        row_ptr, col, dist, _ = index_io.read_graph(path)
+        self._graph = self._fit_graph(row_ptr, col, dist)
+        self._pending = 0                         # appended objects not yet in the graph
+        self._gpu = GpuIndex(self.object_type, self.distance_type, self.dimension, device)
+        self._num_dist = 0
+        # ngtpy defaults, python/src/ngtpy.cpp:43-48
+        self.default_size = 20
+        self.default_epsilon = 0.1
+        self.default_radius = FLT_MAX
+        self.default_edge_size = -1
+        self.default_expected_accuracy = -1.0
+        self._upload()
+
+    # ---- internals -------------------------------------------------------------------------------
+    def _fit_graph(self, row_ptr, col, dist):
+        n = self._objects.shape[0]
+        rp = np.zeros(n + 2, np.uint64)
+        m = min(row_ptr.size, n + 2)
+        rp[:m] = row_ptr[:m]
+        rp[m:] = row_ptr[-1]
+        return rp, col, dist
+
+    def _upload(self):
+        n = self._objects.shape[0]
+        if n == 0:
+            return
+        self._gpu.set_objects(self._objects, normalize=False)
+        removed = np.nonzero(self._present[1:] == 0)[0].astype(np.uint32) + 1
+        if removed.size:
+            self._gpu.set_removed(removed)
+        rp, col, _ = self._graph
+        self._gpu.set_graph(rp, col)
+        self._gpu.set_search_property(int(self.prop.get("EdgeSizeForSearch", 40)),
+                                      int(self.prop.get("DynamicEdgeSizeBase", 30)),
+                                      int(self.prop.get("DynamicEdgeSizeRate", 20)))
+        self._gpu.build_seed_table(min(self.n_pivots, n), 1)
+
+    def _ids_out(self, ids):
+        return ids.astype(np.int64) - 1 if self.zero_numbering else ids.astype(np.int64)
+
+    def _epsilon_from_accuracy(self, accuracy):
+        """Index::getEpsilonFromExpectedAccuracy (lib/NGT/Index.h:293-360): piecewise-linear table in prf."""
+        table = self.prop.get("AccuracyTable", "")
+        pts = []
+        for tok in table.split(","):
+            if ":" in tok:
+                e, a = tok.split(":")
+                pts.append((float(e), float(a)))
+        if not pts:
+            raise NgtGpuError(_lib.ERR_STATE, "expected_accuracy needs an AccuracyTable in the index property")
+        eps = np.array([p[0] for p in pts])
+        acc = np.array([p[1] for p in pts])
+        return float(np.interp(accuracy, acc, eps))
+
+    def _params(self, size, epsilon, edge_size, expected_accuracy):
+        size = self.default_size if size == 0 else int(size)
+        if expected_accuracy is not None and expected_accuracy > 0.0:
+            epsilon = self._epsilon_from_accuracy(expected_accuracy)
+        elif epsilon is None or epsilon <= -1.0:
+            epsilon = self.default_epsilon
+        if edge_size is None or edge_size < -2:
+            edge_size = self.default_edge_size
+        return size, float(epsilon), int(edge_size)
+
+    # ---- ngtpy.Index surface ---------------------------------------------------------------------
+    def set(self, num_of_search_objects=0, search_radius=-FLT_MAX, epsilon=-FLT_MAX, edge_size=INT_MIN,
+            expected_accuracy=-FLT_MAX):
+        if num_of_search_objects > 0:
+            self.default_size = num_of_search_objects
+        if search_radius > -FLT_MAX:
+            self.default_radius = search_radius
+        if epsilon > -FLT_MAX:
+            self.default_epsilon = epsilon
+        if edge_size >= -2:
+            self.default_edge_size = edge_size
+        if expected_accuracy > -FLT_MAX:
+            self.default_expected_accuracy = expected_accuracy
+
+    def batch_search(self, queries, size=0, epsilon=-FLT_MAX, edge_size=INT_MIN, expected_accuracy=-FLT_MAX,
+                     with_stats=False):
+        """queries [nq, dim] -> (ids [nq,size] (numbering per zero_based_numbering, -1 where fewer results),
+        distances [nq,size]); the batch form of search()."""
+        if self._pending:
+            raise NgtGpuError(_lib.ERR_STATE, "objects were appended: call build_index() before searching")
+        size, epsilon, edge_size = self._params(size, epsilon, edge_size, expected_accuracy)
+        radius = -1.0 if self.default_radius >= FLT_MAX else self.default_radius
+        seed_size = int(self.prop.get("SeedSize", 10)) or 10
+        out = self._gpu.search(queries, size, epsilon, radius, edge_size, n_seeds=seed_size, with_stats=True)
+        ids, dists, counts, stats = out
+        self._num_dist += int(stats[:, 0].sum())
+        res = self._ids_out(ids)
+        res[np.arange(size)[None, :] >= counts[:, None]] = -1
+        return (res, dists, stats) if with_stats else (res, dists)
+
+    def batch_linear_search(self, queries, size=0):
+        size = self.default_size if size == 0 else int(size)
+        radius = -1.0 if self.default_radius >= FLT_MAX else self.default_radius
+        ids, dists, counts = self._gpu.linear_search(queries, size, radius)
+        res = self._ids_out(ids)
+        res[np.arange(size)[None, :] >= counts[:, None]] = -1
+        return res, dists
+
+    def _one(self, ids, dists, with_distance):
+        ok = ids[0] >= (0 if self.zero_numbering else 1)
+        if not with_distance:
+            return ids[0][ok].astype(np.int32)
+        return [(int(i), float(d)) for i, d in zip(ids[0][ok], dists[0][ok])]
+
+    def search(self, query, size=0, epsilon=-FLT_MAX, edge_size=INT_MIN, expected_accuracy=-FLT_MAX,
+               with_distance=True):
+        q = np.asarray(query, np.float32).reshape(1, -1)
+        ids, dists = self.batch_search(q, size, epsilon, edge_size, expected_accuracy)
+        return self._one(ids, dists, with_distance)
+
+    def linear_search(self, query, size=0, with_distance=True):
+        q = np.asarray(query, np.float32).reshape(1, -1)
+        ids, dists = self.batch_linear_search(q, size)
+        return self._one(ids, dists, with_distance)
+
+    def get_num_of_distance_computations(self):
+        return self._num_dist
+
+    def get_object(self, object_id):
+        oid = object_id + 1 if self.zero_numbering else object_id
+        if oid < 1 or oid > self._objects.shape[0] or not self._present[oid]:
+            raise NgtGpuError(_lib.ERR_INVALID, "get_object: no such object %d" % object_id)
+        return [float(v) for v in self._objects[oid - 1]]
+
+    def _append(self, objects):
+        x = np.asarray(objects, np.float64)
+        if x.ndim == 1:
+            x = x[None, :]
+        if x.shape[1] != self.dimension:
+            raise NgtGpuError(_lib.ERR_INVALID, "ngtpy::insert: Error! dimensions are inconsitency. %d:%d" % (
+                self.dimension, x.shape[1]))
+        x = x.astype(np.float32)
+        if self.distance_type in NORMALIZED:
+            # ObjectSpace::normalize (lib/NGT/ObjectSpace.h:251-266) happens on the device at upload time:
+            # rows are stored raw here and replaced by the device's normalised rows in build_index()
+            if (np.abs(x).sum(axis=1) == 0).any():
+                raise NgtGpuError(_lib.ERR_ZERO_VECTOR, "normalize: a zero vector cannot be normalised")
+        first = self._objects.shape[0] + 1
+        self._objects = np.concatenate([self._objects, x.astype(self._dtype)], axis=0)
+        self._present = np.concatenate([self._present, np.ones(x.shape[0], np.uint8)])
+        self._pending += x.shape[0]
+        self._raw_from = min(getattr(self, "_raw_from", first), first)
+        return first
+
+    def insert(self, object, debug=False):
+        first = self._append(np.asarray(object).reshape(1, -1))
+        self._num_dist = 0
+        return first - 1 if self.zero_numbering else first
+
+    def batch_insert(self, objects, num_threads=8, debug=False):
+        self._append(objects)
+        self.build_index(num_threads)
+        self._num_dist = 0
+
+    def build_index(self, num_threads=8, target_size_of_graph=0):
+        """NGT::Index::createIndex: (re)builds the graph over all present objects. The reference inserts
+        object by object with approximate searches (lib/NGT/Index.cpp:721-792); here the edge candidates of
+        every node come from one exact kNN pass on the device and the ANNG is its symmetric closure
+        (out-edges + reverse edges, sorted by (distance,id)) -- what insertANNGNode converges to
+        (lib/NGT/Graph.h:611-626)."""
+        import torch
+        n = self._objects.shape[0]
+        if n == 0:
+            return
+        normalize = self.distance_type in NORMALIZED and getattr(self, "_raw_from", None) is not None
+        if normalize:
+            # normalise only the newly appended rows; stored rows are already unit length
+            first = self._raw_from
+            tmp = GpuIndex(self.object_type, self.distance_type, self.dimension, self.device)
+            tmp.set_objects(self._objects[first - 1:], normalize=True)
+            for i in range(first, n + 1):
+                self._objects[i - 1] = tmp.get_object(i - first + 1)
+            tmp.close()
+        self._raw_from = None
+        self._gpu.set_objects(self._objects, normalize=False)
+        removed = np.nonzero(self._present[1:] == 0)[0].astype(np.uint32) + 1
+        if removed.size:
+            self._gpu.set_removed(removed)
+        e = int(self.prop.get("EdgeSizeForCreation", 10))
+        k = min(e, max(n - 1 - removed.size, 1))
+        ids, dists, counts = build.knn_graph(self._gpu, k)
+        row_ptr, col, dist = build.reconstruct_graph(ids, dists, counts, k, k)
+        torch.cuda.synchronize()
+        self._graph = (row_ptr.cpu().numpy().astype(np.uint64), col.cpu().numpy().astype(np.uint32),
+                       dist.cpu().numpy())
+        self._pending = 0
+        rp, c, _ = self._graph
+        self._gpu.set_graph(rp, c)
+        self._gpu.set_search_property(int(self.prop.get("EdgeSizeForSearch", 40)),
+                                      int(self.prop.get("DynamicEdgeSizeBase", 30)),
+                                      int(self.prop.get("DynamicEdgeSizeRate", 20)))
+        self._gpu.build_seed_table(min(self.n_pivots, n), 1)
+        self.prop["GraphType"] = "ANNG"
+
+    def remove(self, object_id):
+        oid = object_id + 1 if self.zero_numbering else object_id
+        if oid < 1 or oid > self._objects.shape[0] or not self._present[oid]:
+            raise NgtGpuError(_lib.ERR_INVALID, "remove: no such object %d" % object_id)
+        self._present[oid] = 0
+        rp, col, dist = self._graph
+        keep = col != oid
+        src = np.repeat(np.arange(rp.size - 1), np.diff(rp.astype(np.int64)))
+        keep &= src != oid
+        deg = np.bincount(src[keep], minlength=rp.size - 1)
+        nrp = np.zeros_like(rp)
+        nrp[1:] = np.cumsum(deg)
+        self._graph = (nrp, col[keep], dist[keep])
+        self._upload()
+
+    def save(self):
+        if self._pending:
+            raise NgtGpuError(_lib.ERR_STATE, "objects were appended: call build_index() before save()")
+        self.prop["IndexType"] = "Graph"      # no `tre` is written; the reference opens Graph indexes without one
+        index_io.write_prf(self.path, self.prop)
+        index_io.write_objects(self.path, self._objects, self._present)
+        rp, col, dist = self._graph
+        index_io.write_graph(self.path, rp, col, dist, self._present)
+
+    def close(self):
+        self._gpu.close()

@@ -177,12 +177,14 @@ def test_seeded_against_port(eng, port, kind):
         check(ids, dists, counts, rids, rdists, rcounts, what=what)
         if kind != "f32cos":
             assert (stats.astype(np.uint64) == rstats).all(), what
-    # the HBM tier (tiny on-chip working set forces every query to overflow) gives the same answers
-    ix.set_search_workspace(hash_bits=8, queue_cap=64)
-    ids, dists, counts = ix.search(q, k, 0.1, edge_size=0, seeds=seeds)
-    assert ix.last_overflows > 0
+    # a tiny on-chip working set forces every query to overflow: the second shared-memory tier, and the
+    # HBM tier (exact bitmap + queue in global memory), give the same answers
     rids, rdists, rcounts, _ = port.graph_search(dtype, otype, pobj, row_ptr, col, pq, seeds, k, 0.1)
-    check(ids, dists, counts, rids, rdists, rcounts, what=kind + " overflow tier")
+    for tiers in (2, 1):
+        ix.set_search_workspace(hash_bits=8, queue_cap=64, onchip_tiers=tiers)
+        ids, dists, counts = ix.search(q, k, 0.1, edge_size=0, seeds=seeds)
+        assert ix.last_overflows > 0
+        check(ids, dists, counts, rids, rdists, rcounts, what="%s overflow, %d on-chip tiers" % (kind, tiers))
     ix.close()
 
 

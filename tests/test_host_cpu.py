@@ -1,0 +1,174 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports what include/ngtgpu.h declares,
+index files round-trip and interoperate with the reference's own files, graph reconstruction follows
+GraphReconstructor::reconstructGraph. No device compute happens here."""
+import ctypes as C
+import os
+import re
+import shutil
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+REF_NGT = os.path.join(ROOT, "oracle", "_ref", "ngt")
+
+
+def test_c_abi_exports_every_declared_symbol():
+    from ngt_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "ngtgpu.h")).read()
+    declared = set(re.findall(r"\b(ngtgpu_[a-z0-9_]+)\s*\(", header))
+    declared -= {"ngtgpu_index", "ngtgpu_search_params"}
+    assert len(declared) >= 20
+    lib = C.CDLL(_lib.SO_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), "libngtgpu.so does not export %s" % name
+    # the ctypes table covers the hot-path entry points
+    for name in ("ngtgpu_search", "ngtgpu_search_device", "ngtgpu_linear_search", "ngtgpu_linear_search_device",
+                 "ngtgpu_index_create", "ngtgpu_index_set_objects", "ngtgpu_index_set_graph"):
+        assert name in _lib.SYMBOLS and name in declared
+
+
+def test_no_device_is_an_error_not_a_fallback():
+    """Without a CUDA device every entry point fails loudly (this container has no GPU)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from ngt_b200 import _lib, engine
+    with pytest.raises(_lib.NgtGpuError) as e:
+        engine.GpuIndex(_lib.OBJECT_FLOAT, _lib.DISTANCE_L2, 16)
+    assert e.value.code == _lib.ERR_NO_DEVICE
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "ngt_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "pyoracle" not in src and "ngt_oracle" not in src and "libngt_ref" not in src, f
+
+
+def _loop_reconstruct(ids, dists, o, i):
+    """GraphReconstructor.h:425-561 as plain loops."""
+    n, k = ids.shape
+    lists = [[] for _ in range(n + 1)]
+    for a in range(1, n + 1):
+        lists[a] = [(float(dists[a - 1, r]), int(ids[a - 1, r])) for r in range(min(o, k))]
+    for a in range(1, n + 1):
+        for r in range(min(i, k)):
+            lists[int(ids[a - 1, r])].append((float(dists[a - 1, r]), a))
+    out = []
+    for a in range(1, n + 1):
+        s = sorted(lists[a])
+        dedup, prev = [], 0
+        for d, t in s:
+            if t == prev:
+                continue
+            prev = t
+            dedup.append((d, t))
+        out.append(dedup)
+    return out
+
+
+def test_reconstruct_graph_matches_reference_semantics():
+    import torch
+    from ngt_b200 import build
+    rng = np.random.default_rng(0)
+    n, k = 300, 12
+    x = rng.integers(0, 50, (n, 8)).astype(np.float32)
+    d = np.sqrt(((x[:, None, :] - x[None, :, :]) ** 2).sum(-1)).astype(np.float32)
+    np.fill_diagonal(d, np.inf)
+    order = np.lexsort((np.broadcast_to(np.arange(n), (n, n)), d), axis=1)[:, :k]
+    ids = (order + 1).astype(np.int32)
+    dist = np.take_along_axis(d, order, 1)
+    for o, i in ((4, 12), (12, 12), (3, 5)):
+        rp, col, dd = build.reconstruct_graph(torch.from_numpy(ids), torch.from_numpy(dist),
+                                              torch.full((n,), k, dtype=torch.int32), o, i)
+        ref = _loop_reconstruct(ids, dist, o, i)
+        rp, col, dd = rp.numpy(), col.numpy(), dd.numpy()
+        assert rp[0] == 0 and rp[1] == 0
+        for a in range(1, n + 1):
+            got = list(zip(dd[rp[a]:rp[a + 1]].tolist(), col[rp[a]:rp[a + 1]].tolist()))
+            assert got == ref[a - 1], (o, i, a)
+
+
+def test_index_files_round_trip_and_interoperate_with_the_reference(sift5k):
+    from ngt_b200 import index_io
+    tmp = tempfile.mkdtemp(prefix="ngt-io-")
+    try:
+        # (1) what we write, we read back
+        n, dim = 200, 128
+        rows = sift5k["data"][:n].astype(np.float32)
+        rp = sift5k["row_ptr"].astype(np.uint64)
+        # sub-graph over the first 200 ids
+        lists = []
+        for a in range(1, n + 1):
+            nb = sift5k["col"][int(rp[a]):int(rp[a + 1])]
+            nb = nb[nb <= n]
+            dd = np.linalg.norm(rows[nb - 1] - rows[a - 1], axis=1).astype(np.float32)
+            o = np.lexsort((nb, dd))
+            lists.append((nb[o], dd[o]))
+        row_ptr = np.zeros(n + 2, np.uint64)
+        row_ptr[2:] = np.cumsum([len(l[0]) for l in lists])
+        col = np.concatenate([l[0] for l in lists]).astype(np.uint32)
+        dist = np.concatenate([l[1] for l in lists]).astype(np.float32)
+        mine = os.path.join(tmp, "mine")
+        os.makedirs(mine)
+        prop = dict(index_io.DEFAULT_PRF)
+        prop.update({"Dimension": str(dim), "ObjectType": "Float-4", "DistanceType": "L2"})
+        index_io.write_prf(mine, prop)
+        present = np.ones(n + 1, np.uint8)
+        present[0] = 0
+        present[17] = 0           # a removed slot
+        index_io.write_objects(mine, rows, present)
+        index_io.write_graph(mine, row_ptr, col, dist, present)
+        p2 = index_io.read_prf(mine)
+        assert p2 == prop
+        r2, pres2 = index_io.read_objects(mine, p2)
+        assert (pres2 == present).all()
+        keep = present[1:] == 1
+        assert (r2[keep] == rows[keep]).all() and (r2[~keep] == 0).all()
+        rp2, col2, dist2, gp2 = index_io.read_graph(mine)
+        assert (gp2 == present).all()
+        deg = np.diff(row_ptr.astype(np.int64))[1:]
+        deg2 = np.diff(rp2.astype(np.int64))[1:]
+        assert (deg2[keep] == deg[keep]).all() and (deg2[~keep] == 0).all()
+        # (2) the reference's own files parse, and ours open in the reference
+        if not os.path.exists(REF_NGT):
+            pytest.skip("oracle/_ref/ngt not built here")
+        tsv = os.path.join(tmp, "d.tsv")
+        np.savetxt(tsv, rows, fmt="%g", delimiter="\t")
+        theirs = os.path.join(tmp, "theirs")
+        subprocess.check_call([REF_NGT, "create", "-d", str(dim), "-o", "f", "-D", "2", theirs, tsv],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        tp = index_io.read_prf(theirs)
+        assert tp["ObjectType"] == "Float-4" and tp["DistanceType"] == "L2" and int(tp["Dimension"]) == dim
+        tr, tpres = index_io.read_objects(theirs, tp)
+        assert (tr == rows).all() and tpres[0] == 0 and (tpres[1:] == 1).all()
+        trp, tcol, tdist, _ = index_io.read_graph(theirs)
+        assert trp[-1] == tcol.size and tcol.size > n and tcol.min() >= 1 and tcol.max() <= n
+        for a in (1, 57, n):       # lists ascending by (distance, id), distances are the true ones
+            nb, dd = tcol[int(trp[a]):int(trp[a + 1])], tdist[int(trp[a]):int(trp[a + 1])]
+            assert (np.diff(dd) >= 0).all()
+            assert np.allclose(dd, np.linalg.norm(rows[nb - 1] - rows[a - 1], axis=1), rtol=1e-6)
+        # our files (IndexType Graph, full present set) opened by the reference CLI: exhaustive search agrees
+        full = os.path.join(tmp, "full")
+        os.makedirs(full)
+        index_io.write_prf(full, prop)
+        index_io.write_objects(full, rows)
+        index_io.write_graph(full, row_ptr, col, dist)
+        q = os.path.join(tmp, "q.tsv")
+        np.savetxt(q, sift5k["queries"][:1].astype(np.float32), fmt="%g", delimiter="\t")
+        out = subprocess.run([REF_NGT, "search", "-i", "s", "-n", "5", full, q], capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+        got = [int(m.group(2)) for m in re.finditer(r"^(\d+)\t(\d+)\t", out.stdout, re.M)]
+        d = np.linalg.norm(rows - sift5k["queries"][0].astype(np.float32), axis=1)
+        assert got == (np.lexsort((np.arange(n), d))[:5] + 1).tolist()
+        out = subprocess.run([REF_NGT, "search", "-i", "g", "-n", "5", "-e", "0.3", full, q], capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+        got = [int(m.group(2)) for m in re.finditer(r"^(\d+)\t(\d+)\t", out.stdout, re.M)]
+        assert len(got) == 5
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
