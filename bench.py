@@ -54,7 +54,7 @@ def parse_args():
     ap.add_argument("--outgoing", type=int, default=10)
     ap.add_argument("--incoming", type=int, default=64)
     ap.add_argument("--edge-size", type=int, default=64, help="edge_size of the search (0 = all edges)")
-    ap.add_argument("--pivots", type=int, default=4096)
+    ap.add_argument("--pivots", type=int, default=1024)
     ap.add_argument("--seeds", type=int, default=10)
     ap.add_argument("--recall", type=float, default=0.95)
     ap.add_argument("--gt-queries", type=int, default=2000)

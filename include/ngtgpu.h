@@ -146,6 +146,14 @@ int ngtgpu_index_set_onchip_tiers(ngtgpu_index *index, int tiers);
 int ngtgpu_index_set_stage_bytes(ngtgpu_index *index, uint32_t bytes);
 uint64_t ngtgpu_index_last_overflows(const ngtgpu_index *index);
 
+/* ---- multi-GPU: per-shard result lists <-> 64-bit keys (ordered distance bits << 32 | global id), and the k-way
+ *      merge of all-gathered key lists by (distance, id) (lib/NGT/Common.h:1946-1952). Device buffers. ---------- */
+int ngtgpu_pack_keys(const uint32_t *ids, const float *dists, const uint32_t *counts, uint32_t nq, uint32_t k,
+                     uint32_t id_offset, uint64_t *keys, void *stream);
+/* keys: [n_lists][nq][k] (n_lists <= 32), each list ascending, padded with 0xffffffffffffffff. */
+int ngtgpu_merge_keys(const uint64_t *keys, uint32_t n_lists, uint32_t nq, uint32_t k, uint32_t *ids, float *dists,
+                      uint32_t *counts, void *stream);
+
 /* Number of kernels this library launched since the index was created (bench.py's gpu_launches). */
 uint64_t ngtgpu_index_launch_count(const ngtgpu_index *index);
 /* Device timing of the traversal kernel with CUDA events on the launching stream (bench.py's roofline leg):

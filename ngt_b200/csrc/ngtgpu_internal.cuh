@@ -117,6 +117,7 @@ struct ScanParams {
   float radius = -1.0f;
   int exclude_self = 0;
   uint32_t self_base = 0;
+  int approx = 0;                       // float kinds: skip the exact re-evaluation (ranking pivots for seeds)
   uint32_t *d_ids = nullptr;
   float *d_dists = nullptr;
   uint32_t *d_counts = nullptr;

@@ -44,6 +44,7 @@ struct ScanArgs {
   uint32_t nsplit;
   uint64_t tiles_per_split;
   uint64_t *partial;        // nq x nsplit x k keys
+  int approx;               // float kinds: rank by the tile's own fp32 sums (seed selection), no exact re-evaluation
 };
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc, uint32_t src_bytes) {
@@ -129,7 +130,6 @@ template <int ACC, int G>
 __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_tile_kernel(const ScanArgs a) {
   constexpr bool IS_INT = ACC == ACC_U8_L2 || ACC == ACC_U8_HAM;
   constexpr int RG = IS_INT ? 1 : G;  // lanes per re-evaluated candidate
-  constexpr int RR = 32 / RG;
   extern __shared__ __align__(16) uint8_t smem_raw[];
   uint4 *stages = reinterpret_cast<uint4 *>(smem_raw);                                  // 2 x (Q | R) x 64 x LD
   uint64_t *buf = reinterpret_cast<uint64_t *>(smem_raw + 2 * 2 * SCAN_TQ * SCAN_LD * 16);  // TQ x TR
@@ -259,6 +259,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_tile_kernel(const ScanAr
               if (ok) {
                 uint32_t slot = atomicAdd(&cnt[m], 1u);
                 uint32_t raw = IS_INT ? acc[i][j].u : __float_as_uint(acc[i][j].f0);
+                if (ACC == ACC_F_COS && a.approx) raw = __float_as_uint(acc[i][j].f0 * rsqrtf(qn * acc[i][j].f1));
                 buf[m * SCAN_TR + slot] = ((uint64_t)raw << 32) | (uint32_t)nn;
               }
             }
@@ -270,11 +271,13 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_tile_kernel(const ScanAr
       for (int m = warp; m < SCAN_TQ; m += SCAN_THREADS / 32) {
         const uint32_t c = cnt[m];
         if (c == 0) continue;
-        const int gl = lane % RG, grp = lane / RG;
+        const int rg = (IS_INT || a.approx) ? 1 : RG;   // lanes per candidate
+        const int rr = 32 / rg;
+        const int gl = lane % rg, grp = lane / rg;
         uint64_t *mytop = topk + (size_t)m * a.k;
         uint32_t n = tn[m];
         const uint8_t *qptr = a.queries + (size_t)(q0 + m) * a.row_bytes;
-        for (uint32_t i0 = 0; i0 < c; i0 += RR) {
+        for (uint32_t i0 = 0; i0 < c; i0 += rr) {
           const uint32_t i = i0 + grp;
           const bool act = i < c;
           const uint64_t entry = act ? buf[m * SCAN_TR + i] : 0ull;
@@ -286,6 +289,12 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_tile_kernel(const ScanAr
             Sums s = zero_sums();
             s.u = (uint32_t)(entry >> 32);
             d = finish_distance<ACC>(a.dtype, s, 0.f);
+          } else if (a.approx) {
+            // seed selection: the tile's fp32 value is good enough to rank pivots
+            Sums s = zero_sums();
+            s.f0 = __uint_as_float((uint32_t)(entry >> 32));
+            s.f1 = 1.0f;   // F_COS: f0 already holds the cosine
+            d = finish_distance<ACC>(a.dtype, s, 1.0f);
           } else {
             d = group_distance_gmem<ACC, RG>(qptr, act ? a.rows + row * a.row_bytes : qptr, a.chunks, gl, a.dtype);
           }
@@ -322,12 +331,12 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_tile_kernel(const ScanAr
 
 // one warp per query: merge nsplit ascending lists (<= 32 of them) into the final top-k
 __global__ void scan_merge_kernel(const uint64_t *__restrict__ partial, uint32_t nq, uint32_t nsplit, uint32_t k,
-                                  uint32_t *__restrict__ ids, float *__restrict__ dists,
-                                  uint32_t *__restrict__ counts) {
+                                  uint64_t query_stride, uint64_t list_stride, uint32_t *__restrict__ ids,
+                                  float *__restrict__ dists, uint32_t *__restrict__ counts) {
   const int lane = threadIdx.x & 31;
   const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (q >= nq) return;
-  const uint64_t *mine = partial + ((size_t)q * nsplit + (lane < (int)nsplit ? lane : 0)) * k;
+  const uint64_t *mine = partial + (size_t)q * query_stride + (size_t)(lane < (int)nsplit ? lane : 0) * list_stride;
   uint32_t pos = 0;
   uint64_t head = lane < (int)nsplit ? mine[0] : KEY_NONE;
   uint32_t n = 0;
@@ -402,6 +411,7 @@ int ngtgpu_scan_topk(ngtgpu_index *ix, const ScanParams &p, cudaStream_t stream)
   a.exclude_self = p.exclude_self;
   a.self_base = p.self_base;
   a.dtype = ix->distance_type;
+  a.approx = p.approx;
   a.qtiles = (p.nq + SCAN_TQ - 1) / SCAN_TQ;
   const uint64_t total_tiles = (p.n_rows + SCAN_TR - 1) / SCAN_TR;
   uint64_t want = ((uint64_t)2 * ix->sm_count + a.qtiles - 1) / a.qtiles;
@@ -428,7 +438,8 @@ int ngtgpu_scan_topk(ngtgpu_index *ix, const ScanParams &p, cudaStream_t stream)
   if (e != cudaSuccess) NGTGPU_FAIL(NGTGPU_ERR_CUDA, std::string("scan kernel launch: ") + cudaGetErrorString(e));
   ix->launches++;
   const unsigned mblocks = (p.nq + 7) / 8;
-  scan_merge_kernel<<<mblocks, 256, 0, stream>>>(partial, p.nq, a.nsplit, p.k, p.d_ids, p.d_dists, p.d_counts);
+  scan_merge_kernel<<<mblocks, 256, 0, stream>>>(partial, p.nq, a.nsplit, p.k, (uint64_t)a.nsplit * p.k, (uint64_t)p.k, p.d_ids,
+                                                  p.d_dists, p.d_counts);
   ix->launches++;
   CUDA_TRY(cudaGetLastError());
   return NGTGPU_OK;
@@ -517,4 +528,43 @@ extern "C" int ngtgpu_index_knn_graph(ngtgpu_index *ix, uint32_t k, uint32_t fir
   p.d_dists = d_dists;
   p.d_counts = d_counts;
   return ngtgpu_scan_topk(ix, p, (cudaStream_t)stream);
+}
+
+// ---- merging per-shard result lists (multi-GPU) ----------------------------------
+// Each GPU searches its own shard of the rows; the per-shard top-k lists are exchanged with one all-gather
+// and merged per query by (distance, id) -- ObjectDistance's order (lib/NGT/Common.h:1946-1952) -- exactly as
+// one priority queue over the union would keep them. Lists travel as 64-bit keys (ordered distance bits in
+// the high word, GLOBAL id in the low word) so the exchange is one flat buffer.
+__global__ void pack_keys_kernel(const uint32_t *__restrict__ ids, const float *__restrict__ dists,
+                                 const uint32_t *__restrict__ counts, uint32_t nq, uint32_t k, uint32_t id_offset,
+                                 uint64_t *__restrict__ keys) {
+  const uint64_t total = (uint64_t)nq * k;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t q = (uint32_t)(i / k), r = (uint32_t)(i % k);
+    keys[i] = r < counts[q] ? make_key(dists[i], ids[i] + id_offset) : KEY_NONE;
+  }
+}
+
+extern "C" int ngtgpu_pack_keys(const uint32_t *d_ids, const float *d_dists, const uint32_t *d_counts, uint32_t nq,
+                                uint32_t k, uint32_t id_offset, uint64_t *d_keys, void *stream) {
+  if (nq == 0 || k == 0) return NGTGPU_OK;
+  if (!d_ids || !d_dists || !d_counts || !d_keys) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "ngtgpu_pack_keys: null buffer");
+  uint64_t total = (uint64_t)nq * k;
+  unsigned blocks = (unsigned)((total + 255) / 256 > 4096 ? 4096 : (total + 255) / 256);
+  pack_keys_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_ids, d_dists, d_counts, nq, k, id_offset, d_keys);
+  CUDA_TRY(cudaGetLastError());
+  return NGTGPU_OK;
+}
+
+// keys: [n_lists][nq][k] ascending lists (KEY_NONE padded), as an all-gather of pack_keys outputs lays them out.
+extern "C" int ngtgpu_merge_keys(const uint64_t *d_keys, uint32_t n_lists, uint32_t nq, uint32_t k, uint32_t *d_ids,
+                                 float *d_dists, uint32_t *d_counts, void *stream) {
+  if (nq == 0 || k == 0) return NGTGPU_OK;
+  if (!d_keys || !d_ids || !d_dists || !d_counts) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "ngtgpu_merge_keys: null buffer");
+  if (n_lists == 0 || n_lists > 32) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "ngtgpu_merge_keys: 1..32 lists");
+  const unsigned mblocks = (nq + 7) / 8;
+  scan_merge_kernel<<<mblocks, 256, 0, (cudaStream_t)stream>>>(d_keys, nq, n_lists, k, (uint64_t)k, (uint64_t)nq * k, d_ids,
+                                                                d_dists, d_counts);
+  CUDA_TRY(cudaGetLastError());
+  return NGTGPU_OK;
 }

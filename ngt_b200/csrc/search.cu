@@ -196,6 +196,7 @@ static int select_seeds(ngtgpu_index *ix, const uint8_t *d_queries, uint32_t nq,
   p.d_id_map = ix->d_pivot_ids;
   p.k = n_seeds;
   p.radius = -1.0f;
+  p.approx = 1;
   p.d_ids = seeds;
   p.d_dists = sd + 64;
   p.d_counts = reinterpret_cast<uint32_t *>(sd + 64 + (size_t)nq * n_seeds);

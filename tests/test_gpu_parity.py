@@ -295,3 +295,41 @@ def test_device_seed_table_recall(eng, port):
     assert (tids.cpu().numpy().astype(np.uint32) == ids).all()
     assert (tdists.cpu().numpy().view(np.uint32) == dists.view(np.uint32)).all()
     ix.close()
+
+
+def test_pack_and_merge_kernels_match_host(eng):
+    """ngtgpu_pack_keys / ngtgpu_merge_keys (the multi-GPU exchange format and merge) against numpy."""
+    import torch
+    from ngt_b200 import sharded
+    rng = np.random.default_rng(9)
+    world, nq, k = 3, 70, 10
+    lists = []
+    for r in range(world):
+        d = np.sort(rng.integers(0, 60, (nq, k)).astype(np.float32), axis=1)     # many cross-shard ties
+        ids = rng.integers(1, 1000, (nq, k)).astype(np.uint32)
+        counts = rng.integers(0, k + 1, nq).astype(np.uint32)
+        order = np.lexsort((ids, d), axis=1)
+        d, ids = np.take_along_axis(d, order, 1), np.take_along_axis(ids, order, 1)
+        lists.append((ids, d, counts))
+    dev = torch.device("cuda", 0)
+    gathered = torch.empty((world, nq, k), dtype=torch.int64, device=dev)
+    host_keys = []
+    for r, (ids, d, counts) in enumerate(lists):
+        s = sharded.ShardedSearcher(None, r, world, 1000)
+        lib = sharded._fn()
+        ti, td, tc = (torch.from_numpy(x.view(np.int32) if x.dtype == np.uint32 else x).to(dev) for x in (ids, d, counts))
+        from ngt_b200 import _lib
+        _lib.check(lib.ngtgpu_pack_keys(ti.data_ptr(), td.data_ptr(), tc.data_ptr(), nq, k, s.id_offset,
+                                        gathered[r].data_ptr(), torch.cuda.current_stream().cuda_stream))
+        host_keys.append(sharded.pack_keys_host(ids, d, counts, r * 1000))
+    torch.cuda.synchronize()
+    assert (gathered.cpu().numpy().view(np.uint64) == np.stack(host_keys)).all()
+    oi = torch.empty((nq, k), dtype=torch.int32, device=dev)
+    od = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    oc = torch.empty((nq,), dtype=torch.int32, device=dev)
+    _lib.check(lib.ngtgpu_merge_keys(gathered.data_ptr(), world, nq, k, oi.data_ptr(), od.data_ptr(), oc.data_ptr(),
+                                     torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    hi, hd, hc = sharded.merge_keys_host(np.stack(host_keys), k)
+    assert (oc.cpu().numpy().astype(np.uint32) == hc).all()
+    assert_bit_exact(oi.cpu().numpy().astype(np.uint32), od.cpu().numpy(), hc, hi, hd, hc, what="merge kernel")
