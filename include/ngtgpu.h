@@ -146,6 +146,12 @@ int ngtgpu_index_set_onchip_tiers(ngtgpu_index *index, int tiers);
 int ngtgpu_index_set_stage_bytes(ngtgpu_index *index, uint32_t bytes);
 uint64_t ngtgpu_index_last_overflows(const ngtgpu_index *index);
 
+/* Exhaustive float batches (>= 1024 queries against >= 32768 objects, size <= 100, dimension <= 384) are filtered
+ * on the tensor cores (tcgen05, bf16-split operands) and re-evaluated exactly; results are identical to the CUDA-core
+ * scan. This switch turns the tensor-core filter off (parity tests); the counter says how many batches used it. */
+int ngtgpu_index_set_tensor_core(ngtgpu_index *index, int enabled);
+uint64_t ngtgpu_index_tensor_core_batches(const ngtgpu_index *index);
+
 /* ---- multi-GPU: per-shard result lists <-> 64-bit keys (ordered distance bits << 32 | global id), and the k-way
  *      merge of all-gathered key lists by (distance, id) (lib/NGT/Common.h:1946-1952). Device buffers. ---------- */
 int ngtgpu_pack_keys(const uint32_t *ids, const float *dists, const uint32_t *counts, uint32_t nq, uint32_t k,

@@ -127,6 +127,13 @@ static void free_graph(ngtgpu_index *ix) {
   ix->d_col = nullptr;
   ix->nnz = 0;
 }
+static void free_tc(ngtgpu_index *ix) {
+  if (ix->d_tc_tiles) cudaFree(ix->d_tc_tiles);
+  if (ix->d_tc_norms) cudaFree(ix->d_tc_norms);
+  ix->d_tc_tiles = nullptr;
+  ix->d_tc_norms = nullptr;
+  ix->tc_rows_valid = false;
+}
 static void free_pivots(ngtgpu_index *ix) {
   if (ix->d_pivot_rows) cudaFree(ix->d_pivot_rows);
   if (ix->d_pivot_ids) cudaFree(ix->d_pivot_ids);
@@ -143,6 +150,7 @@ extern "C" int ngtgpu_index_destroy(ngtgpu_index *ix) {
   if (ix->d_valid) cudaFree(ix->d_valid);
   free_graph(ix);
   free_pivots(ix);
+  free_tc(ix);
   for (int i = 0; i < SCR_COUNT; i++)
     if (ix->d_scratch[i]) cudaFree(ix->d_scratch[i]);
   if (ix->stream) cudaStreamDestroy(ix->stream);
@@ -272,6 +280,7 @@ extern "C" int ngtgpu_index_set_objects(ngtgpu_index *ix, const void *objects, u
   ix->d_valid = nullptr;
   free_graph(ix);
   free_pivots(ix);
+  free_tc(ix);
   ix->n = 0;
   size_t bytes = (size_t)(n + 1) * ix->row_bytes;
   CUDA_TRY(cudaMalloc(&ix->d_objects, bytes));
@@ -335,6 +344,7 @@ extern "C" int ngtgpu_index_set_removed(ngtgpu_index *ix, const uint32_t *ids, u
   CUDA_TRY(cudaStreamSynchronize(ix->stream));
   if (ix->d_valid) CUDA_TRY(cudaFree(ix->d_valid));
   ix->d_valid = nullptr;
+  free_tc(ix);   // the packed norms carry the empty-slot marks
   if (count == 0) return NGTGPU_OK;
   std::vector<uint8_t> valid(ix->n + 1, 1);
   valid[0] = 0;
@@ -408,6 +418,13 @@ extern "C" int ngtgpu_index_set_search_workspace(ngtgpu_index *ix, uint32_t hash
   ix->queue_cap = queue_cap;
   return NGTGPU_OK;
 }
+
+extern "C" int ngtgpu_index_set_tensor_core(ngtgpu_index *ix, int enabled) {
+  if (!ix) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "null index handle");
+  ix->tc_enabled = enabled != 0;
+  return NGTGPU_OK;
+}
+extern "C" uint64_t ngtgpu_index_tensor_core_batches(const ngtgpu_index *ix) { return ix ? ix->tc_batches : 0; }
 
 extern "C" int ngtgpu_index_set_stage_bytes(ngtgpu_index *ix, uint32_t bytes) {
   if (!ix) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "null index handle");

@@ -1,0 +1,687 @@
+// knn_tc.cu -- exhaustive kNN for float objects on the 5th-generation tensor cores (tcgen05 + TMEM).
+//
+// The brute-force pass behind linearSearch batches, kNN-graph construction and ground truth
+// (lib/NGT/ObjectSpaceRepository.h:466-502, Index.h:839-856, Index.cpp:670-719) is a dense contraction:
+//     L2      ||q - x||^2 = ||q||^2 + ||x||^2 - 2 q.x
+//     cosine  q.x / (||q|| ||x||),  normalised kinds  q.x
+// so q.x for a 128-query x 128-row tile is one tcgen05.mma chain with the accumulator in tensor memory.
+// fp32 operands are split into bf16 parts, x = hi + lo, and the three products that matter are obtained from
+// ONE bf16 GEMM over a concatenated K axis:  A' = [q_hi | q_hi | q_lo],  B' = [x_hi | x_lo | x_hi]
+// (q_lo.x_lo, relative 2^-16, is dropped). When every value is exactly a bf16 number (SIFT-like integer
+// data) a single segment is used and the products are exact.
+//
+// The tensor cores only FILTER. Each epilogue thread owns one query (one TMEM lane): it keeps the k
+// smallest approximate scores it has seen in a private max-heap (shared memory, conflict-free) and appends
+// every row whose score is within an error margin of the current k-th score to the query's candidate list.
+// A second kernel re-evaluates the candidates with the engine's one exact summation order
+// (ngtgpu_internal.cuh) and selects the top k by (distance, id), so results are bit-identical to the
+// CUDA-core scan (scan.cu) and to the reference where that is exact. A true k-nearest row cannot be dropped:
+// its approximate score is <= d_k(1+e), the running threshold is >= d_k(1-e), and the margin is > 2e.
+//
+// Kernel anatomy (192 threads, 1 CTA/SM): warps 0-3 epilogue (tcgen05.ld, 32 TMEM lanes each), warp 4
+// producer (cp.async.bulk of pre-swizzled 16 KB operand tiles, mbarrier complete_tx), warp 5 MMA issuer
+// (one elected thread; M=128, N=128, K=16 per instruction, SWIZZLE_128B K-major descriptors). The query
+// operand stays resident in shared memory, row tiles stream through a 4-stage ring, two 128-column
+// accumulators alternate in TMEM so the epilogue of tile t overlaps the MMAs of tile t+1.
+#include <cfloat>
+#include <cstring>
+#include <cuda_bf16.h>
+
+#include "ngtgpu_internal.cuh"
+
+#define TC_TILE 128            // queries per CTA tile == rows per streamed tile
+#define TC_KCHUNK 64           // bf16 elements per swizzle row (128 bytes)
+#define TC_TILE_BYTES (TC_TILE * TC_KCHUNK * 2)   // 16 KB: one operand tile of one k-chunk
+#define TC_STAGES 4
+#define TC_MAX_KCHUNKS 6       // resident query operand <= 96 KB
+#define TC_MAX_K 100           // heap of k floats per query in shared memory
+#define TC_THREADS 192
+#define TC_CAND_CAP 2048       // candidate ids per (query, split)
+
+struct TcPacked {
+  uint8_t *tiles = nullptr;    // [n_tiles][kchunks][16 KB], SWIZZLE_128B K-major images
+  float *norms = nullptr;      // [n_tiles * 128], +inf for padding / empty rows
+  uint64_t n_rows = 0;
+  uint64_t n_tiles = 0;
+  uint32_t kchunks = 0;
+  uint32_t nseg = 0;
+};
+
+// ---- operand preparation --------------------------------------------------------------------------------
+__global__ void tc_check_exact_kernel(const float *__restrict__ rows, uint64_t count, int *flag) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x) {
+    float x = rows[i];
+    if (__bfloat162float(__float2bfloat16_rn(x)) != x) {
+      *flag = 1;
+      return;
+    }
+  }
+}
+
+// One thread per (row, 16-byte unit of the packed K axis). side 0 = query operand [hi|hi|lo], 1 = row operand
+// [hi|lo|hi]. The unit is written where SWIZZLE_128B puts it: byte r*128 + ((u ^ (r & 7)) * 16) of the 16 KB tile.
+__global__ void tc_pack_kernel(const float *__restrict__ rows, uint64_t n_rows, uint32_t padded_dim, int side,
+                               uint32_t nseg, uint32_t kchunks, uint8_t *__restrict__ tiles) {
+  const uint64_t units_per_row = (uint64_t)kchunks * 8;
+  const uint64_t n_pad = (n_rows + TC_TILE - 1) / TC_TILE * TC_TILE;
+  const uint64_t total = n_pad * units_per_row;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t row = i / units_per_row;
+    const uint32_t U = (uint32_t)(i % units_per_row);
+    const uint32_t kappa = U * 8;
+    const uint32_t seg = kappa / padded_dim, d0 = kappa % padded_dim;
+    __nv_bfloat16 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) v[j] = __float2bfloat16_rn(0.f);
+    if (row < n_rows && seg < nseg) {
+      const float *src = rows + row * padded_dim + d0;
+      const bool want_lo = side == 0 ? seg == 2 : seg == 1;
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const float x = src[j];
+        const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+        v[j] = want_lo ? __float2bfloat16_rn(x - __bfloat162float(hi)) : hi;
+      }
+    }
+    const uint64_t tile = row / TC_TILE;
+    const uint32_t r = (uint32_t)(row % TC_TILE), c = U / 8, u = U % 8;
+    uint8_t *dst = tiles + (tile * kchunks + c) * (uint64_t)TC_TILE_BYTES + r * 128 + ((u ^ (r & 7)) * 16);
+    *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(v);
+  }
+}
+
+// squared norms (plain fp32: they only feed the filter); +inf marks padding and empty slots
+__global__ void tc_norms_kernel(const float *__restrict__ rows, uint64_t n_rows, uint32_t padded_dim, uint32_t first_id,
+                                const uint8_t *__restrict__ valid, float *__restrict__ norms) {
+  const int lane = threadIdx.x & 31;
+  const uint64_t n_pad = (n_rows + TC_TILE - 1) / TC_TILE * TC_TILE;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t r = warp; r < n_pad; r += nwarps) {
+    float s = 0.f;
+    bool ok = r < n_rows && !(valid && valid[first_id + r] == 0);
+    if (ok)
+      for (uint32_t i = lane; i < padded_dim; i += 32) {
+        float x = rows[r * padded_dim + i];
+        s = fmaf(x, x, s);
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) norms[r] = ok ? s : __int_as_float(0x7f800000);
+  }
+}
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tc_mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "TC_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra TC_DONE;\n"
+      "bra TC_WAIT;\n"
+      "TC_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tc_bulk_load(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// SWIZZLE_128B, K-major operand tile (rows of 128 bytes, 8-row groups 1024 bytes apart): cute::UMMA::SmemDescriptor
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fff);   // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major): 1
+  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset: 8 rows x 128 B
+  d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                        // layout type SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void tc_tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- the filter kernel ------------------------------------------------------------------------------------
+struct TcArgs {
+  const uint8_t *a_tiles;   // packed query operand  [q_tiles][kchunks][16 KB]
+  const uint8_t *b_tiles;   // packed row operand    [r_tiles][kchunks][16 KB]
+  const float *a_norms;     // [q_tiles * 128]
+  const float *b_norms;     // [r_tiles * 128]
+  uint32_t nq;
+  uint64_t n_rows;
+  uint32_t kchunks;
+  uint32_t k;
+  int mode;                 // 0 L2, 1 dot (normalised kinds), 2 cosine
+  float rel_margin;         // error bound of the bf16 product, relative to ||q||^2+||x||^2 (L2) or absolute (similarities)
+  int exclude_self;
+  uint32_t self_base;       // row index (0-based) of query 0 when queries are stored rows
+  uint32_t qtiles;
+  uint32_t nsplit;
+  uint64_t tiles_per_split;
+  uint32_t *cand;           // [nq][nsplit][TC_CAND_CAP] row indices (0-based)
+  uint32_t *cand_n;         // [nq][nsplit]; 0xffffffff = overflow
+};
+
+// A row passed the filter: append it to the query's candidate list and keep the max-heap of the k smallest
+// approximate scores. Kept out of line on purpose: the column loop of the epilogue must stay small enough for
+// the instruction cache (inlining 128 copies of this made the kernel instruction-fetch bound).
+// st: per-thread words in shared memory, stride 128: [0] heap size, [1] candidates, [2] overflow flag.
+__device__ __noinline__ float tc_push(float score, uint32_t row, float *H, uint32_t *st, uint32_t k, uint32_t *mycand,
+                                      uint32_t skip_row, float thr) {
+  if (row == skip_row) return thr;
+  uint32_t cn = st[128];
+  if (cn < TC_CAND_CAP) {
+    mycand[cn] = row;
+    st[128] = cn + 1;
+  } else {
+    st[256] = 1u;
+  }
+  uint32_t hn = st[0];
+  if (hn < k) {
+    uint32_t i = hn;
+    st[0] = hn + 1;
+    while (i > 0) {
+      uint32_t p = (i - 1) >> 1;
+      float pv = H[p * 128];
+      if (pv >= score) break;
+      H[i * 128] = pv;
+      i = p;
+    }
+    H[i * 128] = score;
+    return hn + 1 == k ? H[0] : thr;
+  }
+  if (score < H[0]) {
+    uint32_t i = 0;
+    for (;;) {
+      uint32_t c = 2 * i + 1;
+      if (c >= k) break;
+      float cv = H[c * 128];
+      if (c + 1 < k) {
+        float c2 = H[(c + 1) * 128];
+        if (c2 > cv) {
+          c++;
+          cv = c2;
+        }
+      }
+      if (cv <= score) break;
+      H[i * 128] = cv;
+      i = c;
+    }
+    H[i * 128] = score;
+    return H[0];
+  }
+  return thr;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_filter_kernel(const TcArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B tiles want 1024-byte alignment
+  __shared__ __align__(8) uint64_t bar_full[TC_STAGES], bar_empty[TC_STAGES], bar_a, bar_tfull[2], bar_tempty[2];
+  __shared__ uint32_t s_tmem;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t qtile = blockIdx.x % a.qtiles, split = blockIdx.x / a.qtiles;
+  const uint64_t total_tiles = (a.n_rows + TC_TILE - 1) / TC_TILE;
+  const uint64_t t_begin = (uint64_t)split * a.tiles_per_split;
+  uint64_t t_end = t_begin + a.tiles_per_split;
+  if (t_end > total_tiles) t_end = total_tiles;
+  const uint64_t ntiles = t_end > t_begin ? t_end - t_begin : 0;
+
+  uint8_t *sA = smem;                                              // kchunks x 16 KB (resident)
+  uint8_t *sB = smem + (size_t)a.kchunks * TC_TILE_BYTES;         // TC_STAGES x 16 KB ring
+  float *heap = reinterpret_cast<float *>(sB + (size_t)TC_STAGES * TC_TILE_BYTES);   // [k][128]
+  uint32_t *state = reinterpret_cast<uint32_t *>(heap + (size_t)a.k * 128);          // [3][128]
+
+  if (tid == 0) {
+    for (int i = 0; i < TC_STAGES; i++) {
+      tc_mbar_init(&bar_full[i], 1);
+      tc_mbar_init(&bar_empty[i], 1);
+    }
+    tc_mbar_init(&bar_a, 1);
+    for (int i = 0; i < 2; i++) {
+      tc_mbar_init(&bar_tfull[i], 1);
+      tc_mbar_init(&bar_tempty[i], 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    // 256 columns: two 128-column fp32 accumulators
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem;
+
+  if (warp == 4) {
+    // ===================== producer =====================
+    if (lane == 0 && ntiles) {
+      tc_mbar_expect_tx(&bar_a, a.kchunks * TC_TILE_BYTES);
+      for (uint32_t c = 0; c < a.kchunks; c++)
+        tc_bulk_load(sA + (size_t)c * TC_TILE_BYTES, a.a_tiles + ((size_t)qtile * a.kchunks + c) * TC_TILE_BYTES, TC_TILE_BYTES, &bar_a);
+      uint64_t it = 0;
+      for (uint64_t t = 0; t < ntiles; t++) {
+        for (uint32_t c = 0; c < a.kchunks; c++, it++) {
+          const uint32_t st = (uint32_t)(it % TC_STAGES);
+          tc_mbar_wait(&bar_empty[st], (uint32_t)((it / TC_STAGES) & 1) ^ 1u);
+          tc_mbar_expect_tx(&bar_full[st], TC_TILE_BYTES);
+          tc_bulk_load(sB + (size_t)st * TC_TILE_BYTES, a.b_tiles + ((size_t)(t_begin + t) * a.kchunks + c) * TC_TILE_BYTES,
+                       TC_TILE_BYTES, &bar_full[st]);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer =====================
+    if (lane == 0 && ntiles) {
+      // kind::f16, A = B = BF16, D = F32, K-major both, N = 128, M = 128 (cute::UMMA::InstrDescriptor)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+      const uint64_t descA0 = tc_smem_desc(smem_u32(sA)), descB0 = tc_smem_desc(smem_u32(sB));
+      tc_mbar_wait(&bar_a, 0);
+      tc_fence_after();
+      uint64_t it = 0;
+      for (uint64_t t = 0; t < ntiles; t++) {
+        const uint32_t acc = (uint32_t)(t & 1);
+        tc_mbar_wait(&bar_tempty[acc], (uint32_t)((t >> 1) & 1) ^ 1u);
+        tc_fence_after();
+        for (uint32_t c = 0; c < a.kchunks; c++, it++) {
+          const uint32_t st = (uint32_t)(it % TC_STAGES);
+          tc_mbar_wait(&bar_full[st], (uint32_t)((it / TC_STAGES) & 1));
+          tc_fence_after();
+#pragma unroll
+          for (uint32_t s = 0; s < TC_KCHUNK / 16; s++) {
+            const uint64_t da = descA0 + (uint64_t)((c * TC_TILE_BYTES + s * 32) >> 4);
+            const uint64_t db = descB0 + (uint64_t)((st * TC_TILE_BYTES + s * 32) >> 4);
+            tc_mma_bf16(tmem_base + acc * 128, da, db, idesc, (c | s) != 0 ? 1u : 0u);
+          }
+          tc_commit(&bar_empty[st]);   // frees the ring slot when these MMAs have read it
+        }
+        tc_commit(&bar_tfull[acc]);    // accumulator complete
+      }
+    }
+  } else {
+    // ===================== epilogue: one query per thread =====================
+    const uint32_t q = qtile * TC_TILE + tid;       // tid in [0,128)
+    const bool q_ok = q < a.nq;
+    const float qn = a.a_norms[(size_t)qtile * TC_TILE + tid];
+    float thr = q_ok ? __int_as_float(0x7f800000) : -__int_as_float(0x7f800000);   // k-th smallest approximate score so far
+    float *H = heap + tid;                           // H[i * 128]
+    uint32_t *st = state + tid;
+    st[0] = 0u;
+    st[128] = 0u;
+    st[256] = 0u;
+    uint32_t *mycand = a.cand + ((size_t)q * a.nsplit + split) * TC_CAND_CAP;
+    const uint32_t skip_row = a.exclude_self ? a.self_base + q : 0xffffffffu;
+    const float m2 = 2.0f * a.rel_margin;
+    for (uint64_t t = 0; t < ntiles; t++) {
+      const uint32_t acc = (uint32_t)(t & 1);
+      tc_mbar_wait(&bar_tfull[acc], (uint32_t)((t >> 1) & 1));
+      tc_fence_after();
+      const uint64_t row0 = (t_begin + t) * TC_TILE;
+      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * 128;
+      uint32_t v[2][32];
+      tc_tmem_ld32(taddr, v[0]);
+#pragma unroll
+      for (uint32_t cb = 0; cb < 4; cb++) {
+        tc_tmem_wait_ld();
+        if (cb + 1 < 4) tc_tmem_ld32(taddr + (cb + 1) * 32, v[(cb + 1) & 1]);   // next 32 columns in flight under this block
+        const float4 *rn4 = reinterpret_cast<const float4 *>(a.b_norms + row0 + cb * 32);
+        const uint32_t rbase = (uint32_t)(row0 + cb * 32);
+        // branch-free pass over the 32 columns against a snapshot of the threshold (it only shrinks, so the
+        // snapshot test admits a superset; tc_push re-checks), then the rare hits one by one
+        float sc[32];
+        uint32_t mask = 0;
+        const float thr0 = thr;
+#pragma unroll
+        for (int j4 = 0; j4 < 8; j4++) {
+          const float4 rnv = __ldg(rn4 + j4);
+          const float rns[4] = {rnv.x, rnv.y, rnv.z, rnv.w};
+#pragma unroll
+          for (int jj = 0; jj < 4; jj++) {
+            const int j = j4 * 4 + jj;
+            const float rn = rns[jj];   // +inf for padding and empty slots: never passes
+            const float dot = __uint_as_float(v[cb & 1][j]);
+            float score, lower;         // lower = score minus twice the error bound
+            if (MODE == 0) {
+              const float nn = qn + rn;
+              score = fmaf(-2.0f, dot, nn);
+              lower = fmaf(-m2, nn, score);
+            } else if (MODE == 1) {
+              score = rn < 3.0e38f ? -dot : __int_as_float(0x7fc00000);   // NaN never passes
+              lower = score - m2;
+            } else {
+              score = rn < 3.0e38f ? -dot * rsqrtf(qn * rn) : __int_as_float(0x7fc00000);
+              lower = score - m2;
+            }
+            sc[j] = score;
+            mask |= (lower <= thr0) ? (1u << j) : 0u;
+          }
+        }
+        if (mask) {
+          float loc[32];   // dynamically indexed below: lives in local memory, touched only on this rare path
+#pragma unroll
+          for (int j = 0; j < 32; j++) loc[j] = sc[j];
+          while (mask) {
+            const int j = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const float score = loc[j];
+            float lower;
+            if (MODE == 0) lower = fmaf(-m2, qn + __ldg(a.b_norms + rbase + j), score);
+            else lower = score - m2;
+            if (lower <= thr) thr = tc_push(score, rbase + j, H, st, a.k, mycand, skip_row, thr);
+          }
+        }
+      }
+      tc_fence_before();
+      tc_mbar_arrive(&bar_tempty[acc]);
+    }
+    if (q_ok) a.cand_n[(size_t)q * a.nsplit + split] = st[256] ? 0xffffffffu : st[128];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+  }
+}
+
+// ---- exact re-evaluation of the candidates + top-k (one warp per query) -----------------------------------
+__device__ __forceinline__ void tc_sorted_insert(uint64_t *arr, uint32_t &n_io, uint32_t k, uint64_t key, int lane) {
+  uint32_t n = n_io;
+  if (n == k) {
+    if (key >= arr[k - 1]) return;
+    n = k - 1;
+  }
+  uint32_t pos = 0;
+  for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+    bool less = i0 + lane < n && arr[i0 + lane] < key;
+    pos += __popc(__ballot_sync(0xffffffffu, less));
+  }
+  for (uint32_t hi = n; hi > pos;) {
+    uint32_t lo = hi - pos > 32 ? hi - 32 : pos;
+    uint32_t idx = lo + lane;
+    uint64_t v = idx < hi ? arr[idx] : 0;
+    __syncwarp();
+    if (idx < hi) arr[idx + 1] = v;
+    __syncwarp();
+    hi = lo;
+  }
+  if (lane == 0) arr[pos] = key;
+  __syncwarp();
+  n_io = n + 1;
+}
+
+struct RerankArgs {
+  const uint8_t *queries;   // prepared rows
+  const uint8_t *rows;
+  uint32_t row_bytes, chunks;
+  uint32_t nq, k, nsplit;
+  uint32_t first_row_id;
+  const uint32_t *id_map;
+  float radius;
+  int dtype;
+  const uint32_t *cand;
+  const uint32_t *cand_n;
+  uint32_t *ids;
+  float *dists;
+  uint32_t *counts;
+  uint32_t *overflowed;     // incremented once per query whose candidate list overflowed
+};
+
+template <int ACC, int G>
+__global__ void __launch_bounds__(256) knn_tc_rerank_kernel(const RerankArgs a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t q = blockIdx.x * 8 + warp;
+  if (q >= a.nq) return;
+  uint64_t *top = reinterpret_cast<uint64_t *>(smem) + (size_t)warp * a.k;
+  uint32_t n = 0;
+  constexpr int R = 32 / G;
+  const int gl = lane % G, grp = lane / G;
+  const uint8_t *qptr = a.queries + (size_t)q * a.row_bytes;
+  bool bad = false;
+  for (uint32_t s = 0; s < a.nsplit; s++) {
+    uint32_t c = a.cand_n[(size_t)q * a.nsplit + s];
+    if (c == 0xffffffffu) {
+      bad = true;
+      c = TC_CAND_CAP;
+    }
+    const uint32_t *list = a.cand + ((size_t)q * a.nsplit + s) * TC_CAND_CAP;
+    for (uint32_t i0 = 0; i0 < c; i0 += R) {
+      const uint32_t i = i0 + grp;
+      const bool act = i < c;
+      const uint32_t row = act ? list[i] : 0u;
+      const float d = group_distance_gmem<ACC, G>(qptr, act ? a.rows + (size_t)row * a.row_bytes : qptr, a.chunks, gl, a.dtype);
+      uint64_t key = KEY_NONE;
+      if (act && gl == 0 && (a.radius < 0.f || d <= a.radius))
+        key = make_key(d, a.id_map ? a.id_map[row] : a.first_row_id + row);
+      uint32_t mm = __ballot_sync(0xffffffffu, key != KEY_NONE);
+      while (mm) {
+        int src = __ffs(mm) - 1;
+        mm &= mm - 1;
+        uint64_t kk = shfl_u64(key, src);
+        tc_sorted_insert(top, n, a.k, kk, lane);
+      }
+    }
+  }
+  for (uint32_t i = lane; i < a.k; i += 32) {
+    const bool ok = i < n;
+    a.ids[(size_t)q * a.k + i] = ok ? key_id(top[i]) : 0u;
+    a.dists[(size_t)q * a.k + i] = ok ? key_dist(top[i]) : 0.f;
+  }
+  if (lane == 0) {
+    a.counts[q] = n;
+    if (bad) atomicAdd(a.overflowed, 1u);
+  }
+}
+
+template <int ACC>
+static cudaError_t launch_rerank(int group, const RerankArgs &a, cudaStream_t stream) {
+  const unsigned grid = (a.nq + 7) / 8;
+  const size_t smem = (size_t)8 * a.k * 8;
+  switch (group) {
+    case 4: knn_tc_rerank_kernel<ACC, 4><<<grid, 256, smem, stream>>>(a); break;
+    case 8: knn_tc_rerank_kernel<ACC, 8><<<grid, 256, smem, stream>>>(a); break;
+    case 16: knn_tc_rerank_kernel<ACC, 16><<<grid, 256, smem, stream>>>(a); break;
+    case 32: knn_tc_rerank_kernel<ACC, 32><<<grid, 256, smem, stream>>>(a); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+// ---- host side -------------------------------------------------------------------------------------------
+static int tc_pack(ngtgpu_index *ix, const float *d_rows, uint64_t n_rows, int side, uint32_t nseg, uint32_t first_id,
+                   const uint8_t *d_valid, uint8_t *tiles, float *norms, cudaStream_t stream) {
+  const uint32_t kchunks = (nseg * ix->padded_dim + TC_KCHUNK - 1) / TC_KCHUNK;
+  const uint64_t n_pad = (n_rows + TC_TILE - 1) / TC_TILE * TC_TILE;
+  uint64_t total = n_pad * kchunks * 8;
+  unsigned blocks = (unsigned)((total + 255) / 256 > (uint64_t)ix->sm_count * 64 ? (uint64_t)ix->sm_count * 64 : (total + 255) / 256);
+  tc_pack_kernel<<<blocks, 256, 0, stream>>>(d_rows, n_rows, ix->padded_dim, side, nseg, kchunks, tiles);
+  CUDA_TRY(cudaGetLastError());
+  tc_norms_kernel<<<ix->sm_count * 8, 256, 0, stream>>>(d_rows, n_rows, ix->padded_dim, first_id, d_valid, norms);
+  CUDA_TRY(cudaGetLastError());
+  ix->launches += 2;
+  return NGTGPU_OK;
+}
+
+static bool all_bf16_exact(ngtgpu_index *ix, const float *d_rows, uint64_t count, int *d_flag, cudaStream_t stream, int *rc) {
+  *rc = NGTGPU_OK;
+  int h = 0;
+  if (cudaMemsetAsync(d_flag, 0, sizeof(int), stream) != cudaSuccess) { *rc = NGTGPU_ERR_CUDA; return false; }
+  tc_check_exact_kernel<<<ix->sm_count * 8, 256, 0, stream>>>(d_rows, count, d_flag);
+  ix->launches++;
+  if (cudaMemcpyAsync(&h, d_flag, sizeof(int), cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+      cudaStreamSynchronize(stream) != cudaSuccess) {
+    ngtgpu_set_error("tensor-core kNN: exactness check failed");
+    *rc = NGTGPU_ERR_CUDA;
+    return false;
+  }
+  return h == 0;
+}
+
+// Returns NGTGPU_OK with *used = 1 when the tensor-core path produced the results, *used = 0 when the shape is
+// outside what it supports (the caller then runs the CUDA-core scan).
+int ngtgpu_scan_topk_tc(ngtgpu_index *ix, const ScanParams &p, cudaStream_t stream, int *used) {
+  *used = 0;
+  if (ix->object_type != NGTGPU_OBJECT_FLOAT) return NGTGPU_OK;
+  if (p.k == 0 || p.k > TC_MAX_K || p.approx) return NGTGPU_OK;
+  if (p.d_id_map != nullptr) return NGTGPU_OK;                          // pivot tables stay on the CUDA-core path
+  if (p.n_rows < 32768 || p.nq < 1024) return NGTGPU_OK;                // too little work to amortise packing
+  if (p.d_rows != ix->d_objects + ix->row_bytes || p.n_rows != ix->n) return NGTGPU_OK;   // only the whole repository is cached
+  if (!ix->tc_enabled || ix->padded_dim > TC_MAX_KCHUNKS * TC_KCHUNK) return NGTGPU_OK;
+
+  int *d_flag = nullptr;
+  NGTGPU_TRY(ngtgpu_scratch(ix, SCR_TC_MISC, 256, (void **)&d_flag));
+  int rc = NGTGPU_OK;
+  // ---- row operand: packed once per set_objects, kept with the index
+  if (!ix->tc_rows_valid) {
+    const float *rows = reinterpret_cast<const float *>(p.d_rows);
+    bool exact = all_bf16_exact(ix, rows, p.n_rows * ix->padded_dim, d_flag, stream, &rc);
+    if (rc != NGTGPU_OK) return rc;
+    uint32_t nseg = exact ? 1 : 3;
+    if (nseg * ix->padded_dim > TC_MAX_KCHUNKS * TC_KCHUNK) return NGTGPU_OK;   // resident query operand would not fit
+    const uint32_t kchunks = (nseg * ix->padded_dim + TC_KCHUNK - 1) / TC_KCHUNK;
+    const uint64_t n_tiles = (p.n_rows + TC_TILE - 1) / TC_TILE;
+    if (ix->d_tc_tiles) cudaFree(ix->d_tc_tiles);
+    if (ix->d_tc_norms) cudaFree(ix->d_tc_norms);
+    ix->d_tc_tiles = nullptr;
+    ix->d_tc_norms = nullptr;
+    CUDA_TRY(cudaMalloc(&ix->d_tc_tiles, n_tiles * kchunks * (size_t)TC_TILE_BYTES));
+    CUDA_TRY(cudaMalloc(&ix->d_tc_norms, n_tiles * TC_TILE * sizeof(float)));
+    NGTGPU_TRY(tc_pack(ix, rows, p.n_rows, 1, nseg, p.first_row_id, p.d_valid, ix->d_tc_tiles, ix->d_tc_norms, stream));
+    ix->tc_nseg = nseg;
+    ix->tc_kchunks = kchunks;
+    ix->tc_rows_valid = true;
+  }
+  uint32_t nseg = ix->tc_nseg;
+  // ---- query operand
+  const float *qrows = reinterpret_cast<const float *>(p.d_queries);
+  if (nseg == 1) {
+    bool qexact = all_bf16_exact(ix, qrows, (uint64_t)p.nq * ix->padded_dim, d_flag, stream, &rc);
+    if (rc != NGTGPU_OK) return rc;
+    if (!qexact) return NGTGPU_OK;   // rows are bf16-exact but the queries are not: leave it to the CUDA-core scan
+  }
+  const uint32_t kchunks = ix->tc_kchunks;
+  const uint32_t qtiles = (p.nq + TC_TILE - 1) / TC_TILE;
+  uint8_t *a_tiles = nullptr;
+  float *a_norms = nullptr;
+  NGTGPU_TRY(ngtgpu_scratch(ix, SCR_TC_QUERY, (size_t)qtiles * kchunks * TC_TILE_BYTES + (size_t)qtiles * TC_TILE * 4, (void **)&a_tiles));
+  a_norms = reinterpret_cast<float *>(a_tiles + (size_t)qtiles * kchunks * TC_TILE_BYTES);
+  NGTGPU_TRY(tc_pack(ix, qrows, p.nq, 0, nseg, 0, nullptr, a_tiles, a_norms, stream));
+
+  TcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.a_tiles = a_tiles;
+  a.b_tiles = ix->d_tc_tiles;
+  a.a_norms = a_norms;
+  a.b_norms = ix->d_tc_norms;
+  a.nq = p.nq;
+  a.n_rows = p.n_rows;
+  a.kchunks = kchunks;
+  a.k = p.k;
+  a.mode = ix->acc_kind == ACC_F_L2 ? 0 : ix->acc_kind == ACC_F_DOT ? 1 : 2;
+  a.rel_margin = nseg == 1 ? 2.0e-6f : 1.0e-4f;
+  a.exclude_self = p.exclude_self;
+  a.self_base = p.self_base - p.first_row_id;
+  a.qtiles = qtiles;
+  const uint64_t total_tiles = (p.n_rows + TC_TILE - 1) / TC_TILE;
+  uint64_t want = ((uint64_t)ix->sm_count + qtiles - 1) / qtiles;
+  if (want > 8) want = 8;
+  if (want > total_tiles) want = total_tiles;
+  if (want < 1) want = 1;
+  a.tiles_per_split = (total_tiles + want - 1) / want;
+  a.nsplit = (uint32_t)((total_tiles + a.tiles_per_split - 1) / a.tiles_per_split);
+  uint32_t *cand = nullptr;
+  NGTGPU_TRY(ngtgpu_scratch(ix, SCR_TC_CAND, ((size_t)p.nq * a.nsplit * (TC_CAND_CAP + 1) + 4) * 4, (void **)&cand));
+  a.cand = cand;
+  a.cand_n = cand + (size_t)p.nq * a.nsplit * TC_CAND_CAP;
+  uint32_t *d_over = a.cand_n + (size_t)p.nq * a.nsplit;
+  CUDA_TRY(cudaMemsetAsync(d_over, 0, 4, stream));
+
+  const size_t smem = (size_t)kchunks * TC_TILE_BYTES + (size_t)TC_STAGES * TC_TILE_BYTES + (size_t)(p.k + 3) * 128 * 4 + 1024;
+  if (a.mode == 0) {
+    CUDA_TRY(cudaFuncSetAttribute(knn_tc_filter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    knn_tc_filter_kernel<0><<<qtiles * a.nsplit, TC_THREADS, smem, stream>>>(a);
+  } else if (a.mode == 1) {
+    CUDA_TRY(cudaFuncSetAttribute(knn_tc_filter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    knn_tc_filter_kernel<1><<<qtiles * a.nsplit, TC_THREADS, smem, stream>>>(a);
+  } else {
+    CUDA_TRY(cudaFuncSetAttribute(knn_tc_filter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    knn_tc_filter_kernel<2><<<qtiles * a.nsplit, TC_THREADS, smem, stream>>>(a);
+  }
+  CUDA_TRY(cudaGetLastError());
+  ix->launches++;
+
+  RerankArgs r;
+  memset(&r, 0, sizeof(r));
+  r.queries = p.d_queries;
+  r.rows = p.d_rows;
+  r.row_bytes = ix->row_bytes;
+  r.chunks = ix->chunks;
+  r.nq = p.nq;
+  r.k = p.k;
+  r.nsplit = a.nsplit;
+  r.first_row_id = p.first_row_id;
+  r.id_map = nullptr;
+  r.radius = p.radius;
+  r.dtype = ix->distance_type;
+  r.cand = a.cand;
+  r.cand_n = a.cand_n;
+  r.ids = p.d_ids;
+  r.dists = p.d_dists;
+  r.counts = p.d_counts;
+  r.overflowed = d_over;
+  cudaError_t e;
+  switch (ix->acc_kind) {
+    case ACC_F_L2: e = launch_rerank<ACC_F_L2>((int)ix->group, r, stream); break;
+    case ACC_F_DOT: e = launch_rerank<ACC_F_DOT>((int)ix->group, r, stream); break;
+    default: e = launch_rerank<ACC_F_COS>((int)ix->group, r, stream); break;
+  }
+  if (e != cudaSuccess) NGTGPU_FAIL(NGTGPU_ERR_CUDA, std::string("tensor-core kNN rerank launch: ") + cudaGetErrorString(e));
+  ix->launches++;
+  uint32_t h_over = 0;
+  CUDA_TRY(cudaMemcpyAsync(&h_over, d_over, 4, cudaMemcpyDeviceToHost, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  if (h_over) return NGTGPU_OK;   // a candidate list overflowed: the caller re-runs the batch on the exact CUDA-core scan
+  *used = 1;
+  return NGTGPU_OK;
+}

@@ -48,7 +48,10 @@ enum ScratchSlot {
   SCR_SEARCH_BIG = 7,  // global-memory working sets of the overflow tier
   SCR_HASH0 = 8,       // visited-hash slabs of the first traversal tier (one per resident CTA)
   SCR_HASH1 = 9,       // ... of the second tier
-  SCR_COUNT = 10
+  SCR_TC_MISC = 10,    // tensor-core kNN: flags
+  SCR_TC_QUERY = 11,   // ... packed query operand + norms
+  SCR_TC_CAND = 12,    // ... candidate lists
+  SCR_COUNT = 13
 };
 
 struct ngtgpu_index {
@@ -90,6 +93,13 @@ struct ngtgpu_index {
   int sm_count = 0;
   uint64_t launches = 0;
   // optional device timing of the traversal kernel (bench.py's roofline leg)
+  // tensor-core kNN (knn_tc.cu): the row operand packed once per set_objects
+  bool tc_enabled = true;
+  bool tc_rows_valid = false;
+  uint8_t *d_tc_tiles = nullptr;
+  float *d_tc_norms = nullptr;
+  uint32_t tc_nseg = 0, tc_kchunks = 0;
+  uint64_t tc_batches = 0;             // batches answered by the tensor-core path
   uint32_t *d_prof = nullptr;          // development aid: per-phase cycle counters of the traversal kernel
   bool timing = false;
   std::vector<cudaEvent_t> timing_events;   // start, stop, start, stop ...
@@ -123,6 +133,7 @@ struct ScanParams {
   uint32_t *d_counts = nullptr;
 };
 int ngtgpu_scan_topk(ngtgpu_index *ix, const ScanParams &p, cudaStream_t stream);
+int ngtgpu_scan_topk_tc(ngtgpu_index *ix, const ScanParams &p, cudaStream_t stream, int *used);
 
 // graph traversal over prepared queries; everything in HBM.
 int ngtgpu_traverse(ngtgpu_index *ix, const uint8_t *d_queries, uint32_t nq, const ngtgpu_search_params *params,

@@ -390,6 +390,15 @@ int ngtgpu_scan_topk(ngtgpu_index *ix, const ScanParams &p, cudaStream_t stream)
     CUDA_TRY(cudaMemsetAsync(p.d_counts, 0, (size_t)p.nq * 4, stream));
     return NGTGPU_OK;
   }
+  {
+    // float batches against the whole repository go to the tensor cores when the shape allows (knn_tc.cu)
+    int used = 0;
+    NGTGPU_TRY(ngtgpu_scan_topk_tc(ix, p, stream, &used));
+    if (used) {
+      ix->tc_batches++;
+      return NGTGPU_OK;
+    }
+  }
   const size_t fixed = (size_t)2 * 2 * SCAN_TQ * SCAN_LD * 16 + (size_t)SCAN_TQ * SCAN_TR * 8 + 4 * SCAN_TQ * 4;
   const size_t smem = fixed + (size_t)SCAN_TQ * p.k * 8;
   if (smem > 220 * 1024)

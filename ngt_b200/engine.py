@@ -141,6 +141,13 @@ class GpuIndex:
         if stage_bytes is not None:
             _lib.check(self._lib.ngtgpu_index_set_stage_bytes(self._h, int(stage_bytes)))
 
+    def set_tensor_core(self, enabled=True):
+        _lib.check(self._lib.ngtgpu_index_set_tensor_core(self._h, int(bool(enabled))))
+
+    @property
+    def tensor_core_batches(self):
+        return int(self._lib.ngtgpu_index_tensor_core_batches(self._h))
+
     def build_seed_table(self, n_pivots=4096, rng_seed=1):
         _lib.check(self._lib.ngtgpu_index_build_seed_table(self._h, int(n_pivots), int(rng_seed)))
 

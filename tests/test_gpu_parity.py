@@ -333,3 +333,46 @@ def test_pack_and_merge_kernels_match_host(eng):
     hi, hd, hc = sharded.merge_keys_host(np.stack(host_keys), k)
     assert (oc.cpu().numpy().astype(np.uint32) == hc).all()
     assert_bit_exact(oi.cpu().numpy().astype(np.uint32), od.cpu().numpy(), hc, hi, hd, hc, what="merge kernel")
+
+
+@pytest.mark.parametrize("case", ["sift_l2_exact_bf16", "glove_l2_split", "glove_ncos_split", "glove_cos_split"])
+def test_tensor_core_knn_matches_cuda_core_scan(eng, case):
+    """knn_tc.cu (tcgen05 filter + exact re-evaluation) returns exactly what the CUDA-core scan returns: ids,
+    distance bits and counts, for batches, kNN-graph construction (self excluded) and with removed slots."""
+    from ngt_b200 import build, synth
+    n, nq = 40000, 1500
+    if case == "sift_l2_exact_bf16":
+        base, qs, dt = synth.make("sift", n, 1), synth.make("sift", nq, 2), po.L2
+    else:
+        base, qs = synth.make("glove", n, 1), synth.make("glove", nq, 2)
+        dt = {"glove_l2_split": po.L2, "glove_ncos_split": po.NORMALIZED_COSINE, "glove_cos_split": po.COSINE}[case]
+    ix = eng.GpuIndex(po.FLOAT, dt, base.shape[1])
+    ix.set_objects(base)
+    for k in (10, 64):
+        ix.set_tensor_core(True)
+        before = ix.tensor_core_batches
+        ids, dists, counts = ix.linear_search(qs, k)
+        assert ix.tensor_core_batches == before + 1, "the tensor-core path did not run"
+        ix.set_tensor_core(False)
+        rids, rdists, rcounts = ix.linear_search(qs, k)
+        assert ix.tensor_core_batches == before + 1
+        assert_bit_exact(ids, dists, counts, rids, rdists, rcounts, what="%s k=%d" % (case, k))
+    # kNN-graph construction: stored rows as queries, the row itself dropped
+    ix.set_tensor_core(True)
+    gi, gd, gc = build.knn_graph(ix, 16, batch=8192)
+    ix.set_tensor_core(False)
+    ri, rd, rc = build.knn_graph(ix, 16, batch=8192)
+    import torch
+    torch.cuda.synchronize()
+    assert (gc == rc).all() and (gi == ri).all() and (gd.view(torch.int32) == rd.view(torch.int32)).all()
+    assert not (gi.cpu().numpy() == np.arange(1, n + 1)[:, None]).any()
+    # removed slots are never returned
+    removed = np.arange(5, n, 7, dtype=np.uint32)
+    ix.set_removed(removed)
+    ix.set_tensor_core(True)
+    ids, dists, counts = ix.linear_search(qs, 10)
+    ix.set_tensor_core(False)
+    rids, rdists, rcounts = ix.linear_search(qs, 10)
+    assert_bit_exact(ids, dists, counts, rids, rdists, rcounts, what=case + " removed")
+    assert not np.isin(ids, removed).any()
+    ix.close()
