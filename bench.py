@@ -50,10 +50,10 @@ def parse_args():
     ap.add_argument("--nq", type=int, default=10000)
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--shape", default="sift")
-    ap.add_argument("--knn", type=int, default=64, help="edges per node of the exact kNN graph")
+    ap.add_argument("--knn", type=int, default=100, help="edges per node of the exact kNN graph")
     ap.add_argument("--outgoing", type=int, default=10)
-    ap.add_argument("--incoming", type=int, default=64)
-    ap.add_argument("--edge-size", type=int, default=64, help="edge_size of the search (0 = all edges)")
+    ap.add_argument("--incoming", type=int, default=100)
+    ap.add_argument("--edge-size", type=int, default=80, help="edge_size of the search (0 = all edges)")
     ap.add_argument("--pivots", type=int, default=1024)
     ap.add_argument("--seeds", type=int, default=10)
     ap.add_argument("--recall", type=float, default=0.95)

@@ -357,14 +357,14 @@ extern "C" int ngtgpu_index_set_removed(ngtgpu_index *ix, const uint32_t *ids, u
   return NGTGPU_OK;
 }
 
-// fixed-stride copy of the first 64 edges of every node (zero padded): the traversal kernel reads one node's
+// fixed-stride copy of the first NGTGPU_HEAD_WIDTH (128) edges of every node (zero padded): the traversal kernel reads one node's
 // edges with a single coalesced access instead of row_ptr -> col (two dependent ones)
 __global__ void build_head_kernel(const uint64_t *__restrict__ row_ptr, const uint32_t *__restrict__ col, uint64_t n,
                                   uint32_t *__restrict__ head) {
-  const uint64_t total = (n + 1) * 64;
+  const uint64_t total = (n + 1) * NGTGPU_HEAD_WIDTH;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t id = i >> 6;
-    const uint32_t e = (uint32_t)(i & 63);
+    const uint64_t id = i / NGTGPU_HEAD_WIDTH;
+    const uint32_t e = (uint32_t)(i % NGTGPU_HEAD_WIDTH);
     const uint64_t b = row_ptr[id], deg = row_ptr[id + 1] - b;
     head[i] = e < deg ? col[b + e] : 0u;
   }
@@ -393,7 +393,7 @@ extern "C" int ngtgpu_index_set_graph(ngtgpu_index *ix, const uint64_t *row_ptr,
   CUDA_TRY(cudaMemcpy(ix->d_row_ptr, row_ptr, (ix->n + 2) * sizeof(uint64_t), kind));
   if (nnz) CUDA_TRY(cudaMemcpy(ix->d_col, col, nnz * sizeof(uint32_t), kind));
   ix->nnz = nnz;
-  CUDA_TRY(cudaMalloc(&ix->d_head, (ix->n + 1) * 64 * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&ix->d_head, (ix->n + 1) * NGTGPU_HEAD_WIDTH * sizeof(uint32_t)));
   build_head_kernel<<<ix->sm_count * 8, 256, 0, ix->stream>>>(ix->d_row_ptr, ix->d_col, ix->n, ix->d_head);
   ix->launches++;
   CUDA_TRY(cudaGetLastError());

@@ -34,6 +34,8 @@ void ngtgpu_set_error(const std::string &msg);
 // F_COS : sum a*a, sum b*b and sum a*b    :487-553   (Cosine, Angle)
 // U8_L2 : exact integer sum (a-b)^2       :200-223
 // U8_HAM: popcount(a^b)                   :340-353
+#define NGTGPU_HEAD_WIDTH 128   // edges per node in the fixed-stride adjacency table read by the traversal kernel
+
 enum AccKind { ACC_F_L2 = 0, ACC_F_DOT = 1, ACC_F_COS = 2, ACC_U8_L2 = 3, ACC_U8_HAM = 4 };
 
 // scratch slots (grown on demand, reused between calls)
@@ -71,7 +73,7 @@ struct ngtgpu_index {
   uint8_t *d_valid = nullptr;     // (n+1) bytes, 0 = empty slot; nullptr when nothing was removed
   uint64_t *d_row_ptr = nullptr;  // n+2
   uint32_t *d_col = nullptr;
-  uint32_t *d_head = nullptr;     // (n+1) x 64: the first 64 edges of every node, zero padded (one coalesced read)
+  uint32_t *d_head = nullptr;     // (n+1) x 128: the first 128 edges of every node, zero padded (one coalesced read)
   uint64_t nnz = 0;
   int64_t edge_size_for_search = 40;   // Graph.h:401 defaults
   int64_t dyn_base = 30;

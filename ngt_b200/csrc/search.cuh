@@ -43,7 +43,7 @@
 #define SEARCH_WARPS 4
 #define SEARCH_THREADS (SEARCH_WARPS * 32)
 #define SEARCH_CMAX 128       // upper bound of edges filtered / rows staged per round (== SEARCH_THREADS)
-#define SEARCH_HEAD 64        // edges per node in the fixed-stride adjacency table
+#define SEARCH_HEAD 128       // edges per node in the fixed-stride adjacency table (== SEARCH_THREADS: one per thread)
 
 struct SearchArgs {
   const uint8_t *objects;
@@ -420,8 +420,8 @@ __global__ void __launch_bounds__(SEARCH_THREADS) search_kernel(const SearchArgs
                 if (use_head) {
                   // its edges will be wanted when it is popped: pull that row of the head table towards L2 now
                   const uint32_t *hp = a.head + (size_t)key_id(key) * SEARCH_HEAD;
-                  asm volatile("prefetch.global.L2 [%0];" ::"l"(hp));
-                  asm volatile("prefetch.global.L2 [%0];" ::"l"(hp + 32));
+                  const uint32_t lines = ((a.edge_cap < SEARCH_HEAD ? a.edge_cap : SEARCH_HEAD) + 31) / 32;
+                  for (uint32_t l = 0; l < lines; l++) asm volatile("prefetch.global.L2 [%0];" ::"l"(hp + l * 32));
                 }
               }
               qsize += cnt;
