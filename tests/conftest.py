@@ -32,3 +32,10 @@ def synth_golden():
     for k in [k for k in z if k.endswith("_objects_alias")]:
         z[k[: -len("_alias")]] = z[str(z[k]) + "_objects"]
     return z
+
+
+@pytest.fixture(scope="session")
+def eng():
+    """The device engine over the C ABI (GPU tests only)."""
+    from ngt_b200 import engine
+    return engine

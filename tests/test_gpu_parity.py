@@ -14,12 +14,6 @@ from parity import (EDGE_GRID, EPS_GRID, FLOAT_CASES, INTEGER_EXACT, NORMALIZED,
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def eng():
-    from ngt_b200 import engine
-    return engine
-
-
 def _gpu_index(eng, otype, dtype, objects, row_ptr=None, col=None, prop=None, normalize=False):
     ix = eng.GpuIndex(otype, dtype, objects.shape[1])
     ix.set_objects(objects, normalize=normalize)

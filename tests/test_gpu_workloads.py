@@ -1,0 +1,178 @@
+"""The BASELINE.json configurations C3-C5 at reduced size, end to end on the device: graph construction from
+the exhaustive kNN pass, seed table, batched graph search, sharding + merge. What is checked is size
+independent: merged shards == the union (bit for bit), uint8/Hamming distances equal the integer formula,
+recall against the exhaustive scan at the reference's default epsilon, the oracle on a sample of queries."""
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+from parity import assert_bit_exact, assert_float_parity
+
+pytestmark = pytest.mark.gpu
+
+
+def _recall(ids, gt_ids):
+    return float(np.mean([(np.isin(ids[q], gt_ids[q])).mean() for q in range(ids.shape[0])]))
+
+
+def _build(eng, otype, dtype, base, knn, outgoing, incoming, pivots=512):
+    import torch
+    from ngt_b200 import build
+    ix = eng.GpuIndex(otype, dtype, base.shape[1])
+    ix.set_objects(base)
+    ids, dists, counts = build.knn_graph(ix, knn)
+    row_ptr, col, dist = build.reconstruct_graph(ids, dists, counts, outgoing, incoming)
+    ix.set_graph(row_ptr, col)
+    ix.build_seed_table(pivots, 3)
+    torch.cuda.synchronize()
+    return ix, row_ptr.cpu().numpy().astype(np.uint64), col.cpu().numpy().astype(np.uint32)
+
+
+@pytest.mark.parametrize("dtype", [po.NORMALIZED_COSINE, po.ANGLE])
+def test_c3_glove_shape_angular(eng, port, dtype):
+    """C3: float angular (glove-shape, dim 100 -> padded 112): kNN graph on the tensor cores, ANNG-style search."""
+    from ngt_b200 import synth
+    n, nq, k = 60000, 1200, 10
+    base, qs = synth.make("glove", n, 1), synth.make("glove", nq, 2)
+    ix, row_ptr, col = _build(eng, po.FLOAT, dtype, base, 24, 24, 24)
+    assert ix.tensor_core_batches > 0                      # the kNN pass ran on tcgen05
+    gt_ids, gt_d, _ = ix.linear_search(qs, k)
+    # 1 - cos distances are small numbers: the same relative epsilon explores less than with L2, use 0.3
+    ids, dists, counts, stats = ix.search(qs, k, 0.3, edge_size=0, n_seeds=10, with_stats=True)
+    assert _recall(ids, gt_ids) >= 0.9
+    assert stats[:, 0].mean() < n / 2                       # it is a graph search, not a scan
+    # a sample of queries against the restated reference, same seeds / graph / stored (normalised) rows
+    import ctypes as C
+    from ngt_b200 import _lib
+    lib = _lib.load()
+    lib.ngtgpu_select_seeds.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p]
+    m = 24
+    seeds = np.zeros((m, 10), np.uint32)
+    q = np.ascontiguousarray(qs[:m])
+    _lib.check(lib.ngtgpu_select_seeds(ix._h, q.ctypes.data, _lib.OBJECT_FLOAT, m, 10, seeds.ctypes.data))
+    stored = np.stack([ix.get_object(i) for i in range(1, n + 1)]) if dtype == po.NORMALIZED_COSINE else base
+    qn = port.normalize(q) if dtype == po.NORMALIZED_COSINE else q
+    gi, gd, gc = ix.search(q, k, 0.1, edge_size=0, seeds=seeds)
+    ri, rd, rc, _ = port.graph_search(dtype, po.FLOAT, po.pad_objects(stored, po.FLOAT), row_ptr, col,
+                                      po.pad_queries(qn, po.FLOAT), seeds, k, 0.1)
+    assert_float_parity(gi, gd, gc, ri, rd, rc, what="glove graph search vs oracle", rtol=2e-6, tie=4e-6)
+    ix.close()
+
+
+def _merge_shards(eng, shards, n_local, queries, k, fn):
+    """Search every shard (all on this GPU), pack with global ids, merge with the device kernel."""
+    import torch
+    from ngt_b200 import _lib, sharded
+    lib = sharded._fn()
+    dev = torch.device("cuda", 0)
+    tq = torch.from_numpy(queries).to(dev)
+    nq = queries.shape[0]
+    gathered = torch.empty((len(shards), nq, k), dtype=torch.int64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    for r, ix in enumerate(shards):
+        ids, dists, counts = fn(ix, tq)
+        _lib.check(lib.ngtgpu_pack_keys(ids.data_ptr(), dists.data_ptr(), counts.data_ptr(), nq, k, r * n_local,
+                                        gathered[r].data_ptr(), stream))
+    oi = torch.empty((nq, k), dtype=torch.int32, device=dev)
+    od = torch.empty((nq, k), dtype=torch.float32, device=dev)
+    oc = torch.empty((nq,), dtype=torch.int32, device=dev)
+    _lib.check(lib.ngtgpu_merge_keys(gathered.data_ptr(), len(shards), nq, k, oi.data_ptr(), od.data_ptr(), oc.data_ptr(), stream))
+    torch.cuda.synchronize()
+    return oi.cpu().numpy().astype(np.uint32), od.cpu().numpy(), oc.cpu().numpy().astype(np.uint32)
+
+
+def test_c4_gist_shape_sharded(eng):
+    """C4: 960-d float L2 sharded: per-shard exhaustive + merge == the union, bit for bit; per-shard graph search
+    merged reaches the recall of the single index."""
+    from ngt_b200 import synth
+    n, nq, k, world = 24000, 300, 10, 4
+    base, qs = synth.make("gist", n, 1), synth.make("gist", nq, 2)
+    whole, _, _ = _build(eng, po.FLOAT, po.L2, base, 16, 16, 16)
+    gt_ids, gt_d, gt_c = whole.linear_search(qs, k)
+    n_local = n // world
+    shards = [_build(eng, po.FLOAT, po.L2, base[r * n_local:(r + 1) * n_local], 16, 16, 16)[0] for r in range(world)]
+    mi, md, mc = _merge_shards(eng, shards, n_local, qs, k, lambda ix, tq: ix.linear_search(tq, k))
+    assert_bit_exact(mi, md, mc, gt_ids, gt_d, gt_c, what="sharded exhaustive == union")
+    si, sd, sc = _merge_shards(eng, shards, n_local, qs, k, lambda ix, tq: ix.search(tq, k, 0.1, edge_size=0, n_seeds=10))
+    wi, wd, wc = whole.search(qs, k, 0.1, edge_size=0, n_seeds=10)
+    assert _recall(si, gt_ids) >= min(0.9, _recall(wi, gt_ids) - 0.02)
+    for ix in shards + [whole]:
+        ix.close()
+
+
+@pytest.mark.parametrize("kind", ["u8l2", "hamming"])
+def test_c5_uint8_sharded_bit_exact(eng, kind):
+    """C5: uint8 L2 / Hamming: graph search + sharded exhaustive search; distances equal the integer formula
+    (float)sqrt((double)sum (a-b)^2) / (float)popcount(a^b) exactly, ids ordered by (distance, id)."""
+    from ngt_b200 import synth
+    n, nq, k, world = 160000, 400, 10, 4
+    raw, rq = synth.make("sift", n, 1), synth.make("sift", nq, 2)
+    if kind == "u8l2":
+        base, qs, dt = raw.astype(np.uint8), rq.astype(np.uint8), po.L2
+    else:
+        base, qs, dt = synth.hamming_from(raw, 64.0), synth.hamming_from(rq, 64.0), po.HAMMING
+    whole, _, _ = _build(eng, po.UINT8, dt, base, 16, 16, 16)
+    gt_ids, gt_d, gt_c = whole.linear_search(qs, k)
+    # the integer formula, for the returned ids
+    for q in range(0, nq, 37):
+        rows = base[gt_ids[q].astype(np.int64) - 1].astype(np.int64)
+        if kind == "u8l2":
+            exact = np.sqrt(((rows - qs[q].astype(np.int64)) ** 2).sum(1).astype(np.float64)).astype(np.float32)
+        else:
+            exact = np.unpackbits(np.bitwise_xor(base[gt_ids[q].astype(np.int64) - 1], qs[q]), axis=1).sum(1).astype(np.float32)
+        assert (exact.view(np.uint32) == gt_d[q].view(np.uint32)).all()
+        assert (np.lexsort((gt_ids[q], gt_d[q])) == np.arange(k)).all()
+    # nothing closer was missed (checked against a full numpy scan for a few queries)
+    for q in (0, 101, 399):
+        if kind == "u8l2":
+            d2 = ((base.astype(np.int32) - qs[q].astype(np.int32)) ** 2).sum(1)
+            full = np.sqrt(d2.astype(np.float64)).astype(np.float32)
+        else:
+            full = np.unpackbits(np.bitwise_xor(base, qs[q]), axis=1).sum(1).astype(np.float32)
+        order = np.lexsort((np.arange(n), full))[:k]
+        assert (order + 1 == gt_ids[q]).all()
+    n_local = n // world
+    shards = [_build(eng, po.UINT8, dt, base[r * n_local:(r + 1) * n_local], 16, 16, 16)[0] for r in range(world)]
+    mi, md, mc = _merge_shards(eng, shards, n_local, qs, k, lambda ix, tq: ix.linear_search(tq, k))
+    assert_bit_exact(mi, md, mc, gt_ids, gt_d, gt_c, what="sharded exhaustive == union (%s)" % kind)
+    gi, gd, gc = whole.search(qs, k, 0.1, edge_size=0, n_seeds=10)
+    if kind == "u8l2":
+        assert _recall(gi, gt_ids) >= 0.9
+    # graph-search distances are exact integers-under-the-root too
+    rows = base[gi[5].astype(np.int64) - 1]
+    if kind == "u8l2":
+        ex = np.sqrt(((rows.astype(np.int64) - qs[5].astype(np.int64)) ** 2).sum(1).astype(np.float64)).astype(np.float32)
+    else:
+        ex = np.unpackbits(np.bitwise_xor(rows, qs[5]), axis=1).sum(1).astype(np.float32)
+    assert (ex.view(np.uint32) == gd[5].view(np.uint32)).all()
+    for ix in shards + [whole]:
+        ix.close()
+
+
+def test_index_mirror_round_trip(eng, tmp_path):
+    """ngt_b200.Index (the ngtpy.Index surface): create -> batch_insert -> search / linear_search -> save -> reopen."""
+    from ngt_b200 import index as ngt
+    from ngt_b200 import synth
+    path = str(tmp_path / "idx")
+    ngt.create(path, 128, edge_size_for_creation=12, edge_size_for_search=40, distance_type="L2", object_type="Float")
+    ix = ngt.Index(path)
+    base = synth.make("sift", 5000, 1)
+    ix.batch_insert(base)
+    q = synth.make("sift", 4, 2)
+    lin = ix.linear_search(q[0], size=5)
+    res = ix.search(q[0], size=5, epsilon=0.3)
+    assert [r[0] for r in res] == [r[0] for r in lin]            # zero-based ids, same as the exhaustive answer
+    d = np.linalg.norm(base - q[0], axis=1)
+    assert [r[0] for r in lin] == np.argsort(d, kind="stable")[:5].tolist()
+    ids, dists = ix.batch_search(q, size=5, epsilon=0.3)
+    assert ids.shape == (4, 5) and (ids[0] == [r[0] for r in res]).all()
+    assert ix.get_num_of_distance_computations() > 0
+    assert np.allclose(ix.get_object(17), base[17])
+    ix.remove(int(lin[0][0]))
+    assert ix.linear_search(q[0], size=5)[0][0] != lin[0][0]
+    ix.save()
+    ix.close()
+    again = ngt.Index(path, zero_based_numbering=False)
+    res2 = again.search(q[0], size=5, epsilon=0.3)
+    assert len(res2) == 5 and all(r[0] != lin[0][0] + 1 for r in res2)
+    again.close()
