@@ -61,7 +61,7 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=2000)
     ap.add_argument("--epsilon", type=float, default=None, help="skip the sweep and use this epsilon")
     ap.add_argument("--hash-bits", type=int, default=14)
-    ap.add_argument("--queue-cap", type=int, default=1024)
+    ap.add_argument("--queue-cap", type=int, default=512)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--index-dir", default=None)
     return ap.parse_args()

@@ -620,17 +620,26 @@ __global__ void __launch_bounds__(SEARCH_THREADS) search_kernel(const SearchArgs
         uint8_t *wstage = stage + (size_t)warp * wrows * a.row_bytes;
         for (uint32_t j0 = warp * wrows; j0 < cn; j0 += SEARCH_WARPS * wrows) {
           const uint32_t nr = cn - j0 < wrows ? cn - j0 : wrows;
-          if (G == 32) {
+          if (G == 32 && CPL > 0) {
+            // lane r fetches the id of the slice's r-th row once; the row loop is unrolled so the copies of
+            // all rows are issued back to back
+            const uint32_t my_id = (uint32_t)lane < nr ? s_cand_ids[j0 + lane] : 0u;
+            const uint8_t *lane_src = a.objects + (size_t)lane * 16;
+            uint8_t *lane_dst = wstage + (size_t)lane * 16;
+#pragma unroll 8
             for (uint32_t r = 0; r < nr; r++) {
-              const uint8_t *srow = a.objects + (size_t)s_cand_ids[j0 + r] * a.row_bytes + (size_t)lane * 16;
-              uint8_t *drow = wstage + (size_t)r * a.row_bytes + (size_t)lane * 16;
-              if (CPL > 0) {
+              const uint32_t id = __shfl_sync(0xffffffffu, my_id, (int)r);
+              const uint8_t *srow = lane_src + (size_t)id * a.row_bytes;
+              uint8_t *drow = lane_dst + (size_t)r * a.row_bytes;
 #pragma unroll
-                for (int c = 0; c < NCH; c++)
-                  if ((uint32_t)lane + c * 32 < a.chunks) cp_async_row16(drow + c * 512, srow + c * 512);
-              } else {
-                for (uint32_t c = lane; c < a.chunks; c += 32) cp_async_row16(drow + (size_t)(c - lane) * 16, srow + (size_t)(c - lane) * 16);
-              }
+              for (int c = 0; c < NCH; c++)
+                if ((uint32_t)lane + c * 32 < a.chunks) cp_async_row16(drow + c * 512, srow + c * 512);
+            }
+          } else if (G == 32) {
+            for (uint32_t r = 0; r < nr; r++) {
+              const uint8_t *srow = a.objects + (size_t)s_cand_ids[j0 + r] * a.row_bytes;
+              uint8_t *drow = wstage + (size_t)r * a.row_bytes;
+              for (uint32_t c = lane; c < a.chunks; c += 32) cp_async_row16(drow + (size_t)c * 16, srow + (size_t)c * 16);
             }
           } else {
             // short rows: the slice is one flat run of nr * chunks 16-byte pieces

@@ -135,7 +135,7 @@ class GpuIndex:
         _lib.check(self._lib.ngtgpu_index_set_search_property(self._h, int(edge_size_for_search),
                                                               int(dynamic_edge_size_base), int(dynamic_edge_size_rate)))
 
-    def set_search_workspace(self, hash_bits=14, queue_cap=1024, onchip_tiers=2, stage_bytes=None):
+    def set_search_workspace(self, hash_bits=14, queue_cap=512, onchip_tiers=2, stage_bytes=None):
         _lib.check(self._lib.ngtgpu_index_set_search_workspace(self._h, int(hash_bits), int(queue_cap)))
         _lib.check(self._lib.ngtgpu_index_set_onchip_tiers(self._h, int(onchip_tiers)))
         if stage_bytes is not None:

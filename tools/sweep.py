@@ -21,7 +21,7 @@ ap.add_argument("--kmax", type=int, default=96)
 ap.add_argument("--configs", default="64,10,64,64")   # knn,outgoing,incoming,cap;...
 ap.add_argument("--eps", default="0.04,0.06,0.08,0.10,0.12")
 ap.add_argument("--hash-bits", type=int, default=14)
-ap.add_argument("--queue-cap", type=int, default=1024)
+ap.add_argument("--queue-cap", type=int, default=512)
 ap.add_argument("--pivots", type=int, default=1024)
 ap.add_argument("--seeds", type=int, default=10)
 ap.add_argument("--target", type=float, default=0.95)
