@@ -42,6 +42,9 @@
 
 #define SEARCH_WARPS 4
 #define SEARCH_THREADS (SEARCH_WARPS * 32)
+#ifndef SEARCH_MIN_CTAS
+#define SEARCH_MIN_CTAS 8     // 64 registers per thread; nine CTAs (56 registers) spill and measured slower
+#endif
 #define SEARCH_CMAX 128       // upper bound of edges filtered / rows staged per round (== SEARCH_THREADS)
 #define SEARCH_HEAD 128       // edges per node in the fixed-stride adjacency table (== SEARCH_THREADS: one per thread)
 
@@ -237,7 +240,7 @@ __device__ __forceinline__ bool bitmap_visit(uint32_t *bitmap, uint32_t nid) {
 }
 
 template <int ACC, int G, int CPL, int WS>
-__global__ void __launch_bounds__(SEARCH_THREADS) search_kernel(const SearchArgs a) {
+__global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel(const SearchArgs a) {
   constexpr int R = 32 / G;                 // rows per warp instruction (G < 32)
   constexpr int NCH = CPL > 0 ? CPL : 1;    // register-resident query chunks per lane
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -786,6 +789,8 @@ static cudaError_t launch_one(const SearchArgs &a, const SearchLaunch &l) {
   cudaError_t e = cudaFuncSetAttribute(search_kernel<ACC, G, CPL, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)l.smem);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(search_kernel<ACC, G, CPL, WS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  if (e != cudaSuccess) return e;
   search_kernel<ACC, G, CPL, WS><<<l.grid, SEARCH_THREADS, l.smem, l.stream>>>(a);
   return cudaGetLastError();
 }
@@ -794,6 +799,8 @@ template <int ACC, int G, int CPL, int WS>
 static cudaError_t occupancy_one(size_t smem, int *blocks) {
   cudaError_t e = cudaFuncSetAttribute(search_kernel<ACC, G, CPL, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(search_kernel<ACC, G, CPL, WS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   if (e != cudaSuccess) return e;
   return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, search_kernel<ACC, G, CPL, WS>, SEARCH_THREADS, smem);
 }
