@@ -92,6 +92,42 @@ def reconstruct_graph(ids, dists, counts, outgoing, incoming):
     return row_ptr, dst.to(torch.int32), d
 
 
+def reconstruct_graph_csr(row_ptr, col, dist, outgoing, incoming):
+    """GraphReconstructor::reconstructGraph (lib/NGT/GraphReconstructor.h:425-561) on adjacency lists of any
+    length (an ANNG as `grp` stores it): node i keeps its first `outgoing` edges -- or ALL of them when it has fewer
+    than `outgoing` (the reference leaves such nodes untouched, :447-456) -- then gets the reverse of the first
+    `incoming` edges of every node; lists are sorted by (distance, id) and de-duplicated.
+    row_ptr: [n+2] over ids 0..n, col: 1-based ids, dist: float32. torch tensors (any device)."""
+    import torch
+    row_ptr = row_ptr.to(torch.int64)
+    dev = col.device
+    n = row_ptr.numel() - 2
+    deg = row_ptr[1:] - row_ptr[:-1]                      # per id 0..n
+    src = torch.repeat_interleave(torch.arange(n + 1, device=dev, dtype=torch.int64), deg)
+    rank = torch.arange(col.numel(), device=dev, dtype=torch.int64) - row_ptr[src]
+    dst = col.to(torch.int64)
+    d = dist.to(torch.float32)
+    keep_all = deg[src] < outgoing
+    mo = (rank < outgoing) | keep_all if outgoing > 0 else torch.zeros_like(rank, dtype=torch.bool)
+    mi = rank < incoming
+    s2 = torch.cat([src[mo], dst[mi]])
+    t2 = torch.cat([dst[mo], src[mi]])
+    d2 = torch.cat([d[mo], d[mi]])
+    key = (_dist_sort_key(d2) << 32) | t2
+    order = torch.argsort(key, stable=True)
+    s2, t2, d2 = s2[order], t2[order], d2[order]
+    order = torch.argsort(s2, stable=True)
+    s2, t2, d2 = s2[order], t2[order], d2[order]
+    # the reference drops an entry when its id equals the previous entry's id in the sorted list (:519-533)
+    keep = torch.ones_like(s2, dtype=torch.bool)
+    keep[1:] = (s2[1:] != s2[:-1]) | (t2[1:] != t2[:-1])
+    s2, t2, d2 = s2[keep], t2[keep], d2[keep]
+    out_deg = torch.bincount(s2, minlength=n + 1)
+    out_ptr = torch.zeros(n + 2, dtype=torch.int64, device=dev)
+    out_ptr[1:] = torch.cumsum(out_deg, 0)
+    return out_ptr, t2.to(torch.int32), d2
+
+
 def graph_statistics(row_ptr):
     deg = (row_ptr[2:] - row_ptr[1:-1]).float()
     return {"edges": int(row_ptr[-1]), "mean_degree": float(deg.mean()), "min_degree": int(deg.min()),

@@ -172,3 +172,21 @@ def test_index_files_round_trip_and_interoperate_with_the_reference(sift5k):
         assert len(got) == 5
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
+
+
+def test_reconstruct_graph_matches_the_reference():
+    """GraphReconstructor::reconstructGraph: ANNG built by the reference in, the graph the reference's
+    GraphOptimizer::execute writes (path adjustment off) out -- tests/golden/reconstruct.npz."""
+    import torch
+    from conftest import GOLDEN
+    from ngt_b200 import build
+    z = np.load(os.path.join(GOLDEN, "reconstruct.npz"))
+    rp = torch.from_numpy(z["anng_row_ptr"].astype(np.int64))
+    col = torch.from_numpy(z["anng_col"].astype(np.int32))
+    dist = torch.from_numpy(z["anng_dist"])
+    for o, i in ((5, 20), (10, 40), (0, 15)):
+        key = "o%d_i%d" % (o, i)
+        orp, ocol, odist = build.reconstruct_graph_csr(rp, col, dist, o, i)
+        assert (orp.numpy() == z[key + "_row_ptr"].astype(np.int64)).all(), key
+        assert (ocol.numpy().astype(np.uint32) == z[key + "_col"]).all(), key
+        assert (odist.numpy().view(np.uint32) == z[key + "_dist"].view(np.uint32)).all(), key
