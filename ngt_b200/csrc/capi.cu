@@ -1,0 +1,843 @@
+// capi.cu -- NGT's C API (lib/NGT/Capi.h:60-212) over the B200 engine, for the hot path and its life cycle.
+//
+// Same names, argument meaning, sentinels and error convention as the reference (lib/NGT/Capi.cpp): every
+// function catches, writes "Capi : <func>() : Error: <what>" into *error (a std::string) when one is given, else to
+// stderr (Capi.cpp:25-38), and returns false / NULL / 0. Handles are opaque pointers owned by the caller and freed
+// with the matching ngt_destroy_* / ngt_close_index. A program written against libngt's C API (python/ngt/base.py
+// binds exactly these) links against this library unchanged for open / search / linear search / insert / build / save;
+// single-query calls are batches of one, and two additive batch entry points feed the device properly.
+// Host code only: all distance work goes through the ngtgpu_* C ABI (include/ngtgpu.h). What is outside the hot
+// path (optimizer, refine_anng, in-memory-only tree functions) fails loudly with a message instead of pretending.
+#include <algorithm>
+#include <cfloat>
+#include <climits>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <memory>
+#include <sstream>
+#include <stdexcept>
+#include <sys/stat.h>
+
+#include "ngtgpu_internal.cuh"
+
+extern "C" {
+int ngtgpu_io_obj_info(const char *path, uint32_t record_bytes, uint64_t *slots, uint64_t *present);
+int ngtgpu_io_read_obj(const char *path, uint32_t record_bytes, void *rows, uint8_t *present);
+int ngtgpu_io_write_obj(const char *path, uint32_t record_bytes, const void *rows, uint64_t n, const uint8_t *present);
+int ngtgpu_io_grp_info(const char *path, uint64_t *slots, uint64_t *nnz);
+int ngtgpu_io_read_grp(const char *path, uint64_t *row_ptr, uint32_t *col, float *dist, uint8_t *present);
+int ngtgpu_io_write_grp(const char *path, uint64_t n, const uint64_t *row_ptr, const uint32_t *col, const float *dist,
+                        const uint8_t *present);
+int ngtgpu_index_knn_graph(ngtgpu_index *ix, uint32_t k, uint32_t first_id, uint32_t count, uint32_t *d_ids,
+                           float *d_dists, uint32_t *d_counts, void *stream);
+}
+
+typedef unsigned int ObjectID;
+typedef void *NGTIndex;
+typedef void *NGTProperty;
+typedef void *NGTObjectSpace;
+typedef void *NGTObjectDistances;
+typedef void *NGTError;
+typedef void *NGTOptimizer;
+typedef struct {
+  ObjectID id;
+  float distance;
+} NGTObjectDistance;
+typedef struct {
+  float *query;
+  size_t size;
+  float epsilon;
+  float accuracy;
+  float radius;
+  size_t edge_size;
+} NGTQuery;
+
+namespace {
+
+struct CapiProperty {   // the part of NGT::Property the C API exposes (Index.h:60-154, Graph.h:385-454)
+  int32_t dimension = 0;
+  int16_t edge_size_for_creation = 10;
+  int16_t edge_size_for_search = 40;
+  int32_t object_type = NGTGPU_OBJECT_FLOAT;
+  int32_t distance_type = NGTGPU_DISTANCE_L2;
+};
+
+struct CapiIndex {
+  std::string path;
+  std::map<std::string, std::string> prf;
+  CapiProperty prop;
+  std::vector<uint8_t> objects;    // ids 1..n, unpadded rows as `obj` stores them
+  std::vector<uint8_t> present;    // n+1
+  std::vector<uint64_t> row_ptr;   // n+2
+  std::vector<uint32_t> col;
+  std::vector<float> dist;
+  ngtgpu_index *gpu = nullptr;
+  size_t pending = 0;              // appended since the last build
+  size_t raw_from = 0;             // first id whose row is not normalised yet (Normalized* types)
+  size_t record_bytes() const { return (size_t)prop.dimension * (prop.object_type == NGTGPU_OBJECT_UINT8 ? 1 : 4); }
+  size_t n() const { return present.empty() ? 0 : present.size() - 1; }
+};
+
+void check(int rc) {
+  if (rc != NGTGPU_OK) throw std::runtime_error(ngtgpu_last_error());
+}
+
+void operate_error_string(const std::stringstream &ss, NGTError error) {   // Capi.cpp:25-38
+  if (error != NULL) {
+    try {
+      *static_cast<std::string *>(error) = ss.str();
+    } catch (...) {
+      std::cerr << ss.str() << " > Failed to track error details" << std::endl;
+    }
+  } else {
+    std::cerr << ss.str() << std::endl;
+  }
+}
+#define CAPI_CATCH(ret)                                                   \
+  catch (std::exception & err) {                                          \
+    std::stringstream ss;                                                 \
+    ss << "Capi : " << __FUNCTION__ << "() : Error: " << err.what();      \
+    operate_error_string(ss, error);                                      \
+    return ret;                                                           \
+  }
+
+const char *object_type_name(int t) { return t == NGTGPU_OBJECT_UINT8 ? "Integer-1" : "Float-4"; }
+int object_type_of(const std::string &s) {
+  if (s == "Integer-1") return NGTGPU_OBJECT_UINT8;
+  if (s == "Float-4") return NGTGPU_OBJECT_FLOAT;
+  throw std::runtime_error("Invalid Object Type in the property. " + s);
+}
+const std::map<std::string, int> &distance_names() {
+  static const std::map<std::string, int> m = {
+      {"L1", 0}, {"L2", NGTGPU_DISTANCE_L2}, {"Hamming", NGTGPU_DISTANCE_HAMMING}, {"Angle", NGTGPU_DISTANCE_ANGLE},
+      {"Cosine", NGTGPU_DISTANCE_COSINE}, {"NormalizedAngle", NGTGPU_DISTANCE_NORMALIZED_ANGLE},
+      {"NormalizedCosine", NGTGPU_DISTANCE_NORMALIZED_COSINE}, {"Jaccard", 7}, {"NormalizedL2", NGTGPU_DISTANCE_NORMALIZED_L2}};
+  return m;
+}
+std::string distance_type_name(int t) {
+  for (auto &kv : distance_names())
+    if (kv.second == t) return kv.first;
+  return "None";
+}
+bool normalizes(int dt) {
+  return dt == NGTGPU_DISTANCE_NORMALIZED_ANGLE || dt == NGTGPU_DISTANCE_NORMALIZED_COSINE || dt == NGTGPU_DISTANCE_NORMALIZED_L2;
+}
+
+std::map<std::string, std::string> default_prf() {   // what `ngt create` writes (Index.h:60-103, Graph.h:385-420)
+  return {{"AccuracyTable", ""}, {"BatchSizeForCreation", "200"}, {"BuildTimeLimit", "0"}, {"DatabaseType", "Memory"},
+          {"Dimension", "0"}, {"DistanceType", "L2"}, {"DynamicEdgeSizeBase", "30"}, {"DynamicEdgeSizeRate", "20"},
+          {"EdgeSizeForCreation", "10"}, {"EdgeSizeForSearch", "40"}, {"EdgeSizeLimitForCreation", "5"},
+          {"EpsilonForCreation", "0.1"}, {"GraphType", "ANNG"}, {"IncomingEdge", "80"},
+          {"IncrimentalEdgeSizeLimitForTruncation", "0"}, {"IndexType", "Graph"}, {"ObjectAlignment", "False"},
+          {"ObjectType", "Float-4"}, {"OutgoingEdge", "10"}, {"PathAdjustmentInterval", "0"}, {"PrefetchOffset", "0"},
+          {"PrefetchSize", "0"}, {"SeedSize", "10"}, {"SeedType", "None"}, {"ThreadPoolSize", "24"},
+          {"TruncationThreadPoolSize", "8"}};
+}
+
+void read_prf(CapiIndex &ix) {
+  std::ifstream f(ix.path + "/prf");
+  if (!f.is_open()) throw std::runtime_error("PropertySet::load: Cannot load the property file " + ix.path + "/prf.");
+  std::string line;
+  while (std::getline(f, line)) {
+    size_t t = line.find('\t');
+    if (t == std::string::npos) continue;
+    ix.prf[line.substr(0, t)] = line.substr(t + 1);
+  }
+  ix.prop.dimension = std::stoi(ix.prf.at("Dimension"));
+  ix.prop.object_type = object_type_of(ix.prf.at("ObjectType"));
+  auto d = distance_names().find(ix.prf.at("DistanceType"));
+  if (d == distance_names().end()) throw std::runtime_error("Invalid Distance Type in the property. " + ix.prf.at("DistanceType"));
+  ix.prop.distance_type = d->second;
+  if (ix.prf.count("EdgeSizeForCreation")) ix.prop.edge_size_for_creation = (int16_t)std::stoi(ix.prf["EdgeSizeForCreation"]);
+  if (ix.prf.count("EdgeSizeForSearch")) ix.prop.edge_size_for_search = (int16_t)std::stoi(ix.prf["EdgeSizeForSearch"]);
+}
+
+void write_prf(CapiIndex &ix, const std::string &path) {
+  ix.prf["Dimension"] = std::to_string(ix.prop.dimension);
+  ix.prf["ObjectType"] = object_type_name(ix.prop.object_type);
+  ix.prf["DistanceType"] = distance_type_name(ix.prop.distance_type);
+  ix.prf["EdgeSizeForCreation"] = std::to_string(ix.prop.edge_size_for_creation);
+  ix.prf["EdgeSizeForSearch"] = std::to_string(ix.prop.edge_size_for_search);
+  ix.prf["IndexType"] = "Graph";   // no `tre` is written; the reference opens Graph indexes without one (Index.cpp:93-111)
+  std::ofstream f(path + "/prf");
+  if (!f.is_open()) throw std::runtime_error("PropertySet::save: Cannot save. " + path + "/prf");
+  for (auto &kv : ix.prf) f << kv.first << "\t" << kv.second << "\n";
+}
+
+long prf_long(CapiIndex &ix, const char *key, long dflt) {
+  auto it = ix.prf.find(key);
+  if (it == ix.prf.end() || it->second.empty()) return dflt;
+  return std::stol(it->second);
+}
+
+void upload(CapiIndex &ix) {
+  const size_t n = ix.n();
+  if (!ix.gpu) check(ngtgpu_index_create(&ix.gpu, 0, ix.prop.object_type, ix.prop.distance_type, (uint32_t)ix.prop.dimension));
+  if (n == 0) return;
+  check(ngtgpu_index_set_objects(ix.gpu, ix.objects.data(), n, 0, 0));
+  std::vector<uint32_t> removed;
+  for (size_t id = 1; id <= n; id++)
+    if (!ix.present[id]) removed.push_back((uint32_t)id);
+  if (!removed.empty()) check(ngtgpu_index_set_removed(ix.gpu, removed.data(), removed.size()));
+  if (ix.row_ptr.size() == n + 2) {
+    check(ngtgpu_index_set_graph(ix.gpu, ix.row_ptr.data(), ix.col.data(), 0));
+    check(ngtgpu_index_set_search_property(ix.gpu, ix.prop.edge_size_for_search, prf_long(ix, "DynamicEdgeSizeBase", 30),
+                                           prf_long(ix, "DynamicEdgeSizeRate", 20)));
+  }
+  uint32_t pivots = (uint32_t)std::min<size_t>(1024, n - removed.size());
+  if (pivots) check(ngtgpu_index_build_seed_table(ix.gpu, pivots, 1));
+}
+
+CapiIndex *open_index(const char *path) {
+  std::unique_ptr<CapiIndex> ix(new CapiIndex);
+  ix->path = path;
+  read_prf(*ix);
+  uint64_t slots = 0, pres = 0, gslots = 0, nnz = 0;
+  const std::string obj = ix->path + "/obj", grp = ix->path + "/grp";
+  check(ngtgpu_io_obj_info(obj.c_str(), (uint32_t)ix->record_bytes(), &slots, &pres));
+  const size_t n = slots ? slots - 1 : 0;
+  ix->objects.assign(n * ix->record_bytes(), 0);
+  ix->present.assign(n + 1, 0);
+  check(ngtgpu_io_read_obj(obj.c_str(), (uint32_t)ix->record_bytes(), ix->objects.data(), ix->present.data()));
+  check(ngtgpu_io_grp_info(grp.c_str(), &gslots, &nnz));
+  std::vector<uint64_t> rp(gslots + 1, 0);
+  ix->col.assign(nnz ? nnz : 1, 0);
+  ix->dist.assign(nnz ? nnz : 1, 0.f);
+  check(ngtgpu_io_read_grp(grp.c_str(), rp.data(), ix->col.data(), ix->dist.data(), nullptr));
+  ix->col.resize(nnz);
+  ix->dist.resize(nnz);
+  ix->row_ptr.assign(n + 2, nnz);
+  for (size_t i = 0; i < rp.size() && i < n + 2; i++) ix->row_ptr[i] = rp[i];
+  upload(*ix);
+  return ix.release();
+}
+
+void require_built(CapiIndex &ix) {
+  if (ix.pending) throw std::runtime_error("objects were appended: call ngt_create_index() before searching");
+  if (!ix.gpu || ix.n() == 0) throw std::runtime_error("the index holds no objects");
+}
+
+void fill_results(NGTObjectDistances results, const uint32_t *ids, const float *dists, uint32_t count) {
+  auto &r = *static_cast<std::vector<NGTObjectDistance> *>(results);
+  r.clear();   // the container is cleared and overwritten per call (Graph.cpp:631-635, ObjectSpace.h:49-57)
+  for (uint32_t i = 0; i < count; i++) r.push_back(NGTObjectDistance{ids[i], dists[i]});
+}
+
+void search_one(CapiIndex &ix, const float *q, int32_t dim, size_t size, float epsilon, float radius, int64_t edge_size,
+                NGTObjectDistances results) {
+  if (dim != ix.prop.dimension) throw std::runtime_error("ObjectSpace::allocateObject: the specified dimension is invalid");
+  require_built(ix);
+  if (ix.row_ptr.size() != ix.n() + 2) throw std::runtime_error("the index has no graph: call ngt_create_index()");
+  ngtgpu_search_params p = {(uint32_t)size, epsilon, radius >= FLT_MAX ? -1.0f : radius, edge_size};
+  std::vector<uint32_t> ids(size ? size : 1), cnt(1, 0);
+  std::vector<float> ds(size ? size : 1);
+  uint32_t seeds = (uint32_t)prf_long(ix, "SeedSize", 10);
+  if (seeds == 0) seeds = 10;
+  check(ngtgpu_search(ix.gpu, q, NGTGPU_OBJECT_FLOAT, 1, &p, nullptr, seeds, ids.data(), ds.data(), cnt.data(), nullptr));
+  fill_results(results, ids.data(), ds.data(), cnt[0]);
+}
+
+void linear_one(CapiIndex &ix, const float *q, int32_t dim, size_t size, float radius, NGTObjectDistances results) {
+  if (dim != ix.prop.dimension) throw std::runtime_error("ObjectSpace::allocateObject: the specified dimension is invalid");
+  if (!ix.gpu || ix.n() == 0) throw std::runtime_error("the index holds no objects");
+  std::vector<uint32_t> ids(size ? size : 1), cnt(1, 0);
+  std::vector<float> ds(size ? size : 1);
+  check(ngtgpu_linear_search(ix.gpu, q, NGTGPU_OBJECT_FLOAT, 1, (uint32_t)size, radius >= FLT_MAX ? -1.0f : radius, ids.data(),
+                             ds.data(), cnt.data()));
+  fill_results(results, ids.data(), ds.data(), cnt[0]);
+}
+
+ObjectID append_rows(CapiIndex &ix, const float *rows, size_t count, uint32_t dim) {
+  if ((int32_t)dim != ix.prop.dimension) throw std::runtime_error("ObjectSpace::allocateObject: the specified dimension is invalid");
+  const size_t rb = ix.record_bytes();
+  const size_t first = ix.n() + 1;
+  if (ix.present.empty()) ix.present.push_back(0);
+  const size_t old = ix.objects.size();
+  ix.objects.resize(old + count * rb);
+  for (size_t r = 0; r < count; r++) {
+    if (ix.prop.object_type == NGTGPU_OBJECT_UINT8) {
+      for (uint32_t j = 0; j < dim; j++) ix.objects[old + r * rb + j] = (uint8_t)rows[r * dim + j];   // ObjectRepository.h:222-258
+    } else {
+      if (normalizes(ix.prop.distance_type)) {
+        bool zero = true;
+        for (uint32_t j = 0; j < dim; j++) zero = zero && rows[r * dim + j] == 0.0f;
+        if (zero) throw std::runtime_error("ObjectSpace::normalize: Error! the object is an invalid zero vector for the cosine similarity or normalized distances.");
+      }
+      memcpy(&ix.objects[old + r * rb], rows + r * dim, rb);
+    }
+    ix.present.push_back(1);
+  }
+  if (normalizes(ix.prop.distance_type) && ix.raw_from == 0) ix.raw_from = first;
+  ix.pending += count;
+  return (ObjectID)first;
+}
+
+// NGT::Index::createIndex on the device: exact kNN of every object (ngtgpu_index_knn_graph), then the ANNG is the
+// symmetric closure of those lists (out-edges + reverse edges, sorted by (distance,id), duplicates dropped) -- what
+// insertANNGNode converges to (lib/NGT/Graph.h:611-626).
+void build_graph(CapiIndex &ix) {
+  const size_t n = ix.n();
+  if (n == 0) return;
+  if (!ix.gpu) check(ngtgpu_index_create(&ix.gpu, 0, ix.prop.object_type, ix.prop.distance_type, (uint32_t)ix.prop.dimension));
+  const size_t rb = ix.record_bytes();
+  if (ix.raw_from) {
+    // ObjectSpace::normalize (ObjectSpace.h:251-266) on the device for the newly appended rows
+    ngtgpu_index *tmp = nullptr;
+    check(ngtgpu_index_create(&tmp, 0, ix.prop.object_type, ix.prop.distance_type, (uint32_t)ix.prop.dimension));
+    int rc = ngtgpu_index_set_objects(tmp, &ix.objects[(ix.raw_from - 1) * rb], n - ix.raw_from + 1, 1, 0);
+    for (size_t id = ix.raw_from; rc == NGTGPU_OK && id <= n; id++)
+      rc = ngtgpu_index_get_object(tmp, (uint32_t)(id - ix.raw_from + 1), &ix.objects[(id - 1) * rb]);
+    ngtgpu_index_destroy(tmp);
+    check(rc);
+    ix.raw_from = 0;
+  }
+  check(ngtgpu_index_set_objects(ix.gpu, ix.objects.data(), n, 0, 0));
+  std::vector<uint32_t> removed;
+  for (size_t id = 1; id <= n; id++)
+    if (!ix.present[id]) removed.push_back((uint32_t)id);
+  if (!removed.empty()) check(ngtgpu_index_set_removed(ix.gpu, removed.data(), removed.size()));
+  size_t live = n - removed.size();
+  uint32_t k = (uint32_t)std::max<long>(1, std::min<long>(ix.prop.edge_size_for_creation, (long)live - 1));
+  uint32_t *d_ids = nullptr, *d_cnt = nullptr;
+  float *d_d = nullptr;
+  if (cudaMalloc(&d_ids, n * k * 4) != cudaSuccess || cudaMalloc(&d_d, n * k * 4) != cudaSuccess ||
+      cudaMalloc(&d_cnt, n * 4) != cudaSuccess)
+    throw std::runtime_error("cudaMalloc failed while building the graph");
+  int rc = NGTGPU_OK;
+  for (size_t s = 0; s < n && rc == NGTGPU_OK; s += 131072) {
+    uint32_t m = (uint32_t)std::min<size_t>(131072, n - s);
+    rc = ngtgpu_index_knn_graph(ix.gpu, k, (uint32_t)s + 1, m, d_ids + s * k, d_d + s * k, d_cnt + s, nullptr);
+  }
+  std::vector<uint32_t> ids(n * k), cnt(n);
+  std::vector<float> ds(n * k);
+  if (rc == NGTGPU_OK) {
+    cudaDeviceSynchronize();
+    cudaMemcpy(ids.data(), d_ids, n * k * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(ds.data(), d_d, n * k * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(cnt.data(), d_cnt, n * 4, cudaMemcpyDeviceToHost);
+  }
+  cudaFree(d_ids);
+  cudaFree(d_d);
+  cudaFree(d_cnt);
+  check(rc);
+  struct Edge {
+    uint32_t src, dst;
+    float d;
+  };
+  std::vector<Edge> edges;
+  edges.reserve(n * k * 2);
+  for (size_t i = 0; i < n; i++) {
+    if (!ix.present[i + 1]) continue;
+    for (uint32_t r = 0; r < cnt[i]; r++) {
+      edges.push_back({(uint32_t)i + 1, ids[i * k + r], ds[i * k + r]});
+      edges.push_back({ids[i * k + r], (uint32_t)i + 1, ds[i * k + r]});
+    }
+  }
+  std::sort(edges.begin(), edges.end(), [](const Edge &a, const Edge &b) {
+    if (a.src != b.src) return a.src < b.src;
+    if (a.d != b.d) return a.d < b.d;
+    return a.dst < b.dst;
+  });
+  ix.row_ptr.assign(n + 2, 0);
+  ix.col.clear();
+  ix.dist.clear();
+  for (size_t e = 0; e < edges.size(); e++) {
+    if (e && edges[e].src == edges[e - 1].src && edges[e].dst == edges[e - 1].dst) continue;
+    ix.col.push_back(edges[e].dst);
+    ix.dist.push_back(edges[e].d);
+    ix.row_ptr[edges[e].src + 1]++;
+  }
+  for (size_t i = 1; i < n + 2; i++) ix.row_ptr[i] += ix.row_ptr[i - 1];
+  ix.pending = 0;
+  ix.prf["GraphType"] = "ANNG";
+  check(ngtgpu_index_set_graph(ix.gpu, ix.row_ptr.data(), ix.col.data(), 0));
+  check(ngtgpu_index_set_search_property(ix.gpu, ix.prop.edge_size_for_search, prf_long(ix, "DynamicEdgeSizeBase", 30),
+                                         prf_long(ix, "DynamicEdgeSizeRate", 20)));
+  check(ngtgpu_index_build_seed_table(ix.gpu, (uint32_t)std::min<size_t>(1024, live), 1));
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---- error objects, Capi.cpp:784-812 --------------------------------------------------------------------
+NGTError ngt_create_error_object() {
+  try {
+    return static_cast<NGTError>(new std::string());
+  } catch (std::exception &err) {
+    std::cerr << "Capi : " << __FUNCTION__ << "() : Error: " << err.what();
+    return NULL;
+  }
+}
+const char *ngt_get_error_string(const NGTError error) { return static_cast<std::string *>(error)->c_str(); }
+void ngt_clear_error_string(NGTError error) { *static_cast<std::string *>(error) = ""; }
+void ngt_destroy_error_object(NGTError error) { delete static_cast<std::string *>(error); }
+
+// ---- properties, Capi.cpp:113-325 -----------------------------------------------------------------------
+NGTProperty ngt_create_property(NGTError error) {
+  try {
+    return static_cast<NGTProperty>(new CapiProperty());
+  }
+  CAPI_CATCH(NULL)
+}
+void ngt_destroy_property(NGTProperty prop) {
+  if (prop) delete static_cast<CapiProperty *>(prop);
+}
+#define PROP_CHECK(ret)                                                                                      \
+  if (prop == NULL) {                                                                                        \
+    std::stringstream ss;                                                                                    \
+    ss << "Capi : " << __FUNCTION__ << "() : parametor error: prop = " << prop;                              \
+    operate_error_string(ss, error);                                                                         \
+    return ret;                                                                                              \
+  }
+bool ngt_get_property(const NGTIndex index, NGTProperty prop, NGTError error) {
+  if (index == NULL || prop == NULL) {
+    std::stringstream ss;
+    ss << "Capi : " << __FUNCTION__ << "() : parametor error: index = " << index << " prop = " << prop;
+    operate_error_string(ss, error);
+    return false;
+  }
+  *static_cast<CapiProperty *>(prop) = static_cast<CapiIndex *>(index)->prop;
+  return true;
+}
+int32_t ngt_get_property_dimension(NGTProperty prop, NGTError error) { PROP_CHECK(-1) return static_cast<CapiProperty *>(prop)->dimension; }
+bool ngt_set_property_dimension(NGTProperty prop, int32_t value, NGTError error) { PROP_CHECK(false) static_cast<CapiProperty *>(prop)->dimension = value; return true; }
+bool ngt_set_property_edge_size_for_creation(NGTProperty prop, int16_t value, NGTError error) { PROP_CHECK(false) static_cast<CapiProperty *>(prop)->edge_size_for_creation = value; return true; }
+bool ngt_set_property_edge_size_for_search(NGTProperty prop, int16_t value, NGTError error) { PROP_CHECK(false) static_cast<CapiProperty *>(prop)->edge_size_for_search = value; return true; }
+int16_t ngt_get_property_edge_size_for_creation(NGTProperty prop, NGTError error) { PROP_CHECK(-1) return static_cast<CapiProperty *>(prop)->edge_size_for_creation; }
+int16_t ngt_get_property_edge_size_for_search(NGTProperty prop, NGTError error) { PROP_CHECK(-1) return static_cast<CapiProperty *>(prop)->edge_size_for_search; }
+int32_t ngt_get_property_object_type(NGTProperty prop, NGTError error) { PROP_CHECK(-1) return static_cast<CapiProperty *>(prop)->object_type; }
+int32_t ngt_get_property_distance_type(NGTProperty prop, NGTError error) { PROP_CHECK(-1) return static_cast<CapiProperty *>(prop)->distance_type; }
+bool ngt_is_property_object_type_float(int32_t t) { return t == NGTGPU_OBJECT_FLOAT; }
+bool ngt_is_property_object_type_integer(int32_t t) { return t == NGTGPU_OBJECT_UINT8; }
+bool ngt_set_property_object_type_float(NGTProperty prop, NGTError error) { PROP_CHECK(false) static_cast<CapiProperty *>(prop)->object_type = NGTGPU_OBJECT_FLOAT; return true; }
+bool ngt_set_property_object_type_integer(NGTProperty prop, NGTError error) { PROP_CHECK(false) static_cast<CapiProperty *>(prop)->object_type = NGTGPU_OBJECT_UINT8; return true; }
+#define SET_DISTANCE(fn, value)                                                                              \
+  bool fn(NGTProperty prop, NGTError error) { PROP_CHECK(false) static_cast<CapiProperty *>(prop)->distance_type = value; return true; }
+SET_DISTANCE(ngt_set_property_distance_type_l1, 0)
+SET_DISTANCE(ngt_set_property_distance_type_l2, NGTGPU_DISTANCE_L2)
+SET_DISTANCE(ngt_set_property_distance_type_angle, NGTGPU_DISTANCE_ANGLE)
+SET_DISTANCE(ngt_set_property_distance_type_hamming, NGTGPU_DISTANCE_HAMMING)
+SET_DISTANCE(ngt_set_property_distance_type_jaccard, 7)
+SET_DISTANCE(ngt_set_property_distance_type_cosine, NGTGPU_DISTANCE_COSINE)
+SET_DISTANCE(ngt_set_property_distance_type_normalized_angle, NGTGPU_DISTANCE_NORMALIZED_ANGLE)
+SET_DISTANCE(ngt_set_property_distance_type_normalized_cosine, NGTGPU_DISTANCE_NORMALIZED_COSINE)
+
+// ---- index life cycle, Capi.cpp:40-111, 694-711 ------------------------------------------------------------
+NGTIndex ngt_open_index(const char *index_path, NGTError error) {
+  try {
+    return static_cast<NGTIndex>(open_index(index_path));
+  }
+  CAPI_CATCH(NULL)
+}
+NGTIndex ngt_open_index_as_read_only(const char *index_path, NGTError error) { return ngt_open_index(index_path, error); }
+
+static NGTIndex create_empty(const char *database, NGTProperty prop, NGTError error, const char *fn) {
+  try {
+    if (prop == NULL) throw std::runtime_error("property is NULL");
+    std::unique_ptr<CapiIndex> ix(new CapiIndex);
+    ix->prop = *static_cast<CapiProperty *>(prop);
+    ix->prf = default_prf();
+    ix->present.push_back(0);
+    ix->row_ptr.assign(2, 0);
+    if (database) {
+      ix->path = database;
+      mkdir(database, 0755);
+      write_prf(*ix, ix->path);
+      check(ngtgpu_io_write_obj((ix->path + "/obj").c_str(), (uint32_t)ix->record_bytes(), nullptr, 0, nullptr));
+      check(ngtgpu_io_write_grp((ix->path + "/grp").c_str(), 0, ix->row_ptr.data(), nullptr, nullptr, nullptr));
+    }
+    check(ngtgpu_index_create(&ix->gpu, 0, ix->prop.object_type, ix->prop.distance_type, (uint32_t)ix->prop.dimension));
+    return static_cast<NGTIndex>(ix.release());
+  } catch (std::exception &err) {
+    std::stringstream ss;
+    ss << "Capi : " << fn << "() : Error: " << err.what();
+    operate_error_string(ss, error);
+    return NULL;
+  }
+}
+NGTIndex ngt_create_graph_and_tree(const char *database, NGTProperty prop, NGTError error) {
+  return create_empty(database, prop, error, __FUNCTION__);
+}
+NGTIndex ngt_create_graph_and_tree_in_memory(NGTProperty prop, NGTError error) {
+  return create_empty(nullptr, prop, error, __FUNCTION__);
+}
+
+bool ngt_save_index(const NGTIndex index, const char *database, NGTError error) {
+  if (index == NULL || database == NULL) {
+    std::stringstream ss;
+    ss << "Capi : " << __FUNCTION__ << "() : parametor error: index = " << index << " database = " << database;
+    operate_error_string(ss, error);
+    return false;
+  }
+  try {
+    CapiIndex &ix = *static_cast<CapiIndex *>(index);
+    if (ix.pending) throw std::runtime_error("objects were appended: call ngt_create_index() before ngt_save_index()");
+    mkdir(database, 0755);
+    write_prf(ix, database);
+    const std::string d(database);
+    check(ngtgpu_io_write_obj((d + "/obj").c_str(), (uint32_t)ix.record_bytes(), ix.objects.data(), ix.n(), ix.present.data()));
+    check(ngtgpu_io_write_grp((d + "/grp").c_str(), ix.n(), ix.row_ptr.data(), ix.col.data(), ix.dist.data(), ix.present.data()));
+  }
+  CAPI_CATCH(false)
+  return true;
+}
+
+void ngt_close_index(NGTIndex index) {
+  if (index == NULL) return;
+  CapiIndex *ix = static_cast<CapiIndex *>(index);
+  if (ix->gpu) ngtgpu_index_destroy(ix->gpu);
+  delete ix;
+}
+
+// ---- results, Capi.cpp:541-578 ---------------------------------------------------------------------------
+NGTObjectDistances ngt_create_empty_results(NGTError error) {
+  try {
+    return static_cast<NGTObjectDistances>(new std::vector<NGTObjectDistance>());
+  }
+  CAPI_CATCH(NULL)
+}
+void ngt_destroy_results(NGTObjectDistances results) {
+  if (results) delete static_cast<std::vector<NGTObjectDistance> *>(results);
+}
+uint32_t ngt_get_result_size(NGTObjectDistances results, NGTError error) {
+  if (results == NULL) {
+    std::stringstream ss;
+    ss << "Capi : " << __FUNCTION__ << "() : parametor error: results = " << results;
+    operate_error_string(ss, error);
+    return 0;
+  }
+  return (uint32_t) static_cast<std::vector<NGTObjectDistance> *>(results)->size();
+}
+int32_t ngt_get_size(NGTObjectDistances results, NGTError error) {   // deprecated twin
+  if (results == NULL) {
+    std::stringstream ss;
+    ss << "Capi : " << __FUNCTION__ << "() : parametor error: results = " << results;
+    operate_error_string(ss, error);
+    return -1;
+  }
+  return (int32_t) static_cast<std::vector<NGTObjectDistance> *>(results)->size();
+}
+NGTObjectDistance ngt_get_result(const NGTObjectDistances results, const uint32_t i, NGTError error) {
+  try {
+    return static_cast<std::vector<NGTObjectDistance> *>(results)->at(i);
+  } catch (std::exception &err) {
+    std::stringstream ss;
+    ss << "Capi : " << __FUNCTION__ << "() : Error: " << err.what();
+    operate_error_string(ss, error);
+    NGTObjectDistance e = {0, 0};
+    return e;
+  }
+}
+
+// ---- search, Capi.cpp:327-539 ------------------------------------------------------------------------------
+#define SEARCH_ARGCHECK(qptr)                                                                               \
+  if (index == NULL || qptr == NULL || results == NULL || query_dim <= 0) {                                 \
+    std::stringstream ss;                                                                                   \
+    ss << "Capi : " << __FUNCTION__ << "() : parametor error: index = " << index << " query = " << (const void *)qptr \
+       << " results = " << results << " query_dim = " << query_dim;                                         \
+    operate_error_string(ss, error);                                                                        \
+    return false;                                                                                           \
+  }
+
+bool ngt_search_index(NGTIndex index, double *query, int32_t query_dim, size_t size, float epsilon, float radius,
+                      NGTObjectDistances results, NGTError error) {
+  SEARCH_ARGCHECK(query)
+  try {
+    if (radius < 0.0) radius = FLT_MAX;   // Capi.cpp:384-386
+    std::vector<float> q(query, query + query_dim);
+    search_one(*static_cast<CapiIndex *>(index), q.data(), query_dim, size, epsilon, radius, -1, results);
+  }
+  CAPI_CATCH(false)
+  return true;
+}
+bool ngt_search_index_as_float(NGTIndex index, float *query, int32_t query_dim, size_t size, float epsilon, float radius,
+                               NGTObjectDistances results, NGTError error) {
+  SEARCH_ARGCHECK(query)
+  try {
+    if (radius < 0.0) radius = FLT_MAX;
+    search_one(*static_cast<CapiIndex *>(index), query, query_dim, size, epsilon, radius, -1, results);
+  }
+  CAPI_CATCH(false)
+  return true;
+}
+bool ngt_search_index_with_query(NGTIndex index, NGTQuery query, NGTObjectDistances results, NGTError error) {
+  if (index == NULL || query.query == NULL || results == NULL) {
+    std::stringstream ss;
+    ss << "Capi : " << __FUNCTION__ << "() : parametor error: index = " << index << " query = " << (const void *)query.query
+       << " results = " << results;
+    operate_error_string(ss, error);
+    return false;
+  }
+  try {
+    CapiIndex &ix = *static_cast<CapiIndex *>(index);
+    if (query.accuracy > 0.0f) throw std::runtime_error("expected accuracy needs the AccuracyTable of the index; it is not supported by this engine, use epsilon");
+    float radius = query.radius < 0.0 ? FLT_MAX : query.radius;
+    int64_t es = query.edge_size == (size_t)INT_MIN ? -1 : (int64_t)(int)query.edge_size;
+    search_one(ix, query.query, ix.prop.dimension, query.size, query.epsilon, radius, es, results);
+  }
+  CAPI_CATCH(false)
+  return true;
+}
+bool ngt_linear_search_index(NGTIndex index, double *query, int32_t query_dim, size_t size, NGTObjectDistances results,
+                             NGTError error) {
+  SEARCH_ARGCHECK(query)
+  try {
+    std::vector<float> q(query, query + query_dim);
+    linear_one(*static_cast<CapiIndex *>(index), q.data(), query_dim, size, FLT_MAX, results);
+  }
+  CAPI_CATCH(false)
+  return true;
+}
+bool ngt_linear_search_index_as_float(NGTIndex index, float *query, int32_t query_dim, size_t size, NGTObjectDistances results,
+                                      NGTError error) {
+  SEARCH_ARGCHECK(query)
+  try {
+    linear_one(*static_cast<CapiIndex *>(index), query, query_dim, size, FLT_MAX, results);
+  }
+  CAPI_CATCH(false)
+  return true;
+}
+bool ngt_linear_search_index_with_query(NGTIndex index, NGTQuery query, NGTObjectDistances results, NGTError error) {
+  if (index == NULL || query.query == NULL || results == NULL) {
+    std::stringstream ss;
+    ss << "Capi : " << __FUNCTION__ << "() : parametor error: index = " << index << " query = " << (const void *)query.query
+       << " results = " << results;
+    operate_error_string(ss, error);
+    return false;
+  }
+  try {
+    CapiIndex &ix = *static_cast<CapiIndex *>(index);
+    linear_one(ix, query.query, ix.prop.dimension, query.size, query.radius < 0.0 ? FLT_MAX : query.radius, results);
+  }
+  CAPI_CATCH(false)
+  return true;
+}
+
+// ---- additive batch entry points: nq queries at once, flat outputs -------------
+bool ngt_batch_search_index_as_float(NGTIndex index, const float *queries, uint32_t nq, int32_t query_dim, size_t size,
+                                     float epsilon, float radius, int64_t edge_size, uint32_t *ids, float *dists,
+                                     uint32_t *counts, NGTError error) {
+  if (index == NULL || queries == NULL || ids == NULL || dists == NULL || counts == NULL || query_dim <= 0) {
+    std::stringstream ss;
+    ss << "Capi : " << __FUNCTION__ << "() : parametor error: index = " << index << " queries = " << (const void *)queries;
+    operate_error_string(ss, error);
+    return false;
+  }
+  try {
+    CapiIndex &ix = *static_cast<CapiIndex *>(index);
+    if (query_dim != ix.prop.dimension) throw std::runtime_error("ObjectSpace::allocateObject: the specified dimension is invalid");
+    require_built(ix);
+    ngtgpu_search_params p = {(uint32_t)size, epsilon, radius, edge_size};
+    uint32_t seeds = (uint32_t)prf_long(ix, "SeedSize", 10);
+    check(ngtgpu_search(ix.gpu, queries, NGTGPU_OBJECT_FLOAT, nq, &p, nullptr, seeds ? seeds : 10, ids, dists, counts, nullptr));
+  }
+  CAPI_CATCH(false)
+  return true;
+}
+bool ngt_batch_linear_search_index_as_float(NGTIndex index, const float *queries, uint32_t nq, int32_t query_dim, size_t size,
+                                            float radius, uint32_t *ids, float *dists, uint32_t *counts, NGTError error) {
+  if (index == NULL || queries == NULL || ids == NULL || dists == NULL || counts == NULL || query_dim <= 0) {
+    std::stringstream ss;
+    ss << "Capi : " << __FUNCTION__ << "() : parametor error: index = " << index << " queries = " << (const void *)queries;
+    operate_error_string(ss, error);
+    return false;
+  }
+  try {
+    CapiIndex &ix = *static_cast<CapiIndex *>(index);
+    if (query_dim != ix.prop.dimension) throw std::runtime_error("ObjectSpace::allocateObject: the specified dimension is invalid");
+    if (!ix.gpu || ix.n() == 0) throw std::runtime_error("the index holds no objects");
+    check(ngtgpu_linear_search(ix.gpu, queries, NGTGPU_OBJECT_FLOAT, nq, (uint32_t)size, radius, ids, dists, counts));
+  }
+  CAPI_CATCH(false)
+  return true;
+}
+
+// ---- insertion and construction, Capi.cpp:580-711 ---------------------------------------------------------
+ObjectID ngt_append_index_as_float(NGTIndex index, float *obj, uint32_t obj_dim, NGTError error) {
+  if (index == NULL || obj == NULL || obj_dim == 0) {
+    std::stringstream ss;
+    ss << "Capi : " << __FUNCTION__ << "() : parametor error: index = " << index << " obj = " << (void *)obj << " obj_dim = " << obj_dim;
+    operate_error_string(ss, error);
+    return 0;
+  }
+  try {
+    return append_rows(*static_cast<CapiIndex *>(index), obj, 1, obj_dim);
+  }
+  CAPI_CATCH(0)
+}
+ObjectID ngt_insert_index_as_float(NGTIndex index, float *obj, uint32_t obj_dim, NGTError error) {
+  return ngt_append_index_as_float(index, obj, obj_dim, error);
+}
+ObjectID ngt_append_index(NGTIndex index, double *obj, uint32_t obj_dim, NGTError error) {
+  if (index == NULL || obj == NULL || obj_dim == 0) {
+    std::stringstream ss;
+    ss << "Capi : " << __FUNCTION__ << "() : parametor error: index = " << index << " obj = " << (void *)obj << " obj_dim = " << obj_dim;
+    operate_error_string(ss, error);
+    return 0;
+  }
+  try {
+    std::vector<float> v(obj, obj + obj_dim);
+    return append_rows(*static_cast<CapiIndex *>(index), v.data(), 1, obj_dim);
+  }
+  CAPI_CATCH(0)
+}
+ObjectID ngt_insert_index(NGTIndex index, double *obj, uint32_t obj_dim, NGTError error) {
+  return ngt_append_index(index, obj, obj_dim, error);
+}
+bool ngt_batch_append_index(NGTIndex index, float *obj, uint32_t data_count, NGTError error) {
+  if (index == NULL || obj == NULL) {
+    std::stringstream ss;
+    ss << "Capi : " << __FUNCTION__ << "() : parametor error: index = " << index << " obj = " << (void *)obj;
+    operate_error_string(ss, error);
+    return false;
+  }
+  try {
+    CapiIndex &ix = *static_cast<CapiIndex *>(index);
+    append_rows(ix, obj, data_count, (uint32_t)ix.prop.dimension);
+  }
+  CAPI_CATCH(false)
+  return true;
+}
+bool ngt_batch_insert_index(NGTIndex index, float *obj, uint32_t data_count, uint32_t *ids, NGTError error) {
+  if (index == NULL || obj == NULL) {
+    std::stringstream ss;
+    ss << "Capi : " << __FUNCTION__ << "() : parametor error: index = " << index << " obj = " << (void *)obj;
+    operate_error_string(ss, error);
+    return false;
+  }
+  try {
+    CapiIndex &ix = *static_cast<CapiIndex *>(index);
+    ObjectID first = append_rows(ix, obj, data_count, (uint32_t)ix.prop.dimension);
+    if (ids)
+      for (uint32_t i = 0; i < data_count; i++) ids[i] = first + i;
+  }
+  CAPI_CATCH(false)
+  return true;
+}
+bool ngt_create_index(NGTIndex index, uint32_t pool_size, NGTError error) {
+  if (index == NULL) {
+    std::stringstream ss;
+    ss << "Capi : " << __FUNCTION__ << "() : parametor error: idnex = " << index;
+    operate_error_string(ss, error);
+    return false;
+  }
+  try {
+    (void)pool_size;   // the thread pool of the reference (Index.cpp:737-741) is replaced by device batching
+    build_graph(*static_cast<CapiIndex *>(index));
+  }
+  CAPI_CATCH(false)
+  return true;
+}
+bool ngt_remove_index(NGTIndex index, ObjectID id, NGTError error) {
+  if (index == NULL) {
+    std::stringstream ss;
+    ss << "Capi : " << __FUNCTION__ << "() : parametor error: index = " << index;
+    operate_error_string(ss, error);
+    return false;
+  }
+  try {
+    CapiIndex &ix = *static_cast<CapiIndex *>(index);
+    if (id == 0 || id > ix.n() || !ix.present[id]) throw std::runtime_error("remove: the specified object does not exist. ID=" + std::to_string(id));
+    ix.present[id] = 0;
+    if (ix.row_ptr.size() == ix.n() + 2) {
+      std::vector<uint64_t> rp(ix.n() + 2, 0);
+      std::vector<uint32_t> col;
+      std::vector<float> dist;
+      for (size_t s = 1; s <= ix.n(); s++) {
+        rp[s] = col.size();
+        if (s != id)
+          for (uint64_t e = ix.row_ptr[s]; e < ix.row_ptr[s + 1]; e++)
+            if (ix.col[e] != id) {
+              col.push_back(ix.col[e]);
+              dist.push_back(ix.dist[e]);
+            }
+      }
+      rp[ix.n() + 1] = col.size();
+      ix.row_ptr.swap(rp);
+      ix.col.swap(col);
+      ix.dist.swap(dist);
+    }
+    upload(ix);
+  }
+  CAPI_CATCH(false)
+  return true;
+}
+
+// ---- objects and edges, Capi.cpp:713-782, 1006-1040 ----------------------------------------------------------
+NGTObjectSpace ngt_get_object_space(NGTIndex index, NGTError error) {
+  if (index == NULL) {
+    std::stringstream ss;
+    ss << "Capi : " << __FUNCTION__ << "() : parametor error: idnex = " << index;
+    operate_error_string(ss, error);
+    return NULL;
+  }
+  return index;   // the object space of this engine lives in the index handle
+}
+float *ngt_get_object_as_float(NGTObjectSpace object_space, ObjectID id, NGTError error) {
+  try {
+    if (object_space == NULL) throw std::runtime_error("object space is NULL");
+    CapiIndex &ix = *static_cast<CapiIndex *>(object_space);
+    if (ix.prop.object_type != NGTGPU_OBJECT_FLOAT) throw std::runtime_error("the object type is not float");
+    if (id == 0 || id > ix.n() || !ix.present[id]) throw std::runtime_error("ObjectSpace::getObject: the object does not exist. ID=" + std::to_string(id));
+    return reinterpret_cast<float *>(&ix.objects[(size_t)(id - 1) * ix.record_bytes()]);   // points into the index, as Capi.cpp:750-765
+  }
+  CAPI_CATCH(NULL)
+}
+uint8_t *ngt_get_object_as_integer(NGTObjectSpace object_space, ObjectID id, NGTError error) {
+  try {
+    if (object_space == NULL) throw std::runtime_error("object space is NULL");
+    CapiIndex &ix = *static_cast<CapiIndex *>(object_space);
+    if (ix.prop.object_type != NGTGPU_OBJECT_UINT8) throw std::runtime_error("the object type is not integer");
+    if (id == 0 || id > ix.n() || !ix.present[id]) throw std::runtime_error("ObjectSpace::getObject: the object does not exist. ID=" + std::to_string(id));
+    return &ix.objects[(size_t)(id - 1) * ix.record_bytes()];
+  }
+  CAPI_CATCH(NULL)
+}
+bool ngt_get_edges(NGTIndex index, ObjectID id, NGTObjectDistances edges, NGTError error) {
+  if (index == NULL || edges == NULL) {
+    std::stringstream ss;
+    ss << "Capi : " << __FUNCTION__ << "() : parametor error: index = " << index << " edges = " << edges;
+    operate_error_string(ss, error);
+    return false;
+  }
+  try {
+    CapiIndex &ix = *static_cast<CapiIndex *>(index);
+    if (id == 0 || id > ix.n() || ix.row_ptr.size() != ix.n() + 2) throw std::runtime_error("the specified node does not exist. ID=" + std::to_string(id));
+    auto &r = *static_cast<std::vector<NGTObjectDistance> *>(edges);
+    r.clear();
+    for (uint64_t e = ix.row_ptr[id]; e < ix.row_ptr[id + 1]; e++) r.push_back(NGTObjectDistance{ix.col[e], ix.dist[e]});
+  }
+  CAPI_CATCH(false)
+  return true;
+}
+uint32_t ngt_get_object_repository_size(NGTIndex index, NGTError error) {
+  if (index == NULL) {
+    std::stringstream ss;
+    ss << "Capi : " << __FUNCTION__ << "() : parametor error: index = " << index;
+    operate_error_string(ss, error);
+    return 0;
+  }
+  return (uint32_t) static_cast<CapiIndex *>(index)->present.size();
+}
+
+// ---- outside the hot path: refused loudly ------------------------------------------------------------------
+static bool unsupported(const char *fn, NGTError error) {
+  std::stringstream ss;
+  ss << "Capi : " << fn << "() : Error: not provided by the B200 engine (outside the search / construction hot path)";
+  operate_error_string(ss, error);
+  return false;
+}
+bool ngt_refine_anng(NGTIndex, float, float, int, int, size_t, NGTError error) { return unsupported(__FUNCTION__, error); }
+NGTOptimizer ngt_create_optimizer(bool, NGTError error) {
+  unsupported(__FUNCTION__, error);
+  return NULL;
+}
+bool ngt_optimizer_adjust_search_coefficients(NGTOptimizer, const char *, NGTError error) { return unsupported(__FUNCTION__, error); }
+bool ngt_optimizer_execute(NGTOptimizer, const char *, const char *, NGTError error) { return unsupported(__FUNCTION__, error); }
+void ngt_destroy_optimizer(NGTOptimizer) {}
+
+}  // extern "C"

@@ -1,0 +1,77 @@
+"""ctypes declarations of NGT's C API (lib/NGT/Capi.h:28-212) as python/ngt/base.py binds it, against any library
+that exports it -- here ngt_b200/libngtgpu.so."""
+import ctypes as C
+
+import numpy as np
+
+
+class ObjectDistance(C.Structure):
+    _fields_ = [("id", C.c_uint32), ("distance", C.c_float)]
+
+
+class Query(C.Structure):
+    _fields_ = [("query", C.POINTER(C.c_float)), ("size", C.c_size_t), ("epsilon", C.c_float), ("accuracy", C.c_float),
+                ("radius", C.c_float), ("edge_size", C.c_size_t)]
+
+
+def bind(path):
+    lib = C.CDLL(path)
+    P, F, D = C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_double)
+    sig = {
+        "ngt_create_error_object": (P, []), "ngt_get_error_string": (C.c_char_p, [P]), "ngt_clear_error_string": (None, [P]),
+        "ngt_destroy_error_object": (None, [P]),
+        "ngt_create_property": (P, [P]), "ngt_destroy_property": (None, [P]), "ngt_get_property": (C.c_bool, [P, P, P]),
+        "ngt_get_property_dimension": (C.c_int32, [P, P]), "ngt_set_property_dimension": (C.c_bool, [P, C.c_int32, P]),
+        "ngt_set_property_edge_size_for_creation": (C.c_bool, [P, C.c_int16, P]),
+        "ngt_set_property_edge_size_for_search": (C.c_bool, [P, C.c_int16, P]),
+        "ngt_get_property_edge_size_for_creation": (C.c_int16, [P, P]), "ngt_get_property_edge_size_for_search": (C.c_int16, [P, P]),
+        "ngt_get_property_object_type": (C.c_int32, [P, P]), "ngt_get_property_distance_type": (C.c_int32, [P, P]),
+        "ngt_is_property_object_type_float": (C.c_bool, [C.c_int32]), "ngt_is_property_object_type_integer": (C.c_bool, [C.c_int32]),
+        "ngt_set_property_object_type_float": (C.c_bool, [P, P]), "ngt_set_property_object_type_integer": (C.c_bool, [P, P]),
+        "ngt_set_property_distance_type_l2": (C.c_bool, [P, P]), "ngt_set_property_distance_type_cosine": (C.c_bool, [P, P]),
+        "ngt_set_property_distance_type_hamming": (C.c_bool, [P, P]),
+        "ngt_set_property_distance_type_normalized_cosine": (C.c_bool, [P, P]),
+        "ngt_open_index": (P, [C.c_char_p, P]), "ngt_create_graph_and_tree": (P, [C.c_char_p, P, P]),
+        "ngt_create_graph_and_tree_in_memory": (P, [P, P]), "ngt_save_index": (C.c_bool, [P, C.c_char_p, P]),
+        "ngt_close_index": (None, [P]),
+        "ngt_create_empty_results": (P, [P]), "ngt_destroy_results": (None, [P]), "ngt_get_result_size": (C.c_uint32, [P, P]),
+        "ngt_get_size": (C.c_int32, [P, P]), "ngt_get_result": (ObjectDistance, [P, C.c_uint32, P]),
+        "ngt_search_index": (C.c_bool, [P, D, C.c_int32, C.c_size_t, C.c_float, C.c_float, P, P]),
+        "ngt_search_index_as_float": (C.c_bool, [P, F, C.c_int32, C.c_size_t, C.c_float, C.c_float, P, P]),
+        "ngt_search_index_with_query": (C.c_bool, [P, Query, P, P]),
+        "ngt_linear_search_index": (C.c_bool, [P, D, C.c_int32, C.c_size_t, P, P]),
+        "ngt_linear_search_index_as_float": (C.c_bool, [P, F, C.c_int32, C.c_size_t, P, P]),
+        "ngt_linear_search_index_with_query": (C.c_bool, [P, Query, P, P]),
+        "ngt_insert_index": (C.c_uint32, [P, D, C.c_uint32, P]), "ngt_append_index": (C.c_uint32, [P, D, C.c_uint32, P]),
+        "ngt_insert_index_as_float": (C.c_uint32, [P, F, C.c_uint32, P]), "ngt_append_index_as_float": (C.c_uint32, [P, F, C.c_uint32, P]),
+        "ngt_batch_append_index": (C.c_bool, [P, F, C.c_uint32, P]),
+        "ngt_batch_insert_index": (C.c_bool, [P, F, C.c_uint32, C.POINTER(C.c_uint32), P]),
+        "ngt_create_index": (C.c_bool, [P, C.c_uint32, P]), "ngt_remove_index": (C.c_bool, [P, C.c_uint32, P]),
+        "ngt_get_object_space": (P, [P, P]), "ngt_get_object_as_float": (F, [P, C.c_uint32, P]),
+        "ngt_get_object_as_integer": (C.POINTER(C.c_uint8), [P, C.c_uint32, P]),
+        "ngt_get_edges": (C.c_bool, [P, C.c_uint32, P, P]), "ngt_get_object_repository_size": (C.c_uint32, [P, P]),
+        "ngt_refine_anng": (C.c_bool, [P, C.c_float, C.c_float, C.c_int, C.c_int, C.c_size_t, P]),
+        # additive batch entry points
+        "ngt_batch_search_index_as_float": (C.c_bool, [P, F, C.c_uint32, C.c_int32, C.c_size_t, C.c_float, C.c_float, C.c_int64,
+                                                       C.POINTER(C.c_uint32), F, C.POINTER(C.c_uint32), P]),
+        "ngt_batch_linear_search_index_as_float": (C.c_bool, [P, F, C.c_uint32, C.c_int32, C.c_size_t, C.c_float,
+                                                              C.POINTER(C.c_uint32), F, C.POINTER(C.c_uint32), P]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    lib._signatures = sig
+    return lib
+
+
+def fptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def results_of(lib, r, err):
+    n = lib.ngt_get_result_size(r, err)
+    out = []
+    for i in range(n):
+        o = lib.ngt_get_result(r, i, err)
+        out.append((int(o.id), float(np.float32(o.distance))))
+    return out

@@ -1,0 +1,123 @@
+"""NGT's C API (lib/NGT/Capi.h) served by libngtgpu.so, driven the way python/ngt/base.py drives libngt:
+open an index the REFERENCE built (tests/golden/idx200: prf/obj/grp/tre written by `ngt create`), search it, and
+the create -> append -> build -> save -> reopen cycle; answers compared with the reference's own C API on the same
+index (tests/golden/idx200_answers.json)."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+import capi
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from ngt_b200 import _lib
+    return capi.bind(_lib.SO_PATH)
+
+
+def test_open_reference_built_index_and_search(lib, sift5k):
+    ans = json.load(open(os.path.join(GOLDEN, "idx200_answers.json")))
+    err = lib.ngt_create_error_object()
+    ix = lib.ngt_open_index(os.path.join(GOLDEN, "idx200").encode(), err)
+    assert ix, lib.ngt_get_error_string(err)
+    prop = lib.ngt_create_property(err)
+    assert lib.ngt_get_property(ix, prop, err)
+    assert lib.ngt_get_property_dimension(prop, err) == 128 and lib.ngt_get_property_distance_type(prop, err) == 1
+    assert lib.ngt_is_property_object_type_float(lib.ngt_get_property_object_type(prop, err))
+    assert lib.ngt_get_object_repository_size(ix, err) == 201
+    qs = sift5k["queries"].astype(np.float32)
+    for qi, q in enumerate(qs):
+        q = np.ascontiguousarray(q)
+        r = lib.ngt_create_empty_results(err)
+        assert lib.ngt_linear_search_index_as_float(ix, capi.fptr(q), 128, 5, r, err), lib.ngt_get_error_string(err)
+        got = capi.results_of(lib, r, err)
+        assert [g[0] for g in got] == [a[0] for a in ans["linear"][qi]]
+        assert [np.float32(g[1]) for g in got] == [np.float32(a[1]) for a in ans["linear"][qi]]     # bit-exact: integer-valued data
+        # graph search (double* entry point, as base.py calls it): on 200 objects at epsilon 0.3 both find the exact answer
+        qd = q.astype(np.float64)
+        assert lib.ngt_search_index(ix, qd.ctypes.data_as(C.POINTER(C.c_double)), 128, 5, 0.3, -1.0, r, err)
+        assert capi.results_of(lib, r, err) == [(a[0], float(np.float32(a[1]))) for a in ans["graph"][qi]]
+        # NGTQuery form
+        nq = capi.Query(capi.fptr(q), 5, 0.3, -1.0, -1.0, C.c_size_t(-2**31 & (2**64 - 1)))
+        assert lib.ngt_search_index_with_query(ix, nq, r, err), lib.ngt_get_error_string(err)
+        assert [g[0] for g in capi.results_of(lib, r, err)] == [a[0] for a in ans["graph"][qi]]
+        lib.ngt_destroy_results(r)
+    # stored objects and edges are what the reference wrote
+    sp = lib.ngt_get_object_space(ix, err)
+    row = np.ctypeslib.as_array(lib.ngt_get_object_as_float(sp, 7, err), shape=(128,))
+    assert (row == sift5k["data"][6].astype(np.float32)).all()
+    e = lib.ngt_create_empty_results(err)
+    assert lib.ngt_get_edges(ix, 7, e, err)
+    edges = capi.results_of(lib, e, err)
+    assert len(edges) >= 10 and all(edges[i][1] <= edges[i + 1][1] for i in range(len(edges) - 1))
+    # misuse: wrong dimension -> false + message, nothing crashes
+    r = lib.ngt_create_empty_results(err)
+    assert lib.ngt_search_index_as_float(ix, capi.fptr(qs[0]), 64, 5, 0.1, -1.0, r, err) is False
+    assert lib.ngt_get_error_string(err).decode().startswith("Capi : ngt_search_index_as_float() : Error: ")
+    # batch entry point == the single-query answers
+    ids = np.zeros((3, 5), np.uint32)
+    ds = np.zeros((3, 5), np.float32)
+    cnt = np.zeros(3, np.uint32)
+    q3 = np.ascontiguousarray(qs)
+    assert lib.ngt_batch_linear_search_index_as_float(ix, capi.fptr(q3), 3, 128, 5, -1.0, ids.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                      capi.fptr(ds), cnt.ctypes.data_as(C.POINTER(C.c_uint32)), err)
+    assert (cnt == 5).all() and ids.tolist() == [[a[0] for a in ans["linear"][i]] for i in range(3)]
+    assert lib.ngt_batch_search_index_as_float(ix, capi.fptr(q3), 3, 128, 5, 0.3, -1.0, -1, ids.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                               capi.fptr(ds), cnt.ctypes.data_as(C.POINTER(C.c_uint32)), err)
+    assert ids.tolist() == [[a[0] for a in ans["graph"][i]] for i in range(3)]
+    lib.ngt_close_index(ix)
+    lib.ngt_destroy_property(prop)
+    lib.ngt_destroy_error_object(err)
+
+
+def test_create_append_build_save_reopen(lib, tmp_path):
+    from ngt_b200 import synth
+    err = lib.ngt_create_error_object()
+    prop = lib.ngt_create_property(err)
+    assert lib.ngt_set_property_dimension(prop, 128, err) and lib.ngt_set_property_edge_size_for_creation(prop, 12, err)
+    assert lib.ngt_set_property_object_type_float(prop, err) and lib.ngt_set_property_distance_type_l2(prop, err)
+    path = str(tmp_path / "idx").encode()
+    ix = lib.ngt_create_graph_and_tree(path, prop, err)
+    assert ix, lib.ngt_get_error_string(err)
+    base = synth.make("sift", 3000, 1)
+    assert lib.ngt_batch_append_index(ix, capi.fptr(base[:2999]), 2999, err)
+    one = base[2999].astype(np.float64)
+    assert lib.ngt_insert_index(ix, one.ctypes.data_as(C.POINTER(C.c_double)), 128, err) == 3000
+    r = lib.ngt_create_empty_results(err)
+    q = synth.make("sift", 2, 2)
+    assert lib.ngt_search_index_as_float(ix, capi.fptr(q[0]), 128, 5, 0.1, -1.0, r, err) is False     # not built yet
+    assert b"ngt_create_index" in lib.ngt_get_error_string(err)
+    assert lib.ngt_create_index(ix, 8, err), lib.ngt_get_error_string(err)
+    d = np.linalg.norm(base - q[0], axis=1)
+    exact = (np.argsort(d, kind="stable")[:5] + 1).tolist()
+    assert lib.ngt_linear_search_index_as_float(ix, capi.fptr(q[0]), 128, 5, r, err)
+    assert [g[0] for g in capi.results_of(lib, r, err)] == exact
+    assert lib.ngt_search_index_as_float(ix, capi.fptr(q[0]), 128, 5, 0.3, -1.0, r, err)
+    assert [g[0] for g in capi.results_of(lib, r, err)] == exact
+    assert lib.ngt_remove_index(ix, exact[0], err)
+    assert lib.ngt_search_index_as_float(ix, capi.fptr(q[0]), 128, 5, 0.3, -1.0, r, err)
+    assert exact[0] not in [g[0] for g in capi.results_of(lib, r, err)]
+    assert lib.ngt_save_index(ix, path, err), lib.ngt_get_error_string(err)
+    lib.ngt_close_index(ix)
+    again = lib.ngt_open_index(path, err)
+    assert again, lib.ngt_get_error_string(err)
+    assert lib.ngt_search_index_as_float(again, capi.fptr(q[0]), 128, 5, 0.3, -1.0, r, err)
+    assert [g[0] for g in capi.results_of(lib, r, err)] == [i for i in (np.argsort(d, kind="stable")[:6] + 1).tolist() if i != exact[0]]
+    lib.ngt_close_index(again)
+    # the files are NGT's own format: the reference CLI opens them when it is available on this box
+    ref_ngt = os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "_ref", "ngt")
+    if os.path.exists(ref_ngt):
+        import subprocess
+        qf = str(tmp_path / "q.tsv")
+        np.savetxt(qf, q[:1], fmt="%g", delimiter="\t")
+        out = subprocess.run([ref_ngt, "search", "-i", "s", "-n", "5", path.decode(), qf], capture_output=True, text=True)
+        assert out.returncode == 0, out.stderr
+    lib.ngt_destroy_results(r)
+    lib.ngt_destroy_property(prop)
+    lib.ngt_destroy_error_object(err)

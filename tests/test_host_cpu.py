@@ -190,3 +190,56 @@ def test_reconstruct_graph_matches_the_reference():
         assert (orp.numpy() == z[key + "_row_ptr"].astype(np.int64)).all(), key
         assert (ocol.numpy().astype(np.uint32) == z[key + "_col"]).all(), key
         assert (odist.numpy().view(np.uint32) == z[key + "_dist"].view(np.uint32)).all(), key
+
+
+def test_ngt_c_api_symbols_and_error_convention():
+    """lib/NGT/Capi.h entry points of the hot path are exported under their own names, and the error convention
+    is the reference's (lib/NGT/Capi.cpp:25-38): message into the NGTError string, sentinel return value.
+    The expected strings for misuse come from the reference itself (tests/golden/idx200_answers.json)."""
+    import json
+    import capi
+    from conftest import GOLDEN
+    from ngt_b200 import _lib
+    lib = capi.bind(_lib.SO_PATH)              # AttributeError here = a Capi.h function is missing
+    assert len(lib._signatures) >= 50
+    err = lib.ngt_create_error_object()
+    assert err and lib.ngt_get_error_string(err) == b""
+    ref = json.load(open(os.path.join(GOLDEN, "idx200_answers.json")))["errors"]
+    # a NULL index: same "parametor error" format as the reference
+    res = lib.ngt_create_empty_results(err)
+    q = np.zeros(128, np.float32)
+    assert lib.ngt_search_index_as_float(None, capi.fptr(q), 128, 5, 0.1, -1.0, res, err) is False
+    msg = lib.ngt_get_error_string(err).decode()
+    assert msg.startswith("Capi : ngt_search_index_as_float() : parametor error: index = 0 query = ")
+    assert ref["null_index"][1].startswith("Capi : ngt_search_index_as_float() : parametor error: index = 0 query = ")
+    assert msg.endswith("query_dim = 128") and ref["null_index"][1].endswith("query_dim = 128")
+    # a path that does not exist: NULL + "Capi : ngt_open_index() : Error: ... Cannot load the property file <path>/prf."
+    assert lib.ngt_open_index(b"/nonexistent/idx", err) is None
+    msg = lib.ngt_get_error_string(err).decode()
+    assert msg.startswith("Capi : ngt_open_index() : Error: ") and msg.endswith("PropertySet::load: Cannot load the property file /nonexistent/idx/prf.")
+    assert ref["bad_path"][1].endswith("PropertySet::load: Cannot load the property file /nonexistent/idx/prf.")
+    lib.ngt_clear_error_string(err)
+    assert lib.ngt_get_error_string(err) == b""
+    # results containers and properties work without a device
+    assert lib.ngt_get_result_size(res, err) == 0 and lib.ngt_get_size(res, err) == 0
+    o = lib.ngt_get_result(res, 3, err)
+    assert (o.id, o.distance) == (0, 0.0) and lib.ngt_get_error_string(err).decode().startswith("Capi : ngt_get_result() : Error: ")
+    prop = lib.ngt_create_property(err)
+    assert lib.ngt_set_property_dimension(prop, 96, err) and lib.ngt_get_property_dimension(prop, err) == 96
+    assert lib.ngt_set_property_edge_size_for_creation(prop, 12, err) and lib.ngt_get_property_edge_size_for_creation(prop, err) == 12
+    assert lib.ngt_get_property_edge_size_for_search(prop, err) == 40        # Graph.h:401 default
+    assert lib.ngt_set_property_object_type_integer(prop, err)
+    assert lib.ngt_is_property_object_type_integer(lib.ngt_get_property_object_type(prop, err))
+    assert lib.ngt_set_property_distance_type_hamming(prop, err) and lib.ngt_get_property_distance_type(prop, err) == 2
+    assert lib.ngt_get_property_dimension(None, err) == -1
+    # outside the hot path: refused, loudly
+    assert lib.ngt_refine_anng(None, 0.1, 0.0, 0, 0, 100, err) is False
+    assert "not provided by the B200 engine" in lib.ngt_get_error_string(err).decode()
+    import torch
+    if not torch.cuda.is_available():
+        # no device: opening a real index fails with a message, it does not fall back to the CPU
+        assert lib.ngt_open_index(os.path.join(GOLDEN, "idx200").encode(), err) is None
+        assert "no CUDA device" in lib.ngt_get_error_string(err).decode()
+    lib.ngt_destroy_property(prop)
+    lib.ngt_destroy_results(res)
+    lib.ngt_destroy_error_object(err)
