@@ -60,27 +60,52 @@ __global__ void tc_check_exact_kernel(const float *__restrict__ rows, uint64_t c
 
 // One thread per (row, 16-byte unit of the packed K axis). side 0 = query operand [hi|hi|lo], 1 = row operand
 // [hi|lo|hi]. The unit is written where SWIZZLE_128B puts it: byte r*128 + ((u ^ (r & 7)) * 16) of the 16 KB tile.
+// fold != 0 (L2): the row operand is scaled by -2 (exact in bf16) and one more k-chunk carries the squared norms,
+// each split into three bf16 parts, against ones on the other side:
+//     A extra = [qn0 qn1 qn2 1 1 1 0 ...],  B extra = [1 1 1 rn0 rn1 rn2 0 ...]
+// so the accumulator IS ||q||^2 + ||x||^2 - 2 q.x and the epilogue only compares. Padding / empty rows get a huge
+// finite norm (3e38) and can never pass.
 __global__ void tc_pack_kernel(const float *__restrict__ rows, uint64_t n_rows, uint32_t padded_dim, int side,
-                               uint32_t nseg, uint32_t kchunks, uint8_t *__restrict__ tiles) {
+                               uint32_t nseg, uint32_t kchunks, int fold, const float *__restrict__ norms,
+                               uint8_t *__restrict__ tiles) {
   const uint64_t units_per_row = (uint64_t)kchunks * 8;
   const uint64_t n_pad = (n_rows + TC_TILE - 1) / TC_TILE * TC_TILE;
   const uint64_t total = n_pad * units_per_row;
+  const uint32_t fold_unit = (kchunks - 1) * 8;   // first unit of the extra chunk
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t row = i / units_per_row;
     const uint32_t U = (uint32_t)(i % units_per_row);
-    const uint32_t kappa = U * 8;
-    const uint32_t seg = kappa / padded_dim, d0 = kappa % padded_dim;
     __nv_bfloat16 v[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) v[j] = __float2bfloat16_rn(0.f);
-    if (row < n_rows && seg < nseg) {
-      const float *src = rows + row * padded_dim + d0;
-      const bool want_lo = side == 0 ? seg == 2 : seg == 1;
+    if (fold && U >= fold_unit) {
+      if (U == fold_unit) {
+        float nrm = norms[row];
+        if (!(nrm < 3.0e38f)) nrm = 3.0e38f;
+        const __nv_bfloat16 p0 = __float2bfloat16_rn(nrm);
+        const float r1 = nrm - __bfloat162float(p0);
+        const __nv_bfloat16 p1 = __float2bfloat16_rn(r1);
+        const __nv_bfloat16 p2 = __float2bfloat16_rn(r1 - __bfloat162float(p1));
+        const __nv_bfloat16 one = __float2bfloat16_rn(1.0f);
+        if (side == 0) {
+          v[0] = p0; v[1] = p1; v[2] = p2; v[3] = one; v[4] = one; v[5] = one;
+        } else {
+          v[0] = one; v[1] = one; v[2] = one; v[3] = p0; v[4] = p1; v[5] = p2;
+        }
+      }
+    } else {
+      const uint32_t kappa = U * 8;
+      const uint32_t seg = kappa / padded_dim, d0 = kappa % padded_dim;
+      if (row < n_rows && seg < nseg) {
+        const float *src = rows + row * padded_dim + d0;
+        const bool want_lo = side == 0 ? seg == 2 : seg == 1;
+        const float scale = (fold && side == 1) ? -2.0f : 1.0f;
 #pragma unroll
-      for (int j = 0; j < 8; j++) {
-        const float x = src[j];
-        const __nv_bfloat16 hi = __float2bfloat16_rn(x);
-        v[j] = want_lo ? __float2bfloat16_rn(x - __bfloat162float(hi)) : hi;
+        for (int j = 0; j < 8; j++) {
+          const float x = src[j];
+          const __nv_bfloat16 hi = __float2bfloat16_rn(x);
+          v[j] = __float2bfloat16_rn(scale * (want_lo ? x - __bfloat162float(hi) : __bfloat162float(hi)));
+        }
       }
     }
     const uint64_t tile = row / TC_TILE;
@@ -88,6 +113,18 @@ __global__ void tc_pack_kernel(const float *__restrict__ rows, uint64_t n_rows, 
     uint8_t *dst = tiles + (tile * kchunks + c) * (uint64_t)TC_TILE_BYTES + r * 128 + ((u ^ (r & 7)) * 16);
     *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(v);
   }
+}
+
+// largest finite squared norm of the rows (bounds the filter's error margin per query)
+__global__ void tc_max_norm_kernel(const float *__restrict__ norms, uint64_t n, float *out) {
+  float m = 0.f;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    float v = norms[i];
+    if (v < 3.0e38f && v > m) m = v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int *>(out), __float_as_int(m));   // non-negative floats order like ints
 }
 
 // squared norms (plain fp32: they only feed the filter); +inf marks padding and empty slots
@@ -191,6 +228,8 @@ struct TcArgs {
   uint32_t k;
   int mode;                 // 0 L2, 1 dot (normalised kinds), 2 cosine
   float rel_margin;         // error bound of the bf16 product, relative to ||q||^2+||x||^2 (L2) or absolute (similarities)
+  float max_row_norm;       // MODE 0: largest ||x||^2, the margin of a query is 2 * rel_margin * (||q||^2 + max_row_norm)
+  uint32_t stages;          // ring depth (2..TC_STAGES)
   int exclude_self;
   uint32_t self_base;       // row index (0-based) of query 0 when queries are stored rows
   uint32_t qtiles;
@@ -268,7 +307,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_filter_kernel(const TcAr
 
   uint8_t *sA = smem;                                              // kchunks x 16 KB (resident)
   uint8_t *sB = smem + (size_t)a.kchunks * TC_TILE_BYTES;         // TC_STAGES x 16 KB ring
-  float *heap = reinterpret_cast<float *>(sB + (size_t)TC_STAGES * TC_TILE_BYTES);   // [k][128]
+  float *heap = reinterpret_cast<float *>(sB + (size_t)a.stages * TC_TILE_BYTES);   // [k][128]
   uint32_t *state = reinterpret_cast<uint32_t *>(heap + (size_t)a.k * 128);          // [3][128]
 
   if (tid == 0) {
@@ -302,8 +341,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_filter_kernel(const TcAr
       uint64_t it = 0;
       for (uint64_t t = 0; t < ntiles; t++) {
         for (uint32_t c = 0; c < a.kchunks; c++, it++) {
-          const uint32_t st = (uint32_t)(it % TC_STAGES);
-          tc_mbar_wait(&bar_empty[st], (uint32_t)((it / TC_STAGES) & 1) ^ 1u);
+          const uint32_t st = (uint32_t)(it % a.stages);
+          tc_mbar_wait(&bar_empty[st], (uint32_t)((it / a.stages) & 1) ^ 1u);
           tc_mbar_expect_tx(&bar_full[st], TC_TILE_BYTES);
           tc_bulk_load(sB + (size_t)st * TC_TILE_BYTES, a.b_tiles + ((size_t)(t_begin + t) * a.kchunks + c) * TC_TILE_BYTES,
                        TC_TILE_BYTES, &bar_full[st]);
@@ -324,8 +363,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_filter_kernel(const TcAr
         tc_mbar_wait(&bar_tempty[acc], (uint32_t)((t >> 1) & 1) ^ 1u);
         tc_fence_after();
         for (uint32_t c = 0; c < a.kchunks; c++, it++) {
-          const uint32_t st = (uint32_t)(it % TC_STAGES);
-          tc_mbar_wait(&bar_full[st], (uint32_t)((it / TC_STAGES) & 1));
+          const uint32_t st = (uint32_t)(it % a.stages);
+          tc_mbar_wait(&bar_full[st], (uint32_t)((it / a.stages) & 1));
           tc_fence_after();
 #pragma unroll
           for (uint32_t s = 0; s < TC_KCHUNK / 16; s++) {
@@ -343,7 +382,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_filter_kernel(const TcAr
     const uint32_t q = qtile * TC_TILE + tid;       // tid in [0,128)
     const bool q_ok = q < a.nq;
     const float qn = a.a_norms[(size_t)qtile * TC_TILE + tid];
-    float thr = q_ok ? __int_as_float(0x7f800000) : -__int_as_float(0x7f800000);   // k-th smallest approximate score so far
+    // k-th smallest approximate score so far; "nothing yet" is a large finite number so that the huge scores of
+    // padding / empty rows (3e38) never pass
+    float thr = q_ok ? 1.0e37f : -__int_as_float(0x7f800000);
     float *H = heap + tid;                           // H[i * 128]
     uint32_t *st = state + tid;
     st[0] = 0u;
@@ -352,6 +393,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_filter_kernel(const TcAr
     uint32_t *mycand = a.cand + ((size_t)q * a.nsplit + split) * TC_CAND_CAP;
     const uint32_t skip_row = a.exclude_self ? a.self_base + q : 0xffffffffu;
     const float m2 = 2.0f * a.rel_margin;
+    const float mq = m2 * (qn + a.max_row_norm);   // MODE 0: per-query bound of twice the error
     for (uint64_t t = 0; t < ntiles; t++) {
       const uint32_t acc = (uint32_t)(t & 1);
       tc_mbar_wait(&bar_tfull[acc], (uint32_t)((t >> 1) & 1));
@@ -364,36 +406,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_filter_kernel(const TcAr
       for (uint32_t cb = 0; cb < 4; cb++) {
         tc_tmem_wait_ld();
         if (cb + 1 < 4) tc_tmem_ld32(taddr + (cb + 1) * 32, v[(cb + 1) & 1]);   // next 32 columns in flight under this block
-        const float4 *rn4 = reinterpret_cast<const float4 *>(a.b_norms + row0 + cb * 32);
         const uint32_t rbase = (uint32_t)(row0 + cb * 32);
         // branch-free pass over the 32 columns against a snapshot of the threshold (it only shrinks, so the
         // snapshot test admits a superset; tc_push re-checks), then the rare hits one by one
         float sc[32];
         uint32_t mask = 0;
-        const float thr0 = thr;
+        if (MODE == 0) {
+          // the accumulator already is ||q||^2 + ||x||^2 - 2 q.x (norms folded into the GEMM): compare only
+          const float thr2 = thr + mq;
 #pragma unroll
-        for (int j4 = 0; j4 < 8; j4++) {
-          const float4 rnv = __ldg(rn4 + j4);
-          const float rns[4] = {rnv.x, rnv.y, rnv.z, rnv.w};
+          for (int j = 0; j < 32; j++) {
+            sc[j] = __uint_as_float(v[cb & 1][j]);
+            mask |= (sc[j] <= thr2) ? (1u << j) : 0u;
+          }
+        } else {
+          const float4 *rn4 = reinterpret_cast<const float4 *>(a.b_norms + row0 + cb * 32);
+          const float thr0 = thr;
 #pragma unroll
-          for (int jj = 0; jj < 4; jj++) {
-            const int j = j4 * 4 + jj;
-            const float rn = rns[jj];   // +inf for padding and empty slots: never passes
-            const float dot = __uint_as_float(v[cb & 1][j]);
-            float score, lower;         // lower = score minus twice the error bound
-            if (MODE == 0) {
-              const float nn = qn + rn;
-              score = fmaf(-2.0f, dot, nn);
-              lower = fmaf(-m2, nn, score);
-            } else if (MODE == 1) {
-              score = rn < 3.0e38f ? -dot : __int_as_float(0x7fc00000);   // NaN never passes
-              lower = score - m2;
-            } else {
-              score = rn < 3.0e38f ? -dot * rsqrtf(qn * rn) : __int_as_float(0x7fc00000);
-              lower = score - m2;
+          for (int j4 = 0; j4 < 8; j4++) {
+            const float4 rnv = __ldg(rn4 + j4);
+            const float rns[4] = {rnv.x, rnv.y, rnv.z, rnv.w};
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) {
+              const int j = j4 * 4 + jj;
+              const float rn = rns[jj];   // +inf for padding and empty slots: never passes
+              const float dot = __uint_as_float(v[cb & 1][j]);
+              float score;
+              if (MODE == 1) score = rn < 3.0e38f ? -dot : __int_as_float(0x7fc00000);   // NaN never passes
+              else score = rn < 3.0e38f ? -dot * rsqrtf(qn * rn) : __int_as_float(0x7fc00000);
+              sc[j] = score;
+              mask |= (score - m2 <= thr0) ? (1u << j) : 0u;
             }
-            sc[j] = score;
-            mask |= (lower <= thr0) ? (1u << j) : 0u;
           }
         }
         if (mask) {
@@ -404,9 +447,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_filter_kernel(const TcAr
             const int j = __ffs(mask) - 1;
             mask &= mask - 1;
             const float score = loc[j];
-            float lower;
-            if (MODE == 0) lower = fmaf(-m2, qn + __ldg(a.b_norms + rbase + j), score);
-            else lower = score - m2;
+            const float lower = score - (MODE == 0 ? mq : m2);
             if (lower <= thr) thr = tc_push(score, rbase + j, H, st, a.k, mycand, skip_row, thr);
           }
         }
@@ -529,15 +570,19 @@ static cudaError_t launch_rerank(int group, const RerankArgs &a, cudaStream_t st
 }
 
 // ---- host side -------------------------------------------------------------------------------------------
-static int tc_pack(ngtgpu_index *ix, const float *d_rows, uint64_t n_rows, int side, uint32_t nseg, uint32_t first_id,
+static uint32_t tc_kchunks(const ngtgpu_index *ix, uint32_t nseg, int fold) {
+  return (nseg * ix->padded_dim + TC_KCHUNK - 1) / TC_KCHUNK + (fold ? 1 : 0);
+}
+
+static int tc_pack(ngtgpu_index *ix, const float *d_rows, uint64_t n_rows, int side, uint32_t nseg, int fold, uint32_t first_id,
                    const uint8_t *d_valid, uint8_t *tiles, float *norms, cudaStream_t stream) {
-  const uint32_t kchunks = (nseg * ix->padded_dim + TC_KCHUNK - 1) / TC_KCHUNK;
+  const uint32_t kchunks = tc_kchunks(ix, nseg, fold);
   const uint64_t n_pad = (n_rows + TC_TILE - 1) / TC_TILE * TC_TILE;
   uint64_t total = n_pad * kchunks * 8;
   unsigned blocks = (unsigned)((total + 255) / 256 > (uint64_t)ix->sm_count * 64 ? (uint64_t)ix->sm_count * 64 : (total + 255) / 256);
-  tc_pack_kernel<<<blocks, 256, 0, stream>>>(d_rows, n_rows, ix->padded_dim, side, nseg, kchunks, tiles);
-  CUDA_TRY(cudaGetLastError());
   tc_norms_kernel<<<ix->sm_count * 8, 256, 0, stream>>>(d_rows, n_rows, ix->padded_dim, first_id, d_valid, norms);
+  CUDA_TRY(cudaGetLastError());
+  tc_pack_kernel<<<blocks, 256, 0, stream>>>(d_rows, n_rows, ix->padded_dim, side, nseg, kchunks, fold, norms, tiles);
   CUDA_TRY(cudaGetLastError());
   ix->launches += 2;
   return NGTGPU_OK;
@@ -578,18 +623,26 @@ int ngtgpu_scan_topk_tc(ngtgpu_index *ix, const ScanParams &p, cudaStream_t stre
     bool exact = all_bf16_exact(ix, rows, p.n_rows * ix->padded_dim, d_flag, stream, &rc);
     if (rc != NGTGPU_OK) return rc;
     uint32_t nseg = exact ? 1 : 3;
-    if (nseg * ix->padded_dim > TC_MAX_KCHUNKS * TC_KCHUNK) return NGTGPU_OK;   // resident query operand would not fit
-    const uint32_t kchunks = (nseg * ix->padded_dim + TC_KCHUNK - 1) / TC_KCHUNK;
+    const int fold = ix->acc_kind == ACC_F_L2 ? 1 : 0;   // L2: norms ride in the GEMM
+    const uint32_t kchunks = tc_kchunks(ix, nseg, fold);
+    if (kchunks > TC_MAX_KCHUNKS + 1) return NGTGPU_OK;   // resident query operand would not fit
     const uint64_t n_tiles = (p.n_rows + TC_TILE - 1) / TC_TILE;
     if (ix->d_tc_tiles) cudaFree(ix->d_tc_tiles);
     if (ix->d_tc_norms) cudaFree(ix->d_tc_norms);
     ix->d_tc_tiles = nullptr;
     ix->d_tc_norms = nullptr;
     CUDA_TRY(cudaMalloc(&ix->d_tc_tiles, n_tiles * kchunks * (size_t)TC_TILE_BYTES));
-    CUDA_TRY(cudaMalloc(&ix->d_tc_norms, n_tiles * TC_TILE * sizeof(float)));
-    NGTGPU_TRY(tc_pack(ix, rows, p.n_rows, 1, nseg, p.first_row_id, p.d_valid, ix->d_tc_tiles, ix->d_tc_norms, stream));
+    CUDA_TRY(cudaMalloc(&ix->d_tc_norms, (n_tiles * TC_TILE + 64) * sizeof(float)));
+    NGTGPU_TRY(tc_pack(ix, rows, p.n_rows, 1, nseg, fold, p.first_row_id, p.d_valid, ix->d_tc_tiles, ix->d_tc_norms, stream));
+    float *d_max = ix->d_tc_norms + n_tiles * TC_TILE;
+    CUDA_TRY(cudaMemsetAsync(d_max, 0, sizeof(float), stream));
+    tc_max_norm_kernel<<<ix->sm_count * 4, 256, 0, stream>>>(ix->d_tc_norms, n_tiles * TC_TILE, d_max);
+    ix->launches++;
+    CUDA_TRY(cudaMemcpyAsync(&ix->tc_max_norm, d_max, sizeof(float), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
     ix->tc_nseg = nseg;
     ix->tc_kchunks = kchunks;
+    ix->tc_fold = fold;
     ix->tc_rows_valid = true;
   }
   uint32_t nseg = ix->tc_nseg;
@@ -606,7 +659,7 @@ int ngtgpu_scan_topk_tc(ngtgpu_index *ix, const ScanParams &p, cudaStream_t stre
   float *a_norms = nullptr;
   NGTGPU_TRY(ngtgpu_scratch(ix, SCR_TC_QUERY, (size_t)qtiles * kchunks * TC_TILE_BYTES + (size_t)qtiles * TC_TILE * 4, (void **)&a_tiles));
   a_norms = reinterpret_cast<float *>(a_tiles + (size_t)qtiles * kchunks * TC_TILE_BYTES);
-  NGTGPU_TRY(tc_pack(ix, qrows, p.nq, 0, nseg, 0, nullptr, a_tiles, a_norms, stream));
+  NGTGPU_TRY(tc_pack(ix, qrows, p.nq, 0, nseg, ix->tc_fold, 0, nullptr, a_tiles, a_norms, stream));
 
   TcArgs a;
   memset(&a, 0, sizeof(a));
@@ -619,7 +672,8 @@ int ngtgpu_scan_topk_tc(ngtgpu_index *ix, const ScanParams &p, cudaStream_t stre
   a.kchunks = kchunks;
   a.k = p.k;
   a.mode = ix->acc_kind == ACC_F_L2 ? 0 : ix->acc_kind == ACC_F_DOT ? 1 : 2;
-  a.rel_margin = nseg == 1 ? 2.0e-6f : 1.0e-4f;
+  a.rel_margin = nseg == 1 ? 4.0e-6f : 1.0e-4f;
+  a.max_row_norm = ix->tc_max_norm;
   a.exclude_self = p.exclude_self;
   a.self_base = p.self_base - p.first_row_id;
   a.qtiles = qtiles;
@@ -637,7 +691,13 @@ int ngtgpu_scan_topk_tc(ngtgpu_index *ix, const ScanParams &p, cudaStream_t stre
   uint32_t *d_over = a.cand_n + (size_t)p.nq * a.nsplit;
   CUDA_TRY(cudaMemsetAsync(d_over, 0, 4, stream));
 
-  const size_t smem = (size_t)kchunks * TC_TILE_BYTES + (size_t)TC_STAGES * TC_TILE_BYTES + (size_t)(p.k + 3) * 128 * 4 + 1024;
+  // ring depth: as many 16 KB stages as fit beside the resident query operand and the heaps (2..TC_STAGES)
+  const size_t fixed_smem = (size_t)kchunks * TC_TILE_BYTES + (size_t)(p.k + 3) * 128 * 4 + 1024;
+  uint32_t stages = TC_STAGES;
+  while (stages > 2 && fixed_smem + (size_t)stages * TC_TILE_BYTES > 225 * 1024) stages--;
+  if (fixed_smem + (size_t)stages * TC_TILE_BYTES > 225 * 1024) return NGTGPU_OK;
+  a.stages = stages;
+  const size_t smem = fixed_smem + (size_t)stages * TC_TILE_BYTES;
   if (a.mode == 0) {
     CUDA_TRY(cudaFuncSetAttribute(knn_tc_filter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     knn_tc_filter_kernel<0><<<qtiles * a.nsplit, TC_THREADS, smem, stream>>>(a);

@@ -101,6 +101,8 @@ struct ngtgpu_index {
   uint8_t *d_tc_tiles = nullptr;
   float *d_tc_norms = nullptr;
   uint32_t tc_nseg = 0, tc_kchunks = 0;
+  int tc_fold = 0;                     // L2: squared norms folded into the GEMM as an extra k-chunk
+  float tc_max_norm = 0.f;
   uint64_t tc_batches = 0;             // batches answered by the tensor-core path
   uint32_t *d_prof = nullptr;          // development aid: per-phase cycle counters of the traversal kernel
   bool timing = false;
