@@ -96,13 +96,16 @@ int ngtgpu_traverse(ngtgpu_index *ix, const uint8_t *d_queries, uint32_t nq, con
   const size_t res_bytes = k > 32 ? (((size_t)k * 8 + 15) & ~(size_t)15) : 0;
   // staging area of the TMA row gather: as many rows as fit the budget, 4..64
   // (split evenly between the 4 warps: a multiple of 4, and of 4 x rows-per-instruction for short rows)
-  uint32_t stage_rows = ix->stage_bytes / ix->row_bytes;
-  const uint32_t unit = 4 * (32 / ix->group);
+  // (rows of the register-query kernels are staged at a stride of 512 * CPL bytes)
+  const uint32_t stage_row = (l.group == 32 && l.cpl > 0) ? 512u * (uint32_t)l.cpl : ix->row_bytes;
+  uint32_t stage_rows = ix->stage_bytes / stage_row;
+  // (the fold8 kernels, CPL 1-2, read whole blocks of 8 slots per warp: a multiple of 32 rows)
+  const uint32_t unit = (l.group == 32 && l.cpl > 0 && l.cpl <= 2) ? 32 : 4 * (32 / ix->group);
   if (stage_rows > 128) stage_rows = 128;
   stage_rows = stage_rows / unit * unit;
   if (stage_rows < unit) stage_rows = unit;
   a.stage_rows = stage_rows;
-  const size_t stage_bytes = ((size_t)stage_rows * ix->row_bytes + 127) & ~(size_t)127;
+  const size_t stage_bytes = ((size_t)stage_rows * stage_row + 127) & ~(size_t)127;
   const size_t extra = stage_bytes + res_bytes + (l.cpl == 0 ? ix->row_bytes : 0);
   uint32_t tier_bits[2] = {ix->hash_bits, 17};
   uint32_t tier_queue[2] = {ix->queue_cap, 4096};

@@ -97,6 +97,15 @@ __device__ __forceinline__ void cp_async_row16(void *smem_dst, const void *gsrc)
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc)
                : "memory");
 }
+// the same with the destination already a 32-bit shared-window address (no generic->shared conversion per call)
+__device__ __forceinline__ void cp_async_s16(uint32_t smem_addr, const void *gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ uint4 lds16(uint32_t smem_addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(smem_addr));
+  return r;
+}
 __device__ __forceinline__ void cp_async_commit_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
@@ -263,7 +272,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
   // ---- carve dynamic shared memory: [staging][results k>32][queue][query copy (CPL==0)]
   uint8_t *sp = smem_raw;
   uint8_t *stage = sp;
-  sp += ((size_t)a.stage_rows * a.row_bytes + 127) & ~(size_t)127;
+  sp += ((size_t)a.stage_rows * ((G == 32 && CPL > 0) ? 512u * (CPL > 0 ? CPL : 1) : a.row_bytes) + 127) & ~(size_t)127;
   uint64_t *s_results = reinterpret_cast<uint64_t *>(sp);
   sp += a.k > 32 ? (((size_t)a.k * 8 + 15) & ~(size_t)15) : 0;
   uint64_t *queue;
@@ -282,6 +291,12 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
   const bool ordered = a.coef < 1.0f;           // negative epsilon: keep the reference's element order
   const bool use_head = a.edge_cap <= SEARCH_HEAD;
 
+  if (G == 32 && CPL > 0) {
+    // padded tails of staged rows (chunks >= row chunks) are never written by the copies: make them zero once
+    uint4 *z = reinterpret_cast<uint4 *>(stage);
+    for (uint32_t i = tid; i < a.stage_rows * (512u * (CPL > 0 ? CPL : 1)) / 16; i += SEARCH_THREADS) z[i] = zero16();
+    __syncthreads();
+  }
   for (;;) {
     // ---- next query (dynamic scheduling over a persistent grid)
     if (tid == 0) {
@@ -620,7 +635,12 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
       // between copying a row and reading it.
       {
         const uint32_t wrows = a.stage_rows / SEARCH_WARPS;
-        uint8_t *wstage = stage + (size_t)warp * wrows * a.row_bytes;
+        // rows of the register-query path (G == 32, CPL > 0) are staged at a compile-time stride of 512 * CPL bytes
+        // (>= row_bytes; the tail was zeroed once at kernel start), so shared addresses are 32-bit constants + shifts
+        constexpr uint32_t SROW = 512u * (CPL > 0 ? CPL : 1);
+        const uint32_t srow_bytes = (G == 32 && CPL > 0) ? SROW : a.row_bytes;
+        uint8_t *wstage = stage + (size_t)warp * wrows * srow_bytes;
+        const uint32_t wstage_s = (uint32_t)__cvta_generic_to_shared(wstage) + (uint32_t)lane * 16u;
         for (uint32_t j0 = warp * wrows; j0 < cn; j0 += SEARCH_WARPS * wrows) {
           const uint32_t nr = cn - j0 < wrows ? cn - j0 : wrows;
           if (G == 32 && CPL > 0) {
@@ -628,15 +648,14 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
             // all rows are issued back to back
             const uint32_t my_id = (uint32_t)lane < nr ? s_cand_ids[j0 + lane] : 0u;
             const uint8_t *lane_src = a.objects + (size_t)lane * 16;
-            uint8_t *lane_dst = wstage + (size_t)lane * 16;
 #pragma unroll 8
             for (uint32_t r = 0; r < nr; r++) {
               const uint32_t id = __shfl_sync(0xffffffffu, my_id, (int)r);
               const uint8_t *srow = lane_src + (size_t)id * a.row_bytes;
-              uint8_t *drow = lane_dst + (size_t)r * a.row_bytes;
+              const uint32_t drow = wstage_s + r * SROW;
 #pragma unroll
               for (int c = 0; c < NCH; c++)
-                if ((uint32_t)lane + c * 32 < a.chunks) cp_async_row16(drow + c * 512, srow + c * 512);
+                if (c < NCH - 1 || (uint32_t)lane + c * 32 < a.chunks) cp_async_s16(drow + c * 512, srow + c * 512);
             }
           } else if (G == 32) {
             for (uint32_t r = 0; r < nr; r++) {
@@ -661,20 +680,17 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
           cp_async_commit_wait_all();
           __syncwarp();
           if (CPL > 0 && CPL <= 2 && G == 32) {
-            // eight rows at a time, folded together (fold8)
+            // eight rows at a time, folded together (fold8). Slots past the slice's last row hold stale rows of
+            // earlier rounds (or the initial zeros): they are read like the others and their result is dropped;
+            // chunks past the row's end read the zeroed tail. No predicates and no address selects in the loop.
             for (uint32_t r0 = 0; r0 < nr; r0 += 8) {
               Sums s[8];
+              const uint32_t ra = wstage_s + r0 * SROW;
 #pragma unroll
               for (int i = 0; i < 8; i++) {
                 s[i] = zero_sums();
-                if (r0 + i < nr) {
-                  const uint4 *rp = reinterpret_cast<const uint4 *>(wstage + (size_t)(r0 + i) * a.row_bytes);
 #pragma unroll
-                  for (int c = 0; c < NCH; c++) {
-                    const uint32_t ch = lane + c * 32;
-                    if (ch < a.chunks) acc_chunk<ACC>(s[i], qreg[c], rp[ch]);
-                  }
-                }
+                for (int c = 0; c < NCH; c++) acc_chunk<ACC>(s[i], qreg[c], lds16(ra + i * SROW + c * 512));
               }
               Sums tot = zero_sums();
               if (ACC == ACC_U8_L2 || ACC == ACC_U8_HAM) {
@@ -703,7 +719,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
           } else if (G == 32) {
             // long rows: one row at a time (query chunks in registers, or in shared memory when CPL == 0)
             for (uint32_t r = 0; r < nr; r++) {
-              const uint4 *rp = reinterpret_cast<const uint4 *>(wstage + (size_t)r * a.row_bytes);
+              const uint4 *rp = reinterpret_cast<const uint4 *>(wstage + (size_t)r * srow_bytes);
               Sums s = zero_sums();
               if (CPL > 0) {
 #pragma unroll
