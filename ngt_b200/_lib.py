@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libngtgpu.so")
+SO_PATH = os.environ.get("NGTGPU_SO", os.path.join(HERE, "libngtgpu.so"))   # NGTGPU_SO: development builds of the same library
 
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_STATE, ERR_ZERO_VECTOR = range(6)
 

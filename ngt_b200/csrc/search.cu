@@ -100,8 +100,9 @@ int ngtgpu_traverse(ngtgpu_index *ix, const uint8_t *d_queries, uint32_t nq, con
   const uint32_t stage_row = (l.group == 32 && l.cpl > 0) ? 512u * (uint32_t)l.cpl : ix->row_bytes;
   uint32_t stage_rows = ix->stage_bytes / stage_row;
   // (the fold8 kernels, CPL 1-2, read whole blocks of 8 slots per warp: a multiple of 32 rows)
-  const uint32_t unit = (l.group == 32 && l.cpl > 0 && l.cpl <= 2) ? 32 : 4 * (32 / ix->group);
+  const uint32_t unit = (l.group == 32 && l.cpl > 0 && l.cpl <= 2) ? 8 * SEARCH_WARPS : SEARCH_WARPS * (32 / ix->group);
   if (stage_rows > 128) stage_rows = 128;
+  if (stage_rows > 32u * SEARCH_WARPS) stage_rows = 32u * SEARCH_WARPS;   // a warp's slice holds at most 32 rows (one id per lane)
   stage_rows = stage_rows / unit * unit;
   if (stage_rows < unit) stage_rows = unit;
   a.stage_rows = stage_rows;

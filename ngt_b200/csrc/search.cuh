@@ -40,13 +40,16 @@
 #pragma once
 #include "ngtgpu_internal.cuh"
 
-#define SEARCH_WARPS 4
+#ifndef SEARCH_WARPS
+#define SEARCH_WARPS 4        // warps per query (1, 2 or 4)
+#endif
 #define SEARCH_THREADS (SEARCH_WARPS * 32)
 #ifndef SEARCH_MIN_CTAS
-#define SEARCH_MIN_CTAS 8     // 64 registers per thread; nine CTAs (56 registers) spill and measured slower
+#define SEARCH_MIN_CTAS (32 / SEARCH_WARPS)   // 64 registers per thread at 4 warps; nine CTAs (56 registers) spill and measured slower
 #endif
-#define SEARCH_CMAX 128       // upper bound of edges filtered / rows staged per round (== SEARCH_THREADS)
-#define SEARCH_HEAD 128       // edges per node in the fixed-stride adjacency table (== SEARCH_THREADS: one per thread)
+#define SEARCH_CMAX 128       // upper bound of edges filtered / rows staged per round
+#define SEARCH_HEAD 128       // edges per node in the fixed-stride adjacency table (== SEARCH_CMAX)
+#define SEARCH_EPT (SEARCH_CMAX / SEARCH_THREADS)   // edges filtered per thread and round
 
 struct SearchArgs {
   const uint8_t *objects;
@@ -100,6 +103,16 @@ __device__ __forceinline__ void cp_async_row16(void *smem_dst, const void *gsrc)
 // the same with the destination already a 32-bit shared-window address (no generic->shared conversion per call)
 __device__ __forceinline__ void cp_async_s16(uint32_t smem_addr, const void *gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gsrc) : "memory");
+}
+// base + a * b in one instruction (IMAD.WIDE.U32 with a 64-bit addend)
+__device__ __forceinline__ const uint8_t *mad_wide_ptr(uint32_t a, uint32_t b, const uint8_t *base) {
+  uint64_t r;
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"((uint64_t)(uintptr_t)base));
+  return reinterpret_cast<const uint8_t *>((uintptr_t)r);
+}
+// 16-byte copy of which only the first src_bytes (0 or 16) are read from global memory; the rest is zero-filled
+__device__ __forceinline__ void cp_async_s16z(uint32_t smem_addr, const void *gsrc, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr), "l"(gsrc), "r"(src_bytes) : "memory");
 }
 __device__ __forceinline__ uint4 lds16(uint32_t smem_addr) {
   uint4 r;
@@ -252,6 +265,10 @@ template <int ACC, int G, int CPL, int WS>
 __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel(const SearchArgs a) {
   constexpr int R = 32 / G;                 // rows per warp instruction (G < 32)
   constexpr int NCH = CPL > 0 ? CPL : 1;    // register-resident query chunks per lane
+  // rows of <= 32 chunks: distances are evaluated by 8 lanes per row (four rows per warp instruction), lane j of a
+  // row taking chunks j, j + 8, j + 16, j + 24 -- the adds of the first two butterfly levels of group_fold<ACC, 32>
+  // become local (same operands, same order: same float bits), three shuffles remain
+  constexpr bool ROW8 = (G == 32 && CPL == 1);
   extern __shared__ __align__(128) uint8_t smem_raw[];
   __shared__ uint32_t s_cand_ids[SEARCH_CMAX];
   __shared__ uint64_t s_cand_keys[SEARCH_CMAX];
@@ -321,8 +338,16 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
     }
     const uint8_t *qrow = a.queries + (size_t)q * a.row_bytes;
     uint4 qreg[NCH];
+    uint4 q8[4];   // ROW8 layout: lane (rr, j) holds query chunks j, j + 8, j + 16, j + 24
     float qn = 0.f;
-    if (CPL > 0) {
+    if (ROW8) {
+#pragma unroll
+      for (int m = 0; m < 4; m++) {
+        const uint32_t c = (lane & 7) + m * 8;
+        q8[m] = c < a.chunks ? ldg16(qrow + (size_t)c * 16) : zero16();
+      }
+      qreg[0] = zero16();
+    } else if (CPL > 0) {
 #pragma unroll
       for (int i = 0; i < NCH; i++) {
         uint32_t c = gl + i * G;
@@ -336,7 +361,15 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
     __syncthreads();
     if (ACC == ACC_F_COS) {
       // query norm^2 in the engine's summation order (PrimitiveComparator.h:487-553 recomputes it per call)
-      if (CPL > 0) {
+      if (ROW8) {
+        // lane c owns chunk c here (one load, once per query) so the fold below is group_fold's
+        const uint4 v = (uint32_t)lane < a.chunks ? ldg16(qrow + (size_t)lane * 16) : zero16();
+        float a0 = __uint_as_float(v.x), a1 = __uint_as_float(v.y), a2 = __uint_as_float(v.z), a3 = __uint_as_float(v.w);
+        qn = fmaf(a0, a0, qn);
+        qn = fmaf(a1, a1, qn);
+        qn = fmaf(a2, a2, qn);
+        qn = fmaf(a3, a3, qn);
+      } else if (CPL > 0) {
 #pragma unroll
         for (int i = 0; i < NCH; i++) {
           float a0 = __uint_as_float(qreg[i].x), a1 = __uint_as_float(qreg[i].y), a2 = __uint_as_float(qreg[i].z),
@@ -377,6 +410,8 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
     bool seeding = true;
     bool head_round = false;      // the round in flight read a head-table row (its edge count comes from s_edge_n)
     uint32_t cand_n = 0;
+    // per-phase cycle counters of warp 0: compiled in only with -DSEARCH_PHASE_PROFILE (they cost ten registers)
+#ifdef SEARCH_PHASE_PROFILE
     uint32_t pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tp = a.prof ? clock64() : 0;
 #define PROF_MARK(i)                     \
@@ -385,6 +420,9 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
     pf[i] += (uint32_t)(_t - tp);        \
     tp = _t;                             \
   }
+#else
+#define PROF_MARK(i)
+#endif
 
     for (;;) {
       // ================= control (warp 0): merge the previous round, choose the next edges =================
@@ -561,40 +599,82 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
       const bool seeding_round = s_seeding != 0;
 
       // ================= filter: one edge per thread, looked up in the visited set =================
-      bool pending_insert = false;   // this thread found a new id whose insertion is still to be issued
-      uint32_t pending_id = 0;
-      BucketProbe bp;
-      bp.bucket = 0;
-      bp.slot = 0;
+      // bit i: this thread found edge i new and its insertion is still to be issued
+      uint32_t pending_mask = 0;
+      uint32_t pending_id[SEARCH_EPT];
+      BucketProbe bp[SEARCH_EPT];
+#pragma unroll
+      for (int i = 0; i < SEARCH_EPT; i++) {
+        pending_id[i] = 0;
+        bp[i].bucket = 0;
+        bp[i].slot = 0;
+      }
       {
         const uint32_t take = s_take;
         const uint32_t *src = s_src;
         const bool immediate = seeding_round;   // seed lists may repeat an id: insert at once so the second copy is seen
         if (!ordered) {
-          uint32_t nid = (uint32_t)tid < take ? __ldg(src + tid) : 0u;
-          const bool valid = nid != 0u && nid <= a.n;
-          bool isnew = false;
-          if (valid) {
-            if (WS == 0) {
-              isnew = !hash_lookup(hash, a.hash_bits - 3, nid, bp);
-              if (isnew && immediate) isnew = hash_insert(hash, a.hash_bits - 3, nid, bp);
-              else if (isnew) {
-                pending_insert = true;
-                pending_id = nid;
-              }
-            } else {
-              isnew = bitmap_visit(bitmap, nid);
-            }
+          // thread t looks at edges t, t + THREADS, ...: all edge loads first, then all bucket lookups
+          uint32_t nid[SEARCH_EPT];
+#pragma unroll
+          for (int i = 0; i < SEARCH_EPT; i++) {
+            const uint32_t e = (uint32_t)tid + i * SEARCH_THREADS;
+            nid[i] = e < take ? __ldg(src + e) : 0u;
           }
-          const uint32_t m = __ballot_sync(0xffffffffu, isnew);
-          const uint32_t mv = __ballot_sync(0xffffffffu, valid);
+          uint32_t new_mask = 0, n_valid = 0;
+#pragma unroll
+          for (int i = 0; i < SEARCH_EPT; i++) {
+            const bool valid = nid[i] != 0u && nid[i] <= a.n;
+            bool isnew = false;
+            if (valid) {
+              n_valid++;
+              if (WS == 0) {
+                isnew = !hash_lookup(hash, a.hash_bits - 3, nid[i], bp[i]);
+                if (isnew && immediate) isnew = hash_insert(hash, a.hash_bits - 3, nid[i], bp[i]);
+                else if (isnew) {
+                  pending_mask |= 1u << i;
+                  pending_id[i] = nid[i];
+                }
+              } else {
+                isnew = bitmap_visit(bitmap, nid[i]);
+              }
+            }
+            if (isnew) new_mask |= 1u << i;
+          }
+          // position of this thread's new ids in the candidate list: exclusive count inside the warp + the warp's base
+          uint32_t before, warp_new, warp_valid;
+          if (SEARCH_EPT == 1) {
+            const uint32_t m = __ballot_sync(0xffffffffu, new_mask != 0);
+            before = __popc(m & lanemask_lt());
+            warp_new = __popc(m);
+            warp_valid = __popc(__ballot_sync(0xffffffffu, n_valid != 0));
+          } else {
+            const uint32_t n_new = __popc(new_mask);
+            uint32_t incl = n_new;
+            warp_valid = n_valid;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+              if (lane >= o) incl += v;
+              warp_valid += __shfl_xor_sync(0xffffffffu, warp_valid, o);
+            }
+            before = incl - n_new;
+            warp_new = __shfl_sync(0xffffffffu, incl, 31);
+          }
           uint32_t base = 0;
           if (lane == 0) {
-            if (m) base = atomicAdd(&s_cand_n, __popc(m));
-            if (mv) atomicAdd(&s_edge_n, __popc(mv));
+            if (SEARCH_WARPS == 1) {
+              s_cand_n = warp_new;
+              s_edge_n = warp_valid;
+            } else {
+              if (warp_new) base = atomicAdd(&s_cand_n, warp_new);
+              if (warp_valid) atomicAdd(&s_edge_n, warp_valid);
+            }
           }
-          base = __shfl_sync(0xffffffffu, base, 0);
-          if (isnew) s_cand_ids[base + __popc(m & lanemask_lt())] = nid;
+          base = __shfl_sync(0xffffffffu, base, 0) + before;
+#pragma unroll
+          for (int i = 0; i < SEARCH_EPT; i++)
+            if (new_mask & (1u << i)) s_cand_ids[base++] = nid[i];
         } else if (warp == 0) {
           // element order kept: warp 0 walks the edges 32 at a time
           uint32_t cn = 0, en = 0;
@@ -604,8 +684,8 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
             bool isnew = false;
             if (valid) {
               if (WS == 0) {
-                isnew = !hash_lookup(hash, a.hash_bits - 3, nid, bp);
-                if (isnew) isnew = hash_insert(hash, a.hash_bits - 3, nid, bp);
+                isnew = !hash_lookup(hash, a.hash_bits - 3, nid, bp[0]);
+                if (isnew) isnew = hash_insert(hash, a.hash_bits - 3, nid, bp[0]);
               } else {
                 isnew = bitmap_visit(bitmap, nid);
               }
@@ -644,18 +724,33 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
         for (uint32_t j0 = warp * wrows; j0 < cn; j0 += SEARCH_WARPS * wrows) {
           const uint32_t nr = cn - j0 < wrows ? cn - j0 : wrows;
           if (G == 32 && CPL > 0) {
-            // lane r fetches the id of the slice's r-th row once; the row loop is unrolled so the copies of
-            // all rows are issued back to back
+            // lane r fetches the id of the slice's r-th row once; rows are issued eight at a time, fully unrolled and
+            // branch-free: a copy past the slice's last row, or of a chunk past the row's end, has source size 0
+            // (nothing is read, the slot is zero-filled)
             const uint32_t my_id = (uint32_t)lane < nr ? s_cand_ids[j0 + lane] : 0u;
             const uint8_t *lane_src = a.objects + (size_t)lane * 16;
-#pragma unroll 8
-            for (uint32_t r = 0; r < nr; r++) {
-              const uint32_t id = __shfl_sync(0xffffffffu, my_id, (int)r);
-              const uint8_t *srow = lane_src + (size_t)id * a.row_bytes;
-              const uint32_t drow = wstage_s + r * SROW;
+            const bool last_ok = (uint32_t)lane + (NCH - 1) * 32 < a.chunks;
+            for (uint32_t r0 = 0; r0 < nr; r0 += 8) {
+              const uint32_t left = nr - r0;
 #pragma unroll
-              for (int c = 0; c < NCH; c++)
-                if (c < NCH - 1 || (uint32_t)lane + c * 32 < a.chunks) cp_async_s16(drow + c * 512, srow + c * 512);
+              for (int i = 0; i < 8; i++) {
+                // (slices of the fold kernels, CPL <= 2, are whole blocks of eight slots; longer rows may have fewer)
+                if (CPL > 2 && r0 + i >= wrows) break;
+                const uint32_t id = __shfl_sync(0xffffffffu, my_id, (int)(r0 + i));   // r0 + i < 32: a slice has <= 32 rows
+                const uint8_t *srow = lane_src + (size_t)id * a.row_bytes;
+                const uint32_t drow = wstage_s + (r0 + i) * SROW;
+                const bool in = (uint32_t)i < left;
+#pragma unroll
+                for (int c = 0; c < NCH; c++)
+                  cp_async_s16z(drow + c * 512, srow + c * 512, (in && (c < NCH - 1 || last_ok)) ? 16u : 0u);
+#ifdef SEARCH_EXPERIMENT_EXTRA_TRAFFIC
+                // development probe: one more random row pulled from HBM into L2 per row copied (nobody waits for it)
+                if (in) {
+                  const uint32_t other = (id * 2654435761u + 12345u) % (uint32_t)a.n;
+                  asm volatile("prefetch.global.L2 [%0];" ::"l"(lane_src + (size_t)other * a.row_bytes));
+                }
+#endif
+              }
             }
           } else if (G == 32) {
             for (uint32_t r = 0; r < nr; r++) {
@@ -672,14 +767,51 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
                              a.objects + (size_t)s_cand_ids[j0 + r] * a.row_bytes + (size_t)c * 16);
             }
           }
-          if (WS == 0 && pending_insert) {
-            // the insertion of this thread's new id, overlapped with the row copies in flight
-            hash_insert(hash, a.hash_bits - 3, pending_id, bp);
-            pending_insert = false;
+          if (WS == 0 && pending_mask) {
+            // the insertions of this thread's new ids, overlapped with the row copies in flight
+#pragma unroll
+            for (int i = 0; i < SEARCH_EPT; i++)
+              if (pending_mask & (1u << i)) hash_insert(hash, a.hash_bits - 3, pending_id[i], bp[i]);
+            pending_mask = 0;
           }
           cp_async_commit_wait_all();
           __syncwarp();
-          if (CPL > 0 && CPL <= 2 && G == 32) {
+          if (ROW8) {
+            // four rows per step, eight lanes each. Slots past the slice's last row hold stale rows of earlier
+            // rounds (or the initial zeros): they are read like the others and their result is dropped; chunks
+            // past the row's end read the zeroed tail against zero query chunks.
+            const uint32_t rr = (uint32_t)lane >> 3;
+            const uint32_t ra0 = wstage_s - (uint32_t)lane * 16u + rr * SROW + ((uint32_t)lane & 7u) * 16u;
+            for (uint32_t r0 = 0; r0 < nr; r0 += 4) {
+              Sums p[4];
+#pragma unroll
+              for (int m = 0; m < 4; m++) {
+                p[m] = zero_sums();
+                acc_chunk<ACC>(p[m], q8[m], lds16(ra0 + r0 * SROW + m * 128));
+              }
+              Sums tot = zero_sums();
+              if (ACC == ACC_U8_L2 || ACC == ACC_U8_HAM) {
+                tot.u = (p[0].u + p[2].u) + (p[1].u + p[3].u);
+                tot.u += __shfl_xor_sync(0xffffffffu, tot.u, 4);
+                tot.u += __shfl_xor_sync(0xffffffffu, tot.u, 2);
+                tot.u += __shfl_xor_sync(0xffffffffu, tot.u, 1);
+              } else {
+                tot.f0 = (p[0].f0 + p[2].f0) + (p[1].f0 + p[3].f0);
+                tot.f0 += __shfl_xor_sync(0xffffffffu, tot.f0, 4);
+                tot.f0 += __shfl_xor_sync(0xffffffffu, tot.f0, 2);
+                tot.f0 += __shfl_xor_sync(0xffffffffu, tot.f0, 1);
+                if (ACC == ACC_F_COS) {
+                  tot.f1 = (p[0].f1 + p[2].f1) + (p[1].f1 + p[3].f1);
+                  tot.f1 += __shfl_xor_sync(0xffffffffu, tot.f1, 4);
+                  tot.f1 += __shfl_xor_sync(0xffffffffu, tot.f1, 2);
+                  tot.f1 += __shfl_xor_sync(0xffffffffu, tot.f1, 1);
+                }
+              }
+              const uint32_t r = r0 + rr;
+              if ((lane & 7) == 0 && r < nr)
+                s_cand_keys[j0 + r] = make_key(finish_distance<ACC>(a.dtype, tot, qn), s_cand_ids[j0 + r]);
+            }
+          } else if (CPL > 0 && CPL <= 2 && G == 32) {
             // eight rows at a time, folded together (fold8). Slots past the slice's last row hold stale rows of
             // earlier rounds (or the initial zeros): they are read like the others and their result is dropped;
             // chunks past the row's end read the zeroed tail. No predicates and no address selects in the loop.
@@ -746,7 +878,11 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
           }
           __syncwarp();
         }
-        if (WS == 0 && pending_insert) hash_insert(hash, a.hash_bits - 3, pending_id, bp);   // warps without rows this round
+        if (WS == 0 && pending_mask) {   // warps without rows this round
+#pragma unroll
+          for (int i = 0; i < SEARCH_EPT; i++)
+            if (pending_mask & (1u << i)) hash_insert(hash, a.hash_bits - 3, pending_id[i], bp[i]);
+        }
         if (warp == 0) { PROF_MARK(5) }
       }
       __syncthreads();  // (C) keys are published; the staging area may be overwritten
@@ -755,9 +891,11 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
 
     // ---- write the outcome
     const int state = s_state;
+#ifdef SEARCH_PHASE_PROFILE
     if (a.prof && tid == 0 && state == 1) {
       for (int i = 0; i < 8; i++) a.prof[(size_t)q * 8 + i] = pf[i];
     }
+#endif
     if (warp == 0) {
       if (state == 1) {
         for (uint32_t i = lane; i < a.k; i += 32) {

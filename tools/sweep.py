@@ -25,7 +25,7 @@ ap.add_argument("--queue-cap", type=int, default=512)
 ap.add_argument("--pivots", type=int, default=1024)
 ap.add_argument("--seeds", type=int, default=10)
 ap.add_argument("--target", type=float, default=0.95)
-ap.add_argument("--prof", action="store_true")
+ap.add_argument("--prof", action="store_true")   # needs a library built with EXTRA=-DSEARCH_PHASE_PROFILE
 ap.add_argument("--stage-bytes", default="16384")
 a = ap.parse_args()
 
