@@ -160,6 +160,16 @@ int ngtgpu_pack_keys(const uint32_t *ids, const float *dists, const uint32_t *co
 int ngtgpu_merge_keys(const uint64_t *keys, uint32_t n_lists, uint32_t nq, uint32_t k, uint32_t *ids, float *dists,
                       uint32_t *counts, void *stream);
 
+/* ---- ONNG construction, second step: GraphReconstructor::adjustPathsEffectively
+ *      (lib/NGT/GraphReconstructor.h:197-386; run by GraphOptimizer::execute after reconstructGraph,
+ *      lib/NGT/GraphOptimizer.h:279-292): drop edge src->dst when src->path->dst with both hops shorter is already
+ *      in the rebuilt graph, unless the node would be left with min_edges edges or fewer. The graph is a DEVICE CSR
+ *      over ids 0..n (row_ptr: n+2 entries, id 0 has no edges), lists ascending by (distance, id) as `grp` stores
+ *      them; keep[e] (device, one byte per edge) becomes 1 for the edges of the adjusted graph -- the reference's
+ *      result exactly. stats (host, nullable): candidates, removed edges, sweep launches, kernels launched. */
+int ngtgpu_graph_adjust_paths(uint64_t n, const uint64_t *row_ptr, const uint32_t *col, const float *dist,
+                              uint32_t min_edges, uint8_t *keep, uint64_t *stats, void *stream);
+
 /* Number of kernels this library launched since the index was created (bench.py's gpu_launches). */
 uint64_t ngtgpu_index_launch_count(const ngtgpu_index *index);
 /* Device timing of the traversal kernel with CUDA events on the launching stream (bench.py's roofline leg):

@@ -128,6 +128,38 @@ def reconstruct_graph_csr(row_ptr, col, dist, outgoing, incoming):
     return out_ptr, t2.to(torch.int32), d2
 
 
+def adjust_paths(row_ptr, col, dist, min_edges=0, with_stats=False):
+    """GraphReconstructor::adjustPathsEffectively (lib/NGT/GraphReconstructor.h:197-386) -- the shortcut reduction
+    GraphOptimizer::execute applies after reconstructGraph -- on a device CSR (row_ptr over ids 0..n, lists
+    ascending by (distance, id)). The decisions are made by libngtgpu.so (ngtgpu_graph_adjust_paths); compaction of
+    the surviving edges is a masked select. -> (row_ptr, col, dist) of the adjusted graph."""
+    import torch
+    lib = _lib.load()
+    dev = col.device
+    if dev.type != "cuda":
+        raise _lib.NgtGpuError(_lib.ERR_NO_DEVICE, "adjust_paths: the graph must be on a CUDA device (no CPU path)")
+    n = row_ptr.numel() - 2
+    rp = row_ptr.to(torch.int64).contiguous()
+    c = col.to(torch.int32).contiguous()
+    d = dist.to(torch.float32).contiguous()
+    keep = torch.zeros(max(c.numel(), 1), dtype=torch.uint8, device=dev)
+    stats = (C.c_uint64 * 4)()
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.ngtgpu_graph_adjust_paths(n, rp.data_ptr(), c.data_ptr(), d.data_ptr(), int(min_edges),
+                                                 keep.data_ptr(), stats, stream))
+    keep = keep[:c.numel()].bool()
+    src = torch.repeat_interleave(torch.arange(n + 1, device=dev, dtype=torch.int64), rp[1:] - rp[:-1])
+    deg = torch.bincount(src[keep], minlength=n + 1)
+    out_ptr = torch.zeros(n + 2, dtype=torch.int64, device=dev)
+    out_ptr[1:] = torch.cumsum(deg, 0)
+    out = (out_ptr, c[keep], d[keep])
+    if with_stats:
+        return out + ({"candidates": int(stats[0]), "removed": int(stats[1]), "sweeps": int(stats[2]),
+                       "launches": int(stats[3])},)
+    return out
+
+
 def graph_statistics(row_ptr):
     deg = (row_ptr[2:] - row_ptr[1:-1]).float()
     return {"edges": int(row_ptr[-1]), "mean_degree": float(deg.mean()), "min_degree": int(deg.min()),

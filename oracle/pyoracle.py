@@ -266,3 +266,50 @@ class Ref:
         self._check(self.lib.ref_linear_search(h, queries, nq, dim, k, radius, ids, dists, counts, threads,
                                                C.byref(sec)))
         return ids, dists, counts, sec.value
+
+
+def adjust_paths_loop(row_ptr, col, dist, min_edges=0):
+    """Sequential restatement of GraphReconstructor::adjustPathsEffectively
+    (lib/NGT/GraphReconstructor.h:197-386) for small graphs (pure-Python loops; test infrastructure).
+    row_ptr over ids 0..n, lists ascending by (distance, id). -> list of kept (id, distance) lists per id 0..n."""
+    n = len(row_ptr) - 2
+    tmp = [[(int(col[e]), float(dist[e])) for e in range(int(row_ptr[i]), int(row_ptr[i + 1]))] for i in range(n + 1)]
+    remove_candidates = [[] for _ in range(n + 1)]
+    for src in range(1, n + 1):                                     # :236-284
+        node = tmp[src]
+        neighbors = {nid: (sni, d) for sni, (nid, d) in enumerate(node)}
+        cands = []
+        for sni, (path, d1) in enumerate(node):
+            for (dst, d2) in tmp[path]:
+                hit = neighbors.get(dst)
+                if hit is not None and d1 < hit[1] and d2 < hit[1]:
+                    cands.append((hit[0], (path, dst)))
+        cands.sort(reverse=True)
+        remove_candidates[src] = [c[1] for c in cands]
+    out = [dict() for _ in range(n + 1)]                            # id -> distance, the graph being rebuilt
+    ids = list(range(1, n + 1))
+    rank = 0
+    while ids:                                                      # :299-371
+        nxt = []
+        for src in ids:
+            node = tmp[src]
+            if rank >= len(node):
+                continue
+            rc = remove_candidates[src]
+            if rc and (len(out[src]) + len(node) - rank) > min_edges:
+                path_exist = False
+                while rc and rc[-1][1] == node[rank][0]:
+                    path, dst = rc.pop()
+                    if path in out[src] and dst in out[path]:
+                        path_exist = True
+                        while rc and rc[-1][1] == node[rank][0]:
+                            rc.pop()
+                        break
+                if path_exist:
+                    nxt.append(src)
+                    continue
+            out[src][node[rank][0]] = node[rank][1]
+            nxt.append(src)
+        ids = nxt
+        rank += 1
+    return [sorted(((d, i) for i, d in o.items())) for o in out]   # :373-383: sorted by (distance, id)

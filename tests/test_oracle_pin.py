@@ -134,3 +134,19 @@ def test_recall_definition(port):
     gt_d = np.array([1.0, 2.0, 3.0, 4.0], np.float32)
     assert port.recall(np.array([1, 2, 9, 8], np.uint32), np.array([1, 2, 4.0, 5.0], np.float32), gt_ids, gt_d) == 0.75
     assert port.recall(np.array([7], np.uint32), np.array([9.0], np.float32), gt_ids, gt_d) == 0.0
+
+
+def test_adjust_paths_restatement_matches_the_reference():
+    """GraphReconstructor::adjustPathsEffectively (GraphReconstructor.h:197-386): the sequential restatement in
+    oracle/pyoracle.py against the graphs the reference's GraphOptimizer::execute wrote with shortcut reduction on
+    (tests/golden/adjust_paths.npz, made by tests/golden/make_golden_adjust_paths.py)."""
+    z = np.load(os.path.join(GOLDEN, "adjust_paths.npz"))
+    for tag in ("sift", "glove"):
+        for o, i in ((5, 20), (10, 40)):
+            k = "%s_o%d_i%d" % (tag, o, i)
+            out = po.adjust_paths_loop(z[k + "_in_row_ptr"], z[k + "_in_col"], z[k + "_in_dist"], 0)
+            arp, acol, adist = z[k + "_adj_row_ptr"], z[k + "_adj_col"], z[k + "_adj_dist"]
+            assert len(acol) < len(z[k + "_in_col"])
+            for nid in range(len(arp) - 1):
+                ref = [(float(adist[e]), int(acol[e])) for e in range(int(arp[nid]), int(arp[nid + 1]))]
+                assert ref == out[nid], (k, nid)

@@ -27,6 +27,7 @@ ap.add_argument("--seeds", type=int, default=10)
 ap.add_argument("--target", type=float, default=0.95)
 ap.add_argument("--prof", action="store_true")   # needs a library built with EXTRA=-DSEARCH_PHASE_PROFILE
 ap.add_argument("--stage-bytes", default="16384")
+ap.add_argument("--adjust", type=int, default=-1)   # >= 0: adjustPathsEffectively with this minNoOfEdges
 a = ap.parse_args()
 
 dev = torch.device("cuda", 0)
@@ -47,6 +48,12 @@ for cfg in a.configs.split(";"):
     K, o, i, cap = [int(v) for v in cfg.split(",")]
     rp, col, dd = build.reconstruct_graph(ids[:, :K].contiguous(), dists[:, :K].contiguous(),
                                           torch.clamp(counts, max=K), o, i)
+    if a.adjust >= 0:
+        torch.cuda.synchronize()
+        t = time.time()
+        rp, col, dd, ast = build.adjust_paths(rp, col, dd, a.adjust, with_stats=True)
+        torch.cuda.synchronize()
+        print("adjust_paths: %.2fs %s" % (time.time() - t, ast), flush=True)
     st = build.graph_statistics(rp)
     ix.set_graph(rp, col)
     ix.set_search_property(cap, 30, 20)
