@@ -160,6 +160,23 @@ int ngtgpu_pack_keys(const uint32_t *ids, const float *dists, const uint32_t *co
 int ngtgpu_merge_keys(const uint64_t *keys, uint32_t n_lists, uint32_t nq, uint32_t k, uint32_t *ids, float *dists,
                       uint32_t *counts, void *stream);
 
+/* ---- graph from the exhaustive kNN pass: a DEVICE [n x k] neighbour table (ngtgpu_index_knn_graph) -> DEVICE CSR over
+ *      ids 0..n with distances, lists ascending by (distance, id). symmetric != 0 adds the reverse of every edge, i.e.
+ *      the graph insertANNGNode's out-edges + reverse edges converge to (lib/NGT/Graph.h:611-626). valid (nullable):
+ *      one byte per id, 0 = removed slot. capacity: entries of out_col / out_dist (n * k * 2 always suffices). */
+int ngtgpu_graph_from_knn_table(uint64_t n, const uint32_t *ids, const float *dists, const uint32_t *counts, uint32_t k,
+                                const uint8_t *valid, int symmetric, uint64_t capacity, uint64_t *out_row_ptr,
+                                uint32_t *out_col, float *out_dist, uint64_t *out_nnz, void *stream);
+
+/* ---- ONNG construction, first step: GraphReconstructor::reconstructGraph (lib/NGT/GraphReconstructor.h:425-561):
+ *      every node keeps its first `outgoing` edges (all, when it has fewer) and receives the reverse of the first
+ *      `incoming` edges of every node; lists sorted by (distance, id), repeated ids dropped. DEVICE CSR in (ids 0..n),
+ *      DEVICE CSR out: out_row_ptr n+2 entries, out_col / out_dist `capacity` entries (2 x the input edges always
+ *      suffice); *out_nnz (host) receives the number of edges written. */
+int ngtgpu_graph_reconstruct(uint64_t n, const uint64_t *row_ptr, const uint32_t *col, const float *dist,
+                             uint32_t outgoing, uint32_t incoming, uint64_t capacity, uint64_t *out_row_ptr,
+                             uint32_t *out_col, float *out_dist, uint64_t *out_nnz, void *stream);
+
 /* ---- ONNG construction, second step: GraphReconstructor::adjustPathsEffectively
  *      (lib/NGT/GraphReconstructor.h:197-386; run by GraphOptimizer::execute after reconstructGraph,
  *      lib/NGT/GraphOptimizer.h:279-292): drop edge src->dst when src->path->dst with both hops shorter is already
@@ -169,6 +186,23 @@ int ngtgpu_merge_keys(const uint64_t *keys, uint32_t n_lists, uint32_t nq, uint3
  *      result exactly. stats (host, nullable): candidates, removed edges, sweep launches, kernels launched. */
 int ngtgpu_graph_adjust_paths(uint64_t n, const uint64_t *row_ptr, const uint32_t *col, const float *dist,
                               uint32_t min_edges, uint8_t *keep, uint64_t *stats, void *stream);
+
+/* The sub-graph of the edges with keep[e] != 0, order inside the lists preserved (compaction after
+ * ngtgpu_graph_adjust_paths). DEVICE buffers; *out_nnz is a host word. */
+int ngtgpu_graph_select_edges(uint64_t n, const uint64_t *row_ptr, const uint32_t *col, const float *dist,
+                              const uint8_t *keep, uint64_t *out_row_ptr, uint32_t *out_col, float *out_dist,
+                              uint64_t *out_nnz, void *stream);
+
+/* ---- GraphReconstructor::refineANNG (lib/NGT/GraphReconstructor.h:814-924; C API ngt_refine_anng): in batches of
+ *      batch_size, every stored object is searched for in the current graph (size searched_edges, epsilon, edge_size
+ *      as in ngtgpu_search_params, seeds = nearest n_seeds pivots), its results are merged into its edge list and --
+ *      when no_of_edges == 0 -- the reverse edges are added; later batches search the refined graph; no_of_edges > 0
+ *      finally cuts every list to that length. d_row_ptr / d_col / d_dist: DEVICE CSR with distances, updated in place
+ *      (col / dist hold `capacity` entries; nnz + 2 * n * searched_edges always suffices). The index's own graph is left
+ *      equal to the result. */
+int ngtgpu_index_refine_anng(ngtgpu_index *index, float epsilon, int32_t no_of_edges, int64_t edge_size,
+                             uint32_t searched_edges, uint64_t batch_size, uint32_t n_seeds, uint64_t capacity,
+                             uint64_t *d_row_ptr, uint32_t *d_col, float *d_dist, uint64_t *nnz_out);
 
 /* Number of kernels this library launched since the index was created (bench.py's gpu_launches). */
 uint64_t ngtgpu_index_launch_count(const ngtgpu_index *index);

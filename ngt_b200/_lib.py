@@ -55,6 +55,13 @@ SYMBOLS = {
     "ngtgpu_search_device": (C.c_int, [_P, _P, C.c_int, C.c_uint32, C.POINTER(SearchParams), _P, C.c_uint32, _P, _P,
                                        _P, _P, _P]),
     "ngtgpu_linear_search": (C.c_int, [_P, _P, C.c_int, C.c_uint32, C.c_uint32, C.c_float, _P, _P, _P]),
+    "ngtgpu_graph_reconstruct": (C.c_int, [C.c_uint64, _P, _P, _P, C.c_uint32, C.c_uint32, C.c_uint64, _P, _P, _P,
+                                           C.POINTER(C.c_uint64), _P]),
+    "ngtgpu_index_refine_anng": (C.c_int, [_P, C.c_float, C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint64,
+                                           _P, _P, _P, C.POINTER(C.c_uint64)]),
+    "ngtgpu_graph_from_knn_table": (C.c_int, [C.c_uint64, _P, _P, _P, C.c_uint32, _P, C.c_int, C.c_uint64, _P, _P, _P,
+                                              C.POINTER(C.c_uint64), _P]),
+    "ngtgpu_graph_select_edges": (C.c_int, [C.c_uint64, _P, _P, _P, _P, _P, _P, _P, C.POINTER(C.c_uint64), _P]),
     "ngtgpu_graph_adjust_paths": (C.c_int, [C.c_uint64, _P, _P, _P, C.c_uint32, _P, C.POINTER(C.c_uint64), _P]),
     "ngtgpu_linear_search_device": (C.c_int, [_P, _P, C.c_int, C.c_uint32, C.c_uint32, C.c_float, _P, _P, _P, _P]),
 }

@@ -128,6 +128,59 @@ def reconstruct_graph_csr(row_ptr, col, dist, outgoing, incoming):
     return out_ptr, t2.to(torch.int32), d2
 
 
+def reconstruct_graph_device(row_ptr, col, dist, outgoing, incoming):
+    """reconstruct_graph_csr done by libngtgpu.so (ngtgpu_graph_reconstruct: emit, two radix sorts, compact) -- what
+    the C API's optimizer entry points run. CUDA tensors in, CUDA tensors out."""
+    import torch
+    lib = _lib.load()
+    dev = col.device
+    if dev.type != "cuda":
+        raise _lib.NgtGpuError(_lib.ERR_NO_DEVICE, "reconstruct_graph_device: the graph must be on a CUDA device")
+    n = row_ptr.numel() - 2
+    rp = row_ptr.to(torch.int64).contiguous()
+    c = col.to(torch.int32).contiguous()
+    d = dist.to(torch.float32).contiguous()
+    cap = 2 * max(c.numel(), 1)
+    out_ptr = torch.zeros(n + 2, dtype=torch.int64, device=dev)
+    out_col = torch.empty(cap, dtype=torch.int32, device=dev)
+    out_dist = torch.empty(cap, dtype=torch.float32, device=dev)
+    nnz = C.c_uint64(0)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.ngtgpu_graph_reconstruct(n, rp.data_ptr(), c.data_ptr(), d.data_ptr(), int(outgoing), int(incoming),
+                                                cap, out_ptr.data_ptr(), out_col.data_ptr(), out_dist.data_ptr(),
+                                                C.byref(nnz), stream))
+    return out_ptr, out_col[:nnz.value].clone(), out_dist[:nnz.value].clone()
+
+
+def refine_anng(ix, row_ptr, col, dist, epsilon=0.1, no_of_edges=0, edge_size=-1, batch_size=10000,
+                edge_size_for_creation=10, n_seeds=10):
+    """GraphReconstructor::refineANNG (lib/NGT/GraphReconstructor.h:814-924) on the device
+    (ngtgpu_index_refine_anng): batched self-search of every object in the current graph, results merged into the
+    out-edges, reverse edges added (unless a kNN graph is asked for with no_of_edges != 0). The graph (CUDA CSR with
+    distances) is returned refined and is also left set on `ix`."""
+    import torch
+    lib = _lib.load()
+    dev = col.device
+    if dev.type != "cuda":
+        raise _lib.NgtGpuError(_lib.ERR_NO_DEVICE, "refine_anng: the graph must be on a CUDA device (no CPU path)")
+    n = ix.size
+    # noOfSearchedEdges, GraphReconstructor.h:825
+    k = -no_of_edges if no_of_edges < 0 else max(no_of_edges, edge_size_for_creation)
+    nnz = col.numel()
+    cap = nnz + 2 * n * k
+    rp = row_ptr.to(torch.int64).clone()
+    c = torch.zeros(cap, dtype=torch.int32, device=dev)
+    d = torch.zeros(cap, dtype=torch.float32, device=dev)
+    c[:nnz] = col
+    d[:nnz] = dist
+    out = C.c_uint64(0)
+    torch.cuda.synchronize(dev)
+    _lib.check(lib.ngtgpu_index_refine_anng(ix._h, float(epsilon), int(no_of_edges), int(edge_size), int(k), int(batch_size),
+                                            int(n_seeds), cap, rp.data_ptr(), c.data_ptr(), d.data_ptr(), C.byref(out)))
+    return rp, c[:out.value].clone(), d[:out.value].clone()
+
+
 def adjust_paths(row_ptr, col, dist, min_edges=0, with_stats=False):
     """GraphReconstructor::adjustPathsEffectively (lib/NGT/GraphReconstructor.h:197-386) -- the shortcut reduction
     GraphOptimizer::execute applies after reconstructGraph -- on a device CSR (row_ptr over ids 0..n, lists

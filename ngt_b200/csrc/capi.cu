@@ -20,6 +20,7 @@
 #include <sstream>
 #include <stdexcept>
 #include <sys/stat.h>
+#include <unistd.h>
 
 #include "ngtgpu_internal.cuh"
 
@@ -311,46 +312,39 @@ void build_graph(CapiIndex &ix) {
     uint32_t m = (uint32_t)std::min<size_t>(131072, n - s);
     rc = ngtgpu_index_knn_graph(ix.gpu, k, (uint32_t)s + 1, m, d_ids + s * k, d_d + s * k, d_cnt + s, nullptr);
   }
-  std::vector<uint32_t> ids(n * k), cnt(n);
-  std::vector<float> ds(n * k);
+  // the ANNG: out-edges + reverse edges, sorted by (distance, id), repeated ids dropped -- on the device
+  uint64_t *d_rp = nullptr, nnz = 0;
+  uint32_t *d_col = nullptr;
+  float *d_dist = nullptr;
+  uint8_t *d_valid = nullptr;
+  const uint64_t cap = (uint64_t)n * k * 2;
+  if (rc == NGTGPU_OK &&
+      (cudaMalloc(&d_rp, (n + 2) * 8) != cudaSuccess || cudaMalloc(&d_col, cap * 4) != cudaSuccess ||
+       cudaMalloc(&d_dist, cap * 4) != cudaSuccess || cudaMalloc(&d_valid, n + 1) != cudaSuccess))
+    rc = NGTGPU_ERR_CUDA;
   if (rc == NGTGPU_OK) {
     cudaDeviceSynchronize();
-    cudaMemcpy(ids.data(), d_ids, n * k * 4, cudaMemcpyDeviceToHost);
-    cudaMemcpy(ds.data(), d_d, n * k * 4, cudaMemcpyDeviceToHost);
-    cudaMemcpy(cnt.data(), d_cnt, n * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(d_valid, ix.present.data(), n + 1, cudaMemcpyHostToDevice);
+    rc = ngtgpu_graph_from_knn_table(n, d_ids, d_d, d_cnt, k, d_valid, 1, cap, d_rp, d_col, d_dist, &nnz, nullptr);
+  }
+  if (rc == NGTGPU_OK) {
+    ix.row_ptr.assign(n + 2, 0);
+    ix.col.assign(nnz, 0);
+    ix.dist.assign(nnz, 0.f);
+    cudaMemcpy(ix.row_ptr.data(), d_rp, (n + 2) * 8, cudaMemcpyDeviceToHost);
+    if (nnz) {
+      cudaMemcpy(ix.col.data(), d_col, nnz * 4, cudaMemcpyDeviceToHost);
+      cudaMemcpy(ix.dist.data(), d_dist, nnz * 4, cudaMemcpyDeviceToHost);
+    }
   }
   cudaFree(d_ids);
   cudaFree(d_d);
   cudaFree(d_cnt);
+  cudaFree(d_rp);
+  cudaFree(d_col);
+  cudaFree(d_dist);
+  cudaFree(d_valid);
   check(rc);
-  struct Edge {
-    uint32_t src, dst;
-    float d;
-  };
-  std::vector<Edge> edges;
-  edges.reserve(n * k * 2);
-  for (size_t i = 0; i < n; i++) {
-    if (!ix.present[i + 1]) continue;
-    for (uint32_t r = 0; r < cnt[i]; r++) {
-      edges.push_back({(uint32_t)i + 1, ids[i * k + r], ds[i * k + r]});
-      edges.push_back({ids[i * k + r], (uint32_t)i + 1, ds[i * k + r]});
-    }
-  }
-  std::sort(edges.begin(), edges.end(), [](const Edge &a, const Edge &b) {
-    if (a.src != b.src) return a.src < b.src;
-    if (a.d != b.d) return a.d < b.d;
-    return a.dst < b.dst;
-  });
-  ix.row_ptr.assign(n + 2, 0);
-  ix.col.clear();
-  ix.dist.clear();
-  for (size_t e = 0; e < edges.size(); e++) {
-    if (e && edges[e].src == edges[e - 1].src && edges[e].dst == edges[e - 1].dst) continue;
-    ix.col.push_back(edges[e].dst);
-    ix.dist.push_back(edges[e].d);
-    ix.row_ptr[edges[e].src + 1]++;
-  }
-  for (size_t i = 1; i < n + 2; i++) ix.row_ptr[i] += ix.row_ptr[i - 1];
   ix.pending = 0;
   ix.prf["GraphType"] = "ANNG";
   check(ngtgpu_index_set_graph(ix.gpu, ix.row_ptr.data(), ix.col.data(), 0));
@@ -824,20 +818,225 @@ uint32_t ngt_get_object_repository_size(NGTIndex index, NGTError error) {
   return (uint32_t) static_cast<CapiIndex *>(index)->present.size();
 }
 
-// ---- outside the hot path: refused loudly ------------------------------------------------------------------
-static bool unsupported(const char *fn, NGTError error) {
+// ---- refineANNG and the ONNG recipe (GraphReconstructor / GraphOptimizer) on the device ------------------------
+}  // extern "C"
+
+namespace {
+
+struct DeviceGraph {   // a CSR with distances in device buffers of `cap` entries
+  size_t n = 0;
+  uint64_t *rp = nullptr;
+  uint32_t *col = nullptr;
+  float *dist = nullptr;
+  uint64_t cap = 0, nnz = 0;
+  DeviceGraph(size_t n_, uint64_t capacity) : n(n_), cap(std::max<uint64_t>(capacity, 1)) {
+    if (cudaMalloc(&rp, (n + 2) * 8) != cudaSuccess || cudaMalloc(&col, cap * 4) != cudaSuccess ||
+        cudaMalloc(&dist, cap * 4) != cudaSuccess) {
+      release();
+      throw std::runtime_error("cudaMalloc failed (graph buffers)");
+    }
+    cudaMemset(rp, 0, (n + 2) * 8);
+  }
+  DeviceGraph(const DeviceGraph &) = delete;
+  ~DeviceGraph() { release(); }
+  void release() {
+    cudaFree(rp);
+    cudaFree(col);
+    cudaFree(dist);
+    rp = nullptr, col = nullptr, dist = nullptr;
+  }
+  void from_host(const CapiIndex &ix) {
+    nnz = ix.col.size();
+    cudaMemcpy(rp, ix.row_ptr.data(), (n + 2) * 8, cudaMemcpyHostToDevice);
+    if (nnz) {
+      cudaMemcpy(col, ix.col.data(), nnz * 4, cudaMemcpyHostToDevice);
+      cudaMemcpy(dist, ix.dist.data(), nnz * 4, cudaMemcpyHostToDevice);
+    }
+  }
+  void to_host(CapiIndex &ix) const {
+    ix.row_ptr.assign(n + 2, 0);
+    ix.col.assign(nnz, 0);
+    ix.dist.assign(nnz, 0.f);
+    cudaMemcpy(ix.row_ptr.data(), rp, (n + 2) * 8, cudaMemcpyDeviceToHost);
+    if (nnz) {
+      cudaMemcpy(ix.col.data(), col, nnz * 4, cudaMemcpyDeviceToHost);
+      cudaMemcpy(ix.dist.data(), dist, nnz * 4, cudaMemcpyDeviceToHost);
+    }
+  }
+};
+
+struct CapiOptimizer {   // the settings of NGT::GraphOptimizer the C API reaches (GraphOptimizer.h:60-78, 600-650)
+  bool log_disabled = false;
+  int outgoing = 10, incoming = 120, queries = 100, results = 20;
+  size_t min_edges = 0;
+  bool shortcut_reduction = true;
+  bool search_parameter = true, prefetch_parameter = true, accuracy_table = true;
+};
+
+// GraphOptimizer::execute (GraphOptimizer.h:230-300): copy the index, reconstructGraph, path adjustment, save the graph
+// and the property. The search-parameter tuning that follows in the reference (optimizeSearchParameters, :302-350:
+// repeated timed searches on the host) is outside the hot path and is not run: `prf` keeps its search parameters.
+void optimizer_execute(const CapiOptimizer &o, const std::string &in, const std::string &out) {
+  if (access(out.c_str(), 0) == 0) throw std::runtime_error("Optimizer::execute: The specified index exists. " + out);
+  const std::string com = "cp -r " + in + " " + out;
+  if (system(com.c_str()) != 0) throw std::runtime_error("Optimizer::execute: Cannot create the specified index. " + out);
+  CapiIndex ix;
+  ix.path = out;
+  read_prf(ix);
+  uint64_t gslots = 0, nnz = 0;
+  const std::string grp = out + "/grp";
+  check(ngtgpu_io_grp_info(grp.c_str(), &gslots, &nnz));
+  if (gslots < 2) throw std::runtime_error("Optimizer::execute: the index holds no graph");
+  const size_t n = gslots - 1;
+  std::vector<uint64_t> rp(gslots + 1, 0);
+  ix.present.assign(n + 1, 0);
+  ix.col.assign(nnz ? nnz : 1, 0);
+  ix.dist.assign(nnz ? nnz : 1, 0.f);
+  check(ngtgpu_io_read_grp(grp.c_str(), rp.data(), ix.col.data(), ix.dist.data(), ix.present.data()));
+  ix.col.resize(nnz);
+  ix.dist.resize(nnz);
+  ix.row_ptr.assign(n + 2, nnz);
+  for (size_t i = 0; i < rp.size() && i < n + 2; i++) ix.row_ptr[i] = rp[i];
+  std::unique_ptr<DeviceGraph> g(new DeviceGraph(n, nnz));
+  g->from_host(ix);
+  if (o.outgoing > 0 || o.incoming > 0) {
+    if (ix.prf["GraphType"] != "ANNG") {   // convertToANNG (GraphReconstructor.h:389-423): add the reverse of every edge
+      std::unique_ptr<DeviceGraph> h(new DeviceGraph(n, 2 * g->nnz));
+      check(ngtgpu_graph_reconstruct(n, g->rp, g->col, g->dist, 0xffffffffu, 0xffffffffu, h->cap, h->rp, h->col, h->dist, &h->nnz,
+                                     nullptr));
+      g.swap(h);
+    }
+    std::unique_ptr<DeviceGraph> h(new DeviceGraph(n, 2 * g->nnz));
+    check(ngtgpu_graph_reconstruct(n, g->rp, g->col, g->dist, (uint32_t)std::max(o.outgoing, 0), (uint32_t)std::max(o.incoming, 0),
+                                   h->cap, h->rp, h->col, h->dist, &h->nnz, nullptr));
+    g.swap(h);
+    ix.prf["GraphType"] = "ONNG";
+  }
+  if (o.shortcut_reduction) {
+    uint8_t *keep = nullptr;
+    if (cudaMalloc(&keep, std::max<uint64_t>(g->nnz, 1)) != cudaSuccess) throw std::runtime_error("cudaMalloc failed (edge mask)");
+    int rc = ngtgpu_graph_adjust_paths(n, g->rp, g->col, g->dist, (uint32_t)o.min_edges, keep, nullptr, nullptr);
+    std::unique_ptr<DeviceGraph> h;
+    if (rc == NGTGPU_OK) {
+      h.reset(new DeviceGraph(n, g->nnz));
+      rc = ngtgpu_graph_select_edges(n, g->rp, g->col, g->dist, keep, h->rp, h->col, h->dist, &h->nnz, nullptr);
+    }
+    cudaFree(keep);
+    check(rc);
+    g.swap(h);
+  }
+  g->to_host(ix);
+  check(ngtgpu_io_write_grp(grp.c_str(), n, ix.row_ptr.data(), ix.col.data(), ix.dist.data(), ix.present.data()));
+  // (IndexType and the rest of the property stay as they were: only GraphType changes, GraphOptimizer.h:272-274)
+  std::ofstream f(out + "/prf");
+  if (!f.is_open()) throw std::runtime_error("PropertySet::save: Cannot save. " + out + "/prf");
+  for (auto &kv : ix.prf) f << kv.first << "\t" << kv.second << "\n";
+}
+
+}  // namespace
+
+extern "C" {
+
+// GraphReconstructor::refineANNG behind Capi.cpp:976-1004. expectedAccuracy > 0 needs the accuracy table the
+// optimizer's tuning writes (Index.h:1147-1149): not available here, refused loudly.
+bool ngt_refine_anng(NGTIndex index, float epsilon, float expectedAccuracy, int noOfEdges, int edgeSize, size_t batchSize,
+                     NGTError error) {
+  if (index == NULL) {
+    std::stringstream ss;
+    ss << "Capi : " << __FUNCTION__ << "() : parametor error: index = " << index;
+    operate_error_string(ss, error);
+    return false;
+  }
+  try {
+    CapiIndex &ix = *static_cast<CapiIndex *>(index);
+    require_built(ix);
+    if (expectedAccuracy > 0.0f) throw std::runtime_error("refineANNG: expected accuracy needs an accuracy table; give epsilon instead");
+    if (ix.row_ptr.size() != ix.n() + 2) throw std::runtime_error("refineANNG: the index holds no graph");
+    const size_t n = ix.n();
+    const int ec = ix.prop.edge_size_for_creation;
+    const uint32_t k = (uint32_t)(noOfEdges < 0 ? -noOfEdges : std::max(noOfEdges, ec));   // GraphReconstructor.h:825
+    if (k == 0) throw std::runtime_error("refineANNG: no edges to search for");
+    if (batchSize == 0) batchSize = 10000;
+    DeviceGraph g(n, ix.col.size() + 2ull * n * k);
+    g.from_host(ix);
+    const int64_t es = edgeSize == INT_MIN ? -1 : (int64_t)edgeSize;
+    check(ngtgpu_index_refine_anng(ix.gpu, epsilon, noOfEdges, es, k, batchSize, 10, g.cap, g.rp, g.col, g.dist, &g.nnz));
+    g.to_host(ix);
+    check(ngtgpu_index_set_search_property(ix.gpu, ix.prop.edge_size_for_search, prf_long(ix, "DynamicEdgeSizeBase", 30),
+                                           prf_long(ix, "DynamicEdgeSizeRate", 20)));
+  }
+  CAPI_CATCH(false)
+  return true;
+}
+
+NGTOptimizer ngt_create_optimizer(bool logDisabled, NGTError error) {
+  try {
+    CapiOptimizer *o = new CapiOptimizer;
+    o->log_disabled = logDisabled;
+    return static_cast<NGTOptimizer>(o);
+  }
+  CAPI_CATCH(NULL)
+}
+
+#define OPT_CHECK(ret)                                                                        \
+  if (optimizer == NULL) {                                                                    \
+    std::stringstream ss;                                                                     \
+    ss << "Capi : " << __FUNCTION__ << "() : parametor error: optimizer = " << optimizer;     \
+    operate_error_string(ss, error);                                                          \
+    return ret;                                                                               \
+  }
+
+// Search-coefficient tuning (GraphOptimizer::adjustSearchCoefficients: timed host searches) is outside the hot path.
+bool ngt_optimizer_adjust_search_coefficients(NGTOptimizer optimizer, const char *, NGTError error) {
+  OPT_CHECK(false)
   std::stringstream ss;
-  ss << "Capi : " << fn << "() : Error: not provided by the B200 engine (outside the search / construction hot path)";
+  ss << "Capi : " << __FUNCTION__ << "() : Error: not provided by the B200 engine (search-parameter tuning is outside the hot path)";
   operate_error_string(ss, error);
   return false;
 }
-bool ngt_refine_anng(NGTIndex, float, float, int, int, size_t, NGTError error) { return unsupported(__FUNCTION__, error); }
-NGTOptimizer ngt_create_optimizer(bool, NGTError error) {
-  unsupported(__FUNCTION__, error);
-  return NULL;
+
+bool ngt_optimizer_execute(NGTOptimizer optimizer, const char *inIndex, const char *outIndex, NGTError error) {
+  OPT_CHECK(false)
+  try {
+    if (inIndex == NULL || outIndex == NULL) throw std::runtime_error("Optimizer::execute: null index path");
+    optimizer_execute(*static_cast<CapiOptimizer *>(optimizer), inIndex, outIndex);
+  }
+  CAPI_CATCH(false)
+  return true;
 }
-bool ngt_optimizer_adjust_search_coefficients(NGTOptimizer, const char *, NGTError error) { return unsupported(__FUNCTION__, error); }
-bool ngt_optimizer_execute(NGTOptimizer, const char *, const char *, NGTError error) { return unsupported(__FUNCTION__, error); }
-void ngt_destroy_optimizer(NGTOptimizer) {}
+
+// Capi.cpp:907-975: negative values leave a setting as it is (GraphOptimizer::set, GraphOptimizer.h:600-628)
+bool ngt_optimizer_set(NGTOptimizer optimizer, int outgoing, int incoming, int nofqs, float, float, float, float, double,
+                       double, NGTError error) {
+  OPT_CHECK(false)
+  CapiOptimizer &o = *static_cast<CapiOptimizer *>(optimizer);
+  if (outgoing >= 0) o.outgoing = outgoing;
+  if (incoming >= 0) o.incoming = incoming;
+  if (nofqs > 0) o.queries = nofqs;
+  return true;
+}
+bool ngt_optimizer_set_minimum(NGTOptimizer optimizer, int outgoing, int incoming, int nofqs, int nofrs, NGTError error) {
+  OPT_CHECK(false)
+  CapiOptimizer &o = *static_cast<CapiOptimizer *>(optimizer);
+  if (outgoing >= 0) o.outgoing = outgoing;
+  if (incoming >= 0) o.incoming = incoming;
+  if (nofqs > 0) o.queries = nofqs;
+  if (nofrs > 0) o.results = nofrs;
+  return true;
+}
+bool ngt_optimizer_set_extension(NGTOptimizer optimizer, float, float, float, float, double, double, NGTError error) {
+  OPT_CHECK(false)
+  return true;   // accuracy ranges of the search-parameter tuning: kept for the signature, the tuning is not run here
+}
+bool ngt_optimizer_set_processing_modes(NGTOptimizer optimizer, bool searchParameter, bool prefetchParameter,
+                                        bool accuracyTable, NGTError error) {
+  OPT_CHECK(false)
+  CapiOptimizer &o = *static_cast<CapiOptimizer *>(optimizer);
+  o.search_parameter = searchParameter;
+  o.prefetch_parameter = prefetchParameter;
+  o.accuracy_table = accuracyTable;
+  return true;
+}
+void ngt_destroy_optimizer(NGTOptimizer optimizer) { delete static_cast<CapiOptimizer *>(optimizer); }
 
 }  // extern "C"

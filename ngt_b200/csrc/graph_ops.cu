@@ -423,3 +423,417 @@ extern "C" int ngtgpu_graph_adjust_paths(uint64_t n, const uint64_t *d_row_ptr, 
   }
   return NGTGPU_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// ngtgpu_graph_reconstruct -- GraphReconstructor::reconstructGraph (lib/NGT/GraphReconstructor.h:425-561), the first
+// step of ONNG construction: node i keeps its first `outgoing` edges (all of them when it has fewer, :447-456), every
+// node then receives the reverse of the first `incoming` edges of every other node, lists are sorted by
+// (distance, id) and an entry whose id repeats the previous entry's id is dropped (:519-533).
+// On the device: emit (source, distance, target) triples, two stable radix sorts (by (distance, target), then by
+// source), flag the survivors, compact.
+namespace {
+
+__global__ void emit_edges_kernel(const uint64_t *__restrict__ row_ptr, const uint32_t *__restrict__ col,
+                                  const float *__restrict__ dist, uint64_t n, uint32_t outgoing, uint32_t incoming,
+                                  uint32_t *__restrict__ out_src, uint64_t *__restrict__ out_key,
+                                  unsigned long long *__restrict__ counter) {
+  const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t id = warp; id <= n; id += warps) {
+    const uint64_t b = row_ptr[id];
+    const uint32_t deg = (uint32_t)(row_ptr[id + 1] - b);
+    const bool keep_all = deg < outgoing;
+    for (uint32_t r0 = 0; r0 < deg; r0 += 32) {
+      const uint32_t r = r0 + lane;
+      const bool have = r < deg;
+      const uint32_t t = have ? col[b + r] : 0u;
+      const uint32_t dord = have ? ord_of_float(dist[b + r]) : 0u;
+      const bool fwd = have && outgoing > 0 && (r < outgoing || keep_all);
+      const bool rev = have && r < incoming;
+      const uint32_t mf = __ballot_sync(0xffffffffu, fwd), mr = __ballot_sync(0xffffffffu, rev);
+      unsigned long long base = 0;
+      if (lane == 0 && (mf | mr)) base = atomicAdd(counter, (unsigned long long)(__popc(mf) + __popc(mr)));
+      base = shfl_u64(base, 0);
+      const uint32_t below = (1u << lane) - 1u;
+      if (fwd) {
+        const uint64_t p = base + __popc(mf & below);
+        out_src[p] = (uint32_t)id;
+        out_key[p] = ((uint64_t)dord << 32) | t;
+      }
+      if (rev) {
+        const uint64_t p = base + __popc(mf) + __popc(mr & below);
+        out_src[p] = t;
+        out_key[p] = ((uint64_t)dord << 32) | (uint32_t)id;
+      }
+    }
+  }
+}
+
+__global__ void flag_unique_kernel(const uint32_t *__restrict__ src, const uint64_t *__restrict__ key, uint64_t m,
+                                   uint8_t *__restrict__ flag, uint32_t *__restrict__ deg) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < m; i += (uint64_t)gridDim.x * blockDim.x) {
+    const bool keep = i == 0 || src[i] != src[i - 1] || (uint32_t)key[i] != (uint32_t)key[i - 1];
+    flag[i] = keep ? 1 : 0;
+    if (keep) atomicAdd(&deg[src[i]], 1u);
+  }
+}
+
+__global__ void unpack_edges_kernel(const uint64_t *__restrict__ key, uint64_t m, uint32_t *__restrict__ col,
+                                    float *__restrict__ dist) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < m; i += (uint64_t)gridDim.x * blockDim.x) {
+    col[i] = (uint32_t)key[i];
+    dist[i] = float_of_ord((uint32_t)(key[i] >> 32));
+  }
+}
+
+}  // namespace
+
+namespace {
+
+// Triples (source, (distance << 32 | target)) in src_a / key_a [m] -> CSR sorted by (source, distance, target) with
+// repeated (source, target) neighbours dropped. src_b / key_b are scratch of the same size; counter: 2 device words.
+int csr_from_triples(DeviceBuffers &mem, uint64_t n, uint32_t *src_a, uint32_t *src_b, uint64_t *key_a, uint64_t *key_b,
+                     unsigned long long *counter, uint64_t m, uint64_t capacity, uint64_t *d_out_row_ptr,
+                     uint32_t *d_out_col, float *d_out_dist, uint64_t *out_nnz, unsigned grid, cudaStream_t stream) {
+  int hi_bits = 1;
+  while (hi_bits < 32 && (n >> hi_bits) != 0) hi_bits++;
+  {
+    size_t t1 = 0, t2 = 0;
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, t1, key_a, key_b, src_a, src_b, (int64_t)m, 0, 64, stream));
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, t2, src_b, src_a, key_b, key_a, (int64_t)m, 0, hi_bits, stream));
+    uint8_t *tmp;
+    CUDA_TRY(mem.alloc(&tmp, t1 > t2 ? t1 : t2));
+    // by (distance, target) ...
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, t1, key_a, key_b, src_a, src_b, (int64_t)m, 0, 64, stream));
+    // ... then, stably, by source
+    CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, t2, src_b, src_a, key_b, key_a, (int64_t)m, 0, hi_bits, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    mem.release(tmp);
+  }
+  uint8_t *flag;
+  uint32_t *deg;
+  CUDA_TRY(mem.alloc(&flag, (size_t)m));
+  CUDA_TRY(mem.alloc(&deg, n + 2));
+  CUDA_TRY(cudaMemsetAsync(deg, 0, (n + 2) * 4, stream));
+  CUDA_TRY(cudaMemsetAsync(d_out_row_ptr, 0, sizeof(uint64_t), stream));
+  flag_unique_kernel<<<grid, 256, 0, stream>>>(src_a, key_a, m, flag, deg);
+  // surviving keys -> key_b, their number -> counter; row_ptr[1 + id] = sum of deg[0..id]
+  size_t t1 = 0, t2 = 0;
+  CUDA_TRY(cub::DeviceSelect::Flagged(nullptr, t1, key_a, flag, key_b, counter, (int64_t)m, stream));
+  CUDA_TRY(cub::DeviceScan::InclusiveScan(nullptr, t2, deg, d_out_row_ptr + 1, cub::Sum(), (int64_t)n + 1, stream));
+  uint8_t *tmp;
+  CUDA_TRY(mem.alloc(&tmp, t1 > t2 ? t1 : t2));
+  CUDA_TRY(cub::DeviceSelect::Flagged(tmp, t1, key_a, flag, key_b, counter, (int64_t)m, stream));
+  CUDA_TRY(cub::DeviceScan::InclusiveScan(tmp, t2, deg, d_out_row_ptr + 1, cub::Sum(), (int64_t)n + 1, stream));
+  unsigned long long kept = 0;
+  CUDA_TRY(cudaMemcpyAsync(&kept, counter, 8, cudaMemcpyDeviceToHost, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  mem.release(tmp);
+  mem.release(flag);
+  mem.release(deg);
+  if (kept > capacity)
+    NGTGPU_FAIL(NGTGPU_ERR_INVALID, "graph output capacity " + std::to_string(capacity) + " < " + std::to_string(kept) + " edges");
+  unpack_edges_kernel<<<grid, 256, 0, stream>>>(key_b, kept, d_out_col, d_out_dist);
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  CUDA_TRY(cudaGetLastError());
+  *out_nnz = kept;
+  return NGTGPU_OK;
+}
+
+}  // namespace
+
+extern "C" int ngtgpu_graph_reconstruct(uint64_t n, const uint64_t *d_row_ptr, const uint32_t *d_col, const float *d_dist,
+                                        uint32_t outgoing, uint32_t incoming, uint64_t capacity, uint64_t *d_out_row_ptr,
+                                        uint32_t *d_out_col, float *d_out_dist, uint64_t *out_nnz, void *stream_) {
+  if (!d_row_ptr || !d_out_row_ptr || !out_nnz) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "ngtgpu_graph_reconstruct: null buffer");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int dev = 0, sms = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const unsigned grid = (unsigned)sms * 8;
+  uint64_t nnz = 0;
+  CUDA_TRY(cudaMemcpyAsync(&nnz, d_row_ptr + n + 1, sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  *out_nnz = 0;
+  CUDA_TRY(cudaMemsetAsync(d_out_row_ptr, 0, (n + 2) * sizeof(uint64_t), stream));
+  if (nnz == 0) return NGTGPU_OK;
+  if (!d_col || !d_dist || !d_out_col || !d_out_dist) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "ngtgpu_graph_reconstruct: null buffer");
+  if (n >= 0xfffffffeull) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "ngtgpu_graph_reconstruct: too many nodes");
+  DeviceBuffers mem;
+  uint32_t *src_a, *src_b;
+  uint64_t *key_a, *key_b;
+  unsigned long long *counter;
+  const uint64_t cap2 = 2 * nnz;
+  CUDA_TRY(mem.alloc(&src_a, cap2));
+  CUDA_TRY(mem.alloc(&src_b, cap2));
+  CUDA_TRY(mem.alloc(&key_a, cap2));
+  CUDA_TRY(mem.alloc(&key_b, cap2));
+  CUDA_TRY(mem.alloc(&counter, 2));
+  CUDA_TRY(cudaMemsetAsync(counter, 0, 16, stream));
+  emit_edges_kernel<<<grid, 256, 0, stream>>>(d_row_ptr, d_col, d_dist, n, outgoing, incoming, src_a, key_a, counter);
+  unsigned long long m = 0;
+  CUDA_TRY(cudaMemcpyAsync(&m, counter, 8, cudaMemcpyDeviceToHost, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  if (m == 0) return NGTGPU_OK;
+  return csr_from_triples(mem, n, src_a, src_b, key_a, key_b, counter, m, capacity, d_out_row_ptr, d_out_col, d_out_dist,
+                          out_nnz, grid, stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// ngtgpu_index_refine_anng -- GraphReconstructor::refineANNG (lib/NGT/GraphReconstructor.h:814-924; C API
+// ngt_refine_anng): batch by batch, every object is searched for in the current graph (size = searched_edges, the given
+// epsilon / edge size), the results (the object itself excluded) are merged into its list (sort, repeated ids
+// dropped, :869-888), and -- unless a kNN graph was asked for (no_of_edges != 0) -- every result gets the reverse edge
+// (addEdge without identity check, :893-901). The next batch searches the refined graph. With no_of_edges > 0 the
+// lists are finally cut to that length (:904-917). The batch search is the traversal kernel; the merges are radix
+// sorts on the device.
+namespace {
+
+__global__ void refine_emit_kernel(const uint32_t *__restrict__ ids, const float *__restrict__ dists,
+                                   const uint32_t *__restrict__ counts, uint32_t first_id, uint32_t count, uint32_t k,
+                                   const uint8_t *__restrict__ valid, int reverse, uint32_t *__restrict__ out_src,
+                                   uint64_t *__restrict__ out_key, unsigned long long *__restrict__ counter) {
+  const uint64_t total = (uint64_t)count * k;
+  for (uint64_t x = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; x < total; x += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t q = (uint32_t)(x / k), r = (uint32_t)(x % k);
+    const uint32_t id = first_id + q;
+    if (valid && valid[id] == 0) continue;          // objectRepository.isEmpty(id)
+    const uint32_t c = counts[q];
+    if (c == 0xffffffffu || r >= c) continue;
+    const uint32_t t = ids[x];
+    if (t == id || t == 0) continue;                // :872
+    const uint32_t dord = ord_of_float(dists[x]);
+    const unsigned long long p = atomicAdd(counter, reverse ? 2ull : 1ull);
+    out_src[p] = id;
+    out_key[p] = ((uint64_t)dord << 32) | t;
+    if (reverse) {
+      out_src[p + 1] = t;
+      out_key[p + 1] = ((uint64_t)dord << 32) | id;
+    }
+  }
+}
+
+__global__ void truncate_lists_kernel(const uint64_t *__restrict__ row_ptr, uint64_t n, uint32_t keep, uint32_t *deg) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i <= n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t d = row_ptr[i + 1] - row_ptr[i];
+    deg[i] = (uint32_t)(d < keep ? d : keep);
+  }
+}
+
+__global__ void gather_truncated_kernel(const uint64_t *__restrict__ old_ptr, const uint64_t *__restrict__ new_ptr, uint64_t n,
+                                        const uint32_t *__restrict__ col, const float *__restrict__ dist,
+                                        uint32_t *__restrict__ out_col, float *__restrict__ out_dist) {
+  const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t id = warp; id <= n; id += warps) {
+    const uint64_t ob = old_ptr[id], nb = new_ptr[id], d = new_ptr[id + 1] - nb;
+    for (uint64_t i = lane; i < d; i += 32) {
+      out_col[nb + i] = col[ob + i];
+      out_dist[nb + i] = dist[ob + i];
+    }
+  }
+}
+
+}  // namespace
+
+// A [n x k] neighbour table (the exhaustive kNN pass, ngtgpu_index_knn_graph) -> CSR. symmetric != 0 adds the reverse
+// of every edge: the ANNG that insertANNGNode's out-edges + reverse edges (lib/NGT/Graph.h:611-626) converge to.
+extern "C" int ngtgpu_graph_from_knn_table(uint64_t n, const uint32_t *d_ids, const float *d_dists, const uint32_t *d_counts,
+                                           uint32_t k, const uint8_t *d_valid, int symmetric, uint64_t capacity,
+                                           uint64_t *d_out_row_ptr, uint32_t *d_out_col, float *d_out_dist, uint64_t *out_nnz,
+                                           void *stream_) {
+  if (!d_ids || !d_dists || !d_counts || !d_out_row_ptr || !d_out_col || !d_out_dist || !out_nnz)
+    NGTGPU_FAIL(NGTGPU_ERR_INVALID, "ngtgpu_graph_from_knn_table: null buffer");
+  if (n >= 0xfffffffeull) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "ngtgpu_graph_from_knn_table: too many nodes");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int dev = 0, sms = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const unsigned grid = (unsigned)sms * 8;
+  *out_nnz = 0;
+  CUDA_TRY(cudaMemsetAsync(d_out_row_ptr, 0, (n + 2) * sizeof(uint64_t), stream));
+  if (n == 0 || k == 0) return NGTGPU_OK;
+  DeviceBuffers mem;
+  const uint64_t m_max = (uint64_t)n * k * (symmetric ? 2 : 1);
+  uint32_t *src_a, *src_b;
+  uint64_t *key_a, *key_b;
+  unsigned long long *counter;
+  CUDA_TRY(mem.alloc(&src_a, m_max));
+  CUDA_TRY(mem.alloc(&src_b, m_max));
+  CUDA_TRY(mem.alloc(&key_a, m_max));
+  CUDA_TRY(mem.alloc(&key_b, m_max));
+  CUDA_TRY(mem.alloc(&counter, 2));
+  CUDA_TRY(cudaMemsetAsync(counter, 0, 16, stream));
+  refine_emit_kernel<<<grid, 256, 0, stream>>>(d_ids, d_dists, d_counts, 1u, (uint32_t)n, k, d_valid, symmetric ? 1 : 0, src_a,
+                                               key_a, counter);
+  unsigned long long m = 0;
+  CUDA_TRY(cudaMemcpyAsync(&m, counter, 8, cudaMemcpyDeviceToHost, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  if (m == 0) return NGTGPU_OK;
+  return csr_from_triples(mem, n, src_a, src_b, key_a, key_b, counter, m, capacity, d_out_row_ptr, d_out_col, d_out_dist,
+                          out_nnz, grid, stream);
+}
+
+namespace {
+__global__ void kept_degree_kernel(const uint64_t *__restrict__ row_ptr, uint64_t n, const uint8_t *__restrict__ keep,
+                                   uint32_t *__restrict__ deg) {
+  const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t id = warp; id <= n; id += warps) {
+    uint32_t c = 0;
+    for (uint64_t e = row_ptr[id] + lane; e < row_ptr[id + 1]; e += 32) c += keep[e] ? 1 : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) deg[id] = c;
+  }
+}
+__global__ void gather_kept_kernel(const uint64_t *__restrict__ row_ptr, const uint64_t *__restrict__ new_ptr, uint64_t n,
+                                   const uint8_t *__restrict__ keep, const uint32_t *__restrict__ col,
+                                   const float *__restrict__ dist, uint32_t *__restrict__ out_col, float *__restrict__ out_dist) {
+  const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t id = warp; id <= n; id += warps) {
+    uint64_t w = new_ptr[id];
+    const uint64_t b = row_ptr[id], e = row_ptr[id + 1];
+    for (uint64_t e0 = b; e0 < e; e0 += 32) {
+      const uint64_t i = e0 + lane;
+      const bool k = i < e && keep[i];
+      const uint32_t m = __ballot_sync(0xffffffffu, k);
+      if (k) {
+        const uint64_t p = w + __popc(m & ((1u << lane) - 1u));
+        out_col[p] = col[i];
+        out_dist[p] = dist[i];
+      }
+      w += __popc(m);
+    }
+  }
+}
+}  // namespace
+
+// The sub-graph of the edges with keep[e] != 0 (order inside the lists preserved). DEVICE buffers; out_col / out_dist
+// need as many entries as edges are kept (the input's count always suffices).
+extern "C" int ngtgpu_graph_select_edges(uint64_t n, const uint64_t *d_row_ptr, const uint32_t *d_col, const float *d_dist,
+                                         const uint8_t *d_keep, uint64_t *d_out_row_ptr, uint32_t *d_out_col,
+                                         float *d_out_dist, uint64_t *out_nnz, void *stream_) {
+  if (!d_row_ptr || !d_out_row_ptr || !out_nnz) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "ngtgpu_graph_select_edges: null buffer");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int dev = 0, sms = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const unsigned grid = (unsigned)sms * 8;
+  DeviceBuffers mem;
+  uint32_t *deg;
+  CUDA_TRY(mem.alloc(&deg, n + 2));
+  CUDA_TRY(cudaMemsetAsync(d_out_row_ptr, 0, 8, stream));
+  kept_degree_kernel<<<grid, 256, 0, stream>>>(d_row_ptr, n, d_keep, deg);
+  size_t tb = 0;
+  CUDA_TRY(cub::DeviceScan::InclusiveScan(nullptr, tb, deg, d_out_row_ptr + 1, cub::Sum(), (int64_t)n + 1, stream));
+  uint8_t *tmp;
+  CUDA_TRY(mem.alloc(&tmp, tb));
+  CUDA_TRY(cub::DeviceScan::InclusiveScan(tmp, tb, deg, d_out_row_ptr + 1, cub::Sum(), (int64_t)n + 1, stream));
+  gather_kept_kernel<<<grid, 256, 0, stream>>>(d_row_ptr, d_out_row_ptr, n, d_keep, d_col, d_dist, d_out_col, d_out_dist);
+  CUDA_TRY(cudaMemcpyAsync(out_nnz, d_out_row_ptr + n + 1, 8, cudaMemcpyDeviceToHost, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  CUDA_TRY(cudaGetLastError());
+  return NGTGPU_OK;
+}
+
+int ngtgpu_search_prepared(ngtgpu_index *ix, const uint8_t *d_queries, uint32_t nq, const ngtgpu_search_params *params,
+                           uint32_t n_seeds, uint32_t *d_ids, float *d_dists, uint32_t *d_counts, cudaStream_t stream);
+
+extern "C" int ngtgpu_index_refine_anng(ngtgpu_index *ix, float epsilon, int32_t no_of_edges, int64_t edge_size,
+                                        uint32_t searched_edges, uint64_t batch_size, uint32_t n_seeds, uint64_t capacity,
+                                        uint64_t *d_row_ptr, uint32_t *d_col, float *d_dist, uint64_t *nnz_out) {
+  if (!ix) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "null index handle");
+  NGTGPU_TRY(ngtgpu_check_device(ix));
+  if (!d_row_ptr || !d_col || !d_dist || !nnz_out) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "ngtgpu_index_refine_anng: null buffer");
+  if (!ix->d_objects || ix->n == 0) NGTGPU_FAIL(NGTGPU_ERR_STATE, "ngtgpu_index_refine_anng: the index holds no objects");
+  if (searched_edges == 0 || batch_size == 0) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "ngtgpu_index_refine_anng: zero size");
+  cudaStream_t stream = ix->stream;
+  const uint64_t n = ix->n;
+  const unsigned grid = (unsigned)ix->sm_count * 8;
+  const uint32_t k = searched_edges;
+  if (batch_size > n) batch_size = n;
+  uint64_t nnz = 0;
+  CUDA_TRY(cudaMemcpyAsync(&nnz, d_row_ptr + n + 1, 8, cudaMemcpyDeviceToHost, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  DeviceBuffers mem;
+  uint32_t *r_ids, *r_counts, *t_col;
+  float *r_dists, *t_dist;
+  uint64_t *t_ptr;
+  unsigned long long *counter;
+  CUDA_TRY(mem.alloc(&r_ids, batch_size * k));
+  CUDA_TRY(mem.alloc(&r_dists, batch_size * k));
+  CUDA_TRY(mem.alloc(&r_counts, batch_size));
+  CUDA_TRY(mem.alloc(&t_ptr, n + 2));
+  CUDA_TRY(mem.alloc(&t_col, capacity));
+  CUDA_TRY(mem.alloc(&t_dist, capacity));
+  CUDA_TRY(mem.alloc(&counter, 2));
+  ngtgpu_search_params sp;
+  sp.size = k;
+  sp.epsilon = epsilon;
+  sp.radius = -1.0f;
+  sp.edge_size = edge_size;
+  for (uint64_t bid = 1; bid <= n; bid += batch_size) {
+    const uint32_t count = (uint32_t)(n - bid + 1 < batch_size ? n - bid + 1 : batch_size);
+    NGTGPU_TRY(ngtgpu_index_set_graph(ix, d_row_ptr, d_col, 1));
+    NGTGPU_TRY(ngtgpu_search_prepared(ix, ix->d_objects + bid * ix->row_bytes, count, &sp, n_seeds, r_ids, r_dists, r_counts,
+                                      stream));
+    // old edges + new triples -> the refined graph
+    const uint64_t m_max = nnz + 2ull * count * k;
+    uint32_t *src_a, *src_b;
+    uint64_t *key_a, *key_b;
+    CUDA_TRY(mem.alloc(&src_a, m_max));
+    CUDA_TRY(mem.alloc(&src_b, m_max));
+    CUDA_TRY(mem.alloc(&key_a, m_max));
+    CUDA_TRY(mem.alloc(&key_b, m_max));
+    CUDA_TRY(cudaMemsetAsync(counter, 0, 16, stream));
+    emit_edges_kernel<<<grid, 256, 0, stream>>>(d_row_ptr, d_col, d_dist, n, 0xffffffffu, 0u, src_a, key_a, counter);
+    refine_emit_kernel<<<grid, 256, 0, stream>>>(r_ids, r_dists, r_counts, (uint32_t)bid, count, k, ix->d_valid,
+                                                 no_of_edges == 0 ? 1 : 0, src_a, key_a, counter);
+    ix->launches += 2;
+    unsigned long long m = 0;
+    CUDA_TRY(cudaMemcpyAsync(&m, counter, 8, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    if (m) {
+      uint64_t out_nnz = 0;
+      NGTGPU_TRY(csr_from_triples(mem, n, src_a, src_b, key_a, key_b, counter, m, capacity, t_ptr, t_col, t_dist, &out_nnz, grid,
+                                  stream));
+      CUDA_TRY(cudaMemcpyAsync(d_row_ptr, t_ptr, (n + 2) * 8, cudaMemcpyDeviceToDevice, stream));
+      CUDA_TRY(cudaMemcpyAsync(d_col, t_col, out_nnz * 4, cudaMemcpyDeviceToDevice, stream));
+      CUDA_TRY(cudaMemcpyAsync(d_dist, t_dist, out_nnz * 4, cudaMemcpyDeviceToDevice, stream));
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      nnz = out_nnz;
+    }
+    mem.release(src_a);
+    mem.release(src_b);
+    mem.release(key_a);
+    mem.release(key_b);
+  }
+  if (no_of_edges > 0) {   // prune to a kNN graph, GraphReconstructor.h:904-917
+    uint32_t *deg;
+    CUDA_TRY(mem.alloc(&deg, n + 2));
+    truncate_lists_kernel<<<grid, 256, 0, stream>>>(d_row_ptr, n, (uint32_t)no_of_edges, deg);
+    size_t tb = 0;
+    CUDA_TRY(cudaMemsetAsync(t_ptr, 0, 8, stream));
+    CUDA_TRY(cub::DeviceScan::InclusiveScan(nullptr, tb, deg, t_ptr + 1, cub::Sum(), (int64_t)n + 1, stream));
+    uint8_t *tmp;
+    CUDA_TRY(mem.alloc(&tmp, tb));
+    CUDA_TRY(cub::DeviceScan::InclusiveScan(tmp, tb, deg, t_ptr + 1, cub::Sum(), (int64_t)n + 1, stream));
+    gather_truncated_kernel<<<grid, 256, 0, stream>>>(d_row_ptr, t_ptr, n, d_col, d_dist, t_col, t_dist);
+    CUDA_TRY(cudaMemcpyAsync(&nnz, t_ptr + n + 1, 8, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    CUDA_TRY(cudaMemcpyAsync(d_row_ptr, t_ptr, (n + 2) * 8, cudaMemcpyDeviceToDevice, stream));
+    CUDA_TRY(cudaMemcpyAsync(d_col, t_col, nnz * 4, cudaMemcpyDeviceToDevice, stream));
+    CUDA_TRY(cudaMemcpyAsync(d_dist, t_dist, nnz * 4, cudaMemcpyDeviceToDevice, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    ix->launches += 3;
+  }
+  NGTGPU_TRY(ngtgpu_index_set_graph(ix, d_row_ptr, d_col, 1));
+  *nnz_out = nnz;
+  return NGTGPU_OK;
+}

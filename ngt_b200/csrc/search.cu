@@ -210,6 +210,18 @@ static int select_seeds(ngtgpu_index *ix, const uint8_t *d_queries, uint32_t nq,
   return NGTGPU_OK;
 }
 
+// prepared (padded, object-type) query rows already on the device, e.g. stored objects: seeds from the pivot table,
+// then the traversal. Used by the batched self-search of refineANNG (graph_ops.cu).
+int ngtgpu_search_prepared(ngtgpu_index *ix, const uint8_t *d_queries, uint32_t nq, const ngtgpu_search_params *params,
+                           uint32_t n_seeds, uint32_t *d_ids, float *d_dists, uint32_t *d_counts, cudaStream_t stream) {
+  if (nq == 0) return NGTGPU_OK;
+  uint32_t *s = nullptr;
+  uint32_t ns = n_seeds;
+  if (ns > ix->n_pivots) ns = ix->n_pivots;
+  NGTGPU_TRY(select_seeds(ix, d_queries, nq, ns, &s, stream));
+  return ngtgpu_traverse(ix, d_queries, nq, params, s, ns, d_ids, d_dists, d_counts, nullptr, stream);
+}
+
 static int search_common(ngtgpu_index *ix, const void *queries, int query_type, uint32_t nq,
                          const ngtgpu_search_params *params, const uint32_t *seeds, uint32_t n_seeds, uint32_t *ids,
                          float *dists, uint32_t *counts, uint32_t *stats, bool on_device, cudaStream_t stream) {

@@ -313,3 +313,46 @@ def adjust_paths_loop(row_ptr, col, dist, min_edges=0):
         ids = nxt
         rank += 1
     return [sorted(((d, i) for i, d in o.items())) for o in out]   # :373-383: sorted by (distance, id)
+
+
+def refine_anng_loop(port, dtype, otype, pobj, row_ptr, col, dist, seeds, epsilon=0.1, no_of_edges=0,
+                     edge_size=2 ** 31 - 1, batch_size=10000, edge_size_for_creation=10):
+    """Sequential restatement of GraphReconstructor::refineANNG (lib/NGT/GraphReconstructor.h:814-924) over the C
+    restatement of the search (Port.graph_search) with explicit seeds per object (seeds[id - 1]); test infrastructure.
+    pobj: padded objects [(n+1) x padDim]. -> per id 0..n a list of (distance, id) ascending."""
+    n = pobj.shape[0] - 1
+    lists = [[(float(dist[e]), int(col[e])) for e in range(int(row_ptr[i]), int(row_ptr[i + 1]))] for i in range(n + 1)]
+    k = -no_of_edges if no_of_edges < 0 else max(no_of_edges, edge_size_for_creation)        # :825
+    for bid in range(1, n + 1, batch_size):
+        ids_b = list(range(bid, min(bid + batch_size, n + 1)))
+        rp = np.zeros(n + 2, np.uint64)
+        rp[1:] = np.cumsum([len(l) for l in lists])
+        cc = np.array([t for l in lists for (_, t) in l], np.uint32)
+        r_ids, r_d, r_cnt, _ = port.graph_search(dtype, otype, pobj, rp, cc, pobj[bid:bid + len(ids_b)],
+                                                 seeds[bid - 1:bid - 1 + len(ids_b)], k, epsilon, edge_size=edge_size)
+        for x, nid in enumerate(ids_b):                                                          # :869-888
+            node = lists[nid] + [(float(r_d[x, r]), int(r_ids[x, r])) for r in range(int(r_cnt[x])) if int(r_ids[x, r]) != nid]
+            node.sort()
+            out, prev = [], 0
+            for e in node:
+                if e[1] == prev:
+                    continue
+                prev = e[1]
+                out.append(e)
+            lists[nid] = out
+        if no_of_edges != 0:
+            continue
+        for x, nid in enumerate(ids_b):                                                          # :893-901, Graph.h:845-875
+            for r in range(int(r_cnt[x])):
+                t, d = int(r_ids[x, r]), float(r_d[x, r])
+                if t == nid:
+                    continue
+                node = lists[t]
+                import bisect
+                pos = bisect.bisect_left(node, (d, nid))
+                if pos < len(node) and node[pos][1] == nid:
+                    continue
+                node.insert(pos, (d, nid))
+    if no_of_edges > 0:
+        lists = [l[:no_of_edges] for l in lists]
+    return lists

@@ -51,6 +51,14 @@ def bind(path):
         "ngt_get_object_as_integer": (C.POINTER(C.c_uint8), [P, C.c_uint32, P]),
         "ngt_get_edges": (C.c_bool, [P, C.c_uint32, P, P]), "ngt_get_object_repository_size": (C.c_uint32, [P, P]),
         "ngt_refine_anng": (C.c_bool, [P, C.c_float, C.c_float, C.c_int, C.c_int, C.c_size_t, P]),
+        "ngt_create_optimizer": (P, [C.c_bool, P]), "ngt_destroy_optimizer": (None, [P]),
+        "ngt_optimizer_execute": (C.c_bool, [P, C.c_char_p, C.c_char_p, P]),
+        "ngt_optimizer_adjust_search_coefficients": (C.c_bool, [P, C.c_char_p, P]),
+        "ngt_optimizer_set": (C.c_bool, [P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_double,
+                                         C.c_double, P]),
+        "ngt_optimizer_set_minimum": (C.c_bool, [P, C.c_int, C.c_int, C.c_int, C.c_int, P]),
+        "ngt_optimizer_set_extension": (C.c_bool, [P, C.c_float, C.c_float, C.c_float, C.c_float, C.c_double, C.c_double, P]),
+        "ngt_optimizer_set_processing_modes": (C.c_bool, [P, C.c_bool, C.c_bool, C.c_bool, P]),
         # additive batch entry points
         "ngt_batch_search_index_as_float": (C.c_bool, [P, F, C.c_uint32, C.c_int32, C.c_size_t, C.c_float, C.c_float, C.c_int64,
                                                        C.POINTER(C.c_uint32), F, C.POINTER(C.c_uint32), P]),

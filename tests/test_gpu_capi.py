@@ -121,3 +121,72 @@ def test_create_append_build_save_reopen(lib, tmp_path):
     lib.ngt_destroy_results(r)
     lib.ngt_destroy_property(prop)
     lib.ngt_destroy_error_object(err)
+
+
+def _edges(lib, ix, n, err):
+    r = lib.ngt_create_empty_results(err)
+    out = []
+    for i in range(1, n + 1):
+        assert lib.ngt_get_edges(ix, i, r, err), lib.ngt_get_error_string(err)
+        out.append(capi.results_of(lib, r, err))
+    lib.ngt_destroy_results(r)
+    return out
+
+
+def test_optimizer_execute_equals_the_reference_onng(lib, tmp_path):
+    """ngt_optimizer_execute (GraphOptimizer::execute: reconstructGraph + path adjustment) on an ANNG written in NGT's
+    own format from the reference's adjacency lists (tests/golden/reconstruct.npz) == the ONNG the reference wrote
+    (tests/golden/adjust_paths.npz), edge for edge."""
+    from ngt_b200 import index_io, synth
+    z = np.load(os.path.join(GOLDEN, "reconstruct.npz"))
+    a = np.load(os.path.join(GOLDEN, "adjust_paths.npz"))
+    base = synth.make("sift", 1500, 1)
+    src = str(tmp_path / "anng")
+    os.makedirs(src)
+    prf = dict(index_io.DEFAULT_PRF, Dimension="128", EdgeSizeForCreation="20", EdgeSizeForSearch="0")
+    index_io.write_prf(src, prf)
+    index_io.write_objects(src, base)
+    index_io.write_graph(src, z["anng_row_ptr"].astype(np.uint64), z["anng_col"], z["anng_dist"])
+    err = lib.ngt_create_error_object()
+    for o, i, shortcut, key in ((5, 20, True, "sift_o5_i20_adj"), (10, 40, True, "sift_o10_i40_adj")):
+        dst = str(tmp_path / ("onng_%d_%d" % (o, i)))
+        opt = lib.ngt_create_optimizer(True, err)
+        assert lib.ngt_optimizer_set_minimum(opt, o, i, -1, -1, err)
+        assert lib.ngt_optimizer_set_processing_modes(opt, False, False, False, err)
+        assert lib.ngt_optimizer_execute(opt, src.encode(), dst.encode(), err), lib.ngt_get_error_string(err)
+        lib.ngt_destroy_optimizer(opt)
+        ix = lib.ngt_open_index(dst.encode(), err)
+        assert ix, lib.ngt_get_error_string(err)
+        got = _edges(lib, ix, 1500, err)
+        rp, col, dist = a[key + "_row_ptr"], a[key + "_col"], a[key + "_dist"]
+        for nid in range(1, 1501):
+            ref = [(int(col[e]), float(dist[e])) for e in range(int(rp[nid]), int(rp[nid + 1]))]
+            assert got[nid - 1] == ref, (key, nid)
+        lib.ngt_close_index(ix)
+        assert "ONNG" in open(os.path.join(dst, "prf")).read()
+    lib.ngt_destroy_error_object(err)
+
+
+def test_refine_anng_through_the_c_api(lib, tmp_path):
+    from ngt_b200 import synth
+    err = lib.ngt_create_error_object()
+    prop = lib.ngt_create_property(err)
+    assert lib.ngt_set_property_dimension(prop, 128, err) and lib.ngt_set_property_edge_size_for_creation(prop, 6, err)
+    ix = lib.ngt_create_graph_and_tree_in_memory(prop, err)
+    base = synth.make("sift", 2000, 4)
+    assert lib.ngt_batch_append_index(ix, capi.fptr(base), 2000, err) and lib.ngt_create_index(ix, 4, err)
+    before = sum(len(e) for e in _edges(lib, ix, 2000, err))
+    assert lib.ngt_refine_anng(ix, 0.1, 0.0, 0, -2147483648, 500, err), lib.ngt_get_error_string(err)
+    assert sum(len(e) for e in _edges(lib, ix, 2000, err)) >= before     # the exact 6-NN closure has little left to find
+    assert lib.ngt_refine_anng(ix, 0.1, 0.0, -12, -2147483648, 800, err), lib.ngt_get_error_string(err)   # search 12 edges
+    lists = _edges(lib, ix, 2000, err)
+    assert sum(len(e) for e in lists) > before and min(len(e) for e in lists) >= 11     # 12 results, the object itself among them
+    for nid, l in enumerate(lists, 1):       # sorted by (distance, id), no self loops, no repeated ids
+        assert all(t != nid for t, _ in l) and len({t for t, _ in l}) == len(l)
+        assert [(d, t) for t, d in l] == sorted((d, t) for t, d in l)
+    assert lib.ngt_refine_anng(ix, 0.1, 0.5, 0, 0, 500, err) is False and b"accuracy table" in lib.ngt_get_error_string(err)
+    assert lib.ngt_refine_anng(ix, 0.1, 0.0, 4, -2147483648, 500, err), lib.ngt_get_error_string(err)     # prune to a 4-NN graph
+    assert max(len(e) for e in _edges(lib, ix, 2000, err)) == 4
+    lib.ngt_close_index(ix)
+    lib.ngt_destroy_property(prop)
+    lib.ngt_destroy_error_object(err)

@@ -70,3 +70,71 @@ def test_adjust_paths_empty_and_edgeless(eng):
     assert out[1].numel() == 0 and int(out[0][-1]) == 0
     with pytest.raises(eng.NgtGpuError):
         build.adjust_paths(rp.cpu(), torch.zeros(0, dtype=torch.int32), torch.zeros(0))
+
+
+@pytest.mark.parametrize("o,i", [(5, 20), (10, 40), (0, 15)])
+def test_reconstruct_graph_on_device_equals_the_reference(eng, o, i):
+    """ngtgpu_graph_reconstruct against the graph the reference's GraphOptimizer::execute wrote from its own ANNG
+    (path adjustment off): tests/golden/reconstruct.npz."""
+    import torch
+    from ngt_b200 import build
+    z = np.load(os.path.join(GOLDEN, "reconstruct.npz"))
+    dev = torch.device("cuda", 0)
+    rp, col, dist = build.reconstruct_graph_device(torch.from_numpy(z["anng_row_ptr"].astype(np.int64)).to(dev),
+                                                   torch.from_numpy(z["anng_col"].astype(np.int32)).to(dev),
+                                                   torch.from_numpy(z["anng_dist"]).to(dev), o, i)
+    key = "o%d_i%d" % (o, i)
+    assert (rp.cpu().numpy() == z[key + "_row_ptr"].astype(np.int64)).all()
+    assert (col.cpu().numpy().astype(np.uint32) == z[key + "_col"]).all()
+    assert (dist.cpu().numpy().view(np.uint32) == z[key + "_dist"].view(np.uint32)).all()
+
+
+def test_onng_recipe_end_to_end_equals_the_reference(eng):
+    """reconstruct + adjust on the device == `ngt reconstruct-graph -o 5 -i 20` of the reference on its own ANNG."""
+    import torch
+    from ngt_b200 import build
+    z = np.load(os.path.join(GOLDEN, "reconstruct.npz"))
+    a = np.load(os.path.join(GOLDEN, "adjust_paths.npz"))
+    dev = torch.device("cuda", 0)
+    # (adjust_paths.npz's sift ANNG is reconstruct.npz's: same data, same build parameters)
+    assert (a["sift_o5_i20_in_col"] == z["o5_i20_col"]).all()
+    g = build.reconstruct_graph_device(torch.from_numpy(z["anng_row_ptr"].astype(np.int64)).to(dev),
+                                       torch.from_numpy(z["anng_col"].astype(np.int32)).to(dev),
+                                       torch.from_numpy(z["anng_dist"]).to(dev), 5, 20)
+    rp, col, dist = build.adjust_paths(*g)
+    assert (rp.cpu().numpy() == a["sift_o5_i20_adj_row_ptr"].astype(np.int64)).all()
+    assert (col.cpu().numpy().astype(np.uint32) == a["sift_o5_i20_adj_col"]).all()
+
+
+@pytest.mark.parametrize("no_of_edges,batch", [(0, 700), (0, 10000), (12, 900), (-6, 10000)])
+def test_refine_anng_equals_the_sequential_restatement(eng, port, no_of_edges, batch):
+    """GraphReconstructor::refineANNG on the device (batched self-search + merges) against the sequential restatement
+    over the C oracle's search, same seeds: integer-valued L2 data, so ids and distance bits must be identical."""
+    import ctypes as C
+    import torch
+    from ngt_b200 import _lib, build, synth
+    n, ec = 2500, 8
+    base = synth.make("sift", n, 11)
+    ix = eng.GpuIndex(po.FLOAT, po.L2, base.shape[1])
+    ix.set_objects(base)
+    ids, dists, counts = build.knn_graph(ix, 6)
+    rp, col, dist = build.reconstruct_graph(ids, dists, counts, 6, 6)      # a sparse ANNG-like start
+    ix.set_graph(rp, col)
+    ix.build_seed_table(256, 5)
+    lib = _lib.load()
+    lib.ngtgpu_select_seeds.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p]
+    seeds = np.zeros((n, 10), np.uint32)
+    _lib.check(lib.ngtgpu_select_seeds(ix._h, base.ctypes.data, _lib.OBJECT_FLOAT, n, 10, seeds.ctypes.data))
+    out_rp, out_col, out_dist = build.refine_anng(ix, rp, col, dist, epsilon=0.1, no_of_edges=no_of_edges, edge_size=-1,
+                                                   batch_size=batch, edge_size_for_creation=ec, n_seeds=10)
+    got = _lists(out_rp.cpu().numpy(), out_col.cpu().numpy().astype(np.uint32), out_dist.cpu().numpy())
+    pobj = po.pad_objects(base, po.FLOAT)
+    ref = po.refine_anng_loop(port, po.L2, po.FLOAT, pobj, rp.cpu().numpy(), col.cpu().numpy().astype(np.uint32),
+                              dist.cpu().numpy(), seeds, 0.1, no_of_edges, 40, batch, ec)
+    assert got == ref
+    assert no_of_edges < 0 or out_col.numel() != col.numel()
+    # the index now searches the refined graph
+    if no_of_edges == 0:
+        r = ix.search(base[:50], 5, 0.1)
+        assert (r[0][:, 0] == np.arange(1, 51)).all()
+    ix.close()

@@ -232,9 +232,20 @@ def test_ngt_c_api_symbols_and_error_convention():
     assert lib.ngt_is_property_object_type_integer(lib.ngt_get_property_object_type(prop, err))
     assert lib.ngt_set_property_distance_type_hamming(prop, err) and lib.ngt_get_property_distance_type(prop, err) == 2
     assert lib.ngt_get_property_dimension(None, err) == -1
-    # outside the hot path: refused, loudly
+    # refine / optimizer: same parameter-error convention as the reference (Capi.cpp:889-895, 976-983)
     assert lib.ngt_refine_anng(None, 0.1, 0.0, 0, 0, 100, err) is False
+    assert lib.ngt_get_error_string(err).decode() == "Capi : ngt_refine_anng() : parametor error: index = 0"
+    opt = lib.ngt_create_optimizer(True, err)
+    assert opt and lib.ngt_optimizer_set_minimum(opt, 5, 20, -1, -1, err)
+    assert lib.ngt_optimizer_execute(None, b"a", b"b", err) is False
+    assert lib.ngt_get_error_string(err).decode().startswith("Capi : ngt_optimizer_execute() : parametor error: optimizer = ")
+    assert lib.ngt_optimizer_execute(opt, b"/nonexistent/in", b"/tmp", err) is False        # the output exists
+    assert lib.ngt_get_error_string(err).decode() == \
+        "Capi : ngt_optimizer_execute() : Error: Optimizer::execute: The specified index exists. /tmp"
+    # search-parameter tuning is outside the hot path: refused, loudly
+    assert lib.ngt_optimizer_adjust_search_coefficients(opt, b"x", err) is False
     assert "not provided by the B200 engine" in lib.ngt_get_error_string(err).decode()
+    lib.ngt_destroy_optimizer(opt)
     import torch
     if not torch.cuda.is_available():
         # no device: opening a real index fails with a message, it does not fall back to the CPU
