@@ -34,7 +34,7 @@
 #define TC_TILE_BYTES (TC_TILE * TC_KCHUNK * 2)   // 16 KB: one operand tile of one k-chunk
 #define TC_STAGES 4
 #define TC_MAX_KCHUNKS 6       // resident query operand <= 96 KB
-#define TC_MAX_K 100           // heap of k floats per query in shared memory
+#define TC_MAX_K 128           // heap of k floats per query in shared memory
 #define TC_THREADS 192
 #define TC_CAND_CAP 2048       // candidate ids per (query, split)
 
@@ -48,6 +48,16 @@ struct TcPacked {
 };
 
 // ---- operand preparation --------------------------------------------------------------------------------
+// Element d of a stored row as a float, for the three object layouts the engine holds (kind 0: float32, 1: uint8,
+// 2: bit vectors for Hamming -- one K element per bit). uint8 values and bits are bf16 numbers exactly, their products
+// and sums (< 2^24) are exact in the fp32 accumulator, so for integer kinds the tensor-core score IS the squared L2
+// distance / the Hamming distance (||a||^2 + ||b||^2 - 2ab with 0/1 entries).
+__device__ __forceinline__ float tc_elem(const uint8_t *rows, int kind, uint64_t row, uint32_t row_bytes, uint32_t d) {
+  const uint8_t *r = rows + row * (uint64_t)row_bytes;
+  if (kind == 0) return reinterpret_cast<const float *>(r)[d];
+  if (kind == 1) return (float)r[d];
+  return (float)((r[d >> 3] >> (d & 7)) & 1);
+}
 __global__ void tc_check_exact_kernel(const float *__restrict__ rows, uint64_t count, int *flag) {
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (uint64_t)gridDim.x * blockDim.x) {
     float x = rows[i];
@@ -65,7 +75,7 @@ __global__ void tc_check_exact_kernel(const float *__restrict__ rows, uint64_t c
 //     A extra = [qn0 qn1 qn2 1 1 1 0 ...],  B extra = [1 1 1 rn0 rn1 rn2 0 ...]
 // so the accumulator IS ||q||^2 + ||x||^2 - 2 q.x and the epilogue only compares. Padding / empty rows get a huge
 // finite norm (3e38) and can never pass.
-__global__ void tc_pack_kernel(const float *__restrict__ rows, uint64_t n_rows, uint32_t padded_dim, int side,
+__global__ void tc_pack_kernel(const uint8_t *__restrict__ rows, int kind, uint32_t row_bytes, uint64_t n_rows, uint32_t padded_dim, int side,
                                uint32_t nseg, uint32_t kchunks, int fold, const float *__restrict__ norms,
                                uint8_t *__restrict__ tiles) {
   const uint64_t units_per_row = (uint64_t)kchunks * 8;
@@ -97,7 +107,9 @@ __global__ void tc_pack_kernel(const float *__restrict__ rows, uint64_t n_rows, 
       const uint32_t kappa = U * 8;
       const uint32_t seg = kappa / padded_dim, d0 = kappa % padded_dim;
       if (row < n_rows && seg < nseg) {
-        const float *src = rows + row * padded_dim + d0;
+        float src[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) src[j] = tc_elem(rows, kind, row, row_bytes, d0 + j);
         const bool want_lo = side == 0 ? seg == 2 : seg == 1;
         const float scale = (fold && side == 1) ? -2.0f : 1.0f;
 #pragma unroll
@@ -128,7 +140,7 @@ __global__ void tc_max_norm_kernel(const float *__restrict__ norms, uint64_t n, 
 }
 
 // squared norms (plain fp32: they only feed the filter); +inf marks padding and empty slots
-__global__ void tc_norms_kernel(const float *__restrict__ rows, uint64_t n_rows, uint32_t padded_dim, uint32_t first_id,
+__global__ void tc_norms_kernel(const uint8_t *__restrict__ rows, int kind, uint32_t row_bytes, uint64_t n_rows, uint32_t padded_dim, uint32_t first_id,
                                 const uint8_t *__restrict__ valid, float *__restrict__ norms) {
   const int lane = threadIdx.x & 31;
   const uint64_t n_pad = (n_rows + TC_TILE - 1) / TC_TILE * TC_TILE;
@@ -139,7 +151,7 @@ __global__ void tc_norms_kernel(const float *__restrict__ rows, uint64_t n_rows,
     bool ok = r < n_rows && !(valid && valid[first_id + r] == 0);
     if (ok)
       for (uint32_t i = lane; i < padded_dim; i += 32) {
-        float x = rows[r * padded_dim + i];
+        float x = tc_elem(rows, kind, r, row_bytes, i);
         s = fmaf(x, x, s);
       }
 #pragma unroll
@@ -560,6 +572,8 @@ static cudaError_t launch_rerank(int group, const RerankArgs &a, cudaStream_t st
   const unsigned grid = (a.nq + 7) / 8;
   const size_t smem = (size_t)8 * a.k * 8;
   switch (group) {
+    case 1: knn_tc_rerank_kernel<ACC, 1><<<grid, 256, smem, stream>>>(a); break;
+    case 2: knn_tc_rerank_kernel<ACC, 2><<<grid, 256, smem, stream>>>(a); break;
     case 4: knn_tc_rerank_kernel<ACC, 4><<<grid, 256, smem, stream>>>(a); break;
     case 8: knn_tc_rerank_kernel<ACC, 8><<<grid, 256, smem, stream>>>(a); break;
     case 16: knn_tc_rerank_kernel<ACC, 16><<<grid, 256, smem, stream>>>(a); break;
@@ -570,19 +584,25 @@ static cudaError_t launch_rerank(int group, const RerankArgs &a, cudaStream_t st
 }
 
 // ---- host side -------------------------------------------------------------------------------------------
+static int tc_kind(const ngtgpu_index *ix) {   // tc_elem's layout code
+  return ix->object_type == NGTGPU_OBJECT_FLOAT ? 0 : ix->acc_kind == ACC_U8_HAM ? 2 : 1;
+}
+static uint32_t tc_kdim(const ngtgpu_index *ix) {   // K elements per stored row (one per bit for Hamming)
+  return ix->acc_kind == ACC_U8_HAM ? ix->padded_dim * 8 : ix->padded_dim;
+}
 static uint32_t tc_kchunks(const ngtgpu_index *ix, uint32_t nseg, int fold) {
-  return (nseg * ix->padded_dim + TC_KCHUNK - 1) / TC_KCHUNK + (fold ? 1 : 0);
+  return (nseg * tc_kdim(ix) + TC_KCHUNK - 1) / TC_KCHUNK + (fold ? 1 : 0);
 }
 
-static int tc_pack(ngtgpu_index *ix, const float *d_rows, uint64_t n_rows, int side, uint32_t nseg, int fold, uint32_t first_id,
+static int tc_pack(ngtgpu_index *ix, const uint8_t *d_rows, uint64_t n_rows, int side, uint32_t nseg, int fold, uint32_t first_id,
                    const uint8_t *d_valid, uint8_t *tiles, float *norms, cudaStream_t stream) {
   const uint32_t kchunks = tc_kchunks(ix, nseg, fold);
   const uint64_t n_pad = (n_rows + TC_TILE - 1) / TC_TILE * TC_TILE;
   uint64_t total = n_pad * kchunks * 8;
   unsigned blocks = (unsigned)((total + 255) / 256 > (uint64_t)ix->sm_count * 64 ? (uint64_t)ix->sm_count * 64 : (total + 255) / 256);
-  tc_norms_kernel<<<ix->sm_count * 8, 256, 0, stream>>>(d_rows, n_rows, ix->padded_dim, first_id, d_valid, norms);
+  tc_norms_kernel<<<ix->sm_count * 8, 256, 0, stream>>>(d_rows, tc_kind(ix), ix->row_bytes, n_rows, tc_kdim(ix), first_id, d_valid, norms);
   CUDA_TRY(cudaGetLastError());
-  tc_pack_kernel<<<blocks, 256, 0, stream>>>(d_rows, n_rows, ix->padded_dim, side, nseg, kchunks, fold, norms, tiles);
+  tc_pack_kernel<<<blocks, 256, 0, stream>>>(d_rows, tc_kind(ix), ix->row_bytes, n_rows, tc_kdim(ix), side, nseg, kchunks, fold, norms, tiles);
   CUDA_TRY(cudaGetLastError());
   ix->launches += 2;
   return NGTGPU_OK;
@@ -607,23 +627,23 @@ static bool all_bf16_exact(ngtgpu_index *ix, const float *d_rows, uint64_t count
 // outside what it supports (the caller then runs the CUDA-core scan).
 int ngtgpu_scan_topk_tc(ngtgpu_index *ix, const ScanParams &p, cudaStream_t stream, int *used) {
   *used = 0;
-  if (ix->object_type != NGTGPU_OBJECT_FLOAT) return NGTGPU_OK;
+  const bool integer_kind = ix->object_type != NGTGPU_OBJECT_FLOAT;   // uint8 L2 / Hamming: exact in bf16 x bf16 -> fp32
   if (p.k == 0 || p.k > TC_MAX_K || p.approx) return NGTGPU_OK;
   if (p.d_id_map != nullptr) return NGTGPU_OK;                          // pivot tables stay on the CUDA-core path
   if (p.n_rows < 32768 || p.nq < 1024) return NGTGPU_OK;                // too little work to amortise packing
   if (p.d_rows != ix->d_objects + ix->row_bytes || p.n_rows != ix->n) return NGTGPU_OK;   // only the whole repository is cached
-  if (!ix->tc_enabled || ix->padded_dim > TC_MAX_KCHUNKS * TC_KCHUNK) return NGTGPU_OK;
+  if (!ix->tc_enabled || tc_kdim(ix) > TC_MAX_KCHUNKS * TC_KCHUNK) return NGTGPU_OK;
 
   int *d_flag = nullptr;
   NGTGPU_TRY(ngtgpu_scratch(ix, SCR_TC_MISC, 256, (void **)&d_flag));
   int rc = NGTGPU_OK;
   // ---- row operand: packed once per set_objects, kept with the index
   if (!ix->tc_rows_valid) {
-    const float *rows = reinterpret_cast<const float *>(p.d_rows);
-    bool exact = all_bf16_exact(ix, rows, p.n_rows * ix->padded_dim, d_flag, stream, &rc);
+    const uint8_t *rows = p.d_rows;
+    bool exact = integer_kind || all_bf16_exact(ix, reinterpret_cast<const float *>(rows), p.n_rows * ix->padded_dim, d_flag, stream, &rc);
     if (rc != NGTGPU_OK) return rc;
     uint32_t nseg = exact ? 1 : 3;
-    const int fold = ix->acc_kind == ACC_F_L2 ? 1 : 0;   // L2: norms ride in the GEMM
+    const int fold = (ix->acc_kind == ACC_F_L2 || integer_kind) ? 1 : 0;   // L2 (and Hamming = L2 of bits): norms ride in the GEMM
     const uint32_t kchunks = tc_kchunks(ix, nseg, fold);
     if (kchunks > TC_MAX_KCHUNKS + 1) return NGTGPU_OK;   // resident query operand would not fit
     const uint64_t n_tiles = (p.n_rows + TC_TILE - 1) / TC_TILE;
@@ -647,9 +667,9 @@ int ngtgpu_scan_topk_tc(ngtgpu_index *ix, const ScanParams &p, cudaStream_t stre
   }
   uint32_t nseg = ix->tc_nseg;
   // ---- query operand
-  const float *qrows = reinterpret_cast<const float *>(p.d_queries);
-  if (nseg == 1) {
-    bool qexact = all_bf16_exact(ix, qrows, (uint64_t)p.nq * ix->padded_dim, d_flag, stream, &rc);
+  const uint8_t *qrows = p.d_queries;
+  if (nseg == 1 && !integer_kind) {
+    bool qexact = all_bf16_exact(ix, reinterpret_cast<const float *>(qrows), (uint64_t)p.nq * ix->padded_dim, d_flag, stream, &rc);
     if (rc != NGTGPU_OK) return rc;
     if (!qexact) return NGTGPU_OK;   // rows are bf16-exact but the queries are not: leave it to the CUDA-core scan
   }
@@ -671,7 +691,7 @@ int ngtgpu_scan_topk_tc(ngtgpu_index *ix, const ScanParams &p, cudaStream_t stre
   a.n_rows = p.n_rows;
   a.kchunks = kchunks;
   a.k = p.k;
-  a.mode = ix->acc_kind == ACC_F_L2 ? 0 : ix->acc_kind == ACC_F_DOT ? 1 : 2;
+  a.mode = (ix->acc_kind == ACC_F_L2 || integer_kind) ? 0 : ix->acc_kind == ACC_F_DOT ? 1 : 2;
   a.rel_margin = nseg == 1 ? 4.0e-6f : 1.0e-4f;
   a.max_row_norm = ix->tc_max_norm;
   a.exclude_self = p.exclude_self;
@@ -734,6 +754,8 @@ int ngtgpu_scan_topk_tc(ngtgpu_index *ix, const ScanParams &p, cudaStream_t stre
   switch (ix->acc_kind) {
     case ACC_F_L2: e = launch_rerank<ACC_F_L2>((int)ix->group, r, stream); break;
     case ACC_F_DOT: e = launch_rerank<ACC_F_DOT>((int)ix->group, r, stream); break;
+    case ACC_U8_L2: e = launch_rerank<ACC_U8_L2>((int)ix->group, r, stream); break;
+    case ACC_U8_HAM: e = launch_rerank<ACC_U8_HAM>((int)ix->group, r, stream); break;
     default: e = launch_rerank<ACC_F_COS>((int)ix->group, r, stream); break;
   }
   if (e != cudaSuccess) NGTGPU_FAIL(NGTGPU_ERR_CUDA, std::string("tensor-core kNN rerank launch: ") + cudaGetErrorString(e));

@@ -329,20 +329,27 @@ def test_pack_and_merge_kernels_match_host(eng):
     assert_bit_exact(oi.cpu().numpy().astype(np.uint32), od.cpu().numpy(), hc, hi, hd, hc, what="merge kernel")
 
 
-@pytest.mark.parametrize("case", ["sift_l2_exact_bf16", "glove_l2_split", "glove_ncos_split", "glove_cos_split"])
+@pytest.mark.parametrize("case", ["sift_l2_exact_bf16", "glove_l2_split", "glove_ncos_split", "glove_cos_split", "sift_u8_l2",
+                                  "sift_hamming"])
 def test_tensor_core_knn_matches_cuda_core_scan(eng, case):
     """knn_tc.cu (tcgen05 filter + exact re-evaluation) returns exactly what the CUDA-core scan returns: ids,
     distance bits and counts, for batches, kNN-graph construction (self excluded) and with removed slots."""
     from ngt_b200 import build, synth
     n, nq = 40000, 1500
+    ot = po.FLOAT
     if case == "sift_l2_exact_bf16":
         base, qs, dt = synth.make("sift", n, 1), synth.make("sift", nq, 2), po.L2
+    elif case == "sift_u8_l2":      # uint8 values are bf16 numbers: one exact segment, integer re-evaluation (dp4a)
+        base, qs, dt, ot = synth.make("sift", n, 1).astype(np.uint8), synth.make("sift", nq, 2).astype(np.uint8), po.L2, po.UINT8
+    elif case == "sift_hamming":    # Hamming = squared L2 of the bits: one K element per bit
+        base, qs = synth.hamming_from(synth.make("sift", n, 1), 64.0), synth.hamming_from(synth.make("sift", nq, 2), 64.0)
+        dt, ot = po.HAMMING, po.UINT8
     else:
         base, qs = synth.make("glove", n, 1), synth.make("glove", nq, 2)
         dt = {"glove_l2_split": po.L2, "glove_ncos_split": po.NORMALIZED_COSINE, "glove_cos_split": po.COSINE}[case]
-    ix = eng.GpuIndex(po.FLOAT, dt, base.shape[1])
+    ix = eng.GpuIndex(ot, dt, base.shape[1])
     ix.set_objects(base)
-    for k in (10, 64):
+    for k in (10, 64, 120):
         ix.set_tensor_core(True)
         before = ix.tensor_core_batches
         ids, dists, counts = ix.linear_search(qs, k)
