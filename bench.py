@@ -18,7 +18,8 @@ truth from the exhaustive scan) is >= 0.95.
             same epsilon) on all host threads, on a bounded sample of the batch
 
 Setup (untimed, identical for both arms): synthetic data (ngt_b200.synth, seeds 1/2), exact kNN graph on the
-device, ONNG-style reconstruction (GraphReconstructor.h:425-561), seed table. N > 1 runs one replica of the
+device, the reference's ONNG recipe on it (reconstructGraph -o 10 -i 120 + shortcut reduction,
+GraphReconstructor.h:425-561 and 197-386, both on the device), seed table. N > 1 runs one replica of the
 index per GPU with its own 10k batch (weak scaling, no data-path collective); `--mode shard` instead shards
 the rows over the ranks and merges per-shard top-k lists after an NCCL all-gather.
 """
@@ -50,9 +51,11 @@ def parse_args():
     ap.add_argument("--nq", type=int, default=10000)
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--shape", default="sift")
-    ap.add_argument("--knn", type=int, default=100, help="edges per node of the exact kNN graph")
+    ap.add_argument("--knn", type=int, default=128, help="edges per node of the exact kNN graph")
     ap.add_argument("--outgoing", type=int, default=10)
-    ap.add_argument("--incoming", type=int, default=100)
+    ap.add_argument("--incoming", type=int, default=120)
+    ap.add_argument("--shortcut-reduction", type=int, default=1,
+                    help="1: GraphReconstructor::adjustPathsEffectively after reconstructGraph (the reference's ONNG recipe)")
     ap.add_argument("--edge-size", type=int, default=80, help="edge_size of the search (0 = all edges)")
     ap.add_argument("--pivots", type=int, default=1024)
     ap.add_argument("--seeds", type=int, default=10)
@@ -141,8 +144,16 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def workload_desc(a, dim):
+    """config.workload: the same string in both arms."""
+    return ("configs[1]: synthetic %dx%d float L2 (%s-shape), ONNG from the exact kNN graph (knn=%d, reconstructGraph "
+            "outgoing=%d incoming=%d, shortcut reduction %s), batch %d queries, k=%d" % (
+                a.n, dim, a.shape, a.knn, a.outgoing, a.incoming, "on" if a.shortcut_reduction else "off", a.nq, a.k))
+
+
 def index_tag(a, rank=0, world=1):
-    return "%s_n%d_k%d_o%d_i%d_r%dof%d_%s" % (a.shape, a.n, a.knn, a.outgoing, a.incoming, rank, world, a.mode)
+    return "%s_n%d_k%d_o%d_i%d_s%d_r%dof%d_%s" % (a.shape, a.n, a.knn, a.outgoing, a.incoming, a.shortcut_reduction, rank,
+                                                  world, a.mode)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -167,6 +178,11 @@ def build_index(a, dev, rank, world, want_files):
     t2 = time.time()
     row_ptr, col, dist = build.reconstruct_graph(ids, dists, counts, a.outgoing, a.incoming)
     del ids, dists, counts
+    torch.cuda.synchronize(dev)
+    t2b = time.time()
+    adj = None
+    if a.shortcut_reduction:
+        row_ptr, col, dist, adj = build.adjust_paths(row_ptr, col, dist, 0, with_stats=True)
     stats = build.graph_statistics(row_ptr)
     ix.set_graph(row_ptr, col)
     ix.set_search_property(a.edge_size if a.edge_size > 0 else 0, 30, 20)
@@ -174,7 +190,9 @@ def build_index(a, dev, rank, world, want_files):
     torch.cuda.synchronize(dev)
     t3 = time.time()
     info = {"n": n_local, "gen_s": round(t1 - t0, 2), "knn_graph_s": round(t2 - t1, 2),
-            "reconstruct_s": round(t3 - t2, 2), "graph": stats}
+            "reconstruct_s": round(t2b - t2, 2), "adjust_paths_s": round(t3 - t2b, 2), "graph": stats}
+    if adj:
+        info["graph"]["shortcut_reduction"] = {"removed_edges": adj["removed"], "candidates": adj["candidates"]}
     index_dir = None
     if want_files:
         index_dir = a.index_dir or os.path.join(tempfile.gettempdir(), "ngt_b200_bench_" + index_tag(a, rank, world))
@@ -391,15 +409,13 @@ def run_ours(a):
         "value": round(value, 1), "unit": "queries/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: synthetic %dx%d float L2 (%s-shape), ONNG-style graph from exact kNN "
-                               "(knn=%d, outgoing=%d, incoming=%d), batch %d queries, k=%d" % (
-                                   a.n, dim, a.shape, a.knn, a.outgoing, a.incoming, a.nq, a.k),
+        "config": {"workload": workload_desc(a, dim),
                    "epsilon": eps, "edge_size": a.edge_size, "recall_at_10": round(rec, 4), "recall_queries": ngt,
                    "seeds": "nearest %d of %d device pivots" % (a.seeds, a.pivots),
                    "parallelism": ("replica x%d (one 10k batch per GPU)" % world) if a.mode == "replica" else
                                   ("rows sharded x%d + all-gather merge" % world),
                    "l2_policy": "inputs larger than L2 (512 MB of rows vs 126 MB), 4 rotating query batches",
-                   "graph": info["graph"], "setup_s": {k: info[k] for k in ("gen_s", "knn_graph_s", "reconstruct_s")},
+                   "graph": info["graph"], "setup_s": {k: info[k] for k in ("gen_s", "knn_graph_s", "reconstruct_s", "adjust_paths_s")},
                    "overflow_queries_per_step": overflow, "epsilon_sweep": curve},
         "e2e": {"value": round(e2e_value, 1), "unit": "queries/s", "ms_per_step": round(e2e_ms, 4),
                 "h2d_bytes_per_step": a.nq * dim * 4, "d2h_bytes_per_step": a.nq * a.k * 8 + a.nq * 4},
@@ -495,9 +511,7 @@ def run_reference(a):
         "value": round(qps, 1), "unit": "queries/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1]: synthetic %dx%d float L2 (%s-shape), same index files as the GPU arm "
-                               "(knn=%d, outgoing=%d, incoming=%d), k=%d" % (a.n, qs.shape[1], a.shape, a.knn,
-                                                                              a.outgoing, a.incoming, a.k),
+        "config": {"workload": workload_desc(a, qs.shape[1]), "index": "the index files the GPU arm searches",
                    "epsilon": eps, "edge_size": a.edge_size, "recall_at_10": round(rrec, 4)},
         "cpu_baseline": {"value": round(qps, 1), "unit": "queries/s", "cores": int(threads), "kind": kind,
                          "sample": "each step = %d queries of the 10k batch (NGT::Index::search, OpenMP over queries, "
