@@ -84,6 +84,9 @@ int ngtgpu_index_set_search_property(ngtgpu_index *index, int64_t edge_size_for_
  * (lib/NGT/Index.h:1524-1567, Tree.cpp:400-563): `n_pivots` sampled objects form a table; each query's
  * seeds are its nearest `seed_size` pivots. */
 int ngtgpu_index_build_seed_table(ngtgpu_index *index, uint32_t n_pivots, uint64_t rng_seed);
+/* The same with pivots drawn from ids 1..limit only (0 = all): used while a graph is grown batch by batch
+ * (ngtgpu_index_insert_batch), when later ids are not in the graph yet. */
+int ngtgpu_index_build_seed_table_range(ngtgpu_index *index, uint32_t n_pivots, uint64_t rng_seed, uint64_t limit);
 
 uint64_t ngtgpu_index_size(const ngtgpu_index *index);          /* n */
 uint32_t ngtgpu_index_padded_dimension(const ngtgpu_index *index);
@@ -186,6 +189,19 @@ int ngtgpu_graph_reconstruct(uint64_t n, const uint64_t *row_ptr, const uint32_t
  *      result exactly. stats (host, nullable): candidates, removed edges, sweep launches, kernels launched. */
 int ngtgpu_graph_adjust_paths(uint64_t n, const uint64_t *row_ptr, const uint32_t *col, const float *dist,
                               uint32_t min_edges, uint8_t *keep, uint64_t *stats, void *stream);
+
+/* ---- one batch of the reference's ANNG construction loop / incremental insertion (lib/NGT/Index.cpp:631-719:
+ *      searchMultipleQueryForCreation + insertMultipleSearchResults; Index.h:815-837 searchForNNGInsertion;
+ *      Graph.h:611-626 insertANNGNode): the stored objects first_id .. first_id+count-1 are searched for in the graph
+ *      as it is (size = edge_size_for_creation, epsilon = the creation epsilon, edge_size as in ngtgpu_search_params;
+ *      seeds = nearest n_seeds of n_pivots pivots drawn from ids < first_id), each also gets the distances to the
+ *      objects before it in the batch, its list is cut to edge_size_for_creation, becomes its edges, and every listed
+ *      node gets the reverse edge. DEVICE CSR with distances, updated in place (capacity entries; grows by at most
+ *      2 * count * edge_size_for_creation). An empty graph (first batch) only links the batch internally. The index's
+ *      own graph is left equal to the result. */
+int ngtgpu_index_insert_batch(ngtgpu_index *index, uint32_t first_id, uint32_t count, uint32_t edge_size_for_creation,
+                              float epsilon, int64_t edge_size, uint32_t n_seeds, uint32_t n_pivots, uint64_t pivot_seed,
+                              uint64_t capacity, uint64_t *d_row_ptr, uint32_t *d_col, float *d_dist, uint64_t *nnz_out);
 
 /* The sub-graph of the edges with keep[e] != 0, order inside the lists preserved (compaction after
  * ngtgpu_graph_adjust_paths). DEVICE buffers; *out_nnz is a host word. */

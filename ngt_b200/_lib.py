@@ -46,6 +46,7 @@ SYMBOLS = {
     "ngtgpu_index_set_tensor_core": (C.c_int, [_P, C.c_int]),
     "ngtgpu_index_tensor_core_batches": (C.c_uint64, [_P]),
     "ngtgpu_index_build_seed_table": (C.c_int, [_P, C.c_uint32, C.c_uint64]),
+    "ngtgpu_index_build_seed_table_range": (C.c_int, [_P, C.c_uint32, C.c_uint64, C.c_uint64]),
     "ngtgpu_index_size": (C.c_uint64, [_P]),
     "ngtgpu_index_padded_dimension": (C.c_uint32, [_P]),
     "ngtgpu_index_get_object": (C.c_int, [_P, C.c_uint32, _P]),
@@ -62,6 +63,8 @@ SYMBOLS = {
     "ngtgpu_graph_from_knn_table": (C.c_int, [C.c_uint64, _P, _P, _P, C.c_uint32, _P, C.c_int, C.c_uint64, _P, _P, _P,
                                               C.POINTER(C.c_uint64), _P]),
     "ngtgpu_graph_select_edges": (C.c_int, [C.c_uint64, _P, _P, _P, _P, _P, _P, _P, C.POINTER(C.c_uint64), _P]),
+    "ngtgpu_index_insert_batch": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, C.c_int64, C.c_uint32, C.c_uint32,
+                                            C.c_uint64, C.c_uint64, _P, _P, _P, C.POINTER(C.c_uint64)]),
     "ngtgpu_graph_adjust_paths": (C.c_int, [C.c_uint64, _P, _P, _P, C.c_uint32, _P, C.POINTER(C.c_uint64), _P]),
     "ngtgpu_linear_search_device": (C.c_int, [_P, _P, C.c_int, C.c_uint32, C.c_uint32, C.c_float, _P, _P, _P, _P]),
 }

@@ -181,6 +181,37 @@ def refine_anng(ix, row_ptr, col, dist, epsilon=0.1, no_of_edges=0, edge_size=-1
     return rp, c[:out.value].clone(), d[:out.value].clone()
 
 
+def insert_objects(ix, first_id, count, graph=None, edge_size_for_creation=10, epsilon=0.1, edge_size=-1, batch_size=200,
+                   n_seeds=10, n_pivots=256, pivot_seed=1):
+    """The reference's ANNG construction loop (lib/NGT/Index.cpp:721-792 createIndex: batches of batchSizeForCreation
+    objects are searched for on the frozen graph, linked among themselves and inserted with their reverse edges) on the
+    device, batch by batch (ngtgpu_index_insert_batch). `graph` = (row_ptr, col, dist) CUDA CSR of the objects already
+    in the index (None: start from nothing); the objects first_id .. first_id+count-1 must be stored in `ix`.
+    -> (row_ptr, col, dist); the graph is also left set on `ix`. With first_id = 1, count = ix.size this is
+    NGT::Index::createIndex; with a graph and the appended ids it is insertion into an existing index."""
+    import torch
+    lib = _lib.load()
+    n = ix.size
+    dev = torch.device("cuda", ix.device)
+    e = int(edge_size_for_creation)
+    old = 0 if graph is None else int(graph[1].numel())
+    cap = old + 2 * count * e + 16
+    rp = torch.zeros(n + 2, dtype=torch.int64, device=dev)
+    c = torch.zeros(cap, dtype=torch.int32, device=dev)
+    d = torch.zeros(cap, dtype=torch.float32, device=dev)
+    if graph is not None:
+        rp.copy_(graph[0].to(torch.int64))
+        c[:old] = graph[1]
+        d[:old] = graph[2]
+    nnz = C.c_uint64(old)
+    torch.cuda.synchronize(dev)
+    for s in range(first_id, first_id + count, batch_size):
+        m = min(batch_size, first_id + count - s)
+        _lib.check(lib.ngtgpu_index_insert_batch(ix._h, s, m, e, float(epsilon), int(edge_size), int(n_seeds), int(n_pivots),
+                                                 int(pivot_seed), cap, rp.data_ptr(), c.data_ptr(), d.data_ptr(), C.byref(nnz)))
+    return rp, c[:nnz.value].clone(), d[:nnz.value].clone()
+
+
 def adjust_paths(row_ptr, col, dist, min_edges=0, with_stats=False):
     """GraphReconstructor::adjustPathsEffectively (lib/NGT/GraphReconstructor.h:197-386) -- the shortcut reduction
     GraphOptimizer::execute applies after reconstructGraph -- on a device CSR (row_ptr over ids 0..n, lists

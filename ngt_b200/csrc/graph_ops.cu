@@ -837,3 +837,244 @@ extern "C" int ngtgpu_index_refine_anng(ngtgpu_index *ix, float epsilon, int32_t
   *nnz_out = nnz;
   return NGTGPU_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// ngtgpu_index_insert_batch -- one batch of the reference's ANNG construction loop (lib/NGT/Index.cpp:631-719,
+// 721-792; Index.h:815-837; Graph.h:611-626, 845-886), which is also how objects are added to an existing index
+// (ngt_insert_index + ngt_create_index):
+//   search    every new object is searched for in the graph as it was BEFORE the batch (size = edgeSizeForCreation,
+//             the creation epsilon; searched again with all edges when fewer results came back, Index.h:826-836)
+//   a-13      insertMultipleSearchResults: object i of the batch also gets the distances to the objects j < i of the
+//             same batch ("to imitate sequential insertion"), the list is sorted and cut to edgeSizeForCreation
+//   a-15      insertANNGNode: the list becomes the node's edges and every listed node gets the reverse edge
+// The searches are one launch of the traversal kernel, the in-batch distances one kernel (a warp per new object, the
+// engine's exact distance), the insertion a radix-sort merge of the edge triples into the CSR.
+namespace {
+
+struct IntraArgs {
+  const uint8_t *rows;        // the index's object table (row 0 = dummy)
+  uint32_t row_bytes, chunks;
+  uint32_t first_id, count, e;
+  int dtype;
+  const uint8_t *valid;
+  const uint32_t *r_ids;      // [count x e] search results (ascending), nullable when the graph was empty
+  const float *r_dists;
+  const uint32_t *r_counts;
+  uint32_t *out_ids;          // [count x e]
+  float *out_dists;
+  uint32_t *out_counts;
+};
+
+template <int ACC, int G>
+__global__ void __launch_bounds__(256) intra_batch_kernel(const IntraArgs a) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t x = blockIdx.x * 8 + warp;
+  if (x >= a.count) return;
+  uint64_t *top = reinterpret_cast<uint64_t *>(smem) + (size_t)warp * a.e;
+  const uint32_t id = a.first_id + x;
+  uint32_t n = 0;
+  const bool live = !(a.valid && a.valid[id] == 0);
+  if (live && a.r_counts) {
+    uint32_t c = a.r_counts[x];
+    if (c == 0xffffffffu) c = 0;
+    if (c > a.e) c = a.e;
+    for (uint32_t i = lane; i < c; i += 32) top[i] = make_key(a.r_dists[(size_t)x * a.e + i], a.r_ids[(size_t)x * a.e + i]);
+    n = c;
+  }
+  __syncwarp();
+  if (live) {
+    constexpr int R = 32 / G;
+    const int gl = lane % G, grp = lane / G;
+    const uint8_t *qptr = a.rows + (size_t)id * a.row_bytes;
+    for (uint32_t j0 = 0; j0 < x; j0 += R) {   // the objects inserted before this one in the same batch
+      const uint32_t j = j0 + grp;
+      const uint32_t jid = a.first_id + j;
+      const bool act = j < x && !(a.valid && a.valid[jid] == 0);
+      const float d = group_distance_gmem<ACC, G>(qptr, act ? a.rows + (size_t)jid * a.row_bytes : qptr, a.chunks, gl, a.dtype);
+      uint64_t key = KEY_NONE;
+      if (act && gl == 0) key = make_key(d, jid);
+      uint32_t mm = __ballot_sync(0xffffffffu, key != KEY_NONE);
+      while (mm) {
+        const int src = __ffs(mm) - 1;
+        mm &= mm - 1;
+        sorted_insert_u64(top, n, a.e, shfl_u64(key, src), lane);
+      }
+    }
+  }
+  for (uint32_t i = lane; i < a.e; i += 32) {
+    const bool ok = i < n;
+    a.out_ids[(size_t)x * a.e + i] = ok ? key_id(top[i]) : 0u;
+    a.out_dists[(size_t)x * a.e + i] = ok ? key_dist(top[i]) : 0.f;
+  }
+  if (lane == 0) a.out_counts[x] = n;
+}
+
+template <int ACC>
+cudaError_t launch_intra(int group, const IntraArgs &a, cudaStream_t stream) {
+  const unsigned grid = (a.count + 7) / 8;
+  const size_t smem = (size_t)8 * a.e * 8;
+  switch (group) {
+    case 1: intra_batch_kernel<ACC, 1><<<grid, 256, smem, stream>>>(a); break;
+    case 2: intra_batch_kernel<ACC, 2><<<grid, 256, smem, stream>>>(a); break;
+    case 4: intra_batch_kernel<ACC, 4><<<grid, 256, smem, stream>>>(a); break;
+    case 8: intra_batch_kernel<ACC, 8><<<grid, 256, smem, stream>>>(a); break;
+    case 16: intra_batch_kernel<ACC, 16><<<grid, 256, smem, stream>>>(a); break;
+    case 32: intra_batch_kernel<ACC, 32><<<grid, 256, smem, stream>>>(a); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+// per query: take the second search (all edges) where the first one came back short (Index.h:826-836)
+__global__ void pick_retry_kernel(uint32_t count, uint32_t e, uint32_t *ids, float *dists, uint32_t *counts,
+                                  const uint32_t *ids2, const float *dists2, const uint32_t *counts2) {
+  const uint64_t total = (uint64_t)count * e;
+  for (uint64_t x = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; x < total; x += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t q = (uint32_t)(x / e);
+    uint32_t c = counts[q];
+    if (c == 0xffffffffu) c = 0;
+    if (c < e) {
+      ids[x] = ids2[x];
+      dists[x] = dists2[x];
+    }
+  }
+}
+__global__ void pick_retry_counts_kernel(uint32_t count, uint32_t e, uint32_t *counts, const uint32_t *counts2) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= count) return;
+  uint32_t c = counts[q];
+  if (c == 0xffffffffu) c = 0;
+  if (c < e) counts[q] = counts2[q];
+}
+
+}  // namespace
+
+extern "C" int ngtgpu_index_insert_batch(ngtgpu_index *ix, uint32_t first_id, uint32_t count, uint32_t edge_size_for_creation,
+                                         float epsilon, int64_t edge_size, uint32_t n_seeds, uint32_t n_pivots,
+                                         uint64_t pivot_seed, uint64_t capacity, uint64_t *d_row_ptr, uint32_t *d_col,
+                                         float *d_dist, uint64_t *nnz_out) {
+  if (!ix) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "null index handle");
+  NGTGPU_TRY(ngtgpu_check_device(ix));
+  if (!d_row_ptr || !d_col || !d_dist || !nnz_out) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "ngtgpu_index_insert_batch: null buffer");
+  if (!ix->d_objects || ix->n == 0) NGTGPU_FAIL(NGTGPU_ERR_STATE, "ngtgpu_index_insert_batch: the index holds no objects");
+  const uint32_t e = edge_size_for_creation;
+  if (e == 0 || e > 1024) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "ngtgpu_index_insert_batch: edge size for creation must be in [1, 1024]");
+  if (first_id == 0 || count == 0 || (uint64_t)first_id + count - 1 > ix->n)
+    NGTGPU_FAIL(NGTGPU_ERR_INVALID, "ngtgpu_index_insert_batch: ids out of range");
+  cudaStream_t stream = ix->stream;
+  const uint64_t n = ix->n;
+  const unsigned grid = (unsigned)ix->sm_count * 8;
+  uint64_t nnz = 0;
+  CUDA_TRY(cudaMemcpyAsync(&nnz, d_row_ptr + n + 1, 8, cudaMemcpyDeviceToHost, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  DeviceBuffers mem;
+  uint32_t *r_ids = nullptr, *r_counts = nullptr, *o_ids, *o_counts;
+  float *r_dists = nullptr, *o_dists;
+  CUDA_TRY(mem.alloc(&o_ids, (size_t)count * e));
+  CUDA_TRY(mem.alloc(&o_dists, (size_t)count * e));
+  CUDA_TRY(mem.alloc(&o_counts, count));
+  const bool have_graph = nnz > 0 && first_id > 1;
+  if (have_graph) {
+    CUDA_TRY(mem.alloc(&r_ids, (size_t)count * e));
+    CUDA_TRY(mem.alloc(&r_dists, (size_t)count * e));
+    CUDA_TRY(mem.alloc(&r_counts, count));
+    NGTGPU_TRY(ngtgpu_index_set_graph(ix, d_row_ptr, d_col, 1));
+    NGTGPU_TRY(ngtgpu_index_build_seed_table_range(ix, n_pivots, pivot_seed, first_id - 1));
+    ngtgpu_search_params sp;
+    sp.size = e;
+    sp.epsilon = epsilon;
+    sp.radius = -1.0f;
+    sp.edge_size = edge_size;
+    const uint8_t *q = ix->d_objects + (size_t)first_id * ix->row_bytes;
+    NGTGPU_TRY(ngtgpu_search_prepared(ix, q, count, &sp, n_seeds, r_ids, r_dists, r_counts, stream));
+    if (ngtgpu_effective_edge_size(ix, &sp) != 0x7fffffff) {
+      // searched again without the edge cap where fewer than E results came back (and the graph has more nodes)
+      std::vector<uint32_t> h_counts(count);
+      CUDA_TRY(cudaMemcpyAsync(h_counts.data(), r_counts, (size_t)count * 4, cudaMemcpyDeviceToHost, stream));
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      bool shortfall = false;
+      for (uint32_t c : h_counts)
+        if (c != 0xffffffffu && c < e && c < first_id) shortfall = true;   // result.size() < repository.size()
+      if (shortfall) {
+        uint32_t *r2_ids, *r2_counts;
+        float *r2_dists;
+        CUDA_TRY(mem.alloc(&r2_ids, (size_t)count * e));
+        CUDA_TRY(mem.alloc(&r2_dists, (size_t)count * e));
+        CUDA_TRY(mem.alloc(&r2_counts, count));
+        sp.edge_size = 0;
+        NGTGPU_TRY(ngtgpu_search_prepared(ix, q, count, &sp, n_seeds, r2_ids, r2_dists, r2_counts, stream));
+        pick_retry_kernel<<<grid, 256, 0, stream>>>(count, e, r_ids, r_dists, r_counts, r2_ids, r2_dists, r2_counts);
+        pick_retry_counts_kernel<<<(count + 255) / 256, 256, 0, stream>>>(count, e, r_counts, r2_counts);
+        ix->launches += 2;
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        mem.release(r2_ids);
+        mem.release(r2_dists);
+        mem.release(r2_counts);
+      }
+    }
+  }
+  IntraArgs ia;
+  ia.rows = ix->d_objects;
+  ia.row_bytes = ix->row_bytes;
+  ia.chunks = ix->chunks;
+  ia.first_id = first_id;
+  ia.count = count;
+  ia.e = e;
+  ia.dtype = ix->distance_type;
+  ia.valid = ix->d_valid;
+  ia.r_ids = r_ids;
+  ia.r_dists = r_dists;
+  ia.r_counts = r_counts;
+  ia.out_ids = o_ids;
+  ia.out_dists = o_dists;
+  ia.out_counts = o_counts;
+  cudaError_t ce;
+  switch (ix->acc_kind) {
+    case ACC_F_L2: ce = launch_intra<ACC_F_L2>((int)ix->group, ia, stream); break;
+    case ACC_F_DOT: ce = launch_intra<ACC_F_DOT>((int)ix->group, ia, stream); break;
+    case ACC_F_COS: ce = launch_intra<ACC_F_COS>((int)ix->group, ia, stream); break;
+    case ACC_U8_L2: ce = launch_intra<ACC_U8_L2>((int)ix->group, ia, stream); break;
+    default: ce = launch_intra<ACC_U8_HAM>((int)ix->group, ia, stream); break;
+  }
+  if (ce != cudaSuccess) NGTGPU_FAIL(NGTGPU_ERR_CUDA, std::string("in-batch distance kernel launch: ") + cudaGetErrorString(ce));
+  ix->launches++;
+  // old edges + (new node -> listed node) + (listed node -> new node)
+  const uint64_t m_max = nnz + 2ull * count * e;
+  uint32_t *src_a, *src_b;
+  uint64_t *key_a, *key_b;
+  unsigned long long *counter;
+  CUDA_TRY(mem.alloc(&src_a, m_max));
+  CUDA_TRY(mem.alloc(&src_b, m_max));
+  CUDA_TRY(mem.alloc(&key_a, m_max));
+  CUDA_TRY(mem.alloc(&key_b, m_max));
+  CUDA_TRY(mem.alloc(&counter, 2));
+  CUDA_TRY(cudaMemsetAsync(counter, 0, 16, stream));
+  if (nnz) emit_edges_kernel<<<grid, 256, 0, stream>>>(d_row_ptr, d_col, d_dist, n, 0xffffffffu, 0u, src_a, key_a, counter);
+  refine_emit_kernel<<<grid, 256, 0, stream>>>(o_ids, o_dists, o_counts, first_id, count, e, ix->d_valid, 1, src_a, key_a, counter);
+  ix->launches += 2;
+  unsigned long long m = 0;
+  CUDA_TRY(cudaMemcpyAsync(&m, counter, 8, cudaMemcpyDeviceToHost, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  if (m) {
+    uint64_t *t_ptr;
+    uint32_t *t_col;
+    float *t_dist;
+    CUDA_TRY(mem.alloc(&t_ptr, n + 2));
+    CUDA_TRY(mem.alloc(&t_col, (size_t)m));
+    CUDA_TRY(mem.alloc(&t_dist, (size_t)m));
+    uint64_t out_nnz = 0;
+    NGTGPU_TRY(csr_from_triples(mem, n, src_a, src_b, key_a, key_b, counter, m, m, t_ptr, t_col, t_dist, &out_nnz, grid, stream));
+    if (out_nnz > capacity)
+      NGTGPU_FAIL(NGTGPU_ERR_INVALID, "ngtgpu_index_insert_batch: graph capacity " + std::to_string(capacity) + " < " +
+                                          std::to_string(out_nnz) + " edges");
+    CUDA_TRY(cudaMemcpyAsync(d_row_ptr, t_ptr, (n + 2) * 8, cudaMemcpyDeviceToDevice, stream));
+    CUDA_TRY(cudaMemcpyAsync(d_col, t_col, out_nnz * 4, cudaMemcpyDeviceToDevice, stream));
+    CUDA_TRY(cudaMemcpyAsync(d_dist, t_dist, out_nnz * 4, cudaMemcpyDeviceToDevice, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    nnz = out_nnz;
+  }
+  NGTGPU_TRY(ngtgpu_index_set_graph(ix, d_row_ptr, d_col, 1));
+  *nnz_out = nnz;
+  return NGTGPU_OK;
+}

@@ -473,12 +473,19 @@ static inline uint64_t splitmix64(uint64_t &x) {
 }
 
 extern "C" int ngtgpu_index_build_seed_table(ngtgpu_index *ix, uint32_t n_pivots, uint64_t rng_seed) {
+  return ngtgpu_index_build_seed_table_range(ix, n_pivots, rng_seed, 0);
+}
+
+// pivots sampled from ids 1..limit only (limit == 0: all objects): while a graph is being grown batch by batch the
+// seeds must be nodes that are already in it
+extern "C" int ngtgpu_index_build_seed_table_range(ngtgpu_index *ix, uint32_t n_pivots, uint64_t rng_seed, uint64_t limit) {
   NGTGPU_TRY(ngtgpu_check_device(ix));
   if (!ix->d_objects || ix->n == 0) NGTGPU_FAIL(NGTGPU_ERR_STATE, "ngtgpu_index_build_seed_table: objects are not set");
   CUDA_TRY(cudaStreamSynchronize(ix->stream));
   free_pivots(ix);
   if (n_pivots == 0) return NGTGPU_OK;
-  if (n_pivots > ix->n) n_pivots = (uint32_t)ix->n;
+  const uint64_t range = (limit == 0 || limit > ix->n) ? ix->n : limit;
+  if (n_pivots > range) n_pivots = (uint32_t)range;
   // evenly strided sample with a random phase per stride: distinct ids, spread over the id range
   std::vector<uint32_t> ids(n_pivots);
   std::vector<uint8_t> valid;
@@ -489,7 +496,7 @@ extern "C" int ngtgpu_index_build_seed_table(ngtgpu_index *ix, uint32_t n_pivots
   uint64_t st = rng_seed;
   uint32_t kept = 0;
   for (uint32_t p = 0; p < n_pivots; p++) {
-    uint64_t lo = (uint64_t)p * ix->n / n_pivots, hi = (uint64_t)(p + 1) * ix->n / n_pivots;
+    uint64_t lo = (uint64_t)p * range / n_pivots, hi = (uint64_t)(p + 1) * range / n_pivots;
     if (hi <= lo) continue;
     uint64_t id = 1 + lo + splitmix64(st) % (hi - lo);
     if (!valid.empty()) {

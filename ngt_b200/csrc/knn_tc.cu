@@ -478,31 +478,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_filter_kernel(const TcAr
 }
 
 // ---- exact re-evaluation of the candidates + top-k (one warp per query) -----------------------------------
-__device__ __forceinline__ void tc_sorted_insert(uint64_t *arr, uint32_t &n_io, uint32_t k, uint64_t key, int lane) {
-  uint32_t n = n_io;
-  if (n == k) {
-    if (key >= arr[k - 1]) return;
-    n = k - 1;
-  }
-  uint32_t pos = 0;
-  for (uint32_t i0 = 0; i0 < n; i0 += 32) {
-    bool less = i0 + lane < n && arr[i0 + lane] < key;
-    pos += __popc(__ballot_sync(0xffffffffu, less));
-  }
-  for (uint32_t hi = n; hi > pos;) {
-    uint32_t lo = hi - pos > 32 ? hi - 32 : pos;
-    uint32_t idx = lo + lane;
-    uint64_t v = idx < hi ? arr[idx] : 0;
-    __syncwarp();
-    if (idx < hi) arr[idx + 1] = v;
-    __syncwarp();
-    hi = lo;
-  }
-  if (lane == 0) arr[pos] = key;
-  __syncwarp();
-  n_io = n + 1;
-}
-
 struct RerankArgs {
   const uint8_t *queries;   // prepared rows
   const uint8_t *rows;
@@ -552,7 +527,7 @@ __global__ void __launch_bounds__(256) knn_tc_rerank_kernel(const RerankArgs a) 
         int src = __ffs(mm) - 1;
         mm &= mm - 1;
         uint64_t kk = shfl_u64(key, src);
-        tc_sorted_insert(top, n, a.k, kk, lane);
+        sorted_insert_u64(top, n, a.k, kk, lane);
       }
     }
   }

@@ -322,4 +322,31 @@ __device__ __forceinline__ float group_distance_gmem(const uint8_t *q, const uin
   }
   return finish_distance<ACC>(dtype, s, qn);
 }
+
+// Insert `key` into the ascending array arr[0..n) of capacity k (the largest entry falls off when full); one warp.
+__device__ __forceinline__ void sorted_insert_u64(uint64_t *arr, uint32_t &n_io, uint32_t k, uint64_t key, int lane) {
+  uint32_t n = n_io;
+  if (n == k) {
+    if (key >= arr[k - 1]) return;
+    n = k - 1;
+  }
+  uint32_t pos = 0;
+  for (uint32_t i0 = 0; i0 < n; i0 += 32) {
+    bool less = i0 + lane < n && arr[i0 + lane] < key;
+    pos += __popc(__ballot_sync(0xffffffffu, less));
+  }
+  for (uint32_t hi = n; hi > pos;) {
+    uint32_t lo = hi - pos > 32 ? hi - 32 : pos;
+    uint32_t idx = lo + lane;
+    uint64_t v = idx < hi ? arr[idx] : 0;
+    __syncwarp();
+    if (idx < hi) arr[idx + 1] = v;
+    __syncwarp();
+    hi = lo;
+  }
+  if (lane == 0) arr[pos] = key;
+  __syncwarp();
+  n_io = n + 1;
+}
+
 #endif  // __CUDACC__

@@ -356,3 +356,46 @@ def refine_anng_loop(port, dtype, otype, pobj, row_ptr, col, dist, seeds, epsilo
     if no_of_edges > 0:
         lists = [l[:no_of_edges] for l in lists]
     return lists
+
+
+def build_anng_loop(port, pobj, rows_int, seeds, first_id, count, lists=None, edge_size_for_creation=10, epsilon=0.1,
+                    edge_size=40, batch_size=200):
+    """Sequential restatement of the ANNG construction loop (lib/NGT/Index.cpp:631-719, 721-792; Index.h:815-837;
+    Graph.h:611-626, 845-886) for integer-valued L2 float data, over the C restatement of the search with explicit seeds
+    (seeds[id - 1]); test infrastructure. rows_int: [(n+1) x dim] int64 copy of the objects (row 0 dummy).
+    -> per id 0..n a list of (distance, id) ascending."""
+    import bisect
+    n = pobj.shape[0] - 1
+    e = edge_size_for_creation
+    lists = [[] for _ in range(n + 1)] if lists is None else [list(l) for l in lists]
+    for s in range(first_id, first_id + count, batch_size):
+        ids_b = list(range(s, min(s + batch_size, first_id + count)))
+        res = [[] for _ in ids_b]
+        nnz = sum(len(l) for l in lists)
+        if nnz and s > 1:                                                                   # searchForNNGInsertion
+            rp = np.zeros(n + 2, np.uint64)
+            rp[1:] = np.cumsum([len(l) for l in lists])
+            cc = np.array([t for l in lists for (_, t) in l], np.uint32)
+            q = pobj[s:s + len(ids_b)]
+            sd = seeds[s - 1:s - 1 + len(ids_b)]
+            cap = 2 ** 31 - 1 if edge_size == 0 else edge_size
+            r_ids, r_d, r_cnt, _ = port.graph_search(L2, FLOAT, pobj, rp, cc, q, sd, e, epsilon, edge_size=cap)
+            short = [x for x in range(len(ids_b)) if r_cnt[x] < e and r_cnt[x] < s]   # result.size() < repository.size()
+            if short and edge_size != 0:                                                    # Index.h:826-836
+                a_ids, a_d, a_cnt, _ = port.graph_search(L2, FLOAT, pobj, rp, cc, q, sd, e, epsilon, edge_size=2 ** 31 - 1)
+                for x in short:
+                    r_ids[x], r_d[x], r_cnt[x] = a_ids[x], a_d[x], a_cnt[x]
+            for x in range(len(ids_b)):
+                res[x] = [(float(r_d[x, r]), int(r_ids[x, r])) for r in range(int(r_cnt[x]))]
+        for x, i in enumerate(ids_b):                                                       # insertMultipleSearchResults
+            objs = list(res[x])
+            for j in ids_b[:x]:
+                d2 = int(((rows_int[i] - rows_int[j]) ** 2).sum())
+                objs.append((float(np.float32(np.sqrt(np.float64(d2)))), j))
+            objs.sort()
+            res[x] = objs[:e]
+        for x, i in enumerate(ids_b):                                                       # insertANNGNode
+            lists[i] = list(res[x])
+            for (d, t) in res[x]:
+                bisect.insort(lists[t], (d, i))
+    return lists

@@ -138,3 +138,42 @@ def test_refine_anng_equals_the_sequential_restatement(eng, port, no_of_edges, b
         r = ix.search(base[:50], 5, 0.1)
         assert (r[0][:, 0] == np.arange(1, 51)).all()
     ix.close()
+
+
+@pytest.mark.parametrize("batch,edge_size", [(200, 40), (64, 0), (1000, 5)])
+def test_anng_construction_loop_equals_the_sequential_restatement(eng, port, batch, edge_size):
+    """NGT::Index::createIndex as the reference runs it (batches searched on the frozen graph, in-batch distances,
+    insertion with reverse edges) on the device, then insertion of more objects into the finished index: the same
+    graph as the sequential restatement over the C oracle's search, edge for edge (integer-valued L2 data)."""
+    import ctypes as C
+    from ngt_b200 import _lib, build, synth
+    n, n_first, e = 2600, 2000, 8
+    base = synth.make("sift", n, 21)
+    ix = eng.GpuIndex(po.FLOAT, po.L2, base.shape[1])
+    ix.set_objects(base)
+    ix.set_search_property(edge_size, 30, 20)
+    lib = _lib.load()
+    lib.ngtgpu_select_seeds.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p]
+    # the seeds every batch will use: nearest pivots among the ids inserted before the batch
+    starts = [(s, min(batch, n_first + 1 - s)) for s in range(1, n_first + 1, batch)] + \
+             [(s, min(batch, n + 1 - s)) for s in range(n_first + 1, n + 1, batch)]
+    seeds = np.zeros((n, 10), np.uint32)
+    for s, m in starts[1:]:
+        _lib.check(lib.ngtgpu_index_build_seed_table_range(ix._h, 128, 9, s - 1))
+        tmp = np.zeros((m, 10), np.uint32)
+        _lib.check(lib.ngtgpu_select_seeds(ix._h, np.ascontiguousarray(base[s - 1:s - 1 + m]).ctypes.data, _lib.OBJECT_FLOAT, m, 10,
+                                           tmp.ctypes.data))
+        seeds[s - 1:s - 1 + m] = tmp
+    g = build.insert_objects(ix, 1, n_first, None, e, 0.1, -1, batch, 10, 128, 9)
+    g2 = build.insert_objects(ix, n_first + 1, n - n_first, g, e, 0.1, -1, batch, 10, 128, 9)
+    pobj = po.pad_objects(base, po.FLOAT)
+    rows_int = np.vstack([np.zeros((1, base.shape[1]), np.int64), base.astype(np.int64)])
+    ref1 = po.build_anng_loop(port, pobj, rows_int, seeds, 1, n_first, None, e, 0.1, edge_size, batch)
+    ref = po.build_anng_loop(port, pobj, rows_int, seeds, n_first + 1, n - n_first, ref1, e, 0.1, edge_size, batch)
+    got = _lists(g2[0].cpu().numpy(), g2[1].cpu().numpy().astype(np.uint32), g2[2].cpu().numpy())
+    assert got == ref
+    # the graph is navigable: (nearly) every object finds itself
+    ix.build_seed_table(128, 1)
+    r = ix.search(base[:200], 3, 0.1, edge_size=0)
+    assert (r[0][:, 0] == np.arange(1, 201)).mean() >= 0.9
+    ix.close()
