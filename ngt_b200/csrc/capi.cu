@@ -301,6 +301,53 @@ void build_graph(CapiIndex &ix) {
     if (!ix.present[id]) removed.push_back((uint32_t)id);
   if (!removed.empty()) check(ngtgpu_index_set_removed(ix.gpu, removed.data(), removed.size()));
   size_t live = n - removed.size();
+  // Objects appended to an index that already has its graph are INSERTED into it the way the reference's
+  // construction loop does (batches searched on the frozen graph, in-batch distances, reverse edges; Index.cpp:721-792),
+  // not by rebuilding everything.
+  if (ix.pending > 0 && ix.pending < n && ix.row_ptr.size() == n - ix.pending + 2 && !ix.col.empty()) {
+    const size_t n_old = n - ix.pending;
+    const uint32_t e = (uint32_t)std::max<int>(1, ix.prop.edge_size_for_creation);
+    const uint64_t cap = ix.col.size() + 2ull * ix.pending * e + 16;
+    uint64_t *d_rp = nullptr, nnz = 0;
+    uint32_t *d_col = nullptr;
+    float *d_dist = nullptr;
+    if (cudaMalloc(&d_rp, (n + 2) * 8) != cudaSuccess || cudaMalloc(&d_col, cap * 4) != cudaSuccess ||
+        cudaMalloc(&d_dist, cap * 4) != cudaSuccess) {
+      cudaFree(d_rp);
+      cudaFree(d_col);
+      cudaFree(d_dist);
+      throw std::runtime_error("cudaMalloc failed while inserting into the graph");
+    }
+    std::vector<uint64_t> rp(n + 2, ix.col.size());
+    for (size_t i = 0; i < n_old + 2; i++) rp[i] = ix.row_ptr[i];
+    cudaMemcpy(d_rp, rp.data(), (n + 2) * 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_col, ix.col.data(), ix.col.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_dist, ix.dist.data(), ix.dist.size() * 4, cudaMemcpyHostToDevice);
+    int rc = NGTGPU_OK;
+    const size_t batch = (size_t)std::max<long>(1, prf_long(ix, "BatchSizeForCreation", 200));
+    const float eps = ix.prf.count("EpsilonForCreation") ? std::stof(ix.prf["EpsilonForCreation"]) : 0.1f;
+    check(ngtgpu_index_set_search_property(ix.gpu, ix.prop.edge_size_for_search, prf_long(ix, "DynamicEdgeSizeBase", 30),
+                                           prf_long(ix, "DynamicEdgeSizeRate", 20)));
+    for (size_t s = n_old + 1; s <= n && rc == NGTGPU_OK; s += batch) {
+      const uint32_t m = (uint32_t)std::min<size_t>(batch, n - s + 1);
+      rc = ngtgpu_index_insert_batch(ix.gpu, (uint32_t)s, m, e, eps, -1, 10, 1024, 1, cap, d_rp, d_col, d_dist, &nnz);
+    }
+    if (rc == NGTGPU_OK) {
+      ix.row_ptr.assign(n + 2, 0);
+      ix.col.assign(nnz, 0);
+      ix.dist.assign(nnz, 0.f);
+      cudaMemcpy(ix.row_ptr.data(), d_rp, (n + 2) * 8, cudaMemcpyDeviceToHost);
+      cudaMemcpy(ix.col.data(), d_col, nnz * 4, cudaMemcpyDeviceToHost);
+      cudaMemcpy(ix.dist.data(), d_dist, nnz * 4, cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d_rp);
+    cudaFree(d_col);
+    cudaFree(d_dist);
+    check(rc);
+    ix.pending = 0;
+    check(ngtgpu_index_build_seed_table(ix.gpu, (uint32_t)std::min<size_t>(1024, live), 1));
+    return;
+  }
   uint32_t k = (uint32_t)std::max<long>(1, std::min<long>(ix.prop.edge_size_for_creation, (long)live - 1));
   uint32_t *d_ids = nullptr, *d_cnt = nullptr;
   float *d_d = nullptr;

@@ -190,3 +190,38 @@ def test_refine_anng_through_the_c_api(lib, tmp_path):
     lib.ngt_close_index(ix)
     lib.ngt_destroy_property(prop)
     lib.ngt_destroy_error_object(err)
+
+
+def test_insert_into_a_built_index_is_incremental(lib):
+    """ngt_insert_index* + ngt_create_index on an index that already has its graph inserts the new objects the way the
+    reference's construction loop does (search on the frozen graph, reverse edges): old edges stay, new nodes are linked
+    and found."""
+    from ngt_b200 import synth
+    err = lib.ngt_create_error_object()
+    prop = lib.ngt_create_property(err)
+    assert lib.ngt_set_property_dimension(prop, 128, err) and lib.ngt_set_property_edge_size_for_creation(prop, 10, err)
+    ix = lib.ngt_create_graph_and_tree_in_memory(prop, err)
+    base = synth.make("sift", 2400, 6)
+    assert lib.ngt_batch_append_index(ix, capi.fptr(base[:2000]), 2000, err) and lib.ngt_create_index(ix, 4, err)
+    before = _edges(lib, ix, 2000, err)
+    ids = np.zeros(400, np.uint32)
+    assert lib.ngt_batch_insert_index(ix, capi.fptr(base[2000:]), 400, ids.ctypes.data_as(C.POINTER(C.c_uint32)), err)
+    assert ids[0] == 2001 and ids[-1] == 2400
+    assert lib.ngt_create_index(ix, 4, err), lib.ngt_get_error_string(err)
+    after = _edges(lib, ix, 2400, err)
+    for nid in range(2000):
+        assert set(before[nid]) <= set(after[nid])                       # nothing was rebuilt
+        assert all(t > 2000 for t, _ in set(after[nid]) - set(before[nid]))   # only reverse edges of new nodes were added
+    assert all(1 <= len(after[nid]) for nid in range(2000, 2400))
+    assert all(len([t for t, _ in after[nid] if t <= 2000]) + len([t for t, _ in after[nid] if t > 2000]) >= 10
+               for nid in range(2000, 2400))
+    r = lib.ngt_create_empty_results(err)
+    found = 0
+    for q in range(2000, 2400, 7):
+        assert lib.ngt_search_index_as_float(ix, capi.fptr(base[q]), 128, 3, 0.1, -1.0, r, err)
+        found += capi.results_of(lib, r, err)[0][0] == q + 1
+    assert found >= 0.9 * len(range(2000, 2400, 7))
+    lib.ngt_destroy_results(r)
+    lib.ngt_close_index(ix)
+    lib.ngt_destroy_property(prop)
+    lib.ngt_destroy_error_object(err)
