@@ -413,6 +413,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
     // per-phase cycle counters of warp 0: compiled in only with -DSEARCH_PHASE_PROFILE (they cost ten registers)
 #ifdef SEARCH_PHASE_PROFILE
     uint32_t pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint64_t spec_second = KEY_NONE, spec_third = KEY_NONE;
     long long tp = a.prof ? clock64() : 0;
 #define PROF_MARK(i)                     \
   if (a.prof) {                          \
@@ -560,6 +561,28 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
           __syncwarp();
           const uint32_t t = key_id(best);
           st_exp++;
+#ifdef SEARCH_PHASE_PROFILE
+          // development probe: how often is the popped node the one that was second best at the previous pop?
+          // (slot 4 of the phase record: it was the second best; slot 2: it was the second or third best)
+          if (a.prof) {
+            if (best == spec_second) pf[4]++;
+            if (best == spec_second || best == spec_third) pf[2]++;
+            uint64_t s2 = KEY_NONE, s3 = KEY_NONE;   // the two smallest remaining keys
+            for (uint32_t i = lane; i < qsize; i += 32) {
+              uint64_t v = queue[i];
+              if (v < s2) { s3 = s2; s2 = v; } else if (v < s3) s3 = v;
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+              uint64_t o2 = shfl_xor_u64(s2, o), o3 = shfl_xor_u64(s3, o);
+              uint64_t lo = s2 < o2 ? s2 : o2, hi = s2 < o2 ? o2 : s2;
+              uint64_t m3 = s3 < o3 ? s3 : o3;
+              s2 = lo;
+              s3 = hi < m3 ? hi : m3;
+            }
+            spec_second = s2;
+            spec_third = s3;
+          }
+#endif
           PROF_MARK(1)
           if (use_head) {
             // the whole (capped) list is one row of the head table; empty slots are zero
@@ -581,7 +604,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
             cur_pos = 0;
             st_edge += cur_deg;
           }
-          PROF_MARK(2)
+          PROF_MARK(1)
         }
         if (WS == 0 && !overflow && !finished && visited_n + take > a.hash_limit) overflow = true;
         if (lane == 0) {

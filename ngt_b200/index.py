@@ -258,6 +258,24 @@ class Index:
         self._gpu.build_seed_table(min(self.n_pivots, n), 1)
         self.prop["GraphType"] = "ANNG"
 
+    def refine_anng(self, epsilon=0.1, expected_accuracy=0.0, num_of_edges=0, num_of_explored_edges=INT_MIN,
+                    batch_size=10000):
+        """ngtpy.Index.refine_anng (python/src/ngtpy.cpp:548-553 -> GraphReconstructor::refineANNG,
+        lib/NGT/GraphReconstructor.h:814-924) on the device."""
+        import torch
+        if self._pending:
+            raise NgtGpuError(_lib.ERR_STATE, "objects were appended: call build_index() first")
+        if expected_accuracy > 0.0:
+            raise NgtGpuError(_lib.ERR_INVALID, "refine_anng: expected accuracy needs an accuracy table; give epsilon")
+        dev = torch.device("cuda", self.device)
+        rp, col, dist = self._graph
+        g = build.refine_anng(self._gpu, torch.from_numpy(rp.astype(np.int64)).to(dev),
+                              torch.from_numpy(col.astype(np.int32)).to(dev), torch.from_numpy(dist).to(dev),
+                              epsilon=epsilon, no_of_edges=num_of_edges,
+                              edge_size=-1 if num_of_explored_edges == INT_MIN else num_of_explored_edges,
+                              batch_size=batch_size, edge_size_for_creation=int(self.prop.get("EdgeSizeForCreation", 10)))
+        self._graph = (g[0].cpu().numpy().astype(np.uint64), g[1].cpu().numpy().astype(np.uint32), g[2].cpu().numpy())
+
     def remove(self, object_id):
         oid = object_id + 1 if self.zero_numbering else object_id
         if oid < 1 or oid > self._objects.shape[0] or not self._present[oid]:
@@ -284,3 +302,56 @@ class Index:
 
     def close(self):
         self._gpu.close()
+
+
+class Optimizer:
+    """ngtpy.Optimizer (python/src/ngtpy.cpp:566-607 over NGT::GraphOptimizer, lib/NGT/GraphOptimizer.h): `execute`
+    runs reconstructGraph + shortcut reduction on the device and writes the ONNG in NGT's file format. The
+    search-parameter tuning steps (timed host searches) are outside the hot path: `adjust_search_coefficients` and
+    `optimize_search_parameters` raise."""
+
+    def __init__(self, num_of_outgoings=-1, num_of_incomings=-1, num_of_queries=-1, num_of_objects=-1,
+                 low_accuracy_from=-1.0, low_accuracy_to=-1.0, high_accuracy_from=-1.0, high_accuracy_to=-1.0,
+                 gt_epsilon=-1.7976931348623157e308, margin=-1.0, log_disabled=False, device=0):
+        # GraphOptimizer::init, lib/NGT/GraphOptimizer.h:60-78
+        self.outgoing, self.incoming, self.min_edges = 10, 120, 0
+        self.shortcut_reduction = True
+        self.device = device
+        self.set(num_of_outgoings, num_of_incomings)
+
+    def set(self, num_of_outgoings=-1, num_of_incomings=-1, *_, **__):
+        if num_of_outgoings >= 0:
+            self.outgoing = num_of_outgoings
+        if num_of_incomings >= 0:
+            self.incoming = num_of_incomings
+
+    def set_processing_modes(self, shortcut_reduction=True, search_parameter_optimization=True,
+                             prefetch_parameter_optimization=True, accuracy_table_generation=True):
+        self.shortcut_reduction = bool(shortcut_reduction)
+
+    def execute(self, in_path, out_path):
+        import shutil
+        import torch
+        if os.path.exists(out_path):
+            raise NgtGpuError(_lib.ERR_INVALID, "Optimizer::execute: The specified index exists. " + out_path)
+        shutil.copytree(in_path, out_path)
+        prop = index_io.read_prf(out_path)
+        row_ptr, col, dist, present = index_io.read_graph(out_path)
+        dev = torch.device("cuda", self.device)
+        g = (torch.from_numpy(row_ptr.astype(np.int64)).to(dev), torch.from_numpy(col.astype(np.int32)).to(dev),
+             torch.from_numpy(dist).to(dev))
+        if self.outgoing > 0 or self.incoming > 0:
+            if prop.get("GraphType", "ANNG") != "ANNG":          # convertToANNG, GraphReconstructor.h:389-423
+                g = build.reconstruct_graph_device(g[0], g[1], g[2], 0xffffffff, 0xffffffff)
+            g = build.reconstruct_graph_device(g[0], g[1], g[2], max(self.outgoing, 0), max(self.incoming, 0))
+            prop["GraphType"] = "ONNG"
+        if self.shortcut_reduction:
+            g = build.adjust_paths(g[0], g[1], g[2], self.min_edges)
+        index_io.write_graph(out_path, g[0].cpu().numpy().astype(np.uint64), g[1].cpu().numpy().astype(np.uint32),
+                             g[2].cpu().numpy(), present)
+        index_io.write_prf(out_path, prop)
+
+    def adjust_search_coefficients(self, path):
+        raise NgtGpuError(_lib.ERR_INVALID, "not provided by the B200 engine (search-parameter tuning is outside the hot path)")
+
+    optimize_search_parameters = adjust_search_coefficients

@@ -176,3 +176,35 @@ def test_index_mirror_round_trip(eng, tmp_path):
     res2 = again.search(q[0], size=5, epsilon=0.3)
     assert len(res2) == 5 and all(r[0] != lin[0][0] + 1 for r in res2)
     again.close()
+
+
+def test_index_mirror_refine_and_optimizer(eng, tmp_path):
+    """ngtpy's Index.refine_anng and Optimizer.execute on the mirror: the ONNG written through Optimizer equals the
+    reference's (tests/golden/adjust_paths.npz) and reopens as an index."""
+    import os
+    from conftest import GOLDEN
+    from ngt_b200 import index as ngt
+    from ngt_b200 import index_io, synth
+    z = np.load(os.path.join(GOLDEN, "reconstruct.npz"))
+    a = np.load(os.path.join(GOLDEN, "adjust_paths.npz"))
+    base = synth.make("sift", 1500, 1)
+    src, dst = str(tmp_path / "anng"), str(tmp_path / "onng")
+    os.makedirs(src)
+    index_io.write_prf(src, dict(index_io.DEFAULT_PRF, Dimension="128", EdgeSizeForCreation="20", EdgeSizeForSearch="0"))
+    index_io.write_objects(src, base)
+    index_io.write_graph(src, z["anng_row_ptr"].astype(np.uint64), z["anng_col"], z["anng_dist"])
+    opt = ngt.Optimizer(num_of_outgoings=10, num_of_incomings=40)
+    opt.execute(src, dst)
+    with pytest.raises(eng.NgtGpuError):
+        opt.execute(src, dst)                                   # the output exists
+    rp, col, dist, _ = index_io.read_graph(dst)
+    assert (col == a["sift_o10_i40_adj_col"]).all() and (rp[:1502] == a["sift_o10_i40_adj_row_ptr"]).all()
+    assert index_io.read_prf(dst)["GraphType"] == "ONNG"
+    ix = ngt.Index(dst)
+    q = synth.make("sift", 3, 2)
+    assert [r[0] for r in ix.search(q[0], size=5, epsilon=0.3)] == [r[0] for r in ix.linear_search(q[0], size=5)]
+    edges = ix._graph[1].size
+    ix.refine_anng(epsilon=0.1, num_of_edges=0, batch_size=400)
+    assert ix._graph[1].size > edges
+    assert [r[0] for r in ix.search(q[0], size=5, epsilon=0.3)] == [r[0] for r in ix.linear_search(q[0], size=5)]
+    ix.close()
