@@ -47,7 +47,7 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="replica", choices=["replica", "shard"])
-    ap.add_argument("--n", type=int, default=1000000)
+    ap.add_argument("--n", "--objects", dest="n", type=int, default=1000000)
     ap.add_argument("--nq", type=int, default=10000)
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--shape", default="sift")
@@ -144,11 +144,18 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def metric_name(a, dim):
+    """BASELINE.json's metric on configs[1]; other shapes (development runs of configs[2..4]) say what they are."""
+    if a.shape == "sift" and a.n == 1000000:
+        return "QPS at recall@10>=0.95, synthetic 1Mx128 float L2 (sift-shape), batch 10k, k=10"
+    return "QPS at recall@10>=%.2f, synthetic %dx%d float L2 (%s-shape), batch %d, k=%d" % (a.recall, a.n, dim, a.shape, a.nq, a.k)
+
+
 def workload_desc(a, dim):
     """config.workload: the same string in both arms."""
-    return ("configs[1]: synthetic %dx%d float L2 (%s-shape), ONNG from the exact kNN graph (knn=%d, reconstructGraph "
+    return ("%s: synthetic %dx%d float L2 (%s-shape), ONNG from the exact kNN graph (knn=%d, reconstructGraph "
             "outgoing=%d incoming=%d, shortcut reduction %s), batch %d queries, k=%d" % (
-                a.n, dim, a.shape, a.knn, a.outgoing, a.incoming, "on" if a.shortcut_reduction else "off", a.nq, a.k))
+                "configs[1]" if a.shape == "sift" else "configs[3]" if a.shape == "gist" else "configs[2]", a.n, dim, a.shape, a.knn, a.outgoing, a.incoming, "on" if a.shortcut_reduction else "off", a.nq, a.k))
 
 
 def index_tag(a, rank=0, world=1):
@@ -405,7 +412,7 @@ def run_ours(a):
     k_ms = kms.value / max(kcnt.value, 1)
     achieved = bytes_step / (k_ms / 1e3) / 1e9 if k_ms > 0 else 0.0
     out = {
-        "metric": "QPS at recall@10>=0.95, synthetic 1Mx128 float L2 (sift-shape), batch 10k, k=10",
+        "metric": metric_name(a, dim),
         "value": round(value, 1), "unit": "queries/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": round(ms_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
@@ -414,14 +421,14 @@ def run_ours(a):
                    "seeds": "nearest %d of %d device pivots" % (a.seeds, a.pivots),
                    "parallelism": ("replica x%d (one 10k batch per GPU)" % world) if a.mode == "replica" else
                                   ("rows sharded x%d + all-gather merge" % world),
-                   "l2_policy": "inputs larger than L2 (512 MB of rows vs 126 MB), 4 rotating query batches",
+                   "l2_policy": "inputs larger than L2 (%d MB of rows vs 126 MB), 4 rotating query batches" % (info["n"] * dim * 4 >> 20),
                    "graph": info["graph"], "setup_s": {k: info[k] for k in ("gen_s", "knn_graph_s", "reconstruct_s", "adjust_paths_s")},
                    "overflow_queries_per_step": overflow, "epsilon_sweep": curve},
         "e2e": {"value": round(e2e_value, 1), "unit": "queries/s", "ms_per_step": round(e2e_ms, 4),
                 "h2d_bytes_per_step": a.nq * dim * 4, "d2h_bytes_per_step": a.nq * a.k * 8 + a.nq * 4},
         "gpu_launches": int(launches),
         "clocks": clock_info,
-        "roofline": {"kernel": "search_kernel<F_L2,G32,CPL1> (graph traversal)", "bound": "hbm",
+        "roofline": {"kernel": "search_kernel<F_L2,G32,CPL%d> (graph traversal)" % (1 if dim <= 128 else 2 if dim <= 256 else 4 if dim <= 512 else 8 if dim <= 1024 else 0), "bound": "hbm",
                      "achieved": round(achieved, 1), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": None,
                      "kernel_ms": round(k_ms, 4), "algorithmic_bytes_per_launch": bytes_step,
@@ -429,7 +436,7 @@ def run_ours(a):
                      "n_expanded_per_query": round(float(st[:, 2].mean()), 1)},
     }
     tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and a.shape == "sift" and a.n == 1000000 and a.mode == "replica":   # the capture is of configs[1]
         try:
             out["roofline"]["traffic"] = json.load(open(tp)).get("search_kernel_dram_bytes_per_launch")
         except Exception:
@@ -507,7 +514,7 @@ def run_reference(a):
         recall_at_k(o[0], o[1], o[2].astype(np.int64), gt_ids[:m], gt_d[:m])
     out = {
         "impl": "reference",
-        "metric": "QPS at recall@10>=0.95, synthetic 1Mx128 float L2 (sift-shape), batch 10k, k=10",
+        "metric": metric_name(a, qs.shape[1]),
         "value": round(qps, 1), "unit": "queries/s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
