@@ -38,6 +38,8 @@
 // re-run by a later launch with a larger slab or, finally (WS == 1), with an exact bitmap and a large
 // queue in HBM (the reference's own structures, Graph.h:751-799).
 #pragma once
+#include <cfloat>
+
 #include "ngtgpu_internal.cuh"
 
 #ifndef SEARCH_WARPS
@@ -206,6 +208,143 @@ __device__ __forceinline__ void fold8(T (&v)[8], int lane) {
   v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
+// ---- unchecked set (UncheckedSet, Graph.h:757-799): a priority queue split in two ------------------------
+// "front": the smallest unchecked keys, sorted, one per lane of warp 0 (registers; empty lanes hold KEY_NONE);
+// "back":  everything else, unsorted, in `queue` (shared memory; global memory in the HBM tier).
+// Invariant: every front key < T <= every back key, where T is the smallest key of the back (KEY_NONE when
+// the back is empty). Popping is a lane shift; a new key that is not below T is appended to the back without
+// looking at anything else; when the front runs dry it is refilled from the back in two passes.
+struct Unchecked {
+  uint64_t front;   // this lane's key
+  uint32_t fn;      // keys in the front
+  uint32_t qsize;   // keys in the back
+  uint64_t T;       // smallest key of the back
+  uint64_t *queue;
+  uint32_t cap;
+};
+
+__device__ __forceinline__ uint64_t shfl_down_u64(uint64_t v, int d) {
+  uint32_t lo = __shfl_down_sync(0xffffffffu, (uint32_t)v, d);
+  uint32_t hi = __shfl_down_sync(0xffffffffu, (uint32_t)(v >> 32), d);
+  return ((uint64_t)hi << 32) | lo;
+}
+
+// drop the back entries beyond the exploration radius: they can never be expanded (the radius only shrinks)
+__device__ __forceinline__ void back_compact(Unchecked &U, float er, int lane) {
+  uint32_t w = 0;
+  for (uint32_t i0 = 0; i0 < U.qsize; i0 += 32) {
+    uint64_t v = i0 + lane < U.qsize ? U.queue[i0 + lane] : KEY_NONE;
+    bool keep = v != KEY_NONE && key_dist(v) <= er;
+    uint32_t km = __ballot_sync(0xffffffffu, keep);
+    __syncwarp();
+    if (keep) U.queue[w + __popc(km & lanemask_lt())] = v;
+    __syncwarp();
+    w += __popc(km);
+  }
+  U.qsize = w;
+  if (w == 0) U.T = KEY_NONE;   // T is the back's minimum: it goes only when everything goes
+}
+
+// one key appended to the back by lane 0; false when the back is full even after compaction
+__device__ __forceinline__ bool back_push(Unchecked &U, uint64_t key, float er, int lane) {
+  if (U.qsize >= U.cap) {
+    back_compact(U, er, lane);
+    if (U.qsize >= U.cap) return false;
+  }
+  if (lane == 0) U.queue[U.qsize] = key;
+  U.qsize++;
+  __syncwarp();
+  return true;
+}
+
+__device__ __forceinline__ void prefetch_head_row(const uint32_t *head, uint32_t id, uint32_t edge_cap) {
+  const uint32_t *hp = head + (size_t)id * SEARCH_HEAD;
+  const uint32_t lines = ((edge_cap < SEARCH_HEAD ? edge_cap : SEARCH_HEAD) + 31) / 32;
+  for (uint32_t l = 0; l < lines; l++) asm volatile("prefetch.global.L2 [%0];" ::"l"(hp + l * 32));
+}
+
+// a key into the sorted front; the key that falls off the end (KEY_NONE unless the front was full) is returned
+__device__ __forceinline__ uint64_t front_insert(Unchecked &U, uint64_t key, int lane) {
+  const uint64_t evicted = shfl_u64(U.front, 31);
+  const uint32_t pos = __popc(__ballot_sync(0xffffffffu, U.front < key));
+  const uint64_t up = shfl_up_u64(U.front, 1);
+  if ((uint32_t)lane == pos) U.front = key;
+  else if ((uint32_t)lane > pos) U.front = up;
+  if (U.fn < 32) U.fn++;
+  return evicted;
+}
+
+// general insertion of one key (warp 0, every lane holds the same `key`); false on overflow of the back.
+// head != nullptr: pull the head-table row of a key that enters the front towards L2 (it is likely to be popped)
+__device__ __forceinline__ bool unchecked_insert(Unchecked &U, uint64_t key, float er, int lane, const uint32_t *head,
+                                                 uint32_t edge_cap) {
+  if (key >= U.T) return back_push(U, key, er, lane);
+  if (U.fn == 32 && key > shfl_u64(U.front, 31)) {
+    // between the front's largest key and T: it becomes the back's new minimum
+    if (!back_push(U, key, er, lane)) return false;
+    U.T = key;
+    return true;
+  }
+  const uint64_t ev = front_insert(U, key, lane);
+  if (head && lane == 0) prefetch_head_row(head, key_id(key), edge_cap);
+  if (ev != KEY_NONE) {
+    if (!back_push(U, ev, er, lane)) return false;
+    U.T = ev;
+  }
+  return true;
+}
+
+// ascending bitonic sort of one key per lane
+__device__ __forceinline__ uint64_t warp_sort_u64(uint64_t v, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const uint64_t o = shfl_xor_u64(v, j);
+      const bool take_min = (((lane & k) == 0) == ((lane & j) == 0));
+      const uint64_t lo = v < o ? v : o, hi = v < o ? o : v;
+      v = take_min ? lo : hi;
+    }
+  }
+  return v;
+}
+
+// The front is empty: move the smallest keys of the back into it. Pass 1: every lane finds the two smallest keys of
+// its stride; with T' = the smallest of the lanes' SECOND keys, at most one key per lane (its first) is below T' and
+// the overall minimum always is. Pass 2: the back is rewritten without them (and without keys beyond the exploration
+// radius). T' stays in the back and is its new minimum.
+__device__ __forceinline__ void front_refill(Unchecked &U, float er, int lane) {
+  uint64_t m1 = KEY_NONE, m2 = KEY_NONE;
+  for (uint32_t i = lane; i < U.qsize; i += 32) {
+    const uint64_t v = U.queue[i];
+    if (v < m1) {
+      m2 = m1;
+      m1 = v;
+    } else if (v < m2) m2 = v;
+  }
+  uint64_t t = m2;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const uint64_t ot = shfl_xor_u64(t, o);
+    if (ot < t) t = ot;
+  }
+  const bool mv = m1 < t;
+  uint32_t w = 0;
+  for (uint32_t i0 = 0; i0 < U.qsize; i0 += 32) {
+    uint64_t v = i0 + lane < U.qsize ? U.queue[i0 + lane] : KEY_NONE;
+    bool keep = v != KEY_NONE && v >= t && key_dist(v) <= er;
+    uint32_t km = __ballot_sync(0xffffffffu, keep);
+    __syncwarp();
+    if (keep) U.queue[w + __popc(km & lanemask_lt())] = v;
+    __syncwarp();
+    w += __popc(km);
+  }
+  U.qsize = w;
+  U.T = w ? t : KEY_NONE;
+  U.fn = __popc(__ballot_sync(0xffffffffu, mv));
+  U.front = warp_sort_u64(mv ? m1 : KEY_NONE, lane);
+}
+
 // ---- visited set of WS == 0: exact hash in a per-CTA slab of global memory (L2 resident) ----------------
 // The slab is an array of 32-byte buckets of eight ids. A lookup is ONE 32-byte read of the home bucket
 // (ld.global.cg: served by L2, never a stale L1 line): the id is there, or the bucket has a free slot and
@@ -261,6 +400,25 @@ __device__ __forceinline__ bool bitmap_visit(uint32_t *bitmap, uint32_t nid) {
   return (old & bit) == 0;
 }
 
+// A finished distance goes to the round's key list. aligned: slot j of the list belongs to candidate j (seed rounds and
+// negative epsilon keep the reference's element order); otherwise keys beyond the exploration radius the round started
+// with are dropped here -- the radius only shrinks, so the merge would drop them anyway -- and the rest is appended in
+// arrival order (the merge has set semantics). Called by all lanes of a warp; `owner` lanes carry a distance.
+__device__ __forceinline__ void publish_key(bool aligned, bool owner, uint32_t j, float d, const uint32_t *cand_ids,
+                                            float er_pub, uint64_t *keys, uint32_t *key_n, int lane) {
+  if (aligned) {
+    if (owner) keys[j] = make_key(d, cand_ids[j]);
+    return;
+  }
+  const bool pass = owner && d <= er_pub;
+  const uint32_t pm = __ballot_sync(0xffffffffu, pass);
+  if (pm == 0) return;
+  uint32_t base = 0;
+  if (lane == 0) base = atomicAdd(key_n, (uint32_t)__popc(pm));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (pass) keys[base + __popc(pm & lanemask_lt())] = make_key(d, cand_ids[j]);
+}
+
 template <int ACC, int G, int CPL, int WS>
 __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel(const SearchArgs a) {
   constexpr int R = 32 / G;                 // rows per warp instruction (G < 32)
@@ -279,6 +437,10 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
   __shared__ int s_seeding;       // the round reads a seed list
   __shared__ uint32_t s_take;     // edges to filter this round
   __shared__ const uint32_t *s_src;  // where they are (head row, CSR slice or seed list)
+  __shared__ int s_src_shared;    // s_src points into s_pref (shared memory)
+  __shared__ uint32_t s_key_n;    // keys published by the distance phase (rounds that drop keys beyond s_er)
+  __shared__ float s_er;          // exploration radius at the start of the round (FLT_MAX: keep every key, in order)
+  __shared__ __align__(16) uint32_t s_pref[2][SEARCH_HEAD];   // head-table row of the node expected to be popped next
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -322,6 +484,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
       s_query = w < total ? (a.query_list ? a.query_list[w] : w) : 0xffffffffu;
       s_state = 0;
       s_cand_n = 0;
+      s_key_n = 0;
       s_edge_n = 0;
     }
     __syncthreads();
@@ -399,7 +562,13 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
     res.smem = s_results;
     res.k = a.k;
     res.n = 0;
-    uint32_t qsize = 0;           // unchecked entries
+    Unchecked U;
+    U.front = KEY_NONE;
+    U.fn = 0;
+    U.qsize = 0;
+    U.T = KEY_NONE;
+    U.queue = queue;
+    U.cap = a.queue_cap;
     float radius = a.radius;      // sc.radius
     float er = a.coef * radius;   // explorationRadius (Graph.cpp:420)
     uint32_t visited_n = 0;
@@ -410,10 +579,12 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
     bool seeding = true;
     bool head_round = false;      // the round in flight read a head-table row (its edge count comes from s_edge_n)
     uint32_t cand_n = 0;
+    uint32_t pref_id = 0;         // node whose head-table row is staged in s_pref[pref_buf] (0: none)
+    uint32_t pref_buf = 0;
+    const uint32_t *head_pf = use_head ? a.head : nullptr;
     // per-phase cycle counters of warp 0: compiled in only with -DSEARCH_PHASE_PROFILE (they cost ten registers)
 #ifdef SEARCH_PHASE_PROFILE
     uint32_t pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    uint64_t spec_second = KEY_NONE, spec_third = KEY_NONE;
     long long tp = a.prof ? clock64() : 0;
 #define PROF_MARK(i)                     \
   if (a.prof) {                          \
@@ -433,11 +604,14 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
         if (head_round) st_edge += s_edge_n;
         visited_n += cand_n;
         st_dist += cand_n;
-        if (cand_n) {
+        // keys of the previous round: all of them in candidate order (seed rounds, negative epsilon), else only
+        // those within the exploration radius the round started with, in no particular order
+        const uint32_t key_n = (ordered || seeding) ? cand_n : s_key_n;
+        if (key_n) {
           if (!ordered && !seeding) {
             // set semantics: results first, then everything within the final explorationRadius
-            for (uint32_t j0 = 0; j0 < cand_n; j0 += 32) {
-              uint64_t key = j0 + lane < cand_n ? s_cand_keys[j0 + lane] : KEY_NONE;
+            for (uint32_t j0 = 0; j0 < key_n; j0 += 32) {
+              uint64_t key = j0 + lane < key_n ? s_cand_keys[j0 + lane] : KEY_NONE;
               uint32_t m = __ballot_sync(0xffffffffu, key != KEY_NONE && key_dist(key) <= radius);
               while (m) {
                 int src = __ffs(m) - 1;
@@ -449,45 +623,38 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
               }
             }
             er = a.coef * radius;
-            for (uint32_t j0 = 0; j0 < cand_n && !overflow; j0 += 32) {
-              uint64_t key = j0 + lane < cand_n ? s_cand_keys[j0 + lane] : KEY_NONE;
-              bool acc = key != KEY_NONE && key_dist(key) <= er;
-              uint32_t m = __ballot_sync(0xffffffffu, acc);
-              uint32_t cnt = __popc(m);
-              if (qsize + cnt > a.queue_cap) {
-                // compact: entries beyond explorationRadius can never be expanded
-                uint32_t w = 0;
-                for (uint32_t i0 = 0; i0 < qsize; i0 += 32) {
-                  uint64_t v = i0 + lane < qsize ? queue[i0 + lane] : KEY_NONE;
-                  bool keep = v != KEY_NONE && key_dist(v) <= er;
-                  uint32_t km = __ballot_sync(0xffffffffu, keep);
-                  __syncwarp();
-                  if (keep) queue[w + __popc(km & lanemask_lt())] = v;
-                  __syncwarp();
-                  w += __popc(km);
+            for (uint32_t j0 = 0; j0 < key_n && !overflow; j0 += 32) {
+              uint64_t key = j0 + lane < key_n ? s_cand_keys[j0 + lane] : KEY_NONE;
+              const bool acc = key != KEY_NONE && key_dist(key) <= er;
+              // keys not below the back's minimum go to the back in one piece (T can only decrease afterwards)
+              const bool low = acc && key < U.T;
+              const uint32_t bm = __ballot_sync(0xffffffffu, acc && !low);
+              uint32_t fm = __ballot_sync(0xffffffffu, low);
+              const uint32_t cnt = __popc(bm);
+              if (cnt) {
+                if (U.qsize + cnt > U.cap) back_compact(U, er, lane);
+                if (U.qsize + cnt > U.cap) {
+                  overflow = true;
+                  break;
                 }
-                qsize = w;
+                if (acc && !low) U.queue[U.qsize + __popc(bm & lanemask_lt())] = key;
+                U.qsize += cnt;
+                __syncwarp();
               }
-              if (qsize + cnt > a.queue_cap) {
-                overflow = true;
-                break;
-              }
-              if (acc) {
-                queue[qsize + __popc(m & lanemask_lt())] = key;
-                if (use_head) {
-                  // its edges will be wanted when it is popped: pull that row of the head table towards L2 now
-                  const uint32_t *hp = a.head + (size_t)key_id(key) * SEARCH_HEAD;
-                  const uint32_t lines = ((a.edge_cap < SEARCH_HEAD ? a.edge_cap : SEARCH_HEAD) + 31) / 32;
-                  for (uint32_t l = 0; l < lines; l++) asm volatile("prefetch.global.L2 [%0];" ::"l"(hp + l * 32));
+              while (fm) {
+                int src = __ffs(fm) - 1;
+                fm &= fm - 1;
+                if (!unchecked_insert(U, shfl_u64(key, src), er, lane, head_pf, a.edge_cap)) {
+                  overflow = true;
+                  break;
                 }
               }
-              qsize += cnt;
             }
             __syncwarp();
           } else {
             // the reference's order: seeds (all go to unchecked, Graph.cpp:352-366) and coef < 1
-            for (uint32_t j0 = 0; j0 < cand_n && !overflow; j0 += 32) {
-              uint64_t key = j0 + lane < cand_n ? s_cand_keys[j0 + lane] : KEY_NONE;
+            for (uint32_t j0 = 0; j0 < key_n && !overflow; j0 += 32) {
+              uint64_t key = j0 + lane < key_n ? s_cand_keys[j0 + lane] : KEY_NONE;
               uint32_t m = __ballot_sync(0xffffffffu, key != KEY_NONE);
               while (m) {
                 int src = __ffs(m) - 1;
@@ -495,12 +662,10 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
                 uint64_t kk = shfl_u64(key, src);
                 float d = key_dist(kk);
                 if (!seeding && d > er) continue;
-                if (qsize >= a.queue_cap) {
+                if (!unchecked_insert(U, kk, er, lane, head_pf, a.edge_cap)) {
                   overflow = true;
                   break;
                 }
-                if (lane == 0) queue[qsize] = kk;
-                qsize++;
                 if (d <= radius) {
                   result_insert(res, kk, lane);
                   if (!seeding && res.n >= res.k) {
@@ -518,6 +683,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
         PROF_MARK(0)
         // ---- next edges: the rest of the current list, or pop the smallest unchecked node
         bool finished = false;
+        bool src_shared = false;
         uint32_t take = 0;
         const uint32_t *src_ptr = nullptr;
         while (!overflow && !finished && take == 0) {
@@ -534,63 +700,50 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
             if (res.n >= res.k) radius = key_dist(result_kth(res));
             er = a.coef * radius;
           }
-          uint64_t best = KEY_NONE;
-          uint32_t bi = 0;
-          for (uint32_t i = lane; i < qsize; i += 32) {
-            uint64_t v = queue[i];
-            if (v < best) {
-              best = v;
-              bi = i;
+          if (U.fn == 0 && U.qsize != 0 && key_dist(U.T) <= er) {
+            front_refill(U, er, lane);
+            if (head_pf) {
+              const uint64_t mine = U.front;
+              if (mine != KEY_NONE) prefetch_head_row(head_pf, key_id(mine), a.edge_cap);
             }
+            PROF_MARK(2)
           }
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            uint64_t ob = shfl_xor_u64(best, o);
-            uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ob < best) {
-              best = ob;
-              bi = oi;
-            }
-          }
-          if (best == KEY_NONE || key_dist(best) > er) {  // Graph.cpp:430-435
+          const uint64_t best = shfl_u64(U.front, 0);
+          if (U.fn == 0 || key_dist(best) > er) {  // Graph.cpp:430-435
             finished = true;
             break;
           }
-          if (lane == 0) queue[bi] = queue[qsize - 1];
-          qsize--;
-          __syncwarp();
+          U.front = shfl_down_u64(U.front, 1);
+          if (lane == 31) U.front = KEY_NONE;
+          U.fn--;
           const uint32_t t = key_id(best);
           st_exp++;
-#ifdef SEARCH_PHASE_PROFILE
-          // development probe: how often is the popped node the one that was second best at the previous pop?
-          // (slot 4 of the phase record: it was the second best; slot 2: it was the second or third best)
-          if (a.prof) {
-            if (best == spec_second) pf[4]++;
-            if (best == spec_second || best == spec_third) pf[2]++;
-            uint64_t s2 = KEY_NONE, s3 = KEY_NONE;   // the two smallest remaining keys
-            for (uint32_t i = lane; i < qsize; i += 32) {
-              uint64_t v = queue[i];
-              if (v < s2) { s3 = s2; s2 = v; } else if (v < s3) s3 = v;
-            }
-            for (int o = 16; o > 0; o >>= 1) {
-              uint64_t o2 = shfl_xor_u64(s2, o), o3 = shfl_xor_u64(s3, o);
-              uint64_t lo = s2 < o2 ? s2 : o2, hi = s2 < o2 ? o2 : s2;
-              uint64_t m3 = s3 < o3 ? s3 : o3;
-              s2 = lo;
-              s3 = hi < m3 ? hi : m3;
-            }
-            spec_second = s2;
-            spec_third = s3;
-          }
-#endif
           PROF_MARK(1)
           if (use_head) {
             // the whole (capped) list is one row of the head table; empty slots are zero
             take = a.edge_cap < SEARCH_HEAD ? a.edge_cap : SEARCH_HEAD;
-            src_ptr = a.head + (size_t)t * SEARCH_HEAD;
+            if (t == pref_id) {
+              src_ptr = s_pref[pref_buf];
+              src_shared = true;
+#ifdef SEARCH_PHASE_PROFILE
+              if (a.prof) pf[4]++;
+#endif
+            } else {
+              src_ptr = a.head + (size_t)t * SEARCH_HEAD;
+            }
             head_round = true;
             cur_deg = 0;
             cur_pos = 0;
+            // the node most likely to be popped next is the front's new first key: stage its row of the head table in
+            // shared memory while this round's rows are in flight (waited for with warp 0's own row copies)
+            const uint64_t nxt = shfl_u64(U.front, 0);
+            pref_id = 0;
+            if (U.fn != 0 && key_dist(nxt) <= er) {
+              pref_buf ^= 1u;
+              pref_id = key_id(nxt);
+              if ((uint32_t)lane * 4u < take)
+                cp_async_row16(&s_pref[pref_buf][lane * 4], a.head + (size_t)pref_id * SEARCH_HEAD + lane * 4);
+            }
           } else {
             // longer lists (edgeSize > 64): walk the CSR slice (Graph.cpp:438 caps it)
             uint64_t b = 0, e = 0;
@@ -609,10 +762,13 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
         if (WS == 0 && !overflow && !finished && visited_n + take > a.hash_limit) overflow = true;
         if (lane == 0) {
           s_cand_n = 0;
+          s_key_n = 0;
           s_edge_n = 0;
           s_take = take;
           s_src = src_ptr;
+          s_src_shared = src_shared ? 1 : 0;
           s_seeding = seeding ? 1 : 0;
+          s_er = (ordered || seeding) ? FLT_MAX : er;
           if (overflow) s_state = 2;
           else if (finished) s_state = 1;
         }
@@ -635,6 +791,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
       {
         const uint32_t take = s_take;
         const uint32_t *src = s_src;
+        const bool src_sh = s_src_shared != 0;   // the row was staged in shared memory by the previous round
         const bool immediate = seeding_round;   // seed lists may repeat an id: insert at once so the second copy is seen
         if (!ordered) {
           // thread t looks at edges t, t + THREADS, ...: all edge loads first, then all bucket lookups
@@ -642,7 +799,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
 #pragma unroll
           for (int i = 0; i < SEARCH_EPT; i++) {
             const uint32_t e = (uint32_t)tid + i * SEARCH_THREADS;
-            nid[i] = e < take ? __ldg(src + e) : 0u;
+            nid[i] = e < take ? (src_sh ? src[e] : __ldg(src + e)) : 0u;
           }
           uint32_t new_mask = 0, n_valid = 0;
 #pragma unroll
@@ -702,7 +859,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
           // element order kept: warp 0 walks the edges 32 at a time
           uint32_t cn = 0, en = 0;
           for (uint32_t e0 = 0; e0 < take; e0 += 32) {
-            uint32_t nid = e0 + lane < take ? __ldg(src + e0 + lane) : 0u;
+            uint32_t nid = e0 + lane < take ? (src_sh ? src[e0 + lane] : __ldg(src + e0 + lane)) : 0u;
             const bool valid = nid != 0u && nid <= a.n;
             bool isnew = false;
             if (valid) {
@@ -744,6 +901,94 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
         const uint32_t srow_bytes = (G == 32 && CPL > 0) ? SROW : a.row_bytes;
         uint8_t *wstage = stage + (size_t)warp * wrows * srow_bytes;
         const uint32_t wstage_s = (uint32_t)__cvta_generic_to_shared(wstage) + (uint32_t)lane * 16u;
+        const bool aligned = ordered || seeding_round;
+        const float er_pub = s_er;
+        if (ROW8) {
+          // Rows of <= 512 bytes, pipelined. The warp's staging slice is two half-buffers of HR rows; its rows (slice
+          // `warp` of every pass of 4 * wrows candidates) are taken as a sequence of groups of HR rows, group g in
+          // half-buffer g & 1, each group one cp.async group: while the distances of group g are evaluated the copies
+          // of group g + 1 are in flight, and group g + 2 is issued as soon as g's buffer is free. Copies are
+          // branch-free: a row past the list's end, or a chunk past the row's end, has source size 0 (nothing is read,
+          // the slot is zero-filled).
+          const uint32_t HR = wrows >> 1;
+          const uint8_t *lane_src = a.objects + (size_t)lane * 16;
+          const uint32_t csize = (uint32_t)lane < a.chunks ? 16u : 0u;
+          const uint32_t rr = (uint32_t)lane >> 3;
+          const uint32_t rd0 = wstage_s - (uint32_t)lane * 16u + rr * SROW + ((uint32_t)lane & 7u) * 16u;
+#define ROW8_GBASE(g) (((g) >> 1) * (SEARCH_WARPS * wrows) + (uint32_t)warp * wrows + ((g) & 1u) * HR)
+#define ROW8_ISSUE(g)                                                                              \
+  {                                                                                                \
+    const uint32_t _b = ROW8_GBASE(g);                                                             \
+    if (_b < cn) {                                                                                 \
+      const uint32_t _left = cn - _b;                                                              \
+      const uint32_t _d0 = wstage_s + ((g) & 1u) * HR * SROW;                                      \
+      for (uint32_t _i0 = 0; _i0 < HR; _i0 += 4) {                                                 \
+        _Pragma("unroll") for (int _i = 0; _i < 4; _i++) {                                         \
+          const bool _in = _i0 + _i < _left;                                                       \
+          const uint32_t _id = _in ? s_cand_ids[_b + _i0 + _i] : 0u;                               \
+          cp_async_s16z(_d0 + (_i0 + _i) * SROW, mad_wide_ptr(_id, a.row_bytes, lane_src), _in ? csize : 0u); \
+        }                                                                                          \
+      }                                                                                            \
+    }                                                                                              \
+    asm volatile("cp.async.commit_group;" ::: "memory");                                           \
+  }
+          ROW8_ISSUE(0u)
+          ROW8_ISSUE(1u)
+          if (WS == 0 && pending_mask) {
+            // the insertions of this thread's new ids, overlapped with the row copies in flight
+#pragma unroll
+            for (int i = 0; i < SEARCH_EPT; i++)
+              if (pending_mask & (1u << i)) hash_insert(hash, a.hash_bits - 3, pending_id[i], bp[i]);
+            pending_mask = 0;
+          }
+          for (uint32_t g = 0;; g++) {
+            const uint32_t gb = ROW8_GBASE(g);
+            if (gb >= cn) break;
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            __syncwarp();
+            const uint32_t nr = cn - gb < HR ? cn - gb : HR;
+            const uint32_t ra0 = rd0 + (g & 1u) * HR * SROW;
+            // four rows per step, eight lanes each. Slots past the group's last row hold stale rows of earlier rounds
+            // (or zeros): they are read like the others and their result is dropped; chunks past the row's end read
+            // the zeroed tail against zero query chunks.
+            for (uint32_t r0 = 0; r0 < nr; r0 += 4) {
+              Sums p[4];
+#pragma unroll
+              for (int m = 0; m < 4; m++) {
+                p[m] = zero_sums();
+                acc_chunk<ACC>(p[m], q8[m], lds16(ra0 + r0 * SROW + m * 128));
+              }
+              Sums tot = zero_sums();
+              if (ACC == ACC_U8_L2 || ACC == ACC_U8_HAM) {
+                tot.u = (p[0].u + p[2].u) + (p[1].u + p[3].u);
+                tot.u += __shfl_xor_sync(0xffffffffu, tot.u, 4);
+                tot.u += __shfl_xor_sync(0xffffffffu, tot.u, 2);
+                tot.u += __shfl_xor_sync(0xffffffffu, tot.u, 1);
+              } else {
+                tot.f0 = (p[0].f0 + p[2].f0) + (p[1].f0 + p[3].f0);
+                tot.f0 += __shfl_xor_sync(0xffffffffu, tot.f0, 4);
+                tot.f0 += __shfl_xor_sync(0xffffffffu, tot.f0, 2);
+                tot.f0 += __shfl_xor_sync(0xffffffffu, tot.f0, 1);
+                if (ACC == ACC_F_COS) {
+                  tot.f1 = (p[0].f1 + p[2].f1) + (p[1].f1 + p[3].f1);
+                  tot.f1 += __shfl_xor_sync(0xffffffffu, tot.f1, 4);
+                  tot.f1 += __shfl_xor_sync(0xffffffffu, tot.f1, 2);
+                  tot.f1 += __shfl_xor_sync(0xffffffffu, tot.f1, 1);
+                }
+              }
+              const uint32_t r = r0 + rr;
+              const bool owner = (lane & 7) == 0 && r < nr;
+              float d = 0.f;
+              if (owner) d = finish_distance<ACC>(a.dtype, tot, qn);
+              publish_key(aligned, owner, gb + r, d, s_cand_ids, er_pub, s_cand_keys, &s_key_n, lane);
+            }
+            __syncwarp();
+            ROW8_ISSUE(g + 2u)
+          }
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+#undef ROW8_ISSUE
+#undef ROW8_GBASE
+        } else
         for (uint32_t j0 = warp * wrows; j0 < cn; j0 += SEARCH_WARPS * wrows) {
           const uint32_t nr = cn - j0 < wrows ? cn - j0 : wrows;
           if (G == 32 && CPL > 0) {
@@ -799,42 +1044,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
           }
           cp_async_commit_wait_all();
           __syncwarp();
-          if (ROW8) {
-            // four rows per step, eight lanes each. Slots past the slice's last row hold stale rows of earlier
-            // rounds (or the initial zeros): they are read like the others and their result is dropped; chunks
-            // past the row's end read the zeroed tail against zero query chunks.
-            const uint32_t rr = (uint32_t)lane >> 3;
-            const uint32_t ra0 = wstage_s - (uint32_t)lane * 16u + rr * SROW + ((uint32_t)lane & 7u) * 16u;
-            for (uint32_t r0 = 0; r0 < nr; r0 += 4) {
-              Sums p[4];
-#pragma unroll
-              for (int m = 0; m < 4; m++) {
-                p[m] = zero_sums();
-                acc_chunk<ACC>(p[m], q8[m], lds16(ra0 + r0 * SROW + m * 128));
-              }
-              Sums tot = zero_sums();
-              if (ACC == ACC_U8_L2 || ACC == ACC_U8_HAM) {
-                tot.u = (p[0].u + p[2].u) + (p[1].u + p[3].u);
-                tot.u += __shfl_xor_sync(0xffffffffu, tot.u, 4);
-                tot.u += __shfl_xor_sync(0xffffffffu, tot.u, 2);
-                tot.u += __shfl_xor_sync(0xffffffffu, tot.u, 1);
-              } else {
-                tot.f0 = (p[0].f0 + p[2].f0) + (p[1].f0 + p[3].f0);
-                tot.f0 += __shfl_xor_sync(0xffffffffu, tot.f0, 4);
-                tot.f0 += __shfl_xor_sync(0xffffffffu, tot.f0, 2);
-                tot.f0 += __shfl_xor_sync(0xffffffffu, tot.f0, 1);
-                if (ACC == ACC_F_COS) {
-                  tot.f1 = (p[0].f1 + p[2].f1) + (p[1].f1 + p[3].f1);
-                  tot.f1 += __shfl_xor_sync(0xffffffffu, tot.f1, 4);
-                  tot.f1 += __shfl_xor_sync(0xffffffffu, tot.f1, 2);
-                  tot.f1 += __shfl_xor_sync(0xffffffffu, tot.f1, 1);
-                }
-              }
-              const uint32_t r = r0 + rr;
-              if ((lane & 7) == 0 && r < nr)
-                s_cand_keys[j0 + r] = make_key(finish_distance<ACC>(a.dtype, tot, qn), s_cand_ids[j0 + r]);
-            }
-          } else if (CPL > 0 && CPL <= 2 && G == 32) {
+          if (CPL > 0 && CPL <= 2 && G == 32) {
             // eight rows at a time, folded together (fold8). Slots past the slice's last row hold stale rows of
             // earlier rounds (or the initial zeros): they are read like the others and their result is dropped;
             // chunks past the row's end read the zeroed tail. No predicates and no address selects in the loop.
@@ -868,8 +1078,10 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
                 }
               }
               const uint32_t r = r0 + ((lane >> 2) & 7);
-              if ((lane & 3) == 0 && r < nr)
-                s_cand_keys[j0 + r] = make_key(finish_distance<ACC>(a.dtype, tot, qn), s_cand_ids[j0 + r]);
+              const bool owner = (lane & 3) == 0 && r < nr;
+              float d = 0.f;
+              if (owner) d = finish_distance<ACC>(a.dtype, tot, qn);
+              publish_key(aligned, owner, j0 + r, d, s_cand_ids, er_pub, s_cand_keys, &s_key_n, lane);
             }
           } else if (G == 32) {
             // long rows: one row at a time (query chunks in registers, or in shared memory when CPL == 0)
@@ -886,7 +1098,9 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
                 for (uint32_t c = lane; c < a.chunks; c += 32) acc_chunk<ACC>(s, s_query_row[c], rp[c]);
               }
               group_fold<ACC, 32>(s);
-              if (lane == 0) s_cand_keys[j0 + r] = make_key(finish_distance<ACC>(a.dtype, s, qn), s_cand_ids[j0 + r]);
+              float d = 0.f;
+              if (lane == 0) d = finish_distance<ACC>(a.dtype, s, qn);
+              publish_key(aligned, lane == 0, j0 + r, d, s_cand_ids, er_pub, s_cand_keys, &s_key_n, lane);
             }
           } else {
             // short rows: R rows per warp instruction, G lanes each
@@ -896,7 +1110,10 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
               if (r < nr && (uint32_t)gl < a.chunks)
                 acc_chunk<ACC>(s, qreg[0], reinterpret_cast<const uint4 *>(wstage + (size_t)r * a.row_bytes)[gl]);
               group_fold<ACC, G>(s);
-              if (gl == 0 && r < nr) s_cand_keys[j0 + r] = make_key(finish_distance<ACC>(a.dtype, s, qn), s_cand_ids[j0 + r]);
+              const bool owner = gl == 0 && r < nr;
+              float d = 0.f;
+              if (owner) d = finish_distance<ACC>(a.dtype, s, qn);
+              publish_key(aligned, owner, j0 + r, d, s_cand_ids, er_pub, s_cand_keys, &s_key_n, lane);
             }
           }
           __syncwarp();
@@ -906,6 +1123,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
           for (int i = 0; i < SEARCH_EPT; i++)
             if (pending_mask & (1u << i)) hash_insert(hash, a.hash_bits - 3, pending_id[i], bp[i]);
         }
+        if (!ROW8 && warp == 0) cp_async_commit_wait_all();   // the staged head-table row of the expected next node
         if (warp == 0) { PROF_MARK(5) }
       }
       __syncthreads();  // (C) keys are published; the staging area may be overwritten
