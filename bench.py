@@ -428,7 +428,8 @@ def run_ours(a):
                 "h2d_bytes_per_step": a.nq * dim * 4, "d2h_bytes_per_step": a.nq * a.k * 8 + a.nq * 4},
         "gpu_launches": int(launches),
         "clocks": clock_info,
-        "roofline": {"kernel": "search_kernel<F_L2,G32,CPL%d> (graph traversal)" % (1 if dim <= 128 else 2 if dim <= 256 else 4 if dim <= 512 else 8 if dim <= 1024 else 0), "bound": "hbm",
+        "roofline": {"kernel": ("search_fast_kernel<F_L2,CH%d> (graph traversal)" % (1 if dim <= 32 else 2 if dim <= 64 else 4)) if 16 < dim <= 128 and a.edge_size <= 128 and 0 < a.edge_size and a.k <= 32 else
+                     "search_kernel<F_L2,G32,CPL%d> (graph traversal)" % (1 if dim <= 128 else 2 if dim <= 256 else 4 if dim <= 512 else 8 if dim <= 1024 else 0), "bound": "hbm",
                      "achieved": round(achieved, 1), "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                      "frac": round(achieved / peak, 4), "traffic": None,
                      "kernel_ms": round(k_ms, 4), "algorithmic_bytes_per_launch": bytes_step,

@@ -145,6 +145,9 @@ int ngtgpu_index_set_search_workspace(ngtgpu_index *index, uint32_t hash_bits, u
 /* Number of shared-memory tiers tried before the HBM tier: 2 (default: the configured one, then the largest
  * that fits an SM) or 1. */
 int ngtgpu_index_set_onchip_tiers(ngtgpu_index *index, int tiers);
+/* The first tier of the common case (rows of 80..512 bytes, edge cap <= 128, epsilon >= 0, size <= 32) runs a leaner
+ * kernel with the same results; 0 sends it through the general kernel as well (default 1). */
+int ngtgpu_index_set_fast_kernel(ngtgpu_index *index, int enabled);
 /* Shared-memory staging area (bytes per CTA) that neighbour rows are copied into with cp.async. */
 int ngtgpu_index_set_stage_bytes(ngtgpu_index *index, uint32_t bytes);
 uint64_t ngtgpu_index_last_overflows(const ngtgpu_index *index);

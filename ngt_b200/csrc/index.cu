@@ -440,6 +440,12 @@ extern "C" int ngtgpu_index_set_onchip_tiers(ngtgpu_index *ix, int tiers) {
   return NGTGPU_OK;
 }
 
+extern "C" int ngtgpu_index_set_fast_kernel(ngtgpu_index *ix, int enabled) {
+  if (!ix) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "null index handle");
+  ix->fast_kernel = enabled != 0;
+  return NGTGPU_OK;
+}
+
 extern "C" int ngtgpu_index_get_object(const ngtgpu_index *ix, uint32_t id, void *out) {
   if (!ix || !out) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "ngtgpu_index_get_object: null argument");
   if (!ix->d_objects || id == 0 || id > ix->n) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "ngtgpu_index_get_object: no such object");

@@ -19,6 +19,28 @@ extern template cudaError_t search_dispatch<ACC_F_COS>(const SearchArgs &, const
 extern template cudaError_t search_dispatch<ACC_U8_L2>(const SearchArgs &, const SearchLaunch &, int, int *);
 extern template cudaError_t search_dispatch<ACC_U8_HAM>(const SearchArgs &, const SearchLaunch &, int, int *);
 
+// the lean kernel of the common case (search_fast.cuh)
+template <int ACC>
+cudaError_t search_fast_dispatch(const SearchArgs &a, int ch, unsigned grid, size_t smem, cudaStream_t stream, int op,
+                                 int *blocks);
+extern template cudaError_t search_fast_dispatch<ACC_F_L2>(const SearchArgs &, int, unsigned, size_t, cudaStream_t, int, int *);
+extern template cudaError_t search_fast_dispatch<ACC_F_DOT>(const SearchArgs &, int, unsigned, size_t, cudaStream_t, int, int *);
+extern template cudaError_t search_fast_dispatch<ACC_F_COS>(const SearchArgs &, int, unsigned, size_t, cudaStream_t, int, int *);
+extern template cudaError_t search_fast_dispatch<ACC_U8_L2>(const SearchArgs &, int, unsigned, size_t, cudaStream_t, int, int *);
+extern template cudaError_t search_fast_dispatch<ACC_U8_HAM>(const SearchArgs &, int, unsigned, size_t, cudaStream_t, int, int *);
+
+static cudaError_t dispatch_fast(int acc, const SearchArgs &a, int ch, unsigned grid, size_t smem, cudaStream_t stream,
+                                 int op, int *blocks) {
+  switch (acc) {
+    case ACC_F_L2: return search_fast_dispatch<ACC_F_L2>(a, ch, grid, smem, stream, op, blocks);
+    case ACC_F_DOT: return search_fast_dispatch<ACC_F_DOT>(a, ch, grid, smem, stream, op, blocks);
+    case ACC_F_COS: return search_fast_dispatch<ACC_F_COS>(a, ch, grid, smem, stream, op, blocks);
+    case ACC_U8_L2: return search_fast_dispatch<ACC_U8_L2>(a, ch, grid, smem, stream, op, blocks);
+    case ACC_U8_HAM: return search_fast_dispatch<ACC_U8_HAM>(a, ch, grid, smem, stream, op, blocks);
+  }
+  return cudaErrorInvalidValue;
+}
+
 static cudaError_t dispatch(int acc, const SearchArgs &a, const SearchLaunch &l, int op, int *blocks) {
   switch (acc) {
     case ACC_F_L2: return search_dispatch<ACC_F_L2>(a, l, op, blocks);
@@ -122,11 +144,18 @@ int ngtgpu_traverse(ngtgpu_index *ix, const uint8_t *d_queries, uint32_t nq, con
     a.query_list = t == 0 ? nullptr : lists[(t - 1) & 1];
     a.query_list_count = t == 0 ? nullptr : ws + 2 * (t - 1) + 1;
     size_t smem = extra + (size_t)a.queue_cap * 8;
+    // the first tier of the common case runs the lean kernel: rows of 5..32 chunks, head-table adjacency, set semantics
+    // (epsilon >= 0), results in one warp's registers, a seed list that is one round
+    const bool fast = t == 0 && ix->fast_kernel && ix->chunks >= 5 && ix->chunks <= 32 && cap <= NGTGPU_HEAD_WIDTH &&
+                      a.coef >= 1.0f && k <= 32 && n_seeds <= SEARCH_CMAX;
+    const int fast_ch = ix->chunks <= 8 ? 1 : ix->chunks <= 16 ? 2 : 4;
+    if (fast) smem = 4 * 4096 + (size_t)a.queue_cap * 8;
     if (smem > 200 * 1024)
       NGTGPU_FAIL(NGTGPU_ERR_INVALID, "search: working set does not fit shared memory; lower queue_cap/size");
     l.smem = smem;
     int blocks = 0;
-    cudaError_t e = dispatch(ix->acc_kind, a, l, 1, &blocks);
+    cudaError_t e = fast ? dispatch_fast(ix->acc_kind, a, fast_ch, 0, smem, stream, 1, &blocks)
+                         : dispatch(ix->acc_kind, a, l, 1, &blocks);
     if (e != cudaSuccess) NGTGPU_FAIL(NGTGPU_ERR_CUDA, std::string("search occupancy query: ") + cudaGetErrorString(e));
     if (blocks < 1) blocks = 1;
     if (t > 0 && blocks > 2) blocks = 2;   // the overflow tier serves few queries: keep its slabs small
@@ -144,7 +173,7 @@ int ngtgpu_traverse(ngtgpu_index *ix, const uint8_t *d_queries, uint32_t nq, con
       CUDA_TRY(cudaEventCreate(&ev1));
       CUDA_TRY(cudaEventRecord(ev0, stream));
     }
-    e = dispatch(ix->acc_kind, a, l, 0, nullptr);
+    e = fast ? dispatch_fast(ix->acc_kind, a, fast_ch, l.grid, smem, stream, 0, nullptr) : dispatch(ix->acc_kind, a, l, 0, nullptr);
     if (e != cudaSuccess) NGTGPU_FAIL(NGTGPU_ERR_CUDA, std::string("search kernel launch: ") + cudaGetErrorString(e));
     ix->launches++;
     if (ix->timing && t == 0) {

@@ -46,6 +46,9 @@
 #define SEARCH_WARPS 4        // warps per query (1, 2 or 4)
 #endif
 #define SEARCH_THREADS (SEARCH_WARPS * 32)
+#ifndef SEARCH_PF_ROWS
+#define SEARCH_PF_ROWS 0      // development switch: 1/2 = prefetch new rows towards L2 from the filter (per line / bulk)
+#endif
 #ifndef SEARCH_MIN_CTAS
 #define SEARCH_MIN_CTAS (32 / SEARCH_WARPS)   // 64 registers per thread at 4 warps; nine CTAs (56 registers) spill and measured slower
 #endif
@@ -815,6 +818,18 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
                   pending_mask |= 1u << i;
                   pending_id[i] = nid[i];
                 }
+#if SEARCH_PF_ROWS == 1
+                if (isnew) {
+                  // the row will be copied to shared memory a few hundred cycles from now: start it towards L2
+                  const uint8_t *rp = a.objects + (size_t)nid[i] * a.row_bytes;
+                  for (uint32_t o = 0; o < a.row_bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + o));
+                }
+#elif SEARCH_PF_ROWS == 2
+                if (isnew) {
+                  const uint8_t *rp = a.objects + (size_t)nid[i] * a.row_bytes;
+                  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(rp), "r"(a.row_bytes) : "memory");
+                }
+#endif
               } else {
                 isnew = bitmap_visit(bitmap, nid[i]);
               }

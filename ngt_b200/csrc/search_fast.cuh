@@ -1,0 +1,451 @@
+// search_fast.cuh -- the traversal kernel for the common case, written for instruction economy.
+//
+// Same algorithm, same state and same results as search_kernel (search.cuh; NeighborhoodGraph::search,
+// lib/NGT/Graph.cpp:398-495 / 499-638), restricted to what the headline workloads use so that the hot loop is a
+// few hundred instructions instead of a few thousand (ncu source attribution of the general kernel: 5.4k
+// warp-instructions per expansion, a third of them address arithmetic around the row copies):
+//
+//   rows of <= 512 bytes (<= 32 chunks), edge cap <= 128 (head table), epsilon >= 0 (set semantics), k <= 32,
+//   <= 128 seeds, visited hash in the L2 slab (tier 0). Everything else runs search_kernel.
+//
+// One CTA (4 warps) per query, persistent grid. Per round:
+//   control  warp 0: merge the previous round's keys (only those within the exploration radius were published),
+//            pop the front of the unchecked set (sorted registers), make the popped node's head-table row
+//            available in shared memory (already there when the pop was predicted -- 63 % of the pops),
+//            stage the row of the node expected next.
+//   filter   one edge per thread from shared memory, one 32-byte bucket read of the visited hash (a single 256-bit
+//            load), compaction of the new ids.
+//   rows     groups of four rows, group g of the round to warp g % 4. A group is copied with cp.async (ids by one
+//            128-bit shared load, then the copies back to back), groups go through a ring of buffers with one
+//            cp.async group each, so copies of later groups are in flight while a group is evaluated. Distances:
+//            eight lanes per row, four rows per step (same summation order as every other kernel: chunk c on
+//            lane c mod 32 of group_fold<ACC, 32>), the scalar tail (sqrt, key, publish) once per eight steps with
+//            one row per lane.
+#pragma once
+#include "search.cuh"
+
+#define FAST_STAGE_PER_WARP 4096u
+
+// ---- visited hash: the bucket in one 256-bit load -------------------------------------------------------
+__device__ __forceinline__ bool hash_lookup256(const uint32_t *hash, uint32_t bucket_bits, uint32_t nid, BucketProbe &bp) {
+  const uint32_t bmask = (1u << bucket_bits) - 1u;
+  uint32_t b = (nid * 2654435761u) >> (32 - bucket_bits);
+  for (;;) {
+    uint32_t v[8];
+    asm volatile("ld.global.cg.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "l"(hash + (size_t)b * 8));
+    uint32_t free_slot = 8;
+#pragma unroll
+    for (int i = 7; i >= 0; i--) {
+      if (v[i] == nid) return true;   // visited
+      if (v[i] == 0u) free_slot = i;
+    }
+    if (free_slot < 8) {
+      bp.bucket = b;
+      bp.slot = free_slot;
+      return false;
+    }
+    b = (b + 1) & bmask;
+  }
+}
+
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int ACC, int CH>
+__global__ void __launch_bounds__(128, 8) search_fast_kernel(const SearchArgs a) {
+  constexpr uint32_t SROW = 128u * CH;                         // staging stride of a row
+  constexpr uint32_t GBYTES = 4u * SROW;                       // one group = four rows
+  constexpr int NB = (int)(FAST_STAGE_PER_WARP / GBYTES);      // ring depth per warp: 2, 4 or 8
+  constexpr uint32_t RPI = 4u / CH;                            // rows per copy instruction
+  constexpr uint32_t LPR = 8u * CH;                            // lanes per row in a copy instruction
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  __shared__ __align__(16) uint32_t s_cand_ids[SEARCH_CMAX + 4];
+  __shared__ uint64_t s_cand_keys[SEARCH_CMAX];
+  __shared__ __align__(16) uint32_t s_edges[2][SEARCH_HEAD];   // edge lists of the round / of the expected next node
+  __shared__ uint32_t s_cand_n, s_key_n, s_edge_n;
+  __shared__ int s_state;         // 0 run, 1 finished, 2 overflow
+  __shared__ uint32_t s_query;
+  __shared__ uint32_t s_take;     // edges to filter this round
+  __shared__ uint32_t s_buf;      // which half of s_edges holds them
+  __shared__ int s_seeding;
+  __shared__ float s_er;
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  const int warp = tid >> 5;
+
+  uint8_t *stage = smem_raw;                                                   // 4 x FAST_STAGE_PER_WARP
+  uint64_t *queue = reinterpret_cast<uint64_t *>(smem_raw + 4 * FAST_STAGE_PER_WARP);
+  uint32_t *hash = a.hash_slabs + ((size_t)blockIdx.x << a.hash_bits);
+  const uint32_t bucket_bits = a.hash_bits - 3;
+  const uint32_t take_head = a.edge_cap < SEARCH_HEAD ? a.edge_cap : SEARCH_HEAD;
+
+  // this lane's constant part of the row copies and reads
+  const uint32_t wstage_s = (uint32_t)__cvta_generic_to_shared(stage + (size_t)warp * FAST_STAGE_PER_WARP);
+  const uint32_t cp_row = (uint32_t)lane / LPR;                   // row inside one copy instruction
+  const uint32_t cp_chunk = (uint32_t)lane % LPR;
+  const uint32_t cp_dst = wstage_s + cp_row * SROW + cp_chunk * 16u;
+  const uint8_t *cp_src = a.objects + (size_t)cp_chunk * 16u;
+  const bool cp_ok = cp_chunk < a.chunks;                         // chunks past the row's end are zero-filled
+  const uint32_t rr = (uint32_t)lane >> 3;                        // row inside a distance step
+  const uint32_t rd = wstage_s + rr * SROW + ((uint32_t)lane & 7u) * 16u;
+
+  for (;;) {
+    // ---- next query (dynamic scheduling over a persistent grid)
+    if (tid == 0) {
+      uint32_t w = atomicAdd(a.work_counter, 1u);
+      s_query = w < a.nq ? w : 0xffffffffu;
+      s_state = 0;
+      s_cand_n = 0;
+      s_key_n = 0;
+      s_edge_n = 0;
+    }
+    __syncthreads();
+    const uint32_t q = s_query;
+    if (q == 0xffffffffu) break;
+    {
+      uint4 *h4 = reinterpret_cast<uint4 *>(hash);
+      for (uint32_t i = tid; i < (1u << a.hash_bits) / 4; i += 128) h4[i] = zero16();
+    }
+    const uint8_t *qrow = a.queries + (size_t)q * a.row_bytes;
+    uint4 q8[CH];   // lane (rr, j) holds query chunks j, j + 8, ...
+#pragma unroll
+    for (int m = 0; m < CH; m++) {
+      const uint32_t c = (lane & 7) + m * 8;
+      q8[m] = c < a.chunks ? ldg16(qrow + (size_t)c * 16) : zero16();
+    }
+    float qn = 0.f;
+    if (ACC == ACC_F_COS) {
+      // query norm^2 in the engine's summation order (lane c owns chunk c, xor butterfly)
+      const uint4 v = (uint32_t)lane < a.chunks ? ldg16(qrow + (size_t)lane * 16) : zero16();
+      float a0 = __uint_as_float(v.x), a1 = __uint_as_float(v.y), a2 = __uint_as_float(v.z), a3 = __uint_as_float(v.w);
+      qn = fmaf(a0, a0, qn);
+      qn = fmaf(a1, a1, qn);
+      qn = fmaf(a2, a2, qn);
+      qn = fmaf(a3, a3, qn);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) qn += __shfl_xor_sync(0xffffffffu, qn, o);
+    }
+    __syncthreads();   // the slab is zero before anybody probes it
+
+    // ---- control-warp state
+    uint64_t res = KEY_NONE;   // result list: lane i holds the i-th smallest key (k <= 32)
+    uint32_t res_n = 0;
+    Unchecked U;
+    U.front = KEY_NONE;
+    U.fn = 0;
+    U.qsize = 0;
+    U.T = KEY_NONE;
+    U.queue = queue;
+    U.cap = a.queue_cap;
+    float radius = a.radius;
+    float er = a.coef * radius;
+    uint32_t visited_n = 0, st_dist = 0, st_edge = 0, st_exp = 0;
+    bool seeding = true, seeds_taken = false, head_round = false;
+    uint32_t cand_n = 0;
+    uint32_t pref_id = 0, buf = 0;   // s_edges[buf ^ 1] holds the head row of node pref_id (0: nothing)
+
+    for (;;) {
+      // ================= control (warp 0) =================
+      if (warp == 0) {
+        bool overflow = false, finished = false;
+        if (head_round) st_edge += s_edge_n;
+        visited_n += cand_n;
+        st_dist += cand_n;
+        const uint32_t key_n = s_key_n;
+        if (key_n) {
+          for (uint32_t j0 = 0; j0 < key_n; j0 += 32) {
+            const uint64_t key = j0 + lane < key_n ? s_cand_keys[j0 + lane] : KEY_NONE;   // KEY_NONE compares false (NaN)
+            uint32_t m = __ballot_sync(0xffffffffu, key_dist(key) <= radius);
+            while (m) {
+              const int src = __ffs(m) - 1;
+              m &= m - 1;
+              const uint64_t kk = shfl_u64(key, src);
+              if (key_dist(kk) > radius) continue;   // the radius shrank meanwhile
+              const uint32_t pos = __popc(__ballot_sync(0xffffffffu, res < kk));
+              const uint64_t up = shfl_up_u64(res, 1);
+              if ((uint32_t)lane == pos) res = kk;
+              else if ((uint32_t)lane > pos) res = up;
+              if ((uint32_t)lane >= a.k) res = KEY_NONE;
+              if (res_n < a.k) res_n++;
+              if (!seeding && res_n >= a.k) radius = key_dist(shfl_u64(res, (int)a.k - 1));
+            }
+          }
+          if (!seeding) er = a.coef * radius;
+          for (uint32_t j0 = 0; j0 < key_n && !overflow; j0 += 32) {
+            const uint64_t key = j0 + lane < key_n ? s_cand_keys[j0 + lane] : KEY_NONE;
+            const bool acc = key != KEY_NONE && (seeding || key_dist(key) <= er);
+            const bool low = acc && key < U.T;
+            const uint32_t bm = __ballot_sync(0xffffffffu, acc && !low);
+            uint32_t fm = __ballot_sync(0xffffffffu, low);
+            const uint32_t cnt = __popc(bm);
+            if (cnt) {
+              if (U.qsize + cnt > U.cap) back_compact(U, er, lane);
+              if (U.qsize + cnt > U.cap) {
+                overflow = true;
+                break;
+              }
+              if (acc && !low) U.queue[U.qsize + __popc(bm & lanemask_lt())] = key;
+              U.qsize += cnt;
+              __syncwarp();
+            }
+            while (fm) {
+              const int src = __ffs(fm) - 1;
+              fm &= fm - 1;
+              if (!unchecked_insert(U, shfl_u64(key, src), er, lane, a.head, a.edge_cap)) {
+                overflow = true;
+                break;
+              }
+            }
+          }
+        }
+        cand_n = 0;
+        head_round = false;
+        uint32_t take = 0;
+        if (!overflow) {
+          if (!seeds_taken) {
+            // the seed list is the first round's edge list (setupDistances/setupSeeds, Graph.cpp:243-394)
+            seeds_taken = true;
+            take = a.n_seeds;
+            const uint32_t *sp = a.seeds + (size_t)q * a.n_seeds;
+            for (uint32_t i = lane; i < take; i += 32) s_edges[buf][i] = __ldg(sp + i);
+          } else {
+            if (seeding) {
+              // setupSeeds: radius from the seeds once k of them are within it (Graph.cpp:349-351)
+              seeding = false;
+              if (res_n >= a.k) radius = key_dist(shfl_u64(res, (int)a.k - 1));
+              er = a.coef * radius;
+            }
+            if (U.fn == 0 && U.qsize != 0 && key_dist(U.T) <= er) {
+              front_refill(U, er, lane);
+              const uint64_t mine = U.front;
+              if (mine != KEY_NONE) prefetch_head_row(a.head, key_id(mine), a.edge_cap);
+            }
+            const uint64_t best = shfl_u64(U.front, 0);
+            if (U.fn == 0 || !(key_dist(best) <= er)) {   // Graph.cpp:430-435
+              finished = true;
+            } else {
+              U.front = shfl_down_u64(U.front, 1);
+              if (lane == 31) U.front = KEY_NONE;
+              U.fn--;
+              const uint32_t t = key_id(best);
+              st_exp++;
+              take = take_head;
+              head_round = true;
+              buf ^= 1u;   // the half that may already hold t's row
+              const bool staged = t == pref_id;
+              if (!staged && (uint32_t)lane * 4u < take)
+                cp_async_row16(&s_edges[buf][lane * 4], a.head + (size_t)t * SEARCH_HEAD + lane * 4);
+              // the node most likely to be popped next is the front's new first key: stage its row in the other half
+              // while this round's rows are in flight
+              const uint64_t nxt = shfl_u64(U.front, 0);
+              pref_id = 0;
+              if (!staged) cp_async_commit_wait_all();
+              if (U.fn != 0 && key_dist(nxt) <= er) {
+                pref_id = key_id(nxt);
+                if ((uint32_t)lane * 4u < take)
+                  cp_async_row16(&s_edges[buf ^ 1u][lane * 4], a.head + (size_t)pref_id * SEARCH_HEAD + lane * 4);
+              }
+            }
+          }
+          if (!finished && visited_n + take > a.hash_limit) overflow = true;
+        }
+        if (lane == 0) {
+          s_cand_n = 0;
+          s_key_n = 0;
+          s_edge_n = 0;
+          s_take = take;
+          s_buf = buf;
+          s_seeding = seeding ? 1 : 0;
+          s_er = seeding ? __int_as_float(0x7f800000) : er;
+          if (overflow) s_state = 2;
+          else if (finished) s_state = 1;
+        }
+      }
+      __syncthreads();  // (A) the round is published
+      if (s_state != 0) break;
+
+      // ================= filter: one edge per thread =================
+      const bool seeding_round = s_seeding != 0;
+      uint32_t pend_id = 0;
+      BucketProbe bp;
+      bp.bucket = 0;
+      bp.slot = 0;
+      {
+        const uint32_t nid = (uint32_t)tid < s_take ? s_edges[s_buf][tid] : 0u;
+        const bool valid = nid != 0u && nid <= a.n;
+        bool isnew = false;
+        if (valid) {
+          isnew = !hash_lookup256(hash, bucket_bits, nid, bp);
+          if (isnew) {
+            // seed lists may repeat an id: insert at once so that the second copy is seen
+            if (seeding_round) isnew = hash_insert(hash, bucket_bits, nid, bp);
+            else pend_id = nid;
+          }
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, isnew);
+        const uint32_t mv = __ballot_sync(0xffffffffu, valid);
+        uint32_t base = 0;
+        if (lane == 0) {
+          if (m) base = atomicAdd(&s_cand_n, (uint32_t)__popc(m));
+          if (mv) atomicAdd(&s_edge_n, (uint32_t)__popc(mv));
+        }
+        base = __shfl_sync(0xffffffffu, base, 0) + __popc(m & lanemask_lt());
+        if (isnew) s_cand_ids[base] = nid;
+      }
+      __syncthreads();  // (B) the candidate list is complete
+      const uint32_t cn = s_cand_n;
+      if (warp == 0) cand_n = cn;
+
+      // ================= rows: copy and evaluate, group g of the round on warp g % 4 =================
+      {
+        const float er_pub = s_er;
+        const uint32_t ng = (cn + 3u) >> 2;                                  // groups of the round
+        const uint32_t ngw = (ng + 3u - (uint32_t)warp) >> 2;                // ... of this warp: g = warp, warp + 4, ...
+        // issue group t of this warp (candidates 4 * (4 t + warp) ..) into ring slot t % NB
+#define FAST_ISSUE(t)                                                                                   \
+  {                                                                                                     \
+    const uint32_t _t = (t);                                                                            \
+    if (_t < ngw) {                                                                                     \
+      const uint32_t _c0 = 4u * (4u * _t + (uint32_t)warp);                                             \
+      const uint32_t _dst = cp_dst + (_t % NB) * GBYTES;                                                \
+      if (CH == 4) {                                                                                    \
+        const uint4 _ids = *reinterpret_cast<const uint4 *>(&s_cand_ids[_c0]);                          \
+        const uint32_t _left = cn - _c0;                                                                \
+        cp_async_s16z(_dst, mad_wide_ptr(_ids.x, a.row_bytes, cp_src), cp_ok ? 16u : 0u);               \
+        cp_async_s16z(_dst + SROW, mad_wide_ptr(_ids.y, a.row_bytes, cp_src), (cp_ok && _left > 1u) ? 16u : 0u);      \
+        cp_async_s16z(_dst + 2 * SROW, mad_wide_ptr(_ids.z, a.row_bytes, cp_src), (cp_ok && _left > 2u) ? 16u : 0u);  \
+        cp_async_s16z(_dst + 3 * SROW, mad_wide_ptr(_ids.w, a.row_bytes, cp_src), (cp_ok && _left > 3u) ? 16u : 0u);  \
+      } else {                                                                                          \
+        uint32_t _id[CH];                                                                               \
+        _Pragma("unroll") for (int _i = 0; _i < CH; _i++) _id[_i] = s_cand_ids[_c0 + _i * RPI + cp_row];\
+        _Pragma("unroll") for (int _i = 0; _i < CH; _i++)                                               \
+          cp_async_s16z(_dst + _i * RPI * SROW, mad_wide_ptr(_id[_i], a.row_bytes, cp_src),             \
+                        (cp_ok && _c0 + _i * RPI + cp_row < cn) ? 16u : 0u);                            \
+      }                                                                                                 \
+    }                                                                                                   \
+    asm volatile("cp.async.commit_group;" ::: "memory");                                                \
+  }
+#pragma unroll
+        for (int b = 0; b < NB; b++) FAST_ISSUE((uint32_t)b)
+        if (pend_id) hash_insert(hash, bucket_bits, pend_id, bp);   // under the row copies in flight
+        float tot0 = 0.f, tot1 = 0.f;   // this lane's row of the current block of eight steps
+        uint32_t totu = 0;
+        for (uint32_t t = 0; t < ngw; t++) {
+          cp_async_wait_group<NB - 1>();
+          __syncwarp();
+          const uint32_t ra = rd + (t % NB) * GBYTES;
+          Sums p[CH];
+#pragma unroll
+          for (int m = 0; m < CH; m++) {
+            p[m] = zero_sums();
+            acc_chunk<ACC>(p[m], q8[m], lds16(ra + m * 128));
+          }
+          // chunks j, j + 8, j + 16, j + 24 of a row sit on lanes j, j + 8, ... of group_fold<ACC, 32>: the xor-16 and
+          // xor-8 levels of its butterfly are these local adds, the remaining three levels are shuffles
+          Sums tot = p[0];
+          if (ACC == ACC_U8_L2 || ACC == ACC_U8_HAM) {
+            if (CH == 2) tot.u = p[0].u + p[1].u;
+            if (CH == 4) tot.u = (p[0].u + p[2].u) + (p[1].u + p[3].u);
+            tot.u += __shfl_xor_sync(0xffffffffu, tot.u, 4);
+            tot.u += __shfl_xor_sync(0xffffffffu, tot.u, 2);
+            tot.u += __shfl_xor_sync(0xffffffffu, tot.u, 1);
+            if ((uint32_t)(lane & 7) == (t & 7u)) totu = tot.u;
+          } else {
+            if (CH == 2) tot.f0 = p[0].f0 + p[1].f0;
+            if (CH == 4) tot.f0 = (p[0].f0 + p[2].f0) + (p[1].f0 + p[3].f0);
+            tot.f0 += __shfl_xor_sync(0xffffffffu, tot.f0, 4);
+            tot.f0 += __shfl_xor_sync(0xffffffffu, tot.f0, 2);
+            tot.f0 += __shfl_xor_sync(0xffffffffu, tot.f0, 1);
+            if ((uint32_t)(lane & 7) == (t & 7u)) tot0 = tot.f0;
+            if (ACC == ACC_F_COS) {
+              if (CH == 2) tot.f1 = p[0].f1 + p[1].f1;
+              if (CH == 4) tot.f1 = (p[0].f1 + p[2].f1) + (p[1].f1 + p[3].f1);
+              tot.f1 += __shfl_xor_sync(0xffffffffu, tot.f1, 4);
+              tot.f1 += __shfl_xor_sync(0xffffffffu, tot.f1, 2);
+              tot.f1 += __shfl_xor_sync(0xffffffffu, tot.f1, 1);
+              if ((uint32_t)(lane & 7) == (t & 7u)) tot1 = tot.f1;
+            }
+          }
+          __syncwarp();
+          FAST_ISSUE(t + NB)
+          if ((t & 7u) == 7u || t + 1 == ngw) {
+            // the scalar tail for up to 32 rows at once: lane (rr, s) owns row rr of step (t & ~7) + s
+            const uint32_t ts = (t & ~7u) + ((uint32_t)lane & 7u);
+            const uint32_t j = 4u * (4u * ts + (uint32_t)warp) + rr;
+            const bool owner = ts <= t && j < cn;
+            float d = 0.f;
+            if (owner) {
+              Sums s;
+              s.f0 = tot0;
+              s.f1 = tot1;
+              s.u = totu;
+              d = finish_distance<ACC>(a.dtype, s, qn);
+            }
+            const bool pass = owner && d <= er_pub;
+            const uint32_t pm = __ballot_sync(0xffffffffu, pass);
+            if (pm) {
+              uint32_t base = 0;
+              if (lane == 0) base = atomicAdd(&s_key_n, (uint32_t)__popc(pm));
+              base = __shfl_sync(0xffffffffu, base, 0);
+              if (pass) s_cand_keys[base + __popc(pm & lanemask_lt())] = make_key(d, s_cand_ids[j]);
+            }
+          }
+        }
+        cp_async_wait_group<0>();   // also the staged head-table row of the expected next node (warp 0)
+#undef FAST_ISSUE
+      }
+      __syncthreads();  // (C) keys are published; buffers may be overwritten
+    }
+
+    // ---- write the outcome
+    const int state = s_state;
+    if (warp == 0) {
+      if (state == 1) {
+        if ((uint32_t)lane < a.k) {
+          const bool ok = (uint32_t)lane < res_n;
+          a.ids[(size_t)q * a.k + lane] = ok ? key_id(res) : 0u;
+          a.dists[(size_t)q * a.k + lane] = ok ? key_dist(res) : 0.f;
+        }
+        if (lane == 0) {
+          a.counts[q] = res_n;
+          if (a.stats) {
+            a.stats[(size_t)q * 3 + 0] = st_dist;
+            a.stats[(size_t)q * 3 + 1] = st_edge;
+            a.stats[(size_t)q * 3 + 2] = st_exp;
+          }
+        }
+      } else if (lane == 0) {
+        a.counts[q] = 0xffffffffu;
+        const uint32_t slot = atomicAdd(a.overflow_count, 1u);
+        a.overflow_list[slot] = q;
+      }
+    }
+    __syncthreads();  // s_query / s_state are rewritten by thread 0 next
+  }
+}
+
+// op == 0: launch, op == 1: occupancy query
+template <int ACC, int CH>
+static cudaError_t fast_one(const SearchArgs &a, unsigned grid, size_t smem, cudaStream_t stream, int op, int *blocks) {
+  cudaError_t e = cudaFuncSetAttribute(search_fast_kernel<ACC, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(search_fast_kernel<ACC, CH>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  if (e != cudaSuccess) return e;
+  if (op == 1) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, search_fast_kernel<ACC, CH>, 128, smem);
+  search_fast_kernel<ACC, CH><<<grid, 128, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+
+template <int ACC>
+cudaError_t search_fast_dispatch(const SearchArgs &a, int ch, unsigned grid, size_t smem, cudaStream_t stream, int op,
+                                 int *blocks) {
+  if (ch == 1) return fast_one<ACC, 1>(a, grid, smem, stream, op, blocks);
+  if (ch == 2) return fast_one<ACC, 2>(a, grid, smem, stream, op, blocks);
+  if (ch == 4) return fast_one<ACC, 4>(a, grid, smem, stream, op, blocks);
+  return cudaErrorInvalidValue;
+}

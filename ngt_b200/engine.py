@@ -141,6 +141,10 @@ class GpuIndex:
         if stage_bytes is not None:
             _lib.check(self._lib.ngtgpu_index_set_stage_bytes(self._h, int(stage_bytes)))
 
+    def set_fast_kernel(self, enabled=True):
+        """First traversal tier of the common case on the lean kernel (default) or on the general one."""
+        _lib.check(self._lib.ngtgpu_index_set_fast_kernel(self._h, int(bool(enabled))))
+
     def set_tensor_core(self, enabled=True):
         _lib.check(self._lib.ngtgpu_index_set_tensor_core(self._h, int(bool(enabled))))
 

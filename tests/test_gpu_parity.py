@@ -182,6 +182,74 @@ def test_seeded_against_port(eng, port, kind):
     ix.close()
 
 
+@pytest.mark.parametrize("kind", ["f32l2_128", "f32cos_100", "f32l2_48", "u8l2_128", "f32ncos_32", "u8l2_256"])
+def test_fast_kernel_equals_general_kernel(eng, port, kind):
+    """The lean first-tier kernel (search_fast.cuh) and the general one (search.cuh) restate the same loop
+    (Graph.cpp:398-495): ids, distance bits, counts and work counters are identical, for every row width class
+    (1, 2, 4 chunks per lane), with repeated seeds, small and large edge caps, k up to 32, and when queries
+    overflow the first tier. Integer-valued kinds are also compared with the C restatement of the reference."""
+    from ngt_b200 import synth
+    rng = np.random.default_rng(11)
+    name, dim = kind.split("_")
+    dim = int(dim)
+    n, nq = 20000, 300
+    base = synth.make("sift", n, 1)[:, :min(dim, 128)]
+    qs = synth.make("sift", nq, 2)[:, :min(dim, 128)]
+    if dim > 128:
+        base, qs = np.concatenate([base, base[:, ::-1]], 1), np.concatenate([qs, qs[:, ::-1]], 1)
+    normalize = False
+    if name == "f32l2":
+        otype, dtype, objs, q = po.FLOAT, po.L2, base, qs
+    elif name == "u8l2":
+        otype, dtype, objs, q = po.UINT8, po.L2, base.astype(np.uint8), qs
+    elif name == "f32cos":
+        otype, dtype = po.FLOAT, po.COSINE
+        objs, q = (base - 64.0).astype(np.float32) / 40.0, (qs - 64.0).astype(np.float32) / 40.0
+    else:
+        otype, dtype, normalize = po.FLOAT, po.NORMALIZED_COSINE, True
+        objs, q = (base - 64.0).astype(np.float32) / 40.0, (qs - 64.0).astype(np.float32) / 40.0
+    ix = eng.GpuIndex(otype, dtype, objs.shape[1])
+    ix.set_objects(objs, normalize=normalize)
+    gids, _, gcounts = ix.linear_search(objs.astype(np.float32), 25)
+    row_ptr, col = _knn_csr(gids, gcounts)
+    ix.set_graph(row_ptr, col)
+    seeds = np.stack([rng.choice(n, 10, replace=False) + 1 for _ in range(nq)]).astype(np.uint32)
+    seeds_rep = seeds.copy()
+    seeds_rep[::3, 5] = seeds_rep[::3, 1]   # a repeated seed is evaluated once by both kernels
+    exact = name in ("f32l2", "u8l2")
+    for eps, cap, kk in ((0.1, 16, 10), (0.3, 100, 10), (0.0, 24, 32), (0.2, 128, 1)):
+        out = {}
+        for fast in (True, False):
+            ix.set_fast_kernel(fast)
+            out[fast] = ix.search(q, kk, eps, edge_size=cap, seeds=seeds, with_stats=True)
+        what = "%s eps=%g cap=%d k=%d" % (kind, eps, cap, kk)
+        for a, b in zip(out[True], out[False]):
+            a, b = np.asarray(a), np.asarray(b)
+            assert (a.view(np.uint32) == b.view(np.uint32)).all(), what
+        rep = {}
+        for fast in (True, False):
+            ix.set_fast_kernel(fast)
+            rep[fast] = ix.search(q, kk, eps, edge_size=cap, seeds=seeds_rep, with_stats=True)
+        for a, b in zip(rep[True], rep[False]):
+            assert (np.asarray(a).view(np.uint32) == np.asarray(b).view(np.uint32)).all(), what + " repeated seeds"
+        if exact:
+            pobj, pq = po.pad_objects(objs, otype), po.pad_queries(q, otype)
+            rids, rdists, rcounts, rstats = port.graph_search(dtype, otype, pobj, row_ptr, col, pq, seeds, kk, eps,
+                                                              edge_size=cap)
+            assert_bit_exact(out[True][0], out[True][1], out[True][2], rids, rdists, rcounts, what=what)
+            assert (out[True][3].astype(np.uint64) == rstats).all(), what
+    # queries that outgrow the first tier leave the lean kernel for the general one's later tiers
+    ix.set_fast_kernel(False)
+    ref = ix.search(q, 10, 0.3, edge_size=100, seeds=seeds)
+    ix.set_fast_kernel(True)
+    ix.set_search_workspace(hash_bits=9, queue_cap=64)
+    got = ix.search(q, 10, 0.3, edge_size=100, seeds=seeds)
+    assert ix.last_overflows > 0
+    for a, b in zip(got, ref):
+        assert (np.asarray(a).view(np.uint32) == np.asarray(b).view(np.uint32)).all(), kind + " overflow"
+    ix.close()
+
+
 def test_edge_cases(eng, port):
     rng = np.random.default_rng(3)
     objs = rng.integers(0, 256, (50, 24)).astype(np.uint8)       # ragged dimension: padded to 32
