@@ -25,6 +25,18 @@
 #include "search.cuh"
 
 #define FAST_STAGE_PER_WARP 4096u
+#ifndef FAST_PF_ROWS
+#define FAST_PF_ROWS 1    // development switch: prefetch new rows towards L2 from the filter
+#endif
+#ifndef FAST_WARP_LISTS
+#define FAST_WARP_LISTS 1  // 1: every warp copies and evaluates the new ids of its own edges (no CTA barrier after the filter)
+#endif
+#ifndef FAST_EVICT_FIRST
+#define FAST_EVICT_FIRST 1  // row copies carry the L2 evict-first policy
+#endif
+#ifndef FAST_MIN_CTAS
+#define FAST_MIN_CTAS 8   // resident CTAs per SM the register allocation aims at
+#endif
 
 // ---- visited hash: the bucket in one 256-bit load -------------------------------------------------------
 __device__ __forceinline__ bool hash_lookup256(const uint32_t *hash, uint32_t bucket_bits, uint32_t nid, BucketProbe &bp) {
@@ -50,20 +62,33 @@ __device__ __forceinline__ bool hash_lookup256(const uint32_t *hash, uint32_t bu
   }
 }
 
+// 16-byte copy with zero fill (src_bytes 0 or 16) and an L2 eviction policy: rows are touched once per query and must
+// not push the visited-hash slabs and head-table rows out of L2
+__device__ __forceinline__ void cp_async_s16z_hint(uint32_t smem_addr, const void *gsrc, uint32_t src_bytes, uint64_t policy) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;" ::"r"(smem_addr), "l"(gsrc), "r"(src_bytes),
+               "l"(policy)
+               : "memory");
+}
+
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
 template <int ACC, int CH>
-__global__ void __launch_bounds__(128, 8) search_fast_kernel(const SearchArgs a) {
+__global__ void __launch_bounds__(128, FAST_MIN_CTAS) search_fast_kernel(const SearchArgs a) {
   constexpr uint32_t SROW = 128u * CH;                         // staging stride of a row
   constexpr uint32_t GBYTES = 4u * SROW;                       // one group = four rows
   constexpr int NB = (int)(FAST_STAGE_PER_WARP / GBYTES);      // ring depth per warp: 2, 4 or 8
   constexpr uint32_t RPI = 4u / CH;                            // rows per copy instruction
   constexpr uint32_t LPR = 8u * CH;                            // lanes per row in a copy instruction
   extern __shared__ __align__(128) uint8_t smem_raw[];
+#if FAST_WARP_LISTS
+  __shared__ __align__(16) uint32_t s_wids[4][SEARCH_CMAX / 4 + 4];   // new ids per warp
+  __shared__ uint32_t s_wcnt[4], s_wval[4];
+#else
   __shared__ __align__(16) uint32_t s_cand_ids[SEARCH_CMAX + 4];
+#endif
   __shared__ uint64_t s_cand_keys[SEARCH_CMAX];
   __shared__ __align__(16) uint32_t s_edges[2][SEARCH_HEAD];   // edge lists of the round / of the expected next node
   __shared__ uint32_t s_cand_n, s_key_n, s_edge_n;
@@ -93,6 +118,13 @@ __global__ void __launch_bounds__(128, 8) search_fast_kernel(const SearchArgs a)
   const bool cp_ok = cp_chunk < a.chunks;                         // chunks past the row's end are zero-filled
   const uint32_t rr = (uint32_t)lane >> 3;                        // row inside a distance step
   const uint32_t rd = wstage_s + rr * SROW + ((uint32_t)lane & 7u) * 16u;
+#if FAST_EVICT_FIRST
+  uint64_t row_policy;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(row_policy));
+#define FAST_ROWCP(dst, src, bytes) cp_async_s16z_hint(dst, src, bytes, row_policy)
+#else
+#define FAST_ROWCP(dst, src, bytes) cp_async_s16z(dst, src, bytes)
+#endif
 
   for (;;) {
     // ---- next query (dynamic scheduling over a persistent grid)
@@ -147,13 +179,22 @@ __global__ void __launch_bounds__(128, 8) search_fast_kernel(const SearchArgs a)
     uint32_t visited_n = 0, st_dist = 0, st_edge = 0, st_exp = 0;
     bool seeding = true, seeds_taken = false, head_round = false;
     uint32_t cand_n = 0;
+    bool rounds_done = false;
     uint32_t pref_id = 0, buf = 0;   // s_edges[buf ^ 1] holds the head row of node pref_id (0: nothing)
 
     for (;;) {
       // ================= control (warp 0) =================
       if (warp == 0) {
         bool overflow = false, finished = false;
+#if FAST_WARP_LISTS
+        if (rounds_done) {
+          cand_n = (s_wcnt[0] + s_wcnt[1]) + (s_wcnt[2] + s_wcnt[3]);
+          if (head_round) st_edge += (s_wval[0] + s_wval[1]) + (s_wval[2] + s_wval[3]);
+        }
+        rounds_done = true;
+#else
         if (head_round) st_edge += s_edge_n;
+#endif
         visited_n += cand_n;
         st_dist += cand_n;
         const uint32_t key_n = s_key_n;
@@ -272,11 +313,17 @@ __global__ void __launch_bounds__(128, 8) search_fast_kernel(const SearchArgs a)
       // ================= filter: one edge per thread =================
       const bool seeding_round = s_seeding != 0;
       uint32_t pend_id = 0;
+      uint32_t cn_w = 0;
       BucketProbe bp;
       bp.bucket = 0;
       bp.slot = 0;
       {
-        const uint32_t nid = (uint32_t)tid < s_take ? s_edges[s_buf][tid] : 0u;
+#if FAST_WARP_LISTS
+        const uint32_t e = 4u * (uint32_t)lane + (uint32_t)warp;   // edges dealt round-robin: the warps get equal shares
+#else
+        const uint32_t e = (uint32_t)tid;
+#endif
+        const uint32_t nid = e < s_take ? s_edges[s_buf][e] : 0u;
         const bool valid = nid != 0u && nid <= a.n;
         bool isnew = false;
         if (valid) {
@@ -285,10 +332,29 @@ __global__ void __launch_bounds__(128, 8) search_fast_kernel(const SearchArgs a)
             // seed lists may repeat an id: insert at once so that the second copy is seen
             if (seeding_round) isnew = hash_insert(hash, bucket_bits, nid, bp);
             else pend_id = nid;
+#if FAST_PF_ROWS
+            // the row is copied to shared memory a few hundred cycles from now: start it towards L2
+            if (isnew) {
+              const uint8_t *rp = a.objects + (size_t)nid * a.row_bytes;
+              for (uint32_t o = 0; o < a.row_bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + o));
+            }
+#endif
           }
         }
         const uint32_t m = __ballot_sync(0xffffffffu, isnew);
         const uint32_t mv = __ballot_sync(0xffffffffu, valid);
+#if FAST_WARP_LISTS
+        if (isnew) s_wids[warp][__popc(m & lanemask_lt())] = nid;
+        if (lane == 0) {
+          s_wcnt[warp] = (uint32_t)__popc(m);
+          s_wval[warp] = (uint32_t)__popc(mv);
+        }
+        __syncwarp();
+        cn_w = (uint32_t)__popc(m);
+      }
+      const uint32_t cn = cn_w;           // this warp's rows
+      const uint32_t *cand_ids = s_wids[warp];
+#else
         uint32_t base = 0;
         if (lane == 0) {
           if (m) base = atomicAdd(&s_cand_n, (uint32_t)__popc(m));
@@ -299,32 +365,40 @@ __global__ void __launch_bounds__(128, 8) search_fast_kernel(const SearchArgs a)
       }
       __syncthreads();  // (B) the candidate list is complete
       const uint32_t cn = s_cand_n;
+      const uint32_t *cand_ids = s_cand_ids;
       if (warp == 0) cand_n = cn;
+#endif
 
       // ================= rows: copy and evaluate, group g of the round on warp g % 4 =================
       {
         const float er_pub = s_er;
+#if FAST_WARP_LISTS
+        const uint32_t ngw = (cn + 3u) >> 2;                                 // groups of four rows of this warp
+#define FAST_GROUP_C0(t) (4u * (t))
+#else
         const uint32_t ng = (cn + 3u) >> 2;                                  // groups of the round
         const uint32_t ngw = (ng + 3u - (uint32_t)warp) >> 2;                // ... of this warp: g = warp, warp + 4, ...
+#define FAST_GROUP_C0(t) (4u * (4u * (t) + (uint32_t)warp))
+#endif
         // issue group t of this warp (candidates 4 * (4 t + warp) ..) into ring slot t % NB
 #define FAST_ISSUE(t)                                                                                   \
   {                                                                                                     \
     const uint32_t _t = (t);                                                                            \
     if (_t < ngw) {                                                                                     \
-      const uint32_t _c0 = 4u * (4u * _t + (uint32_t)warp);                                             \
+      const uint32_t _c0 = FAST_GROUP_C0(_t);                                                           \
       const uint32_t _dst = cp_dst + (_t % NB) * GBYTES;                                                \
       if (CH == 4) {                                                                                    \
-        const uint4 _ids = *reinterpret_cast<const uint4 *>(&s_cand_ids[_c0]);                          \
+        const uint4 _ids = *reinterpret_cast<const uint4 *>(&cand_ids[_c0]);                            \
         const uint32_t _left = cn - _c0;                                                                \
-        cp_async_s16z(_dst, mad_wide_ptr(_ids.x, a.row_bytes, cp_src), cp_ok ? 16u : 0u);               \
-        cp_async_s16z(_dst + SROW, mad_wide_ptr(_ids.y, a.row_bytes, cp_src), (cp_ok && _left > 1u) ? 16u : 0u);      \
-        cp_async_s16z(_dst + 2 * SROW, mad_wide_ptr(_ids.z, a.row_bytes, cp_src), (cp_ok && _left > 2u) ? 16u : 0u);  \
-        cp_async_s16z(_dst + 3 * SROW, mad_wide_ptr(_ids.w, a.row_bytes, cp_src), (cp_ok && _left > 3u) ? 16u : 0u);  \
+        FAST_ROWCP(_dst, mad_wide_ptr(_ids.x, a.row_bytes, cp_src), cp_ok ? 16u : 0u);               \
+        FAST_ROWCP(_dst + SROW, mad_wide_ptr(_ids.y, a.row_bytes, cp_src), (cp_ok && _left > 1u) ? 16u : 0u);      \
+        FAST_ROWCP(_dst + 2 * SROW, mad_wide_ptr(_ids.z, a.row_bytes, cp_src), (cp_ok && _left > 2u) ? 16u : 0u);  \
+        FAST_ROWCP(_dst + 3 * SROW, mad_wide_ptr(_ids.w, a.row_bytes, cp_src), (cp_ok && _left > 3u) ? 16u : 0u);  \
       } else {                                                                                          \
         uint32_t _id[CH];                                                                               \
-        _Pragma("unroll") for (int _i = 0; _i < CH; _i++) _id[_i] = s_cand_ids[_c0 + _i * RPI + cp_row];\
+        _Pragma("unroll") for (int _i = 0; _i < CH; _i++) _id[_i] = cand_ids[_c0 + _i * RPI + cp_row];  \
         _Pragma("unroll") for (int _i = 0; _i < CH; _i++)                                               \
-          cp_async_s16z(_dst + _i * RPI * SROW, mad_wide_ptr(_id[_i], a.row_bytes, cp_src),             \
+          FAST_ROWCP(_dst + _i * RPI * SROW, mad_wide_ptr(_id[_i], a.row_bytes, cp_src),             \
                         (cp_ok && _c0 + _i * RPI + cp_row < cn) ? 16u : 0u);                            \
       }                                                                                                 \
     }                                                                                                   \
@@ -376,7 +450,7 @@ __global__ void __launch_bounds__(128, 8) search_fast_kernel(const SearchArgs a)
           if ((t & 7u) == 7u || t + 1 == ngw) {
             // the scalar tail for up to 32 rows at once: lane (rr, s) owns row rr of step (t & ~7) + s
             const uint32_t ts = (t & ~7u) + ((uint32_t)lane & 7u);
-            const uint32_t j = 4u * (4u * ts + (uint32_t)warp) + rr;
+            const uint32_t j = FAST_GROUP_C0(ts) + rr;
             const bool owner = ts <= t && j < cn;
             float d = 0.f;
             if (owner) {
@@ -392,12 +466,13 @@ __global__ void __launch_bounds__(128, 8) search_fast_kernel(const SearchArgs a)
               uint32_t base = 0;
               if (lane == 0) base = atomicAdd(&s_key_n, (uint32_t)__popc(pm));
               base = __shfl_sync(0xffffffffu, base, 0);
-              if (pass) s_cand_keys[base + __popc(pm & lanemask_lt())] = make_key(d, s_cand_ids[j]);
+              if (pass) s_cand_keys[base + __popc(pm & lanemask_lt())] = make_key(d, cand_ids[j]);
             }
           }
         }
         cp_async_wait_group<0>();   // also the staged head-table row of the expected next node (warp 0)
 #undef FAST_ISSUE
+#undef FAST_GROUP_C0
       }
       __syncthreads();  // (C) keys are published; buffers may be overwritten
     }
