@@ -25,15 +25,6 @@
 #include "search.cuh"
 
 #define FAST_STAGE_PER_WARP 4096u
-#ifndef FAST_PF_ROWS
-#define FAST_PF_ROWS 1    // development switch: prefetch new rows towards L2 from the filter
-#endif
-#ifndef FAST_WARP_LISTS
-#define FAST_WARP_LISTS 1  // 1: every warp copies and evaluates the new ids of its own edges (no CTA barrier after the filter)
-#endif
-#ifndef FAST_EVICT_FIRST
-#define FAST_EVICT_FIRST 1  // row copies carry the L2 evict-first policy
-#endif
 #ifndef FAST_MIN_CTAS
 #define FAST_MIN_CTAS 8   // resident CTAs per SM the register allocation aims at
 #endif
@@ -83,21 +74,22 @@ __global__ void __launch_bounds__(128, FAST_MIN_CTAS) search_fast_kernel(const S
   constexpr uint32_t RPI = 4u / CH;                            // rows per copy instruction
   constexpr uint32_t LPR = 8u * CH;                            // lanes per row in a copy instruction
   extern __shared__ __align__(128) uint8_t smem_raw[];
-#if FAST_WARP_LISTS
   __shared__ __align__(16) uint32_t s_wids[4][SEARCH_CMAX / 4 + 4];   // new ids per warp
   __shared__ uint32_t s_wcnt[4], s_wval[4];
-#else
-  __shared__ __align__(16) uint32_t s_cand_ids[SEARCH_CMAX + 4];
-#endif
   __shared__ uint64_t s_cand_keys[SEARCH_CMAX];
   __shared__ __align__(16) uint32_t s_edges[2][SEARCH_HEAD];   // edge lists of the round / of the expected next node
-  __shared__ uint32_t s_cand_n, s_key_n, s_edge_n;
+  __shared__ uint32_t s_key_n;
   __shared__ int s_state;         // 0 run, 1 finished, 2 overflow
   __shared__ uint32_t s_query;
   __shared__ uint32_t s_take;     // edges to filter this round
   __shared__ uint32_t s_buf;      // which half of s_edges holds them
   __shared__ int s_seeding;
   __shared__ float s_er;
+  // control-warp state between rounds: it lives here while the rows are copied and evaluated, so that the row loop
+  // has the register file to itself (lane constants stay in registers instead of being recomputed every step)
+  __shared__ uint64_t s_res[32], s_front[32];
+  __shared__ uint64_t s_T;
+  __shared__ uint32_t s_ctl[12];   // fn, qsize, res_n, visited_n, st_dist, st_edge, st_exp, pref_id, buf, flags, radius, er
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -118,13 +110,9 @@ __global__ void __launch_bounds__(128, FAST_MIN_CTAS) search_fast_kernel(const S
   const bool cp_ok = cp_chunk < a.chunks;                         // chunks past the row's end are zero-filled
   const uint32_t rr = (uint32_t)lane >> 3;                        // row inside a distance step
   const uint32_t rd = wstage_s + rr * SROW + ((uint32_t)lane & 7u) * 16u;
-#if FAST_EVICT_FIRST
   uint64_t row_policy;
   asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(row_policy));
 #define FAST_ROWCP(dst, src, bytes) cp_async_s16z_hint(dst, src, bytes, row_policy)
-#else
-#define FAST_ROWCP(dst, src, bytes) cp_async_s16z(dst, src, bytes)
-#endif
 
   for (;;) {
     // ---- next query (dynamic scheduling over a persistent grid)
@@ -132,9 +120,7 @@ __global__ void __launch_bounds__(128, FAST_MIN_CTAS) search_fast_kernel(const S
       uint32_t w = atomicAdd(a.work_counter, 1u);
       s_query = w < a.nq ? w : 0xffffffffu;
       s_state = 0;
-      s_cand_n = 0;
       s_key_n = 0;
-      s_edge_n = 0;
     }
     __syncthreads();
     const uint32_t q = s_query;
@@ -164,37 +150,41 @@ __global__ void __launch_bounds__(128, FAST_MIN_CTAS) search_fast_kernel(const S
     }
     __syncthreads();   // the slab is zero before anybody probes it
 
-    // ---- control-warp state
-    uint64_t res = KEY_NONE;   // result list: lane i holds the i-th smallest key (k <= 32)
-    uint32_t res_n = 0;
-    Unchecked U;
-    U.front = KEY_NONE;
-    U.fn = 0;
-    U.qsize = 0;
-    U.T = KEY_NONE;
-    U.queue = queue;
-    U.cap = a.queue_cap;
-    float radius = a.radius;
-    float er = a.coef * radius;
-    uint32_t visited_n = 0, st_dist = 0, st_edge = 0, st_exp = 0;
-    bool seeding = true, seeds_taken = false, head_round = false;
-    uint32_t cand_n = 0;
-    bool rounds_done = false;
-    uint32_t pref_id = 0, buf = 0;   // s_edges[buf ^ 1] holds the head row of node pref_id (0: nothing)
+    // ---- control-warp state (kept in shared memory between rounds)
+    if (warp == 0) {
+      s_res[lane] = KEY_NONE;     // result list: lane i holds the i-th smallest key (k <= 32)
+      s_front[lane] = KEY_NONE;
+      if (lane == 0) s_T = KEY_NONE;
+      if (lane < 10) s_ctl[lane] = lane == 9 ? 1u : 0u;   // flags: bit 0 seeding, bit 1 seeds taken, bit 2 head round, bit 3 a round ran
+      if (lane == 10) s_ctl[10] = __float_as_uint(a.radius);
+      if (lane == 11) s_ctl[11] = __float_as_uint(a.coef * a.radius);
+      __syncwarp();
+    }
 
     for (;;) {
       // ================= control (warp 0) =================
       if (warp == 0) {
+        uint64_t res = s_res[lane];
+        Unchecked U;
+        U.front = s_front[lane];
+        U.T = s_T;
+        U.fn = s_ctl[0];
+        U.qsize = s_ctl[1];
+        U.queue = queue;
+        U.cap = a.queue_cap;
+        uint32_t res_n = s_ctl[2], visited_n = s_ctl[3], st_dist = s_ctl[4], st_edge = s_ctl[5], st_exp = s_ctl[6];
+        uint32_t pref_id = s_ctl[7], buf = s_ctl[8];   // s_edges[buf ^ 1] holds the head row of node pref_id (0: nothing)
+        const uint32_t flags = s_ctl[9];
+        bool seeding = (flags & 1u) != 0, seeds_taken = (flags & 2u) != 0, head_round = (flags & 4u) != 0;
+        const bool rounds_done = (flags & 8u) != 0;
+        float radius = __uint_as_float(s_ctl[10]);
+        float er = __uint_as_float(s_ctl[11]);
+        uint32_t cand_n = 0;
         bool overflow = false, finished = false;
-#if FAST_WARP_LISTS
         if (rounds_done) {
           cand_n = (s_wcnt[0] + s_wcnt[1]) + (s_wcnt[2] + s_wcnt[3]);
           if (head_round) st_edge += (s_wval[0] + s_wval[1]) + (s_wval[2] + s_wval[3]);
         }
-        rounds_done = true;
-#else
-        if (head_round) st_edge += s_edge_n;
-#endif
         visited_n += cand_n;
         st_dist += cand_n;
         const uint32_t key_n = s_key_n;
@@ -244,7 +234,6 @@ __global__ void __launch_bounds__(128, FAST_MIN_CTAS) search_fast_kernel(const S
             }
           }
         }
-        cand_n = 0;
         head_round = false;
         uint32_t take = 0;
         if (!overflow) {
@@ -295,10 +284,23 @@ __global__ void __launch_bounds__(128, FAST_MIN_CTAS) search_fast_kernel(const S
           }
           if (!finished && visited_n + take > a.hash_limit) overflow = true;
         }
+        s_res[lane] = res;
+        s_front[lane] = U.front;
         if (lane == 0) {
-          s_cand_n = 0;
+          s_T = U.T;
+          s_ctl[0] = U.fn;
+          s_ctl[1] = U.qsize;
+          s_ctl[2] = res_n;
+          s_ctl[3] = visited_n;
+          s_ctl[4] = st_dist;
+          s_ctl[5] = st_edge;
+          s_ctl[6] = st_exp;
+          s_ctl[7] = pref_id;
+          s_ctl[8] = buf;
+          s_ctl[9] = (seeding ? 1u : 0u) | (seeds_taken ? 2u : 0u) | (head_round ? 4u : 0u) | 8u;
+          s_ctl[10] = __float_as_uint(radius);
+          s_ctl[11] = __float_as_uint(er);
           s_key_n = 0;
-          s_edge_n = 0;
           s_take = take;
           s_buf = buf;
           s_seeding = seeding ? 1 : 0;
@@ -318,11 +320,7 @@ __global__ void __launch_bounds__(128, FAST_MIN_CTAS) search_fast_kernel(const S
       bp.bucket = 0;
       bp.slot = 0;
       {
-#if FAST_WARP_LISTS
         const uint32_t e = 4u * (uint32_t)lane + (uint32_t)warp;   // edges dealt round-robin: the warps get equal shares
-#else
-        const uint32_t e = (uint32_t)tid;
-#endif
         const uint32_t nid = e < s_take ? s_edges[s_buf][e] : 0u;
         const bool valid = nid != 0u && nid <= a.n;
         bool isnew = false;
@@ -332,18 +330,15 @@ __global__ void __launch_bounds__(128, FAST_MIN_CTAS) search_fast_kernel(const S
             // seed lists may repeat an id: insert at once so that the second copy is seen
             if (seeding_round) isnew = hash_insert(hash, bucket_bits, nid, bp);
             else pend_id = nid;
-#if FAST_PF_ROWS
             // the row is copied to shared memory a few hundred cycles from now: start it towards L2
             if (isnew) {
               const uint8_t *rp = a.objects + (size_t)nid * a.row_bytes;
               for (uint32_t o = 0; o < a.row_bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + o));
             }
-#endif
           }
         }
         const uint32_t m = __ballot_sync(0xffffffffu, isnew);
         const uint32_t mv = __ballot_sync(0xffffffffu, valid);
-#if FAST_WARP_LISTS
         if (isnew) s_wids[warp][__popc(m & lanemask_lt())] = nid;
         if (lane == 0) {
           s_wcnt[warp] = (uint32_t)__popc(m);
@@ -354,32 +349,12 @@ __global__ void __launch_bounds__(128, FAST_MIN_CTAS) search_fast_kernel(const S
       }
       const uint32_t cn = cn_w;           // this warp's rows
       const uint32_t *cand_ids = s_wids[warp];
-#else
-        uint32_t base = 0;
-        if (lane == 0) {
-          if (m) base = atomicAdd(&s_cand_n, (uint32_t)__popc(m));
-          if (mv) atomicAdd(&s_edge_n, (uint32_t)__popc(mv));
-        }
-        base = __shfl_sync(0xffffffffu, base, 0) + __popc(m & lanemask_lt());
-        if (isnew) s_cand_ids[base] = nid;
-      }
-      __syncthreads();  // (B) the candidate list is complete
-      const uint32_t cn = s_cand_n;
-      const uint32_t *cand_ids = s_cand_ids;
-      if (warp == 0) cand_n = cn;
-#endif
 
       // ================= rows: copy and evaluate, group g of the round on warp g % 4 =================
       {
         const float er_pub = s_er;
-#if FAST_WARP_LISTS
         const uint32_t ngw = (cn + 3u) >> 2;                                 // groups of four rows of this warp
 #define FAST_GROUP_C0(t) (4u * (t))
-#else
-        const uint32_t ng = (cn + 3u) >> 2;                                  // groups of the round
-        const uint32_t ngw = (ng + 3u - (uint32_t)warp) >> 2;                // ... of this warp: g = warp, warp + 4, ...
-#define FAST_GROUP_C0(t) (4u * (4u * (t) + (uint32_t)warp))
-#endif
         // issue group t of this warp (candidates 4 * (4 t + warp) ..) into ring slot t % NB
 #define FAST_ISSUE(t)                                                                                   \
   {                                                                                                     \
@@ -464,7 +439,11 @@ __global__ void __launch_bounds__(128, FAST_MIN_CTAS) search_fast_kernel(const S
             const uint32_t pm = __ballot_sync(0xffffffffu, pass);
             if (pm) {
               uint32_t base = 0;
-              if (lane == 0) base = atomicAdd(&s_key_n, (uint32_t)__popc(pm));
+              if (lane == 0)
+                asm volatile("atom.shared.add.u32 %0, [%1], %2;"
+                             : "=r"(base)
+                             : "r"((uint32_t)__cvta_generic_to_shared(&s_key_n)), "r"((uint32_t)__popc(pm))
+                             : "memory");
               base = __shfl_sync(0xffffffffu, base, 0);
               if (pass) s_cand_keys[base + __popc(pm & lanemask_lt())] = make_key(d, cand_ids[j]);
             }
@@ -481,6 +460,8 @@ __global__ void __launch_bounds__(128, FAST_MIN_CTAS) search_fast_kernel(const S
     const int state = s_state;
     if (warp == 0) {
       if (state == 1) {
+        const uint64_t res = s_res[lane];
+        const uint32_t res_n = s_ctl[2];
         if ((uint32_t)lane < a.k) {
           const bool ok = (uint32_t)lane < res_n;
           a.ids[(size_t)q * a.k + lane] = ok ? key_id(res) : 0u;
@@ -489,9 +470,9 @@ __global__ void __launch_bounds__(128, FAST_MIN_CTAS) search_fast_kernel(const S
         if (lane == 0) {
           a.counts[q] = res_n;
           if (a.stats) {
-            a.stats[(size_t)q * 3 + 0] = st_dist;
-            a.stats[(size_t)q * 3 + 1] = st_edge;
-            a.stats[(size_t)q * 3 + 2] = st_exp;
+            a.stats[(size_t)q * 3 + 0] = s_ctl[4];
+            a.stats[(size_t)q * 3 + 1] = s_ctl[5];
+            a.stats[(size_t)q * 3 + 2] = s_ctl[6];
           }
         }
       } else if (lane == 0) {

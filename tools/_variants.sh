@@ -1,2 +1,2 @@
-python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "fast_kernel or seeded" 2>&1 | tail -2
-for w in base w1 w2 w3; do so=$PWD/ngt_b200/libngtgpu_$w.so; [ $w = base ] && so=$PWD/ngt_b200/libngtgpu.so; NGTGPU_SO=$so python bench.py --no-cpu --epsilon 0.08 --queue-cap 384 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$w', d['value'], d['roofline']['kernel_ms'], d['roofline']['frac'], d['config']['recall_at_10'], d['config']['overflow_queries_per_step'])"; done
+python -m pytest tests/test_gpu_parity.py -m gpu -x -q 2>&1 | tail -2
+python bench.py --no-cpu --epsilon 0.08 --queue-cap 384 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('base', d['value'], d['e2e']['value'], d['roofline']['kernel_ms'], d['roofline']['frac'], d['config']['recall_at_10'], d['config']['overflow_queries_per_step'])"
