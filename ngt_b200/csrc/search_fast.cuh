@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(128, FAST_MIN_CTAS) search_fast_kernel(const S
   const uint32_t cp_chunk = (uint32_t)lane % LPR;
   const uint32_t cp_dst = wstage_s + cp_row * SROW + cp_chunk * 16u;
   const uint8_t *cp_src = a.objects + (size_t)cp_chunk * 16u;
-  const bool cp_ok = cp_chunk < a.chunks;                         // chunks past the row's end are zero-filled
+  const uint32_t cp_size = cp_chunk < a.chunks ? 16u : 0u;        // chunks past the row's end are zero-filled
   const uint32_t rr = (uint32_t)lane >> 3;                        // row inside a distance step
   const uint32_t rd = wstage_s + rr * SROW + ((uint32_t)lane & 7u) * 16u;
   uint64_t row_policy;
@@ -333,13 +333,18 @@ __global__ void __launch_bounds__(128, FAST_MIN_CTAS) search_fast_kernel(const S
             // the row is copied to shared memory a few hundred cycles from now: start it towards L2
             if (isnew) {
               const uint8_t *rp = a.objects + (size_t)nid * a.row_bytes;
-              for (uint32_t o = 0; o < a.row_bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + o));
+#pragma unroll
+              for (int o = 0; o < CH; o++)
+                if (o == 0 || (uint32_t)o * 128u < a.row_bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + o * 128));
             }
           }
         }
         const uint32_t m = __ballot_sync(0xffffffffu, isnew);
         const uint32_t mv = __ballot_sync(0xffffffffu, valid);
         if (isnew) s_wids[warp][__popc(m & lanemask_lt())] = nid;
+        // the last group of four is filled up with row 0 (the all-zero dummy object, an L2 hit): its copies need no
+        // predicates and its distances are dropped
+        if (lane < 3) s_wids[warp][__popc(m) + lane] = 0u;
         if (lane == 0) {
           s_wcnt[warp] = (uint32_t)__popc(m);
           s_wval[warp] = (uint32_t)__popc(mv);
@@ -364,17 +369,15 @@ __global__ void __launch_bounds__(128, FAST_MIN_CTAS) search_fast_kernel(const S
       const uint32_t _dst = cp_dst + (_t % NB) * GBYTES;                                                \
       if (CH == 4) {                                                                                    \
         const uint4 _ids = *reinterpret_cast<const uint4 *>(&cand_ids[_c0]);                            \
-        const uint32_t _left = cn - _c0;                                                                \
-        FAST_ROWCP(_dst, mad_wide_ptr(_ids.x, a.row_bytes, cp_src), cp_ok ? 16u : 0u);               \
-        FAST_ROWCP(_dst + SROW, mad_wide_ptr(_ids.y, a.row_bytes, cp_src), (cp_ok && _left > 1u) ? 16u : 0u);      \
-        FAST_ROWCP(_dst + 2 * SROW, mad_wide_ptr(_ids.z, a.row_bytes, cp_src), (cp_ok && _left > 2u) ? 16u : 0u);  \
-        FAST_ROWCP(_dst + 3 * SROW, mad_wide_ptr(_ids.w, a.row_bytes, cp_src), (cp_ok && _left > 3u) ? 16u : 0u);  \
+        FAST_ROWCP(_dst, mad_wide_ptr(_ids.x, a.row_bytes, cp_src), cp_size);                           \
+        FAST_ROWCP(_dst + SROW, mad_wide_ptr(_ids.y, a.row_bytes, cp_src), cp_size);                    \
+        FAST_ROWCP(_dst + 2 * SROW, mad_wide_ptr(_ids.z, a.row_bytes, cp_src), cp_size);                \
+        FAST_ROWCP(_dst + 3 * SROW, mad_wide_ptr(_ids.w, a.row_bytes, cp_src), cp_size);                \
       } else {                                                                                          \
         uint32_t _id[CH];                                                                               \
         _Pragma("unroll") for (int _i = 0; _i < CH; _i++) _id[_i] = cand_ids[_c0 + _i * RPI + cp_row];  \
         _Pragma("unroll") for (int _i = 0; _i < CH; _i++)                                               \
-          FAST_ROWCP(_dst + _i * RPI * SROW, mad_wide_ptr(_id[_i], a.row_bytes, cp_src),             \
-                        (cp_ok && _c0 + _i * RPI + cp_row < cn) ? 16u : 0u);                            \
+          FAST_ROWCP(_dst + _i * RPI * SROW, mad_wide_ptr(_id[_i], a.row_bytes, cp_src), cp_size);      \
       }                                                                                                 \
     }                                                                                                   \
     asm volatile("cp.async.commit_group;" ::: "memory");                                                \
