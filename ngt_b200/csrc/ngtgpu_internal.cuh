@@ -182,21 +182,62 @@ __device__ __forceinline__ uint64_t shfl_up_u64(uint64_t v, int d) {
 }
 
 // ---- per-chunk (16 B) accumulation -----------------------------------------------------------------
+// Float kinds keep TWO accumulators per sum, one for the even and one for the odd elements of the chunks a lane
+// owns (the packed f32x2 pipes of sm_100 compute both halves in one FADD2 / FFMA2); a lane's total is their sum.
 struct Sums {
-  float f0;   // F_L2: sum sq ; F_DOT/F_COS: dot
-  float f1;   // F_COS: row norm^2
-  uint32_t u; // integer kinds
+  float f0, f0h;   // F_L2: sum sq ; F_DOT/F_COS: dot          (even elements, odd elements)
+  float f1, f1h;   // F_COS: row norm^2
+  uint32_t u;      // integer kinds
 };
 __device__ __forceinline__ Sums zero_sums() {
   Sums s;
-  s.f0 = 0.f;
-  s.f1 = 0.f;
+  s.f0 = s.f0h = 0.f;
+  s.f1 = s.f1h = 0.f;
   s.u = 0u;
   return s;
 }
 
 template <int ACC>
 __device__ __forceinline__ void acc_chunk(Sums &s, const uint4 &q, const uint4 &r) {
+  if (ACC == ACC_F_L2) {
+    float d0 = __uint_as_float(q.x) - __uint_as_float(r.x);
+    float d1 = __uint_as_float(q.y) - __uint_as_float(r.y);
+    float d2 = __uint_as_float(q.z) - __uint_as_float(r.z);
+    float d3 = __uint_as_float(q.w) - __uint_as_float(r.w);
+    s.f0 = fmaf(d0, d0, s.f0);
+    s.f0h = fmaf(d1, d1, s.f0h);
+    s.f0 = fmaf(d2, d2, s.f0);
+    s.f0h = fmaf(d3, d3, s.f0h);
+  } else if (ACC == ACC_F_DOT) {
+    s.f0 = fmaf(__uint_as_float(q.x), __uint_as_float(r.x), s.f0);
+    s.f0h = fmaf(__uint_as_float(q.y), __uint_as_float(r.y), s.f0h);
+    s.f0 = fmaf(__uint_as_float(q.z), __uint_as_float(r.z), s.f0);
+    s.f0h = fmaf(__uint_as_float(q.w), __uint_as_float(r.w), s.f0h);
+  } else if (ACC == ACC_F_COS) {
+    float r0 = __uint_as_float(r.x), r1 = __uint_as_float(r.y), r2 = __uint_as_float(r.z), r3 = __uint_as_float(r.w);
+    s.f0 = fmaf(__uint_as_float(q.x), r0, s.f0);
+    s.f0h = fmaf(__uint_as_float(q.y), r1, s.f0h);
+    s.f0 = fmaf(__uint_as_float(q.z), r2, s.f0);
+    s.f0h = fmaf(__uint_as_float(q.w), r3, s.f0h);
+    s.f1 = fmaf(r0, r0, s.f1);
+    s.f1h = fmaf(r1, r1, s.f1h);
+    s.f1 = fmaf(r2, r2, s.f1);
+    s.f1h = fmaf(r3, r3, s.f1h);
+  } else if (ACC == ACC_U8_L2) {
+    uint32_t d;
+    d = __vabsdiffu4(q.x, r.x); s.u = __dp4a(d, d, s.u);
+    d = __vabsdiffu4(q.y, r.y); s.u = __dp4a(d, d, s.u);
+    d = __vabsdiffu4(q.z, r.z); s.u = __dp4a(d, d, s.u);
+    d = __vabsdiffu4(q.w, r.w); s.u = __dp4a(d, d, s.u);
+  } else {
+    s.u += __popc(q.x ^ r.x) + __popc(q.y ^ r.y) + __popc(q.z ^ r.z) + __popc(q.w ^ r.w);
+  }
+}
+
+// One accumulator per sum, element after element: for values that only FILTER (the tile pass of the exhaustive scan,
+// which re-evaluates survivors in the engine's order) -- half the registers of the two-accumulator form.
+template <int ACC>
+__device__ __forceinline__ void acc_chunk_seq(Sums &s, const uint4 &q, const uint4 &r) {
   if (ACC == ACC_F_L2) {
     float d0 = __uint_as_float(q.x) - __uint_as_float(r.x);
     float d1 = __uint_as_float(q.y) - __uint_as_float(r.y);
@@ -221,25 +262,73 @@ __device__ __forceinline__ void acc_chunk(Sums &s, const uint4 &q, const uint4 &
     s.f1 = fmaf(r1, r1, s.f1);
     s.f1 = fmaf(r2, r2, s.f1);
     s.f1 = fmaf(r3, r3, s.f1);
-  } else if (ACC == ACC_U8_L2) {
-    uint32_t d;
-    d = __vabsdiffu4(q.x, r.x); s.u = __dp4a(d, d, s.u);
-    d = __vabsdiffu4(q.y, r.y); s.u = __dp4a(d, d, s.u);
-    d = __vabsdiffu4(q.z, r.z); s.u = __dp4a(d, d, s.u);
-    d = __vabsdiffu4(q.w, r.w); s.u = __dp4a(d, d, s.u);
   } else {
-    s.u += __popc(q.x ^ r.x) + __popc(q.y ^ r.y) + __popc(q.z ^ r.z) + __popc(q.w ^ r.w);
+    acc_chunk<ACC>(s, q, r);
   }
+}
+
+// The same sums with the packed pipes: one FADD2 + one FFMA2 per pair of elements (identical bits: every half is
+// the IEEE operation of the scalar version).
+__device__ __forceinline__ uint64_t pack_f2(uint32_t lo, uint32_t hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f2(uint64_t v, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t sub_f2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t fma_f2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+template <int ACC>
+__device__ __forceinline__ void acc_chunk_packed(Sums &s, const uint4 &q, const uint4 &r) {
+  if (ACC == ACC_F_L2 || ACC == ACC_F_DOT || ACC == ACC_F_COS) {
+    const uint64_t q01 = pack_f2(q.x, q.y), q23 = pack_f2(q.z, q.w);
+    const uint64_t r01 = pack_f2(r.x, r.y), r23 = pack_f2(r.z, r.w);
+    uint64_t a0 = pack_f2(__float_as_uint(s.f0), __float_as_uint(s.f0h));
+    if (ACC == ACC_F_L2) {
+      const uint64_t d01 = sub_f2(q01, r01), d23 = sub_f2(q23, r23);
+      a0 = fma_f2(d01, d01, a0);
+      a0 = fma_f2(d23, d23, a0);
+    } else {
+      a0 = fma_f2(q01, r01, a0);
+      a0 = fma_f2(q23, r23, a0);
+    }
+    unpack_f2(a0, s.f0, s.f0h);
+    if (ACC == ACC_F_COS) {
+      uint64_t a1 = pack_f2(__float_as_uint(s.f1), __float_as_uint(s.f1h));
+      a1 = fma_f2(r01, r01, a1);
+      a1 = fma_f2(r23, r23, a1);
+      unpack_f2(a1, s.f1, s.f1h);
+    }
+  } else {
+    acc_chunk<ACC>(s, q, r);
+  }
+}
+
+// a lane's total of the chunks it owns
+template <int ACC>
+__device__ __forceinline__ void lane_total(Sums &s) {
+  if (ACC == ACC_F_L2 || ACC == ACC_F_DOT || ACC == ACC_F_COS) s.f0 += s.f0h;
+  if (ACC == ACC_F_COS) s.f1 += s.f1h;
 }
 
 // The engine's ONE summation order, used by every kernel that reports a distance, so the same
 // (query, object) pair gives the same float bits whichever path computed it:
-//   chunk c (16 B) is accumulated, element by element with fma, by lane (c mod G) of a group of
-//   G = min(32, pow2ceil(chunks)) lanes, chunks in increasing order; the G lane sums are then folded
-//   by an xor butterfly in float (as the reference folds its SIMD lanes in float,
-//   PrimitiveComparator.h:153-193). Integer kinds are exact whatever the order.
+//   chunk c (16 B) is accumulated with fma by lane (c mod G) of a group of G = min(32, pow2ceil(chunks)) lanes,
+//   chunks in increasing order, even and odd elements in separate accumulators that are added at the end
+//   (lane_total); the G lane totals are then folded by an xor butterfly in float (as the reference folds its
+//   SIMD lanes in float, PrimitiveComparator.h:153-193). Integer kinds are exact whatever the order.
 template <int ACC, int G>
 __device__ __forceinline__ void group_fold(Sums &s) {
+  lane_total<ACC>(s);
   if (ACC == ACC_U8_L2 || ACC == ACC_U8_HAM) {
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) s.u += __shfl_xor_sync(0xffffffffu, s.u, o);

@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_tile_kernel(const ScanAr
 #pragma unroll
         for (int i = 0; i < 4; i++)
 #pragma unroll
-          for (int j = 0; j < 4; j++) acc_chunk<ACC>(acc[i][j], qv[i], rv[j]);
+          for (int j = 0; j < 4; j++) acc_chunk_seq<ACC>(acc[i][j], qv[i], rv[j]);
       }
     }
     if (kc == nkc - 1) {

@@ -53,6 +53,9 @@ static cudaError_t dispatch(int acc, const SearchArgs &a, const SearchLaunch &l,
 }
 
 #define BIG_TIER_QUEUE (1u << 18)
+#ifndef FAST_MIN_CHUNKS
+#define FAST_MIN_CHUNKS 5   // shorter rows stay on the general kernel (many rows per copy instruction)
+#endif
 
 int ngtgpu_traverse(ngtgpu_index *ix, const uint8_t *d_queries, uint32_t nq, const ngtgpu_search_params *params,
                     const uint32_t *d_seeds, uint32_t n_seeds, uint32_t *d_ids, float *d_dists, uint32_t *d_counts,
@@ -144,9 +147,9 @@ int ngtgpu_traverse(ngtgpu_index *ix, const uint8_t *d_queries, uint32_t nq, con
     a.query_list = t == 0 ? nullptr : lists[(t - 1) & 1];
     a.query_list_count = t == 0 ? nullptr : ws + 2 * (t - 1) + 1;
     size_t smem = extra + (size_t)a.queue_cap * 8;
-    // the first tier of the common case runs the lean kernel: rows of 5..32 chunks, head-table adjacency, set semantics
+    // the on-chip tiers of the common case run the lean kernel: rows of 5..32 chunks, head-table adjacency, set semantics
     // (epsilon >= 0), results in one warp's registers, a seed list that is one round
-    const bool fast = t == 0 && ix->fast_kernel && ix->chunks >= 5 && ix->chunks <= 32 && cap <= NGTGPU_HEAD_WIDTH &&
+    const bool fast = ix->fast_kernel && ix->chunks >= FAST_MIN_CHUNKS && ix->chunks <= 32 && cap <= NGTGPU_HEAD_WIDTH &&
                       a.coef >= 1.0f && k <= 32 && n_seeds <= SEARCH_CMAX;
     const int fast_ch = ix->chunks <= 8 ? 1 : ix->chunks <= 16 ? 2 : 4;
     if (fast) smem = 4 * 4096 + (size_t)a.queue_cap * 8;
@@ -158,7 +161,7 @@ int ngtgpu_traverse(ngtgpu_index *ix, const uint8_t *d_queries, uint32_t nq, con
                          : dispatch(ix->acc_kind, a, l, 1, &blocks);
     if (e != cudaSuccess) NGTGPU_FAIL(NGTGPU_ERR_CUDA, std::string("search occupancy query: ") + cudaGetErrorString(e));
     if (blocks < 1) blocks = 1;
-    if (t > 0 && blocks > 2) blocks = 2;   // the overflow tier serves few queries: keep its slabs small
+    if (t > 0 && blocks > (fast ? 4 : 2)) blocks = fast ? 4 : 2;   // the overflow tier serves few queries: keep its slabs small
     uint64_t grid = (uint64_t)blocks * ix->sm_count;
     if (grid > nq) grid = nq;
     if (grid == 0) return NGTGPU_OK;

@@ -37,6 +37,10 @@
 // share an SM instead of 3. A query that outgrows its slab or queue is appended to an overflow list and
 // re-run by a later launch with a larger slab or, finally (WS == 1), with an exact bitmap and a large
 // queue in HBM (the reference's own structures, Graph.h:751-799).
+//
+// The first tier of the common case (rows of 80..512 bytes, edge cap <= 128, epsilon >= 0, size <= 32) runs the leaner
+// search_fast_kernel (search_fast.cuh) instead; the unchecked-set helpers below (sorted register front + unsorted
+// back) are its queue.
 #pragma once
 #include <cfloat>
 
@@ -46,9 +50,6 @@
 #define SEARCH_WARPS 4        // warps per query (1, 2 or 4)
 #endif
 #define SEARCH_THREADS (SEARCH_WARPS * 32)
-#ifndef SEARCH_PF_ROWS
-#define SEARCH_PF_ROWS 0      // development switch: 1/2 = prefetch new rows towards L2 from the filter (per line / bulk)
-#endif
 #ifndef SEARCH_MIN_CTAS
 #define SEARCH_MIN_CTAS (32 / SEARCH_WARPS)   // 64 registers per thread at 4 warps; nine CTAs (56 registers) spill and measured slower
 #endif
@@ -403,25 +404,6 @@ __device__ __forceinline__ bool bitmap_visit(uint32_t *bitmap, uint32_t nid) {
   return (old & bit) == 0;
 }
 
-// A finished distance goes to the round's key list. aligned: slot j of the list belongs to candidate j (seed rounds and
-// negative epsilon keep the reference's element order); otherwise keys beyond the exploration radius the round started
-// with are dropped here -- the radius only shrinks, so the merge would drop them anyway -- and the rest is appended in
-// arrival order (the merge has set semantics). Called by all lanes of a warp; `owner` lanes carry a distance.
-__device__ __forceinline__ void publish_key(bool aligned, bool owner, uint32_t j, float d, const uint32_t *cand_ids,
-                                            float er_pub, uint64_t *keys, uint32_t *key_n, int lane) {
-  if (aligned) {
-    if (owner) keys[j] = make_key(d, cand_ids[j]);
-    return;
-  }
-  const bool pass = owner && d <= er_pub;
-  const uint32_t pm = __ballot_sync(0xffffffffu, pass);
-  if (pm == 0) return;
-  uint32_t base = 0;
-  if (lane == 0) base = atomicAdd(key_n, (uint32_t)__popc(pm));
-  base = __shfl_sync(0xffffffffu, base, 0);
-  if (pass) keys[base + __popc(pm & lanemask_lt())] = make_key(d, cand_ids[j]);
-}
-
 template <int ACC, int G, int CPL, int WS>
 __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel(const SearchArgs a) {
   constexpr int R = 32 / G;                 // rows per warp instruction (G < 32)
@@ -440,10 +422,6 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
   __shared__ int s_seeding;       // the round reads a seed list
   __shared__ uint32_t s_take;     // edges to filter this round
   __shared__ const uint32_t *s_src;  // where they are (head row, CSR slice or seed list)
-  __shared__ int s_src_shared;    // s_src points into s_pref (shared memory)
-  __shared__ uint32_t s_key_n;    // keys published by the distance phase (rounds that drop keys beyond s_er)
-  __shared__ float s_er;          // exploration radius at the start of the round (FLT_MAX: keep every key, in order)
-  __shared__ __align__(16) uint32_t s_pref[2][SEARCH_HEAD];   // head-table row of the node expected to be popped next
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -487,7 +465,6 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
       s_query = w < total ? (a.query_list ? a.query_list[w] : w) : 0xffffffffu;
       s_state = 0;
       s_cand_n = 0;
-      s_key_n = 0;
       s_edge_n = 0;
     }
     __syncthreads();
@@ -565,13 +542,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
     res.smem = s_results;
     res.k = a.k;
     res.n = 0;
-    Unchecked U;
-    U.front = KEY_NONE;
-    U.fn = 0;
-    U.qsize = 0;
-    U.T = KEY_NONE;
-    U.queue = queue;
-    U.cap = a.queue_cap;
+    uint32_t qsize = 0;           // unchecked entries
     float radius = a.radius;      // sc.radius
     float er = a.coef * radius;   // explorationRadius (Graph.cpp:420)
     uint32_t visited_n = 0;
@@ -582,12 +553,10 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
     bool seeding = true;
     bool head_round = false;      // the round in flight read a head-table row (its edge count comes from s_edge_n)
     uint32_t cand_n = 0;
-    uint32_t pref_id = 0;         // node whose head-table row is staged in s_pref[pref_buf] (0: none)
-    uint32_t pref_buf = 0;
-    const uint32_t *head_pf = use_head ? a.head : nullptr;
     // per-phase cycle counters of warp 0: compiled in only with -DSEARCH_PHASE_PROFILE (they cost ten registers)
 #ifdef SEARCH_PHASE_PROFILE
     uint32_t pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    uint64_t spec_second = KEY_NONE, spec_third = KEY_NONE;
     long long tp = a.prof ? clock64() : 0;
 #define PROF_MARK(i)                     \
   if (a.prof) {                          \
@@ -607,14 +576,11 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
         if (head_round) st_edge += s_edge_n;
         visited_n += cand_n;
         st_dist += cand_n;
-        // keys of the previous round: all of them in candidate order (seed rounds, negative epsilon), else only
-        // those within the exploration radius the round started with, in no particular order
-        const uint32_t key_n = (ordered || seeding) ? cand_n : s_key_n;
-        if (key_n) {
+        if (cand_n) {
           if (!ordered && !seeding) {
             // set semantics: results first, then everything within the final explorationRadius
-            for (uint32_t j0 = 0; j0 < key_n; j0 += 32) {
-              uint64_t key = j0 + lane < key_n ? s_cand_keys[j0 + lane] : KEY_NONE;
+            for (uint32_t j0 = 0; j0 < cand_n; j0 += 32) {
+              uint64_t key = j0 + lane < cand_n ? s_cand_keys[j0 + lane] : KEY_NONE;
               uint32_t m = __ballot_sync(0xffffffffu, key != KEY_NONE && key_dist(key) <= radius);
               while (m) {
                 int src = __ffs(m) - 1;
@@ -626,38 +592,45 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
               }
             }
             er = a.coef * radius;
-            for (uint32_t j0 = 0; j0 < key_n && !overflow; j0 += 32) {
-              uint64_t key = j0 + lane < key_n ? s_cand_keys[j0 + lane] : KEY_NONE;
-              const bool acc = key != KEY_NONE && key_dist(key) <= er;
-              // keys not below the back's minimum go to the back in one piece (T can only decrease afterwards)
-              const bool low = acc && key < U.T;
-              const uint32_t bm = __ballot_sync(0xffffffffu, acc && !low);
-              uint32_t fm = __ballot_sync(0xffffffffu, low);
-              const uint32_t cnt = __popc(bm);
-              if (cnt) {
-                if (U.qsize + cnt > U.cap) back_compact(U, er, lane);
-                if (U.qsize + cnt > U.cap) {
-                  overflow = true;
-                  break;
+            for (uint32_t j0 = 0; j0 < cand_n && !overflow; j0 += 32) {
+              uint64_t key = j0 + lane < cand_n ? s_cand_keys[j0 + lane] : KEY_NONE;
+              bool acc = key != KEY_NONE && key_dist(key) <= er;
+              uint32_t m = __ballot_sync(0xffffffffu, acc);
+              uint32_t cnt = __popc(m);
+              if (qsize + cnt > a.queue_cap) {
+                // compact: entries beyond explorationRadius can never be expanded
+                uint32_t w = 0;
+                for (uint32_t i0 = 0; i0 < qsize; i0 += 32) {
+                  uint64_t v = i0 + lane < qsize ? queue[i0 + lane] : KEY_NONE;
+                  bool keep = v != KEY_NONE && key_dist(v) <= er;
+                  uint32_t km = __ballot_sync(0xffffffffu, keep);
+                  __syncwarp();
+                  if (keep) queue[w + __popc(km & lanemask_lt())] = v;
+                  __syncwarp();
+                  w += __popc(km);
                 }
-                if (acc && !low) U.queue[U.qsize + __popc(bm & lanemask_lt())] = key;
-                U.qsize += cnt;
-                __syncwarp();
+                qsize = w;
               }
-              while (fm) {
-                int src = __ffs(fm) - 1;
-                fm &= fm - 1;
-                if (!unchecked_insert(U, shfl_u64(key, src), er, lane, head_pf, a.edge_cap)) {
-                  overflow = true;
-                  break;
+              if (qsize + cnt > a.queue_cap) {
+                overflow = true;
+                break;
+              }
+              if (acc) {
+                queue[qsize + __popc(m & lanemask_lt())] = key;
+                if (use_head) {
+                  // its edges will be wanted when it is popped: pull that row of the head table towards L2 now
+                  const uint32_t *hp = a.head + (size_t)key_id(key) * SEARCH_HEAD;
+                  const uint32_t lines = ((a.edge_cap < SEARCH_HEAD ? a.edge_cap : SEARCH_HEAD) + 31) / 32;
+                  for (uint32_t l = 0; l < lines; l++) asm volatile("prefetch.global.L2 [%0];" ::"l"(hp + l * 32));
                 }
               }
+              qsize += cnt;
             }
             __syncwarp();
           } else {
             // the reference's order: seeds (all go to unchecked, Graph.cpp:352-366) and coef < 1
-            for (uint32_t j0 = 0; j0 < key_n && !overflow; j0 += 32) {
-              uint64_t key = j0 + lane < key_n ? s_cand_keys[j0 + lane] : KEY_NONE;
+            for (uint32_t j0 = 0; j0 < cand_n && !overflow; j0 += 32) {
+              uint64_t key = j0 + lane < cand_n ? s_cand_keys[j0 + lane] : KEY_NONE;
               uint32_t m = __ballot_sync(0xffffffffu, key != KEY_NONE);
               while (m) {
                 int src = __ffs(m) - 1;
@@ -665,10 +638,12 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
                 uint64_t kk = shfl_u64(key, src);
                 float d = key_dist(kk);
                 if (!seeding && d > er) continue;
-                if (!unchecked_insert(U, kk, er, lane, head_pf, a.edge_cap)) {
+                if (qsize >= a.queue_cap) {
                   overflow = true;
                   break;
                 }
+                if (lane == 0) queue[qsize] = kk;
+                qsize++;
                 if (d <= radius) {
                   result_insert(res, kk, lane);
                   if (!seeding && res.n >= res.k) {
@@ -686,7 +661,6 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
         PROF_MARK(0)
         // ---- next edges: the rest of the current list, or pop the smallest unchecked node
         bool finished = false;
-        bool src_shared = false;
         uint32_t take = 0;
         const uint32_t *src_ptr = nullptr;
         while (!overflow && !finished && take == 0) {
@@ -703,50 +677,63 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
             if (res.n >= res.k) radius = key_dist(result_kth(res));
             er = a.coef * radius;
           }
-          if (U.fn == 0 && U.qsize != 0 && key_dist(U.T) <= er) {
-            front_refill(U, er, lane);
-            if (head_pf) {
-              const uint64_t mine = U.front;
-              if (mine != KEY_NONE) prefetch_head_row(head_pf, key_id(mine), a.edge_cap);
+          uint64_t best = KEY_NONE;
+          uint32_t bi = 0;
+          for (uint32_t i = lane; i < qsize; i += 32) {
+            uint64_t v = queue[i];
+            if (v < best) {
+              best = v;
+              bi = i;
             }
-            PROF_MARK(2)
           }
-          const uint64_t best = shfl_u64(U.front, 0);
-          if (U.fn == 0 || key_dist(best) > er) {  // Graph.cpp:430-435
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            uint64_t ob = shfl_xor_u64(best, o);
+            uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ob < best) {
+              best = ob;
+              bi = oi;
+            }
+          }
+          if (best == KEY_NONE || key_dist(best) > er) {  // Graph.cpp:430-435
             finished = true;
             break;
           }
-          U.front = shfl_down_u64(U.front, 1);
-          if (lane == 31) U.front = KEY_NONE;
-          U.fn--;
+          if (lane == 0) queue[bi] = queue[qsize - 1];
+          qsize--;
+          __syncwarp();
           const uint32_t t = key_id(best);
           st_exp++;
+#ifdef SEARCH_PHASE_PROFILE
+          // development probe: how often is the popped node the one that was second best at the previous pop?
+          // (slot 4 of the phase record: it was the second best; slot 2: it was the second or third best)
+          if (a.prof) {
+            if (best == spec_second) pf[4]++;
+            if (best == spec_second || best == spec_third) pf[2]++;
+            uint64_t s2 = KEY_NONE, s3 = KEY_NONE;   // the two smallest remaining keys
+            for (uint32_t i = lane; i < qsize; i += 32) {
+              uint64_t v = queue[i];
+              if (v < s2) { s3 = s2; s2 = v; } else if (v < s3) s3 = v;
+            }
+            for (int o = 16; o > 0; o >>= 1) {
+              uint64_t o2 = shfl_xor_u64(s2, o), o3 = shfl_xor_u64(s3, o);
+              uint64_t lo = s2 < o2 ? s2 : o2, hi = s2 < o2 ? o2 : s2;
+              uint64_t m3 = s3 < o3 ? s3 : o3;
+              s2 = lo;
+              s3 = hi < m3 ? hi : m3;
+            }
+            spec_second = s2;
+            spec_third = s3;
+          }
+#endif
           PROF_MARK(1)
           if (use_head) {
             // the whole (capped) list is one row of the head table; empty slots are zero
             take = a.edge_cap < SEARCH_HEAD ? a.edge_cap : SEARCH_HEAD;
-            if (t == pref_id) {
-              src_ptr = s_pref[pref_buf];
-              src_shared = true;
-#ifdef SEARCH_PHASE_PROFILE
-              if (a.prof) pf[4]++;
-#endif
-            } else {
-              src_ptr = a.head + (size_t)t * SEARCH_HEAD;
-            }
+            src_ptr = a.head + (size_t)t * SEARCH_HEAD;
             head_round = true;
             cur_deg = 0;
             cur_pos = 0;
-            // the node most likely to be popped next is the front's new first key: stage its row of the head table in
-            // shared memory while this round's rows are in flight (waited for with warp 0's own row copies)
-            const uint64_t nxt = shfl_u64(U.front, 0);
-            pref_id = 0;
-            if (U.fn != 0 && key_dist(nxt) <= er) {
-              pref_buf ^= 1u;
-              pref_id = key_id(nxt);
-              if ((uint32_t)lane * 4u < take)
-                cp_async_row16(&s_pref[pref_buf][lane * 4], a.head + (size_t)pref_id * SEARCH_HEAD + lane * 4);
-            }
           } else {
             // longer lists (edgeSize > 64): walk the CSR slice (Graph.cpp:438 caps it)
             uint64_t b = 0, e = 0;
@@ -765,13 +752,10 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
         if (WS == 0 && !overflow && !finished && visited_n + take > a.hash_limit) overflow = true;
         if (lane == 0) {
           s_cand_n = 0;
-          s_key_n = 0;
           s_edge_n = 0;
           s_take = take;
           s_src = src_ptr;
-          s_src_shared = src_shared ? 1 : 0;
           s_seeding = seeding ? 1 : 0;
-          s_er = (ordered || seeding) ? FLT_MAX : er;
           if (overflow) s_state = 2;
           else if (finished) s_state = 1;
         }
@@ -794,7 +778,6 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
       {
         const uint32_t take = s_take;
         const uint32_t *src = s_src;
-        const bool src_sh = s_src_shared != 0;   // the row was staged in shared memory by the previous round
         const bool immediate = seeding_round;   // seed lists may repeat an id: insert at once so the second copy is seen
         if (!ordered) {
           // thread t looks at edges t, t + THREADS, ...: all edge loads first, then all bucket lookups
@@ -802,7 +785,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
 #pragma unroll
           for (int i = 0; i < SEARCH_EPT; i++) {
             const uint32_t e = (uint32_t)tid + i * SEARCH_THREADS;
-            nid[i] = e < take ? (src_sh ? src[e] : __ldg(src + e)) : 0u;
+            nid[i] = e < take ? __ldg(src + e) : 0u;
           }
           uint32_t new_mask = 0, n_valid = 0;
 #pragma unroll
@@ -818,18 +801,6 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
                   pending_mask |= 1u << i;
                   pending_id[i] = nid[i];
                 }
-#if SEARCH_PF_ROWS == 1
-                if (isnew) {
-                  // the row will be copied to shared memory a few hundred cycles from now: start it towards L2
-                  const uint8_t *rp = a.objects + (size_t)nid[i] * a.row_bytes;
-                  for (uint32_t o = 0; o < a.row_bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + o));
-                }
-#elif SEARCH_PF_ROWS == 2
-                if (isnew) {
-                  const uint8_t *rp = a.objects + (size_t)nid[i] * a.row_bytes;
-                  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(rp), "r"(a.row_bytes) : "memory");
-                }
-#endif
               } else {
                 isnew = bitmap_visit(bitmap, nid[i]);
               }
@@ -874,7 +845,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
           // element order kept: warp 0 walks the edges 32 at a time
           uint32_t cn = 0, en = 0;
           for (uint32_t e0 = 0; e0 < take; e0 += 32) {
-            uint32_t nid = e0 + lane < take ? (src_sh ? src[e0 + lane] : __ldg(src + e0 + lane)) : 0u;
+            uint32_t nid = e0 + lane < take ? __ldg(src + e0 + lane) : 0u;
             const bool valid = nid != 0u && nid <= a.n;
             bool isnew = false;
             if (valid) {
@@ -916,94 +887,6 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
         const uint32_t srow_bytes = (G == 32 && CPL > 0) ? SROW : a.row_bytes;
         uint8_t *wstage = stage + (size_t)warp * wrows * srow_bytes;
         const uint32_t wstage_s = (uint32_t)__cvta_generic_to_shared(wstage) + (uint32_t)lane * 16u;
-        const bool aligned = ordered || seeding_round;
-        const float er_pub = s_er;
-        if (ROW8) {
-          // Rows of <= 512 bytes, pipelined. The warp's staging slice is two half-buffers of HR rows; its rows (slice
-          // `warp` of every pass of 4 * wrows candidates) are taken as a sequence of groups of HR rows, group g in
-          // half-buffer g & 1, each group one cp.async group: while the distances of group g are evaluated the copies
-          // of group g + 1 are in flight, and group g + 2 is issued as soon as g's buffer is free. Copies are
-          // branch-free: a row past the list's end, or a chunk past the row's end, has source size 0 (nothing is read,
-          // the slot is zero-filled).
-          const uint32_t HR = wrows >> 1;
-          const uint8_t *lane_src = a.objects + (size_t)lane * 16;
-          const uint32_t csize = (uint32_t)lane < a.chunks ? 16u : 0u;
-          const uint32_t rr = (uint32_t)lane >> 3;
-          const uint32_t rd0 = wstage_s - (uint32_t)lane * 16u + rr * SROW + ((uint32_t)lane & 7u) * 16u;
-#define ROW8_GBASE(g) (((g) >> 1) * (SEARCH_WARPS * wrows) + (uint32_t)warp * wrows + ((g) & 1u) * HR)
-#define ROW8_ISSUE(g)                                                                              \
-  {                                                                                                \
-    const uint32_t _b = ROW8_GBASE(g);                                                             \
-    if (_b < cn) {                                                                                 \
-      const uint32_t _left = cn - _b;                                                              \
-      const uint32_t _d0 = wstage_s + ((g) & 1u) * HR * SROW;                                      \
-      for (uint32_t _i0 = 0; _i0 < HR; _i0 += 4) {                                                 \
-        _Pragma("unroll") for (int _i = 0; _i < 4; _i++) {                                         \
-          const bool _in = _i0 + _i < _left;                                                       \
-          const uint32_t _id = _in ? s_cand_ids[_b + _i0 + _i] : 0u;                               \
-          cp_async_s16z(_d0 + (_i0 + _i) * SROW, mad_wide_ptr(_id, a.row_bytes, lane_src), _in ? csize : 0u); \
-        }                                                                                          \
-      }                                                                                            \
-    }                                                                                              \
-    asm volatile("cp.async.commit_group;" ::: "memory");                                           \
-  }
-          ROW8_ISSUE(0u)
-          ROW8_ISSUE(1u)
-          if (WS == 0 && pending_mask) {
-            // the insertions of this thread's new ids, overlapped with the row copies in flight
-#pragma unroll
-            for (int i = 0; i < SEARCH_EPT; i++)
-              if (pending_mask & (1u << i)) hash_insert(hash, a.hash_bits - 3, pending_id[i], bp[i]);
-            pending_mask = 0;
-          }
-          for (uint32_t g = 0;; g++) {
-            const uint32_t gb = ROW8_GBASE(g);
-            if (gb >= cn) break;
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-            __syncwarp();
-            const uint32_t nr = cn - gb < HR ? cn - gb : HR;
-            const uint32_t ra0 = rd0 + (g & 1u) * HR * SROW;
-            // four rows per step, eight lanes each. Slots past the group's last row hold stale rows of earlier rounds
-            // (or zeros): they are read like the others and their result is dropped; chunks past the row's end read
-            // the zeroed tail against zero query chunks.
-            for (uint32_t r0 = 0; r0 < nr; r0 += 4) {
-              Sums p[4];
-#pragma unroll
-              for (int m = 0; m < 4; m++) {
-                p[m] = zero_sums();
-                acc_chunk<ACC>(p[m], q8[m], lds16(ra0 + r0 * SROW + m * 128));
-              }
-              Sums tot = zero_sums();
-              if (ACC == ACC_U8_L2 || ACC == ACC_U8_HAM) {
-                tot.u = (p[0].u + p[2].u) + (p[1].u + p[3].u);
-                tot.u += __shfl_xor_sync(0xffffffffu, tot.u, 4);
-                tot.u += __shfl_xor_sync(0xffffffffu, tot.u, 2);
-                tot.u += __shfl_xor_sync(0xffffffffu, tot.u, 1);
-              } else {
-                tot.f0 = (p[0].f0 + p[2].f0) + (p[1].f0 + p[3].f0);
-                tot.f0 += __shfl_xor_sync(0xffffffffu, tot.f0, 4);
-                tot.f0 += __shfl_xor_sync(0xffffffffu, tot.f0, 2);
-                tot.f0 += __shfl_xor_sync(0xffffffffu, tot.f0, 1);
-                if (ACC == ACC_F_COS) {
-                  tot.f1 = (p[0].f1 + p[2].f1) + (p[1].f1 + p[3].f1);
-                  tot.f1 += __shfl_xor_sync(0xffffffffu, tot.f1, 4);
-                  tot.f1 += __shfl_xor_sync(0xffffffffu, tot.f1, 2);
-                  tot.f1 += __shfl_xor_sync(0xffffffffu, tot.f1, 1);
-                }
-              }
-              const uint32_t r = r0 + rr;
-              const bool owner = (lane & 7) == 0 && r < nr;
-              float d = 0.f;
-              if (owner) d = finish_distance<ACC>(a.dtype, tot, qn);
-              publish_key(aligned, owner, gb + r, d, s_cand_ids, er_pub, s_cand_keys, &s_key_n, lane);
-            }
-            __syncwarp();
-            ROW8_ISSUE(g + 2u)
-          }
-          asm volatile("cp.async.wait_group 0;" ::: "memory");
-#undef ROW8_ISSUE
-#undef ROW8_GBASE
-        } else
         for (uint32_t j0 = warp * wrows; j0 < cn; j0 += SEARCH_WARPS * wrows) {
           const uint32_t nr = cn - j0 < wrows ? cn - j0 : wrows;
           if (G == 32 && CPL > 0) {
@@ -1059,7 +942,43 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
           }
           cp_async_commit_wait_all();
           __syncwarp();
-          if (CPL > 0 && CPL <= 2 && G == 32) {
+          if (ROW8) {
+            // four rows per step, eight lanes each. Slots past the slice's last row hold stale rows of earlier
+            // rounds (or the initial zeros): they are read like the others and their result is dropped; chunks
+            // past the row's end read the zeroed tail against zero query chunks.
+            const uint32_t rr = (uint32_t)lane >> 3;
+            const uint32_t ra0 = wstage_s - (uint32_t)lane * 16u + rr * SROW + ((uint32_t)lane & 7u) * 16u;
+            for (uint32_t r0 = 0; r0 < nr; r0 += 4) {
+              Sums p[4];
+#pragma unroll
+              for (int m = 0; m < 4; m++) {
+                p[m] = zero_sums();
+                acc_chunk<ACC>(p[m], q8[m], lds16(ra0 + r0 * SROW + m * 128));
+                lane_total<ACC>(p[m]);
+              }
+              Sums tot = zero_sums();
+              if (ACC == ACC_U8_L2 || ACC == ACC_U8_HAM) {
+                tot.u = (p[0].u + p[2].u) + (p[1].u + p[3].u);
+                tot.u += __shfl_xor_sync(0xffffffffu, tot.u, 4);
+                tot.u += __shfl_xor_sync(0xffffffffu, tot.u, 2);
+                tot.u += __shfl_xor_sync(0xffffffffu, tot.u, 1);
+              } else {
+                tot.f0 = (p[0].f0 + p[2].f0) + (p[1].f0 + p[3].f0);
+                tot.f0 += __shfl_xor_sync(0xffffffffu, tot.f0, 4);
+                tot.f0 += __shfl_xor_sync(0xffffffffu, tot.f0, 2);
+                tot.f0 += __shfl_xor_sync(0xffffffffu, tot.f0, 1);
+                if (ACC == ACC_F_COS) {
+                  tot.f1 = (p[0].f1 + p[2].f1) + (p[1].f1 + p[3].f1);
+                  tot.f1 += __shfl_xor_sync(0xffffffffu, tot.f1, 4);
+                  tot.f1 += __shfl_xor_sync(0xffffffffu, tot.f1, 2);
+                  tot.f1 += __shfl_xor_sync(0xffffffffu, tot.f1, 1);
+                }
+              }
+              const uint32_t r = r0 + rr;
+              if ((lane & 7) == 0 && r < nr)
+                s_cand_keys[j0 + r] = make_key(finish_distance<ACC>(a.dtype, tot, qn), s_cand_ids[j0 + r]);
+            }
+          } else if (CPL > 0 && CPL <= 2 && G == 32) {
             // eight rows at a time, folded together (fold8). Slots past the slice's last row hold stale rows of
             // earlier rounds (or the initial zeros): they are read like the others and their result is dropped;
             // chunks past the row's end read the zeroed tail. No predicates and no address selects in the loop.
@@ -1071,6 +990,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
                 s[i] = zero_sums();
 #pragma unroll
                 for (int c = 0; c < NCH; c++) acc_chunk<ACC>(s[i], qreg[c], lds16(ra + i * SROW + c * 512));
+                lane_total<ACC>(s[i]);
               }
               Sums tot = zero_sums();
               if (ACC == ACC_U8_L2 || ACC == ACC_U8_HAM) {
@@ -1093,10 +1013,8 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
                 }
               }
               const uint32_t r = r0 + ((lane >> 2) & 7);
-              const bool owner = (lane & 3) == 0 && r < nr;
-              float d = 0.f;
-              if (owner) d = finish_distance<ACC>(a.dtype, tot, qn);
-              publish_key(aligned, owner, j0 + r, d, s_cand_ids, er_pub, s_cand_keys, &s_key_n, lane);
+              if ((lane & 3) == 0 && r < nr)
+                s_cand_keys[j0 + r] = make_key(finish_distance<ACC>(a.dtype, tot, qn), s_cand_ids[j0 + r]);
             }
           } else if (G == 32) {
             // long rows: one row at a time (query chunks in registers, or in shared memory when CPL == 0)
@@ -1113,9 +1031,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
                 for (uint32_t c = lane; c < a.chunks; c += 32) acc_chunk<ACC>(s, s_query_row[c], rp[c]);
               }
               group_fold<ACC, 32>(s);
-              float d = 0.f;
-              if (lane == 0) d = finish_distance<ACC>(a.dtype, s, qn);
-              publish_key(aligned, lane == 0, j0 + r, d, s_cand_ids, er_pub, s_cand_keys, &s_key_n, lane);
+              if (lane == 0) s_cand_keys[j0 + r] = make_key(finish_distance<ACC>(a.dtype, s, qn), s_cand_ids[j0 + r]);
             }
           } else {
             // short rows: R rows per warp instruction, G lanes each
@@ -1125,10 +1041,7 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
               if (r < nr && (uint32_t)gl < a.chunks)
                 acc_chunk<ACC>(s, qreg[0], reinterpret_cast<const uint4 *>(wstage + (size_t)r * a.row_bytes)[gl]);
               group_fold<ACC, G>(s);
-              const bool owner = gl == 0 && r < nr;
-              float d = 0.f;
-              if (owner) d = finish_distance<ACC>(a.dtype, s, qn);
-              publish_key(aligned, owner, j0 + r, d, s_cand_ids, er_pub, s_cand_keys, &s_key_n, lane);
+              if (gl == 0 && r < nr) s_cand_keys[j0 + r] = make_key(finish_distance<ACC>(a.dtype, s, qn), s_cand_ids[j0 + r]);
             }
           }
           __syncwarp();
@@ -1138,7 +1051,6 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
           for (int i = 0; i < SEARCH_EPT; i++)
             if (pending_mask & (1u << i)) hash_insert(hash, a.hash_bits - 3, pending_id[i], bp[i]);
         }
-        if (!ROW8 && warp == 0) cp_async_commit_wait_all();   // the staged head-table row of the expected next node
         if (warp == 0) { PROF_MARK(5) }
       }
       __syncthreads();  // (C) keys are published; the staging area may be overwritten

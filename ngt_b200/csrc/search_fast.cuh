@@ -6,7 +6,7 @@
 // warp-instructions per expansion, a third of them address arithmetic around the row copies):
 //
 //   rows of <= 512 bytes (<= 32 chunks), edge cap <= 128 (head table), epsilon >= 0 (set semantics), k <= 32,
-//   <= 128 seeds, visited hash in the L2 slab (tier 0). Everything else runs search_kernel.
+//   <= 128 seeds, visited hash in a slab of global memory (both on-chip tiers). Everything else runs search_kernel.
 //
 // One CTA (4 warps) per query, persistent grid. Per round:
 //   control  warp 0: merge the previous round's keys (only those within the exploration radius were published),
@@ -118,7 +118,8 @@ __global__ void __launch_bounds__(128, FAST_MIN_CTAS) search_fast_kernel(const S
     // ---- next query (dynamic scheduling over a persistent grid)
     if (tid == 0) {
       uint32_t w = atomicAdd(a.work_counter, 1u);
-      s_query = w < a.nq ? w : 0xffffffffu;
+      const uint32_t total = a.query_list ? *a.query_list_count : a.nq;   // later tiers: the previous tier's overflow list
+      s_query = w < total ? (a.query_list ? a.query_list[w] : w) : 0xffffffffu;
       s_state = 0;
       s_key_n = 0;
     }
@@ -395,7 +396,8 @@ __global__ void __launch_bounds__(128, FAST_MIN_CTAS) search_fast_kernel(const S
 #pragma unroll
           for (int m = 0; m < CH; m++) {
             p[m] = zero_sums();
-            acc_chunk<ACC>(p[m], q8[m], lds16(ra + m * 128));
+            acc_chunk_packed<ACC>(p[m], q8[m], lds16(ra + m * 128));
+            lane_total<ACC>(p[m]);
           }
           // chunks j, j + 8, j + 16, j + 24 of a row sit on lanes j, j + 8, ... of group_fold<ACC, 32>: the xor-16 and
           // xor-8 levels of its butterfly are these local adds, the remaining three levels are shuffles
@@ -432,7 +434,7 @@ __global__ void __launch_bounds__(128, FAST_MIN_CTAS) search_fast_kernel(const S
             const bool owner = ts <= t && j < cn;
             float d = 0.f;
             if (owner) {
-              Sums s;
+              Sums s = zero_sums();
               s.f0 = tot0;
               s.f1 = tot1;
               s.u = totu;

@@ -182,7 +182,7 @@ def test_seeded_against_port(eng, port, kind):
     ix.close()
 
 
-@pytest.mark.parametrize("kind", ["f32l2_128", "f32cos_100", "f32l2_48", "u8l2_128", "f32ncos_32", "u8l2_256"])
+@pytest.mark.parametrize("kind", ["f32l2_128", "f32cos_100", "f32l2_48", "u8l2_128", "f32ncos_32", "u8l2_256", "u8ham_128"])
 def test_fast_kernel_equals_general_kernel(eng, port, kind):
     """The lean first-tier kernel (search_fast.cuh) and the general one (search.cuh) restate the same loop
     (Graph.cpp:398-495): ids, distance bits, counts and work counters are identical, for every row width class
@@ -202,6 +202,9 @@ def test_fast_kernel_equals_general_kernel(eng, port, kind):
         otype, dtype, objs, q = po.FLOAT, po.L2, base, qs
     elif name == "u8l2":
         otype, dtype, objs, q = po.UINT8, po.L2, base.astype(np.uint8), qs
+    elif name == "u8ham":
+        otype, dtype = po.UINT8, po.HAMMING   # 128 bits = one 16-byte chunk per object
+        objs, q = synth.hamming_from(base, 64.0), synth.hamming_from(qs, 64.0).astype(np.float32)
     elif name == "f32cos":
         otype, dtype = po.FLOAT, po.COSINE
         objs, q = (base - 64.0).astype(np.float32) / 40.0, (qs - 64.0).astype(np.float32) / 40.0
@@ -216,7 +219,7 @@ def test_fast_kernel_equals_general_kernel(eng, port, kind):
     seeds = np.stack([rng.choice(n, 10, replace=False) + 1 for _ in range(nq)]).astype(np.uint32)
     seeds_rep = seeds.copy()
     seeds_rep[::3, 5] = seeds_rep[::3, 1]   # a repeated seed is evaluated once by both kernels
-    exact = name in ("f32l2", "u8l2")
+    exact = name in ("f32l2", "u8l2", "u8ham")
     for eps, cap, kk in ((0.1, 16, 10), (0.3, 100, 10), (0.0, 24, 32), (0.2, 128, 1)):
         out = {}
         for fast in (True, False):

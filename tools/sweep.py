@@ -85,7 +85,7 @@ for cfg in a.configs.split(";"):
             torch.cuda.synchronize()
             lib.ngtgpu_index_set_phase_profile(ix._h, None)
             pm = pb.float().mean(0).cpu().numpy()
-            names = ["merge", "pop", "refill", "filter", "pops-from-staged-head-row", "rows", "sync", "other"]
+            names = ["merge", "pop", "next-was-2nd-or-3rd", "filter", "next-was-2nd", "row-wait", "dist+sync", "other"]
             print("   cycles/query by phase: " + "  ".join("%s=%.0f" % (n_, v) for n_, v in zip(names, pm)) +
                   "  total=%.0f  per-expansion=%.0f" % (pm.sum(), pm.sum() / max(s[2], 1)), flush=True)
         print("K=%d o=%d i=%d cap=%d deg=%.1f eps=%.2f recall=%.4f ndist=%.0f nedge=%.0f nexp=%.1f  %.2f ms  %.0f QPS  %.0f GB/s(step)" % (
