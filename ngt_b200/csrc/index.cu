@@ -415,6 +415,7 @@ extern "C" int ngtgpu_index_set_search_workspace(ngtgpu_index *ix, uint32_t hash
   if (hash_bits < 8 || hash_bits > 17) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "hash_bits must be in [8, 17]");
   if (queue_cap < 64 || queue_cap > 8192) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "queue_cap must be in [64, 8192]");
   ix->hash_bits = hash_bits;
+  ix->hash_bits_auto = false;
   ix->queue_cap = queue_cap;
   return NGTGPU_OK;
 }

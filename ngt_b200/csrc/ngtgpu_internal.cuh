@@ -84,6 +84,7 @@ struct ngtgpu_index {
   uint32_t *d_pivot_ids = nullptr;
   // traversal working-set sizing (on-chip tier)
   uint32_t hash_bits = 14;             // visited hash slots = 1 << hash_bits (4 B each, per-CTA slab in L2)
+  bool hash_bits_auto = true;          // until ngtgpu_index_set_search_workspace: 15 for indexes over 4M objects (deeper searches)
   uint32_t queue_cap = 512;            // unchecked queue entries (8 B each, shared memory)
   uint32_t stage_bytes = 16384;        // shared-memory staging area the TMA engine fills with neighbour rows
   int onchip_tiers = 2;                // 1: overflow goes straight to the HBM tier (tests)

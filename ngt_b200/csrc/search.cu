@@ -133,7 +133,10 @@ int ngtgpu_traverse(ngtgpu_index *ix, const uint8_t *d_queries, uint32_t nq, con
   a.stage_rows = stage_rows;
   const size_t stage_bytes = ((size_t)stage_rows * stage_row + 127) & ~(size_t)127;
   const size_t extra = stage_bytes + res_bytes + (l.cpl == 0 ? ix->row_bytes : 0);
-  uint32_t tier_bits[2] = {ix->hash_bits, 17};
+  // first-tier slab: the configured size, or by index size (measured on the 12.5M x 128 uint8 shard at recall 0.96:
+  // 10 % of the queries visit more than 12 288 objects; 2^15 slots serve them in the first tier, 1.18 M vs 0.90 M queries/s)
+  const uint32_t bits0 = ix->hash_bits_auto ? (ix->n > 4000000ull ? 15u : 14u) : ix->hash_bits;
+  uint32_t tier_bits[2] = {bits0, 17};
   uint32_t tier_queue[2] = {ix->queue_cap, 4096};
   int n_tiers = ix->onchip_tiers >= 2 ? 2 : 1;
   if (tier_bits[0] >= 17) n_tiers = 1;

@@ -104,7 +104,7 @@ gstats = build.graph_statistics(row_ptr)
 ix.set_graph(row_ptr, col)
 ix.set_search_property(cap, 30, 20)
 # long rows (960-d) need many more distance evaluations per query: a larger visited slab / queue per CTA
-hb = a.hash_bits or (16 if a.workload == "gist" else 14)
+hb = a.hash_bits or (16 if a.workload == "gist" else 15 if n > 4000000 else 14)
 qc = a.queue_cap or (2048 if a.workload == "gist" else 512)
 ix.set_search_workspace(hb, qc)
 ix.build_seed_table(1024, 1)
