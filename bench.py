@@ -57,7 +57,7 @@ def parse_args():
     ap.add_argument("--shortcut-reduction", type=int, default=1,
                     help="1: GraphReconstructor::adjustPathsEffectively after reconstructGraph (the reference's ONNG recipe)")
     ap.add_argument("--edge-size", type=int, default=80, help="edge_size of the search (0 = all edges)")
-    ap.add_argument("--pivots", type=int, default=1024)
+    ap.add_argument("--pivots", type=int, default=256)
     ap.add_argument("--seeds", type=int, default=10)
     ap.add_argument("--recall", type=float, default=0.95)
     ap.add_argument("--gt-queries", type=int, default=2000)

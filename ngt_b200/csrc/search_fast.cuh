@@ -490,6 +490,111 @@ __global__ void __launch_bounds__(128, FAST_MIN_CTAS) search_fast_kernel(const S
   }
 }
 
+// ---- seed selection: the n_seeds nearest pivots of the seed table, one warp per query -----------------------
+// Stands where GraphAndTreeIndex::getSeedsFromTree stands (lib/NGT/Index.h:1524-1567: a DVP-tree descent to one
+// leaf). The table is small (hundreds of rows, L1/L2 resident), so every warp walks all of it: four rows per step,
+// eight lanes per row like the traversal, exact distances, the k smallest (distance, id) keys kept sorted one per lane.
+struct SeedArgs {
+  const uint8_t *queries;     // prepared rows, nq x row_bytes
+  const uint8_t *pivots;      // n_pivots x row_bytes
+  const uint32_t *pivot_ids;
+  uint32_t nq, n_pivots, row_bytes, chunks, k;
+  int dtype;
+  uint32_t *seeds;            // nq x k, ascending by (distance, id)
+};
+
+template <int ACC, int CH>
+__global__ void __launch_bounds__(128) seed_select_kernel(const SeedArgs a) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t q = blockIdx.x * 4u + (threadIdx.x >> 5);
+  if (q >= a.nq) return;
+  const uint32_t rr = (uint32_t)lane >> 3, j = (uint32_t)lane & 7u;
+  const uint8_t *qrow = a.queries + (size_t)q * a.row_bytes;
+  uint4 q8[CH];
+#pragma unroll
+  for (int m = 0; m < CH; m++) {
+    const uint32_t c = j + m * 8;
+    q8[m] = c < a.chunks ? ldg16(qrow + (size_t)c * 16) : zero16();
+  }
+  float qn = 0.f;
+  if (ACC == ACC_F_COS) {
+    const uint4 v = (uint32_t)lane < a.chunks ? ldg16(qrow + (size_t)lane * 16) : zero16();
+    float a0 = __uint_as_float(v.x), a1 = __uint_as_float(v.y), a2 = __uint_as_float(v.z), a3 = __uint_as_float(v.w);
+    qn = fmaf(a0, a0, qn);
+    qn = fmaf(a1, a1, qn);
+    qn = fmaf(a2, a2, qn);
+    qn = fmaf(a3, a3, qn);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) qn += __shfl_xor_sync(0xffffffffu, qn, o);
+  }
+  uint64_t res = KEY_NONE, thr = KEY_NONE;   // lane i: the i-th smallest key so far; thr: the k-th
+#pragma unroll 2
+  for (uint32_t p0 = 0; p0 < a.n_pivots; p0 += 4) {
+    const uint32_t row = p0 + rr;
+    const bool valid = row < a.n_pivots;
+    const uint8_t *rp = a.pivots + (size_t)(valid ? row : 0u) * a.row_bytes;
+    Sums p[CH];
+#pragma unroll
+    for (int m = 0; m < CH; m++) {
+      const uint32_t c = j + m * 8;
+      p[m] = zero_sums();
+      acc_chunk_packed<ACC>(p[m], q8[m], c < a.chunks ? ldg16(rp + (size_t)c * 16) : zero16());
+      lane_total<ACC>(p[m]);
+    }
+    Sums tot = p[0];
+    if (ACC == ACC_U8_L2 || ACC == ACC_U8_HAM) {
+      if (CH == 2) tot.u = p[0].u + p[1].u;
+      if (CH == 4) tot.u = (p[0].u + p[2].u) + (p[1].u + p[3].u);
+      tot.u += __shfl_xor_sync(0xffffffffu, tot.u, 4);
+      tot.u += __shfl_xor_sync(0xffffffffu, tot.u, 2);
+      tot.u += __shfl_xor_sync(0xffffffffu, tot.u, 1);
+    } else {
+      if (CH == 2) tot.f0 = p[0].f0 + p[1].f0;
+      if (CH == 4) tot.f0 = (p[0].f0 + p[2].f0) + (p[1].f0 + p[3].f0);
+      tot.f0 += __shfl_xor_sync(0xffffffffu, tot.f0, 4);
+      tot.f0 += __shfl_xor_sync(0xffffffffu, tot.f0, 2);
+      tot.f0 += __shfl_xor_sync(0xffffffffu, tot.f0, 1);
+      if (ACC == ACC_F_COS) {
+        if (CH == 2) tot.f1 = p[0].f1 + p[1].f1;
+        if (CH == 4) tot.f1 = (p[0].f1 + p[2].f1) + (p[1].f1 + p[3].f1);
+        tot.f1 += __shfl_xor_sync(0xffffffffu, tot.f1, 4);
+        tot.f1 += __shfl_xor_sync(0xffffffffu, tot.f1, 2);
+        tot.f1 += __shfl_xor_sync(0xffffffffu, tot.f1, 1);
+      }
+    }
+    uint64_t key = KEY_NONE;
+    if (j == 0 && valid) key = make_key(finish_distance<ACC>(a.dtype, tot, qn), __ldg(a.pivot_ids + row));
+    uint32_t m = __ballot_sync(0xffffffffu, key < thr);
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const uint64_t kk = shfl_u64(key, src);
+      if (kk >= thr) continue;
+      const uint32_t pos = __popc(__ballot_sync(0xffffffffu, res < kk));
+      const uint64_t up = shfl_up_u64(res, 1);
+      if ((uint32_t)lane == pos) res = kk;
+      else if ((uint32_t)lane > pos) res = up;
+      if ((uint32_t)lane >= a.k) res = KEY_NONE;
+      thr = shfl_u64(res, (int)a.k - 1);
+    }
+  }
+  if ((uint32_t)lane < a.k) a.seeds[(size_t)q * a.k + lane] = res != KEY_NONE ? key_id(res) : 0u;
+}
+
+template <int ACC, int CH>
+static cudaError_t seed_one(const SeedArgs &a, cudaStream_t stream) {
+  seed_select_kernel<ACC, CH><<<(a.nq + 3) / 4, 128, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+template <int ACC>
+cudaError_t seed_select_dispatch(const SeedArgs &a, cudaStream_t stream) {
+  const int ch = a.chunks <= 8 ? 1 : a.chunks <= 16 ? 2 : 4;
+  if (ch == 1) return seed_one<ACC, 1>(a, stream);
+  if (ch == 2) return seed_one<ACC, 2>(a, stream);
+  return seed_one<ACC, 4>(a, stream);
+}
+
 // op == 0: launch, op == 1: occupancy query
 template <int ACC, int CH>
 static cudaError_t fast_one(const SearchArgs &a, unsigned grid, size_t smem, cudaStream_t stream, int op, int *blocks) {

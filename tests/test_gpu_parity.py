@@ -325,6 +325,44 @@ def test_long_rows_and_wide_results(eng, port):
     ix.close()
 
 
+@pytest.mark.parametrize("kind", ["f32l2_128", "u8l2_128", "f32l2_48", "u8ham_128", "f32cos_100"])
+def test_seed_selection_is_the_exact_nearest_pivots(eng, port, kind):
+    """ngtgpu_select_seeds returns the n_seeds nearest pivots by (distance, id). With every object a pivot that is the
+    exhaustive search itself (same ids, same order), for every row-width class of the one-warp-per-query kernel."""
+    import ctypes as C
+    from ngt_b200 import _lib, synth
+    name, dim = kind.split("_")
+    dim = int(dim)
+    n, nq = 3000, 257
+    base, qs = synth.make("sift", n, 1)[:, :dim], synth.make("sift", nq, 2)[:, :dim]
+    if name == "u8l2":
+        otype, dtype, objs, q = po.UINT8, po.L2, base.astype(np.uint8), qs
+    elif name == "u8ham":
+        otype, dtype = po.UINT8, po.HAMMING
+        objs, q = synth.hamming_from(base, 64.0), synth.hamming_from(qs, 64.0).astype(np.float32)
+    elif name == "f32cos":
+        otype, dtype = po.FLOAT, po.COSINE
+        objs, q = (base - 64.0).astype(np.float32) / 40.0, (qs - 64.0).astype(np.float32) / 40.0
+    else:
+        otype, dtype, objs, q = po.FLOAT, po.L2, base, qs
+    ix = eng.GpuIndex(otype, dtype, objs.shape[1])
+    ix.set_objects(objs)
+    ix.build_seed_table(n, 1)   # one pivot per stride of one id: every object
+    lib = _lib.load()
+    lib.ngtgpu_select_seeds.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p]
+    q = np.ascontiguousarray(q, np.float32)
+    for ns in (1, 10, 32):
+        seeds = np.zeros((nq, ns), np.uint32)
+        _lib.check(lib.ngtgpu_select_seeds(ix._h, q.ctypes.data, _lib.OBJECT_FLOAT, nq, ns, seeds.ctypes.data))
+        ids, dists, counts = ix.linear_search(q, ns)
+        if name == "f32cos":   # general float data: equal up to swaps among (near-)ties
+            same = (np.sort(seeds, 1) == np.sort(np.asarray(ids), 1)).all(1).mean()
+            assert same > 0.98, (kind, ns, same)
+        else:
+            assert (seeds == np.asarray(ids)).all(), (kind, ns)
+    ix.close()
+
+
 def test_device_seed_table_recall(eng, port):
     """Seeds from the device pivot table (stand-in for the DVP-tree leaf): recall at the reference's epsilon
     is at least what the restated search reaches from the same seeds, and >= 0.9 on this set."""
