@@ -167,9 +167,10 @@ int ngtgpu_traverse(ngtgpu_index *ix, const uint8_t *d_queries, uint32_t nq, con
     // the on-chip tiers of the common case run the lean kernel: rows of 5..32 chunks, head-table adjacency, set semantics
     // (epsilon >= 0), results in one warp's registers, a seed list that is one round
     const bool fast = ix->fast_kernel && ix->chunks >= FAST_MIN_CHUNKS && ix->chunks <= 32 && cap <= NGTGPU_HEAD_WIDTH &&
-                      a.coef >= 1.0f && k <= 32 && n_seeds <= SEARCH_CMAX;
+                      a.coef >= 1.0f && k <= 32 && n_seeds <= 32 * FAST_WARPS && cap <= 32 * FAST_WARPS &&   // one edge per thread
+                      (ix->n + 1) * (uint64_t)ix->row_bytes < (1ull << 36);   // 32-bit row offsets in 16-byte units
     const int fast_ch = ix->chunks <= 8 ? 1 : ix->chunks <= 16 ? 2 : 4;
-    if (fast) smem = 4 * 4096 + (size_t)a.queue_cap * 8;
+    if (fast) smem = (size_t)FAST_WARPS * FAST_STAGE_PER_WARP + (size_t)a.queue_cap * 8;
     if (smem > 200 * 1024)
       NGTGPU_FAIL(NGTGPU_ERR_INVALID, "search: working set does not fit shared memory; lower queue_cap/size");
     l.smem = smem;

@@ -25,11 +25,18 @@
 #include "search.cuh"
 
 #define FAST_STAGE_PER_WARP 4096u
+#ifndef FAST_WARPS
+#define FAST_WARPS 4      // warps per query (CTA); 3 warps x 10 CTAs/SM measured the same as 4 x 8
+#endif
+#define FAST_THREADS (FAST_WARPS * 32)
 #ifndef FAST_MIN_CTAS
-#define FAST_MIN_CTAS 8   // resident CTAs per SM the register allocation aims at
+#define FAST_MIN_CTAS (32 / FAST_WARPS)   // resident CTAs per SM the register allocation aims at
 #endif
 
 // ---- visited hash: the bucket in one 256-bit load -------------------------------------------------------
+// Slots of a bucket are taken in increasing order (hash_insert tries slot i only after slot i - 1 was seen occupied),
+// so the occupied slots are a prefix: the id is present iff some word equals it (a min over the xors), the bucket is
+// full iff its last word is taken, and the first free slot is found by a three-step binary search.
 __device__ __forceinline__ bool hash_lookup256(const uint32_t *hash, uint32_t bucket_bits, uint32_t nid, BucketProbe &bp) {
   const uint32_t bmask = (1u << bucket_bits) - 1u;
   uint32_t b = (nid * 2654435761u) >> (32 - bucket_bits);
@@ -38,15 +45,18 @@ __device__ __forceinline__ bool hash_lookup256(const uint32_t *hash, uint32_t bu
     asm volatile("ld.global.cg.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "l"(hash + (size_t)b * 8));
-    uint32_t free_slot = 8;
-#pragma unroll
-    for (int i = 7; i >= 0; i--) {
-      if (v[i] == nid) return true;   // visited
-      if (v[i] == 0u) free_slot = i;
-    }
-    if (free_slot < 8) {
+    const uint32_t x = min(min(min(v[0] ^ nid, v[1] ^ nid), min(v[2] ^ nid, v[3] ^ nid)),
+                           min(min(v[4] ^ nid, v[5] ^ nid), min(v[6] ^ nid, v[7] ^ nid)));
+    if (x == 0u) return true;   // visited
+    if (v[7] == 0u) {
+      uint32_t s0 = v[3] != 0u ? 4u : 0u;
+      const uint32_t m1 = s0 ? v[5] : v[1];
+      s0 += m1 != 0u ? 2u : 0u;
+      const uint32_t lo = (s0 & 2u) ? v[2] : v[0], hi = (s0 & 2u) ? v[6] : v[4];
+      const uint32_t m0 = (s0 & 4u) ? hi : lo;
+      s0 += m0 != 0u ? 1u : 0u;
       bp.bucket = b;
-      bp.slot = free_slot;
+      bp.slot = s0;
       return false;
     }
     b = (b + 1) & bmask;
@@ -61,21 +71,28 @@ __device__ __forceinline__ void cp_async_s16z_hint(uint32_t smem_addr, const voi
                : "memory");
 }
 
+// base + 16 * off16 in one IMAD.WIDE (the base is the kernel parameter: an aligned register pair)
+__device__ __forceinline__ const uint8_t *addr16(uint32_t off16, const uint8_t *base) {
+  uint64_t r;
+  asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(r) : "r"(off16), "l"((uint64_t)(uintptr_t)base));
+  return reinterpret_cast<const uint8_t *>((uintptr_t)r);
+}
+
 template <int N>
 __device__ __forceinline__ void cp_async_wait_group() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
 template <int ACC, int CH>
-__global__ void __launch_bounds__(128, FAST_MIN_CTAS) search_fast_kernel(const SearchArgs a) {
+__global__ void __launch_bounds__(FAST_THREADS, FAST_MIN_CTAS) search_fast_kernel(const SearchArgs a) {
   constexpr uint32_t SROW = 128u * CH;                         // staging stride of a row
   constexpr uint32_t GBYTES = 4u * SROW;                       // one group = four rows
   constexpr int NB = (int)(FAST_STAGE_PER_WARP / GBYTES);      // ring depth per warp: 2, 4 or 8
   constexpr uint32_t RPI = 4u / CH;                            // rows per copy instruction
   constexpr uint32_t LPR = 8u * CH;                            // lanes per row in a copy instruction
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  __shared__ __align__(16) uint32_t s_wids[4][SEARCH_CMAX / 4 + 4];   // new ids per warp
-  __shared__ uint32_t s_wcnt[4], s_wval[4];
+  __shared__ __align__(16) uint32_t s_wids[FAST_WARPS][32 + 4];   // new ids per warp
+  __shared__ uint32_t s_wcnt[FAST_WARPS], s_wval[FAST_WARPS];
   __shared__ uint64_t s_cand_keys[SEARCH_CMAX];
   __shared__ __align__(16) uint32_t s_edges[2][SEARCH_HEAD];   // edge lists of the round / of the expected next node
   __shared__ uint32_t s_key_n;
@@ -96,7 +113,7 @@ __global__ void __launch_bounds__(128, FAST_MIN_CTAS) search_fast_kernel(const S
   const int warp = tid >> 5;
 
   uint8_t *stage = smem_raw;                                                   // 4 x FAST_STAGE_PER_WARP
-  uint64_t *queue = reinterpret_cast<uint64_t *>(smem_raw + 4 * FAST_STAGE_PER_WARP);
+  uint64_t *queue = reinterpret_cast<uint64_t *>(smem_raw + FAST_WARPS * FAST_STAGE_PER_WARP);
   uint32_t *hash = a.hash_slabs + ((size_t)blockIdx.x << a.hash_bits);
   const uint32_t bucket_bits = a.hash_bits - 3;
   const uint32_t take_head = a.edge_cap < SEARCH_HEAD ? a.edge_cap : SEARCH_HEAD;
@@ -106,7 +123,7 @@ __global__ void __launch_bounds__(128, FAST_MIN_CTAS) search_fast_kernel(const S
   const uint32_t cp_row = (uint32_t)lane / LPR;                   // row inside one copy instruction
   const uint32_t cp_chunk = (uint32_t)lane % LPR;
   const uint32_t cp_dst = wstage_s + cp_row * SROW + cp_chunk * 16u;
-  const uint8_t *cp_src = a.objects + (size_t)cp_chunk * 16u;
+  const uint32_t rb16 = a.row_bytes >> 4;                         // a row in 16-byte units (tables up to 64 GB)
   const uint32_t cp_size = cp_chunk < a.chunks ? 16u : 0u;        // chunks past the row's end are zero-filled
   const uint32_t rr = (uint32_t)lane >> 3;                        // row inside a distance step
   const uint32_t rd = wstage_s + rr * SROW + ((uint32_t)lane & 7u) * 16u;
@@ -128,7 +145,7 @@ __global__ void __launch_bounds__(128, FAST_MIN_CTAS) search_fast_kernel(const S
     if (q == 0xffffffffu) break;
     {
       uint4 *h4 = reinterpret_cast<uint4 *>(hash);
-      for (uint32_t i = tid; i < (1u << a.hash_bits) / 4; i += 128) h4[i] = zero16();
+      for (uint32_t i = tid; i < (1u << a.hash_bits) / 4; i += FAST_THREADS) h4[i] = zero16();
     }
     const uint8_t *qrow = a.queries + (size_t)q * a.row_bytes;
     uint4 q8[CH];   // lane (rr, j) holds query chunks j, j + 8, ...
@@ -183,8 +200,12 @@ __global__ void __launch_bounds__(128, FAST_MIN_CTAS) search_fast_kernel(const S
         uint32_t cand_n = 0;
         bool overflow = false, finished = false;
         if (rounds_done) {
-          cand_n = (s_wcnt[0] + s_wcnt[1]) + (s_wcnt[2] + s_wcnt[3]);
-          if (head_round) st_edge += (s_wval[0] + s_wval[1]) + (s_wval[2] + s_wval[3]);
+#pragma unroll
+          for (int w = 0; w < FAST_WARPS; w++) cand_n += s_wcnt[w];
+          if (head_round) {
+#pragma unroll
+            for (int w = 0; w < FAST_WARPS; w++) st_edge += s_wval[w];
+          }
         }
         visited_n += cand_n;
         st_dist += cand_n;
@@ -228,7 +249,7 @@ __global__ void __launch_bounds__(128, FAST_MIN_CTAS) search_fast_kernel(const S
             while (fm) {
               const int src = __ffs(fm) - 1;
               fm &= fm - 1;
-              if (!unchecked_insert(U, shfl_u64(key, src), er, lane, a.head, a.edge_cap)) {
+              if (!unchecked_insert(U, shfl_u64(key, src), er, lane, nullptr, a.edge_cap)) {
                 overflow = true;
                 break;
               }
@@ -321,7 +342,7 @@ __global__ void __launch_bounds__(128, FAST_MIN_CTAS) search_fast_kernel(const S
       bp.bucket = 0;
       bp.slot = 0;
       {
-        const uint32_t e = 4u * (uint32_t)lane + (uint32_t)warp;   // edges dealt round-robin: the warps get equal shares
+        const uint32_t e = (uint32_t)FAST_WARPS * (uint32_t)lane + (uint32_t)warp;   // edges dealt round-robin: the warps get equal shares
         const uint32_t nid = e < s_take ? s_edges[s_buf][e] : 0u;
         const bool valid = nid != 0u && nid <= a.n;
         bool isnew = false;
@@ -370,15 +391,15 @@ __global__ void __launch_bounds__(128, FAST_MIN_CTAS) search_fast_kernel(const S
       const uint32_t _dst = cp_dst + (_t % NB) * GBYTES;                                                \
       if (CH == 4) {                                                                                    \
         const uint4 _ids = *reinterpret_cast<const uint4 *>(&cand_ids[_c0]);                            \
-        FAST_ROWCP(_dst, mad_wide_ptr(_ids.x, a.row_bytes, cp_src), cp_size);                           \
-        FAST_ROWCP(_dst + SROW, mad_wide_ptr(_ids.y, a.row_bytes, cp_src), cp_size);                    \
-        FAST_ROWCP(_dst + 2 * SROW, mad_wide_ptr(_ids.z, a.row_bytes, cp_src), cp_size);                \
-        FAST_ROWCP(_dst + 3 * SROW, mad_wide_ptr(_ids.w, a.row_bytes, cp_src), cp_size);                \
+        FAST_ROWCP(_dst, addr16(_ids.x * rb16 + cp_chunk, a.objects), cp_size);                           \
+        FAST_ROWCP(_dst + SROW, addr16(_ids.y * rb16 + cp_chunk, a.objects), cp_size);                    \
+        FAST_ROWCP(_dst + 2 * SROW, addr16(_ids.z * rb16 + cp_chunk, a.objects), cp_size);                \
+        FAST_ROWCP(_dst + 3 * SROW, addr16(_ids.w * rb16 + cp_chunk, a.objects), cp_size);                \
       } else {                                                                                          \
         uint32_t _id[CH];                                                                               \
         _Pragma("unroll") for (int _i = 0; _i < CH; _i++) _id[_i] = cand_ids[_c0 + _i * RPI + cp_row];  \
         _Pragma("unroll") for (int _i = 0; _i < CH; _i++)                                               \
-          FAST_ROWCP(_dst + _i * RPI * SROW, mad_wide_ptr(_id[_i], a.row_bytes, cp_src), cp_size);      \
+          FAST_ROWCP(_dst + _i * RPI * SROW, addr16(_id[_i] * rb16 + cp_chunk, a.objects), cp_size);      \
       }                                                                                                 \
     }                                                                                                   \
     asm volatile("cp.async.commit_group;" ::: "memory");                                                \
@@ -602,8 +623,8 @@ static cudaError_t fast_one(const SearchArgs &a, unsigned grid, size_t smem, cud
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(search_fast_kernel<ACC, CH>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   if (e != cudaSuccess) return e;
-  if (op == 1) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, search_fast_kernel<ACC, CH>, 128, smem);
-  search_fast_kernel<ACC, CH><<<grid, 128, smem, stream>>>(a);
+  if (op == 1) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, search_fast_kernel<ACC, CH>, FAST_THREADS, smem);
+  search_fast_kernel<ACC, CH><<<grid, FAST_THREADS, smem, stream>>>(a);
   return cudaGetLastError();
 }
 
