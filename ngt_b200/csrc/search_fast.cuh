@@ -355,6 +355,7 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_MIN_CTAS) search_fast_kerne
             // the row is copied to shared memory a few hundred cycles from now: start it towards L2
             if (isnew) {
               const uint8_t *rp = a.objects + (size_t)nid * a.row_bytes;
+              // (one cp.async.bulk.prefetch.L2 per row instead of a prefetch per line measured slower: 4.22 vs 4.10 ms)
 #pragma unroll
               for (int o = 0; o < CH; o++)
                 if (o == 0 || (uint32_t)o * 128u < a.row_bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + o * 128));
