@@ -38,6 +38,7 @@ ap.add_argument("--gt", type=int, default=1000)
 ap.add_argument("--recall", type=float, default=0.95)
 ap.add_argument("--hash-bits", type=int, default=0)
 ap.add_argument("--queue-cap", type=int, default=0)
+ap.add_argument("--pivots", type=int, default=256)
 a = ap.parse_args()
 
 W = {   # shape, object type, distance, default n, knn, outgoing, incoming, edge cap
@@ -107,7 +108,7 @@ ix.set_search_property(cap, 30, 20)
 hb = a.hash_bits or (16 if a.workload == "gist" else 15 if n > 4000000 else 14)
 qc = a.queue_cap or (2048 if a.workload == "gist" else 512)
 ix.set_search_workspace(hb, qc)
-ix.build_seed_table(1024, 1)
+ix.build_seed_table(a.pivots, 1)
 del row_ptr, col, dist
 torch.cuda.empty_cache()
 
