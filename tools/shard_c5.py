@@ -78,7 +78,7 @@ t3 = time.time()
 gstats = build.graph_statistics(row_ptr)
 ix.set_graph(row_ptr, col)
 ix.set_search_property(64, 30, 20)
-ix.build_seed_table(1024, 1)
+ix.build_seed_table(256, 1)
 del row_ptr, col, dd
 torch.cuda.empty_cache()
 
