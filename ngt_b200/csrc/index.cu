@@ -441,6 +441,12 @@ extern "C" int ngtgpu_index_set_onchip_tiers(ngtgpu_index *ix, int tiers) {
   return NGTGPU_OK;
 }
 
+extern "C" int ngtgpu_index_set_seed_fusion(ngtgpu_index *ix, int enabled) {
+  if (!ix) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "null index handle");
+  ix->fuse_seeds = enabled != 0;
+  return NGTGPU_OK;
+}
+
 extern "C" int ngtgpu_index_set_fast_kernel(ngtgpu_index *ix, int enabled) {
   if (!ix) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "null index handle");
   ix->fast_kernel = enabled != 0;

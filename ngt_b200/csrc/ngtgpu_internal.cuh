@@ -88,6 +88,7 @@ struct ngtgpu_index {
   uint32_t queue_cap = 512;            // unchecked queue entries (8 B each, shared memory)
   uint32_t stage_bytes = 16384;        // shared-memory staging area the TMA engine fills with neighbour rows
   int onchip_tiers = 2;                // 1: overflow goes straight to the HBM tier (tests)
+  bool fuse_seeds = false;             // seed selection inside the lean traversal kernel instead of its own launch
   bool fast_kernel = true;             // first tier of the common case on search_fast_kernel (off: tests of the general kernel)
   uint64_t last_overflows = 0;         // queries of the last call that fell to the global-memory tier
   // scratch

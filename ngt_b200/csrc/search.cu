@@ -66,6 +66,9 @@ static cudaError_t dispatch(int acc, const SearchArgs &a, const SearchLaunch &l,
   return cudaErrorInvalidValue;
 }
 
+static int select_seeds(ngtgpu_index *ix, const uint8_t *d_queries, uint32_t nq, uint32_t n_seeds, uint32_t **d_seeds,
+                        cudaStream_t stream);
+
 #define BIG_TIER_QUEUE (1u << 18)
 #ifndef FAST_MIN_CHUNKS
 #define FAST_MIN_CHUNKS 5   // shorter rows stay on the general kernel (many rows per copy instruction)
@@ -111,6 +114,32 @@ int ngtgpu_traverse(ngtgpu_index *ix, const uint8_t *d_queries, uint32_t nq, con
   a.counts = d_counts;
   a.stats = d_stats;
   a.prof = ix->d_prof;
+  // No seed list: the nearest pivots of the seed table, from a selection pass that runs first -- or, when seed fusion is
+  // switched on and the table is small, selected by the lean kernel itself in the first tier (and written out for the
+  // later tiers).
+  uint32_t *d_sel = nullptr;
+  bool fused_seeds = false;
+  if (!d_seeds) {
+    if (ix->n_pivots == 0)
+      NGTGPU_FAIL(NGTGPU_ERR_STATE, "search: no seeds given and no seed table built (ngtgpu_index_build_seed_table)");
+    if (n_seeds == 0) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "search: n_seeds is zero");
+    if (n_seeds > ix->n_pivots) n_seeds = ix->n_pivots;
+    a.n_seeds = n_seeds;
+    const bool lean = ix->fast_kernel && ix->chunks >= FAST_MIN_CHUNKS && ix->chunks <= 32 && cap <= 32 * FAST_WARPS &&
+                      a.coef >= 1.0f && k <= 32 && (ix->n + 1) * (uint64_t)ix->row_bytes < (1ull << 36);
+    if (lean && ix->fuse_seeds && n_seeds <= 32 && ix->n_pivots <= 512) {
+      NGTGPU_TRY(ngtgpu_scratch(ix, SCR_SEEDS, (size_t)nq * n_seeds * sizeof(uint32_t), (void **)&d_sel));
+      fused_seeds = true;
+      a.seeds = nullptr;
+      a.pivots = ix->d_pivot_rows;
+      a.pivot_ids = ix->d_pivot_ids;
+      a.n_pivots = ix->n_pivots;
+      a.seeds_out = d_sel;
+    } else {
+      NGTGPU_TRY(select_seeds(ix, d_queries, nq, n_seeds, &d_sel, stream));
+      a.seeds = d_sel;
+    }
+  }
 
   // counters (16 words): [2t] work counter of tier t, [2t+1] overflow count of tier t (t = 0, 1), [4] work counter
   // of the HBM tier, [5] failed count; then two overflow lists of nq entries each
@@ -161,6 +190,7 @@ int ngtgpu_traverse(ngtgpu_index *ix, const uint8_t *d_queries, uint32_t nq, con
     a.work_counter = ws + 2 * t;
     a.overflow_count = ws + 2 * t + 1;
     a.overflow_list = lists[t & 1];
+    if (fused_seeds && t > 0) a.seeds = d_sel;   // written by the first tier
     a.query_list = t == 0 ? nullptr : lists[(t - 1) & 1];
     a.query_list_count = t == 0 ? nullptr : ws + 2 * (t - 1) + 1;
     size_t smem = extra + (size_t)a.queue_cap * 8;
@@ -213,6 +243,7 @@ int ngtgpu_traverse(ngtgpu_index *ix, const uint8_t *d_queries, uint32_t nq, con
   uint8_t *big = nullptr;
   NGTGPU_TRY(ngtgpu_scratch(ix, SCR_SEARCH_BIG, big_bytes, (void **)&big));
   SearchArgs b = a;
+  if (fused_seeds) b.seeds = d_sel;
   b.work_counter = ws + 4;
   b.query_list = lists[last & 1];
   b.query_list_count = ws + 2 * last + 1;
@@ -320,10 +351,7 @@ static int search_common(ngtgpu_index *ix, const void *queries, int query_type, 
       d_seeds = s;
     }
   } else {
-    uint32_t *s = nullptr;
-    if (ns > ix->n_pivots) ns = ix->n_pivots;
-    NGTGPU_TRY(select_seeds(ix, d_q, nq, ns, &s, stream));
-    d_seeds = s;
+    d_seeds = nullptr;   // the traversal takes the nearest pivots of the seed table
   }
   uint32_t *d_ids = ids, *d_counts = counts, *d_stats = stats;
   float *d_dists = dists;

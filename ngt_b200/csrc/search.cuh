@@ -66,7 +66,7 @@ struct SearchArgs {
   const uint32_t *col;
   const uint32_t *head;    // (n+1) x SEARCH_HEAD, zero padded
   const uint8_t *queries;  // prepared rows, nq x row_bytes
-  const uint32_t *seeds;   // nq x n_seeds
+  const uint32_t *seeds;   // nq x n_seeds; null (lean kernel, first tier only): the nearest n_seeds pivots, selected by the kernel
   uint32_t n_seeds;
   uint32_t nq;
   uint32_t k;
@@ -93,6 +93,10 @@ struct SearchArgs {
   uint64_t *big_queues;              // WS == 1: gridDim.x x queue_cap
   uint64_t bitmap_words;
   uint32_t *prof;                    // nullable, nq x 8: cycles of warp 0 per phase (development aid)
+  const uint8_t *pivots;             // seed table (seeds == null): n_pivots x row_bytes
+  const uint32_t *pivot_ids;
+  uint32_t n_pivots;
+  uint32_t *seeds_out;               // nq x n_seeds: the seeds the kernel selected, for the later tiers
 };
 
 __device__ __forceinline__ uint32_t lanemask_lt() {

@@ -168,6 +168,89 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_MIN_CTAS) search_fast_kerne
     }
     __syncthreads();   // the slab is zero before anybody probes it
 
+    if (a.seeds == nullptr) {
+      // ---- seeds: the n_seeds nearest pivots of the seed table (the same selection as seed_select_kernel, without
+      // its launch): every warp scans a quarter of the table, four rows per step read straight from L1/L2, and keeps
+      // its k smallest keys sorted one per lane; warp 0 merges the lists into the first round's edge list
+      uint64_t wres = KEY_NONE, wthr = KEY_NONE;
+      for (uint32_t p0 = 4u * (uint32_t)warp; p0 < a.n_pivots; p0 += 4u * FAST_WARPS) {
+        const uint32_t row = p0 + rr;
+        const bool valid = row < a.n_pivots;
+        const uint8_t *rp = a.pivots + (size_t)(valid ? row : 0u) * a.row_bytes;
+        Sums p[CH];
+#pragma unroll
+        for (int m = 0; m < CH; m++) {
+          const uint32_t c = ((uint32_t)lane & 7u) + m * 8;
+          p[m] = zero_sums();
+          acc_chunk_packed<ACC>(p[m], q8[m], c < a.chunks ? ldg16(rp + (size_t)c * 16) : zero16());
+          lane_total<ACC>(p[m]);
+        }
+        Sums tot = p[0];
+        if (ACC == ACC_U8_L2 || ACC == ACC_U8_HAM) {
+          if (CH == 2) tot.u = p[0].u + p[1].u;
+          if (CH == 4) tot.u = (p[0].u + p[2].u) + (p[1].u + p[3].u);
+          tot.u += __shfl_xor_sync(0xffffffffu, tot.u, 4);
+          tot.u += __shfl_xor_sync(0xffffffffu, tot.u, 2);
+          tot.u += __shfl_xor_sync(0xffffffffu, tot.u, 1);
+        } else {
+          if (CH == 2) tot.f0 = p[0].f0 + p[1].f0;
+          if (CH == 4) tot.f0 = (p[0].f0 + p[2].f0) + (p[1].f0 + p[3].f0);
+          tot.f0 += __shfl_xor_sync(0xffffffffu, tot.f0, 4);
+          tot.f0 += __shfl_xor_sync(0xffffffffu, tot.f0, 2);
+          tot.f0 += __shfl_xor_sync(0xffffffffu, tot.f0, 1);
+          if (ACC == ACC_F_COS) {
+            if (CH == 2) tot.f1 = p[0].f1 + p[1].f1;
+            if (CH == 4) tot.f1 = (p[0].f1 + p[2].f1) + (p[1].f1 + p[3].f1);
+            tot.f1 += __shfl_xor_sync(0xffffffffu, tot.f1, 4);
+            tot.f1 += __shfl_xor_sync(0xffffffffu, tot.f1, 2);
+            tot.f1 += __shfl_xor_sync(0xffffffffu, tot.f1, 1);
+          }
+        }
+        uint64_t key = KEY_NONE;
+        if (((uint32_t)lane & 7u) == 0u && valid) key = make_key(finish_distance<ACC>(a.dtype, tot, qn), __ldg(a.pivot_ids + row));
+        uint32_t m = __ballot_sync(0xffffffffu, key < wthr);
+        while (m) {
+          const int src = __ffs(m) - 1;
+          m &= m - 1;
+          const uint64_t kk = shfl_u64(key, src);
+          if (kk >= wthr) continue;
+          const uint32_t pos = __popc(__ballot_sync(0xffffffffu, wres < kk));
+          const uint64_t up = shfl_up_u64(wres, 1);
+          if ((uint32_t)lane == pos) wres = kk;
+          else if ((uint32_t)lane > pos) wres = up;
+          if ((uint32_t)lane >= a.n_seeds) wres = KEY_NONE;
+          wthr = shfl_u64(wres, (int)a.n_seeds - 1);
+        }
+      }
+      s_cand_keys[warp * 32 + lane] = wres;
+      __syncthreads();
+      if (warp == 0) {
+        uint64_t mres = KEY_NONE, mthr = KEY_NONE;
+        for (int w = 0; w < FAST_WARPS; w++) {
+          const uint64_t key = s_cand_keys[w * 32 + lane];
+          uint32_t m = __ballot_sync(0xffffffffu, key < mthr);
+          while (m) {
+            const int src = __ffs(m) - 1;
+            m &= m - 1;
+            const uint64_t kk = shfl_u64(key, src);
+            if (kk >= mthr) continue;
+            const uint32_t pos = __popc(__ballot_sync(0xffffffffu, mres < kk));
+            const uint64_t up = shfl_up_u64(mres, 1);
+            if ((uint32_t)lane == pos) mres = kk;
+            else if ((uint32_t)lane > pos) mres = up;
+            if ((uint32_t)lane >= a.n_seeds) mres = KEY_NONE;
+            mthr = shfl_u64(mres, (int)a.n_seeds - 1);
+          }
+        }
+        if ((uint32_t)lane < a.n_seeds) {
+          const uint32_t sid = mres != KEY_NONE ? key_id(mres) : 0u;
+          s_edges[0][lane] = sid;
+          a.seeds_out[(size_t)q * a.n_seeds + lane] = sid;
+        }
+        __syncwarp();
+      }
+    }
+
     // ---- control-warp state (kept in shared memory between rounds)
     if (warp == 0) {
       s_res[lane] = KEY_NONE;     // result list: lane i holds the i-th smallest key (k <= 32)
@@ -263,8 +346,10 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_MIN_CTAS) search_fast_kerne
             // the seed list is the first round's edge list (setupDistances/setupSeeds, Graph.cpp:243-394)
             seeds_taken = true;
             take = a.n_seeds;
-            const uint32_t *sp = a.seeds + (size_t)q * a.n_seeds;
-            for (uint32_t i = lane; i < take; i += 32) s_edges[buf][i] = __ldg(sp + i);
+            if (a.seeds) {   // (else the kernel selected them above: they are in s_edges[0] already)
+              const uint32_t *sp = a.seeds + (size_t)q * a.n_seeds;
+              for (uint32_t i = lane; i < take; i += 32) s_edges[buf][i] = __ldg(sp + i);
+            }
           } else {
             if (seeding) {
               // setupSeeds: radius from the seeds once k of them are within it (Graph.cpp:349-351)

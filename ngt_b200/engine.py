@@ -145,6 +145,10 @@ class GpuIndex:
         """First traversal tier of the common case on the lean kernel (default) or on the general one."""
         _lib.check(self._lib.ngtgpu_index_set_fast_kernel(self._h, int(bool(enabled))))
 
+    def set_seed_fusion(self, enabled=True):
+        """Seed selection inside the lean traversal kernel (True) or by its own launch (default)."""
+        _lib.check(self._lib.ngtgpu_index_set_seed_fusion(self._h, int(bool(enabled))))
+
     def set_tensor_core(self, enabled=True):
         _lib.check(self._lib.ngtgpu_index_set_tensor_core(self._h, int(bool(enabled))))
 

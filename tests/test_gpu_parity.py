@@ -363,6 +363,47 @@ def test_seed_selection_is_the_exact_nearest_pivots(eng, port, kind):
     ix.close()
 
 
+@pytest.mark.parametrize("kind", ["f32l2_128", "u8l2_128", "f32cos_100", "f32l2_48"])
+def test_seeds_selected_inside_the_traversal_equal_explicit_seeds(eng, kind):
+    """Without a seed list the nearest pivots are selected by a pass of their own or (seed fusion) by the lean kernel
+    itself in the first tier, which hands them to the later tiers: every output equals a search from the seeds
+    ngtgpu_select_seeds returns, also when queries overflow."""
+    import ctypes as C
+    from ngt_b200 import _lib, synth
+    name, dim = kind.split("_")
+    dim = int(dim)
+    n, nq = 6000, 200
+    base, qs = synth.make("sift", n, 1)[:, :dim], synth.make("sift", nq, 2)[:, :dim]
+    if name == "u8l2":
+        otype, dtype, objs, q = po.UINT8, po.L2, base.astype(np.uint8), qs
+    elif name == "f32cos":
+        otype, dtype = po.FLOAT, po.COSINE
+        objs, q = (base - 64.0).astype(np.float32) / 40.0, (qs - 64.0).astype(np.float32) / 40.0
+    else:
+        otype, dtype, objs, q = po.FLOAT, po.L2, base, qs
+    q = np.ascontiguousarray(q, np.float32)
+    ix = eng.GpuIndex(otype, dtype, objs.shape[1])
+    ix.set_objects(objs)
+    gids, _, gcounts = ix.linear_search(objs.astype(np.float32), 13)
+    row_ptr, col = _knn_csr(gids, gcounts)
+    ix.set_graph(row_ptr, col)
+    ix.build_seed_table(200, 3)
+    lib = _lib.load()
+    lib.ngtgpu_select_seeds.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p]
+    seeds = np.zeros((nq, 10), np.uint32)
+    _lib.check(lib.ngtgpu_select_seeds(ix._h, q.ctypes.data, _lib.OBJECT_FLOAT, nq, 10, seeds.ctypes.data))
+    for hb, qc in ((14, 512), (9, 64)):
+        ix.set_search_workspace(hash_bits=hb, queue_cap=qc)
+        b = ix.search(q, 10, 0.2, edge_size=12, seeds=seeds, with_stats=True)
+        for fused in (True, False):
+            ix.set_seed_fusion(fused)
+            a = ix.search(q, 10, 0.2, edge_size=12, n_seeds=10, with_stats=True)
+            for x, y in zip(a, b):
+                assert (np.asarray(x).view(np.uint32) == np.asarray(y).view(np.uint32)).all(), (kind, hb, fused)
+    assert ix.last_overflows > 0
+    ix.close()
+
+
 def test_device_seed_table_recall(eng, port):
     """Seeds from the device pivot table (stand-in for the DVP-tree leaf): recall at the reference's epsilon
     is at least what the restated search reaches from the same seeds, and >= 0.9 on this set."""
