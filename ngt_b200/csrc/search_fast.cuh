@@ -9,18 +9,21 @@
 //   <= 128 seeds, visited hash in a slab of global memory (both on-chip tiers). Everything else runs search_kernel.
 //
 // One CTA (4 warps) per query, persistent grid. Per round:
-//   control  warp 0: merge the previous round's keys (only those within the exploration radius were published),
-//            pop the front of the unchecked set (sorted registers), make the popped node's head-table row
-//            available in shared memory (already there when the pop was predicted -- 63 % of the pops),
-//            stage the row of the node expected next.
-//   filter   one edge per thread from shared memory, one 32-byte bucket read of the visited hash (a single 256-bit
-//            load), compaction of the new ids.
-//   rows     groups of four rows, group g of the round to warp g % 4. A group is copied with cp.async (ids by one
-//            128-bit shared load, then the copies back to back), groups go through a ring of buffers with one
-//            cp.async group each, so copies of later groups are in flight while a group is evaluated. Distances:
-//            eight lanes per row, four rows per step (same summation order as every other kernel: chunk c on
-//            lane c mod 32 of group_fold<ACC, 32>), the scalar tail (sqrt, key, publish) once per eight steps with
-//            one row per lane.
+//   control  warp 0 (its state lives in shared memory between rounds): merge the previous round's keys (only those
+//            within the exploration radius were published), pop the front of the unchecked set (sorted registers),
+//            make the popped node's head-table row available in shared memory (already there when the pop was
+//            predicted -- 63 % of the pops), stage the row of the node expected next.
+//   filter   edges dealt round-robin to the warps, one per thread, from shared memory; one 32-byte bucket read of the
+//            visited hash (a single 256-bit load); every warp keeps the new ids of its own edges (no CTA-wide
+//            compaction) and prefetches their rows towards L2.
+//   rows     every warp copies and evaluates its own new ids in groups of four rows. A group is copied with cp.async
+//            (ids by one 128-bit shared load, then the copies back to back, L2 evict-first), groups go through a ring
+//            of buffers with one cp.async group each, so copies of later groups are in flight while a group is
+//            evaluated. Distances: eight lanes per row, four rows per step, packed FADD2 / FFMA2 (same summation
+//            order as every other kernel: chunk c on lane c mod 32 of group_fold<ACC, 32>), the scalar tail (sqrt,
+//            key, publish) once per eight steps with one row per lane.
+// Without a seed list the seeds are the nearest pivots of the seed table: from seed_select_kernel (below), or selected
+// by this kernel itself when seed fusion is switched on.
 #pragma once
 #include "search.cuh"
 
