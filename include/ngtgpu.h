@@ -87,6 +87,9 @@ int ngtgpu_index_build_seed_table(ngtgpu_index *index, uint32_t n_pivots, uint64
 /* The same with pivots drawn from ids 1..limit only (0 = all): used while a graph is grown batch by batch
  * (ngtgpu_index_insert_batch), when later ids are not in the graph yet. */
 int ngtgpu_index_build_seed_table_range(ngtgpu_index *index, uint32_t n_pivots, uint64_t rng_seed, uint64_t limit);
+/* An explicit pivot list (host ids). ids 1..seedSize with n_seeds == seedSize in the search calls is the reference's
+ * SeedTypeFixedNodes (lib/NGT/Index.h:1122-1127). */
+int ngtgpu_index_set_seed_table_ids(ngtgpu_index *index, const uint32_t *pivot_ids, uint32_t n_pivots);
 
 uint64_t ngtgpu_index_size(const ngtgpu_index *index);          /* n */
 uint32_t ngtgpu_index_padded_dimension(const ngtgpu_index *index);
@@ -201,7 +204,8 @@ int ngtgpu_graph_adjust_paths(uint64_t n, const uint64_t *row_ptr, const uint32_
  *      searchMultipleQueryForCreation + insertMultipleSearchResults; Index.h:815-837 searchForNNGInsertion;
  *      Graph.h:611-626 insertANNGNode): the stored objects first_id .. first_id+count-1 are searched for in the graph
  *      as it is (size = edge_size_for_creation, epsilon = the creation epsilon, edge_size as in ngtgpu_search_params;
- *      seeds = nearest n_seeds of n_pivots pivots drawn from ids < first_id), each also gets the distances to the
+ *      seeds = nearest n_seeds of n_pivots pivots drawn from ids < first_id; n_pivots == 0: the reference's
+ *      SeedTypeFixedNodes, ids 1..min(n_seeds, first_id - 1), Index.h:1122-1127), each also gets the distances to the
  *      objects before it in the batch, its list is cut to edge_size_for_creation, becomes its edges, and every listed
  *      node gets the reverse edge. DEVICE CSR with distances, updated in place (capacity entries; grows by at most
  *      2 * count * edge_size_for_creation). An empty graph (first batch) only links the batch internally. The index's

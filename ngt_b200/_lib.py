@@ -49,6 +49,7 @@ SYMBOLS = {
     "ngtgpu_index_tensor_core_batches": (C.c_uint64, [_P]),
     "ngtgpu_index_build_seed_table": (C.c_int, [_P, C.c_uint32, C.c_uint64]),
     "ngtgpu_index_build_seed_table_range": (C.c_int, [_P, C.c_uint32, C.c_uint64, C.c_uint64]),
+    "ngtgpu_index_set_seed_table_ids": (C.c_int, [_P, _P, C.c_uint32]),
     "ngtgpu_index_size": (C.c_uint64, [_P]),
     "ngtgpu_index_padded_dimension": (C.c_uint32, [_P]),
     "ngtgpu_index_get_object": (C.c_int, [_P, C.c_uint32, _P]),

@@ -980,7 +980,13 @@ extern "C" int ngtgpu_index_insert_batch(ngtgpu_index *ix, uint32_t first_id, ui
     CUDA_TRY(mem.alloc(&r_dists, (size_t)count * e));
     CUDA_TRY(mem.alloc(&r_counts, count));
     NGTGPU_TRY(ngtgpu_index_set_graph(ix, d_row_ptr, d_col, 1));
-    NGTGPU_TRY(ngtgpu_index_build_seed_table_range(ix, n_pivots, pivot_seed, first_id - 1));
+    if (n_pivots == 0) {   // SeedTypeFixedNodes (Index.h:1122-1127): ids 1..min(seedSize, nodes in the graph)
+      std::vector<uint32_t> fixed(std::min<uint32_t>(n_seeds, first_id - 1));
+      for (uint32_t i = 0; i < fixed.size(); i++) fixed[i] = i + 1;
+      NGTGPU_TRY(ngtgpu_index_set_seed_table_ids(ix, fixed.data(), (uint32_t)fixed.size()));
+    } else {
+      NGTGPU_TRY(ngtgpu_index_build_seed_table_range(ix, n_pivots, pivot_seed, first_id - 1));
+    }
     ngtgpu_search_params sp;
     sp.size = e;
     sp.epsilon = epsilon;

@@ -485,6 +485,20 @@ static inline uint64_t splitmix64(uint64_t &x) {
   return z ^ (z >> 31);
 }
 
+static int install_pivots(ngtgpu_index *ix, const std::vector<uint32_t> &ids) {
+  const uint32_t n_pivots = (uint32_t)ids.size();
+  CUDA_TRY(cudaMalloc(&ix->d_pivot_ids, n_pivots * sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&ix->d_pivot_rows, (size_t)n_pivots * ix->row_bytes));
+  CUDA_TRY(cudaMemcpy(ix->d_pivot_ids, ids.data(), n_pivots * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  gather_pivots_kernel<<<ix->sm_count * 4, 256, 0, ix->stream>>>(ix->d_objects, ix->row_bytes, ix->d_pivot_ids,
+                                                                 n_pivots, ix->d_pivot_rows);
+  ix->launches++;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(ix->stream));
+  ix->n_pivots = n_pivots;
+  return NGTGPU_OK;
+}
+
 extern "C" int ngtgpu_index_build_seed_table(ngtgpu_index *ix, uint32_t n_pivots, uint64_t rng_seed) {
   return ngtgpu_index_build_seed_table_range(ix, n_pivots, rng_seed, 0);
 }
@@ -520,17 +534,22 @@ extern "C" int ngtgpu_index_build_seed_table_range(ngtgpu_index *ix, uint32_t n_
     ids[kept++] = (uint32_t)id;
   }
   if (kept == 0) NGTGPU_FAIL(NGTGPU_ERR_STATE, "ngtgpu_index_build_seed_table: no valid objects");
-  n_pivots = kept;
-  CUDA_TRY(cudaMalloc(&ix->d_pivot_ids, n_pivots * sizeof(uint32_t)));
-  CUDA_TRY(cudaMalloc(&ix->d_pivot_rows, (size_t)n_pivots * ix->row_bytes));
-  CUDA_TRY(cudaMemcpy(ix->d_pivot_ids, ids.data(), n_pivots * sizeof(uint32_t), cudaMemcpyHostToDevice));
-  gather_pivots_kernel<<<ix->sm_count * 4, 256, 0, ix->stream>>>(ix->d_objects, ix->row_bytes, ix->d_pivot_ids,
-                                                                 n_pivots, ix->d_pivot_rows);
-  ix->launches++;
-  CUDA_TRY(cudaGetLastError());
+  ids.resize(kept);
+  return install_pivots(ix, ids);
+}
+
+// An explicit pivot list. ids 1..seedSize is the reference's SeedTypeFixedNodes (lib/NGT/Index.h:1122-1127): with
+// n_seeds == the table size every search starts from exactly those nodes.
+extern "C" int ngtgpu_index_set_seed_table_ids(ngtgpu_index *ix, const uint32_t *pivot_ids, uint32_t n_pivots) {
+  NGTGPU_TRY(ngtgpu_check_device(ix));
+  if (!ix->d_objects || ix->n == 0) NGTGPU_FAIL(NGTGPU_ERR_STATE, "ngtgpu_index_set_seed_table_ids: objects are not set");
+  if (!pivot_ids || n_pivots == 0) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "ngtgpu_index_set_seed_table_ids: empty pivot list");
+  for (uint32_t i = 0; i < n_pivots; i++)
+    if (pivot_ids[i] == 0 || pivot_ids[i] > ix->n)
+      NGTGPU_FAIL(NGTGPU_ERR_INVALID, "ngtgpu_index_set_seed_table_ids: id " + std::to_string(pivot_ids[i]) + " out of range");
   CUDA_TRY(cudaStreamSynchronize(ix->stream));
-  ix->n_pivots = n_pivots;
-  return NGTGPU_OK;
+  free_pivots(ix);
+  return install_pivots(ix, std::vector<uint32_t>(pivot_ids, pivot_ids + n_pivots));
 }
 
 // NeighborhoodGraph::getEdgeSize, lib/NGT/Graph.h:675-692. Returns < 0 for invalid parameters.

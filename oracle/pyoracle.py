@@ -176,6 +176,12 @@ class Ref:
         lib.ref_linear_search.argtypes = [C.c_void_p, _f32p, C.c_size_t, C.c_int, C.c_size_t, C.c_float, _u32p,
                                           _f32p, _u32p, C.c_int, C.POINTER(C.c_double)]
         lib.ref_max_threads.restype = C.c_int
+        lib.ref_build_anng_fixed_seeds.argtypes = [C.c_char_p, _f32p, C.c_size_t, C.c_size_t, C.c_int, C.c_char, C.c_int,
+                                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+        lib.ref_refine_anng.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_int, C.c_size_t]
+        lib.ref_object_distance.restype = C.c_double
+        lib.ref_object_distance.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+        lib.ref_insert_node.argtypes = [C.c_void_p, C.c_uint32, _u32p, _f32p, C.c_size_t]
         lib.ref_tree_seeds.argtypes = [C.c_void_p, _f32p, C.c_size_t, C.c_int, C.c_size_t, _u32p, C.c_size_t, _u32p]
 
     def _check(self, rc):
@@ -191,6 +197,27 @@ class Ref:
         self._check(self.lib.ref_build_index(path.encode(), data, data.shape[0], data.shape[1],
                                              objtype.encode(), disttype, edge_creation, edge_search,
                                              indextype.encode(), threads))
+
+    def build_anng_fixed_seeds(self, path, data, n_first=None, objtype="f", disttype=L2, edge_creation=10,
+                               edge_search=40, seed_size=10, batch_size=200, threads=4):
+        """createIndex's batched loop on a graph-only index with SeedType FixedNodes (deterministic); rows after
+        n_first are inserted into the finished graph by a second createIndex."""
+        data = np.ascontiguousarray(data, np.float32)
+        n = data.shape[0]
+        self._check(self.lib.ref_build_anng_fixed_seeds(path.encode(), data, n, n if n_first is None else n_first,
+                                                        data.shape[1], objtype.encode(), disttype, edge_creation,
+                                                        edge_search, seed_size, batch_size, threads))
+
+    def refine_anng(self, h, epsilon=0.1, accuracy=0.0, no_of_edges=0, explore_edge_size=-2 ** 31, batch_size=10000):
+        self._check(self.lib.ref_refine_anng(h, epsilon, accuracy, no_of_edges, explore_edge_size, batch_size))
+
+    def object_distance(self, h, a, b):
+        return self.lib.ref_object_distance(h, a, b)
+
+    def insert_node(self, h, node_id, ids, dists):
+        ids = np.ascontiguousarray(ids, np.uint32)
+        dists = np.ascontiguousarray(dists, np.float32)
+        self._check(self.lib.ref_insert_node(h, node_id, ids, dists, ids.shape[0]))
 
     def build_onng(self, anng, onng, outgoing=10, incoming=120, shortcut=True):
         self._check(self.lib.ref_build_onng(anng.encode(), onng.encode(), outgoing, incoming, int(shortcut)))
@@ -358,12 +385,18 @@ def refine_anng_loop(port, dtype, otype, pobj, row_ptr, col, dist, seeds, epsilo
     return lists
 
 
+def fixed_node_seeds(n, seed_size):
+    """SeedTypeFixedNodes (lib/NGT/Index.h:1122-1127): every search starts from ids 1..seed_size. [n x seed_size]."""
+    return np.tile(np.arange(1, seed_size + 1, dtype=np.uint32), (n, 1))
+
+
 def build_anng_loop(port, pobj, rows_int, seeds, first_id, count, lists=None, edge_size_for_creation=10, epsilon=0.1,
-                    edge_size=40, batch_size=200):
+                    edge_size=40, batch_size=200, dtype=L2, otype=FLOAT):
     """Sequential restatement of the ANNG construction loop (lib/NGT/Index.cpp:631-719, 721-792; Index.h:815-837;
-    Graph.h:611-626, 845-886) for integer-valued L2 float data, over the C restatement of the search with explicit seeds
-    (seeds[id - 1]); test infrastructure. rows_int: [(n+1) x dim] int64 copy of the objects (row 0 dummy).
-    -> per id 0..n a list of (distance, id) ascending."""
+    Graph.h:611-626, 845-886) over the C restatement of the search with explicit seeds (seeds[id - 1]); test
+    infrastructure. Pinned to the reference's createIndex by tests/golden/anng_build.npz (test_oracle_pin.py).
+    rows_int: [(n+1) x dim] int64 copy of the objects (row 0 dummy) for integer-valued L2 data, or None: the in-batch
+    distances then come from the C restatement of the comparator. -> per id 0..n a list of (distance, id) ascending."""
     import bisect
     n = pobj.shape[0] - 1
     e = edge_size_for_creation
@@ -379,10 +412,10 @@ def build_anng_loop(port, pobj, rows_int, seeds, first_id, count, lists=None, ed
             q = pobj[s:s + len(ids_b)]
             sd = seeds[s - 1:s - 1 + len(ids_b)]
             cap = 2 ** 31 - 1 if edge_size == 0 else edge_size
-            r_ids, r_d, r_cnt, _ = port.graph_search(L2, FLOAT, pobj, rp, cc, q, sd, e, epsilon, edge_size=cap)
+            r_ids, r_d, r_cnt, _ = port.graph_search(dtype, otype, pobj, rp, cc, q, sd, e, epsilon, edge_size=cap)
             short = [x for x in range(len(ids_b)) if r_cnt[x] < e and r_cnt[x] < s]   # result.size() < repository.size()
             if short and edge_size != 0:                                                    # Index.h:826-836
-                a_ids, a_d, a_cnt, _ = port.graph_search(L2, FLOAT, pobj, rp, cc, q, sd, e, epsilon, edge_size=2 ** 31 - 1)
+                a_ids, a_d, a_cnt, _ = port.graph_search(dtype, otype, pobj, rp, cc, q, sd, e, epsilon, edge_size=2 ** 31 - 1)
                 for x in short:
                     r_ids[x], r_d[x], r_cnt[x] = a_ids[x], a_d[x], a_cnt[x]
             for x in range(len(ids_b)):
@@ -390,8 +423,11 @@ def build_anng_loop(port, pobj, rows_int, seeds, first_id, count, lists=None, ed
         for x, i in enumerate(ids_b):                                                       # insertMultipleSearchResults
             objs = list(res[x])
             for j in ids_b[:x]:
-                d2 = int(((rows_int[i] - rows_int[j]) ** 2).sum())
-                objs.append((float(np.float32(np.sqrt(np.float64(d2)))), j))
+                if rows_int is not None:
+                    d2 = int(((rows_int[i] - rows_int[j]) ** 2).sum())
+                    objs.append((float(np.float32(np.sqrt(np.float64(d2)))), j))
+                else:
+                    objs.append((float(np.float32(port.distance(dtype, otype, pobj[i], pobj[j]))), j))
             objs.sort()
             res[x] = objs[:e]
         for x, i in enumerate(ids_b):                                                       # insertANNGNode

@@ -8,6 +8,7 @@
 // ngt_b200/ links or loads it.
 #include <NGT/Index.h>
 #include <NGT/GraphOptimizer.h>
+#include <NGT/GraphReconstructor.h>
 #include <omp.h>
 #include <chrono>
 #include <cstring>
@@ -241,6 +242,74 @@ int ref_tree_seeds(void *h, const float *queries, size_t nq, int dim, size_t k, 
     nseeds[q] = (uint32_t)sd.size();
     for (size_t i = 0; i < sd.size() && i < max_seeds; i++) seeds[q * max_seeds + i] = sd[i].id;
   }
+  return 0;
+  REF_CATCH(-1)
+}
+
+
+// ---- construction path, made deterministic with the reference's OWN switches only:
+// a graph-only index (Index::createGraph) whose SeedType property is FixedNodes, so every search of the build loop
+// starts from ids 1..seedSize (Index.h:1122-1127) instead of rand() / the growing DVP-tree. createIndex(threads > 1)
+// is the batched loop (Index.cpp:721-792: searchMultipleQueryForCreation on the frozen graph, then
+// insertMultipleSearchResults sorted by batchIdx, then insertNode -> insertANNGNode/addEdge, Graph.h:611-626,845-886);
+// its result does not depend on thread scheduling.
+// The first n_first rows are appended and indexed, then the remaining rows are appended and indexed into the finished
+// graph (incremental insertion through the same loop). n_first == n: one pass.
+int ref_build_anng_fixed_seeds(const char *path, const float *data, size_t n, size_t n_first, int dim, char objtype,
+                               int disttype, int edge_creation, int edge_search, int seed_size, int batch_size,
+                               int threads) {
+  REF_TRY
+  NGT::Property p;
+  p.dimension = dim;
+  p.objectType = objtype == 'c' ? NGT::ObjectSpace::ObjectType::Uint8 : NGT::ObjectSpace::ObjectType::Float;
+  p.distanceType = (NGT::Index::Property::DistanceType)disttype;
+  p.edgeSizeForCreation = edge_creation;
+  p.edgeSizeForSearch = edge_search;
+  p.seedType = NGT::NeighborhoodGraph::SeedTypeFixedNodes;
+  p.seedSize = seed_size;
+  p.batchSizeForCreation = batch_size;
+  NGT::Index::createGraph(path, p, "", 0, true);
+  NGT::Index idx(path);
+  idx.disableLog();
+  if (n_first > n) n_first = n;
+  idx.append(data, n_first);
+  idx.createIndex(threads);
+  if (n_first < n) {
+    idx.append(data + n_first * (size_t)dim, n - n_first);
+    idx.createIndex(threads);
+  }
+  idx.save();
+  return 0;
+  REF_CATCH(-1)
+}
+
+// GraphReconstructor::refineANNG (GraphReconstructor.h:814-924) on an open writable index; searches take the
+// index's own seeds (FixedNodes for indexes made by ref_build_anng_fixed_seeds), so the result is deterministic.
+int ref_refine_anng(void *h, float epsilon, float accuracy, int no_of_edges, int explore_edge_size, size_t batch_size) {
+  REF_TRY
+  NGT::Index &idx = *static_cast<NGT::Index *>(h);
+  NGT::GraphReconstructor::refineANNG(idx, epsilon, accuracy, no_of_edges, explore_edge_size, batch_size);
+  return 0;
+  REF_CATCH(-1)
+}
+
+// insertMultipleSearchResults's in-batch step in isolation cannot be reached (file-static, Index.cpp:670), but its
+// two halves can: the comparator the step calls (ObjectSpace::getComparator()(a, b)) on two stored objects ...
+double ref_object_distance(void *h, uint32_t a, uint32_t b) {
+  REF_TRY
+  NGT::Index &idx = *static_cast<NGT::Index *>(h);
+  NGT::ObjectSpace &os = idx.getObjectSpace();
+  return os.getComparator()(*os.getRepository().get(a), *os.getRepository().get(b));
+  REF_CATCH(-1.0)
+}
+// ... and insertNode (GraphIndex::insertNode -> insertANNGNode, Graph.h:611-626) with a caller-given result list.
+int ref_insert_node(void *h, uint32_t id, const uint32_t *ids, const float *dists, size_t count) {
+  REF_TRY
+  NGT::Index &idx = *static_cast<NGT::Index *>(h);
+  NGT::GraphIndex &g = static_cast<NGT::GraphIndex &>(idx.getIndex());
+  NGT::ObjectDistances r;
+  for (size_t i = 0; i < count; i++) r.push_back(NGT::ObjectDistance(ids[i], dists[i]));
+  g.insertNode(id, r);
   return 0;
   REF_CATCH(-1)
 }

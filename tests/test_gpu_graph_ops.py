@@ -177,3 +177,63 @@ def test_anng_construction_loop_equals_the_sequential_restatement(eng, port, bat
     r = ix.search(base[:200], 3, 0.1, edge_size=0)
     assert (r[0][:, 0] == np.arange(1, 201)).mean() >= 0.9
     ix.close()
+
+
+# ---- the construction path against graphs the UNMODIFIED reference built (tests/golden/anng_build.npz,
+# refine_anng.npz; generator make_golden_anng.py): NGT::Index::createIndex's batched loop and refineANNG with the
+# reference's SeedTypeFixedNodes, i.e. every search starts from ids 1..seedSize
+def _set_fixed_seeds(ix, seed_size):
+    import ctypes as C
+    from ngt_b200 import _lib
+    lib = _lib.load()
+    lib.ngtgpu_index_set_seed_table_ids.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+    ids = np.arange(1, seed_size + 1, dtype=np.uint32)
+    _lib.check(lib.ngtgpu_index_set_seed_table_ids(ix._h, ids.ctypes.data, seed_size))
+
+
+@pytest.mark.parametrize("tag", ["f_b200", "f_b64_all", "f_b1000_s5", "u8_b200"])
+def test_anng_construction_loop_equals_the_reference(eng, tag):
+    """ngtgpu_index_insert_batch == createIndex of the reference (Index.cpp:631-719,721-792; Index.h:815-837;
+    Graph.h:611-626,845-886), edge for edge with distance bits: build, then insertion into the built graph."""
+    from test_oracle_pin import anng_case
+    from ngt_b200 import build
+    c = anng_case(np.load(os.path.join(GOLDEN, "anng_build.npz")), tag)
+    base = c["base"].astype(np.uint8) if c["otype"] == po.UINT8 else c["base"]
+    ix = eng.GpuIndex(c["otype"], po.L2, base.shape[1])
+    ix.set_objects(base)
+    ix.set_search_property(c["es"], 30, 20)
+    g = build.insert_objects(ix, 1, c["n_first"], None, c["e"], 0.1, -1, c["bs"], c["ss"], 0, 0)
+    if c["n_first"] < c["n"]:
+        g = build.insert_objects(ix, c["n_first"] + 1, c["n"] - c["n_first"], g, c["e"], 0.1, -1, c["bs"], c["ss"], 0, 0)
+    got = _lists(g[0].cpu().numpy(), g[1].cpu().numpy().astype(np.uint32), g[2].cpu().numpy())
+    assert got == c["lists"]
+    ix.close()
+
+
+@pytest.mark.parametrize("tag", ["r0_all", "r0_b400", "r12_b500", "rm6_all", "u8_r0_b500"])
+def test_refine_anng_equals_the_reference(eng, tag):
+    """ngtgpu_index_refine_anng == GraphReconstructor::refineANNG of the reference (GraphReconstructor.h:814-924)."""
+    import torch
+    from test_oracle_pin import anng_case
+    from ngt_b200 import build
+    zb = np.load(os.path.join(GOLDEN, "anng_build.npz"))
+    zr = np.load(os.path.join(GOLDEN, "refine_anng.npz"))
+    src = str(zr[tag + "_src"][0])
+    c = anng_case(zb, src)
+    noe, explore, bs = [int(v) for v in zr[tag + "_meta"]]
+    n = c["n"]
+    base = c["base"].astype(np.uint8) if c["otype"] == po.UINT8 else c["base"]
+    ix = eng.GpuIndex(c["otype"], po.L2, base.shape[1])
+    ix.set_objects(base)
+    ix.set_search_property(c["es"], 30, 20)
+    dev = torch.device("cuda", 0)
+    rp = torch.from_numpy(zb[src + "_row_ptr"][:n + 2].astype(np.int64)).to(dev)
+    col = torch.from_numpy(zb[src + "_col"].astype(np.int32)).to(dev)
+    dist = torch.from_numpy(zb[src + "_dist"]).to(dev)
+    ix.set_graph(rp, col)
+    _set_fixed_seeds(ix, c["ss"])
+    out = build.refine_anng(ix, rp, col, dist, epsilon=float(zr[tag + "_eps"][0]), no_of_edges=noe, edge_size=-1, batch_size=bs,
+                            edge_size_for_creation=c["e"], n_seeds=c["ss"])
+    got = _lists(out[0].cpu().numpy(), out[1].cpu().numpy().astype(np.uint32), out[2].cpu().numpy())
+    assert got == _lists(zr[tag + "_row_ptr"], zr[tag + "_col"], zr[tag + "_dist"])[:n + 1]
+    ix.close()

@@ -150,3 +150,55 @@ def test_adjust_paths_restatement_matches_the_reference():
             for nid in range(len(arp) - 1):
                 ref = [(float(adist[e]), int(acol[e])) for e in range(int(arp[nid]), int(arp[nid + 1]))]
                 assert ref == out[nid], (k, nid)
+
+
+# ---- construction path: the sequential restatements in oracle/pyoracle.py against graphs
+# the UNMODIFIED reference built (tests/golden/make_golden_anng.py: createIndex's batched loop and refineANNG on a
+# graph-only index with SeedType FixedNodes, the reference's own deterministic seed mode)
+def _lists(rp, col, dist):
+    rp = np.asarray(rp, np.int64)
+    return [[(float(dist[e]), int(col[e])) for e in range(int(rp[i]), int(rp[i + 1]))] for i in range(len(rp) - 1)]
+
+
+def anng_case(z, tag):
+    from ngt_b200 import synth
+    objtype, n, n_first, seed, e, es, ss, bs = [int(v) for v in z[tag + "_meta"]]
+    base = synth.make("sift", n, seed)
+    otype = po.UINT8 if chr(objtype) == "c" else po.FLOAT
+    return dict(base=base, otype=otype, n=n, n_first=n_first, e=e, es=es, ss=ss, bs=bs,
+                lists=_lists(z[tag + "_row_ptr"], z[tag + "_col"], z[tag + "_dist"])[:n + 1])
+
+
+@pytest.mark.parametrize("tag", ["f_b200", "f_b64_all", "f_b1000_s5", "u8_b200"])
+def test_anng_build_loop_restatement_equals_the_reference(port, tag):
+    """Index.cpp:631-719,721-792 + Index.h:815-837 + Graph.h:611-626,845-886: build, then insertion into the built
+    graph, edge for edge (ids and float bits) against NGT::Index::createIndex of the reference."""
+    c = anng_case(np.load(os.path.join(GOLDEN, "anng_build.npz")), tag)
+    pobj = po.pad_objects(c["base"], c["otype"])
+    seeds = po.fixed_node_seeds(c["n"], c["ss"])
+    rows_int = np.vstack([np.zeros((1, c["base"].shape[1]), np.int64), c["base"].astype(np.int64)])
+    # the uint8 case takes the in-batch distances from the C restatement of the comparator instead
+    ri = rows_int if c["otype"] == po.FLOAT else None
+    got = po.build_anng_loop(port, pobj, ri, seeds, 1, c["n_first"], None, c["e"], 0.1, c["es"], c["bs"], po.L2, c["otype"])
+    if c["n_first"] < c["n"]:
+        got = po.build_anng_loop(port, pobj, ri, seeds, c["n_first"] + 1, c["n"] - c["n_first"], got, c["e"], 0.1, c["es"],
+                                 c["bs"], po.L2, c["otype"])
+    assert got == c["lists"]
+
+
+@pytest.mark.parametrize("tag", ["r0_all", "r0_b400", "r12_b500", "rm6_all", "u8_r0_b500"])
+def test_refine_anng_restatement_equals_the_reference(port, tag):
+    """GraphReconstructor.h:814-924 against GraphReconstructor::refineANNG of the reference (all three noOfEdges modes,
+    several batch sizes)."""
+    zb = np.load(os.path.join(GOLDEN, "anng_build.npz"))
+    zr = np.load(os.path.join(GOLDEN, "refine_anng.npz"))
+    src = str(zr[tag + "_src"][0])
+    c = anng_case(zb, src)
+    noe, explore, bs = [int(v) for v in zr[tag + "_meta"]]
+    eps = float(zr[tag + "_eps"][0])
+    pobj = po.pad_objects(c["base"], c["otype"])
+    seeds = po.fixed_node_seeds(c["n"], c["ss"])
+    n = c["n"]
+    got = po.refine_anng_loop(port, po.L2, c["otype"], pobj, zb[src + "_row_ptr"][:n + 2].astype(np.uint64), zb[src + "_col"],
+                              zb[src + "_dist"], seeds, eps, noe, c["es"] if c["es"] else 2 ** 31 - 1, bs, c["e"])
+    assert got == _lists(zr[tag + "_row_ptr"], zr[tag + "_col"], zr[tag + "_dist"])[:n + 1]
