@@ -96,6 +96,8 @@ uint32_t ngtgpu_index_padded_dimension(const ngtgpu_index *index);
 /* Copies the stored (possibly normalised) object `id` back: ngt_get_object_as_float/_as_integer
  * (lib/NGT/Capi.cpp:750-782). `out` holds `dimension` elements of the object type. */
 int ngtgpu_index_get_object(const ngtgpu_index *index, uint32_t id, void *out);
+/* Objects first .. first+count-1 into `out` (count x dimension elements, packed) with one strided copy. */
+int ngtgpu_index_get_objects(const ngtgpu_index *index, uint32_t first, uint64_t count, void *out);
 
 /* ---- graph beam search: replaces NeighborhoodGraph::search / searchReadOnlyGraph
  *      (lib/NGT/Graph.cpp:398-495, 499-638) behind GraphIndex::search(sc, seeds)
@@ -230,6 +232,11 @@ int ngtgpu_graph_select_edges(uint64_t n, const uint64_t *row_ptr, const uint32_
 int ngtgpu_index_refine_anng(ngtgpu_index *index, float epsilon, int32_t no_of_edges, int64_t edge_size,
                              uint32_t searched_edges, uint64_t batch_size, uint32_t n_seeds, uint64_t capacity,
                              uint64_t *d_row_ptr, uint32_t *d_col, float *d_dist, uint64_t *nnz_out);
+
+/* Index::AccuracyTable::getEpsilon (lib/NGT/Index.h:293-360): the epsilon GraphIndex::search substitutes when a query
+ * carries an expected accuracy (Index.h:1156-1158). table: the `AccuracyTable` line of `prf` ("epsilon:accuracy,...").
+ * Host arithmetic; fails with the reference's messages for a table of two or fewer points or a malformed token. */
+int ngtgpu_epsilon_from_accuracy_table(const char *table, double accuracy, float *epsilon);
 
 /* Number of kernels this library launched since the index was created (bench.py's gpu_launches). */
 uint64_t ngtgpu_index_launch_count(const ngtgpu_index *index);

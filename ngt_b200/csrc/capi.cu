@@ -13,6 +13,7 @@
 #include <climits>
 #include <cstdio>
 #include <cstring>
+#include <filesystem>
 #include <fstream>
 #include <iostream>
 #include <map>
@@ -55,6 +56,57 @@ typedef struct {
   float radius;
   size_t edge_size;
 } NGTQuery;
+
+typedef struct {   // Capi.h:49-58
+  size_t no_of_queries;
+  size_t no_of_results;
+  size_t no_of_threads;
+  float target_accuracy;
+  size_t target_no_of_objects;
+  size_t no_of_sample_objects;
+  size_t max_of_no_of_edges;
+  bool log;
+} NGTAnngEdgeOptimizationParameter;
+
+// Index::AccuracyTable (lib/NGT/Index.h:293-360): `table` is "epsilon:accuracy,..." as the optimizer's tuning wrote it
+// into `prf` (GraphOptimizer.h:355-365); getEpsilon interpolates linearly between the two entries around the asked
+// accuracy (the last two when it is above the table) and clamps at -0.9. Host arithmetic only.
+extern "C" int ngtgpu_epsilon_from_accuracy_table(const char *table_string, double accuracy, float *epsilon) {
+  if (!table_string || !epsilon) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "ngtgpu_epsilon_from_accuracy_table: null argument");
+  std::vector<std::pair<float, double>> table;
+  const std::string str(table_string);
+  std::vector<std::string> tokens;
+  {
+    std::stringstream ss(str);
+    std::string tok;
+    while (std::getline(ss, tok, ','))
+      if (!tok.empty()) tokens.push_back(tok);
+  }
+  if (tokens.size() >= 2) {   // fewer than two tokens: the table stays empty (Index.h:303-305)
+    for (auto &t : tokens) {
+      const size_t c = t.find(':');
+      if (c == std::string::npos || t.find(':', c + 1) != std::string::npos)
+        NGTGPU_FAIL(NGTGPU_ERR_INVALID, "AccuracyTable: Invalid accuracy table string " + t + ":" + str);
+      table.push_back(std::make_pair((float)strtod(t.substr(0, c).c_str(), nullptr), strtod(t.substr(c + 1).c_str(), nullptr)));
+    }
+  }
+  if (table.size() <= 2)
+    NGTGPU_FAIL(NGTGPU_ERR_STATE, "AccuracyTable: The accuracy table is not set yet. The table size=" + std::to_string(table.size()));
+  if (accuracy > 1.0) accuracy = 1.0;
+  size_t i = 0;
+  for (; i < table.size(); ++i)
+    if (table[i].second >= accuracy) break;
+  if (i == table.size()) {
+    i -= 2;
+  } else if (i != 0) {
+    i--;
+  }
+  const std::pair<float, double> lower = table[i], upper = table[i + 1];
+  float e = lower.first + (upper.first - lower.first) * (accuracy - lower.second) / (upper.second - lower.second);
+  if (e < -0.9) e = -0.9;
+  *epsilon = e;
+  return NGTGPU_OK;
+}
 
 namespace {
 
@@ -174,6 +226,15 @@ long prf_long(CapiIndex &ix, const char *key, long dflt) {
   return std::stol(it->second);
 }
 
+// expectedAccuracy -> epsilon through the `AccuracyTable` line of `prf` (ngtgpu_epsilon_from_accuracy_table below):
+// GraphIndex::search replaces the query's epsilon by it when expectedAccuracy > 0 (Index.h:1156-1158).
+float epsilon_from_expected_accuracy(CapiIndex &ix, double accuracy) {
+  auto it = ix.prf.find("AccuracyTable");
+  float e = 0.f;
+  check(ngtgpu_epsilon_from_accuracy_table(it == ix.prf.end() ? "" : it->second.c_str(), accuracy, &e));
+  return e;
+}
+
 void upload(CapiIndex &ix) {
   const size_t n = ix.n();
   if (!ix.gpu) check(ngtgpu_index_create(&ix.gpu, 0, ix.prop.object_type, ix.prop.distance_type, (uint32_t)ix.prop.dimension));
@@ -282,6 +343,9 @@ ObjectID append_rows(CapiIndex &ix, const float *rows, size_t count, uint32_t di
 void build_graph(CapiIndex &ix) {
   const size_t n = ix.n();
   if (n == 0) return;
+  // createIndex only indexes objects that are not in the graph yet (Index.cpp:645-648): with nothing queued and a
+  // graph in place (loaded ONNG, refined or optimised graph) it is a no-op.
+  if (ix.pending == 0 && ix.row_ptr.size() == n + 2 && !ix.col.empty()) return;
   if (!ix.gpu) check(ngtgpu_index_create(&ix.gpu, 0, ix.prop.object_type, ix.prop.distance_type, (uint32_t)ix.prop.dimension));
   const size_t rb = ix.record_bytes();
   if (ix.raw_from) {
@@ -289,8 +353,7 @@ void build_graph(CapiIndex &ix) {
     ngtgpu_index *tmp = nullptr;
     check(ngtgpu_index_create(&tmp, 0, ix.prop.object_type, ix.prop.distance_type, (uint32_t)ix.prop.dimension));
     int rc = ngtgpu_index_set_objects(tmp, &ix.objects[(ix.raw_from - 1) * rb], n - ix.raw_from + 1, 1, 0);
-    for (size_t id = ix.raw_from; rc == NGTGPU_OK && id <= n; id++)
-      rc = ngtgpu_index_get_object(tmp, (uint32_t)(id - ix.raw_from + 1), &ix.objects[(id - 1) * rb]);
+    if (rc == NGTGPU_OK) rc = ngtgpu_index_get_objects(tmp, 1, n - ix.raw_from + 1, &ix.objects[(ix.raw_from - 1) * rb]);
     ngtgpu_index_destroy(tmp);
     check(rc);
     ix.raw_from = 0;
@@ -522,6 +585,9 @@ bool ngt_save_index(const NGTIndex index, const char *database, NGTError error) 
     const std::string d(database);
     check(ngtgpu_io_write_obj((d + "/obj").c_str(), (uint32_t)ix.record_bytes(), ix.objects.data(), ix.n(), ix.present.data()));
     check(ngtgpu_io_write_grp((d + "/grp").c_str(), ix.n(), ix.row_ptr.data(), ix.col.data(), ix.dist.data(), ix.present.data()));
+    // `prf` now says IndexType Graph: a DVP-tree file left by the reference in this directory would describe another
+    // object set, so it goes (the reference opens Graph indexes without one, Index.cpp:93-111)
+    ::unlink((d + "/tre").c_str());
   }
   CAPI_CATCH(false)
   return true;
@@ -615,10 +681,11 @@ bool ngt_search_index_with_query(NGTIndex index, NGTQuery query, NGTObjectDistan
   }
   try {
     CapiIndex &ix = *static_cast<CapiIndex *>(index);
-    if (query.accuracy > 0.0f) throw std::runtime_error("expected accuracy needs the AccuracyTable of the index; it is not supported by this engine, use epsilon");
     float radius = query.radius < 0.0 ? FLT_MAX : query.radius;
     int64_t es = query.edge_size == (size_t)INT_MIN ? -1 : (int64_t)(int)query.edge_size;
-    search_one(ix, query.query, ix.prop.dimension, query.size, query.epsilon, radius, es, results);
+    // Capi.cpp:346-375 passes query.accuracy as the expected accuracy; Index.h:1156-1158 turns it into epsilon
+    const float eps = query.accuracy > 0.0f ? epsilon_from_expected_accuracy(ix, query.accuracy) : query.epsilon;
+    search_one(ix, query.query, ix.prop.dimension, query.size, eps, radius, es, results);
   }
   CAPI_CATCH(false)
   return true;
@@ -692,6 +759,47 @@ bool ngt_batch_linear_search_index_as_float(NGTIndex index, const float *queries
     if (query_dim != ix.prop.dimension) throw std::runtime_error("ObjectSpace::allocateObject: the specified dimension is invalid");
     if (!ix.gpu || ix.n() == 0) throw std::runtime_error("the index holds no objects");
     check(ngtgpu_linear_search(ix.gpu, queries, NGTGPU_OBJECT_FLOAT, nq, (uint32_t)size, radius, ids, dists, counts));
+  }
+  CAPI_CATCH(false)
+  return true;
+}
+
+// uint8 twins: the queries are already bytes, as the objects of an Integer-1 index are stored
+bool ngt_batch_search_index_as_uint8(NGTIndex index, const uint8_t *queries, uint32_t nq, int32_t query_dim, size_t size,
+                                     float epsilon, float radius, int64_t edge_size, uint32_t *ids, float *dists,
+                                     uint32_t *counts, NGTError error) {
+  if (index == NULL || queries == NULL || ids == NULL || dists == NULL || counts == NULL || query_dim <= 0) {
+    std::stringstream ss;
+    ss << "Capi : " << __FUNCTION__ << "() : parametor error: index = " << index << " queries = " << (const void *)queries;
+    operate_error_string(ss, error);
+    return false;
+  }
+  try {
+    CapiIndex &ix = *static_cast<CapiIndex *>(index);
+    if (query_dim != ix.prop.dimension) throw std::runtime_error("ObjectSpace::allocateObject: the specified dimension is invalid");
+    if (ix.prop.object_type != NGTGPU_OBJECT_UINT8) throw std::runtime_error("the object type of the index is not integer (uint8)");
+    require_built(ix);
+    ngtgpu_search_params p = {(uint32_t)size, epsilon, radius, edge_size};
+    uint32_t seeds = (uint32_t)prf_long(ix, "SeedSize", 10);
+    check(ngtgpu_search(ix.gpu, queries, NGTGPU_OBJECT_UINT8, nq, &p, nullptr, seeds ? seeds : 10, ids, dists, counts, nullptr));
+  }
+  CAPI_CATCH(false)
+  return true;
+}
+bool ngt_batch_linear_search_index_as_uint8(NGTIndex index, const uint8_t *queries, uint32_t nq, int32_t query_dim, size_t size,
+                                            float radius, uint32_t *ids, float *dists, uint32_t *counts, NGTError error) {
+  if (index == NULL || queries == NULL || ids == NULL || dists == NULL || counts == NULL || query_dim <= 0) {
+    std::stringstream ss;
+    ss << "Capi : " << __FUNCTION__ << "() : parametor error: index = " << index << " queries = " << (const void *)queries;
+    operate_error_string(ss, error);
+    return false;
+  }
+  try {
+    CapiIndex &ix = *static_cast<CapiIndex *>(index);
+    if (query_dim != ix.prop.dimension) throw std::runtime_error("ObjectSpace::allocateObject: the specified dimension is invalid");
+    if (ix.prop.object_type != NGTGPU_OBJECT_UINT8) throw std::runtime_error("the object type of the index is not integer (uint8)");
+    if (!ix.gpu || ix.n() == 0) throw std::runtime_error("the index holds no objects");
+    check(ngtgpu_linear_search(ix.gpu, queries, NGTGPU_OBJECT_UINT8, nq, (uint32_t)size, radius, ids, dists, counts));
   }
   CAPI_CATCH(false)
   return true;
@@ -784,11 +892,14 @@ bool ngt_remove_index(NGTIndex index, ObjectID id, NGTError error) {
     CapiIndex &ix = *static_cast<CapiIndex *>(index);
     if (id == 0 || id > ix.n() || !ix.present[id]) throw std::runtime_error("remove: the specified object does not exist. ID=" + std::to_string(id));
     ix.present[id] = 0;
-    if (ix.row_ptr.size() == ix.n() + 2) {
-      std::vector<uint64_t> rp(ix.n() + 2, 0);
+    // the graph covers ids 1..n_graph (= n when nothing is queued; the objects appended since the last build are not in
+    // it yet): the node and every edge to it go, whether or not objects are pending
+    if (ix.row_ptr.size() >= 2 && ix.row_ptr.size() <= ix.n() + 2) {
+      const size_t n_graph = ix.row_ptr.size() - 2;
+      std::vector<uint64_t> rp(n_graph + 2, 0);
       std::vector<uint32_t> col;
       std::vector<float> dist;
-      for (size_t s = 1; s <= ix.n(); s++) {
+      for (size_t s = 1; s <= n_graph; s++) {
         rp[s] = col.size();
         if (s != id)
           for (uint64_t e = ix.row_ptr[s]; e < ix.row_ptr[s + 1]; e++)
@@ -797,7 +908,7 @@ bool ngt_remove_index(NGTIndex index, ObjectID id, NGTError error) {
               dist.push_back(ix.dist[e]);
             }
       }
-      rp[ix.n() + 1] = col.size();
+      rp[n_graph + 1] = col.size();
       ix.row_ptr.swap(rp);
       ix.col.swap(col);
       ix.dist.swap(dist);
@@ -925,8 +1036,11 @@ struct CapiOptimizer {   // the settings of NGT::GraphOptimizer the C API reache
 // repeated timed searches on the host) is outside the hot path and is not run: `prf` keeps its search parameters.
 void optimizer_execute(const CapiOptimizer &o, const std::string &in, const std::string &out) {
   if (access(out.c_str(), 0) == 0) throw std::runtime_error("Optimizer::execute: The specified index exists. " + out);
-  const std::string com = "cp -r " + in + " " + out;
-  if (system(com.c_str()) != 0) throw std::runtime_error("Optimizer::execute: Cannot create the specified index. " + out);
+  {   // GraphOptimizer.h:244-248 shells out to `cp -r`; same effect without a shell
+    std::error_code ec;
+    std::filesystem::copy(in, out, std::filesystem::copy_options::recursive, ec);
+    if (ec) throw std::runtime_error("Optimizer::execute: Cannot create the specified index. " + out);
+  }
   CapiIndex ix;
   ix.path = out;
   read_prf(ix);
@@ -984,8 +1098,8 @@ void optimizer_execute(const CapiOptimizer &o, const std::string &in, const std:
 
 extern "C" {
 
-// GraphReconstructor::refineANNG behind Capi.cpp:976-1004. expectedAccuracy > 0 needs the accuracy table the
-// optimizer's tuning writes (Index.h:1147-1149): not available here, refused loudly.
+// GraphReconstructor::refineANNG behind Capi.cpp:976-1004. expectedAccuracy > 0 is turned into epsilon through the
+// index's accuracy table (Index.h:1156-1158); an index without one fails with the reference's message.
 bool ngt_refine_anng(NGTIndex index, float epsilon, float expectedAccuracy, int noOfEdges, int edgeSize, size_t batchSize,
                      NGTError error) {
   if (index == NULL) {
@@ -997,7 +1111,7 @@ bool ngt_refine_anng(NGTIndex index, float epsilon, float expectedAccuracy, int 
   try {
     CapiIndex &ix = *static_cast<CapiIndex *>(index);
     require_built(ix);
-    if (expectedAccuracy > 0.0f) throw std::runtime_error("refineANNG: expected accuracy needs an accuracy table; give epsilon instead");
+    if (expectedAccuracy > 0.0f) epsilon = epsilon_from_expected_accuracy(ix, expectedAccuracy);   // GraphReconstructor.h:843-847
     if (ix.row_ptr.size() != ix.n() + 2) throw std::runtime_error("refineANNG: the index holds no graph");
     const size_t n = ix.n();
     const int ec = ix.prop.edge_size_for_creation;
@@ -1085,5 +1199,31 @@ bool ngt_optimizer_set_processing_modes(NGTOptimizer optimizer, bool searchParam
   return true;
 }
 void ngt_destroy_optimizer(NGTOptimizer optimizer) { delete static_cast<CapiOptimizer *>(optimizer); }
+
+// Capi.cpp:1043-1058: the defaults of GraphOptimizer::ANNGEdgeOptimizationParameter (GraphOptimizer.h:28-36)
+NGTAnngEdgeOptimizationParameter ngt_get_anng_edge_optimization_parameter() {
+  NGTAnngEdgeOptimizationParameter p;
+  p.no_of_queries = 200;
+  p.no_of_results = 50;
+  p.no_of_threads = 16;
+  p.target_accuracy = 0.9f;
+  p.target_no_of_objects = 0;
+  p.no_of_sample_objects = 100000;
+  p.max_of_no_of_edges = 100;
+  p.log = false;
+  return p;
+}
+
+// Capi.cpp:1060-1088 -> GraphOptimizer::optimizeNumberOfEdgesForANNG (GraphOptimizer.h:387-533): a tuner that rebuilds
+// the index on growing samples and extrapolates the edge count from timed host searches. Like the other search-parameter
+// tuners it is outside the hot path; the symbol exists so programs written against Capi.h link, and it fails loudly.
+bool ngt_optimize_number_of_edges(const char *indexPath, NGTAnngEdgeOptimizationParameter parameter, NGTError error) {
+  (void)indexPath;
+  (void)parameter;
+  std::stringstream ss;
+  ss << "Capi : " << __FUNCTION__ << "() : Error: not provided by the B200 engine (edge-number tuning is outside the hot path)";
+  operate_error_string(ss, error);
+  return false;
+}
 
 }  // extern "C"

@@ -462,6 +462,18 @@ extern "C" int ngtgpu_index_get_object(const ngtgpu_index *ix, uint32_t id, void
   return NGTGPU_OK;
 }
 
+// The stored rows of objects first..first+count-1 in ONE strided copy (padded device rows -> packed host rows).
+extern "C" int ngtgpu_index_get_objects(const ngtgpu_index *ix, uint32_t first, uint64_t count, void *out) {
+  if (!ix || !out) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "ngtgpu_index_get_objects: null argument");
+  if (!ix->d_objects || first == 0 || count == 0 || (uint64_t)first + count - 1 > ix->n)
+    NGTGPU_FAIL(NGTGPU_ERR_INVALID, "ngtgpu_index_get_objects: no such objects");
+  CUDA_TRY(cudaSetDevice(ix->device));
+  const size_t width = (size_t)ix->dim * ix->elem_size;
+  CUDA_TRY(cudaMemcpy2D(out, width, ix->d_objects + (size_t)first * ix->row_bytes, ix->row_bytes, width, count,
+                        cudaMemcpyDeviceToHost));
+  return NGTGPU_OK;
+}
+
 // Copies the padded device rows of objects first..first+count-1 (device pointer out) -- used by shards.
 extern "C" const void *ngtgpu_index_device_objects(const ngtgpu_index *ix) { return ix ? ix->d_objects : nullptr; }
 

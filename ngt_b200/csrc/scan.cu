@@ -553,7 +553,9 @@ __global__ void pack_keys_kernel(const uint32_t *__restrict__ ids, const float *
   const uint64_t total = (uint64_t)nq * k;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
     const uint32_t q = (uint32_t)(i / k), r = (uint32_t)(i % k);
-    keys[i] = r < counts[q] ? make_key(dists[i], ids[i] + id_offset) : KEY_NONE;
+    uint32_t c = counts[q];
+    if (c == 0xffffffffu) c = 0;   // a query that outgrew every tier of the device-pointer search: no results, not k zeros
+    keys[i] = r < c ? make_key(dists[i], ids[i] + id_offset) : KEY_NONE;
   }
 }
 

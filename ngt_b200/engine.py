@@ -164,6 +164,12 @@ class GpuIndex:
         _lib.check(self._lib.ngtgpu_index_get_object(self._h, int(object_id), out.ctypes.data))
         return out
 
+    def get_objects(self, first, count):
+        """Stored rows first .. first+count-1, one strided copy."""
+        out = np.zeros((int(count), self.dimension), _np_type(self.object_type))
+        _lib.check(self._lib.ngtgpu_index_get_objects(self._h, int(first), int(count), out.ctypes.data))
+        return out
+
     # ---- the hot path ----------------------------------------------------------------------------
     def search(self, queries, size=10, epsilon=0.1, radius=-1.0, edge_size=-1, seeds=None, n_seeds=10,
                with_stats=False):

@@ -44,6 +44,32 @@ def create(path, dimension, edge_size_for_creation=10, edge_size_for_search=40, 
     index_io.write_graph(path, np.zeros(2, np.uint64), np.zeros(0, np.uint32), np.zeros(0, np.float32))
 
 
+def epsilon_from_accuracy_table(table, accuracy):
+    """Index::AccuracyTable::set + getEpsilon (lib/NGT/Index.h:299-347): "epsilon:accuracy,..." pairs; linear through
+    the two entries around `accuracy` (the last two when it lies above the table, the first two below), clamped at -0.9."""
+    tokens = [t for t in table.split(",") if t]
+    pts = []
+    if len(tokens) >= 2:
+        for tok in tokens:
+            ts = tok.split(":")
+            if len(ts) != 2:
+                raise NgtGpuError(_lib.ERR_INVALID, "AccuracyTable: Invalid accuracy table string %s:%s" % (tok, table))
+            pts.append((float(np.float32(float(ts[0]))), float(ts[1])))
+    if len(pts) <= 2:
+        raise NgtGpuError(_lib.ERR_STATE, "AccuracyTable: The accuracy table is not set yet. The table size=%d" % len(pts))
+    accuracy = min(float(accuracy), 1.0)
+    i = 0
+    while i < len(pts) and pts[i][1] < accuracy:
+        i += 1
+    if i == len(pts):
+        i -= 2
+    elif i != 0:
+        i -= 1
+    lo, up = pts[i], pts[i + 1]
+    e = float(np.float32(lo[0] + (up[0] - lo[0]) * (accuracy - lo[1]) / (up[1] - lo[1])))
+    return max(e, float(np.float32(-0.9)))
+
+
 class Index:
     def __init__(self, path, read_only=False, zero_based_numbering=True, tree_disabled=False, log_disabled=False,
                  device=0, n_pivots=4096):
@@ -63,6 +89,7 @@ class Index:
         row_ptr, col, dist, _ = index_io.read_graph(path)
         self._graph = self._fit_graph(row_ptr, col, dist)
         self._pending = 0                         # appended objects not yet in the graph
+        self._raw_from = None                     # first id whose row is not normalised yet (Normalized* types)
         self._gpu = GpuIndex(self.object_type, self.distance_type, self.dimension, device)
         self._num_dist = 0
         # ngtpy defaults, python/src/ngtpy.cpp:43-48
@@ -90,7 +117,7 @@ class Index:
         removed = np.nonzero(self._present[1:] == 0)[0].astype(np.uint32) + 1
         if removed.size:
             self._gpu.set_removed(removed)
-        rp, col, _ = self._graph
+        rp, col, _ = self._fit_graph(*self._graph)     # objects appended since the last build have no edges yet
         self._gpu.set_graph(rp, col)
         self._gpu.set_search_property(int(self.prop.get("EdgeSizeForSearch", 40)),
                                       int(self.prop.get("DynamicEdgeSizeBase", 30)),
@@ -102,17 +129,7 @@ class Index:
 
     def _epsilon_from_accuracy(self, accuracy):
         """Index::getEpsilonFromExpectedAccuracy (lib/NGT/Index.h:293-360): piecewise-linear table in prf."""
-        table = self.prop.get("AccuracyTable", "")
-        pts = []
-        for tok in table.split(","):
-            if ":" in tok:
-                e, a = tok.split(":")
-                pts.append((float(e), float(a)))
-        if not pts:
-            raise NgtGpuError(_lib.ERR_STATE, "expected_accuracy needs an AccuracyTable in the index property")
-        eps = np.array([p[0] for p in pts])
-        acc = np.array([p[1] for p in pts])
-        return float(np.interp(accuracy, acc, eps))
+        return epsilon_from_accuracy_table(self.prop.get("AccuracyTable", ""), accuracy)
 
     def _params(self, size, epsilon, edge_size, expected_accuracy):
         size = self.default_size if size == 0 else int(size)
@@ -205,7 +222,7 @@ class Index:
         self._objects = np.concatenate([self._objects, x.astype(self._dtype)], axis=0)
         self._present = np.concatenate([self._present, np.ones(x.shape[0], np.uint8)])
         self._pending += x.shape[0]
-        self._raw_from = min(getattr(self, "_raw_from", first), first)
+        self._raw_from = first if self._raw_from is None else min(self._raw_from, first)
         return first
 
     def insert(self, object, debug=False):
@@ -219,23 +236,28 @@ class Index:
         self._num_dist = 0
 
     def build_index(self, num_threads=8, target_size_of_graph=0):
-        """NGT::Index::createIndex: (re)builds the graph over all present objects. The reference inserts
+        """NGT::Index::createIndex. An index without a graph gets one over all present objects: the reference inserts
         object by object with approximate searches (lib/NGT/Index.cpp:721-792); here the edge candidates of
         every node come from one exact kNN pass on the device and the ANNG is its symmetric closure
         (out-edges + reverse edges, sorted by (distance,id)) -- what insertANNGNode converges to
-        (lib/NGT/Graph.h:611-626)."""
+        (lib/NGT/Graph.h:611-626). Objects appended to an index that already has its graph (loaded ONNG, refined or
+        optimised graph included) are INSERTED into it with the reference's construction loop on the device
+        (ngtgpu_index_insert_batch), as ngt_create_index of the C API does; with nothing queued it is a no-op
+        (createIndex only indexes objects that are not in the graph yet, Index.cpp:645-648)."""
         import torch
         n = self._objects.shape[0]
         if n == 0:
             return
-        normalize = self.distance_type in NORMALIZED and getattr(self, "_raw_from", None) is not None
+        have_graph = self._graph[1].size > 0
+        if self._pending == 0 and have_graph:
+            return
+        normalize = self.distance_type in NORMALIZED and self._raw_from is not None
         if normalize:
             # normalise only the newly appended rows; stored rows are already unit length
             first = self._raw_from
             tmp = GpuIndex(self.object_type, self.distance_type, self.dimension, self.device)
             tmp.set_objects(self._objects[first - 1:], normalize=True)
-            for i in range(first, n + 1):
-                self._objects[i - 1] = tmp.get_object(i - first + 1)
+            self._objects[first - 1:] = tmp.get_objects(1, n - first + 1)
             tmp.close()
         self._raw_from = None
         self._gpu.set_objects(self._objects, normalize=False)
@@ -243,6 +265,25 @@ class Index:
         if removed.size:
             self._gpu.set_removed(removed)
         e = int(self.prop.get("EdgeSizeForCreation", 10))
+        if have_graph and 0 < self._pending < n:
+            dev = torch.device("cuda", self.device)
+            n_old = n - self._pending
+            rp, col, dist = self._graph
+            rp_new = np.full(n + 2, rp[n_old + 1], np.int64)
+            rp_new[:n_old + 2] = rp[:n_old + 2].astype(np.int64)
+            g = (torch.from_numpy(rp_new).to(dev), torch.from_numpy(col.astype(np.int32)).to(dev),
+                 torch.from_numpy(np.asarray(dist, np.float32)).to(dev))
+            self._gpu.set_search_property(int(self.prop.get("EdgeSizeForSearch", 40)),
+                                          int(self.prop.get("DynamicEdgeSizeBase", 30)),
+                                          int(self.prop.get("DynamicEdgeSizeRate", 20)))
+            g = build.insert_objects(self._gpu, n_old + 1, self._pending, g, max(e, 1),
+                                     float(self.prop.get("EpsilonForCreation", 0.1)), -1,
+                                     max(int(self.prop.get("BatchSizeForCreation", 200)), 1), 10, 1024, 1)
+            torch.cuda.synchronize()
+            self._graph = (g[0].cpu().numpy().astype(np.uint64), g[1].cpu().numpy().astype(np.uint32), g[2].cpu().numpy())
+            self._pending = 0
+            self._gpu.build_seed_table(min(self.n_pivots, n), 1)
+            return
         k = min(e, max(n - 1 - removed.size, 1))
         ids, dists, counts = build.knn_graph(self._gpu, k)
         row_ptr, col, dist = build.reconstruct_graph(ids, dists, counts, k, k)
@@ -265,8 +306,8 @@ class Index:
         import torch
         if self._pending:
             raise NgtGpuError(_lib.ERR_STATE, "objects were appended: call build_index() first")
-        if expected_accuracy > 0.0:
-            raise NgtGpuError(_lib.ERR_INVALID, "refine_anng: expected accuracy needs an accuracy table; give epsilon")
+        if expected_accuracy > 0.0:     # GraphReconstructor.h:843-847 -> Index.h:1156-1158
+            epsilon = self._epsilon_from_accuracy(expected_accuracy)
         dev = torch.device("cuda", self.device)
         rp, col, dist = self._graph
         g = build.refine_anng(self._gpu, torch.from_numpy(rp.astype(np.int64)).to(dev),
@@ -296,6 +337,8 @@ class Index:
             raise NgtGpuError(_lib.ERR_STATE, "objects were appended: call build_index() before save()")
         self.prop["IndexType"] = "Graph"      # no `tre` is written; the reference opens Graph indexes without one
         index_io.write_prf(self.path, self.prop)
+        if os.path.exists(os.path.join(self.path, "tre")):   # a DVP-tree the reference left here describes another object set
+            os.remove(os.path.join(self.path, "tre"))
         index_io.write_objects(self.path, self._objects, self._present)
         rp, col, dist = self._graph
         index_io.write_graph(self.path, rp, col, dist, self._present)

@@ -182,6 +182,8 @@ class Ref:
         lib.ref_object_distance.restype = C.c_double
         lib.ref_object_distance.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
         lib.ref_insert_node.argtypes = [C.c_void_p, C.c_uint32, _u32p, _f32p, C.c_size_t]
+        lib.ref_epsilon_from_accuracy_table.restype = C.c_float
+        lib.ref_epsilon_from_accuracy_table.argtypes = [C.c_char_p, C.c_double]
         lib.ref_tree_seeds.argtypes = [C.c_void_p, _f32p, C.c_size_t, C.c_int, C.c_size_t, _u32p, C.c_size_t, _u32p]
 
     def _check(self, rc):
@@ -210,6 +212,12 @@ class Ref:
 
     def refine_anng(self, h, epsilon=0.1, accuracy=0.0, no_of_edges=0, explore_edge_size=-2 ** 31, batch_size=10000):
         self._check(self.lib.ref_refine_anng(h, epsilon, accuracy, no_of_edges, explore_edge_size, batch_size))
+
+    def epsilon_from_accuracy_table(self, table, accuracy):
+        e = self.lib.ref_epsilon_from_accuracy_table(table.encode(), accuracy)
+        if e != e:
+            raise RuntimeError(self.lib.ref_last_error().decode())
+        return e
 
     def object_distance(self, h, a, b):
         return self.lib.ref_object_distance(h, a, b)

@@ -11,6 +11,7 @@
 #include <NGT/GraphReconstructor.h>
 #include <omp.h>
 #include <chrono>
+#include <cmath>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -312,6 +313,15 @@ int ref_insert_node(void *h, uint32_t id, const uint32_t *ids, const float *dist
   g.insertNode(id, r);
   return 0;
   REF_CATCH(-1)
+}
+
+// Index::AccuracyTable (Index.h:293-360): set(string) + getEpsilon(accuracy), standalone (what GraphIndex::search
+// applies when expectedAccuracy > 0, Index.h:1156-1158). Returns NaN and sets the error text when the table throws.
+float ref_epsilon_from_accuracy_table(const char *table, double accuracy) {
+  REF_TRY
+  NGT::Index::AccuracyTable t{std::string(table)};
+  return t.getEpsilon(accuracy);
+  REF_CATCH(std::nanf(""))
 }
 
 int ref_max_threads() { return omp_get_max_threads(); }

@@ -225,3 +225,154 @@ def test_insert_into_a_built_index_is_incremental(lib):
     lib.ngt_close_index(ix)
     lib.ngt_destroy_property(prop)
     lib.ngt_destroy_error_object(err)
+
+
+def test_reference_base_py_runs_on_libngtgpu(tmp_path):
+    """The reference's ctypes binding (python/ngt/base.py, UNMODIFIED) with libngtgpu.so standing where libngt.so would:
+    create -> insert_blob -> build -> search -> get_object -> remove -> save -> reopen, answers checked against numpy."""
+    from ngt_b200 import _lib, synth
+    mod = capi.load_reference_base_py(_lib.SO_PATH)
+    if mod is None:
+        pytest.skip("no copy of the reference's python/ngt/base.py on this box")
+    path = str(tmp_path / "idx").encode()
+    base = synth.make("sift", 1200, 3)
+    index = mod.Index.create(path, 128, edge_size_for_creation=12)
+    index.insert_blob(base.tolist())
+    q = synth.make("sift", 3, 4)
+    d = np.linalg.norm(base.astype(np.float64) - q[0].astype(np.float64), axis=1)
+    exact = (np.argsort(d, kind="stable")[:5] + 1).tolist()
+    res = index.search(q[0].tolist(), 5, 0.3)
+    assert [o.id for o in res] == exact
+    assert [np.float32(o.distance) for o in res] == [np.float32(x) for x in np.sqrt((d[np.array(exact) - 1] ** 2))]
+    assert index.get_object(17) == base[16].tolist()
+    new_id = index.insert_object(q[1].tolist())            # ngt_insert_index (double*), then ngt_create_index
+    assert new_id == 1201
+    index.build_index()
+    assert index.search(q[1].tolist(), 1, 0.1)[0].id == 1201
+    index.remove(exact[0])
+    assert exact[0] not in [o.id for o in index.search(q[0].tolist(), 5, 0.3)]
+    with pytest.raises(mod.NativeError):
+        index.get_object(exact[0])
+    index.save()
+    again = mod.Index(path)
+    assert [o.id for o in again.search(q[0].tolist(), 4, 0.3)] == exact[1:]
+    del again, index
+
+
+def test_expected_accuracy_search_uses_the_accuracy_table(lib, sift5k, tmp_path):
+    """NGTQuery.accuracy > 0 (Capi.cpp:346-375 -> Index.h:1156-1158): epsilon comes from the AccuracyTable of `prf`; the
+    answers equal a search with the epsilon the REFERENCE derives from the same table (tests/golden/accuracy_table.json).
+    An index without a table fails with the reference's message."""
+    import shutil
+    tab = json.load(open(os.path.join(GOLDEN, "accuracy_table.json")))
+    src = os.path.join(GOLDEN, "idx200")
+    dst = str(tmp_path / "idx200_acc")
+    shutil.copytree(src, dst)
+    lines = open(os.path.join(dst, "prf")).read().splitlines()
+    open(os.path.join(dst, "prf"), "w").write("\n".join(("AccuracyTable\t" + tab["table"]) if l.startswith("AccuracyTable") else l
+                                                       for l in lines) + "\n")
+    err = lib.ngt_create_error_object()
+    ix = lib.ngt_open_index(dst.encode(), err)
+    assert ix, lib.ngt_get_error_string(err)
+    q = np.ascontiguousarray(sift5k["queries"][0].astype(np.float32))
+    r = lib.ngt_create_empty_results(err)
+    for acc, eps in tab["cases"]:
+        if acc < 0.5:
+            continue
+        nq = capi.Query(capi.fptr(q), 10, 9.0, acc, -1.0, C.c_size_t(-2**31 & (2**64 - 1)))    # epsilon 9.0 must be ignored
+        assert lib.ngt_search_index_with_query(ix, nq, r, err), lib.ngt_get_error_string(err)
+        with_acc = capi.results_of(lib, r, err)
+        ne = capi.Query(capi.fptr(q), 10, eps, 0.0, -1.0, C.c_size_t(-2**31 & (2**64 - 1)))
+        assert lib.ngt_search_index_with_query(ix, ne, r, err)
+        assert with_acc == capi.results_of(lib, r, err) and len(with_acc) == 10, acc
+    lib.ngt_close_index(ix)
+    plain = lib.ngt_open_index(src.encode(), err)
+    nq = capi.Query(capi.fptr(q), 10, 0.1, 0.9, -1.0, C.c_size_t(-2**31 & (2**64 - 1)))
+    assert lib.ngt_search_index_with_query(plain, nq, r, err) is False
+    assert lib.ngt_get_error_string(err).decode() == \
+        "Capi : ngt_search_index_with_query() : Error: AccuracyTable: The accuracy table is not set yet. The table size=0"
+    lib.ngt_close_index(plain)
+    lib.ngt_destroy_results(r)
+    lib.ngt_destroy_error_object(err)
+
+
+def test_uint8_batch_entry_points(lib, sift5k, tmp_path):
+    """ngt_batch_search_index_as_uint8 / ngt_batch_linear_search_index_as_uint8: byte queries give the
+    answers of the float entry points on an Integer-1 index; on a Float-4 index they are refused."""
+    err = lib.ngt_create_error_object()
+    prop = lib.ngt_create_property(err)
+    assert lib.ngt_set_property_dimension(prop, 128, err) and lib.ngt_set_property_object_type_integer(prop, err)
+    ix = lib.ngt_create_graph_and_tree_in_memory(prop, err)
+    base = np.ascontiguousarray(sift5k["data"][:3000].astype(np.float32))
+    assert lib.ngt_batch_append_index(ix, capi.fptr(base), 3000, err) and lib.ngt_create_index(ix, 4, err)
+    qf = np.ascontiguousarray(sift5k["queries"].astype(np.float32))
+    qb = np.ascontiguousarray(qf.astype(np.uint8))
+    u32, u8 = C.POINTER(C.c_uint32), C.POINTER(C.c_uint8)
+    out = {}
+    for tag in ("f", "b"):
+        ids, ds, cnt = np.zeros((3, 7), np.uint32), np.zeros((3, 7), np.float32), np.zeros(3, np.uint32)
+        lids, lds, lcnt = np.zeros((3, 7), np.uint32), np.zeros((3, 7), np.float32), np.zeros(3, np.uint32)
+        if tag == "f":
+            assert lib.ngt_batch_search_index_as_float(ix, capi.fptr(qf), 3, 128, 7, 0.2, -1.0, -1, ids.ctypes.data_as(u32),
+                                                       capi.fptr(ds), cnt.ctypes.data_as(u32), err)
+            assert lib.ngt_batch_linear_search_index_as_float(ix, capi.fptr(qf), 3, 128, 7, -1.0, lids.ctypes.data_as(u32),
+                                                              capi.fptr(lds), lcnt.ctypes.data_as(u32), err)
+        else:
+            assert lib.ngt_batch_search_index_as_uint8(ix, qb.ctypes.data_as(u8), 3, 128, 7, 0.2, -1.0, -1, ids.ctypes.data_as(u32),
+                                                       capi.fptr(ds), cnt.ctypes.data_as(u32), err), lib.ngt_get_error_string(err)
+            assert lib.ngt_batch_linear_search_index_as_uint8(ix, qb.ctypes.data_as(u8), 3, 128, 7, -1.0, lids.ctypes.data_as(u32),
+                                                              capi.fptr(lds), lcnt.ctypes.data_as(u32), err)
+        out[tag] = (ids, ds, cnt, lids, lds, lcnt)
+    for a, b in zip(out["f"], out["b"]):
+        assert (a.view(np.uint32) == b.view(np.uint32)).all()
+    # exhaustive answers == the integer formula
+    d2 = ((base[None, :, :].astype(np.int64) - qb[:, None, :].astype(np.int64)) ** 2).sum(-1)
+    assert (out["b"][3] == np.argsort(d2, axis=1, kind="stable")[:, :7] + 1).all()
+    lib.ngt_close_index(ix)
+    fprop = lib.ngt_create_property(err)
+    assert lib.ngt_set_property_dimension(fprop, 128, err)
+    fx = lib.ngt_create_graph_and_tree_in_memory(fprop, err)
+    assert lib.ngt_batch_append_index(fx, capi.fptr(base), 100, err) and lib.ngt_create_index(fx, 4, err)
+    ids, ds, cnt = np.zeros((3, 7), np.uint32), np.zeros((3, 7), np.float32), np.zeros(3, np.uint32)
+    assert lib.ngt_batch_search_index_as_uint8(fx, qb.ctypes.data_as(u8), 3, 128, 7, 0.2, -1.0, -1, ids.ctypes.data_as(u32),
+                                               capi.fptr(ds), cnt.ctypes.data_as(u32), err) is False
+    assert b"not integer" in lib.ngt_get_error_string(err)
+    lib.ngt_close_index(fx)
+    lib.ngt_destroy_property(prop)
+    lib.ngt_destroy_property(fprop)
+    lib.ngt_destroy_error_object(err)
+
+
+def test_create_index_with_nothing_queued_keeps_the_graph(lib, tmp_path):
+    """ngt_create_index on an opened ONNG with nothing appended is a no-op (createIndex only indexes objects that are
+    not in the graph, Index.cpp:645-648): the optimised graph and GraphType stay. Removal while objects are queued
+    strips the id from the old graph, and the queued objects are then inserted incrementally."""
+    from ngt_b200 import index_io, synth
+    z = np.load(os.path.join(GOLDEN, "reconstruct.npz"))
+    base = synth.make("sift", 1500, 1)
+    src = str(tmp_path / "onng")
+    os.makedirs(src)
+    index_io.write_prf(src, dict(index_io.DEFAULT_PRF, Dimension="128", EdgeSizeForCreation="20", EdgeSizeForSearch="0", GraphType="ONNG"))
+    index_io.write_objects(src, base)
+    index_io.write_graph(src, z["o10_i40_row_ptr"].astype(np.uint64), z["o10_i40_col"], z["o10_i40_dist"])
+    err = lib.ngt_create_error_object()
+    ix = lib.ngt_open_index(src.encode(), err)
+    assert ix, lib.ngt_get_error_string(err)
+    before = _edges(lib, ix, 1500, err)
+    assert lib.ngt_create_index(ix, 4, err)
+    assert _edges(lib, ix, 1500, err) == before
+    more = synth.make("sift", 300, 9)
+    assert lib.ngt_batch_append_index(ix, capi.fptr(more), 300, err)
+    assert lib.ngt_remove_index(ix, 7, err), lib.ngt_get_error_string(err)          # while 300 objects are queued
+    assert lib.ngt_create_index(ix, 4, err), lib.ngt_get_error_string(err)
+    after = _edges(lib, ix, 1800, err)
+    assert after[6] == [] and all(7 not in [t for t, _ in l] for l in after)
+    for nid in range(1500):
+        if nid != 6:
+            assert set(e for e in before[nid] if e[0] != 7) <= set(after[nid])     # the old graph was kept, not rebuilt
+    assert all(len(after[nid]) >= 1 for nid in range(1500, 1800))
+    out = str(tmp_path / "saved")
+    assert lib.ngt_save_index(ix, out.encode(), err), lib.ngt_get_error_string(err)
+    assert "ONNG" in open(os.path.join(out, "prf")).read()
+    lib.ngt_close_index(ix)
+    lib.ngt_destroy_error_object(err)

@@ -178,6 +178,36 @@ def test_index_mirror_round_trip(eng, tmp_path):
     again.close()
 
 
+@pytest.mark.parametrize("dtype", ["L2", "Normalized Cosine"])
+def test_index_mirror_repeated_batch_insert_is_incremental(eng, tmp_path, dtype):
+    """batch_insert -> batch_insert -> search on the mirror (also for a normalising space): the second call inserts into
+    the existing graph (the reference's construction loop on the device) instead of rebuilding it; build_index with
+    nothing queued is a no-op."""
+    from ngt_b200 import index as ngt
+    from ngt_b200 import synth
+    path = str(tmp_path / "idx")
+    ngt.create(path, 128, edge_size_for_creation=10, distance_type=dtype)
+    ix = ngt.Index(path)
+    base = synth.make("sift", 2600, 5) + (1.0 if dtype != "L2" else 0.0)
+    ix.batch_insert(base[:2000])
+    g0 = [a.copy() for a in ix._graph]
+    ix.build_index()                                   # nothing queued
+    assert all((a == b).all() for a, b in zip(g0, ix._graph))
+    ix.batch_insert(base[2000:])
+    rp, col, dist = ix._graph
+    old = lambda g, i: set(zip(g[1][int(g[0][i]):int(g[0][i + 1])].tolist(), g[2][int(g[0][i]):int(g[0][i + 1])].tolist()))
+    for nid in range(1, 2001, 37):
+        assert old(g0, nid) <= old(ix._graph, nid)     # old edges kept; only reverse edges of new nodes were added
+        assert all(t > 2000 for t, _ in old(ix._graph, nid) - old(g0, nid))
+    hits = 0
+    for q in range(2000, 2600, 11):
+        hits += ix.search(base[q], size=1, epsilon=0.1)[0][0] == q
+    assert hits >= 0.9 * len(range(2000, 2600, 11))
+    if dtype != "L2":
+        assert abs(np.linalg.norm(ix.get_object(2300)) - 1.0) < 1e-5      # stored rows are the normalised ones
+    ix.close()
+
+
 def test_index_mirror_refine_and_optimizer(eng, tmp_path):
     """ngtpy's Index.refine_anng and Optimizer.execute on the mirror: the ONNG written through Optimizer equals the
     reference's (tests/golden/adjust_paths.npz) and reopens as an index."""

@@ -254,3 +254,63 @@ def test_ngt_c_api_symbols_and_error_convention():
     lib.ngt_destroy_property(prop)
     lib.ngt_destroy_results(res)
     lib.ngt_destroy_error_object(err)
+
+
+def test_every_capi_h_function_is_exported():
+    """All 67 functions lib/NGT/Capi.h:60-212 declares resolve in libngtgpu.so (plus the additive batch entry points),
+    and the one struct-returning call works without a device (Capi.cpp:1043-1058 defaults)."""
+    import capi
+    from ngt_b200 import _lib
+    lib = capi.bind(_lib.SO_PATH)
+    assert len(capi.CAPI_H_FUNCTIONS) == 67
+    for name in capi.CAPI_H_FUNCTIONS:
+        assert hasattr(lib, name), name
+    for name in ("ngt_batch_search_index_as_float", "ngt_batch_search_index_as_uint8", "ngt_batch_linear_search_index_as_float",
+                 "ngt_batch_linear_search_index_as_uint8"):
+        assert hasattr(lib, name), name
+    p = lib.ngt_get_anng_edge_optimization_parameter()
+    assert (p.no_of_queries, p.no_of_results, p.no_of_threads, p.target_no_of_objects, p.no_of_sample_objects,
+            p.max_of_no_of_edges, p.log) == (200, 50, 16, 0, 100000, 100, False)
+    assert abs(p.target_accuracy - 0.9) < 1e-7
+    err = lib.ngt_create_error_object()
+    assert lib.ngt_optimize_number_of_edges(b"/nonexistent", p, err) is False        # a tuner: outside the hot path, refused loudly
+    assert "not provided by the B200 engine" in lib.ngt_get_error_string(err).decode()
+    lib.ngt_destroy_error_object(err)
+
+
+def test_reference_base_py_binds_libngtgpu_unmodified():
+    """python/ngt/base.py of the reference, unmodified, imports against libngtgpu.so: every ngt_* symbol its class body
+    touches resolves (the functional run of the same module is in tests/test_gpu_capi.py)."""
+    import capi
+    from ngt_b200 import _lib
+    mod = capi.load_reference_base_py(_lib.SO_PATH)
+    if mod is None:
+        pytest.skip("no copy of the reference's python/ngt/base.py on this box")
+    assert hasattr(mod.Index, "search") and hasattr(mod.Index, "insert_blob") and hasattr(mod, "NativeError")
+    with pytest.raises(mod.NativeError) as ei:          # error convention: NULL + message -> NativeError
+        mod.Index(b"/nonexistent/idx")
+    assert b"Cannot load the property file /nonexistent/idx/prf." in ei.value.args[0]
+
+
+def test_accuracy_table_equals_the_reference():
+    """Index::AccuracyTable::getEpsilon (Index.h:293-360): the C ABI function and the Python mirror against values the
+    reference returned (tests/golden/accuracy_table.json), bit for bit, and the reference's messages for bad tables."""
+    import ctypes as C
+    import json
+    from conftest import GOLDEN
+    from ngt_b200 import _lib
+    from ngt_b200.index import epsilon_from_accuracy_table
+    lib = _lib.load()
+    z = json.load(open(os.path.join(GOLDEN, "accuracy_table.json")))
+    for acc, eps in z["cases"]:
+        e = C.c_float(0)
+        assert lib.ngtgpu_epsilon_from_accuracy_table(z["table"].encode(), acc, C.byref(e)) == 0
+        assert np.float32(e.value) == np.float32(eps), (acc, e.value, eps)
+        assert np.float32(epsilon_from_accuracy_table(z["table"], acc)) == np.float32(eps)
+    for name, (table, msg) in z["errors"].items():
+        e = C.c_float(0)
+        assert lib.ngtgpu_epsilon_from_accuracy_table(table.encode(), 0.9, C.byref(e)) != 0
+        assert lib.ngtgpu_last_error().decode() == msg, name
+        with pytest.raises(_lib.NgtGpuError) as ei:
+            epsilon_from_accuracy_table(table, 0.9)
+        assert str(ei.value) == msg
