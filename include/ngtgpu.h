@@ -175,6 +175,54 @@ int ngtgpu_pack_keys(const uint32_t *ids, const float *dists, const uint32_t *co
 int ngtgpu_merge_keys(const uint64_t *keys, uint32_t n_lists, uint32_t nq, uint32_t k, uint32_t *ids, float *dists,
                       uint32_t *counts, void *stream);
 
+/* ---- multi-GPU: the objects sharded by rows over the GPUs of one box (the reference has no
+ *      distribution). Shard g is an ordinary ngtgpu_index over its block of the objects (own graph, own seed table),
+ *      global id = local id + id_offset. Every shard answers the whole query batch; the traversal kernel writes its
+ *      results as 64-bit keys straight into the shard's slot of the gather buffer, ONE ncclAllGather (in place, NVLink)
+ *      exchanges them and a device merge keeps the k smallest (distance, id) per query -- what one priority queue over
+ *      the union keeps (lib/NGT/Common.h:1946-1952), so merged == search of the union, bit for bit.
+ *      NCCL is bound at run time (libnccl.so.2; NGTGPU_NCCL_SO overrides), only when these entry points are used. ----
+ *
+ *  (1) one process per GPU (torchrun / MPI): the launcher carries the 128-byte id from rank 0 to the other ranks. */
+#define NGTGPU_COMM_ID_BYTES 128
+typedef struct ngtgpu_comm ngtgpu_comm;
+int ngtgpu_comm_get_unique_id(void *id_out /* NGTGPU_COMM_ID_BYTES */);
+int ngtgpu_comm_create(ngtgpu_comm **out, const void *id, int rank, int world, int device);
+int ngtgpu_comm_destroy(ngtgpu_comm *comm);
+/* This rank's shard `index` searched for the batch (DEVICE queries, identical on every rank), all-gather, merge: every
+ * rank receives the merged lists (DEVICE buffers, global ids). Enqueued on `stream`. */
+int ngtgpu_shard_search_device(ngtgpu_index *index, ngtgpu_comm *comm, const void *queries, int query_type, uint32_t nq,
+                               const ngtgpu_search_params *params, uint32_t n_seeds, uint32_t id_offset, uint32_t *ids,
+                               float *dists, uint32_t *counts, void *stream);
+int ngtgpu_shard_linear_search_device(ngtgpu_index *index, ngtgpu_comm *comm, const void *queries, int query_type, uint32_t nq,
+                                      uint32_t size, float radius, uint32_t id_offset, uint32_t *ids, float *dists,
+                                      uint32_t *counts, void *stream);
+/* CUDA-event timing of the calls above: ms3 = {this shard's search, all-gather (waits for the slowest shard), merge}. */
+int ngtgpu_comm_set_timing(ngtgpu_comm *comm, int enabled);
+int ngtgpu_comm_pop_timing(ngtgpu_comm *comm, double *ms3, uint64_t *calls);
+
+/*  (2) one process driving several GPUs -- what a program written against lib/NGT/Capi.h is (ngt_open_index uses this
+ *      handle when NGTGPU_DEVICES lists several devices). HOST buffers in and out, like ngtgpu_search. */
+typedef struct ngtgpu_sharded ngtgpu_sharded;
+int ngtgpu_sharded_create(ngtgpu_sharded **out, const int *devices, int n_devices, int object_type, int distance_type,
+                          uint32_t dimension);
+int ngtgpu_sharded_destroy(ngtgpu_sharded *sharded);
+/* objects 1..n (host rows): rows [g*n/G, (g+1)*n/G) become shard g */
+int ngtgpu_sharded_set_objects(ngtgpu_sharded *sharded, const void *objects, uint64_t n, int normalize);
+/* every shard builds its own ONNG (ngtgpu_index_build_onng) and seed table, all devices at once */
+int ngtgpu_sharded_build_onng(ngtgpu_sharded *sharded, uint32_t knn, uint32_t outgoing, uint32_t incoming,
+                              int shortcut_reduction, int64_t edge_size_for_search, uint32_t n_pivots);
+int ngtgpu_sharded_shard_count(const ngtgpu_sharded *sharded);
+/* shard g's own index handle (to set an explicit graph, tune its workspace, ...), its id offset and size */
+int ngtgpu_sharded_shard(ngtgpu_sharded *sharded, int shard, ngtgpu_index **index, uint64_t *id_offset, uint64_t *count);
+/* upload to the first device, ncclBroadcast, per-shard search, ncclAllGather, merge, download */
+int ngtgpu_sharded_search(ngtgpu_sharded *sharded, const void *queries, int query_type, uint32_t nq,
+                          const ngtgpu_search_params *params, uint32_t n_seeds, uint32_t *ids, float *dists, uint32_t *counts);
+int ngtgpu_sharded_linear_search(ngtgpu_sharded *sharded, const void *queries, int query_type, uint32_t nq, uint32_t size,
+                                 float radius, uint32_t *ids, float *dists, uint32_t *counts);
+/* ms5 of the last call, on the first device's stream: upload + broadcast, search, all-gather, merge, download */
+int ngtgpu_sharded_last_timing(const ngtgpu_sharded *sharded, double *ms5);
+
 /* ---- graph from the exhaustive kNN pass: a DEVICE [n x k] neighbour table (ngtgpu_index_knn_graph) -> DEVICE CSR over
  *      ids 0..n with distances, lists ascending by (distance, id). symmetric != 0 adds the reverse of every edge, i.e.
  *      the graph insertANNGNode's out-edges + reverse edges converge to (lib/NGT/Graph.h:611-626). valid (nullable):
@@ -215,6 +263,21 @@ int ngtgpu_graph_adjust_paths(uint64_t n, const uint64_t *row_ptr, const uint32_
 int ngtgpu_index_insert_batch(ngtgpu_index *index, uint32_t first_id, uint32_t count, uint32_t edge_size_for_creation,
                               float epsilon, int64_t edge_size, uint32_t n_seeds, uint32_t n_pivots, uint64_t pivot_seed,
                               uint64_t capacity, uint64_t *d_row_ptr, uint32_t *d_col, float *d_dist, uint64_t *nnz_out);
+
+/* ---- the reference's ONNG recipe for the objects of one index, all on the device: exact kNN table (the brute-force pass
+ *      of lib/NGT/Index.h:839-856) -> kNN graph -> reconstructGraph(outgoing, incoming) (GraphReconstructor.h:425-561) ->
+ *      adjustPathsEffectively when shortcut_reduction != 0 (:197-386, min_edges as there) -> the index's graph. graph_out
+ *      (nullable) receives device copies of the CSR with distances, to be released with ngtgpu_device_free; seconds
+ *      (nullable, 3 entries): kNN pass, reconstructGraph, path adjustment, from CUDA events. */
+typedef struct {
+  uint64_t n, nnz;
+  uint64_t *row_ptr; /* n + 2 */
+  uint32_t *col;
+  float *dist;
+} ngtgpu_graph_buffers;
+int ngtgpu_index_build_onng(ngtgpu_index *index, uint32_t knn, uint32_t outgoing, uint32_t incoming, int shortcut_reduction,
+                            uint32_t min_edges, ngtgpu_graph_buffers *graph_out, double *seconds);
+int ngtgpu_device_free(void *device_pointer);
 
 /* The sub-graph of the edges with keep[e] != 0, order inside the lists preserved (compaction after
  * ngtgpu_graph_adjust_paths). DEVICE buffers; *out_nnz is a host word. */

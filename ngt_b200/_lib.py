@@ -72,6 +72,27 @@ SYMBOLS = {
                                             C.c_uint64, C.c_uint64, _P, _P, _P, C.POINTER(C.c_uint64)]),
     "ngtgpu_graph_adjust_paths": (C.c_int, [C.c_uint64, _P, _P, _P, C.c_uint32, _P, C.POINTER(C.c_uint64), _P]),
     "ngtgpu_linear_search_device": (C.c_int, [_P, _P, C.c_int, C.c_uint32, C.c_uint32, C.c_float, _P, _P, _P, _P]),
+    "ngtgpu_index_build_onng": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, _P, C.POINTER(C.c_double)]),
+    "ngtgpu_device_free": (C.c_int, [_P]),
+    # multi-GPU (shard.cu)
+    "ngtgpu_comm_get_unique_id": (C.c_int, [_P]),
+    "ngtgpu_comm_create": (C.c_int, [C.POINTER(_P), _P, C.c_int, C.c_int, C.c_int]),
+    "ngtgpu_comm_destroy": (C.c_int, [_P]),
+    "ngtgpu_comm_set_timing": (C.c_int, [_P, C.c_int]),
+    "ngtgpu_comm_pop_timing": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "ngtgpu_shard_search_device": (C.c_int, [_P, _P, _P, C.c_int, C.c_uint32, C.POINTER(SearchParams), C.c_uint32, C.c_uint32,
+                                             _P, _P, _P, _P]),
+    "ngtgpu_shard_linear_search_device": (C.c_int, [_P, _P, _P, C.c_int, C.c_uint32, C.c_uint32, C.c_float, C.c_uint32,
+                                                    _P, _P, _P, _P]),
+    "ngtgpu_sharded_create": (C.c_int, [C.POINTER(_P), C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_uint32]),
+    "ngtgpu_sharded_destroy": (C.c_int, [_P]),
+    "ngtgpu_sharded_set_objects": (C.c_int, [_P, _P, C.c_uint64, C.c_int]),
+    "ngtgpu_sharded_build_onng": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_int64, C.c_uint32]),
+    "ngtgpu_sharded_shard_count": (C.c_int, [_P]),
+    "ngtgpu_sharded_shard": (C.c_int, [_P, C.c_int, C.POINTER(_P), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "ngtgpu_sharded_search": (C.c_int, [_P, _P, C.c_int, C.c_uint32, C.POINTER(SearchParams), C.c_uint32, _P, _P, _P]),
+    "ngtgpu_sharded_linear_search": (C.c_int, [_P, _P, C.c_int, C.c_uint32, C.c_uint32, C.c_float, _P, _P, _P]),
+    "ngtgpu_sharded_last_timing": (C.c_int, [_P, C.POINTER(C.c_double)]),
 }
 
 _lib = None

@@ -128,6 +128,7 @@ struct CapiIndex {
   std::vector<uint32_t> col;
   std::vector<float> dist;
   ngtgpu_index *gpu = nullptr;
+  ngtgpu_sharded *sharded = nullptr;   // opened over several GPUs (NGTGPU_DEVICES / ngt_open_index_sharded): read-only
   size_t pending = 0;              // appended since the last build
   size_t raw_from = 0;             // first id whose row is not normalised yet (Normalized* types)
   size_t record_bytes() const { return (size_t)prop.dimension * (prop.object_type == NGTGPU_OBJECT_UINT8 ? 1 : 4); }
@@ -253,7 +254,41 @@ void upload(CapiIndex &ix) {
   if (pivots) check(ngtgpu_index_build_seed_table(ix.gpu, pivots, 1));
 }
 
-CapiIndex *open_index(const char *path) {
+// NGTGPU_DEVICES="0,1,2,3": the devices an index is sharded over when it is opened (rows split evenly, a graph per shard)
+std::vector<int> devices_from_env() {
+  std::vector<int> d;
+  const char *env = getenv("NGTGPU_DEVICES");
+  if (!env) return d;
+  std::stringstream ss(env);
+  std::string tok;
+  while (std::getline(ss, tok, ','))
+    if (!tok.empty()) d.push_back(std::stoi(tok));
+  return d;
+}
+
+// Rows sharded over `devices`: every shard gets its own graph from the reference's recipe on an exact neighbour table
+// (ngtgpu_index_build_onng: -E EdgeSizeForCreation, then -o OutgoingEdge -i IncomingEdge + shortcut reduction when the
+// index is an ONNG, the symmetric closure of the table -- what insertANNGNode converges to -- when it is an ANNG);
+// the index's own `grp` spans shards and is kept only for ngt_get_edges.
+void shard_index(CapiIndex &ix, const std::vector<int> &devices) {
+  const size_t n = ix.n();
+  for (size_t id = 1; id <= n; id++)
+    if (!ix.present[id]) throw std::runtime_error("a sharded index cannot hold removed objects (id " + std::to_string(id) + ")");
+  check(ngtgpu_sharded_create(&ix.sharded, devices.data(), (int)devices.size(), ix.prop.object_type, ix.prop.distance_type,
+                              (uint32_t)ix.prop.dimension));
+  check(ngtgpu_sharded_set_objects(ix.sharded, ix.objects.data(), n, 0));
+  const uint32_t e = (uint32_t)std::max<int>(1, ix.prop.edge_size_for_creation);
+  const bool onng = ix.prf.count("GraphType") && ix.prf["GraphType"] == "ONNG";
+  const uint32_t out = onng ? (uint32_t)std::max<long>(0, prf_long(ix, "OutgoingEdge", 10)) : e;
+  const uint32_t in = onng ? (uint32_t)std::max<long>(0, prf_long(ix, "IncomingEdge", 80)) : e;
+  check(ngtgpu_sharded_build_onng(ix.sharded, e, out, in, onng ? 1 : 0, ix.prop.edge_size_for_search, 1024));
+}
+
+void require_single(CapiIndex &ix, const char *what) {
+  if (ix.sharded) throw std::runtime_error(std::string(what) + ": the index is sharded over several GPUs and read-only");
+}
+
+CapiIndex *open_index(const char *path, const std::vector<int> &devices = devices_from_env()) {
   std::unique_ptr<CapiIndex> ix(new CapiIndex);
   ix->path = path;
   read_prf(*ix);
@@ -273,11 +308,21 @@ CapiIndex *open_index(const char *path) {
   ix->dist.resize(nnz);
   ix->row_ptr.assign(n + 2, nnz);
   for (size_t i = 0; i < rp.size() && i < n + 2; i++) ix->row_ptr[i] = rp[i];
-  upload(*ix);
+  if (devices.size() > 1 && n >= devices.size()) {
+    try {
+      shard_index(*ix, devices);
+    } catch (...) {
+      if (ix->sharded) ngtgpu_sharded_destroy(ix->sharded);
+      throw;
+    }
+  } else {
+    upload(*ix);
+  }
   return ix.release();
 }
 
 void require_built(CapiIndex &ix) {
+  if (ix.sharded) return;
   if (ix.pending) throw std::runtime_error("objects were appended: call ngt_create_index() before searching");
   if (!ix.gpu || ix.n() == 0) throw std::runtime_error("the index holds no objects");
 }
@@ -292,27 +337,33 @@ void search_one(CapiIndex &ix, const float *q, int32_t dim, size_t size, float e
                 NGTObjectDistances results) {
   if (dim != ix.prop.dimension) throw std::runtime_error("ObjectSpace::allocateObject: the specified dimension is invalid");
   require_built(ix);
-  if (ix.row_ptr.size() != ix.n() + 2) throw std::runtime_error("the index has no graph: call ngt_create_index()");
+  if (!ix.sharded && ix.row_ptr.size() != ix.n() + 2) throw std::runtime_error("the index has no graph: call ngt_create_index()");
   ngtgpu_search_params p = {(uint32_t)size, epsilon, radius >= FLT_MAX ? -1.0f : radius, edge_size};
   std::vector<uint32_t> ids(size ? size : 1), cnt(1, 0);
   std::vector<float> ds(size ? size : 1);
   uint32_t seeds = (uint32_t)prf_long(ix, "SeedSize", 10);
   if (seeds == 0) seeds = 10;
-  check(ngtgpu_search(ix.gpu, q, NGTGPU_OBJECT_FLOAT, 1, &p, nullptr, seeds, ids.data(), ds.data(), cnt.data(), nullptr));
+  if (ix.sharded) check(ngtgpu_sharded_search(ix.sharded, q, NGTGPU_OBJECT_FLOAT, 1, &p, seeds, ids.data(), ds.data(), cnt.data()));
+  else check(ngtgpu_search(ix.gpu, q, NGTGPU_OBJECT_FLOAT, 1, &p, nullptr, seeds, ids.data(), ds.data(), cnt.data(), nullptr));
   fill_results(results, ids.data(), ds.data(), cnt[0]);
 }
 
 void linear_one(CapiIndex &ix, const float *q, int32_t dim, size_t size, float radius, NGTObjectDistances results) {
   if (dim != ix.prop.dimension) throw std::runtime_error("ObjectSpace::allocateObject: the specified dimension is invalid");
-  if (!ix.gpu || ix.n() == 0) throw std::runtime_error("the index holds no objects");
+  if ((!ix.gpu && !ix.sharded) || ix.n() == 0) throw std::runtime_error("the index holds no objects");
   std::vector<uint32_t> ids(size ? size : 1), cnt(1, 0);
   std::vector<float> ds(size ? size : 1);
-  check(ngtgpu_linear_search(ix.gpu, q, NGTGPU_OBJECT_FLOAT, 1, (uint32_t)size, radius >= FLT_MAX ? -1.0f : radius, ids.data(),
-                             ds.data(), cnt.data()));
+  if (ix.sharded)
+    check(ngtgpu_sharded_linear_search(ix.sharded, q, NGTGPU_OBJECT_FLOAT, 1, (uint32_t)size, radius >= FLT_MAX ? -1.0f : radius,
+                                       ids.data(), ds.data(), cnt.data()));
+  else
+    check(ngtgpu_linear_search(ix.gpu, q, NGTGPU_OBJECT_FLOAT, 1, (uint32_t)size, radius >= FLT_MAX ? -1.0f : radius, ids.data(),
+                               ds.data(), cnt.data()));
   fill_results(results, ids.data(), ds.data(), cnt[0]);
 }
 
 ObjectID append_rows(CapiIndex &ix, const float *rows, size_t count, uint32_t dim) {
+  require_single(ix, "insert");
   if ((int32_t)dim != ix.prop.dimension) throw std::runtime_error("ObjectSpace::allocateObject: the specified dimension is invalid");
   const size_t rb = ix.record_bytes();
   const size_t first = ix.n() + 1;
@@ -342,7 +393,7 @@ ObjectID append_rows(CapiIndex &ix, const float *rows, size_t count, uint32_t di
 // insertANNGNode converges to (lib/NGT/Graph.h:611-626).
 void build_graph(CapiIndex &ix) {
   const size_t n = ix.n();
-  if (n == 0) return;
+  if (n == 0 || ix.sharded) return;   // a sharded index is built when it is opened
   // createIndex only indexes objects that are not in the graph yet (Index.cpp:645-648): with nothing queued and a
   // graph in place (loaded ONNG, refined or optimised graph) it is a no-op.
   if (ix.pending == 0 && ix.row_ptr.size() == n + 2 && !ix.col.empty()) return;
@@ -538,6 +589,14 @@ NGTIndex ngt_open_index(const char *index_path, NGTError error) {
   CAPI_CATCH(NULL)
 }
 NGTIndex ngt_open_index_as_read_only(const char *index_path, NGTError error) { return ngt_open_index(index_path, error); }
+// additive: the index opened with its rows sharded over `devices` (what NGTGPU_DEVICES does for ngt_open_index)
+NGTIndex ngt_open_index_sharded(const char *index_path, const int *devices, int n_devices, NGTError error) {
+  try {
+    if (!devices || n_devices < 1) throw std::runtime_error("no devices given");
+    return static_cast<NGTIndex>(open_index(index_path, std::vector<int>(devices, devices + n_devices)));
+  }
+  CAPI_CATCH(NULL)
+}
 
 static NGTIndex create_empty(const char *database, NGTProperty prop, NGTError error, const char *fn) {
   try {
@@ -597,6 +656,7 @@ void ngt_close_index(NGTIndex index) {
   if (index == NULL) return;
   CapiIndex *ix = static_cast<CapiIndex *>(index);
   if (ix->gpu) ngtgpu_index_destroy(ix->gpu);
+  if (ix->sharded) ngtgpu_sharded_destroy(ix->sharded);
   delete ix;
 }
 
@@ -741,7 +801,8 @@ bool ngt_batch_search_index_as_float(NGTIndex index, const float *queries, uint3
     require_built(ix);
     ngtgpu_search_params p = {(uint32_t)size, epsilon, radius, edge_size};
     uint32_t seeds = (uint32_t)prf_long(ix, "SeedSize", 10);
-    check(ngtgpu_search(ix.gpu, queries, NGTGPU_OBJECT_FLOAT, nq, &p, nullptr, seeds ? seeds : 10, ids, dists, counts, nullptr));
+    if (ix.sharded) check(ngtgpu_sharded_search(ix.sharded, queries, NGTGPU_OBJECT_FLOAT, nq, &p, seeds ? seeds : 10, ids, dists, counts));
+    else check(ngtgpu_search(ix.gpu, queries, NGTGPU_OBJECT_FLOAT, nq, &p, nullptr, seeds ? seeds : 10, ids, dists, counts, nullptr));
   }
   CAPI_CATCH(false)
   return true;
@@ -757,8 +818,9 @@ bool ngt_batch_linear_search_index_as_float(NGTIndex index, const float *queries
   try {
     CapiIndex &ix = *static_cast<CapiIndex *>(index);
     if (query_dim != ix.prop.dimension) throw std::runtime_error("ObjectSpace::allocateObject: the specified dimension is invalid");
-    if (!ix.gpu || ix.n() == 0) throw std::runtime_error("the index holds no objects");
-    check(ngtgpu_linear_search(ix.gpu, queries, NGTGPU_OBJECT_FLOAT, nq, (uint32_t)size, radius, ids, dists, counts));
+    if ((!ix.gpu && !ix.sharded) || ix.n() == 0) throw std::runtime_error("the index holds no objects");
+    if (ix.sharded) check(ngtgpu_sharded_linear_search(ix.sharded, queries, NGTGPU_OBJECT_FLOAT, nq, (uint32_t)size, radius, ids, dists, counts));
+    else check(ngtgpu_linear_search(ix.gpu, queries, NGTGPU_OBJECT_FLOAT, nq, (uint32_t)size, radius, ids, dists, counts));
   }
   CAPI_CATCH(false)
   return true;
@@ -781,7 +843,8 @@ bool ngt_batch_search_index_as_uint8(NGTIndex index, const uint8_t *queries, uin
     require_built(ix);
     ngtgpu_search_params p = {(uint32_t)size, epsilon, radius, edge_size};
     uint32_t seeds = (uint32_t)prf_long(ix, "SeedSize", 10);
-    check(ngtgpu_search(ix.gpu, queries, NGTGPU_OBJECT_UINT8, nq, &p, nullptr, seeds ? seeds : 10, ids, dists, counts, nullptr));
+    if (ix.sharded) check(ngtgpu_sharded_search(ix.sharded, queries, NGTGPU_OBJECT_UINT8, nq, &p, seeds ? seeds : 10, ids, dists, counts));
+    else check(ngtgpu_search(ix.gpu, queries, NGTGPU_OBJECT_UINT8, nq, &p, nullptr, seeds ? seeds : 10, ids, dists, counts, nullptr));
   }
   CAPI_CATCH(false)
   return true;
@@ -798,8 +861,9 @@ bool ngt_batch_linear_search_index_as_uint8(NGTIndex index, const uint8_t *queri
     CapiIndex &ix = *static_cast<CapiIndex *>(index);
     if (query_dim != ix.prop.dimension) throw std::runtime_error("ObjectSpace::allocateObject: the specified dimension is invalid");
     if (ix.prop.object_type != NGTGPU_OBJECT_UINT8) throw std::runtime_error("the object type of the index is not integer (uint8)");
-    if (!ix.gpu || ix.n() == 0) throw std::runtime_error("the index holds no objects");
-    check(ngtgpu_linear_search(ix.gpu, queries, NGTGPU_OBJECT_UINT8, nq, (uint32_t)size, radius, ids, dists, counts));
+    if ((!ix.gpu && !ix.sharded) || ix.n() == 0) throw std::runtime_error("the index holds no objects");
+    if (ix.sharded) check(ngtgpu_sharded_linear_search(ix.sharded, queries, NGTGPU_OBJECT_UINT8, nq, (uint32_t)size, radius, ids, dists, counts));
+    else check(ngtgpu_linear_search(ix.gpu, queries, NGTGPU_OBJECT_UINT8, nq, (uint32_t)size, radius, ids, dists, counts));
   }
   CAPI_CATCH(false)
   return true;
@@ -890,6 +954,7 @@ bool ngt_remove_index(NGTIndex index, ObjectID id, NGTError error) {
   }
   try {
     CapiIndex &ix = *static_cast<CapiIndex *>(index);
+    require_single(ix, "remove");
     if (id == 0 || id > ix.n() || !ix.present[id]) throw std::runtime_error("remove: the specified object does not exist. ID=" + std::to_string(id));
     ix.present[id] = 0;
     // the graph covers ids 1..n_graph (= n when nothing is queued; the objects appended since the last build are not in
@@ -1110,6 +1175,7 @@ bool ngt_refine_anng(NGTIndex index, float epsilon, float expectedAccuracy, int 
   }
   try {
     CapiIndex &ix = *static_cast<CapiIndex *>(index);
+    require_single(ix, "refineANNG");
     require_built(ix);
     if (expectedAccuracy > 0.0f) epsilon = epsilon_from_expected_accuracy(ix, expectedAccuracy);   // GraphReconstructor.h:843-847
     if (ix.row_ptr.size() != ix.n() + 2) throw std::runtime_error("refineANNG: the index holds no graph");

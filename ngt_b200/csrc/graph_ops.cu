@@ -1084,3 +1084,113 @@ extern "C" int ngtgpu_index_insert_batch(ngtgpu_index *ix, uint32_t first_id, ui
   *nnz_out = nnz;
   return NGTGPU_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// ngtgpu_index_build_onng -- the reference's ONNG recipe for the objects of one index, entirely on the device:
+//   exact kNN table (the brute-force pass of Index.h:839-856, tensor cores where the shape allows)
+//   -> kNN graph as CSR -> GraphReconstructor::reconstructGraph (outgoing / incoming, GraphReconstructor.h:425-561)
+//   -> GraphReconstructor::adjustPathsEffectively (shortcut reduction, :197-386) -> the index's graph.
+// What `ngt create -E knn` + `ngt reconstruct-graph -o outgoing -i incoming` produce from an exact neighbour table.
+// graph_out (nullable): receives cudaMalloc'ed copies of the CSR with distances (free with ngtgpu_device_free).
+extern "C" int ngtgpu_index_build_onng(ngtgpu_index *ix, uint32_t knn, uint32_t outgoing, uint32_t incoming,
+                                       int shortcut_reduction, uint32_t min_edges, ngtgpu_graph_buffers *graph_out,
+                                       double *seconds) {
+  if (!ix) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "null index handle");
+  NGTGPU_TRY(ngtgpu_check_device(ix));
+  if (!ix->d_objects || ix->n < 2) NGTGPU_FAIL(NGTGPU_ERR_STATE, "ngtgpu_index_build_onng: the index holds fewer than two objects");
+  if (knn == 0) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "ngtgpu_index_build_onng: knn is zero");
+  cudaStream_t stream = ix->stream;
+  const uint64_t n = ix->n;
+  const uint32_t k = (uint32_t)std::min<uint64_t>(knn, n - 1);
+  cudaEvent_t ev[4];
+  for (auto &e : ev) CUDA_TRY(cudaEventCreate(&e));
+  struct EvGuard {
+    cudaEvent_t *e;
+    ~EvGuard() { for (int i = 0; i < 4; i++) cudaEventDestroy(e[i]); }
+  } guard{ev};
+  DeviceBuffers mem;
+  uint32_t *t_ids, *t_counts;
+  float *t_dists;
+  CUDA_TRY(mem.alloc(&t_ids, n * k));
+  CUDA_TRY(mem.alloc(&t_dists, n * k));
+  CUDA_TRY(mem.alloc(&t_counts, n));
+  CUDA_TRY(cudaEventRecord(ev[0], stream));
+  for (uint64_t s = 0; s < n; s += 131072) {
+    const uint32_t m = (uint32_t)std::min<uint64_t>(131072, n - s);
+    NGTGPU_TRY(ngtgpu_index_knn_graph(ix, k, (uint32_t)s + 1, m, t_ids + s * k, t_dists + s * k, t_counts + s, stream));
+  }
+  CUDA_TRY(cudaEventRecord(ev[1], stream));
+  // kNN table -> CSR (lists ascending by (distance, id))
+  uint64_t *a_rp, nnz_a = 0;
+  uint32_t *a_col;
+  float *a_dist;
+  CUDA_TRY(mem.alloc(&a_rp, n + 2));
+  CUDA_TRY(mem.alloc(&a_col, n * k));
+  CUDA_TRY(mem.alloc(&a_dist, n * k));
+  NGTGPU_TRY(ngtgpu_graph_from_knn_table(n, t_ids, t_dists, t_counts, k, ix->d_valid, 0, n * k, a_rp, a_col, a_dist, &nnz_a, stream));
+  mem.release(t_ids);
+  mem.release(t_dists);
+  mem.release(t_counts);
+  // reconstructGraph
+  const uint64_t cap_b = std::max<uint64_t>(2 * nnz_a, 1);
+  uint64_t *b_rp, nnz_b = 0;
+  uint32_t *b_col;
+  float *b_dist;
+  CUDA_TRY(mem.alloc(&b_rp, n + 2));
+  CUDA_TRY(mem.alloc(&b_col, cap_b));
+  CUDA_TRY(mem.alloc(&b_dist, cap_b));
+  NGTGPU_TRY(ngtgpu_graph_reconstruct(n, a_rp, a_col, a_dist, outgoing, incoming, cap_b, b_rp, b_col, b_dist, &nnz_b, stream));
+  mem.release(a_rp);
+  mem.release(a_col);
+  mem.release(a_dist);
+  CUDA_TRY(cudaEventRecord(ev[2], stream));
+  uint64_t *g_rp = b_rp, nnz = nnz_b;
+  uint32_t *g_col = b_col;
+  float *g_dist = b_dist;
+  if (shortcut_reduction && nnz_b) {
+    uint8_t *keep;
+    CUDA_TRY(mem.alloc(&keep, nnz_b));
+    NGTGPU_TRY(ngtgpu_graph_adjust_paths(n, b_rp, b_col, b_dist, min_edges, keep, nullptr, stream));
+    uint64_t *c_rp;
+    uint32_t *c_col;
+    float *c_dist;
+    CUDA_TRY(mem.alloc(&c_rp, n + 2));
+    CUDA_TRY(mem.alloc(&c_col, nnz_b));
+    CUDA_TRY(mem.alloc(&c_dist, nnz_b));
+    NGTGPU_TRY(ngtgpu_graph_select_edges(n, b_rp, b_col, b_dist, keep, c_rp, c_col, c_dist, &nnz, stream));
+    mem.release(keep);
+    mem.release(b_rp);
+    mem.release(b_col);
+    mem.release(b_dist);
+    g_rp = c_rp, g_col = c_col, g_dist = c_dist;
+  }
+  CUDA_TRY(cudaEventRecord(ev[3], stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  NGTGPU_TRY(ngtgpu_index_set_graph(ix, g_rp, g_col, 1));
+  if (seconds) {
+    float ms = 0.f;
+    for (int i = 0; i < 3; i++) {
+      cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+      seconds[i] = ms * 1e-3;   // kNN pass, reconstructGraph, path adjustment
+    }
+  }
+  if (graph_out) {
+    graph_out->n = n;
+    graph_out->nnz = nnz;
+    graph_out->row_ptr = nullptr, graph_out->col = nullptr, graph_out->dist = nullptr;
+    CUDA_TRY(cudaMalloc(&graph_out->row_ptr, (n + 2) * 8));
+    CUDA_TRY(cudaMalloc(&graph_out->col, std::max<uint64_t>(nnz, 1) * 4));
+    CUDA_TRY(cudaMalloc(&graph_out->dist, std::max<uint64_t>(nnz, 1) * 4));
+    CUDA_TRY(cudaMemcpy(graph_out->row_ptr, g_rp, (n + 2) * 8, cudaMemcpyDeviceToDevice));
+    if (nnz) {
+      CUDA_TRY(cudaMemcpy(graph_out->col, g_col, nnz * 4, cudaMemcpyDeviceToDevice));
+      CUDA_TRY(cudaMemcpy(graph_out->dist, g_dist, nnz * 4, cudaMemcpyDeviceToDevice));
+    }
+  }
+  return NGTGPU_OK;
+}
+
+extern "C" int ngtgpu_device_free(void *device_pointer) {
+  if (device_pointer) CUDA_TRY(cudaFree(device_pointer));
+  return NGTGPU_OK;
+}

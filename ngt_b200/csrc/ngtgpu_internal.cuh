@@ -145,7 +145,12 @@ int ngtgpu_scan_topk_tc(ngtgpu_index *ix, const ScanParams &p, cudaStream_t stre
 // graph traversal over prepared queries; everything in HBM.
 int ngtgpu_traverse(ngtgpu_index *ix, const uint8_t *d_queries, uint32_t nq, const ngtgpu_search_params *params,
                     const uint32_t *d_seeds, uint32_t n_seeds, uint32_t *d_ids, float *d_dists, uint32_t *d_counts,
-                    uint32_t *d_stats, cudaStream_t stream);
+                    uint32_t *d_stats, cudaStream_t stream, uint64_t *d_keys = nullptr, uint32_t id_offset = 0);
+// device-pointer search whose results leave as 64-bit keys (ordered distance bits << 32 | id + id_offset, KEY_NONE padded)
+// written by the traversal kernel itself: the send buffer of the row-sharded search's all-gather (shard.cu)
+int ngtgpu_search_keys_device(ngtgpu_index *ix, const void *queries, int query_type, uint32_t nq,
+                              const ngtgpu_search_params *params, uint32_t n_seeds, uint32_t id_offset, uint64_t *d_keys,
+                              uint32_t *d_counts, cudaStream_t stream);
 
 int64_t ngtgpu_effective_edge_size(const ngtgpu_index *ix, const ngtgpu_search_params *p);
 

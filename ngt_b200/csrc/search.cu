@@ -76,7 +76,7 @@ static int select_seeds(ngtgpu_index *ix, const uint8_t *d_queries, uint32_t nq,
 
 int ngtgpu_traverse(ngtgpu_index *ix, const uint8_t *d_queries, uint32_t nq, const ngtgpu_search_params *params,
                     const uint32_t *d_seeds, uint32_t n_seeds, uint32_t *d_ids, float *d_dists, uint32_t *d_counts,
-                    uint32_t *d_stats, cudaStream_t stream) {
+                    uint32_t *d_stats, cudaStream_t stream, uint64_t *d_keys, uint32_t id_offset) {
   if (!ix->d_row_ptr) NGTGPU_FAIL(NGTGPU_ERR_STATE, "search: the graph is not set");
   int64_t cap = ngtgpu_effective_edge_size(ix, params);
   if (cap < 0) {
@@ -113,6 +113,8 @@ int ngtgpu_traverse(ngtgpu_index *ix, const uint8_t *d_queries, uint32_t nq, con
   a.dists = d_dists;
   a.counts = d_counts;
   a.stats = d_stats;
+  a.keys_out = d_keys;
+  a.id_offset = id_offset;
   a.prof = ix->d_prof;
   // No seed list: the nearest pivots of the seed table, from a selection pass that runs first -- or, when seed fusion is
   // switched on and the table is small, selected by the lean kernel itself in the first tier (and written out for the
@@ -387,6 +389,22 @@ extern "C" int ngtgpu_search(ngtgpu_index *ix, const void *queries, int query_ty
                              float *dists, uint32_t *counts, uint32_t *stats) {
   if (!ix) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "null index handle");
   return search_common(ix, queries, query_type, nq, params, seeds, n_seeds, ids, dists, counts, stats, false, ix->stream);
+}
+
+int ngtgpu_search_keys_device(ngtgpu_index *ix, const void *queries, int query_type, uint32_t nq,
+                              const ngtgpu_search_params *params, uint32_t n_seeds, uint32_t id_offset, uint64_t *d_keys,
+                              uint32_t *d_counts, cudaStream_t stream) {
+  NGTGPU_TRY(ngtgpu_check_device(ix));
+  if (!params || !queries || !d_keys || !d_counts) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "search: null argument");
+  if (!ix->d_objects || ix->n == 0) NGTGPU_FAIL(NGTGPU_ERR_STATE, "search: the index holds no objects");
+  if (nq == 0 || params->size == 0) return NGTGPU_OK;
+  if ((uint64_t)id_offset + ix->n > 0xffffffffull) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "search: global ids do not fit 32 bits");
+  uint8_t *d_q = nullptr;
+  NGTGPU_TRY(ngtgpu_scratch(ix, SCR_QUERIES, (size_t)nq * ix->row_bytes, (void **)&d_q));
+  NGTGPU_TRY(ngtgpu_prepare_queries(ix, queries, query_type, nq, true, d_q, stream));
+  // a query that outgrows every tier leaves no keys behind: start from all-KEY_NONE
+  CUDA_TRY(cudaMemsetAsync(d_keys, 0xff, (size_t)nq * params->size * 8, stream));
+  return ngtgpu_traverse(ix, d_q, nq, params, nullptr, n_seeds, nullptr, nullptr, d_counts, nullptr, stream, d_keys, id_offset);
 }
 
 extern "C" int ngtgpu_search_device(ngtgpu_index *ix, const void *queries, int query_type, uint32_t nq,

@@ -97,7 +97,9 @@ struct SearchArgs {
   const uint32_t *pivot_ids;
   uint32_t n_pivots;
   uint32_t *seeds_out;               // nq x n_seeds: the seeds the kernel selected, for the later tiers
-};
+  uint64_t *keys_out;                // nullable, nq x k: results as (ordered distance bits << 32 | id + id_offset) keys, KEY_NONE
+  uint32_t id_offset;                //   padded -- the all-gather send buffer of a row-sharded search (shard.cu); ids/dists are then
+};                                   //   not written
 
 __device__ __forceinline__ uint32_t lanemask_lt() {
   uint32_t m;
@@ -1075,8 +1077,12 @@ __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_CTAS) search_kernel
           if (a.k <= 32) key = res.reg;
           else if (i < res.n) key = res.smem[i];
           bool ok = i < res.n;
-          a.ids[(size_t)q * a.k + i] = ok ? key_id(key) : 0u;
-          a.dists[(size_t)q * a.k + i] = ok ? key_dist(key) : 0.f;
+          if (a.keys_out) {
+            a.keys_out[(size_t)q * a.k + i] = ok ? key + a.id_offset : KEY_NONE;
+          } else {
+            a.ids[(size_t)q * a.k + i] = ok ? key_id(key) : 0u;
+            a.dists[(size_t)q * a.k + i] = ok ? key_dist(key) : 0.f;
+          }
         }
         if (lane == 0) {
           a.counts[q] = res.n;

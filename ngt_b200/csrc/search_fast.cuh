@@ -579,8 +579,12 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_MIN_CTAS) search_fast_kerne
         const uint32_t res_n = s_ctl[2];
         if ((uint32_t)lane < a.k) {
           const bool ok = (uint32_t)lane < res_n;
-          a.ids[(size_t)q * a.k + lane] = ok ? key_id(res) : 0u;
-          a.dists[(size_t)q * a.k + lane] = ok ? key_dist(res) : 0.f;
+          if (a.keys_out) {
+            a.keys_out[(size_t)q * a.k + lane] = ok ? res + a.id_offset : KEY_NONE;
+          } else {
+            a.ids[(size_t)q * a.k + lane] = ok ? key_id(res) : 0u;
+            a.dists[(size_t)q * a.k + lane] = ok ? key_dist(res) : 0.f;
+          }
         }
         if (lane == 0) {
           a.counts[q] = res_n;
