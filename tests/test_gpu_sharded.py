@@ -69,8 +69,9 @@ def test_one_process_sharded_handle_equals_union(eng, kind):
     t = sh.last_timing()
     assert t["search_ms"] > 0 and t["allgather_ms"] > 0
     # and it is a good search: recall against the exhaustive answer
-    gt = whole.linear_search(qs, k)[0]
-    hit = np.mean([(len(set(ids[q]) & set(gt[q])) / k) for q in range(nq)])
+    # (recall as lib/NGT/Optimizer.h:496-507 counts it: an id of the ground truth, or a distance within its k-th)
+    gt, gt_d, _ = whole.linear_search(qs, k)
+    hit = np.mean([np.mean([(ids[q, r] in gt[q]) or dists[q, r] <= gt_d[q, -1] for r in range(k)]) for q in range(nq)])
     assert hit >= 0.9, hit
     assert sh.search(qs, 0, 0.1)[2].sum() == 0
     whole.close()
