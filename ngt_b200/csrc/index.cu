@@ -34,22 +34,62 @@ int ngtgpu_check_device(ngtgpu_index *ix) {
   return NGTGPU_OK;
 }
 
+// the lane the calling thread holds (ngtgpu_lane_guard), and of which index; none: lane 0 of whatever index is asked
+static thread_local ngtgpu_lane *tls_lane = nullptr;
+static thread_local ngtgpu_index *tls_lane_owner = nullptr;
+
+ngtgpu_lane_guard::ngtgpu_lane_guard(ngtgpu_index *index) : ix(index), lane(0), prev(tls_lane) {
+  int got = -1;
+  for (int l = 0; l < NGTGPU_LANES && got < 0; l++)
+    if (ix->lane_mutex[l].try_lock()) got = l;
+  if (got < 0) {
+    ix->lane_mutex[0].lock();
+    got = 0;
+  }
+  lane = got;
+  if (lane > 0) {
+    ngtgpu_lane &L = ix->lanes[lane - 1];
+    if (!L.stream) {
+      cudaSetDevice(ix->device);
+      if (cudaStreamCreateWithFlags(&L.stream, cudaStreamNonBlocking) != cudaSuccess) {
+        ngtgpu_set_error("cudaStreamCreate failed for a search lane");
+        status = NGTGPU_ERR_CUDA;
+      }
+    }
+    tls_lane = &L;
+    tls_lane_owner = ix;
+  } else {
+    tls_lane = nullptr;
+    tls_lane_owner = nullptr;
+  }
+}
+ngtgpu_lane_guard::~ngtgpu_lane_guard() {
+  tls_lane = prev;
+  if (!prev) tls_lane_owner = nullptr;
+  ix->lane_mutex[lane].unlock();
+}
+cudaStream_t ngtgpu_lane_guard::stream() const { return lane > 0 ? ix->lanes[lane - 1].stream : ix->stream; }
+
 int ngtgpu_scratch(ngtgpu_index *ix, int slot, size_t bytes, void **out) {
+  const bool mine = tls_lane && tls_lane_owner == ix;
+  void **ptrs = mine ? tls_lane->d_scratch : ix->d_scratch;
+  size_t *sizes = mine ? tls_lane->scratch_bytes : ix->scratch_bytes;
+  cudaStream_t stream = mine ? tls_lane->stream : ix->stream;
   if (bytes == 0) bytes = 16;
-  if (ix->scratch_bytes[slot] < bytes) {
-    if (ix->d_scratch[slot]) {
-      // buffers may still be in use by work queued on the index stream
-      CUDA_TRY(cudaStreamSynchronize(ix->stream));
-      CUDA_TRY(cudaFree(ix->d_scratch[slot]));
-      ix->d_scratch[slot] = nullptr;
-      ix->scratch_bytes[slot] = 0;
+  if (sizes[slot] < bytes) {
+    if (ptrs[slot]) {
+      // buffers may still be in use by work queued on the lane's stream
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      CUDA_TRY(cudaFree(ptrs[slot]));
+      ptrs[slot] = nullptr;
+      sizes[slot] = 0;
     }
     size_t want = bytes + bytes / 4;
     want = (want + 255) & ~(size_t)255;
-    CUDA_TRY(cudaMalloc(&ix->d_scratch[slot], want));
-    ix->scratch_bytes[slot] = want;
+    CUDA_TRY(cudaMalloc(&ptrs[slot], want));
+    sizes[slot] = want;
   }
-  *out = ix->d_scratch[slot];
+  *out = ptrs[slot];
   return NGTGPU_OK;
 }
 
@@ -153,6 +193,12 @@ extern "C" int ngtgpu_index_destroy(ngtgpu_index *ix) {
   free_tc(ix);
   for (int i = 0; i < SCR_COUNT; i++)
     if (ix->d_scratch[i]) cudaFree(ix->d_scratch[i]);
+  for (auto &L : ix->lanes) {
+    if (L.stream) cudaStreamSynchronize(L.stream);
+    for (int i = 0; i < SCR_COUNT; i++)
+      if (L.d_scratch[i]) cudaFree(L.d_scratch[i]);
+    if (L.stream) cudaStreamDestroy(L.stream);
+  }
   if (ix->stream) cudaStreamDestroy(ix->stream);
   delete ix;
   return NGTGPU_OK;
@@ -160,8 +206,8 @@ extern "C" int ngtgpu_index_destroy(ngtgpu_index *ix) {
 
 extern "C" uint64_t ngtgpu_index_size(const ngtgpu_index *ix) { return ix ? ix->n : 0; }
 extern "C" uint32_t ngtgpu_index_padded_dimension(const ngtgpu_index *ix) { return ix ? ix->padded_dim : 0; }
-extern "C" uint64_t ngtgpu_index_launch_count(const ngtgpu_index *ix) { return ix ? ix->launches : 0; }
-extern "C" uint64_t ngtgpu_index_last_overflows(const ngtgpu_index *ix) { return ix ? ix->last_overflows : 0; }
+extern "C" uint64_t ngtgpu_index_launch_count(const ngtgpu_index *ix) { return ix ? ix->launches.load() : 0; }
+extern "C" uint64_t ngtgpu_index_last_overflows(const ngtgpu_index *ix) { return ix ? ix->last_overflows.load() : 0; }
 
 // ---- row preparation ---------------------------------------------------------------------------------
 // One warp per row: cast `src` (float or uint8, `dim` wide) to the object type, zero pad to the padded

@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -56,6 +58,17 @@ enum ScratchSlot {
   SCR_COUNT = 13
 };
 
+// Concurrent host-pointer searches on one handle (the reference's contract: many threads search a read-only index,
+// SURVEY.md 8b "Threading") each take a LANE: a stream and a scratch set of their own. Lane 0 is the index's own
+// stream / scratch (what the device-pointer entry points and the construction functions use); the others are created
+// the first time two calls overlap. A call that finds every lane busy waits for lane 0.
+#define NGTGPU_LANES 3
+struct ngtgpu_lane {
+  void *d_scratch[32] = {nullptr};
+  size_t scratch_bytes[32] = {0};
+  cudaStream_t stream = nullptr;
+};
+
 struct ngtgpu_index {
   int device = 0;
   int object_type = 0;
@@ -90,13 +103,16 @@ struct ngtgpu_index {
   int onchip_tiers = 2;                // 1: overflow goes straight to the HBM tier (tests)
   bool fuse_seeds = false;             // seed selection inside the lean traversal kernel instead of its own launch
   bool fast_kernel = true;             // first tier of the common case on search_fast_kernel (off: tests of the general kernel)
-  uint64_t last_overflows = 0;         // queries of the last call that fell to the global-memory tier
+  std::atomic<uint64_t> last_overflows{0};   // queries of the last call that fell to the global-memory tier
   // scratch
   void *d_scratch[SCR_COUNT] = {nullptr};
   size_t scratch_bytes[SCR_COUNT] = {0};
   cudaStream_t stream = nullptr;       // owned; host-pointer entry points run here
   int sm_count = 0;
-  uint64_t launches = 0;
+  std::atomic<uint64_t> launches{0};
+  ngtgpu_lane lanes[NGTGPU_LANES - 1];   // lanes 1.. (lane 0 = d_scratch / stream above)
+  std::mutex lane_mutex[NGTGPU_LANES];
+  std::mutex state_mutex;                // timing_events
   // optional device timing of the traversal kernel (bench.py's roofline leg)
   // tensor-core kNN (knn_tc.cu): the row operand packed once per set_objects
   bool tc_enabled = true;
@@ -112,7 +128,18 @@ struct ngtgpu_index {
   std::vector<cudaEvent_t> timing_events;   // start, stop, start, stop ...
 };
 
-int ngtgpu_scratch(ngtgpu_index *ix, int slot, size_t bytes, void **out);
+int ngtgpu_scratch(ngtgpu_index *ix, int slot, size_t bytes, void **out);   // of the calling thread's lane
+
+// Takes a free lane of `ix` for the calling thread until it goes out of scope; ngtgpu_scratch then serves that lane.
+struct ngtgpu_lane_guard {
+  ngtgpu_index *ix;
+  int lane;
+  ngtgpu_lane *prev;
+  explicit ngtgpu_lane_guard(ngtgpu_index *index);
+  ~ngtgpu_lane_guard();
+  cudaStream_t stream() const;
+  int status = NGTGPU_OK;   // creating the lane's stream can fail
+};
 int ngtgpu_check_device(ngtgpu_index *ix);   // cudaSetDevice + sanity
 
 // queries (host or device, float or uint8, `dim` wide) -> padded object-type rows in HBM.

@@ -502,7 +502,9 @@ static int linear_common(ngtgpu_index *ix, const void *queries, int query_type, 
 extern "C" int ngtgpu_linear_search(ngtgpu_index *ix, const void *queries, int query_type, uint32_t nq, uint32_t size,
                                     float radius, uint32_t *ids, float *dists, uint32_t *counts) {
   if (!ix) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "null index handle");
-  return linear_common(ix, queries, query_type, nq, size, radius, ids, dists, counts, false, ix->stream);
+  ngtgpu_lane_guard lane(ix);
+  NGTGPU_TRY(lane.status);
+  return linear_common(ix, queries, query_type, nq, size, radius, ids, dists, counts, false, lane.stream());
 }
 
 extern "C" int ngtgpu_linear_search_device(ngtgpu_index *ix, const void *queries, int query_type, uint32_t nq,

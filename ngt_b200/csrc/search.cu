@@ -231,6 +231,7 @@ int ngtgpu_traverse(ngtgpu_index *ix, const uint8_t *d_queries, uint32_t nq, con
     ix->launches++;
     if (ix->timing && t == 0) {
       CUDA_TRY(cudaEventRecord(ev1, stream));
+      std::lock_guard<std::mutex> lock(ix->state_mutex);
       ix->timing_events.push_back(ev0);
       ix->timing_events.push_back(ev1);
     }
@@ -368,7 +369,8 @@ static int search_common(ngtgpu_index *ix, const void *queries, int query_type, 
   }
   NGTGPU_TRY(ngtgpu_traverse(ix, d_q, nq, params, d_seeds, ns, d_ids, d_dists, d_counts, d_stats, stream));
   if (!on_device) {
-    uint32_t *ws = (uint32_t *)ix->d_scratch[SCR_SEARCH_WS];
+    uint32_t *ws = nullptr;
+    NGTGPU_TRY(ngtgpu_scratch(ix, SCR_SEARCH_WS, 16, (void **)&ws));   // this lane's counters (already sized by the traversal)
     uint32_t h_ws[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     CUDA_TRY(cudaMemcpyAsync(ids, d_ids, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaMemcpyAsync(dists, d_dists, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, stream));
@@ -388,7 +390,9 @@ extern "C" int ngtgpu_search(ngtgpu_index *ix, const void *queries, int query_ty
                              const ngtgpu_search_params *params, const uint32_t *seeds, uint32_t n_seeds, uint32_t *ids,
                              float *dists, uint32_t *counts, uint32_t *stats) {
   if (!ix) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "null index handle");
-  return search_common(ix, queries, query_type, nq, params, seeds, n_seeds, ids, dists, counts, stats, false, ix->stream);
+  ngtgpu_lane_guard lane(ix);   // concurrent callers each get a stream and a scratch set of their own
+  NGTGPU_TRY(lane.status);
+  return search_common(ix, queries, query_type, nq, params, seeds, n_seeds, ids, dists, counts, stats, false, lane.stream());
 }
 
 int ngtgpu_search_keys_device(ngtgpu_index *ix, const void *queries, int query_type, uint32_t nq,
@@ -428,6 +432,7 @@ extern "C" int ngtgpu_index_pop_timing(ngtgpu_index *ix, double *total_ms, uint6
   NGTGPU_TRY(ngtgpu_check_device(ix));
   double sum = 0.0;
   uint64_t cnt = 0;
+  std::lock_guard<std::mutex> lock(ix->state_mutex);
   for (size_t i = 0; i + 1 < ix->timing_events.size(); i += 2) {
     CUDA_TRY(cudaEventSynchronize(ix->timing_events[i + 1]));
     float ms = 0.f;

@@ -376,3 +376,52 @@ def test_create_index_with_nothing_queued_keeps_the_graph(lib, tmp_path):
     assert "ONNG" in open(os.path.join(out, "prf")).read()
     lib.ngt_close_index(ix)
     lib.ngt_destroy_error_object(err)
+
+
+def test_concurrent_searches_on_one_handle(lib, sift5k):
+    """The reference's threading contract: many threads search one read-only index at once. Every thread
+    gets the answers of the same calls made one after another (each concurrent call runs on a lane of its own)."""
+    import threading
+    err = lib.ngt_create_error_object()
+    prop = lib.ngt_create_property(err)
+    assert lib.ngt_set_property_dimension(prop, 128, err)
+    ix = lib.ngt_create_graph_and_tree_in_memory(prop, err)
+    base = np.ascontiguousarray(sift5k["data"].astype(np.float32))
+    assert lib.ngt_batch_append_index(ix, capi.fptr(base), base.shape[0], err) and lib.ngt_create_index(ix, 4, err)
+    u32 = C.POINTER(C.c_uint32)
+    rng = np.random.default_rng(5)
+    batches = [np.ascontiguousarray(base[rng.integers(0, base.shape[0], 700)] + rng.integers(0, 3, (700, 128)).astype(np.float32))
+               for _ in range(6)]
+
+    def run(b, e):
+        ids, ds, cnt = np.zeros((700, 8), np.uint32), np.zeros((700, 8), np.float32), np.zeros(700, np.uint32)
+        ok = lib.ngt_batch_search_index_as_float(ix, capi.fptr(b), 700, 128, 8, 0.1, -1.0, -1, ids.ctypes.data_as(u32), capi.fptr(ds),
+                                                 cnt.ctypes.data_as(u32), e)
+        lids, lds, lcnt = np.zeros((700, 8), np.uint32), np.zeros((700, 8), np.float32), np.zeros(700, np.uint32)
+        ok = ok and lib.ngt_batch_linear_search_index_as_float(ix, capi.fptr(b), 700, 128, 8, -1.0, lids.ctypes.data_as(u32),
+                                                               capi.fptr(lds), lcnt.ctypes.data_as(u32), e)
+        return ok, ids, ds, cnt, lids, lds
+
+    serial = [run(b, err) for b in batches]
+    assert all(s[0] for s in serial)
+    out = [None] * 24
+
+    def worker(t):
+        e = lib.ngt_create_error_object()
+        for rep in range(4):
+            j = (t + rep) % len(batches)
+            out[t * 4 + rep] = (j, run(batches[j], e))
+        lib.ngt_destroy_error_object(e)
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(6)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for j, got in out:
+        assert got[0]
+        for a, b in zip(got[1:], serial[j][1:]):
+            assert (a.view(np.uint32) == b.view(np.uint32)).all()
+    lib.ngt_close_index(ix)
+    lib.ngt_destroy_property(prop)
+    lib.ngt_destroy_error_object(err)
