@@ -278,6 +278,7 @@ typedef struct {
 int ngtgpu_index_build_onng(ngtgpu_index *index, uint32_t knn, uint32_t outgoing, uint32_t incoming, int shortcut_reduction,
                             uint32_t min_edges, ngtgpu_graph_buffers *graph_out, double *seconds);
 int ngtgpu_device_free(void *device_pointer);
+int ngtgpu_device_copy(void *dst, const void *src, uint64_t bytes); /* device to device, synchronous */
 
 /* The sub-graph of the edges with keep[e] != 0, order inside the lists preserved (compaction after
  * ngtgpu_graph_adjust_paths). DEVICE buffers; *out_nnz is a host word. */

@@ -74,6 +74,7 @@ SYMBOLS = {
     "ngtgpu_linear_search_device": (C.c_int, [_P, _P, C.c_int, C.c_uint32, C.c_uint32, C.c_float, _P, _P, _P, _P]),
     "ngtgpu_index_build_onng": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, _P, C.POINTER(C.c_double)]),
     "ngtgpu_device_free": (C.c_int, [_P]),
+    "ngtgpu_device_copy": (C.c_int, [_P, _P, C.c_uint64]),
     # multi-GPU (shard.cu)
     "ngtgpu_comm_get_unique_id": (C.c_int, [_P]),
     "ngtgpu_comm_create": (C.c_int, [C.POINTER(_P), _P, C.c_int, C.c_int, C.c_int]),

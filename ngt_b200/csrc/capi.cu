@@ -236,6 +236,16 @@ float epsilon_from_expected_accuracy(CapiIndex &ix, double accuracy) {
   return e;
 }
 
+// The device an index handle of the C API lives on: NGTGPU_DEVICE when set, else the calling thread's current CUDA device
+// (a one-process-per-GPU host selects its GPU the usual way, with cudaSetDevice).
+int default_device() {
+  const char *env = getenv("NGTGPU_DEVICE");
+  if (env && *env) return atoi(env);
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+  return dev;
+}
+
 // Size of the device seed table that stands in for the DVP-tree (each query starts from its nearest SeedSize pivots).
 // 256 measured best for batch throughput on 1M x 128 (one warp per query walks the table);
 // NGTGPU_PIVOTS overrides.
@@ -247,7 +257,7 @@ size_t seed_table_pivots() {
 
 void upload(CapiIndex &ix) {
   const size_t n = ix.n();
-  if (!ix.gpu) check(ngtgpu_index_create(&ix.gpu, 0, ix.prop.object_type, ix.prop.distance_type, (uint32_t)ix.prop.dimension));
+  if (!ix.gpu) check(ngtgpu_index_create(&ix.gpu, default_device(), ix.prop.object_type, ix.prop.distance_type, (uint32_t)ix.prop.dimension));
   if (n == 0) return;
   check(ngtgpu_index_set_objects(ix.gpu, ix.objects.data(), n, 0, 0));
   std::vector<uint32_t> removed;
@@ -406,12 +416,12 @@ void build_graph(CapiIndex &ix) {
   // createIndex only indexes objects that are not in the graph yet (Index.cpp:645-648): with nothing queued and a
   // graph in place (loaded ONNG, refined or optimised graph) it is a no-op.
   if (ix.pending == 0 && ix.row_ptr.size() == n + 2 && !ix.col.empty()) return;
-  if (!ix.gpu) check(ngtgpu_index_create(&ix.gpu, 0, ix.prop.object_type, ix.prop.distance_type, (uint32_t)ix.prop.dimension));
+  if (!ix.gpu) check(ngtgpu_index_create(&ix.gpu, default_device(), ix.prop.object_type, ix.prop.distance_type, (uint32_t)ix.prop.dimension));
   const size_t rb = ix.record_bytes();
   if (ix.raw_from) {
     // ObjectSpace::normalize (ObjectSpace.h:251-266) on the device for the newly appended rows
     ngtgpu_index *tmp = nullptr;
-    check(ngtgpu_index_create(&tmp, 0, ix.prop.object_type, ix.prop.distance_type, (uint32_t)ix.prop.dimension));
+    check(ngtgpu_index_create(&tmp, default_device(), ix.prop.object_type, ix.prop.distance_type, (uint32_t)ix.prop.dimension));
     int rc = ngtgpu_index_set_objects(tmp, &ix.objects[(ix.raw_from - 1) * rb], n - ix.raw_from + 1, 1, 0);
     if (rc == NGTGPU_OK) rc = ngtgpu_index_get_objects(tmp, 1, n - ix.raw_from + 1, &ix.objects[(ix.raw_from - 1) * rb]);
     ngtgpu_index_destroy(tmp);
@@ -622,7 +632,7 @@ static NGTIndex create_empty(const char *database, NGTProperty prop, NGTError er
       check(ngtgpu_io_write_obj((ix->path + "/obj").c_str(), (uint32_t)ix->record_bytes(), nullptr, 0, nullptr));
       check(ngtgpu_io_write_grp((ix->path + "/grp").c_str(), 0, ix->row_ptr.data(), nullptr, nullptr, nullptr));
     }
-    check(ngtgpu_index_create(&ix->gpu, 0, ix->prop.object_type, ix->prop.distance_type, (uint32_t)ix->prop.dimension));
+    check(ngtgpu_index_create(&ix->gpu, default_device(), ix->prop.object_type, ix->prop.distance_type, (uint32_t)ix->prop.dimension));
     return static_cast<NGTIndex>(ix.release());
   } catch (std::exception &err) {
     std::stringstream ss;

@@ -1190,6 +1190,11 @@ extern "C" int ngtgpu_index_build_onng(ngtgpu_index *ix, uint32_t knn, uint32_t 
   return NGTGPU_OK;
 }
 
+extern "C" int ngtgpu_device_copy(void *dst, const void *src, uint64_t bytes) {
+  if (bytes) CUDA_TRY(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToDevice));
+  return NGTGPU_OK;
+}
+
 extern "C" int ngtgpu_device_free(void *device_pointer) {
   if (device_pointer) CUDA_TRY(cudaFree(device_pointer));
   return NGTGPU_OK;

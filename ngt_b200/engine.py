@@ -156,6 +156,33 @@ class GpuIndex:
     def tensor_core_batches(self):
         return int(self._lib.ngtgpu_index_tensor_core_batches(self._h))
 
+    def build_onng(self, knn, outgoing=10, incoming=120, shortcut_reduction=True, min_edges=0, want_graph=False):
+        """The reference's ONNG recipe on the device for this index's objects (ngtgpu_index_build_onng): exact kNN table,
+        reconstructGraph(outgoing, incoming), path adjustment; the graph is left set on the index.
+        -> {"knn_s", "reconstruct_s", "adjust_paths_s"[, "graph": (row_ptr, col, dist) torch CUDA tensors]}"""
+        import ctypes as C
+
+        class _Graph(C.Structure):
+            _fields_ = [("n", C.c_uint64), ("nnz", C.c_uint64), ("row_ptr", C.c_void_p), ("col", C.c_void_p), ("dist", C.c_void_p)]
+        g = _Graph()
+        sec = (C.c_double * 3)()
+        _lib.check(self._lib.ngtgpu_index_build_onng(self._h, int(knn), int(outgoing), int(incoming), int(bool(shortcut_reduction)),
+                                                     int(min_edges), C.byref(g) if want_graph else None, sec))
+        out = {"knn_s": sec[0], "reconstruct_s": sec[1], "adjust_paths_s": sec[2]}
+        if want_graph:
+            import torch
+            dev = torch.device("cuda", self.device)
+            rp = torch.empty(int(g.n) + 2, dtype=torch.int64, device=dev)
+            col = torch.empty(int(g.nnz), dtype=torch.int32, device=dev)
+            dist = torch.empty(int(g.nnz), dtype=torch.float32, device=dev)
+            # device-to-device copies into torch-owned storage, then the library's buffers are released
+            for dst, src, nbytes in ((rp, g.row_ptr, (int(g.n) + 2) * 8), (col, g.col, int(g.nnz) * 4), (dist, g.dist, int(g.nnz) * 4)):
+                if nbytes:
+                    _lib.check(self._lib.ngtgpu_device_copy(dst.data_ptr(), src, nbytes))
+                _lib.check(self._lib.ngtgpu_device_free(src))
+            out["graph"] = (rp, col, dist)
+        return out
+
     def build_seed_table(self, n_pivots=4096, rng_seed=1):
         _lib.check(self._lib.ngtgpu_index_build_seed_table(self._h, int(n_pivots), int(rng_seed)))
 

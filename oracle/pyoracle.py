@@ -16,7 +16,16 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 PORT_SO = os.path.join(HERE, "libngt_oracle.so")
-REF_SO = os.path.join(HERE, "_ref", "libngt_ref.so")
+REF_SO = os.path.join(HERE, "_ref", "libngt_ref.so")          # -march=x86-64-v3: the reference's AVX2 path (runs anywhere)
+REF_SO_V4 = os.path.join(HERE, "_ref", "v4", "libngt_ref.so")  # -march=x86-64-v4: its AVX-512 path
+
+
+def host_has_avx512():
+    try:
+        flags = next(l for l in open("/proc/cpuinfo") if l.startswith("flags")).split()
+    except (OSError, StopIteration):
+        return False
+    return all(f in flags for f in ("avx512f", "avx512dq", "avx512bw", "avx512vl", "avx512cd"))
 
 # ObjectSpace.h:166-186
 L1, L2, HAMMING, ANGLE, COSINE, NORMALIZED_ANGLE, NORMALIZED_COSINE, JACCARD = range(8)
@@ -155,10 +164,15 @@ class Port:
 class Ref:
     """The unmodified reference behind oracle/ref_shim.cpp."""
 
-    def __init__(self):
-        if not os.path.exists(REF_SO):
-            raise FileNotFoundError(REF_SO + " (build it with `make -C oracle ref` where /root/reference exists)")
-        self.lib = lib = C.CDLL(REF_SO)
+    def __init__(self, isa="avx2"):
+        """isa: "avx2" (default: the build every golden vector was made with), or "native": the AVX-512 build when the
+        host has AVX-512 (what the reference's own -march=native build would use there), else AVX2."""
+        so, self.isa = REF_SO, "avx2 (-march=x86-64-v3)"
+        if isa == "native" and os.path.exists(REF_SO_V4) and host_has_avx512():
+            so, self.isa = REF_SO_V4, "avx512 (-march=x86-64-v4)"
+        if not os.path.exists(so):
+            raise FileNotFoundError(so + " (build it with `make -C oracle ref` where /root/reference exists)")
+        self.lib = lib = C.CDLL(so)
         lib.ref_last_error.restype = C.c_char_p
         lib.ref_build_index.argtypes = [C.c_char_p, _f32p, C.c_size_t, C.c_int, C.c_char, C.c_int, C.c_int,
                                         C.c_int, C.c_char, C.c_int]
