@@ -44,6 +44,7 @@ SYMBOLS = {
     "ngtgpu_index_set_onchip_tiers": (C.c_int, [_P, C.c_int]),
     "ngtgpu_index_set_fast_kernel": (C.c_int, [_P, C.c_int]),
     "ngtgpu_index_set_seed_fusion": (C.c_int, [_P, C.c_int]),
+    "ngtgpu_index_set_fast_shape": (C.c_int, [_P, C.c_int, C.c_int]),
     "ngtgpu_index_set_stage_bytes": (C.c_int, [_P, C.c_uint32]),
     "ngtgpu_index_set_tensor_core": (C.c_int, [_P, C.c_int]),
     "ngtgpu_index_tensor_core_batches": (C.c_uint64, [_P]),

@@ -102,6 +102,8 @@ struct ngtgpu_index {
   uint32_t stage_bytes = 16384;        // shared-memory staging area the TMA engine fills with neighbour rows
   int onchip_tiers = 2;                // 1: overflow goes straight to the HBM tier (tests)
   bool fuse_seeds = false;             // seed selection inside the lean traversal kernel instead of its own launch
+  int fast_warps = 0;                  // warps per query of the lean kernel: 0 = two when a round fits 64 threads, else four; 2 or 4 as asked (ngtgpu_index_set_fast_shape)
+  int fast_ctas_per_sm = 0;            // cap on resident CTAs per SM of its first tier (0: what fits)
   bool fast_kernel = true;             // first tier of the common case on search_fast_kernel (off: tests of the general kernel)
   std::atomic<uint64_t> last_overflows{0};   // queries of the last call that fell to the global-memory tier
   // scratch

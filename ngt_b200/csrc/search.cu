@@ -20,11 +20,11 @@ extern template cudaError_t search_dispatch<ACC_U8_L2>(const SearchArgs &, const
 extern template cudaError_t search_dispatch<ACC_U8_HAM>(const SearchArgs &, const SearchLaunch &, int, int *);
 
 // the lean kernel of the common case (search_fast.cuh)
-extern template cudaError_t search_fast_dispatch<ACC_F_L2>(const SearchArgs &, int, unsigned, size_t, cudaStream_t, int, int *);
-extern template cudaError_t search_fast_dispatch<ACC_F_DOT>(const SearchArgs &, int, unsigned, size_t, cudaStream_t, int, int *);
-extern template cudaError_t search_fast_dispatch<ACC_F_COS>(const SearchArgs &, int, unsigned, size_t, cudaStream_t, int, int *);
-extern template cudaError_t search_fast_dispatch<ACC_U8_L2>(const SearchArgs &, int, unsigned, size_t, cudaStream_t, int, int *);
-extern template cudaError_t search_fast_dispatch<ACC_U8_HAM>(const SearchArgs &, int, unsigned, size_t, cudaStream_t, int, int *);
+extern template cudaError_t search_fast_dispatch<ACC_F_L2>(const SearchArgs &, int, int, unsigned, size_t, cudaStream_t, int, int *);
+extern template cudaError_t search_fast_dispatch<ACC_F_DOT>(const SearchArgs &, int, int, unsigned, size_t, cudaStream_t, int, int *);
+extern template cudaError_t search_fast_dispatch<ACC_F_COS>(const SearchArgs &, int, int, unsigned, size_t, cudaStream_t, int, int *);
+extern template cudaError_t search_fast_dispatch<ACC_U8_L2>(const SearchArgs &, int, int, unsigned, size_t, cudaStream_t, int, int *);
+extern template cudaError_t search_fast_dispatch<ACC_U8_HAM>(const SearchArgs &, int, int, unsigned, size_t, cudaStream_t, int, int *);
 
 extern template cudaError_t seed_select_dispatch<ACC_F_L2>(const SeedArgs &, cudaStream_t);
 extern template cudaError_t seed_select_dispatch<ACC_F_DOT>(const SeedArgs &, cudaStream_t);
@@ -43,14 +43,14 @@ static cudaError_t dispatch_seeds(int acc, const SeedArgs &a, cudaStream_t strea
   return cudaErrorInvalidValue;
 }
 
-static cudaError_t dispatch_fast(int acc, const SearchArgs &a, int ch, unsigned grid, size_t smem, cudaStream_t stream,
+static cudaError_t dispatch_fast(int acc, const SearchArgs &a, int ch, int warps, unsigned grid, size_t smem, cudaStream_t stream,
                                  int op, int *blocks) {
   switch (acc) {
-    case ACC_F_L2: return search_fast_dispatch<ACC_F_L2>(a, ch, grid, smem, stream, op, blocks);
-    case ACC_F_DOT: return search_fast_dispatch<ACC_F_DOT>(a, ch, grid, smem, stream, op, blocks);
-    case ACC_F_COS: return search_fast_dispatch<ACC_F_COS>(a, ch, grid, smem, stream, op, blocks);
-    case ACC_U8_L2: return search_fast_dispatch<ACC_U8_L2>(a, ch, grid, smem, stream, op, blocks);
-    case ACC_U8_HAM: return search_fast_dispatch<ACC_U8_HAM>(a, ch, grid, smem, stream, op, blocks);
+    case ACC_F_L2: return search_fast_dispatch<ACC_F_L2>(a, ch, warps, grid, smem, stream, op, blocks);
+    case ACC_F_DOT: return search_fast_dispatch<ACC_F_DOT>(a, ch, warps, grid, smem, stream, op, blocks);
+    case ACC_F_COS: return search_fast_dispatch<ACC_F_COS>(a, ch, warps, grid, smem, stream, op, blocks);
+    case ACC_U8_L2: return search_fast_dispatch<ACC_U8_L2>(a, ch, warps, grid, smem, stream, op, blocks);
+    case ACC_U8_HAM: return search_fast_dispatch<ACC_U8_HAM>(a, ch, warps, grid, smem, stream, op, blocks);
   }
   return cudaErrorInvalidValue;
 }
@@ -202,16 +202,22 @@ int ngtgpu_traverse(ngtgpu_index *ix, const uint8_t *d_queries, uint32_t nq, con
                       a.coef >= 1.0f && k <= 32 && n_seeds <= 32 * FAST_WARPS && cap <= 32 * FAST_WARPS &&   // one edge per thread
                       (ix->n + 1) * (uint64_t)ix->row_bytes < (1ull << 36);   // 32-bit row offsets in 16-byte units
     const int fast_ch = ix->chunks <= 8 ? 1 : ix->chunks <= 16 ? 2 : 4;
-    if (fast) smem = (size_t)FAST_WARPS * FAST_STAGE_PER_WARP + (size_t)a.queue_cap * 8;
+    // two warps per query (16 CTAs per SM) for narrow rows whose rounds fit 64 threads (edge cap and seeds <= 64)
+    // two warps per query whenever a round fits 64 threads (measured: uint8 128-byte rows 4.09 -> 3.35 ms per 10k batch,
+    // 12.5M shard 7.66 -> 6.73 ms, glove-shape 448-byte rows 4.03 -> 3.74 ms); fast_warps = 4 keeps four
+    const bool two_fit = cap <= 64 && n_seeds <= 64;
+    const int fast_w = two_fit && ix->fast_warps != 4 ? 2 : FAST_WARPS;
+    if (fast) smem = (size_t)fast_w * fast_stage_per_warp(fast_ch, fast_w) + (size_t)a.queue_cap * 8;
     if (smem > 200 * 1024)
       NGTGPU_FAIL(NGTGPU_ERR_INVALID, "search: working set does not fit shared memory; lower queue_cap/size");
     l.smem = smem;
     int blocks = 0;
-    cudaError_t e = fast ? dispatch_fast(ix->acc_kind, a, fast_ch, 0, smem, stream, 1, &blocks)
+    cudaError_t e = fast ? dispatch_fast(ix->acc_kind, a, fast_ch, fast_w, 0, smem, stream, 1, &blocks)
                          : dispatch(ix->acc_kind, a, l, 1, &blocks);
     if (e != cudaSuccess) NGTGPU_FAIL(NGTGPU_ERR_CUDA, std::string("search occupancy query: ") + cudaGetErrorString(e));
     if (blocks < 1) blocks = 1;
-    if (t > 0 && blocks > (fast ? 4 : 2)) blocks = fast ? 4 : 2;   // the overflow tier serves few queries: keep its slabs small
+    if (t > 0 && blocks > (fast ? 4 : 2)) blocks = fast ? 4 : 2;
+    if (t == 0 && fast && ix->fast_ctas_per_sm > 0 && blocks > ix->fast_ctas_per_sm) blocks = ix->fast_ctas_per_sm;   // the overflow tier serves few queries: keep its slabs small
     uint64_t grid = (uint64_t)blocks * ix->sm_count;
     if (grid > nq) grid = nq;
     if (grid == 0) return NGTGPU_OK;
@@ -226,7 +232,7 @@ int ngtgpu_traverse(ngtgpu_index *ix, const uint8_t *d_queries, uint32_t nq, con
       CUDA_TRY(cudaEventCreate(&ev1));
       CUDA_TRY(cudaEventRecord(ev0, stream));
     }
-    e = fast ? dispatch_fast(ix->acc_kind, a, fast_ch, l.grid, smem, stream, 0, nullptr) : dispatch(ix->acc_kind, a, l, 0, nullptr);
+    e = fast ? dispatch_fast(ix->acc_kind, a, fast_ch, fast_w, l.grid, smem, stream, 0, nullptr) : dispatch(ix->acc_kind, a, l, 0, nullptr);
     if (e != cudaSuccess) NGTGPU_FAIL(NGTGPU_ERR_CUDA, std::string("search kernel launch: ") + cudaGetErrorString(e));
     ix->launches++;
     if (ix->timing && t == 0) {

@@ -27,14 +27,12 @@
 #pragma once
 #include "search.cuh"
 
+// Warps per query (CTA), W: 4 (8 CTAs per SM) for every row width; 2 (16 CTAs per SM: twice the queries in flight) is
+// offered for rows of <= 128 bytes with <= 64 edges and seeds per round, where a round moves a quarter of the bytes and
+// its latency chain, not the bandwidth, sets the pace. 3 warps x 10 CTAs/SM measured the same as 4 x 8 on 512-byte rows.
+#define FAST_WARPS 4
 #define FAST_STAGE_PER_WARP 4096u
-#ifndef FAST_WARPS
-#define FAST_WARPS 4      // warps per query (CTA); 3 warps x 10 CTAs/SM measured the same as 4 x 8
-#endif
-#define FAST_THREADS (FAST_WARPS * 32)
-#ifndef FAST_MIN_CTAS
-#define FAST_MIN_CTAS (32 / FAST_WARPS)   // resident CTAs per SM the register allocation aims at
-#endif
+__host__ __device__ constexpr uint32_t fast_stage_per_warp(int ch, int w) { return (ch == 1 && w == 2) ? 2048u : 4096u; }
 
 // ---- visited hash: the bucket in one 256-bit load -------------------------------------------------------
 // Slots of a bucket are taken in increasing order (hash_insert tries slot i only after slot i - 1 was seen occupied),
@@ -86,16 +84,17 @@ __device__ __forceinline__ void cp_async_wait_group() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-template <int ACC, int CH>
-__global__ void __launch_bounds__(FAST_THREADS, FAST_MIN_CTAS) search_fast_kernel(const SearchArgs a) {
+template <int ACC, int CH, int W>
+__global__ void __launch_bounds__(W * 32, 32 / W) search_fast_kernel(const SearchArgs a) {
+  constexpr uint32_t SPW = fast_stage_per_warp(CH, W);         // staging ring of one warp
   constexpr uint32_t SROW = 128u * CH;                         // staging stride of a row
   constexpr uint32_t GBYTES = 4u * SROW;                       // one group = four rows
-  constexpr int NB = (int)(FAST_STAGE_PER_WARP / GBYTES);      // ring depth per warp: 2, 4 or 8
+  constexpr int NB = (int)(SPW / GBYTES);      // ring depth per warp: 2, 4 or 8
   constexpr uint32_t RPI = 4u / CH;                            // rows per copy instruction
   constexpr uint32_t LPR = 8u * CH;                            // lanes per row in a copy instruction
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  __shared__ __align__(16) uint32_t s_wids[FAST_WARPS][32 + 4];   // new ids per warp
-  __shared__ uint32_t s_wcnt[FAST_WARPS], s_wval[FAST_WARPS];
+  __shared__ __align__(16) uint32_t s_wids[W][32 + 4];   // new ids per warp
+  __shared__ uint32_t s_wcnt[W], s_wval[W];
   __shared__ uint64_t s_cand_keys[SEARCH_CMAX];
   __shared__ __align__(16) uint32_t s_edges[2][SEARCH_HEAD];   // edge lists of the round / of the expected next node
   __shared__ uint32_t s_key_n;
@@ -115,14 +114,14 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_MIN_CTAS) search_fast_kerne
   const int lane = tid & 31;
   const int warp = tid >> 5;
 
-  uint8_t *stage = smem_raw;                                                   // 4 x FAST_STAGE_PER_WARP
-  uint64_t *queue = reinterpret_cast<uint64_t *>(smem_raw + FAST_WARPS * FAST_STAGE_PER_WARP);
+  uint8_t *stage = smem_raw;                                                   // 4 x SPW
+  uint64_t *queue = reinterpret_cast<uint64_t *>(smem_raw + W * SPW);
   uint32_t *hash = a.hash_slabs + ((size_t)blockIdx.x << a.hash_bits);
   const uint32_t bucket_bits = a.hash_bits - 3;
   const uint32_t take_head = a.edge_cap < SEARCH_HEAD ? a.edge_cap : SEARCH_HEAD;
 
   // this lane's constant part of the row copies and reads
-  const uint32_t wstage_s = (uint32_t)__cvta_generic_to_shared(stage + (size_t)warp * FAST_STAGE_PER_WARP);
+  const uint32_t wstage_s = (uint32_t)__cvta_generic_to_shared(stage + (size_t)warp * SPW);
   const uint32_t cp_row = (uint32_t)lane / LPR;                   // row inside one copy instruction
   const uint32_t cp_chunk = (uint32_t)lane % LPR;
   const uint32_t cp_dst = wstage_s + cp_row * SROW + cp_chunk * 16u;
@@ -148,7 +147,7 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_MIN_CTAS) search_fast_kerne
     if (q == 0xffffffffu) break;
     {
       uint4 *h4 = reinterpret_cast<uint4 *>(hash);
-      for (uint32_t i = tid; i < (1u << a.hash_bits) / 4; i += FAST_THREADS) h4[i] = zero16();
+      for (uint32_t i = tid; i < (1u << a.hash_bits) / 4; i += (W * 32)) h4[i] = zero16();
     }
     const uint8_t *qrow = a.queries + (size_t)q * a.row_bytes;
     uint4 q8[CH];   // lane (rr, j) holds query chunks j, j + 8, ...
@@ -176,7 +175,7 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_MIN_CTAS) search_fast_kerne
       // its launch): every warp scans a quarter of the table, four rows per step read straight from L1/L2, and keeps
       // its k smallest keys sorted one per lane; warp 0 merges the lists into the first round's edge list
       uint64_t wres = KEY_NONE, wthr = KEY_NONE;
-      for (uint32_t p0 = 4u * (uint32_t)warp; p0 < a.n_pivots; p0 += 4u * FAST_WARPS) {
+      for (uint32_t p0 = 4u * (uint32_t)warp; p0 < a.n_pivots; p0 += 4u * W) {
         const uint32_t row = p0 + rr;
         const bool valid = row < a.n_pivots;
         const uint8_t *rp = a.pivots + (size_t)(valid ? row : 0u) * a.row_bytes;
@@ -229,7 +228,7 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_MIN_CTAS) search_fast_kerne
       __syncthreads();
       if (warp == 0) {
         uint64_t mres = KEY_NONE, mthr = KEY_NONE;
-        for (int w = 0; w < FAST_WARPS; w++) {
+        for (int w = 0; w < W; w++) {
           const uint64_t key = s_cand_keys[w * 32 + lane];
           uint32_t m = __ballot_sync(0xffffffffu, key < mthr);
           while (m) {
@@ -287,10 +286,10 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_MIN_CTAS) search_fast_kerne
         bool overflow = false, finished = false;
         if (rounds_done) {
 #pragma unroll
-          for (int w = 0; w < FAST_WARPS; w++) cand_n += s_wcnt[w];
+          for (int w = 0; w < W; w++) cand_n += s_wcnt[w];
           if (head_round) {
 #pragma unroll
-            for (int w = 0; w < FAST_WARPS; w++) st_edge += s_wval[w];
+            for (int w = 0; w < W; w++) st_edge += s_wval[w];
           }
         }
         visited_n += cand_n;
@@ -430,7 +429,7 @@ __global__ void __launch_bounds__(FAST_THREADS, FAST_MIN_CTAS) search_fast_kerne
       bp.bucket = 0;
       bp.slot = 0;
       {
-        const uint32_t e = (uint32_t)FAST_WARPS * (uint32_t)lane + (uint32_t)warp;   // edges dealt round-robin: the warps get equal shares
+        const uint32_t e = (uint32_t)W * (uint32_t)lane + (uint32_t)warp;   // edges dealt round-robin: the warps get equal shares
         const uint32_t nid = e < s_take ? s_edges[s_buf][e] : 0u;
         const bool valid = nid != 0u && nid <= a.n;
         bool isnew = false;
@@ -710,22 +709,26 @@ cudaError_t seed_select_dispatch(const SeedArgs &a, cudaStream_t stream) {
 }
 
 // op == 0: launch, op == 1: occupancy query
-template <int ACC, int CH>
+template <int ACC, int CH, int W>
 static cudaError_t fast_one(const SearchArgs &a, unsigned grid, size_t smem, cudaStream_t stream, int op, int *blocks) {
-  cudaError_t e = cudaFuncSetAttribute(search_fast_kernel<ACC, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(search_fast_kernel<ACC, CH, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(search_fast_kernel<ACC, CH>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  e = cudaFuncSetAttribute(search_fast_kernel<ACC, CH, W>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   if (e != cudaSuccess) return e;
-  if (op == 1) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, search_fast_kernel<ACC, CH>, FAST_THREADS, smem);
-  search_fast_kernel<ACC, CH><<<grid, FAST_THREADS, smem, stream>>>(a);
+  if (op == 1) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, search_fast_kernel<ACC, CH, W>, W * 32, smem);
+  search_fast_kernel<ACC, CH, W><<<grid, W * 32, smem, stream>>>(a);
   return cudaGetLastError();
 }
 
+// ch: chunks per lane of a row's eight lanes (1, 2, 4); warps per query: 4 or 2
 template <int ACC>
-cudaError_t search_fast_dispatch(const SearchArgs &a, int ch, unsigned grid, size_t smem, cudaStream_t stream, int op,
+cudaError_t search_fast_dispatch(const SearchArgs &a, int ch, int warps, unsigned grid, size_t smem, cudaStream_t stream, int op,
                                  int *blocks) {
-  if (ch == 1) return fast_one<ACC, 1>(a, grid, smem, stream, op, blocks);
-  if (ch == 2) return fast_one<ACC, 2>(a, grid, smem, stream, op, blocks);
-  if (ch == 4) return fast_one<ACC, 4>(a, grid, smem, stream, op, blocks);
+  if (ch == 1 && warps == 2) return fast_one<ACC, 1, 2>(a, grid, smem, stream, op, blocks);
+  if (ch == 2 && warps == 2) return fast_one<ACC, 2, 2>(a, grid, smem, stream, op, blocks);
+  if (ch == 4 && warps == 2) return fast_one<ACC, 4, 2>(a, grid, smem, stream, op, blocks);
+  if (ch == 1) return fast_one<ACC, 1, 4>(a, grid, smem, stream, op, blocks);
+  if (ch == 2) return fast_one<ACC, 2, 4>(a, grid, smem, stream, op, blocks);
+  if (ch == 4) return fast_one<ACC, 4, 4>(a, grid, smem, stream, op, blocks);
   return cudaErrorInvalidValue;
 }
