@@ -10,20 +10,28 @@
 // (q_lo.x_lo, relative 2^-16, is dropped). When every value is exactly a bf16 number (SIFT-like integer
 // data) a single segment is used and the products are exact.
 //
-// The tensor cores only FILTER. Each epilogue thread owns one query (one TMEM lane): it keeps the k
-// smallest approximate scores it has seen in a private max-heap (shared memory, conflict-free) and appends
-// every row whose score is within an error margin of the current k-th score to the query's candidate list.
+// The tensor cores only FILTER. Each epilogue thread owns one query (one TMEM lane) and a buffer of (score, row) pairs
+// in global memory (L2-resident): a row whose approximate score is within an error margin of the query's running
+// threshold is appended with two predicated instructions; when a buffer is nearly full the WARP compacts it together
+// (its 32 lanes hold the entries in registers, find the k-th smallest score by bisection over the ordered bit
+// patterns with one warp-wide add per step, and write back the entries within the margin of it), which also
+// refreshes the threshold. Between compactions the threshold is stale, i.e. larger: the tests admit a superset. There
+// is no per-thread heap and no shared-memory state; what is left in the buffers at the end IS the candidate list
+// (k plus the few rows inside the margin).
 // A second kernel re-evaluates the candidates with the engine's one exact summation order
 // (ngtgpu_internal.cuh) and selects the top k by (distance, id), so results are bit-identical to the
 // CUDA-core scan (scan.cu) and to the reference where that is exact. A true k-nearest row cannot be dropped:
 // its approximate score is <= d_k(1+e), the running threshold is >= d_k(1-e), and the margin is > 2e.
 //
-// Kernel anatomy (192 threads, 1 CTA/SM): warps 0-3 epilogue (tcgen05.ld, 32 TMEM lanes each), warp 4
-// producer (cp.async.bulk of pre-swizzled 16 KB operand tiles, mbarrier complete_tx), warp 5 MMA issuer
-// (one elected thread; M=128, N=128, K=16 per instruction, SWIZZLE_128B K-major descriptors). The query
-// operand stays resident in shared memory, row tiles stream through a 4-stage ring, two 128-column
-// accumulators alternate in TMEM so the epilogue of tile t overlaps the MMAs of tile t+1.
+// Kernel anatomy (320 threads, 1 CTA/SM): warps 0-7 epilogue in two groups of four (tcgen05.ld, 32 TMEM lanes per
+// warp; group g owns accumulator g, i.e. the even / the odd row tiles, with buffers and thresholds of its own, so the
+// two groups never share state), warp 8 producer (cp.async.bulk of pre-swizzled 16 KB operand tiles, mbarrier
+// complete_tx), warp 9 MMA issuer (one elected thread; M=128, N=128, K=16 per instruction, SWIZZLE_128B K-major
+// descriptors). The query operand stays resident in shared memory, row tiles stream through a ring of up to six
+// stages, and the two 128-column accumulators in TMEM alternate, so each epilogue group has two tile times per tile.
+#include <algorithm>
 #include <cfloat>
+#include <cstdlib>
 #include <cstring>
 #include <cuda_bf16.h>
 
@@ -32,11 +40,12 @@
 #define TC_TILE 128            // queries per CTA tile == rows per streamed tile
 #define TC_KCHUNK 64           // bf16 elements per swizzle row (128 bytes)
 #define TC_TILE_BYTES (TC_TILE * TC_KCHUNK * 2)   // 16 KB: one operand tile of one k-chunk
-#define TC_STAGES 4
+#define TC_STAGES 10
 #define TC_MAX_KCHUNKS 6       // resident query operand <= 96 KB
-#define TC_MAX_K 128           // heap of k floats per query in shared memory
-#define TC_THREADS 192
-#define TC_CAND_CAP 2048       // candidate ids per (query, split)
+#define TC_MAX_K 128
+#define TC_EPI_WARPS 8          // two groups of four: group g takes the tiles whose accumulator is g
+#define TC_THREADS ((TC_EPI_WARPS + 2) * 32)
+#define TC_CAND_MAX 512        // largest (score, row) buffer per (query, split): 16 entries per lane during a compaction
 
 struct TcPacked {
   uint8_t *tiles = nullptr;    // [n_tiles][kchunks][16 KB], SWIZZLE_128B K-major images
@@ -227,6 +236,27 @@ __device__ __forceinline__ void tc_tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) 
       : "r"(taddr));
 }
 __device__ __forceinline__ void tc_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// min / max of 32 values as a tree (five dependent levels instead of a chain of 32)
+__device__ __forceinline__ float tc_min32(const uint32_t (&v)[32]) {
+  float m[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) m[i] = fminf(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+#pragma unroll
+  for (int w = 8; w > 0; w >>= 1)
+#pragma unroll
+    for (int i = 0; i < w; i++) m[i] = fminf(m[i], m[i + w]);
+  return m[0];
+}
+__device__ __forceinline__ float tc_max32(const uint32_t (&v)[32]) {
+  float m[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) m[i] = fmaxf(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+#pragma unroll
+  for (int w = 8; w > 0; w >>= 1)
+#pragma unroll
+    for (int i = 0; i < w; i++) m[i] = fmaxf(m[i], m[i + w]);
+  return m[0];
+}
 
 // ---- the filter kernel ------------------------------------------------------------------------------------
 struct TcArgs {
@@ -247,59 +277,101 @@ struct TcArgs {
   uint32_t qtiles;
   uint32_t nsplit;
   uint64_t tiles_per_split;
-  uint32_t *cand;           // [nq][nsplit][TC_CAND_CAP] row indices (0-based)
-  uint32_t *cand_n;         // [nq][nsplit]; 0xffffffff = overflow
+  int debug_skip;           // development: 1 = the epilogue only releases the accumulators (timing of the MMA side alone)
+  uint32_t cap;             // entries of one (query, split) buffer: a multiple of 32, <= TC_CAND_MAX
+  uint2 *cand;              // [nq][nsplit][2 groups][cap] (score bits, row index 0-based)
+  uint32_t *cand_n;         // [nq][nsplit][2]; 0xffffffff = overflow
 };
 
-// A row passed the filter: append it to the query's candidate list and keep the max-heap of the k smallest
-// approximate scores. Kept out of line on purpose: the column loop of the epilogue must stay small enough for
-// the instruction cache (inlining 128 copies of this made the kernel instruction-fetch bound).
-// st: per-thread words in shared memory, stride 128: [0] heap size, [1] candidates, [2] overflow flag.
-__device__ __noinline__ float tc_push(float score, uint32_t row, float *H, uint32_t *st, uint32_t k, uint32_t *mycand,
-                                      uint32_t skip_row, float thr) {
-  if (row == skip_row) return thr;
-  uint32_t cn = st[128];
-  if (cn < TC_CAND_CAP) {
-    mycand[cn] = row;
-    st[128] = cn + 1;
-  } else {
-    st[256] = 1u;
-  }
-  uint32_t hn = st[0];
-  if (hn < k) {
-    uint32_t i = hn;
-    st[0] = hn + 1;
-    while (i > 0) {
-      uint32_t p = (i - 1) >> 1;
-      float pv = H[p * 128];
-      if (pv >= score) break;
-      H[i * 128] = pv;
-      i = p;
+// Compaction of ONE query's buffer by the whole warp (`buf`, `cnt` are warp-uniform: broadcast from the owning lane).
+// The K-th smallest score of the buffer becomes the query's threshold; entries within `margin` of it stay (everything else
+// can never be within the margin of a later, smaller threshold). Returns the new count; *thr_out is left alone when the
+// buffer holds fewer than K entries.
+__device__ __noinline__ uint32_t tc_compact(uint2 *buf, uint32_t cnt, uint32_t K, float margin, float *thr_out, int lane) {
+  constexpr int PER = TC_CAND_MAX / 32;
+  uint32_t o[PER], r[PER];
+  __syncwarp();   // the owner's appends are ordered before the other lanes' reads
+#pragma unroll
+  for (int i = 0; i < PER; i++) {
+    const uint32_t idx = (uint32_t)i * 32u + (uint32_t)lane;
+    o[i] = 0xffffffffu;
+    r[i] = 0u;
+    if (idx < cnt) {
+      const uint2 e = __ldcg(buf + idx);
+      o[i] = ord_of_float(__uint_as_float(e.x));
+      r[i] = e.y;
     }
-    H[i * 128] = score;
-    return hn + 1 == k ? H[0] : thr;
   }
-  if (score < H[0]) {
-    uint32_t i = 0;
-    for (;;) {
-      uint32_t c = 2 * i + 1;
-      if (c >= k) break;
-      float cv = H[c * 128];
-      if (c + 1 < k) {
-        float c2 = H[(c + 1) * 128];
-        if (c2 > cv) {
-          c++;
-          cv = c2;
-        }
+  uint32_t limit = 0xfffffffeu;   // fewer than K entries: keep them all
+  if (cnt >= K) {
+    // the K-th smallest ordered value, bit by bit: the largest v with fewer than K entries below it
+    uint32_t ans = 0;
+#pragma unroll 1
+    for (int b = 31; b >= 0; b--) {
+      const uint32_t c = ans | (1u << b);
+      uint32_t below = 0;
+#pragma unroll
+      for (int i = 0; i < PER; i++) below += o[i] < c ? 1u : 0u;
+      below = __reduce_add_sync(0xffffffffu, below);
+      if (below < K) ans = c;
+    }
+    const float kth = float_of_ord(ans);
+    *thr_out = kth;
+    limit = ord_of_float(kth + margin);
+  }
+  uint32_t mine = 0;
+#pragma unroll
+  for (int i = 0; i < PER; i++) mine += o[i] <= limit ? 1u : 0u;
+  uint32_t incl = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t up = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += up;
+  }
+  uint32_t pos = incl - mine;
+  __syncwarp();   // every lane has its entries in registers before anything is overwritten
+#pragma unroll
+  for (int i = 0; i < PER; i++)
+    if (o[i] <= limit) {
+      __stcg(buf + pos, make_uint2(__float_as_uint(float_of_ord(o[i])), r[i]));
+      pos++;
+    }
+  return __shfl_sync(0xffffffffu, incl, 31);
+}
+
+// Eight columns of one query against its threshold snapshot; out of line on purpose: the column loop of the epilogue must
+// stay small (eight warps in two phases share the instruction cache; with the appends inlined sixteen times the kernel was
+// instruction-fetch bound: 58 % I-cache hit rate, 6 "no instruction" stall cycles per issue).
+template <int MODE>
+__device__ __noinline__ uint32_t tc_append8(uint4 lo, uint4 hi, float thr, float margin, float qn, uint32_t rbase,
+                                             const float *__restrict__ b_norms, uint2 *buf, uint32_t cnt) {
+  const uint32_t v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+  if (MODE == 0) {
+    const float lim = thr + margin;   // the accumulator already is ||q||^2 + ||x||^2 - 2 q.x
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      if (__uint_as_float(v[j]) <= lim) {
+        __stcg(buf + cnt, make_uint2(v[j], rbase + j));
+        cnt++;
       }
-      if (cv <= score) break;
-      H[i * 128] = cv;
-      i = c;
+  } else {
+    const float4 *rn4 = reinterpret_cast<const float4 *>(b_norms + rbase);
+    const float4 r0 = __ldg(rn4), r1 = __ldg(rn4 + 1);
+    const float rns[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const float rn = rns[j];   // +inf for padding and empty slots: never passes
+      const float dot = __uint_as_float(v[j]);
+      float score;
+      if (MODE == 1) score = rn < 3.0e38f ? -dot : __int_as_float(0x7fc00000);   // NaN never passes
+      else score = rn < 3.0e38f ? -dot * rsqrtf(qn * rn) : __int_as_float(0x7fc00000);
+      if (score - margin <= thr) {
+        __stcg(buf + cnt, make_uint2(__float_as_uint(score), rbase + j));
+        cnt++;
+      }
     }
-    H[i * 128] = score;
-    return H[0];
   }
-  return thr;
+  return cnt;
 }
 
 template <int MODE>
@@ -318,9 +390,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_filter_kernel(const TcAr
   const uint64_t ntiles = t_end > t_begin ? t_end - t_begin : 0;
 
   uint8_t *sA = smem;                                              // kchunks x 16 KB (resident)
-  uint8_t *sB = smem + (size_t)a.kchunks * TC_TILE_BYTES;         // TC_STAGES x 16 KB ring
-  float *heap = reinterpret_cast<float *>(sB + (size_t)a.stages * TC_TILE_BYTES);   // [k][128]
-  uint32_t *state = reinterpret_cast<uint32_t *>(heap + (size_t)a.k * 128);          // [3][128]
+  uint8_t *sB = smem + (size_t)a.kchunks * TC_TILE_BYTES;         // a.stages x 16 KB ring
 
   if (tid == 0) {
     for (int i = 0; i < TC_STAGES; i++) {
@@ -334,7 +404,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_filter_kernel(const TcAr
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == TC_EPI_WARPS) {
     // 256 columns: two 128-column fp32 accumulators
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(256u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -344,7 +414,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_filter_kernel(const TcAr
   tc_fence_after();
   const uint32_t tmem_base = s_tmem;
 
-  if (warp == 4) {
+  if (warp == TC_EPI_WARPS) {
     // ===================== producer =====================
     if (lane == 0 && ntiles) {
       tc_mbar_expect_tx(&bar_a, a.kchunks * TC_TILE_BYTES);
@@ -361,7 +431,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_filter_kernel(const TcAr
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == TC_EPI_WARPS + 1) {
     // ===================== MMA issuer =====================
     if (lane == 0 && ntiles) {
       // kind::f16, A = B = BF16, D = F32, K-major both, N = 128, M = 128 (cute::UMMA::InstrDescriptor)
@@ -390,88 +460,110 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_filter_kernel(const TcAr
       }
     }
   } else {
-    // ===================== epilogue: one query per thread =====================
-    const uint32_t q = qtile * TC_TILE + tid;       // tid in [0,128)
+    // ===================== epilogue: one query per thread and group =====================
+    const uint32_t g = (uint32_t)warp >> 2;            // group: the tiles t = g, g + 2, ... (accumulator g)
+    const uint32_t qlane = (uint32_t)tid & 127u;       // TMEM lane == query of the tile
+    const uint32_t q = qtile * TC_TILE + qlane;
     const bool q_ok = q < a.nq;
-    const float qn = a.a_norms[(size_t)qtile * TC_TILE + tid];
-    // k-th smallest approximate score so far; "nothing yet" is a large finite number so that the huge scores of
-    // padding / empty rows (3e38) never pass
+    const float qn = a.a_norms[(size_t)qtile * TC_TILE + qlane];
+    // K-th smallest approximate score so far; "nothing yet" is a large finite number so that the huge scores of
+    // padding / empty rows (3e38) never pass. When the queries are stored rows the row itself (score ~ 0) is one of
+    // the K = k + 1 smallest and is dropped by the re-evaluation.
+    const uint32_t K = a.k + (a.exclude_self ? 1u : 0u);
     float thr = q_ok ? 1.0e37f : -__int_as_float(0x7f800000);
-    float *H = heap + tid;                           // H[i * 128]
-    uint32_t *st = state + tid;
-    st[0] = 0u;
-    st[128] = 0u;
-    st[256] = 0u;
-    uint32_t *mycand = a.cand + ((size_t)q * a.nsplit + split) * TC_CAND_CAP;
-    const uint32_t skip_row = a.exclude_self ? a.self_base + q : 0xffffffffu;
+    uint32_t cnt = 0;
+    bool bad = false;
+    const size_t list = ((size_t)(q_ok ? q : 0u) * a.nsplit + split) * 2 + g;
+    uint2 *mybuf = a.cand + list * a.cap;
     const float m2 = 2.0f * a.rel_margin;
-    const float mq = m2 * (qn + a.max_row_norm);   // MODE 0: per-query bound of twice the error
-    for (uint64_t t = 0; t < ntiles; t++) {
-      const uint32_t acc = (uint32_t)(t & 1);
-      tc_mbar_wait(&bar_tfull[acc], (uint32_t)((t >> 1) & 1));
+    const float margin = MODE == 0 ? m2 * (qn + a.max_row_norm) : m2;   // MODE 0: per-query bound of twice the error
+    const uint32_t room = a.cap - TC_TILE;            // one tile can add 128 entries
+    for (uint64_t t = g; t < ntiles; t += 2) {
+      tc_mbar_wait(&bar_tfull[g], (uint32_t)((t >> 1) & 1));
       tc_fence_after();
+      if (a.debug_skip) {
+        tc_fence_before();
+        tc_mbar_arrive(&bar_tempty[g]);
+        continue;
+      }
       const uint64_t row0 = (t_begin + t) * TC_TILE;
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + acc * 128;
+      const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + g * 128;
       uint32_t v[2][32];
       tc_tmem_ld32(taddr, v[0]);
+#pragma unroll 1
+      for (uint32_t cbp = 0; cbp < 2; cbp++) {
 #pragma unroll
-      for (uint32_t cb = 0; cb < 4; cb++) {
-        tc_tmem_wait_ld();
-        if (cb + 1 < 4) tc_tmem_ld32(taddr + (cb + 1) * 32, v[(cb + 1) & 1]);   // next 32 columns in flight under this block
-        const uint32_t rbase = (uint32_t)(row0 + cb * 32);
-        // branch-free pass over the 32 columns against a snapshot of the threshold (it only shrinks, so the
-        // snapshot test admits a superset; tc_push re-checks), then the rare hits one by one
-        float sc[32];
-        uint32_t mask = 0;
-        if (MODE == 0) {
-          // the accumulator already is ||q||^2 + ||x||^2 - 2 q.x (norms folded into the GEMM): compare only
-          const float thr2 = thr + mq;
+        for (int h = 0; h < 2; h++) {
+          const uint32_t cb = cbp * 2 + h;
+          tc_tmem_wait_ld();
+          if (cb + 1 < 4) tc_tmem_ld32(taddr + (cb + 1) * 32, v[(h + 1) & 1]);   // next 32 columns in flight under this block
+          const uint32_t(&blk)[32] = v[h];
+          // Most groups of eight columns hold nothing for any of the warp's 32 queries: a min (max) tree and one vote
+          // decide that in a dozen instructions. The threshold is a snapshot (it only shrinks): the tests admit a superset.
 #pragma unroll
-          for (int j = 0; j < 32; j++) {
-            sc[j] = __uint_as_float(v[cb & 1][j]);
-            mask |= (sc[j] <= thr2) ? (1u << j) : 0u;
-          }
-        } else {
-          const float4 *rn4 = reinterpret_cast<const float4 *>(a.b_norms + row0 + cb * 32);
-          const float thr0 = thr;
-#pragma unroll
-          for (int j4 = 0; j4 < 8; j4++) {
-            const float4 rnv = __ldg(rn4 + j4);
-            const float rns[4] = {rnv.x, rnv.y, rnv.z, rnv.w};
-#pragma unroll
-            for (int jj = 0; jj < 4; jj++) {
-              const int j = j4 * 4 + jj;
-              const float rn = rns[jj];   // +inf for padding and empty slots: never passes
-              const float dot = __uint_as_float(v[cb & 1][j]);
-              float score;
-              if (MODE == 1) score = rn < 3.0e38f ? -dot : __int_as_float(0x7fc00000);   // NaN never passes
-              else score = rn < 3.0e38f ? -dot * rsqrtf(qn * rn) : __int_as_float(0x7fc00000);
-              sc[j] = score;
-              mask |= (score - m2 <= thr0) ? (1u << j) : 0u;
+          for (int c8 = 0; c8 < 4; c8++) {
+            bool maybe = true;   // cosine scales every column by its row norm: no cheap bound
+            if (MODE == 0) {
+              const float m = fminf(fminf(fminf(__uint_as_float(blk[c8 * 8]), __uint_as_float(blk[c8 * 8 + 1])),
+                                          fminf(__uint_as_float(blk[c8 * 8 + 2]), __uint_as_float(blk[c8 * 8 + 3]))),
+                                    fminf(fminf(__uint_as_float(blk[c8 * 8 + 4]), __uint_as_float(blk[c8 * 8 + 5])),
+                                          fminf(__uint_as_float(blk[c8 * 8 + 6]), __uint_as_float(blk[c8 * 8 + 7]))));
+              maybe = __any_sync(0xffffffffu, m <= thr + margin);
+            } else if (MODE == 1) {
+              const float m = fmaxf(fmaxf(fmaxf(__uint_as_float(blk[c8 * 8]), __uint_as_float(blk[c8 * 8 + 1])),
+                                          fmaxf(__uint_as_float(blk[c8 * 8 + 2]), __uint_as_float(blk[c8 * 8 + 3]))),
+                                    fmaxf(fmaxf(__uint_as_float(blk[c8 * 8 + 4]), __uint_as_float(blk[c8 * 8 + 5])),
+                                          fmaxf(__uint_as_float(blk[c8 * 8 + 6]), __uint_as_float(blk[c8 * 8 + 7]))));
+              maybe = __any_sync(0xffffffffu, -m - margin <= thr);   // score = -dot
             }
-          }
-        }
-        if (mask) {
-          float loc[32];   // dynamically indexed below: lives in local memory, touched only on this rare path
-#pragma unroll
-          for (int j = 0; j < 32; j++) loc[j] = sc[j];
-          while (mask) {
-            const int j = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const float score = loc[j];
-            const float lower = score - (MODE == 0 ? mq : m2);
-            if (lower <= thr) thr = tc_push(score, rbase + j, H, st, a.k, mycand, skip_row, thr);
+            if (maybe)
+              cnt = tc_append8<MODE>(make_uint4(blk[c8 * 8], blk[c8 * 8 + 1], blk[c8 * 8 + 2], blk[c8 * 8 + 3]),
+                                     make_uint4(blk[c8 * 8 + 4], blk[c8 * 8 + 5], blk[c8 * 8 + 6], blk[c8 * 8 + 7]), thr, margin, qn,
+                                     (uint32_t)(row0 + cb * 32 + c8 * 8), a.b_norms, mybuf, cnt);
           }
         }
       }
       tc_fence_before();
-      tc_mbar_arrive(&bar_tempty[acc]);
+      tc_mbar_arrive(&bar_tempty[g]);   // the accumulator is free again: the next MMAs run under the compaction below
+      // buffers that could not take another tile are compacted by the warp, one query at a time
+      uint32_t full = __ballot_sync(0xffffffffu, cnt > room);
+      while (full) {
+        const int src = __ffs(full) - 1;
+        full &= full - 1;
+        const uint64_t bp = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)mybuf, src);
+        const uint32_t bc = __shfl_sync(0xffffffffu, cnt, src);
+        const float bm = __shfl_sync(0xffffffffu, margin, src);
+        float nthr = 0.f;
+        const uint32_t kept = tc_compact(reinterpret_cast<uint2 *>((uintptr_t)bp), bc, K, bm, &nthr, lane);
+        if (lane == src) {
+          cnt = kept;
+          thr = nthr;
+          if (kept > room) {   // K plus the rows inside the margin do not fit: the batch goes to the exact scan
+            bad = true;
+            cnt = 0;
+          }
+        }
+      }
     }
-    if (q_ok) a.cand_n[(size_t)q * a.nsplit + split] = st[256] ? 0xffffffffu : st[128];
+    // final compaction: what stays is the candidate list
+    {
+      uint32_t todo = __ballot_sync(0xffffffffu, cnt > K);
+      while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint64_t bp = __shfl_sync(0xffffffffu, (unsigned long long)(uintptr_t)mybuf, src);
+        const uint32_t bc = __shfl_sync(0xffffffffu, cnt, src);
+        const float bm = __shfl_sync(0xffffffffu, margin, src);
+        float nthr = 0.f;
+        const uint32_t kept = tc_compact(reinterpret_cast<uint2 *>((uintptr_t)bp), bc, K, bm, &nthr, lane);
+        if (lane == src) cnt = kept;
+      }
+    }
+    if (q_ok) a.cand_n[list] = bad ? 0xffffffffu : cnt;
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == TC_EPI_WARPS) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
   }
@@ -487,8 +579,11 @@ struct RerankArgs {
   const uint32_t *id_map;
   float radius;
   int dtype;
-  const uint32_t *cand;
+  const uint2 *cand;        // (score bits, row) pairs: only the rows are used here
   const uint32_t *cand_n;
+  uint32_t cap;
+  int exclude_self;         // drop the candidate whose row is the query's own (queries are stored rows)
+  uint32_t self_base;
   uint32_t *ids;
   float *dists;
   uint32_t *counts;
@@ -511,13 +606,14 @@ __global__ void __launch_bounds__(256) knn_tc_rerank_kernel(const RerankArgs a) 
     uint32_t c = a.cand_n[(size_t)q * a.nsplit + s];
     if (c == 0xffffffffu) {
       bad = true;
-      c = TC_CAND_CAP;
+      c = 0;
     }
-    const uint32_t *list = a.cand + ((size_t)q * a.nsplit + s) * TC_CAND_CAP;
+    const uint2 *list = a.cand + ((size_t)q * a.nsplit + s) * a.cap;
+    const uint32_t skip = a.exclude_self ? a.self_base + q : 0xffffffffu;
     for (uint32_t i0 = 0; i0 < c; i0 += R) {
       const uint32_t i = i0 + grp;
-      const bool act = i < c;
-      const uint32_t row = act ? list[i] : 0u;
+      const uint32_t row = i < c ? list[i].y : 0u;
+      const bool act = i < c && row != skip;
       const float d = group_distance_gmem<ACC, G>(qptr, act ? a.rows + (size_t)row * a.row_bytes : qptr, a.chunks, gl, a.dtype);
       uint64_t key = KEY_NONE;
       if (act && gl == 0 && (a.radius < 0.f || d <= a.radius))
@@ -679,16 +775,27 @@ int ngtgpu_scan_topk_tc(ngtgpu_index *ix, const ScanParams &p, cudaStream_t stre
   if (want < 1) want = 1;
   a.tiles_per_split = (total_tiles + want - 1) / want;
   a.nsplit = (uint32_t)((total_tiles + a.tiles_per_split - 1) / a.tiles_per_split);
-  uint32_t *cand = nullptr;
-  NGTGPU_TRY(ngtgpu_scratch(ix, SCR_TC_CAND, ((size_t)p.nq * a.nsplit * (TC_CAND_CAP + 1) + 4) * 4, (void **)&cand));
-  a.cand = cand;
-  a.cand_n = cand + (size_t)p.nq * a.nsplit * TC_CAND_CAP;
-  uint32_t *d_over = a.cand_n + (size_t)p.nq * a.nsplit;
+  // (score, row) buffers: room for K entries, the rows inside the margin and one more block of 32 columns
+  const uint32_t K = p.k + (p.exclude_self ? 1u : 0u);
+  // (two lists per (query, split): one per epilogue group)
+  uint32_t cap = (K + TC_TILE + 96 + 31u) & ~31u;
+  if (cap > TC_CAND_MAX) cap = TC_CAND_MAX;
+  a.cap = cap;
+  a.debug_skip = getenv("NGTGPU_TC_SKIP_EPILOGUE") ? 1 : 0;
+  uint8_t *cand_raw = nullptr;
+  const size_t n_lists = (size_t)p.nq * a.nsplit * 2;
+  const size_t list_bytes = n_lists * cap * sizeof(uint2);
+  NGTGPU_TRY(ngtgpu_scratch(ix, SCR_TC_CAND, list_bytes + (n_lists + 4) * 4, (void **)&cand_raw));
+  a.cand = reinterpret_cast<uint2 *>(cand_raw);
+  a.cand_n = reinterpret_cast<uint32_t *>(cand_raw + list_bytes);
+  CUDA_TRY(cudaMemsetAsync(a.cand_n, 0, n_lists * 4, stream));   // a group without tiles leaves its list empty
+  uint32_t *d_over = a.cand_n + n_lists;
   CUDA_TRY(cudaMemsetAsync(d_over, 0, 4, stream));
 
-  // ring depth: as many 16 KB stages as fit beside the resident query operand and the heaps (2..TC_STAGES)
-  const size_t fixed_smem = (size_t)kchunks * TC_TILE_BYTES + (size_t)(p.k + 3) * 128 * 4 + 1024;
+  // ring depth: as many 16 KB stages as fit beside the resident query operand (2..TC_STAGES)
+  const size_t fixed_smem = (size_t)kchunks * TC_TILE_BYTES + 1024;
   uint32_t stages = TC_STAGES;
+  if (const char *env = getenv("NGTGPU_TC_STAGES")) stages = std::max(2, std::min(TC_STAGES, atoi(env)));   // development knob
   while (stages > 2 && fixed_smem + (size_t)stages * TC_TILE_BYTES > 225 * 1024) stages--;
   if (fixed_smem + (size_t)stages * TC_TILE_BYTES > 225 * 1024) return NGTGPU_OK;
   a.stages = stages;
@@ -714,13 +821,16 @@ int ngtgpu_scan_topk_tc(ngtgpu_index *ix, const ScanParams &p, cudaStream_t stre
   r.chunks = ix->chunks;
   r.nq = p.nq;
   r.k = p.k;
-  r.nsplit = a.nsplit;
+  r.nsplit = a.nsplit * 2;
   r.first_row_id = p.first_row_id;
   r.id_map = nullptr;
   r.radius = p.radius;
   r.dtype = ix->distance_type;
   r.cand = a.cand;
   r.cand_n = a.cand_n;
+  r.cap = a.cap;
+  r.exclude_self = a.exclude_self;
+  r.self_base = a.self_base;
   r.ids = p.d_ids;
   r.dists = p.d_dists;
   r.counts = p.d_counts;
