@@ -46,6 +46,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+KNN_BATCH = 148 * 256 * 3      # query batch of ngtgpu_index_build_onng's exhaustive pass (three waves of 256-query CTAs on 148 SMs)
 
 
 def parse_args():
@@ -239,7 +240,7 @@ def build_index(a, dev, want_files):
     info = {"n": a.n, "gen_s": round(t1 - t0, 2), "knn_graph_s": round(b["knn_s"], 3),
             "reconstruct_s": round(b["reconstruct_s"], 3), "adjust_paths_s": round(b["adjust_paths_s"], 3),
             "knn_pass": {"useful_tflops": round(tf, 1), "frac_of_bf16_sustained": round(tf / bf_sus, 4),
-                         "tensor_core_batches": "%d of %d" % (ix.tensor_core_batches - tc0, (a.n + (1 << 17) - 1) >> 17)}}
+                         "tensor_core_batches": "%d of %d" % (ix.tensor_core_batches - tc0, -(-a.n // KNN_BATCH))}}
     index_dir = None
     if want_files:
         info["graph"] = build.graph_statistics(row_ptr)
@@ -484,7 +485,7 @@ def run_workload(spec, a, dev, rank, world, lib):
     ms, knn_s = float(red[0]), float(red[5])
     kdim = dim * 8 if kind == "ham" else dim
     tf = 2.0 * n_local * n_local * kdim / max(knn_s, 1e-9) / 1e12
-    n_batches = (n_local + (1 << 17) - 1) >> 17
+    n_batches = -(-n_local // KNN_BATCH)
     return {
         "workload": spec["desc"] % {"total": n_local * world, "world": world, "n_local": n_local},
         "n_gpus": world, "objects": n_local * world, "objects_per_gpu": n_local, "batch": nq, "k": k, "edge_size": cap,

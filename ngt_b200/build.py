@@ -27,7 +27,7 @@ def _fn():
     return lib
 
 
-def knn_graph(ix, k, batch=1 << 17):
+def knn_graph(ix, k, batch=148 * 256 * 3):
     """Exact k nearest OTHER objects of every stored object. -> (ids [n,k] int32, dists [n,k] float32,
     counts [n] int32) as torch CUDA tensors; lists ascending by (distance,id)."""
     import torch

@@ -1115,8 +1115,10 @@ extern "C" int ngtgpu_index_build_onng(ngtgpu_index *ix, uint32_t knn, uint32_t 
   CUDA_TRY(mem.alloc(&t_dists, n * k));
   CUDA_TRY(mem.alloc(&t_counts, n));
   CUDA_TRY(cudaEventRecord(ev[0], stream));
-  for (uint64_t s = 0; s < n; s += 131072) {
-    const uint32_t m = (uint32_t)std::min<uint64_t>(131072, n - s);
+  // query batches of three full waves of the tensor-core kernel's 256-query CTAs (no partly filled last wave)
+  const uint64_t batch = (uint64_t)ix->sm_count * 256 * 3;
+  for (uint64_t s = 0; s < n; s += batch) {
+    const uint32_t m = (uint32_t)std::min<uint64_t>(batch, n - s);
     NGTGPU_TRY(ngtgpu_index_knn_graph(ix, k, (uint32_t)s + 1, m, t_ids + s * k, t_dists + s * k, t_counts + s, stream));
   }
   CUDA_TRY(cudaEventRecord(ev[1], stream));

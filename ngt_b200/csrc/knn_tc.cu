@@ -84,11 +84,10 @@ __global__ void tc_check_exact_kernel(const float *__restrict__ rows, uint64_t c
 //     A extra = [qn0 qn1 qn2 1 1 1 0 ...],  B extra = [1 1 1 rn0 rn1 rn2 0 ...]
 // so the accumulator IS ||q||^2 + ||x||^2 - 2 q.x and the epilogue only compares. Padding / empty rows get a huge
 // finite norm (3e38) and can never pass.
-__global__ void tc_pack_kernel(const uint8_t *__restrict__ rows, int kind, uint32_t row_bytes, uint64_t n_rows, uint32_t padded_dim, int side,
-                               uint32_t nseg, uint32_t kchunks, int fold, const float *__restrict__ norms,
-                               uint8_t *__restrict__ tiles) {
+__global__ void tc_pack_kernel(const uint8_t *__restrict__ rows, int kind, uint32_t row_bytes, uint64_t n_rows, uint64_t n_pad,
+                               uint32_t padded_dim, int side, uint32_t nseg, uint32_t kchunks, int fold,
+                               const float *__restrict__ norms, uint8_t *__restrict__ tiles) {
   const uint64_t units_per_row = (uint64_t)kchunks * 8;
-  const uint64_t n_pad = (n_rows + TC_TILE - 1) / TC_TILE * TC_TILE;
   const uint64_t total = n_pad * units_per_row;
   const uint32_t fold_unit = (kchunks - 1) * 8;   // first unit of the extra chunk
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -149,10 +148,9 @@ __global__ void tc_max_norm_kernel(const float *__restrict__ norms, uint64_t n, 
 }
 
 // squared norms (plain fp32: they only feed the filter); +inf marks padding and empty slots
-__global__ void tc_norms_kernel(const uint8_t *__restrict__ rows, int kind, uint32_t row_bytes, uint64_t n_rows, uint32_t padded_dim, uint32_t first_id,
-                                const uint8_t *__restrict__ valid, float *__restrict__ norms) {
+__global__ void tc_norms_kernel(const uint8_t *__restrict__ rows, int kind, uint32_t row_bytes, uint64_t n_rows, uint64_t n_pad,
+                                uint32_t padded_dim, uint32_t first_id, const uint8_t *__restrict__ valid, float *__restrict__ norms) {
   const int lane = threadIdx.x & 31;
-  const uint64_t n_pad = (n_rows + TC_TILE - 1) / TC_TILE * TC_TILE;
   const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
   for (uint64_t r = warp; r < n_pad; r += nwarps) {
@@ -198,6 +196,21 @@ __device__ __forceinline__ void tc_bulk_load(void *smem_dst, const void *gsrc, u
                    smem_u32(smem_dst)),
                "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+// one lane of the (fully active) warp, chosen by the hardware: code under this predicate is known to the compiler to run in
+// a single thread, so tcgen05.mma / cp.async.bulk take their descriptors through one R2UR each instead of a
+// value-uniformity loop per instruction (VOTEU / ELECT / R2UR.BROADCAST / BRA.U.ANY around every UTCHMMA made the
+// issuing thread, not the tensor pipe, the limit: 170-200 cycles per 92-cycle MMA)
+__device__ __forceinline__ bool tc_elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -277,10 +290,11 @@ struct TcArgs {
   uint32_t qtiles;
   uint32_t nsplit;
   uint64_t tiles_per_split;
+  uint32_t qgroups;         // query tiles per CTA: 2 (256 queries share every row tile) or 1 when two query operands do not fit
   int debug_skip;           // development: 1 = the epilogue only releases the accumulators (timing of the MMA side alone)
   uint32_t cap;             // entries of one (query, split) buffer: a multiple of 32, <= TC_CAND_MAX
-  uint2 *cand;              // [nq][nsplit][2 groups][cap] (score bits, row index 0-based)
-  uint32_t *cand_n;         // [nq][nsplit][2]; 0xffffffff = overflow
+  uint2 *cand;              // [nq][nsplit][cap] (score bits, row index 0-based)
+  uint32_t *cand_n;         // [nq][nsplit]; 0xffffffff = overflow
 };
 
 // Compaction of ONE query's buffer by the whole warp (`buf`, `cnt` are warp-uniform: broadcast from the owning lane).
@@ -382,15 +396,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_filter_kernel(const TcAr
   __shared__ uint32_t s_tmem;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t qtile = blockIdx.x % a.qtiles, split = blockIdx.x / a.qtiles;
+  const uint32_t qtile = blockIdx.x % a.qtiles, split = blockIdx.x / a.qtiles;   // qtile: a.qgroups query tiles of 128
   const uint64_t total_tiles = (a.n_rows + TC_TILE - 1) / TC_TILE;
   const uint64_t t_begin = (uint64_t)split * a.tiles_per_split;
   uint64_t t_end = t_begin + a.tiles_per_split;
   if (t_end > total_tiles) t_end = total_tiles;
   const uint64_t ntiles = t_end > t_begin ? t_end - t_begin : 0;
 
-  uint8_t *sA = smem;                                              // kchunks x 16 KB (resident)
-  uint8_t *sB = smem + (size_t)a.kchunks * TC_TILE_BYTES;         // a.stages x 16 KB ring
+  uint8_t *sA = smem;                                                        // qgroups x kchunks x 16 KB (resident)
+  uint8_t *sB = smem + (size_t)a.qgroups * a.kchunks * TC_TILE_BYTES;       // a.stages x 16 KB ring
 
   if (tid == 0) {
     for (int i = 0; i < TC_STAGES; i++) {
@@ -400,13 +414,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_filter_kernel(const TcAr
     tc_mbar_init(&bar_a, 1);
     for (int i = 0; i < 2; i++) {
       tc_mbar_init(&bar_tfull[i], 1);
-      tc_mbar_init(&bar_tempty[i], 128);
+      tc_mbar_init(&bar_tempty[i], 128 * a.qgroups);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == TC_EPI_WARPS) {
-    // 256 columns: two 128-column fp32 accumulators
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(256u) : "memory");
+    // 512 columns: two alternating sets of (one 128-column fp32 accumulator per query group)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -416,10 +430,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_filter_kernel(const TcAr
 
   if (warp == TC_EPI_WARPS) {
     // ===================== producer =====================
-    if (lane == 0 && ntiles) {
-      tc_mbar_expect_tx(&bar_a, a.kchunks * TC_TILE_BYTES);
-      for (uint32_t c = 0; c < a.kchunks; c++)
-        tc_bulk_load(sA + (size_t)c * TC_TILE_BYTES, a.a_tiles + ((size_t)qtile * a.kchunks + c) * TC_TILE_BYTES, TC_TILE_BYTES, &bar_a);
+    if (ntiles && tc_elect_one()) {
+      tc_mbar_expect_tx(&bar_a, a.qgroups * a.kchunks * TC_TILE_BYTES);
+      for (uint32_t c = 0; c < a.qgroups * a.kchunks; c++)   // the query tiles of this CTA are consecutive in a_tiles
+        tc_bulk_load(sA + (size_t)c * TC_TILE_BYTES, a.a_tiles + ((size_t)qtile * a.qgroups * a.kchunks + c) * TC_TILE_BYTES, TC_TILE_BYTES,
+                     &bar_a);
       uint64_t it = 0;
       for (uint64_t t = 0; t < ntiles; t++) {
         for (uint32_t c = 0; c < a.kchunks; c++, it++) {
@@ -433,7 +448,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_filter_kernel(const TcAr
     }
   } else if (warp == TC_EPI_WARPS + 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && ntiles) {
+    if (ntiles && tc_elect_one()) {
       // kind::f16, A = B = BF16, D = F32, K-major both, N = 128, M = 128 (cute::UMMA::InstrDescriptor)
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
       const uint64_t descA0 = tc_smem_desc(smem_u32(sA)), descB0 = tc_smem_desc(smem_u32(sB));
@@ -448,11 +463,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_filter_kernel(const TcAr
           const uint32_t st = (uint32_t)(it % a.stages);
           tc_mbar_wait(&bar_full[st], (uint32_t)((it / a.stages) & 1));
           tc_fence_after();
+          for (uint32_t qg = 0; qg < a.qgroups; qg++) {   // every row tile in shared memory feeds all the CTA's query tiles
 #pragma unroll
-          for (uint32_t s = 0; s < TC_KCHUNK / 16; s++) {
-            const uint64_t da = descA0 + (uint64_t)((c * TC_TILE_BYTES + s * 32) >> 4);
-            const uint64_t db = descB0 + (uint64_t)((st * TC_TILE_BYTES + s * 32) >> 4);
-            tc_mma_bf16(tmem_base + acc * 128, da, db, idesc, (c | s) != 0 ? 1u : 0u);
+            for (uint32_t s = 0; s < TC_KCHUNK / 16; s++) {
+              const uint64_t da = descA0 + (uint64_t)(((qg * a.kchunks + c) * TC_TILE_BYTES + s * 32) >> 4);
+              const uint64_t db = descB0 + (uint64_t)((st * TC_TILE_BYTES + s * 32) >> 4);
+              tc_mma_bf16(tmem_base + (acc * 2 + qg) * 128, da, db, idesc, (c | s) != 0 ? 1u : 0u);
+            }
           }
           tc_commit(&bar_empty[st]);   // frees the ring slot when these MMAs have read it
         }
@@ -460,12 +477,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_filter_kernel(const TcAr
       }
     }
   } else {
-    // ===================== epilogue: one query per thread and group =====================
-    const uint32_t g = (uint32_t)warp >> 2;            // group: the tiles t = g, g + 2, ... (accumulator g)
+    // ===================== epilogue: one query per thread =====================
+    const uint32_t g = (uint32_t)warp >> 2;            // query group: warps 0-3 the CTA's first query tile, 4-7 its second
     const uint32_t qlane = (uint32_t)tid & 127u;       // TMEM lane == query of the tile
-    const uint32_t q = qtile * TC_TILE + qlane;
-    const bool q_ok = q < a.nq;
-    const float qn = a.a_norms[(size_t)qtile * TC_TILE + qlane];
+    const uint32_t q = (qtile * a.qgroups + g) * TC_TILE + qlane;
+    const bool q_ok = q < a.nq && g < a.qgroups;
+    const float qn = g < a.qgroups ? a.a_norms[(size_t)(qtile * a.qgroups + g) * TC_TILE + qlane] : 0.f;
     // K-th smallest approximate score so far; "nothing yet" is a large finite number so that the huge scores of
     // padding / empty rows (3e38) never pass. When the queries are stored rows the row itself (score ~ 0) is one of
     // the K = k + 1 smallest and is dropped by the re-evaluation.
@@ -473,21 +490,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_filter_kernel(const TcAr
     float thr = q_ok ? 1.0e37f : -__int_as_float(0x7f800000);
     uint32_t cnt = 0;
     bool bad = false;
-    const size_t list = ((size_t)(q_ok ? q : 0u) * a.nsplit + split) * 2 + g;
+    const size_t list = (size_t)(q_ok ? q : 0u) * a.nsplit + split;
     uint2 *mybuf = a.cand + list * a.cap;
     const float m2 = 2.0f * a.rel_margin;
     const float margin = MODE == 0 ? m2 * (qn + a.max_row_norm) : m2;   // MODE 0: per-query bound of twice the error
     const uint32_t room = a.cap - TC_TILE;            // one tile can add 128 entries
-    for (uint64_t t = g; t < ntiles; t += 2) {
-      tc_mbar_wait(&bar_tfull[g], (uint32_t)((t >> 1) & 1));
+    for (uint64_t t = 0; t < ntiles && g < a.qgroups; t++) {
+      const uint32_t acc = (uint32_t)(t & 1);
+      tc_mbar_wait(&bar_tfull[acc], (uint32_t)((t >> 1) & 1));
       tc_fence_after();
       if (a.debug_skip) {
         tc_fence_before();
-        tc_mbar_arrive(&bar_tempty[g]);
+        tc_mbar_arrive(&bar_tempty[acc]);
         continue;
       }
       const uint64_t row0 = (t_begin + t) * TC_TILE;
-      const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + g * 128;
+      const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (acc * 2 + g) * 128;
       uint32_t v[2][32];
       tc_tmem_ld32(taddr, v[0]);
 #pragma unroll 1
@@ -524,7 +542,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_filter_kernel(const TcAr
         }
       }
       tc_fence_before();
-      tc_mbar_arrive(&bar_tempty[g]);   // the accumulator is free again: the next MMAs run under the compaction below
+      tc_mbar_arrive(&bar_tempty[acc]);   // the accumulator is free again: the next MMAs run under the compaction below
       // buffers that could not take another tile are compacted by the warp, one query at a time
       uint32_t full = __ballot_sync(0xffffffffu, cnt > room);
       while (full) {
@@ -565,7 +583,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_filter_kernel(const TcAr
   __syncthreads();
   if (warp == TC_EPI_WARPS) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -665,15 +683,16 @@ static uint32_t tc_kchunks(const ngtgpu_index *ix, uint32_t nseg, int fold) {
   return (nseg * tc_kdim(ix) + TC_KCHUNK - 1) / TC_KCHUNK + (fold ? 1 : 0);
 }
 
-static int tc_pack(ngtgpu_index *ix, const uint8_t *d_rows, uint64_t n_rows, int side, uint32_t nseg, int fold, uint32_t first_id,
-                   const uint8_t *d_valid, uint8_t *tiles, float *norms, cudaStream_t stream) {
+// rows are padded (zeros, norm +inf) to a multiple of `pad_rows`
+static int tc_pack(ngtgpu_index *ix, const uint8_t *d_rows, uint64_t n_rows, uint32_t pad_rows, int side, uint32_t nseg, int fold,
+                   uint32_t first_id, const uint8_t *d_valid, uint8_t *tiles, float *norms, cudaStream_t stream) {
   const uint32_t kchunks = tc_kchunks(ix, nseg, fold);
-  const uint64_t n_pad = (n_rows + TC_TILE - 1) / TC_TILE * TC_TILE;
+  const uint64_t n_pad = (n_rows + pad_rows - 1) / pad_rows * pad_rows;
   uint64_t total = n_pad * kchunks * 8;
   unsigned blocks = (unsigned)((total + 255) / 256 > (uint64_t)ix->sm_count * 64 ? (uint64_t)ix->sm_count * 64 : (total + 255) / 256);
-  tc_norms_kernel<<<ix->sm_count * 8, 256, 0, stream>>>(d_rows, tc_kind(ix), ix->row_bytes, n_rows, tc_kdim(ix), first_id, d_valid, norms);
+  tc_norms_kernel<<<ix->sm_count * 8, 256, 0, stream>>>(d_rows, tc_kind(ix), ix->row_bytes, n_rows, n_pad, tc_kdim(ix), first_id, d_valid, norms);
   CUDA_TRY(cudaGetLastError());
-  tc_pack_kernel<<<blocks, 256, 0, stream>>>(d_rows, tc_kind(ix), ix->row_bytes, n_rows, tc_kdim(ix), side, nseg, kchunks, fold, norms, tiles);
+  tc_pack_kernel<<<blocks, 256, 0, stream>>>(d_rows, tc_kind(ix), ix->row_bytes, n_rows, n_pad, tc_kdim(ix), side, nseg, kchunks, fold, norms, tiles);
   CUDA_TRY(cudaGetLastError());
   ix->launches += 2;
   return NGTGPU_OK;
@@ -724,7 +743,7 @@ int ngtgpu_scan_topk_tc(ngtgpu_index *ix, const ScanParams &p, cudaStream_t stre
     ix->d_tc_norms = nullptr;
     CUDA_TRY(cudaMalloc(&ix->d_tc_tiles, n_tiles * kchunks * (size_t)TC_TILE_BYTES));
     CUDA_TRY(cudaMalloc(&ix->d_tc_norms, (n_tiles * TC_TILE + 64) * sizeof(float)));
-    NGTGPU_TRY(tc_pack(ix, rows, p.n_rows, 1, nseg, fold, p.first_row_id, p.d_valid, ix->d_tc_tiles, ix->d_tc_norms, stream));
+    NGTGPU_TRY(tc_pack(ix, rows, p.n_rows, TC_TILE, 1, nseg, fold, p.first_row_id, p.d_valid, ix->d_tc_tiles, ix->d_tc_norms, stream));
     float *d_max = ix->d_tc_norms + n_tiles * TC_TILE;
     CUDA_TRY(cudaMemsetAsync(d_max, 0, sizeof(float), stream));
     tc_max_norm_kernel<<<ix->sm_count * 4, 256, 0, stream>>>(ix->d_tc_norms, n_tiles * TC_TILE, d_max);
@@ -745,12 +764,16 @@ int ngtgpu_scan_topk_tc(ngtgpu_index *ix, const ScanParams &p, cudaStream_t stre
     if (!qexact) return NGTGPU_OK;   // rows are bf16-exact but the queries are not: leave it to the CUDA-core scan
   }
   const uint32_t kchunks = ix->tc_kchunks;
-  const uint32_t qtiles = (p.nq + TC_TILE - 1) / TC_TILE;
+  // two query tiles per CTA (every row tile read from L2 feeds 256 queries: the kernel is bound by that stream) when two
+  // resident query operands and a ring of two stages fit shared memory, else one
+  const uint32_t qgroups = (2 * (size_t)kchunks + 2) * TC_TILE_BYTES + 1024 <= 225 * 1024 ? 2u : 1u;
+  const uint32_t qtiles128 = ((p.nq + TC_TILE * qgroups - 1) / (TC_TILE * qgroups)) * qgroups;   // 128-query tiles, padded to whole CTAs
+  const uint32_t qtiles = qtiles128 / qgroups;                                                   // CTAs per split
   uint8_t *a_tiles = nullptr;
   float *a_norms = nullptr;
-  NGTGPU_TRY(ngtgpu_scratch(ix, SCR_TC_QUERY, (size_t)qtiles * kchunks * TC_TILE_BYTES + (size_t)qtiles * TC_TILE * 4, (void **)&a_tiles));
-  a_norms = reinterpret_cast<float *>(a_tiles + (size_t)qtiles * kchunks * TC_TILE_BYTES);
-  NGTGPU_TRY(tc_pack(ix, qrows, p.nq, 0, nseg, ix->tc_fold, 0, nullptr, a_tiles, a_norms, stream));
+  NGTGPU_TRY(ngtgpu_scratch(ix, SCR_TC_QUERY, (size_t)qtiles128 * kchunks * TC_TILE_BYTES + (size_t)qtiles128 * TC_TILE * 4, (void **)&a_tiles));
+  a_norms = reinterpret_cast<float *>(a_tiles + (size_t)qtiles128 * kchunks * TC_TILE_BYTES);
+  NGTGPU_TRY(tc_pack(ix, qrows, p.nq, TC_TILE * qgroups, 0, nseg, ix->tc_fold, 0, nullptr, a_tiles, a_norms, stream));
 
   TcArgs a;
   memset(&a, 0, sizeof(a));
@@ -768,6 +791,7 @@ int ngtgpu_scan_topk_tc(ngtgpu_index *ix, const ScanParams &p, cudaStream_t stre
   a.exclude_self = p.exclude_self;
   a.self_base = p.self_base - p.first_row_id;
   a.qtiles = qtiles;
+  a.qgroups = qgroups;
   const uint64_t total_tiles = (p.n_rows + TC_TILE - 1) / TC_TILE;
   uint64_t want = ((uint64_t)ix->sm_count + qtiles - 1) / qtiles;
   if (want > 8) want = 8;
@@ -777,23 +801,21 @@ int ngtgpu_scan_topk_tc(ngtgpu_index *ix, const ScanParams &p, cudaStream_t stre
   a.nsplit = (uint32_t)((total_tiles + a.tiles_per_split - 1) / a.tiles_per_split);
   // (score, row) buffers: room for K entries, the rows inside the margin and one more block of 32 columns
   const uint32_t K = p.k + (p.exclude_self ? 1u : 0u);
-  // (two lists per (query, split): one per epilogue group)
   uint32_t cap = (K + TC_TILE + 96 + 31u) & ~31u;
   if (cap > TC_CAND_MAX) cap = TC_CAND_MAX;
   a.cap = cap;
   a.debug_skip = getenv("NGTGPU_TC_SKIP_EPILOGUE") ? 1 : 0;
   uint8_t *cand_raw = nullptr;
-  const size_t n_lists = (size_t)p.nq * a.nsplit * 2;
+  const size_t n_lists = (size_t)p.nq * a.nsplit;
   const size_t list_bytes = n_lists * cap * sizeof(uint2);
   NGTGPU_TRY(ngtgpu_scratch(ix, SCR_TC_CAND, list_bytes + (n_lists + 4) * 4, (void **)&cand_raw));
   a.cand = reinterpret_cast<uint2 *>(cand_raw);
   a.cand_n = reinterpret_cast<uint32_t *>(cand_raw + list_bytes);
-  CUDA_TRY(cudaMemsetAsync(a.cand_n, 0, n_lists * 4, stream));   // a group without tiles leaves its list empty
   uint32_t *d_over = a.cand_n + n_lists;
   CUDA_TRY(cudaMemsetAsync(d_over, 0, 4, stream));
 
   // ring depth: as many 16 KB stages as fit beside the resident query operand (2..TC_STAGES)
-  const size_t fixed_smem = (size_t)kchunks * TC_TILE_BYTES + 1024;
+  const size_t fixed_smem = (size_t)qgroups * kchunks * TC_TILE_BYTES + 1024;
   uint32_t stages = TC_STAGES;
   if (const char *env = getenv("NGTGPU_TC_STAGES")) stages = std::max(2, std::min(TC_STAGES, atoi(env)));   // development knob
   while (stages > 2 && fixed_smem + (size_t)stages * TC_TILE_BYTES > 225 * 1024) stages--;
@@ -821,7 +843,7 @@ int ngtgpu_scan_topk_tc(ngtgpu_index *ix, const ScanParams &p, cudaStream_t stre
   r.chunks = ix->chunks;
   r.nq = p.nq;
   r.k = p.k;
-  r.nsplit = a.nsplit * 2;
+  r.nsplit = a.nsplit;
   r.first_row_id = p.first_row_id;
   r.id_map = nullptr;
   r.radius = p.radius;

@@ -27,8 +27,8 @@ counts = torch.zeros((nq,), dtype=torch.int32, device=dev)
 for rep in range(2):
     torch.cuda.synchronize()
     t0 = time.time()
-    for s in range(0, nq, 1 << 17):
-        m = min(1 << 17, nq - s)
+    for s in range(0, nq, 148 * 768):
+        m = min(148 * 768, nq - s)
         _lib.check(lib.ngtgpu_index_knn_graph(ix._h, a.k, s + 1, m, ids[s:].data_ptr(), dists[s:].data_ptr(), counts[s:].data_ptr(), 0))
     torch.cuda.synchronize()
     t = time.time() - t0
