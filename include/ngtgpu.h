@@ -306,6 +306,11 @@ int ngtgpu_index_refine_anng(ngtgpu_index *index, float epsilon, int32_t no_of_e
  * Host arithmetic; fails with the reference's messages for a table of two or fewer points or a malformed token. */
 int ngtgpu_epsilon_from_accuracy_table(const char *table, double accuracy, float *epsilon);
 
+/* The m x m distances among the stored objects `ids` (host ids in, host floats out; m <= 4096), with the engine's exact
+ * distance: the comparator calls of NeighborhoodGraph::removeEdgesReliably (lib/NGT/Graph.cpp:641-864), which re-links
+ * the neighbours of a node that NGT::Index::remove takes out. */
+int ngtgpu_index_pairwise_distances(ngtgpu_index *index, const uint32_t *ids, uint32_t m, float *out);
+
 /* Number of kernels this library launched since the index was created (bench.py's gpu_launches). */
 uint64_t ngtgpu_index_launch_count(const ngtgpu_index *index);
 /* Device timing of the traversal kernel with CUDA events on the launching stream (bench.py's roofline leg):

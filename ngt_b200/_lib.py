@@ -56,6 +56,7 @@ SYMBOLS = {
     "ngtgpu_index_get_object": (C.c_int, [_P, C.c_uint32, _P]),
     "ngtgpu_index_get_objects": (C.c_int, [_P, C.c_uint32, C.c_uint64, _P]),
     "ngtgpu_epsilon_from_accuracy_table": (C.c_int, [C.c_char_p, C.c_double, C.POINTER(C.c_float)]),
+    "ngtgpu_index_pairwise_distances": (C.c_int, [_P, _P, C.c_uint32, _P]),
     "ngtgpu_index_launch_count": (C.c_uint64, [_P]),
     "ngtgpu_index_last_overflows": (C.c_uint64, [_P]),
     "ngtgpu_search": (C.c_int, [_P, _P, C.c_int, C.c_uint32, C.POINTER(SearchParams), _P, C.c_uint32, _P, _P, _P, _P]),

@@ -303,6 +303,97 @@ void shard_index(CapiIndex &ix, const std::vector<int> &devices) {
   check(ngtgpu_sharded_build_onng(ix.sharded, e, out, in, onng ? 1 : 0, ix.prop.edge_size_for_search, 1024));
 }
 
+// NeighborhoodGraph::removeEdgesReliably (lib/NGT/Graph.cpp:641-864) on the host copy of the graph: the removed node's
+// back edges go (each neighbour must hold one: the graph is an ANNG), then the neighbours are chained -- neighbour i is
+// linked both ways to the nearest of the neighbours after it, which then takes place i + 1 -- so that they stay connected;
+// the distances of that chain come from the device (the engine's exact distance). The graph covers ids 1..n_graph
+// (= n when nothing is queued): an id appended since the last build has no node yet and is simply dropped.
+void remove_edges_reliably(CapiIndex &ix, ObjectID id) {
+  if (ix.row_ptr.size() < 2 || ix.row_ptr.size() > ix.n() + 2) return;
+  const size_t n_graph = ix.row_ptr.size() - 2;
+  if (id > n_graph) return;
+  typedef std::pair<float, uint32_t> Edge;   // ordered like ObjectDistance: (distance, id)
+  std::vector<Edge> node;
+  for (uint64_t e = ix.row_ptr[id]; e < ix.row_ptr[id + 1]; e++)
+    if (ix.col[e] != id) node.push_back(Edge(ix.dist[e], ix.col[e]));
+  std::map<uint32_t, std::vector<Edge>> edited;   // the lists this removal touches
+  auto list_of = [&](uint32_t nid) -> std::vector<Edge> & {
+    auto it = edited.find(nid);
+    if (it != edited.end()) return it->second;
+    std::vector<Edge> &l = edited[nid];
+    for (uint64_t e = ix.row_ptr[nid]; e < ix.row_ptr[nid + 1]; e++) l.push_back(Edge(ix.dist[e], ix.col[e]));
+    return l;
+  };
+  for (const Edge &e : node) {
+    std::vector<Edge> &n = list_of(e.second);
+    auto pos = std::lower_bound(n.begin(), n.end(), Edge(e.first, id));
+    // (no back edge -- e.g. an ONNG, whose lists are not symmetric: the reference is built with NGT_FORCED_REMOVE,
+    // defines.h.in:36, reports it on stderr and goes on, Graph.cpp:727-733; so does this)
+    if (pos != n.end() && pos->second == id) n.erase(pos);
+  }
+  const uint32_t m = (uint32_t)node.size();
+  if (m > 1) {
+    std::vector<uint32_t> order(m);
+    for (uint32_t i = 0; i < m; i++) order[i] = node[i].second;
+    std::vector<float> D((size_t)m * m);
+    check(ngtgpu_index_pairwise_distances(ix.gpu, order.data(), m, D.data()));
+    std::vector<uint32_t> slot(m);   // slot[i]: which row of D the object now at place i is
+    for (uint32_t i = 0; i < m; i++) slot[i] = i;
+    for (uint32_t i = 0; i + 1 < m; i++) {
+      int minj = -1;
+      float mind = FLT_MAX;
+      for (uint32_t j = i + 1; j < m; j++) {
+        const float d = D[(size_t)slot[i] * m + slot[j]];
+        if (d < mind) {
+          minj = (int)j;
+          mind = d;
+        }
+      }
+      if (minj < 0) throw std::runtime_error("removeEdgesReliably : Relink error ID=" + std::to_string(id));
+      bool inserted[2];
+      const uint32_t pair[2][2] = {{order[i], order[minj]}, {order[minj], order[i]}};
+      for (int s2 = 0; s2 < 2; s2++) {
+        std::vector<Edge> &n = list_of(pair[s2][0]);
+        const Edge obj(mind, pair[s2][1]);
+        auto pos = std::lower_bound(n.begin(), n.end(), obj);
+        inserted[s2] = pos == n.end() || pos->second != obj.second;
+        if (inserted[s2]) n.insert(pos, obj);
+      }
+      // (inserted[0] != inserted[1]: "Lost conectivity! Isn't this ANNG?" -- a warning under NGT_FORCED_REMOVE, Graph.cpp:805-813)
+      if (i + 1 != (uint32_t)minj) {
+        std::swap(order[i + 1], order[minj]);
+        std::swap(slot[i + 1], slot[minj]);
+      }
+    }
+  }
+  edited[id].clear();
+  // the CSR again, with the touched lists replaced
+  std::vector<uint64_t> rp(n_graph + 2, 0);
+  std::vector<uint32_t> col;
+  std::vector<float> dist;
+  col.reserve(ix.col.size() + 2 * m);
+  dist.reserve(ix.col.size() + 2 * m);
+  for (size_t s2 = 1; s2 <= n_graph; s2++) {
+    rp[s2] = col.size();
+    auto it = edited.find((uint32_t)s2);
+    if (it != edited.end()) {
+      for (const Edge &e : it->second) {
+        col.push_back(e.second);
+        dist.push_back(e.first);
+      }
+    } else {
+      for (uint64_t e = ix.row_ptr[s2]; e < ix.row_ptr[s2 + 1]; e++) {
+        col.push_back(ix.col[e]);
+        dist.push_back(ix.dist[e]);
+      }
+    }
+  }
+  rp[n_graph + 1] = col.size();
+  ix.row_ptr.swap(rp);
+  ix.col.swap(col);
+  ix.dist.swap(dist);
+}
+
 void require_single(CapiIndex &ix, const char *what) {
   if (ix.sharded) throw std::runtime_error(std::string(what) + ": the index is sharded over several GPUs and read-only");
 }
@@ -975,28 +1066,8 @@ bool ngt_remove_index(NGTIndex index, ObjectID id, NGTError error) {
     CapiIndex &ix = *static_cast<CapiIndex *>(index);
     require_single(ix, "remove");
     if (id == 0 || id > ix.n() || !ix.present[id]) throw std::runtime_error("remove: the specified object does not exist. ID=" + std::to_string(id));
+    remove_edges_reliably(ix, id);
     ix.present[id] = 0;
-    // the graph covers ids 1..n_graph (= n when nothing is queued; the objects appended since the last build are not in
-    // it yet): the node and every edge to it go, whether or not objects are pending
-    if (ix.row_ptr.size() >= 2 && ix.row_ptr.size() <= ix.n() + 2) {
-      const size_t n_graph = ix.row_ptr.size() - 2;
-      std::vector<uint64_t> rp(n_graph + 2, 0);
-      std::vector<uint32_t> col;
-      std::vector<float> dist;
-      for (size_t s = 1; s <= n_graph; s++) {
-        rp[s] = col.size();
-        if (s != id)
-          for (uint64_t e = ix.row_ptr[s]; e < ix.row_ptr[s + 1]; e++)
-            if (ix.col[e] != id) {
-              col.push_back(ix.col[e]);
-              dist.push_back(ix.dist[e]);
-            }
-      }
-      rp[n_graph + 1] = col.size();
-      ix.row_ptr.swap(rp);
-      ix.col.swap(col);
-      ix.dist.swap(dist);
-    }
     upload(ix);
   }
   CAPI_CATCH(false)

@@ -1201,3 +1201,70 @@ extern "C" int ngtgpu_device_free(void *device_pointer) {
   if (device_pointer) CUDA_TRY(cudaFree(device_pointer));
   return NGTGPU_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Distances among a handful of stored objects, the engine's exact distance: what NeighborhoodGraph::removeEdgesReliably
+// (lib/NGT/Graph.cpp:641-864) asks the comparator for when it re-links the neighbours of a removed node.
+namespace {
+template <int ACC, int G>
+__global__ void __launch_bounds__(256) pairwise_kernel(const uint8_t *__restrict__ rows, uint32_t row_bytes, uint32_t chunks, int dtype,
+                                                       const uint32_t *__restrict__ ids, uint32_t m, float *__restrict__ out) {
+  constexpr int R = 32 / G;
+  const int lane = threadIdx.x & 31, gl = lane % G, grp = lane / G;
+  const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint64_t total = (uint64_t)m * m;
+  const uint64_t pair = warp * R + grp;
+  const bool act = pair < total;
+  const uint32_t i = act ? (uint32_t)(pair / m) : 0u, j = act ? (uint32_t)(pair % m) : 0u;
+  const float d = group_distance_gmem<ACC, G>(rows + (size_t)ids[i] * row_bytes, rows + (size_t)ids[j] * row_bytes, chunks, gl, dtype);
+  if (act && gl == 0) out[pair] = d;
+}
+template <int ACC>
+cudaError_t launch_pairwise(int group, const uint8_t *rows, uint32_t row_bytes, uint32_t chunks, int dtype, const uint32_t *ids, uint32_t m,
+                            float *out, cudaStream_t stream) {
+  const uint64_t pairs = (uint64_t)m * m;
+  const uint64_t warps = (pairs + (32 / group) - 1) / (32 / group);
+  const unsigned grid = (unsigned)((warps + 7) / 8);
+  switch (group) {
+    case 1: pairwise_kernel<ACC, 1><<<grid, 256, 0, stream>>>(rows, row_bytes, chunks, dtype, ids, m, out); break;
+    case 2: pairwise_kernel<ACC, 2><<<grid, 256, 0, stream>>>(rows, row_bytes, chunks, dtype, ids, m, out); break;
+    case 4: pairwise_kernel<ACC, 4><<<grid, 256, 0, stream>>>(rows, row_bytes, chunks, dtype, ids, m, out); break;
+    case 8: pairwise_kernel<ACC, 8><<<grid, 256, 0, stream>>>(rows, row_bytes, chunks, dtype, ids, m, out); break;
+    case 16: pairwise_kernel<ACC, 16><<<grid, 256, 0, stream>>>(rows, row_bytes, chunks, dtype, ids, m, out); break;
+    case 32: pairwise_kernel<ACC, 32><<<grid, 256, 0, stream>>>(rows, row_bytes, chunks, dtype, ids, m, out); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+}  // namespace
+
+extern "C" int ngtgpu_index_pairwise_distances(ngtgpu_index *ix, const uint32_t *ids, uint32_t m, float *out) {
+  if (!ix) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "null index handle");
+  NGTGPU_TRY(ngtgpu_check_device(ix));
+  if (m == 0) return NGTGPU_OK;
+  if (!ids || !out) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "ngtgpu_index_pairwise_distances: null buffer");
+  if (!ix->d_objects) NGTGPU_FAIL(NGTGPU_ERR_STATE, "ngtgpu_index_pairwise_distances: the index holds no objects");
+  if (m > 4096) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "ngtgpu_index_pairwise_distances: at most 4096 objects");
+  for (uint32_t i = 0; i < m; i++)
+    if (ids[i] == 0 || ids[i] > ix->n) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "ngtgpu_index_pairwise_distances: id out of range");
+  cudaStream_t stream = ix->stream;
+  DeviceBuffers mem;
+  uint32_t *d_ids;
+  float *d_out;
+  CUDA_TRY(mem.alloc(&d_ids, m));
+  CUDA_TRY(mem.alloc(&d_out, (size_t)m * m));
+  CUDA_TRY(cudaMemcpyAsync(d_ids, ids, (size_t)m * 4, cudaMemcpyHostToDevice, stream));
+  cudaError_t ce;
+  switch (ix->acc_kind) {
+    case ACC_F_L2: ce = launch_pairwise<ACC_F_L2>((int)ix->group, ix->d_objects, ix->row_bytes, ix->chunks, ix->distance_type, d_ids, m, d_out, stream); break;
+    case ACC_F_DOT: ce = launch_pairwise<ACC_F_DOT>((int)ix->group, ix->d_objects, ix->row_bytes, ix->chunks, ix->distance_type, d_ids, m, d_out, stream); break;
+    case ACC_F_COS: ce = launch_pairwise<ACC_F_COS>((int)ix->group, ix->d_objects, ix->row_bytes, ix->chunks, ix->distance_type, d_ids, m, d_out, stream); break;
+    case ACC_U8_L2: ce = launch_pairwise<ACC_U8_L2>((int)ix->group, ix->d_objects, ix->row_bytes, ix->chunks, ix->distance_type, d_ids, m, d_out, stream); break;
+    default: ce = launch_pairwise<ACC_U8_HAM>((int)ix->group, ix->d_objects, ix->row_bytes, ix->chunks, ix->distance_type, d_ids, m, d_out, stream); break;
+  }
+  if (ce != cudaSuccess) NGTGPU_FAIL(NGTGPU_ERR_CUDA, std::string("pairwise distance kernel launch: ") + cudaGetErrorString(ce));
+  ix->launches++;
+  CUDA_TRY(cudaMemcpyAsync(out, d_out, (size_t)m * m * 4, cudaMemcpyDeviceToHost, stream));
+  CUDA_TRY(cudaStreamSynchronize(stream));
+  return NGTGPU_OK;
+}

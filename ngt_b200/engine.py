@@ -191,6 +191,13 @@ class GpuIndex:
         _lib.check(self._lib.ngtgpu_index_get_object(self._h, int(object_id), out.ctypes.data))
         return out
 
+    def pairwise_distances(self, ids):
+        """[m, m] float32 distances among the stored objects `ids` (the engine's exact distance)."""
+        ids = np.ascontiguousarray(ids, np.uint32)
+        out = np.zeros((ids.size, ids.size), np.float32)
+        _lib.check(self._lib.ngtgpu_index_pairwise_distances(self._h, ids.ctypes.data, ids.size, out.ctypes.data))
+        return out
+
     def get_objects(self, first, count):
         """Stored rows first .. first+count-1, one strided copy."""
         out = np.zeros((int(count), self.dimension), _np_type(self.object_type))

@@ -321,16 +321,71 @@ class Index:
         oid = object_id + 1 if self.zero_numbering else object_id
         if oid < 1 or oid > self._objects.shape[0] or not self._present[oid]:
             raise NgtGpuError(_lib.ERR_INVALID, "remove: no such object %d" % object_id)
+        self._remove_edges_reliably(oid)
         self._present[oid] = 0
+        self._upload()
+
+    def _remove_edges_reliably(self, oid):
+        """NeighborhoodGraph::removeEdgesReliably (lib/NGT/Graph.cpp:641-864), as ngt_remove_index of the C API does it:
+        back edges go, the neighbours are chained nearest-first with distances from the device; a missing back edge is
+        skipped like the reference's NGT_FORCED_REMOVE build does."""
+        import bisect
         rp, col, dist = self._graph
-        keep = col != oid
-        src = np.repeat(np.arange(rp.size - 1), np.diff(rp.astype(np.int64)))
-        keep &= src != oid
-        deg = np.bincount(src[keep], minlength=rp.size - 1)
+        n_graph = rp.size - 2
+        if oid > n_graph:
+            return
+        lists = {}
+
+        def get(nid):
+            if nid not in lists:
+                lists[nid] = [(float(dist[e]), int(col[e])) for e in range(int(rp[nid]), int(rp[nid + 1]))]
+            return lists[nid]
+        node = [e for e in get(oid) if e[1] != oid]
+        for (d, nid) in node:
+            lst = get(nid)
+            pos = bisect.bisect_left(lst, (d, oid))
+            if pos < len(lst) and lst[pos][1] == oid:
+                del lst[pos]
+        order = [nid for (_, nid) in node]
+        m = len(order)
+        if m > 1:
+            D = self._gpu.pairwise_distances(np.array(order, np.uint32))
+            slot = list(range(m))
+            for i in range(m - 1):
+                row = D[slot[i]]
+                minj, mind = -1, np.float32(3.4028235e38)
+                for j in range(i + 1, m):
+                    if row[slot[j]] < mind:
+                        minj, mind = j, row[slot[j]]
+                a, b = order[i], order[minj]
+                for (src, dst) in ((a, b), (b, a)):
+                    lst = get(src)
+                    pos = bisect.bisect_left(lst, (float(mind), dst))
+                    if pos == len(lst) or lst[pos][1] != dst:
+                        lst.insert(pos, (float(mind), dst))
+                if i + 1 != minj:
+                    order[i + 1], order[minj] = order[minj], order[i + 1]
+                    slot[i + 1], slot[minj] = slot[minj], slot[i + 1]
+        lists[oid] = []
+        deg = np.diff(rp.astype(np.int64))
+        for nid, lst in lists.items():
+            deg[nid] = len(lst)
         nrp = np.zeros_like(rp)
         nrp[1:] = np.cumsum(deg)
-        self._graph = (nrp, col[keep], dist[keep])
-        self._upload()
+        ncol = np.zeros(int(nrp[-1]), col.dtype)
+        ndist = np.zeros(int(nrp[-1]), dist.dtype)
+        touched = np.zeros(rp.size - 1, bool)
+        touched[list(lists.keys())] = True
+        src = np.repeat(np.arange(rp.size - 1), np.diff(rp.astype(np.int64)))
+        keep = ~touched[src]
+        dst_pos = (nrp[:-1].astype(np.int64)[src] + (np.arange(col.size) - rp[:-1].astype(np.int64)[src]))[keep]
+        ncol[dst_pos] = col[keep]
+        ndist[dst_pos] = dist[keep]
+        for nid, lst in lists.items():
+            b = int(nrp[nid])
+            for t, (d, c) in enumerate(lst):
+                ncol[b + t], ndist[b + t] = c, d
+        self._graph = (nrp, ncol, ndist)
 
     def save(self):
         if self._pending:

@@ -196,6 +196,7 @@ class Ref:
         lib.ref_object_distance.restype = C.c_double
         lib.ref_object_distance.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
         lib.ref_insert_node.argtypes = [C.c_void_p, C.c_uint32, _u32p, _f32p, C.c_size_t]
+        lib.ref_remove.argtypes = [C.c_void_p, C.c_uint32]
         lib.ref_epsilon_from_accuracy_table.restype = C.c_float
         lib.ref_epsilon_from_accuracy_table.argtypes = [C.c_char_p, C.c_double]
         lib.ref_tree_seeds.argtypes = [C.c_void_p, _f32p, C.c_size_t, C.c_int, C.c_size_t, _u32p, C.c_size_t, _u32p]
@@ -226,6 +227,9 @@ class Ref:
 
     def refine_anng(self, h, epsilon=0.1, accuracy=0.0, no_of_edges=0, explore_edge_size=-2 ** 31, batch_size=10000):
         self._check(self.lib.ref_refine_anng(h, epsilon, accuracy, no_of_edges, explore_edge_size, batch_size))
+
+    def remove(self, h, object_id):
+        self._check(self.lib.ref_remove(h, int(object_id)))
 
     def epsilon_from_accuracy_table(self, table, accuracy):
         e = self.lib.ref_epsilon_from_accuracy_table(table.encode(), accuracy)
@@ -457,3 +461,40 @@ def build_anng_loop(port, pobj, rows_int, seeds, first_id, count, lists=None, ed
             for (d, t) in res[x]:
                 bisect.insort(lists[t], (d, i))
     return lists
+
+
+def remove_edges_reliably_loop(port, dtype, otype, pobj, lists, node_id):
+    """Sequential restatement of NeighborhoodGraph::removeEdgesReliably (lib/NGT/Graph.cpp:641-864), what
+    NGT::Index::remove does to the graph: the removed node's back edges go, then its neighbours are chained -- neighbour
+    i is linked (both ways, at their own distance) to the nearest of the neighbours after it, which then takes place
+    i + 1 -- so that the removal does not disconnect them. `lists`: per id a list of (distance, id) ascending, edited in
+    place. Pinned to the reference by tests/golden/remove.npz (test_oracle_pin.py); test infrastructure."""
+    import bisect
+    node = list(lists[node_id])
+    if not node:
+        return
+    for (d, nid) in node:
+        n = lists[nid]
+        pos = bisect.bisect_left(n, (d, node_id))
+        if pos < len(n) and n[pos][1] == node_id:     # (else: reported and skipped, NGT_FORCED_REMOVE, defines.h.in:36)
+            del n[pos]
+    order = [nid for (_, nid) in node]
+    for i in range(len(order) - 1):
+        minj, mind = -1, np.float32(3.4028235e38)
+        for j in range(i + 1, len(order)):
+            d = np.float32(port.distance(dtype, otype, pobj[order[i]], pobj[order[j]]))
+            if d < mind:
+                minj, mind = j, d
+        a, b = order[i], order[minj]
+        ins = []
+        for (src, dst) in ((a, b), (b, a)):
+            n = lists[src]
+            pos = bisect.bisect_left(n, (float(mind), dst))
+            if pos == len(n) or n[pos][1] != dst:
+                n.insert(pos, (float(mind), dst))
+                ins.append(True)
+            else:
+                ins.append(False)
+        if i + 1 != minj:
+            order[i + 1], order[minj] = order[minj], order[i + 1]
+    lists[node_id] = []

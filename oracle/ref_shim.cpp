@@ -315,6 +315,15 @@ int ref_insert_node(void *h, uint32_t id, const uint32_t *ids, const float *dist
   REF_CATCH(-1)
 }
 
+// NGT::Index::remove(id) (Index.h:463 -> GraphIndex::remove, Index.h:803-815 -> removeEdgesReliably, Graph.cpp:641-864)
+int ref_remove(void *h, uint32_t id) {
+  REF_TRY
+  NGT::Index &idx = *static_cast<NGT::Index *>(h);
+  idx.remove(id);
+  return 0;
+  REF_CATCH(-1)
+}
+
 // Index::AccuracyTable (Index.h:293-360): set(string) + getEpsilon(accuracy), standalone (what GraphIndex::search
 // applies when expectedAccuracy > 0, Index.h:1156-1158). Returns NaN and sets the error text when the table throws.
 float ref_epsilon_from_accuracy_table(const char *table, double accuracy) {

@@ -425,3 +425,38 @@ def test_concurrent_searches_on_one_handle(lib, sift5k):
     lib.ngt_close_index(ix)
     lib.ngt_destroy_property(prop)
     lib.ngt_destroy_error_object(err)
+
+
+def test_remove_repairs_edges_like_the_reference(lib, tmp_path):
+    """ngt_remove_index == NGT::Index::remove of the reference (removeEdgesReliably, Graph.cpp:641-864): the ANNG the
+    reference built (tests/golden/anng_build.npz), written in NGT's file format, opened through the C API, the same nine
+    removals: every list equals the reference's (tests/golden/remove.npz). The Python mirror does the same."""
+    from ngt_b200 import index as ngt
+    from ngt_b200 import index_io, synth
+    zb = np.load(os.path.join(GOLDEN, "anng_build.npz"))
+    zr = np.load(os.path.join(GOLDEN, "remove.npz"))
+    objtype, n, n_first, seed, e, es, ss, bs = [int(v) for v in zb["f_b200_meta"]]
+    base = synth.make("sift", n, seed)
+    src = str(tmp_path / "anng")
+    os.makedirs(src)
+    index_io.write_prf(src, dict(index_io.DEFAULT_PRF, Dimension="128", EdgeSizeForCreation=str(e), EdgeSizeForSearch=str(es)))
+    index_io.write_objects(src, base)
+    index_io.write_graph(src, zb["f_b200_row_ptr"][:n + 2].astype(np.uint64), zb["f_b200_col"], zb["f_b200_dist"])
+    rp, col, dist = zr["row_ptr"], zr["col"], zr["dist"]
+    want = [[(int(col[x]), float(dist[x])) for x in range(int(rp[i]), int(rp[i + 1]))] for i in range(1, n + 1)]
+    err = lib.ngt_create_error_object()
+    ix = lib.ngt_open_index(src.encode(), err)
+    assert ix, lib.ngt_get_error_string(err)
+    for rid in zr["removed"]:
+        assert lib.ngt_remove_index(ix, int(rid), err), lib.ngt_get_error_string(err)
+    assert _edges(lib, ix, n, err) == want
+    assert lib.ngt_remove_index(ix, int(zr["removed"][0]), err) is False        # already gone
+    lib.ngt_close_index(ix)
+    lib.ngt_destroy_error_object(err)
+    m = ngt.Index(src, zero_based_numbering=False)
+    for rid in zr["removed"]:
+        m.remove(int(rid))
+    mrp, mcol, mdist = m._graph
+    got = [[(int(mcol[x]), float(mdist[x])) for x in range(int(mrp[i]), int(mrp[i + 1]))] for i in range(1, n + 1)]
+    assert got == want
+    m.close()

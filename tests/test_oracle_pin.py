@@ -202,3 +202,16 @@ def test_refine_anng_restatement_equals_the_reference(port, tag):
     got = po.refine_anng_loop(port, po.L2, c["otype"], pobj, zb[src + "_row_ptr"][:n + 2].astype(np.uint64), zb[src + "_col"],
                               zb[src + "_dist"], seeds, eps, noe, c["es"] if c["es"] else 2 ** 31 - 1, bs, c["e"])
     assert got == _lists(zr[tag + "_row_ptr"], zr[tag + "_col"], zr[tag + "_dist"])[:n + 1]
+
+
+def test_remove_edges_reliably_restatement_equals_the_reference(port):
+    """Graph.cpp:641-864 (NGT::Index::remove): nine removals from the reference-built ANNG of anng_build.npz, edge for edge
+    against the graph the reference was left with (tests/golden/remove.npz)."""
+    zb = np.load(os.path.join(GOLDEN, "anng_build.npz"))
+    zr = np.load(os.path.join(GOLDEN, "remove.npz"))
+    c = anng_case(zb, "f_b200")
+    pobj = po.pad_objects(c["base"], po.FLOAT)
+    lists = [list(l) for l in c["lists"]]
+    for rid in zr["removed"]:
+        po.remove_edges_reliably_loop(port, po.L2, po.FLOAT, pobj, lists, int(rid))
+    assert lists == _lists(zr["row_ptr"], zr["col"], zr["dist"])[:c["n"] + 1]
