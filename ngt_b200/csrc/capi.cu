@@ -394,6 +394,165 @@ void remove_edges_reliably(CapiIndex &ix, ObjectID id) {
   ix.dist.swap(dist);
 }
 
+void require_built(CapiIndex &ix);
+
+// ---- Optimizer::generateAccuracyTable (lib/NGT/Optimizer.h:1494-1573), the batched self-search consumer behind the
+// `AccuracyTable` of an optimised index (GraphOptimizer::execute, GraphOptimizer.h:355-368): queries are objects taken
+// at even strides from the repository (extractQueries, :1139-1190); a pseudo ground truth comes from raising epsilon
+// until the answers stop changing (generatePseudoGroundTruth, :1418-1492) and one search with all edges at that epsilon;
+// then accuracy(epsilon) -- relevant = id in the ground truth or distance within its farthest, :496-507 -- is sampled
+// with the reference's adaptive step. Every search of the reference's loops is ONE batch call here. The reference ends
+// the ground-truth loop when a sweep takes 40x the time of the first; here the distance computations of the sweep are
+// the clock (same meaning, no timer in the result).
+struct BatchAnswer {
+  std::vector<uint32_t> ids, counts;
+  std::vector<float> dists;
+  uint64_t n_dist = 0;
+};
+void batch_answer(CapiIndex &ix, const std::vector<float> &queries, uint32_t nq, uint32_t size, float epsilon, int64_t edge_size,
+                  BatchAnswer &out) {
+  out.ids.assign((size_t)nq * size, 0);
+  out.dists.assign((size_t)nq * size, 0.f);
+  out.counts.assign(nq, 0);
+  std::vector<uint32_t> stats((size_t)nq * 3, 0);
+  ngtgpu_search_params p = {size, epsilon, -1.0f, edge_size};
+  uint32_t seeds = (uint32_t)prf_long(ix, "SeedSize", 10);
+  check(ngtgpu_search(ix.gpu, queries.data(), NGTGPU_OBJECT_FLOAT, nq, &p, nullptr, seeds ? seeds : 10, out.ids.data(), out.dists.data(),
+                      out.counts.data(), stats.data()));
+  out.n_dist = 0;
+  for (uint32_t q = 0; q < nq; q++) out.n_dist += stats[(size_t)q * 3];
+}
+
+std::vector<std::pair<float, double>> generate_accuracy_table(CapiIndex &ix, size_t n_results, size_t n_queries) {
+  if (ix.prop.edge_size_for_search != 0 && ix.prop.edge_size_for_search != -2) {
+    std::stringstream msg;
+    msg << "Optimizer::generateAccuracyTable: edgeSizeForSearch is invalid to call generateAccuracyTable, because accuracy 1.0 cannot "
+           "be achieved with the setting. edgeSizeForSearch=" << ix.prop.edge_size_for_search << ".";
+    throw std::runtime_error(msg.str());
+  }
+  require_built(ix);
+  const size_t osize = ix.n() + 1, dim = (size_t)ix.prop.dimension;
+  if (n_queries == 0 || osize / n_queries == 0) throw std::runtime_error("Optimizer::extractQueries: too few objects for the queries asked for");
+  // extractQueries: the objects at even strides, the next present one where a slot is empty
+  std::vector<float> queries;
+  const size_t interval = osize / n_queries;
+  size_t count = 0;
+  for (size_t id1 = 1; id1 < osize && count < n_queries; id1 += interval, count++) {
+    size_t oft = 0;
+    while (!ix.present[id1 + oft]) {
+      oft++;
+      if (id1 + oft >= osize) {
+        std::stringstream msg;
+        msg << "Too many empty entries to extract. Object repository size=" << osize << " " << id1 << ":" << oft;
+        throw std::runtime_error(msg.str());
+      }
+    }
+    const uint8_t *row = &ix.objects[(id1 + oft - 1) * ix.record_bytes()];
+    for (size_t j = 0; j < dim; j++)
+      queries.push_back(ix.prop.object_type == NGTGPU_OBJECT_UINT8 ? (float)row[j] : reinterpret_cast<const float *>(row)[j]);
+  }
+  const uint32_t nq = (uint32_t)count, size = (uint32_t)n_results;
+  BatchAnswer ans;
+  // generatePseudoGroundTruth
+  float max_epsilon = 0.0f;
+  {
+    int identity_count = 0;
+    std::vector<float> last(nq, 0.f);
+    uint64_t work0 = 0;
+    double step = 0.02;
+    for (float e = 0.0f; e < 10.0f; e += step) {
+      batch_answer(ix, queries, nq, size, e, -1, ans);
+      bool identity = true;
+      for (uint32_t q = 0; q < nq; q++) {
+        const float d = ans.counts[q] ? ans.dists[(size_t)q * size + ans.counts[q] - 1] : 0.f;
+        if (d != last[q]) identity = false;
+        last[q] = d;
+      }
+      if (e == 0.0f) work0 = ans.n_dist;
+      if (ans.n_dist > work0 * 40) {
+        max_epsilon = e;
+        break;
+      }
+      if (identity) {
+        identity_count++;
+        step *= 1.2;
+        if (identity_count > 5) {
+          max_epsilon = e;
+          break;
+        }
+      } else {
+        identity_count = 0;
+      }
+    }
+  }
+  BatchAnswer gt;
+  batch_answer(ix, queries, nq, size, max_epsilon, 0, gt);   // all edges: the best accuracy the graph gives
+  auto accuracy_at = [&](float epsilon) {
+    batch_answer(ix, queries, nq, size, epsilon, -1, ans);
+    double sum = 0.0;
+    for (uint32_t q = 0; q < nq; q++) {
+      const uint32_t gn = gt.counts[q];
+      if (gn == 0) continue;
+      const uint32_t *gi = &gt.ids[(size_t)q * size];
+      const float farthest = gt.dists[(size_t)q * size + gn - 1];
+      uint32_t relevant = 0;
+      for (uint32_t r = 0; r < ans.counts[q]; r++) {
+        const uint32_t id = ans.ids[(size_t)q * size + r];
+        const float d = ans.dists[(size_t)q * size + r];
+        if (std::find(gi, gi + gn, id) != gi + gn) relevant++;
+        else if (farthest > 0.0f && d <= farthest) relevant++;
+      }
+      sum += (double)relevant / (double)gn;
+    }
+    return sum / (double)nq;
+  };
+  std::map<float, double> map;
+  {
+    float interval2 = 0.05f, prev = 0.0f, epsilon = -0.6f;
+    double accuracy;
+    do {
+      auto pair = map.find(epsilon);
+      if (pair == map.end()) {
+        accuracy = accuracy_at(epsilon);
+        map.insert(std::make_pair(epsilon, accuracy));
+      } else {
+        accuracy = pair->second;
+      }
+      if (prev != 0.0f) {
+        if (accuracy - prev < 0.02) {
+          interval2 *= 2.0f;
+        } else if (accuracy - prev > 0.05 && interval2 > 0.0001f) {
+          epsilon -= interval2;
+          interval2 /= 2.0f;
+          accuracy = prev;
+        }
+      }
+      prev = (float)accuracy;
+      epsilon += interval2;
+      if (accuracy > 0.98 && epsilon > max_epsilon) break;
+    } while (accuracy < 1.0);
+  }
+  std::vector<std::pair<float, double>> table;
+  std::pair<float, double> prev(0.0f, -1.0);
+  for (auto &kv : map) {
+    if (fabs(kv.first - prev.first) <= FLT_EPSILON) continue;
+    if (kv.second - prev.second < DBL_EPSILON) continue;
+    table.push_back(kv);
+    if (kv.second >= 1.0) break;
+    prev = kv;
+  }
+  return table;
+}
+
+std::string accuracy_table_string(const std::vector<std::pair<float, double>> &t) {   // Index::AccuracyTable::getString, Index.h:349-358
+  std::stringstream str;
+  for (size_t i = 0; i < t.size(); i++) {
+    str << t[i].first << ":" << t[i].second;
+    if (i + 1 != t.size()) str << ",";
+  }
+  return str.str();
+}
+
 void require_single(CapiIndex &ix, const char *what) {
   if (ix.sharded) throw std::runtime_error(std::string(what) + ": the index is sharded over several GPUs and read-only");
 }
@@ -1244,9 +1403,27 @@ void optimizer_execute(const CapiOptimizer &o, const std::string &in, const std:
   g->to_host(ix);
   check(ngtgpu_io_write_grp(grp.c_str(), n, ix.row_ptr.data(), ix.col.data(), ix.dist.data(), ix.present.data()));
   // (IndexType and the rest of the property stay as they were: only GraphType changes, GraphOptimizer.h:272-274)
-  std::ofstream f(out + "/prf");
-  if (!f.is_open()) throw std::runtime_error("PropertySet::save: Cannot save. " + out + "/prf");
-  for (auto &kv : ix.prf) f << kv.first << "\t" << kv.second << "\n";
+  auto save_prf = [&]() {
+    std::ofstream f(out + "/prf");
+    if (!f.is_open()) throw std::runtime_error("PropertySet::save: Cannot save. " + out + "/prf");
+    for (auto &kv : ix.prf) f << kv.first << "\t" << kv.second << "\n";
+  };
+  save_prf();
+  // The accuracy table (GraphOptimizer.h:355-368): generated on the device when the index's edge-size mode allows an
+  // accuracy of 1.0 (0 or -2, Optimizer.h:1497-1502). The reference reaches -2 through its timed coefficient tuning, which
+  // is not run here; an index still on a fixed edge cap keeps its (empty) table instead of failing the whole call.
+  if (o.accuracy_table && (ix.prop.edge_size_for_search == 0 || ix.prop.edge_size_for_search == -2)) {
+    std::unique_ptr<CapiIndex, void (*)(CapiIndex *)> opened(open_index(out.c_str(), std::vector<int>()), [](CapiIndex *p) {
+      if (p->gpu) ngtgpu_index_destroy(p->gpu);
+      delete p;
+    });
+    try {
+      ix.prf["AccuracyTable"] = accuracy_table_string(generate_accuracy_table(*opened, (size_t)o.results, (size_t)o.queries));
+    } catch (std::exception &err) {
+      throw std::runtime_error(std::string("Optimizer::execute: Cannot generate the accuracy table. ") + err.what());
+    }
+    save_prf();
+  }
 }
 
 }  // namespace

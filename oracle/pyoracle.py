@@ -197,6 +197,7 @@ class Ref:
         lib.ref_object_distance.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
         lib.ref_insert_node.argtypes = [C.c_void_p, C.c_uint32, _u32p, _f32p, C.c_size_t]
         lib.ref_remove.argtypes = [C.c_void_p, C.c_uint32]
+        lib.ref_build_onng_with_accuracy_table.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
         lib.ref_epsilon_from_accuracy_table.restype = C.c_float
         lib.ref_epsilon_from_accuracy_table.argtypes = [C.c_char_p, C.c_double]
         lib.ref_tree_seeds.argtypes = [C.c_void_p, _f32p, C.c_size_t, C.c_int, C.c_size_t, _u32p, C.c_size_t, _u32p]
@@ -227,6 +228,10 @@ class Ref:
 
     def refine_anng(self, h, epsilon=0.1, accuracy=0.0, no_of_edges=0, explore_edge_size=-2 ** 31, batch_size=10000):
         self._check(self.lib.ref_refine_anng(h, epsilon, accuracy, no_of_edges, explore_edge_size, batch_size))
+
+    def build_onng_with_accuracy_table(self, anng, onng, outgoing, incoming, shortcut=True, n_queries=100, n_results=20):
+        self._check(self.lib.ref_build_onng_with_accuracy_table(anng.encode(), onng.encode(), outgoing, incoming, int(shortcut),
+                                                                n_queries, n_results))
 
     def remove(self, h, object_id):
         self._check(self.lib.ref_remove(h, int(object_id)))

@@ -315,6 +315,18 @@ int ref_insert_node(void *h, uint32_t id, const uint32_t *ids, const float *dist
   REF_CATCH(-1)
 }
 
+// GraphOptimizer::execute with the accuracy-table step on (GraphOptimizer.h:230-372); the timed tuning steps stay off.
+int ref_build_onng_with_accuracy_table(const char *anng_path, const char *onng_path, int outgoing, int incoming,
+                                       int shortcut_reduction, int n_queries, int n_results) {
+  REF_TRY
+  NGT::GraphOptimizer go(true);
+  go.set(outgoing, incoming, n_queries, n_results);
+  go.setProcessingModes(shortcut_reduction != 0, false, false, true);
+  go.execute(anng_path, onng_path);
+  return 0;
+  REF_CATCH(-1)
+}
+
 // NGT::Index::remove(id) (Index.h:463 -> GraphIndex::remove, Index.h:803-815 -> removeEdgesReliably, Graph.cpp:641-864)
 int ref_remove(void *h, uint32_t id) {
   REF_TRY

@@ -460,3 +460,52 @@ def test_remove_repairs_edges_like_the_reference(lib, tmp_path):
     got = [[(int(mcol[x]), float(mdist[x])) for x in range(int(mrp[i]), int(mrp[i + 1]))] for i in range(1, n + 1)]
     assert got == want
     m.close()
+
+
+def test_optimizer_execute_generates_the_accuracy_table(lib, tmp_path):
+    """ngt_optimizer_execute with the accuracy-table step on (GraphOptimizer.h:355-368 -> Optimizer::generateAccuracyTable,
+    Optimizer.h:1494-1573: every search of its loops is one batch call here) on the ANNG the reference built
+    (anng_build.npz, f_b64_all), against the table the reference generated from the same ANNG with the same settings
+    (tests/golden/accuracy_table.json "generated"). The graphs are identical; the seeds differ (device pivots vs the
+    reference's fixed nodes), so the tables agree closely where accuracy is high and only in shape below."""
+    from ngt_b200 import index_io, synth
+    from ngt_b200.index import epsilon_from_accuracy_table
+    gen = json.load(open(os.path.join(GOLDEN, "accuracy_table.json")))["generated"]
+    zb = np.load(os.path.join(GOLDEN, "anng_build.npz"))
+    objtype, n, n_first, seed, e, es, ss, bs = [int(v) for v in zb[gen["case"] + "_meta"]]
+    src, dst = str(tmp_path / "anng"), str(tmp_path / "onng")
+    os.makedirs(src)
+    index_io.write_prf(src, dict(index_io.DEFAULT_PRF, Dimension="128", EdgeSizeForCreation=str(e), EdgeSizeForSearch=str(es)))
+    index_io.write_objects(src, synth.make("sift", n, seed))
+    index_io.write_graph(src, zb[gen["case"] + "_row_ptr"][:n + 2].astype(np.uint64), zb[gen["case"] + "_col"], zb[gen["case"] + "_dist"])
+    err = lib.ngt_create_error_object()
+    opt = lib.ngt_create_optimizer(True, err)
+    assert lib.ngt_optimizer_set_minimum(opt, gen["outgoing"], gen["incoming"], gen["queries"], gen["results"], err)
+    assert lib.ngt_optimizer_set_processing_modes(opt, False, False, True, err)
+    assert lib.ngt_optimizer_execute(opt, src.encode(), dst.encode(), err), lib.ngt_get_error_string(err)
+    lib.ngt_destroy_optimizer(opt)
+    table = index_io.read_prf(dst)["AccuracyTable"]
+    pts = [(float(t.split(":")[0]), float(t.split(":")[1])) for t in table.split(",")]
+    assert len(pts) >= 8 and abs(pts[0][0] + 0.6) < 1e-6                  # starts at epsilon -0.6 like the reference's sweep
+    assert all(b[0] > a[0] and b[1] > a[1] for a, b in zip(pts, pts[1:]))      # strictly increasing in both
+    assert pts[-1][1] > 0.98
+    for acc in (0.9, 0.95, 0.98):
+        assert abs(epsilon_from_accuracy_table(table, acc) - epsilon_from_accuracy_table(gen["table"], acc)) <= 0.05, acc
+    # the table is used: an expected-accuracy search through the C API on the written index
+    ix = lib.ngt_open_index(dst.encode(), err)
+    assert ix, lib.ngt_get_error_string(err)
+    q = np.ascontiguousarray(synth.make("sift", 1, 3)[0])
+    r = lib.ngt_create_empty_results(err)
+    nq = capi.Query(capi.fptr(q), 10, 0.0, 0.95, -1.0, C.c_size_t(-2**31 & (2**64 - 1)))
+    assert lib.ngt_search_index_with_query(ix, nq, r, err), lib.ngt_get_error_string(err)
+    assert len(capi.results_of(lib, r, err)) == 10
+    lib.ngt_destroy_results(r)
+    lib.ngt_close_index(ix)
+    # an index on a fixed edge cap keeps its empty table (the reference gets to -2 through its timed tuning, not run here)
+    index_io.write_prf(src, dict(index_io.DEFAULT_PRF, Dimension="128", EdgeSizeForCreation=str(e), EdgeSizeForSearch="40"))
+    dst2 = str(tmp_path / "onng40")
+    opt = lib.ngt_create_optimizer(True, err)
+    assert lib.ngt_optimizer_execute(opt, src.encode(), dst2.encode(), err), lib.ngt_get_error_string(err)
+    lib.ngt_destroy_optimizer(opt)
+    assert index_io.read_prf(dst2)["AccuracyTable"] == ""
+    lib.ngt_destroy_error_object(err)
