@@ -382,10 +382,13 @@ void remove_edges_reliably(CapiIndex &ix, ObjectID id) {
         dist.push_back(e.first);
       }
     } else {
-      for (uint64_t e = ix.row_ptr[s2]; e < ix.row_ptr[s2 + 1]; e++) {
-        col.push_back(ix.col[e]);
-        dist.push_back(ix.dist[e]);
-      }
+      // (an asymmetric graph -- an ONNG -- can hold edges to the removed node in lists the node itself does not name;
+      // the reference leaves those dangling, here they go too, so a search never walks into an empty slot)
+      for (uint64_t e = ix.row_ptr[s2]; e < ix.row_ptr[s2 + 1]; e++)
+        if (ix.col[e] != id) {
+          col.push_back(ix.col[e]);
+          dist.push_back(ix.dist[e]);
+        }
     }
   }
   rp[n_graph + 1] = col.size();

@@ -367,7 +367,10 @@ class Index:
                     order[i + 1], order[minj] = order[minj], order[i + 1]
                     slot[i + 1], slot[minj] = slot[minj], slot[i + 1]
         lists[oid] = []
-        deg = np.diff(rp.astype(np.int64))
+        # (edges to the removed node from lists it does not name itself -- asymmetric graphs -- go as well)
+        src_all = np.repeat(np.arange(rp.size - 1), np.diff(rp.astype(np.int64)))
+        alive = col != oid
+        deg = np.bincount(src_all[alive], minlength=rp.size - 1).astype(np.int64)
         for nid, lst in lists.items():
             deg[nid] = len(lst)
         nrp = np.zeros_like(rp)
@@ -376,9 +379,12 @@ class Index:
         ndist = np.zeros(int(nrp[-1]), dist.dtype)
         touched = np.zeros(rp.size - 1, bool)
         touched[list(lists.keys())] = True
-        src = np.repeat(np.arange(rp.size - 1), np.diff(rp.astype(np.int64)))
-        keep = ~touched[src]
-        dst_pos = (nrp[:-1].astype(np.int64)[src] + (np.arange(col.size) - rp[:-1].astype(np.int64)[src]))[keep]
+        keep = ~touched[src_all] & alive
+        rank = np.cumsum(keep) - 1                                  # position among the kept entries ...
+        first = np.zeros(rp.size - 1, np.int64)
+        kept_deg = np.bincount(src_all[keep], minlength=rp.size - 1)
+        first[1:] = np.cumsum(kept_deg)[:-1]                          # ... minus the kept entries of earlier lists
+        dst_pos = (nrp[:-1].astype(np.int64)[src_all] + (rank - first[src_all]))[keep]
         ncol[dst_pos] = col[keep]
         ndist[dst_pos] = dist[keep]
         for nid, lst in lists.items():
