@@ -83,6 +83,8 @@ def parse_args():
     ap.add_argument("--glove-n", type=int, default=1200000)
     ap.add_argument("--gist-n", type=int, default=0, help="gist rows in total (default: 250k on one GPU, 1M sharded over N > 1)")
     ap.add_argument("--recipe-n", type=int, default=100000, help="objects of the reference_recipe leg (0: skip)")
+    ap.add_argument("--profile-region", action="store_true",
+                    help="cudaProfilerStart/Stop around the timed steps (ncu --profile-from-start off lists exactly the step's launches)")
     return ap.parse_args()
 
 
@@ -210,6 +212,10 @@ def bind_capi(so_path):
     lib.ngt_destroy_error_object.argtypes = [P]
     lib.ngt_open_index.restype, lib.ngt_open_index.argtypes = P, [C.c_char_p, P]
     lib.ngt_close_index.argtypes = [P]
+    lib.ngt_create_empty_results.restype, lib.ngt_create_empty_results.argtypes = P, [P]
+    lib.ngt_destroy_results.argtypes = [P]
+    lib.ngt_search_index_as_float.restype = C.c_bool
+    lib.ngt_search_index_as_float.argtypes = [P, P, C.c_int32, C.c_size_t, C.c_float, C.c_float, P, P]
     lib.ngt_batch_search_index_as_float.restype = C.c_bool
     lib.ngt_batch_search_index_as_float.argtypes = [P, P, C.c_uint32, C.c_int32, C.c_size_t, C.c_float, C.c_float, C.c_int64, P, P, P, P]
     return lib
@@ -684,11 +690,15 @@ def run_ours(a):
     barrier()
     t_begin = clocks.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if a.profile_region:
+        torch.cuda.profiler.start()
     ev0.record()
     for s in range(a.steps):
         step_fn(batches[s % n_batches])
     ev1.record()
     barrier()
+    if a.profile_region:
+        torch.cuda.profiler.stop()
     t_end = clocks.mark()
     ms_total = ev0.elapsed_time(ev1)
     launches = ix.launch_count - launches0
@@ -767,7 +777,18 @@ def run_ours(a):
             t = torch.tensor([e2e_ms, e2e_ms1], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_ms, e2e_ms1 = float(t[0]), float(t[1])
+        # the single-query call of lib/NGT/Capi.h (a batch of one): latency, for callers that cannot batch
+        res1 = capi.ngt_create_empty_results(err)
+        for i in range(20):
+            capi.ngt_search_index_as_float(cix, hq[0].data_ptr() + (i % a.nq) * dim * 4, dim, a.k, eps, -1.0, res1, err)
+        t1 = time.perf_counter()
+        n1 = 200
+        for i in range(n1):
+            capi.ngt_search_index_as_float(cix, hq[0].data_ptr() + (i % a.nq) * dim * 4, dim, a.k, eps, -1.0, res1, err)
+        single_us = (time.perf_counter() - t1) * 1e6 / n1
+        capi.ngt_destroy_results(res1)
         e2e = {"value": round(units / (e2e_ms / 1e3), 1), "unit": "queries/s", "ms_per_step": round(e2e_ms, 4),
+               "single_query_call": {"entry_point": "ngt_search_index_as_float", "mean_latency_us": round(single_us, 1)},
                "h2d_bytes_per_step": a.nq * dim * 4, "d2h_bytes_per_step": a.nq * a.k * 8 + a.nq * 4,
                "entry_point": "ngt_batch_search_index_as_float (lib/NGT/Capi.h batch twin) on ngt_open_index(<NGT index files>)",
                "host_threads": n_threads, "single_thread": {"value": round(units / (e2e_ms1 / 1e3), 1), "ms_per_step": round(e2e_ms1, 4)},
