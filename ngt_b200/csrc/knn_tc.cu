@@ -290,7 +290,6 @@ struct TcArgs {
   uint32_t qtiles;
   uint32_t nsplit;
   uint64_t tiles_per_split;
-  int fold;                 // the last k-chunk carries the squared norms in its first six elements: one K = 16 step of it is enough
   uint32_t qgroups;         // query tiles per CTA: 2 (256 queries share every row tile) or 1 when two query operands do not fit
   int debug_skip;           // development: 1 = the epilogue only releases the accumulators (timing of the MMA side alone)
   uint32_t cap;             // entries of one (query, split) buffer: a multiple of 32, <= TC_CAND_MAX
@@ -464,11 +463,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_filter_kernel(const TcAr
           const uint32_t st = (uint32_t)(it % a.stages);
           tc_mbar_wait(&bar_full[st], (uint32_t)((it / a.stages) & 1));
           tc_fence_after();
-          // (the norm chunk of the L2 kinds is zero past its first K = 16 slice: one MMA instead of four)
-          const uint32_t steps = (a.fold && c + 1 == a.kchunks) ? 1u : (uint32_t)(TC_KCHUNK / 16);
           for (uint32_t qg = 0; qg < a.qgroups; qg++) {   // every row tile in shared memory feeds all the CTA's query tiles
-#pragma unroll 1
-            for (uint32_t s = 0; s < steps; s++) {
+#pragma unroll
+            for (uint32_t s = 0; s < TC_KCHUNK / 16; s++) {
               const uint64_t da = descA0 + (uint64_t)(((qg * a.kchunks + c) * TC_TILE_BYTES + s * 32) >> 4);
               const uint64_t db = descB0 + (uint64_t)((st * TC_TILE_BYTES + s * 32) >> 4);
               tc_mma_bf16(tmem_base + (acc * 2 + qg) * 128, da, db, idesc, (c | s) != 0 ? 1u : 0u);
@@ -795,7 +792,6 @@ int ngtgpu_scan_topk_tc(ngtgpu_index *ix, const ScanParams &p, cudaStream_t stre
   a.self_base = p.self_base - p.first_row_id;
   a.qtiles = qtiles;
   a.qgroups = qgroups;
-  a.fold = ix->tc_fold;
   const uint64_t total_tiles = (p.n_rows + TC_TILE - 1) / TC_TILE;
   uint64_t want = ((uint64_t)ix->sm_count + qtiles - 1) / qtiles;
   if (want > 8) want = 8;
