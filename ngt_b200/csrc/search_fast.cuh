@@ -32,6 +32,9 @@
 // its latency chain, not the bandwidth, sets the pace. 3 warps x 10 CTAs/SM measured the same as 4 x 8 on 512-byte rows.
 #define FAST_WARPS 4
 #define FAST_STAGE_PER_WARP 4096u
+#ifndef FAST_INT_LD
+#define FAST_INT_LD 4u    // lanes per row for integer rows of <= 128 bytes in a distance step (8 rows per step)
+#endif
 __host__ __device__ constexpr uint32_t fast_stage_per_warp(int ch, int w) { return (ch == 1 && w == 2) ? 2048u : 4096u; }
 
 // ---- visited hash: the bucket in one 256-bit load -------------------------------------------------------
@@ -88,12 +91,19 @@ template <int ACC, int CH, int W>
 __global__ void __launch_bounds__(W * 32, 32 / W) search_fast_kernel(const SearchArgs a) {
   constexpr uint32_t SPW = fast_stage_per_warp(CH, W);         // staging ring of one warp
   constexpr uint32_t SROW = 128u * CH;                         // staging stride of a row
-  constexpr uint32_t GBYTES = 4u * SROW;                       // one group = four rows
-  constexpr int NB = (int)(SPW / GBYTES);      // ring depth per warp: 2, 4 or 8
+  // lanes per row in a distance step: eight (four rows per step; the float summation order needs it), or FAST_INT_LD
+  // for integer rows of <= 128 bytes, whose sums are exact in any order: 32 / LD rows per step, so the per-step
+  // overhead (waits, syncs, issue of the next group, loop) is paid once per 8 or 16 rows instead of once per 4
+  constexpr uint32_t LD = (CH == 1 && (ACC == ACC_U8_L2 || ACC == ACC_U8_HAM)) ? FAST_INT_LD : 8u;
+  constexpr uint32_t RPS = 32u / LD;                           // rows per step = rows of one group
+  constexpr uint32_t CPL = 8u * CH / LD;                       // 16-byte chunks of a row per lane
+  constexpr uint32_t GBYTES = RPS * SROW;                      // one group
+  constexpr int NB = (int)(SPW / GBYTES);                      // ring depth per warp: 2, 4 or 8
+  static_assert(NB >= 2, "the staging ring must hold two groups");
   constexpr uint32_t RPI = 4u / CH;                            // rows per copy instruction
   constexpr uint32_t LPR = 8u * CH;                            // lanes per row in a copy instruction
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  __shared__ __align__(16) uint32_t s_wids[W][32 + 4];   // new ids per warp
+  __shared__ __align__(16) uint32_t s_wids[W][32 + 16];  // new ids per warp (+ padding up to a whole group)
   __shared__ uint32_t s_wcnt[W], s_wval[W];
   __shared__ uint64_t s_cand_keys[SEARCH_CMAX];
   __shared__ __align__(16) uint32_t s_edges[2][SEARCH_HEAD];   // edge lists of the round / of the expected next node
@@ -124,11 +134,15 @@ __global__ void __launch_bounds__(W * 32, 32 / W) search_fast_kernel(const Searc
   const uint32_t wstage_s = (uint32_t)__cvta_generic_to_shared(stage + (size_t)warp * SPW);
   const uint32_t cp_row = (uint32_t)lane / LPR;                   // row inside one copy instruction
   const uint32_t cp_chunk = (uint32_t)lane % LPR;
-  const uint32_t cp_dst = wstage_s + cp_row * SROW + cp_chunk * 16u;
+  // LD < 8: chunk c of row r of a group sits at position (c + LD * r) % 8 of the row's 128 bytes, so that the 16-byte
+  // reads of a quarter-warp (8 / LD rows x LD lanes) fall into eight distinct bank groups
+  const uint32_t cp_pos = LD == 8u ? cp_chunk : ((cp_chunk + LD * cp_row) & 7u);
+  const uint32_t cp_dst = wstage_s + cp_row * SROW + cp_pos * 16u;
   const uint32_t rb16 = a.row_bytes >> 4;                         // a row in 16-byte units (tables up to 64 GB)
   const uint32_t cp_size = cp_chunk < a.chunks ? 16u : 0u;        // chunks past the row's end are zero-filled
-  const uint32_t rr = (uint32_t)lane >> 3;                        // row inside a distance step
-  const uint32_t rd = wstage_s + rr * SROW + ((uint32_t)lane & 7u) * 16u;
+  const uint32_t rr = (uint32_t)lane / LD;                        // row inside a distance step
+  const uint32_t ll = (uint32_t)lane % LD;                        // lane inside the row
+  const uint32_t rd = wstage_s + rr * SROW + (LD == 8u ? ll : ((ll + LD * rr) & 7u)) * 16u;   // its first chunk
   uint64_t row_policy;
   asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(row_policy));
 #define FAST_ROWCP(dst, src, bytes) cp_async_s16z_hint(dst, src, bytes, row_policy)
@@ -150,10 +164,10 @@ __global__ void __launch_bounds__(W * 32, 32 / W) search_fast_kernel(const Searc
       for (uint32_t i = tid; i < (1u << a.hash_bits) / 4; i += (W * 32)) h4[i] = zero16();
     }
     const uint8_t *qrow = a.queries + (size_t)q * a.row_bytes;
-    uint4 q8[CH];   // lane (rr, j) holds query chunks j, j + 8, ...
+    uint4 q8[CPL];   // lane (rr, ll) holds query chunks ll, ll + LD, ...
 #pragma unroll
-    for (int m = 0; m < CH; m++) {
-      const uint32_t c = (lane & 7) + m * 8;
+    for (int m = 0; m < (int)CPL; m++) {
+      const uint32_t c = ll + m * LD;
       q8[m] = c < a.chunks ? ldg16(qrow + (size_t)c * 16) : zero16();
     }
     float qn = 0.f;
@@ -175,8 +189,14 @@ __global__ void __launch_bounds__(W * 32, 32 / W) search_fast_kernel(const Searc
       // its launch): every warp scans a quarter of the table, four rows per step read straight from L1/L2, and keeps
       // its k smallest keys sorted one per lane; warp 0 merges the lists into the first round's edge list
       uint64_t wres = KEY_NONE, wthr = KEY_NONE;
+      uint4 qp[CH];   // eight lanes per pivot row here whatever LD is: lane j of a row holds query chunks j, j + 8, ...
+#pragma unroll
+      for (int m = 0; m < CH; m++) {
+        const uint32_t c = ((uint32_t)lane & 7u) + m * 8;
+        qp[m] = c < a.chunks ? ldg16(qrow + (size_t)c * 16) : zero16();
+      }
       for (uint32_t p0 = 4u * (uint32_t)warp; p0 < a.n_pivots; p0 += 4u * W) {
-        const uint32_t row = p0 + rr;
+        const uint32_t row = p0 + ((uint32_t)lane >> 3);
         const bool valid = row < a.n_pivots;
         const uint8_t *rp = a.pivots + (size_t)(valid ? row : 0u) * a.row_bytes;
         Sums p[CH];
@@ -184,7 +204,7 @@ __global__ void __launch_bounds__(W * 32, 32 / W) search_fast_kernel(const Searc
         for (int m = 0; m < CH; m++) {
           const uint32_t c = ((uint32_t)lane & 7u) + m * 8;
           p[m] = zero_sums();
-          acc_chunk_packed<ACC>(p[m], q8[m], c < a.chunks ? ldg16(rp + (size_t)c * 16) : zero16());
+          acc_chunk_packed<ACC>(p[m], qp[m], c < a.chunks ? ldg16(rp + (size_t)c * 16) : zero16());
           lane_total<ACC>(p[m]);
         }
         Sums tot = p[0];
@@ -452,9 +472,9 @@ __global__ void __launch_bounds__(W * 32, 32 / W) search_fast_kernel(const Searc
         const uint32_t m = __ballot_sync(0xffffffffu, isnew);
         const uint32_t mv = __ballot_sync(0xffffffffu, valid);
         if (isnew) s_wids[warp][__popc(m & lanemask_lt())] = nid;
-        // the last group of four is filled up with row 0 (the all-zero dummy object, an L2 hit): its copies need no
+        // the last group (four rows, or RPS) is filled up with row 0 (the all-zero dummy object, an L2 hit): its copies need no
         // predicates and its distances are dropped
-        if (lane < 3) s_wids[warp][__popc(m) + lane] = 0u;
+        if ((uint32_t)lane < RPS - 1u) s_wids[warp][__popc(m) + lane] = 0u;
         if (lane == 0) {
           s_wcnt[warp] = (uint32_t)__popc(m);
           s_wval[warp] = (uint32_t)__popc(mv);
@@ -468,9 +488,9 @@ __global__ void __launch_bounds__(W * 32, 32 / W) search_fast_kernel(const Searc
       // ================= rows: copy and evaluate, group g of the round on warp g % 4 =================
       {
         const float er_pub = s_er;
-        const uint32_t ngw = (cn + 3u) >> 2;                                 // groups of four rows of this warp
-#define FAST_GROUP_C0(t) (4u * (t))
-        // issue group t of this warp (candidates 4 * (4 t + warp) ..) into ring slot t % NB
+        const uint32_t ngw = (cn + RPS - 1u) / RPS;                           // groups of RPS rows of this warp
+#define FAST_GROUP_C0(t) (RPS * (t))
+        // issue group t of this warp into ring slot t % NB
 #define FAST_ISSUE(t)                                                                                   \
   {                                                                                                     \
     const uint32_t _t = (t);                                                                            \
@@ -484,9 +504,10 @@ __global__ void __launch_bounds__(W * 32, 32 / W) search_fast_kernel(const Searc
         FAST_ROWCP(_dst + 2 * SROW, addr16(_ids.z * rb16 + cp_chunk, a.objects), cp_size);                \
         FAST_ROWCP(_dst + 3 * SROW, addr16(_ids.w * rb16 + cp_chunk, a.objects), cp_size);                \
       } else {                                                                                          \
-        uint32_t _id[CH];                                                                               \
-        _Pragma("unroll") for (int _i = 0; _i < CH; _i++) _id[_i] = cand_ids[_c0 + _i * RPI + cp_row];  \
-        _Pragma("unroll") for (int _i = 0; _i < CH; _i++)                                               \
+        constexpr int _NI = (int)(RPS / RPI);   /* copy instructions of one group: RPI rows each */       \
+        uint32_t _id[_NI];                                                                              \
+        _Pragma("unroll") for (int _i = 0; _i < _NI; _i++) _id[_i] = cand_ids[_c0 + _i * RPI + cp_row]; \
+        _Pragma("unroll") for (int _i = 0; _i < _NI; _i++)                                              \
           FAST_ROWCP(_dst + _i * RPI * SROW, addr16(_id[_i] * rb16 + cp_chunk, a.objects), cp_size);      \
       }                                                                                                 \
     }                                                                                                   \
@@ -495,50 +516,64 @@ __global__ void __launch_bounds__(W * 32, 32 / W) search_fast_kernel(const Searc
 #pragma unroll
         for (int b = 0; b < NB; b++) FAST_ISSUE((uint32_t)b)
         if (pend_id) hash_insert(hash, bucket_bits, pend_id, bp);   // under the row copies in flight
-        float tot0 = 0.f, tot1 = 0.f;   // this lane's row of the current block of eight steps
+        float tot0 = 0.f, tot1 = 0.f;   // this lane's row of the current block of LD steps
         uint32_t totu = 0;
         for (uint32_t t = 0; t < ngw; t++) {
           cp_async_wait_group<NB - 1>();
           __syncwarp();
-          const uint32_t ra = rd + (t % NB) * GBYTES;
-          Sums p[CH];
+          const uint32_t slot = (t % NB) * GBYTES;
+          if (LD == 8u) {
+            const uint32_t ra = rd + slot;
+            Sums p[CH];
 #pragma unroll
-          for (int m = 0; m < CH; m++) {
-            p[m] = zero_sums();
-            acc_chunk_packed<ACC>(p[m], q8[m], lds16(ra + m * 128));
-            lane_total<ACC>(p[m]);
-          }
-          // chunks j, j + 8, j + 16, j + 24 of a row sit on lanes j, j + 8, ... of group_fold<ACC, 32>: the xor-16 and
-          // xor-8 levels of its butterfly are these local adds, the remaining three levels are shuffles
-          Sums tot = p[0];
-          if (ACC == ACC_U8_L2 || ACC == ACC_U8_HAM) {
-            if (CH == 2) tot.u = p[0].u + p[1].u;
-            if (CH == 4) tot.u = (p[0].u + p[2].u) + (p[1].u + p[3].u);
-            tot.u += __shfl_xor_sync(0xffffffffu, tot.u, 4);
-            tot.u += __shfl_xor_sync(0xffffffffu, tot.u, 2);
-            tot.u += __shfl_xor_sync(0xffffffffu, tot.u, 1);
-            if ((uint32_t)(lane & 7) == (t & 7u)) totu = tot.u;
-          } else {
-            if (CH == 2) tot.f0 = p[0].f0 + p[1].f0;
-            if (CH == 4) tot.f0 = (p[0].f0 + p[2].f0) + (p[1].f0 + p[3].f0);
-            tot.f0 += __shfl_xor_sync(0xffffffffu, tot.f0, 4);
-            tot.f0 += __shfl_xor_sync(0xffffffffu, tot.f0, 2);
-            tot.f0 += __shfl_xor_sync(0xffffffffu, tot.f0, 1);
-            if ((uint32_t)(lane & 7) == (t & 7u)) tot0 = tot.f0;
-            if (ACC == ACC_F_COS) {
-              if (CH == 2) tot.f1 = p[0].f1 + p[1].f1;
-              if (CH == 4) tot.f1 = (p[0].f1 + p[2].f1) + (p[1].f1 + p[3].f1);
-              tot.f1 += __shfl_xor_sync(0xffffffffu, tot.f1, 4);
-              tot.f1 += __shfl_xor_sync(0xffffffffu, tot.f1, 2);
-              tot.f1 += __shfl_xor_sync(0xffffffffu, tot.f1, 1);
-              if ((uint32_t)(lane & 7) == (t & 7u)) tot1 = tot.f1;
+            for (int m = 0; m < CH; m++) {
+              p[m] = zero_sums();
+              acc_chunk_packed<ACC>(p[m], q8[m], lds16(ra + m * 128));
+              lane_total<ACC>(p[m]);
             }
+            // chunks j, j + 8, j + 16, j + 24 of a row sit on lanes j, j + 8, ... of group_fold<ACC, 32>: the xor-16 and
+            // xor-8 levels of its butterfly are these local adds, the remaining three levels are shuffles
+            Sums tot = p[0];
+            if (ACC == ACC_U8_L2 || ACC == ACC_U8_HAM) {
+              if (CH == 2) tot.u = p[0].u + p[1].u;
+              if (CH == 4) tot.u = (p[0].u + p[2].u) + (p[1].u + p[3].u);
+              tot.u += __shfl_xor_sync(0xffffffffu, tot.u, 4);
+              tot.u += __shfl_xor_sync(0xffffffffu, tot.u, 2);
+              tot.u += __shfl_xor_sync(0xffffffffu, tot.u, 1);
+              if ((uint32_t)(lane & 7) == (t & 7u)) totu = tot.u;
+            } else {
+              if (CH == 2) tot.f0 = p[0].f0 + p[1].f0;
+              if (CH == 4) tot.f0 = (p[0].f0 + p[2].f0) + (p[1].f0 + p[3].f0);
+              tot.f0 += __shfl_xor_sync(0xffffffffu, tot.f0, 4);
+              tot.f0 += __shfl_xor_sync(0xffffffffu, tot.f0, 2);
+              tot.f0 += __shfl_xor_sync(0xffffffffu, tot.f0, 1);
+              if ((uint32_t)(lane & 7) == (t & 7u)) tot0 = tot.f0;
+              if (ACC == ACC_F_COS) {
+                if (CH == 2) tot.f1 = p[0].f1 + p[1].f1;
+                if (CH == 4) tot.f1 = (p[0].f1 + p[2].f1) + (p[1].f1 + p[3].f1);
+                tot.f1 += __shfl_xor_sync(0xffffffffu, tot.f1, 4);
+                tot.f1 += __shfl_xor_sync(0xffffffffu, tot.f1, 2);
+                tot.f1 += __shfl_xor_sync(0xffffffffu, tot.f1, 1);
+                if ((uint32_t)(lane & 7) == (t & 7u)) tot1 = tot.f1;
+              }
+            }
+          } else {
+            // integer rows of <= 128 bytes, LD lanes per row: lane (rr, ll) takes chunks ll, ll + LD, ... of row rr from
+            // their swizzled positions; integer sums are exact in any order
+            const uint32_t base = wstage_s + slot + rr * SROW;
+            const uint32_t p0 = (ll + LD * rr) & 7u;
+            Sums acc = zero_sums();
+#pragma unroll
+            for (int m = 0; m < (int)CPL; m++) acc_chunk<ACC>(acc, q8[m], lds16(base + ((p0 + LD * m) & 7u) * 16u));
+#pragma unroll
+            for (uint32_t o = LD / 2; o > 0; o >>= 1) acc.u += __shfl_xor_sync(0xffffffffu, acc.u, o);
+            if (ll == t % LD) totu = acc.u;
           }
           __syncwarp();
           FAST_ISSUE(t + NB)
-          if ((t & 7u) == 7u || t + 1 == ngw) {
-            // the scalar tail for up to 32 rows at once: lane (rr, s) owns row rr of step (t & ~7) + s
-            const uint32_t ts = (t & ~7u) + ((uint32_t)lane & 7u);
+          if (t % LD == LD - 1u || t + 1 == ngw) {
+            // the scalar tail for up to 32 rows at once: lane (rr, s) owns row rr of step (t - t % LD) + s
+            const uint32_t ts = (t - t % LD) + ll;
             const uint32_t j = FAST_GROUP_C0(ts) + rr;
             const bool owner = ts <= t && j < cn;
             float d = 0.f;
