@@ -41,7 +41,6 @@
 #define TC_KCHUNK 64           // bf16 elements per swizzle row (128 bytes)
 #define TC_TILE_BYTES (TC_TILE * TC_KCHUNK * 2)   // 16 KB: one operand tile of one k-chunk
 #define TC_STAGES 10
-#define TC_MAX_KCHUNKS 6       // resident query operand <= 96 KB
 #define TC_MAX_K 128
 #define TC_EPI_WARPS 8          // two groups of four: group g takes the tiles whose accumulator is g
 #define TC_THREADS ((TC_EPI_WARPS + 2) * 32)
@@ -291,6 +290,7 @@ struct TcArgs {
   uint32_t nsplit;
   uint64_t tiles_per_split;
   uint32_t qgroups;         // query tiles per CTA: 2 (256 queries share every row tile) or 1 when two query operands do not fit
+  int stream;               // 1: the query operand does not fit shared memory and streams through the ring with the rows (long K axis)
   int debug_skip;           // development: 1 = the epilogue only releases the accumulators (timing of the MMA side alone)
   uint32_t cap;             // entries of one (query, split) buffer: a multiple of 32, <= TC_CAND_MAX
   uint2 *cand;              // [nq][nsplit][cap] (score bits, row index 0-based)
@@ -396,15 +396,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_filter_kernel(const TcAr
   __shared__ uint32_t s_tmem;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t qtile = blockIdx.x % a.qtiles, split = blockIdx.x / a.qtiles;   // qtile: a.qgroups query tiles of 128
+  // qtile: a.qgroups query tiles of 128. Resident query operand: the CTAs of a wave are different query tiles of one split
+  // (they read the same row tiles at about the same time). Streamed query operand: a wave is a few query tiles times all
+  // the splits, so that the query tiles re-read for every row tile (the wave's working set) stay in L2.
+  const uint32_t qtile = a.stream ? blockIdx.x / a.nsplit : blockIdx.x % a.qtiles;
+  const uint32_t split = a.stream ? blockIdx.x % a.nsplit : blockIdx.x / a.qtiles;
   const uint64_t total_tiles = (a.n_rows + TC_TILE - 1) / TC_TILE;
   const uint64_t t_begin = (uint64_t)split * a.tiles_per_split;
   uint64_t t_end = t_begin + a.tiles_per_split;
   if (t_end > total_tiles) t_end = total_tiles;
   const uint64_t ntiles = t_end > t_begin ? t_end - t_begin : 0;
 
-  uint8_t *sA = smem;                                                        // qgroups x kchunks x 16 KB (resident)
-  uint8_t *sB = smem + (size_t)a.qgroups * a.kchunks * TC_TILE_BYTES;       // a.stages x 16 KB ring
+  // resident: [qgroups x kchunks x 16 KB query operand][a.stages x 16 KB ring of row tiles]
+  // streamed: a.stages x (qgroups + 1) x 16 KB, one k-chunk of every query tile and of the row tile per stage
+  uint8_t *sA = smem;
+  uint8_t *sB = a.stream ? smem : smem + (size_t)a.qgroups * a.kchunks * TC_TILE_BYTES;
+  const uint32_t stage_bytes = a.stream ? (a.qgroups + 1) * TC_TILE_BYTES : TC_TILE_BYTES;
+  const uint32_t b_off = a.stream ? a.qgroups * TC_TILE_BYTES : 0u;          // the row tile inside a stage
 
   if (tid == 0) {
     for (int i = 0; i < TC_STAGES; i++) {
@@ -431,18 +439,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_filter_kernel(const TcAr
   if (warp == TC_EPI_WARPS) {
     // ===================== producer =====================
     if (ntiles && tc_elect_one()) {
-      tc_mbar_expect_tx(&bar_a, a.qgroups * a.kchunks * TC_TILE_BYTES);
-      for (uint32_t c = 0; c < a.qgroups * a.kchunks; c++)   // the query tiles of this CTA are consecutive in a_tiles
-        tc_bulk_load(sA + (size_t)c * TC_TILE_BYTES, a.a_tiles + ((size_t)qtile * a.qgroups * a.kchunks + c) * TC_TILE_BYTES, TC_TILE_BYTES,
-                     &bar_a);
+      const uint8_t *a_src = a.a_tiles + (size_t)qtile * a.qgroups * a.kchunks * TC_TILE_BYTES;   // this CTA's query tiles are consecutive
+      if (!a.stream) {
+        tc_mbar_expect_tx(&bar_a, a.qgroups * a.kchunks * TC_TILE_BYTES);
+        for (uint32_t c = 0; c < a.qgroups * a.kchunks; c++)
+          tc_bulk_load(sA + (size_t)c * TC_TILE_BYTES, a_src + (size_t)c * TC_TILE_BYTES, TC_TILE_BYTES, &bar_a);
+      }
       uint64_t it = 0;
       for (uint64_t t = 0; t < ntiles; t++) {
         for (uint32_t c = 0; c < a.kchunks; c++, it++) {
           const uint32_t st = (uint32_t)(it % a.stages);
           tc_mbar_wait(&bar_empty[st], (uint32_t)((it / a.stages) & 1) ^ 1u);
-          tc_mbar_expect_tx(&bar_full[st], TC_TILE_BYTES);
-          tc_bulk_load(sB + (size_t)st * TC_TILE_BYTES, a.b_tiles + ((size_t)(t_begin + t) * a.kchunks + c) * TC_TILE_BYTES,
-                       TC_TILE_BYTES, &bar_full[st]);
+          tc_mbar_expect_tx(&bar_full[st], stage_bytes);
+          uint8_t *dst = sB + (size_t)st * stage_bytes;
+          if (a.stream)
+            for (uint32_t qg = 0; qg < a.qgroups; qg++)
+              tc_bulk_load(dst + (size_t)qg * TC_TILE_BYTES, a_src + ((size_t)qg * a.kchunks + c) * TC_TILE_BYTES, TC_TILE_BYTES,
+                           &bar_full[st]);
+          tc_bulk_load(dst + b_off, a.b_tiles + ((size_t)(t_begin + t) * a.kchunks + c) * TC_TILE_BYTES, TC_TILE_BYTES, &bar_full[st]);
         }
       }
     }
@@ -452,8 +466,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_filter_kernel(const TcAr
       // kind::f16, A = B = BF16, D = F32, K-major both, N = 128, M = 128 (cute::UMMA::InstrDescriptor)
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
       const uint64_t descA0 = tc_smem_desc(smem_u32(sA)), descB0 = tc_smem_desc(smem_u32(sB));
-      tc_mbar_wait(&bar_a, 0);
-      tc_fence_after();
+      if (!a.stream) {
+        tc_mbar_wait(&bar_a, 0);
+        tc_fence_after();
+      }
       uint64_t it = 0;
       for (uint64_t t = 0; t < ntiles; t++) {
         const uint32_t acc = (uint32_t)(t & 1);
@@ -466,8 +482,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_filter_kernel(const TcAr
           for (uint32_t qg = 0; qg < a.qgroups; qg++) {   // every row tile in shared memory feeds all the CTA's query tiles
 #pragma unroll
             for (uint32_t s = 0; s < TC_KCHUNK / 16; s++) {
-              const uint64_t da = descA0 + (uint64_t)(((qg * a.kchunks + c) * TC_TILE_BYTES + s * 32) >> 4);
-              const uint64_t db = descB0 + (uint64_t)((st * TC_TILE_BYTES + s * 32) >> 4);
+              const uint32_t a_at = a.stream ? st * stage_bytes + qg * TC_TILE_BYTES : (qg * a.kchunks + c) * TC_TILE_BYTES;
+              const uint64_t da = descA0 + (uint64_t)((a_at + s * 32) >> 4);
+              const uint64_t db = descB0 + (uint64_t)((st * stage_bytes + b_off + s * 32) >> 4);
               tc_mma_bf16(tmem_base + (acc * 2 + qg) * 128, da, db, idesc, (c | s) != 0 ? 1u : 0u);
             }
           }
@@ -722,7 +739,7 @@ int ngtgpu_scan_topk_tc(ngtgpu_index *ix, const ScanParams &p, cudaStream_t stre
   if (p.d_id_map != nullptr) return NGTGPU_OK;                          // pivot tables stay on the CUDA-core path
   if (p.n_rows < 32768 || p.nq < 1024) return NGTGPU_OK;                // too little work to amortise packing
   if (p.d_rows != ix->d_objects + ix->row_bytes || p.n_rows != ix->n) return NGTGPU_OK;   // only the whole repository is cached
-  if (!ix->tc_enabled || tc_kdim(ix) > TC_MAX_KCHUNKS * TC_KCHUNK) return NGTGPU_OK;
+  if (!ix->tc_enabled) return NGTGPU_OK;
 
   int *d_flag = nullptr;
   NGTGPU_TRY(ngtgpu_scratch(ix, SCR_TC_MISC, 256, (void **)&d_flag));
@@ -735,7 +752,6 @@ int ngtgpu_scan_topk_tc(ngtgpu_index *ix, const ScanParams &p, cudaStream_t stre
     uint32_t nseg = exact ? 1 : 3;
     const int fold = (ix->acc_kind == ACC_F_L2 || integer_kind) ? 1 : 0;   // L2 (and Hamming = L2 of bits): norms ride in the GEMM
     const uint32_t kchunks = tc_kchunks(ix, nseg, fold);
-    if (kchunks > TC_MAX_KCHUNKS + 1) return NGTGPU_OK;   // resident query operand would not fit
     const uint64_t n_tiles = (p.n_rows + TC_TILE - 1) / TC_TILE;
     if (ix->d_tc_tiles) cudaFree(ix->d_tc_tiles);
     if (ix->d_tc_norms) cudaFree(ix->d_tc_norms);
@@ -764,9 +780,12 @@ int ngtgpu_scan_topk_tc(ngtgpu_index *ix, const ScanParams &p, cudaStream_t stre
     if (!qexact) return NGTGPU_OK;   // rows are bf16-exact but the queries are not: leave it to the CUDA-core scan
   }
   const uint32_t kchunks = ix->tc_kchunks;
-  // two query tiles per CTA (every row tile read from L2 feeds 256 queries: the kernel is bound by that stream) when two
-  // resident query operands and a ring of two stages fit shared memory, else one
-  const uint32_t qgroups = (2 * (size_t)kchunks + 2) * TC_TILE_BYTES + 1024 <= 225 * 1024 ? 2u : 1u;
+  // two query tiles per CTA: every row tile read from L2 feeds 256 queries (the kernel is bound by that stream). The query
+  // operand is resident when both tiles and a ring of two stages fit shared memory (K axis of <= 6 chunks: 128-d split
+  // floats, 384-d bf16-exact data); longer K axes (960-d, > 128-d split floats) stream it through the ring with the rows.
+  const uint32_t qgroups = 2u;
+  int stream_a = (2 * (size_t)kchunks + 2) * TC_TILE_BYTES + 1024 <= 225 * 1024 ? 0 : 1;
+  if (const char *env = getenv("NGTGPU_TC_STREAM")) stream_a = atoi(env) != 0 || stream_a;   // development knob: force streaming
   const uint32_t qtiles128 = ((p.nq + TC_TILE * qgroups - 1) / (TC_TILE * qgroups)) * qgroups;   // 128-query tiles, padded to whole CTAs
   const uint32_t qtiles = qtiles128 / qgroups;                                                   // CTAs per split
   uint8_t *a_tiles = nullptr;
@@ -786,15 +805,19 @@ int ngtgpu_scan_topk_tc(ngtgpu_index *ix, const ScanParams &p, cudaStream_t stre
   a.kchunks = kchunks;
   a.k = p.k;
   a.mode = (ix->acc_kind == ACC_F_L2 || integer_kind) ? 0 : ix->acc_kind == ACC_F_DOT ? 1 : 2;
-  a.rel_margin = nseg == 1 ? 4.0e-6f : 1.0e-4f;
+  // split floats: the dropped lo x lo products (2^-16) and the bf16 rounding of the lo parts, plus fp32 accumulation over
+  // the K axis, which grows with its length
+  a.rel_margin = nseg == 1 ? 4.0e-6f : std::max(1.0e-4f, 6.0e-8f * (float)(kchunks * TC_KCHUNK));
   a.max_row_norm = ix->tc_max_norm;
   a.exclude_self = p.exclude_self;
   a.self_base = p.self_base - p.first_row_id;
   a.qtiles = qtiles;
   a.qgroups = qgroups;
+  a.stream = stream_a;
   const uint64_t total_tiles = (p.n_rows + TC_TILE - 1) / TC_TILE;
   uint64_t want = ((uint64_t)ix->sm_count + qtiles - 1) / qtiles;
   if (want > 8) want = 8;
+  if (stream_a) want = 8;   // a wave = sm_count / 8 query-tile pairs x 8 splits: the pairs' operands stay in L2 between row tiles
   if (want > total_tiles) want = total_tiles;
   if (want < 1) want = 1;
   a.tiles_per_split = (total_tiles + want - 1) / want;
@@ -815,13 +838,14 @@ int ngtgpu_scan_topk_tc(ngtgpu_index *ix, const ScanParams &p, cudaStream_t stre
   CUDA_TRY(cudaMemsetAsync(d_over, 0, 4, stream));
 
   // ring depth: as many 16 KB stages as fit beside the resident query operand (2..TC_STAGES)
-  const size_t fixed_smem = (size_t)qgroups * kchunks * TC_TILE_BYTES + 1024;
+  const size_t fixed_smem = (stream_a ? 0 : (size_t)qgroups * kchunks * TC_TILE_BYTES) + 1024;
+  const size_t stage_bytes = stream_a ? (size_t)(qgroups + 1) * TC_TILE_BYTES : TC_TILE_BYTES;
   uint32_t stages = TC_STAGES;
   if (const char *env = getenv("NGTGPU_TC_STAGES")) stages = std::max(2, std::min(TC_STAGES, atoi(env)));   // development knob
-  while (stages > 2 && fixed_smem + (size_t)stages * TC_TILE_BYTES > 225 * 1024) stages--;
-  if (fixed_smem + (size_t)stages * TC_TILE_BYTES > 225 * 1024) return NGTGPU_OK;
+  while (stages > 2 && fixed_smem + (size_t)stages * stage_bytes > 225 * 1024) stages--;
+  if (fixed_smem + (size_t)stages * stage_bytes > 225 * 1024) return NGTGPU_OK;
   a.stages = stages;
-  const size_t smem = fixed_smem + (size_t)stages * TC_TILE_BYTES;
+  const size_t smem = fixed_smem + (size_t)stages * stage_bytes;
   if (a.mode == 0) {
     CUDA_TRY(cudaFuncSetAttribute(knn_tc_filter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     knn_tc_filter_kernel<0><<<qtiles * a.nsplit, TC_THREADS, smem, stream>>>(a);

@@ -480,14 +480,21 @@ def test_pack_and_merge_kernels_match_host(eng):
 
 
 @pytest.mark.parametrize("case", ["sift_l2_exact_bf16", "glove_l2_split", "glove_ncos_split", "glove_cos_split", "sift_u8_l2",
-                                  "sift_hamming"])
-def test_tensor_core_knn_matches_cuda_core_scan(eng, case):
+                                  "sift_hamming", "gist_l2_split_streamed", "gist_cos_split_streamed", "sift_l2_forced_stream"])
+def test_tensor_core_knn_matches_cuda_core_scan(eng, case, monkeypatch):
     """knn_tc.cu (tcgen05 filter + exact re-evaluation) returns exactly what the CUDA-core scan returns: ids,
     distance bits and counts, for batches, kNN-graph construction (self excluded) and with removed slots."""
     from ngt_b200 import build, synth
     n, nq = 40000, 1500
     ot = po.FLOAT
-    if case == "sift_l2_exact_bf16":
+    if case == "sift_l2_forced_stream":   # the streamed query operand on a K axis that would fit: same answers
+        monkeypatch.setenv("NGTGPU_TC_STREAM", "1")
+        base, qs, dt = synth.make("sift", n, 1), synth.make("sift", nq, 2), po.L2
+    elif case.startswith("gist"):         # 960-d split floats: 46 k-chunks, query operand streamed through the ring
+        n = 33000
+        base, qs = synth.make("gist", n, 1), synth.make("gist", nq, 2)
+        dt = po.L2 if case == "gist_l2_split_streamed" else po.COSINE
+    elif case == "sift_l2_exact_bf16":
         base, qs, dt = synth.make("sift", n, 1), synth.make("sift", nq, 2), po.L2
     elif case == "sift_u8_l2":      # uint8 values are bf16 numbers: one exact segment, integer re-evaluation (dp4a)
         base, qs, dt, ot = synth.make("sift", n, 1).astype(np.uint8), synth.make("sift", nq, 2).astype(np.uint8), po.L2, po.UINT8
