@@ -468,8 +468,8 @@ extern "C" int ngtgpu_index_set_search_workspace(ngtgpu_index *ix, uint32_t hash
 
 extern "C" int ngtgpu_index_set_fast_shape(ngtgpu_index *ix, int warps_per_query, int ctas_per_sm) {
   if (!ix) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "null index handle");
-  if (warps_per_query != 0 && warps_per_query != 2 && warps_per_query != 4)
-    NGTGPU_FAIL(NGTGPU_ERR_INVALID, "warps per query must be 0 (by row width), 2 or 4");
+  if (warps_per_query != 0 && warps_per_query != 1 && warps_per_query != 2 && warps_per_query != 4)
+    NGTGPU_FAIL(NGTGPU_ERR_INVALID, "warps per query must be 0 (by row width), 1, 2 or 4");
   if (ctas_per_sm < 0 || ctas_per_sm > 32) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "CTAs per SM must be in [0, 32]");
   ix->fast_warps = warps_per_query;
   ix->fast_ctas_per_sm = ctas_per_sm;

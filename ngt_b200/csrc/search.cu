@@ -206,8 +206,10 @@ int ngtgpu_traverse(ngtgpu_index *ix, const uint8_t *d_queries, uint32_t nq, con
     // two warps per query whenever a round fits 64 threads (measured: uint8 128-byte rows 4.09 -> 3.35 ms per 10k batch,
     // 12.5M shard 7.66 -> 6.73 ms, glove-shape 448-byte rows 4.03 -> 3.74 ms); fast_warps = 4 keeps four
     const bool two_fit = cap <= 64 && n_seeds <= 64;
-    const int fast_w = two_fit && ix->fast_warps != 4 ? 2 : FAST_WARPS;
-    if (fast) smem = (size_t)fast_w * fast_stage_per_warp(fast_ch, fast_w) + (size_t)a.queue_cap * 8;
+    // one warp per query (32 CTAs per SM, the back of the unchecked set in a global slab) in the first tier, when asked for
+    const bool one_fit = two_fit && fast_ch == 1 && t == 0 && ix->fast_warps == 1;
+    const int fast_w = one_fit ? 1 : two_fit && ix->fast_warps != 4 ? 2 : FAST_WARPS;
+    if (fast) smem = (size_t)fast_w * fast_stage_per_warp(fast_ch, fast_w) + (fast_w == 1 ? 0 : (size_t)a.queue_cap * 8);
     if (smem > 200 * 1024)
       NGTGPU_FAIL(NGTGPU_ERR_INVALID, "search: working set does not fit shared memory; lower queue_cap/size");
     l.smem = smem;
@@ -224,8 +226,11 @@ int ngtgpu_traverse(ngtgpu_index *ix, const uint8_t *d_queries, uint32_t nq, con
     l.grid = (unsigned)grid;
     // visited-hash slabs of this tier: one per CTA, in global memory (they live in L2)
     uint32_t *slabs = nullptr;
-    NGTGPU_TRY(ngtgpu_scratch(ix, t == 0 ? SCR_HASH0 : SCR_HASH1, (size_t)grid * ((size_t)4 << a.hash_bits), (void **)&slabs));
+    const size_t slab_bytes = (size_t)grid * ((size_t)4 << a.hash_bits);
+    const size_t queue_bytes = fast && fast_w == 1 ? (size_t)grid * a.queue_cap * 8 : 0;
+    NGTGPU_TRY(ngtgpu_scratch(ix, t == 0 ? SCR_HASH0 : SCR_HASH1, slab_bytes + queue_bytes, (void **)&slabs));
     a.hash_slabs = slabs;
+    a.queue_slabs = queue_bytes ? reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(slabs) + slab_bytes) : nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (ix->timing && t == 0) {
       CUDA_TRY(cudaEventCreate(&ev0));

@@ -89,6 +89,7 @@ struct SearchArgs {
   uint32_t *overflow_count;
   uint32_t *failed_count;            // WS == 1: queries that outgrew even the HBM tier
   uint32_t *hash_slabs;              // WS == 0: gridDim.x x 2^hash_bits words, L2-resident
+  uint64_t *queue_slabs;             // lean kernel, one warp per query: gridDim.x x queue_cap keys (the back of the unchecked set)
   uint32_t *big_bitmaps;             // WS == 1: gridDim.x x bitmap_words
   uint64_t *big_queues;              // WS == 1: gridDim.x x queue_cap
   uint64_t bitmap_words;

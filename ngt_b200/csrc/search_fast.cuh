@@ -35,12 +35,40 @@
 #ifndef FAST_INT_LD
 #define FAST_INT_LD 4u    // lanes per row for integer rows of <= 128 bytes in a distance step (8 rows per step)
 #endif
-__host__ __device__ constexpr uint32_t fast_stage_per_warp(int ch, int w) { return (ch == 1 && w == 2) ? 2048u : 4096u; }
+__host__ __device__ constexpr uint32_t fast_stage_per_warp(int ch, int w) { return (ch == 1 && w <= 2) ? 2048u : 4096u; }
 
 // ---- visited hash: the bucket in one 256-bit load -------------------------------------------------------
 // Slots of a bucket are taken in increasing order (hash_insert tries slot i only after slot i - 1 was seen occupied),
 // so the occupied slots are a prefix: the id is present iff some word equals it (a min over the xors), the bucket is
 // full iff its last word is taken, and the first free slot is found by a three-step binary search.
+__device__ __forceinline__ void hash_load256(const uint32_t *hash, uint32_t b, uint32_t (&v)[8]) {
+  asm volatile("ld.global.cg.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "l"(hash + (size_t)b * 8));
+}
+// `v` holds the home bucket of `nid` already (hash_load256 issued earlier, so that several probes of one thread overlap)
+__device__ __forceinline__ bool hash_lookup256_loaded(const uint32_t *hash, uint32_t bucket_bits, uint32_t nid, uint32_t b, uint32_t (&v)[8],
+                                                      BucketProbe &bp) {
+  const uint32_t bmask = (1u << bucket_bits) - 1u;
+  for (;;) {
+    const uint32_t x = min(min(min(v[0] ^ nid, v[1] ^ nid), min(v[2] ^ nid, v[3] ^ nid)),
+                           min(min(v[4] ^ nid, v[5] ^ nid), min(v[6] ^ nid, v[7] ^ nid)));
+    if (x == 0u) return true;   // visited
+    if (v[7] == 0u) {
+      uint32_t s0 = v[3] != 0u ? 4u : 0u;
+      const uint32_t m1 = s0 ? v[5] : v[1];
+      s0 += m1 != 0u ? 2u : 0u;
+      const uint32_t lo = (s0 & 2u) ? v[2] : v[0], hi = (s0 & 2u) ? v[6] : v[4];
+      const uint32_t m0 = (s0 & 4u) ? hi : lo;
+      s0 += m0 != 0u ? 1u : 0u;
+      bp.bucket = b;
+      bp.slot = s0;
+      return false;
+    }
+    b = (b + 1) & bmask;
+    hash_load256(hash, b, v);
+  }
+}
 __device__ __forceinline__ bool hash_lookup256(const uint32_t *hash, uint32_t bucket_bits, uint32_t nid, BucketProbe &bp) {
   const uint32_t bmask = (1u << bucket_bits) - 1u;
   uint32_t b = (nid * 2654435761u) >> (32 - bucket_bits);
@@ -87,8 +115,21 @@ __device__ __forceinline__ void cp_async_wait_group() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// W == 1 (opt-in, ngtgpu_index_set_fast_shape): the whole round runs in one warp (32 CTAs per SM, nobody waiting at a
+// barrier behind the control chain): a round of up to 64 edges is filtered in two passes whose bucket reads are issued
+// together, CTA barriers become warp barriers, and the unsorted back of the unchecked set lives in a per-CTA slab of
+// global memory next to the visited hash so that 32 CTAs fit the SM's shared memory. Measured slower than W == 2 on
+// 128-byte rows (3.6 vs 3.2 ms per 10k batch, 3.0 vs 2.9 ms per 10k at batch 40k): twice the slabs fall out of L2.
 template <int ACC, int CH, int W>
 __global__ void __launch_bounds__(W * 32, 32 / W) search_fast_kernel(const SearchArgs a) {
+  constexpr int P = W == 1 ? 2 : 1;                            // filter passes = edges per thread and round
+  constexpr int EDG = W == 1 ? 64 : SEARCH_HEAD;               // edges (or seeds) of one round
+  constexpr int CK = W == 1 ? 64 : SEARCH_CMAX;                // keys one round can publish
+#define FAST_SYNC()                 \
+  {                                 \
+    if (W == 1) __syncwarp();       \
+    else __syncthreads();           \
+  }
   constexpr uint32_t SPW = fast_stage_per_warp(CH, W);         // staging ring of one warp
   constexpr uint32_t SROW = 128u * CH;                         // staging stride of a row
   // lanes per row in a distance step: eight (four rows per step; the float summation order needs it), or FAST_INT_LD
@@ -103,10 +144,10 @@ __global__ void __launch_bounds__(W * 32, 32 / W) search_fast_kernel(const Searc
   constexpr uint32_t RPI = 4u / CH;                            // rows per copy instruction
   constexpr uint32_t LPR = 8u * CH;                            // lanes per row in a copy instruction
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  __shared__ __align__(16) uint32_t s_wids[W][32 + 16];  // new ids per warp (+ padding up to a whole group)
+  __shared__ __align__(16) uint32_t s_wids[W][32 * P + 16];  // new ids per warp (+ padding up to a whole group)
   __shared__ uint32_t s_wcnt[W], s_wval[W];
-  __shared__ uint64_t s_cand_keys[SEARCH_CMAX];
-  __shared__ __align__(16) uint32_t s_edges[2][SEARCH_HEAD];   // edge lists of the round / of the expected next node
+  __shared__ uint64_t s_cand_keys[CK];
+  __shared__ __align__(16) uint32_t s_edges[2][EDG];   // edge lists of the round / of the expected next node
   __shared__ uint32_t s_key_n;
   __shared__ int s_state;         // 0 run, 1 finished, 2 overflow
   __shared__ uint32_t s_query;
@@ -125,7 +166,7 @@ __global__ void __launch_bounds__(W * 32, 32 / W) search_fast_kernel(const Searc
   const int warp = tid >> 5;
 
   uint8_t *stage = smem_raw;                                                   // 4 x SPW
-  uint64_t *queue = reinterpret_cast<uint64_t *>(smem_raw + W * SPW);
+  uint64_t *queue = W == 1 ? a.queue_slabs + (size_t)blockIdx.x * a.queue_cap : reinterpret_cast<uint64_t *>(smem_raw + W * SPW);
   uint32_t *hash = a.hash_slabs + ((size_t)blockIdx.x << a.hash_bits);
   const uint32_t bucket_bits = a.hash_bits - 3;
   const uint32_t take_head = a.edge_cap < SEARCH_HEAD ? a.edge_cap : SEARCH_HEAD;
@@ -156,7 +197,7 @@ __global__ void __launch_bounds__(W * 32, 32 / W) search_fast_kernel(const Searc
       s_state = 0;
       s_key_n = 0;
     }
-    __syncthreads();
+    FAST_SYNC();
     const uint32_t q = s_query;
     if (q == 0xffffffffu) break;
     {
@@ -182,7 +223,7 @@ __global__ void __launch_bounds__(W * 32, 32 / W) search_fast_kernel(const Searc
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) qn += __shfl_xor_sync(0xffffffffu, qn, o);
     }
-    __syncthreads();   // the slab is zero before anybody probes it
+    FAST_SYNC();   // the slab is zero before anybody probes it
 
     if (a.seeds == nullptr) {
       // ---- seeds: the n_seeds nearest pivots of the seed table (the same selection as seed_select_kernel, without
@@ -245,7 +286,7 @@ __global__ void __launch_bounds__(W * 32, 32 / W) search_fast_kernel(const Searc
         }
       }
       s_cand_keys[warp * 32 + lane] = wres;
-      __syncthreads();
+      FAST_SYNC();
       if (warp == 0) {
         uint64_t mres = KEY_NONE, mthr = KEY_NONE;
         for (int w = 0; w < W; w++) {
@@ -285,6 +326,21 @@ __global__ void __launch_bounds__(W * 32, 32 / W) search_fast_kernel(const Searc
     }
 
     for (;;) {
+      // The head-table row of the node expected to be popped next was staged during the round that just ended: the warps
+      // that wait for the control warp pull the visited-hash buckets of its edges towards L2 meanwhile (a hint only: when
+      // the prediction fails, 37 % of the rounds, the lines are simply not used). uint8 128-byte rows 3.28 -> 3.19 ms per
+      // 10k batch, 512-byte float rows 3.39 -> 3.37 ms.
+      if (W > 1 && warp != 0) {
+        const uint32_t pid = s_ctl[7];
+        if (pid) {
+          const uint32_t *pe = s_edges[(s_buf ^ 1u) & 1u];
+          for (uint32_t e = (uint32_t)(warp - 1) * 32u + (uint32_t)lane; e < take_head; e += (uint32_t)(W - 1) * 32u) {
+            const uint32_t nid = pe[e];
+            if (nid != 0u && nid <= a.n)
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(hash + (size_t)((nid * 2654435761u) >> (32 - bucket_bits)) * 8));
+          }
+        }
+      }
       // ================= control (warp 0) =================
       if (warp == 0) {
         uint64_t res = s_res[lane];
@@ -438,27 +494,63 @@ __global__ void __launch_bounds__(W * 32, 32 / W) search_fast_kernel(const Searc
           else if (finished) s_state = 1;
         }
       }
-      __syncthreads();  // (A) the round is published
+      FAST_SYNC();  // (A) the round is published
       if (s_state != 0) break;
 
-      // ================= filter: one edge per thread =================
+      // ================= filter: one edge per thread (and pass) =================
       const bool seeding_round = s_seeding != 0;
-      uint32_t pend_id = 0;
-      uint32_t cn_w = 0;
-      BucketProbe bp;
-      bp.bucket = 0;
-      bp.slot = 0;
-      {
-        const uint32_t e = (uint32_t)W * (uint32_t)lane + (uint32_t)warp;   // edges dealt round-robin: the warps get equal shares
+      uint32_t pend_id[P];
+      BucketProbe bp[P];
+      uint32_t cn_w = 0, val_w = 0;
+      if (P == 2 && !seeding_round) {
+        // one warp per query: the bucket reads of both passes are issued before either is looked at
+        uint32_t nid2[P], b2[P], v2[P][8];
+        bool valid2[P];
+#pragma unroll
+        for (int ps = 0; ps < P; ps++) {
+          pend_id[ps] = 0;
+          bp[ps].bucket = 0;
+          bp[ps].slot = 0;
+          const uint32_t e = (uint32_t)(lane + 32 * ps);
+          nid2[ps] = e < s_take ? s_edges[s_buf][e] : 0u;
+          valid2[ps] = nid2[ps] != 0u && nid2[ps] <= a.n;
+          b2[ps] = (nid2[ps] * 2654435761u) >> (32 - bucket_bits);
+          if (valid2[ps]) hash_load256(hash, b2[ps], v2[ps]);
+        }
+#pragma unroll
+        for (int ps = 0; ps < P; ps++) {
+          bool isnew = false;
+          if (valid2[ps]) {
+            isnew = !hash_lookup256_loaded(hash, bucket_bits, nid2[ps], b2[ps], v2[ps], bp[ps]);
+            if (isnew) {
+              pend_id[ps] = nid2[ps];
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(a.objects + (size_t)nid2[ps] * a.row_bytes));
+            }
+          }
+          const uint32_t m = __ballot_sync(0xffffffffu, isnew);
+          const uint32_t mv = __ballot_sync(0xffffffffu, valid2[ps]);
+          if (isnew) s_wids[warp][cn_w + __popc(m & lanemask_lt())] = nid2[ps];
+          cn_w += (uint32_t)__popc(m);
+          val_w += (uint32_t)__popc(mv);
+        }
+      } else
+#pragma unroll
+      for (int ps = 0; ps < P; ps++) {
+        pend_id[ps] = 0;
+        bp[ps].bucket = 0;
+        bp[ps].slot = 0;
+        if (ps > 0 && (uint32_t)(32 * W * ps) >= s_take) continue;
+        if (ps > 0 && seeding_round) __syncwarp();   // a repeated seed id must see the insertion of the first pass
+        const uint32_t e = (uint32_t)W * (uint32_t)(lane + 32 * ps) + (uint32_t)warp;   // edges dealt round-robin: the warps get equal shares
         const uint32_t nid = e < s_take ? s_edges[s_buf][e] : 0u;
         const bool valid = nid != 0u && nid <= a.n;
         bool isnew = false;
         if (valid) {
-          isnew = !hash_lookup256(hash, bucket_bits, nid, bp);
+          isnew = !hash_lookup256(hash, bucket_bits, nid, bp[ps]);
           if (isnew) {
             // seed lists may repeat an id: insert at once so that the second copy is seen
-            if (seeding_round) isnew = hash_insert(hash, bucket_bits, nid, bp);
-            else pend_id = nid;
+            if (seeding_round) isnew = hash_insert(hash, bucket_bits, nid, bp[ps]);
+            else pend_id[ps] = nid;
             // the row is copied to shared memory a few hundred cycles from now: start it towards L2
             if (isnew) {
               const uint8_t *rp = a.objects + (size_t)nid * a.row_bytes;
@@ -471,17 +563,18 @@ __global__ void __launch_bounds__(W * 32, 32 / W) search_fast_kernel(const Searc
         }
         const uint32_t m = __ballot_sync(0xffffffffu, isnew);
         const uint32_t mv = __ballot_sync(0xffffffffu, valid);
-        if (isnew) s_wids[warp][__popc(m & lanemask_lt())] = nid;
-        // the last group (four rows, or RPS) is filled up with row 0 (the all-zero dummy object, an L2 hit): its copies need no
-        // predicates and its distances are dropped
-        if ((uint32_t)lane < RPS - 1u) s_wids[warp][__popc(m) + lane] = 0u;
-        if (lane == 0) {
-          s_wcnt[warp] = (uint32_t)__popc(m);
-          s_wval[warp] = (uint32_t)__popc(mv);
-        }
-        __syncwarp();
-        cn_w = (uint32_t)__popc(m);
+        if (isnew) s_wids[warp][cn_w + __popc(m & lanemask_lt())] = nid;
+        cn_w += (uint32_t)__popc(m);
+        val_w += (uint32_t)__popc(mv);
       }
+      // the last group (four rows, or RPS) is filled up with row 0 (the all-zero dummy object, an L2 hit): its copies need no
+      // predicates and its distances are dropped
+      if ((uint32_t)lane < RPS - 1u) s_wids[warp][cn_w + lane] = 0u;
+      if (lane == 0) {
+        s_wcnt[warp] = cn_w;
+        s_wval[warp] = val_w;
+      }
+      __syncwarp();
       const uint32_t cn = cn_w;           // this warp's rows
       const uint32_t *cand_ids = s_wids[warp];
 
@@ -515,7 +608,9 @@ __global__ void __launch_bounds__(W * 32, 32 / W) search_fast_kernel(const Searc
   }
 #pragma unroll
         for (int b = 0; b < NB; b++) FAST_ISSUE((uint32_t)b)
-        if (pend_id) hash_insert(hash, bucket_bits, pend_id, bp);   // under the row copies in flight
+#pragma unroll
+        for (int ps = 0; ps < P; ps++)
+          if (pend_id[ps]) hash_insert(hash, bucket_bits, pend_id[ps], bp[ps]);   // under the row copies in flight
         float tot0 = 0.f, tot1 = 0.f;   // this lane's row of the current block of LD steps
         uint32_t totu = 0;
         for (uint32_t t = 0; t < ngw; t++) {
@@ -602,7 +697,7 @@ __global__ void __launch_bounds__(W * 32, 32 / W) search_fast_kernel(const Searc
 #undef FAST_ISSUE
 #undef FAST_GROUP_C0
       }
-      __syncthreads();  // (C) keys are published; buffers may be overwritten
+      FAST_SYNC();  // (C) keys are published; buffers may be overwritten
     }
 
     // ---- write the outcome
@@ -634,8 +729,9 @@ __global__ void __launch_bounds__(W * 32, 32 / W) search_fast_kernel(const Searc
         a.overflow_list[slot] = q;
       }
     }
-    __syncthreads();  // s_query / s_state are rewritten by thread 0 next
+    FAST_SYNC();  // s_query / s_state are rewritten by thread 0 next
   }
+#undef FAST_SYNC
 }
 
 // ---- seed selection: the n_seeds nearest pivots of the seed table, one warp per query -----------------------
@@ -759,6 +855,7 @@ static cudaError_t fast_one(const SearchArgs &a, unsigned grid, size_t smem, cud
 template <int ACC>
 cudaError_t search_fast_dispatch(const SearchArgs &a, int ch, int warps, unsigned grid, size_t smem, cudaStream_t stream, int op,
                                  int *blocks) {
+  if (ch == 1 && warps == 1) return fast_one<ACC, 1, 1>(a, grid, smem, stream, op, blocks);
   if (ch == 1 && warps == 2) return fast_one<ACC, 1, 2>(a, grid, smem, stream, op, blocks);
   if (ch == 2 && warps == 2) return fast_one<ACC, 2, 2>(a, grid, smem, stream, op, blocks);
   if (ch == 4 && warps == 2) return fast_one<ACC, 4, 2>(a, grid, smem, stream, op, blocks);

@@ -145,6 +145,10 @@ class GpuIndex:
         """First traversal tier of the common case on the lean kernel (default) or on the general one."""
         _lib.check(self._lib.ngtgpu_index_set_fast_kernel(self._h, int(bool(enabled))))
 
+    def set_fast_shape(self, warps_per_query=0, ctas_per_sm=0):
+        """Warps per query of the lean kernel (0: by row width; 1, 2, 4) and a cap on its resident CTAs per SM (0: what fits)."""
+        _lib.check(self._lib.ngtgpu_index_set_fast_shape(self._h, int(warps_per_query), int(ctas_per_sm)))
+
     def set_seed_fusion(self, enabled=True):
         """Seed selection inside the lean traversal kernel (True) or by its own launch (default)."""
         _lib.check(self._lib.ngtgpu_index_set_seed_fusion(self._h, int(bool(enabled))))

@@ -21,7 +21,8 @@ ap.add_argument("--eps", type=float, default=0.1)
 ap.add_argument("--knn", type=int, default=64)
 ap.add_argument("--shape", default="")
 ap.add_argument("--steps", type=int, default=5)
-ap.add_argument("--settings", default="4:0:0,2:0:0")   # warps:ctas:hash_bits (0 = default)
+ap.add_argument("--batch", type=int, default=10000)
+ap.add_argument("--settings", default="2:0:0,1:32:0,1:24:0,1:16:0")   # warps:ctas:hash_bits (0 = default)
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 lib = _lib.load()
@@ -38,8 +39,8 @@ ix.set_objects(base)
 ix.build_onng(64, 10, 64, True)
 ix.set_search_property(64, 30, 20)
 ix.build_seed_table(256, 1)
-qs = make_rows(shape, kind, 30000, 2, dev)
-batches = [qs[i * 10000:(i + 1) * 10000].contiguous() for i in range(3)]
+qs = make_rows(shape, kind, 3 * a.batch, 2, dev)
+batches = [qs[i * a.batch:(i + 1) * a.batch].contiguous() for i in range(3)]
 gt = ix.linear_search(batches[0][:1000], 10)
 peak, _ = measured_peak_gbs()
 elem = 4 if kind == "f32" else 1
@@ -74,7 +75,7 @@ for s in a.settings.split(","):
     lib.ngtgpu_index_pop_timing(ix._h, C.byref(kms), C.byref(kc))
     lib.ngtgpu_index_set_timing(ix._h, 0)
     k_ms = kms.value / max(kc.value, 1)
-    print(json.dumps({"kind": a.kind, "n": a.n, "warps": w, "ctas_cap": ctas, "hash_bits": hb, "eps": a.eps, "recall": round(rec, 4),
+    print(json.dumps({"kind": a.kind, "n": a.n, "batch": a.batch, "warps": w, "ctas_cap": ctas, "hash_bits": hb, "eps": a.eps, "recall": round(rec, 4),
                       "step_ms": round(e0.elapsed_time(e1) / a.steps, 3), "kernel_ms": round(k_ms, 3), "overflow": ovf,
                       "gbs": round(bytes_step / k_ms / 1e6, 1), "frac": round(bytes_step / k_ms / 1e6 / peak, 4),
-                      "n_dist": round(float(st[:, 0].mean()), 1), "same_ids_as_first": same}), flush=True)
+                      "n_dist": round(float(st[:, 0].mean()), 1), "n_exp": round(float(st[:, 2].mean()), 1), "same_ids_as_first": same}), flush=True)
