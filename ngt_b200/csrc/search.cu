@@ -208,7 +208,9 @@ int ngtgpu_traverse(ngtgpu_index *ix, const uint8_t *d_queries, uint32_t nq, con
     const bool two_fit = cap <= 64 && n_seeds <= 64;
     // one warp per query (32 CTAs per SM, the back of the unchecked set in a global slab) in the first tier, when asked for
     const bool one_fit = two_fit && fast_ch == 1 && t == 0 && ix->fast_warps == 1;
-    const int fast_w = one_fit ? 1 : two_fit && ix->fast_warps != 4 ? 2 : FAST_WARPS;
+    // (two warps also take rounds of up to 128 edges, two per thread, when asked for)
+    const bool two_asked = ix->fast_warps == 2 && cap <= 128 && n_seeds <= 128;
+    const int fast_w = one_fit ? 1 : (two_fit && ix->fast_warps != 4) || two_asked ? 2 : FAST_WARPS;
     if (fast) smem = (size_t)fast_w * fast_stage_per_warp(fast_ch, fast_w) + (fast_w == 1 ? 0 : (size_t)a.queue_cap * 8);
     if (smem > 200 * 1024)
       NGTGPU_FAIL(NGTGPU_ERR_INVALID, "search: working set does not fit shared memory; lower queue_cap/size");

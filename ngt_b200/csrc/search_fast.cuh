@@ -122,7 +122,8 @@ __device__ __forceinline__ void cp_async_wait_group() {
 // 128-byte rows (3.6 vs 3.2 ms per 10k batch, 3.0 vs 2.9 ms per 10k at batch 40k): twice the slabs fall out of L2.
 template <int ACC, int CH, int W>
 __global__ void __launch_bounds__(W * 32, 32 / W) search_fast_kernel(const SearchArgs a) {
-  constexpr int P = W == 1 ? 2 : 1;                            // filter passes = edges per thread and round
+  constexpr int P = W <= 2 ? 2 : 1;                            // filter passes = edges per thread and round (the second
+                                                               // one only when the round has more than 32 * W edges)
   constexpr int EDG = W == 1 ? 64 : SEARCH_HEAD;               // edges (or seeds) of one round
   constexpr int CK = W == 1 ? 64 : SEARCH_CMAX;                // keys one round can publish
 #define FAST_SYNC()                 \
@@ -502,8 +503,8 @@ __global__ void __launch_bounds__(W * 32, 32 / W) search_fast_kernel(const Searc
       uint32_t pend_id[P];
       BucketProbe bp[P];
       uint32_t cn_w = 0, val_w = 0;
-      if (P == 2 && !seeding_round) {
-        // one warp per query: the bucket reads of both passes are issued before either is looked at
+      if (W == 1 && !seeding_round && s_take > 32u) {
+        // two edges per thread: the bucket reads of both passes are issued before either is looked at
         uint32_t nid2[P], b2[P], v2[P][8];
         bool valid2[P];
 #pragma unroll
@@ -511,7 +512,7 @@ __global__ void __launch_bounds__(W * 32, 32 / W) search_fast_kernel(const Searc
           pend_id[ps] = 0;
           bp[ps].bucket = 0;
           bp[ps].slot = 0;
-          const uint32_t e = (uint32_t)(lane + 32 * ps);
+          const uint32_t e = (uint32_t)W * (uint32_t)(lane + 32 * ps) + (uint32_t)warp;
           nid2[ps] = e < s_take ? s_edges[s_buf][e] : 0u;
           valid2[ps] = nid2[ps] != 0u && nid2[ps] <= a.n;
           b2[ps] = (nid2[ps] * 2654435761u) >> (32 - bucket_bits);
@@ -524,7 +525,10 @@ __global__ void __launch_bounds__(W * 32, 32 / W) search_fast_kernel(const Searc
             isnew = !hash_lookup256_loaded(hash, bucket_bits, nid2[ps], b2[ps], v2[ps], bp[ps]);
             if (isnew) {
               pend_id[ps] = nid2[ps];
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(a.objects + (size_t)nid2[ps] * a.row_bytes));
+              const uint8_t *rp = a.objects + (size_t)nid2[ps] * a.row_bytes;
+#pragma unroll
+              for (int o = 0; o < CH; o++)
+                if (o == 0 || (uint32_t)o * 128u < a.row_bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + o * 128));
             }
           }
           const uint32_t m = __ballot_sync(0xffffffffu, isnew);

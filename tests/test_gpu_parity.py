@@ -244,6 +244,14 @@ def test_fast_kernel_equals_general_kernel(eng, port, kind):
                     for x, y in zip(one, two):
                         assert (np.asarray(x).view(np.uint32) == np.asarray(y).view(np.uint32)).all(), what + " %d warp(s) per query" % w
             ix.set_fast_shape(0, 0)
+        if cap > 64:
+            # the two-warp shape asked for on rounds of 65..128 edges (two edges per thread)
+            ix.set_fast_kernel(True)
+            ix.set_fast_shape(2, 0)
+            two = ix.search(q, kk, eps, edge_size=cap, seeds=seeds, with_stats=True)
+            ix.set_fast_shape(0, 0)
+            for x, y in zip(two, out[False]):
+                assert (np.asarray(x).view(np.uint32) == np.asarray(y).view(np.uint32)).all(), what + " two warps, two passes"
         rep = {}
         for fast in (True, False):
             ix.set_fast_kernel(fast)

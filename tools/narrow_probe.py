@@ -22,6 +22,7 @@ ap.add_argument("--knn", type=int, default=64)
 ap.add_argument("--shape", default="")
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--batch", type=int, default=10000)
+ap.add_argument("--edge", type=int, default=64)
 ap.add_argument("--settings", default="2:0:0,1:32:0,1:24:0,1:16:0")   # warps:ctas:hash_bits (0 = default)
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
@@ -37,7 +38,7 @@ dist = _lib.DISTANCE_NORMALIZED_COSINE if a.kind == "glove" else _lib.DISTANCE_H
 ix = engine.GpuIndex(otype, dist, dim)
 ix.set_objects(base)
 ix.build_onng(64, 10, 64, True)
-ix.set_search_property(64, 30, 20)
+ix.set_search_property(a.edge, 30, 20)
 ix.build_seed_table(256, 1)
 qs = make_rows(shape, kind, 3 * a.batch, 2, dev)
 batches = [qs[i * a.batch:(i + 1) * a.batch].contiguous() for i in range(3)]
@@ -50,7 +51,7 @@ for s in a.settings.split(","):
     _lib.check(lib.ngtgpu_index_set_fast_shape(ix._h, w, ctas))
     if hb:
         ix.set_search_workspace(hb, 512)
-    r = ix.search(batches[0], 10, a.eps, edge_size=64, n_seeds=10, with_stats=True)
+    r = ix.search(batches[0], 10, a.eps, edge_size=a.edge, n_seeds=10, with_stats=True)
     st = r[3].cpu().numpy().astype(np.int64)
     ids = r[0].cpu().numpy()
     if ref is None:
@@ -58,17 +59,17 @@ for s in a.settings.split(","):
     same = bool((ids == ref).all())
     rec = recall_at_k(ids[:1000].astype(np.uint32), r[1].cpu().numpy()[:1000], r[2].cpu().numpy()[:1000].astype(np.int64),
                       gt[0].cpu().numpy().astype(np.uint32), gt[1].cpu().numpy())
-    ix.search(batches[0].cpu().numpy(), 10, a.eps, edge_size=64, n_seeds=10)
+    ix.search(batches[0].cpu().numpy(), 10, a.eps, edge_size=a.edge, n_seeds=10)
     ovf = ix.last_overflows
     bytes_step = int((st[:, 0] * dim * elem + st[:, 1] * 4).sum())
     for i in range(3):
-        ix.search(batches[i % 3], 10, a.eps, edge_size=64, n_seeds=10)
+        ix.search(batches[i % 3], 10, a.eps, edge_size=a.edge, n_seeds=10)
     torch.cuda.synchronize()
     lib.ngtgpu_index_set_timing(ix._h, 1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(a.steps):
-        ix.search(batches[i % 3], 10, a.eps, edge_size=64, n_seeds=10)
+        ix.search(batches[i % 3], 10, a.eps, edge_size=a.edge, n_seeds=10)
     e1.record()
     torch.cuda.synchronize()
     kms, kc = C.c_double(0), C.c_uint64(0)
