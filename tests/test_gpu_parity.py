@@ -276,14 +276,16 @@ def test_fast_kernel_equals_general_kernel(eng, port, kind):
     ix.close()
 
 
-@pytest.mark.parametrize("kind", ["u8l2_128", "f32l2_32"])
+@pytest.mark.parametrize("kind", ["u8l2_128", "f32l2_32", "u8l2_128_wide"])
 def test_one_warp_per_query_shape(eng, port, kind):
     """search_fast_kernel<.., W = 1>: rounds of 33..64 edges and seed lists of 40 (two filter passes per round, a seed id
     repeated across the passes), the back of the unchecked set in its global slab: identical to the general kernel and,
     being integer-valued, to the C restatement of the reference -- ids, distance bits, counts, work counters."""
     from ngt_b200 import synth
     rng = np.random.default_rng(5)
-    name, dim = kind.split("_")
+    # "wide": rounds of 65..100 edges and 80 seeds -- the two-warp shape with two edges per thread (asked for), against four warps
+    wide = kind.endswith("_wide")
+    name, dim = kind.split("_")[:2]
     dim = int(dim)
     n, nq = 20000, 400
     base, qs = synth.make("sift", n, 1)[:, :dim], synth.make("sift", nq, 2)[:, :dim]
@@ -291,20 +293,21 @@ def test_one_warp_per_query_shape(eng, port, kind):
     objs = base.astype(np.uint8) if name == "u8l2" else base
     ix = eng.GpuIndex(otype, po.L2, dim)
     ix.set_objects(objs)
-    gids, _, gcounts = ix.linear_search(objs.astype(np.float32), 60)
+    gids, _, gcounts = ix.linear_search(objs.astype(np.float32), 100 if wide else 60)
     row_ptr, col = _knn_csr(gids, gcounts)
     ix.set_graph(row_ptr, col)
-    seeds = np.stack([rng.choice(n, 40, replace=False) + 1 for _ in range(nq)]).astype(np.uint32)
+    ns = 80 if wide else 40
+    seeds = np.stack([rng.choice(n, ns, replace=False) + 1 for _ in range(nq)]).astype(np.uint32)
     seeds_rep = seeds.copy()
-    seeds_rep[::3, 35] = seeds_rep[::3, 1]   # evaluated once (the engine's contract for repeated seeds)
+    seeds_rep[::3, ns - 5] = seeds_rep[::3, 1]   # evaluated once (the engine's contract for repeated seeds)
     pobj, pq = po.pad_objects(objs, otype), po.pad_queries(qs, otype)
-    for eps, cap, kk in ((0.1, 64, 10), (0.25, 48, 32), (0.0, 33, 1)):
+    for eps, cap, kk in (((0.1, 100, 10), (0.2, 96, 32), (0.0, 65, 1)) if wide else ((0.1, 64, 10), (0.25, 48, 32), (0.0, 33, 1))):
         what = "%s eps=%g cap=%d k=%d" % (kind, eps, cap, kk)
         for sd in (seeds_rep, seeds):
             ix.set_fast_kernel(False)
             ref = ix.search(qs, kk, eps, edge_size=cap, seeds=sd, with_stats=True)
             ix.set_fast_kernel(True)
-            for w in (2, 1):
+            for w in ((4, 2) if wide else (2, 1)):
                 ix.set_fast_shape(w, 0)
                 got = ix.search(qs, kk, eps, edge_size=cap, seeds=sd, with_stats=True)
                 for x, y in zip(got, ref):
@@ -313,7 +316,7 @@ def test_one_warp_per_query_shape(eng, port, kind):
         assert_bit_exact(got[0], got[1], got[2], rids, rdists, rcounts, what=what)
         assert (got[3].astype(np.uint64) == rstats).all(), what
     # a small slab and queue: the queries that outgrow the one-warp tier are finished by the later tiers
-    ix.set_fast_shape(1, 0)
+    ix.set_fast_shape(2 if wide else 1, 0)
     ix.set_search_workspace(hash_bits=9, queue_cap=64)
     got = ix.search(qs, 10, 0.25, edge_size=48, seeds=seeds)
     assert ix.last_overflows > 0
