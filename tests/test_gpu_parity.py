@@ -556,7 +556,7 @@ def test_pack_and_merge_kernels_match_host(eng):
 
 @pytest.mark.parametrize("case", ["sift_l2_exact_bf16", "glove_l2_split", "glove_ncos_split", "glove_cos_split", "sift_u8_l2",
                                   "sift_hamming", "gist_l2_split_streamed", "gist_cos_split_streamed", "sift_l2_forced_stream"])
-def test_tensor_core_knn_matches_cuda_core_scan(eng, case, monkeypatch):
+def test_tensor_core_knn_matches_cuda_core_scan(eng, port, case, monkeypatch):
     """knn_tc.cu (tcgen05 filter + exact re-evaluation) returns exactly what the CUDA-core scan returns: ids,
     distance bits and counts, for batches, kNN-graph construction (self excluded) and with removed slots."""
     from ngt_b200 import build, synth
@@ -590,6 +590,20 @@ def test_tensor_core_knn_matches_cuda_core_scan(eng, case, monkeypatch):
         rids, rdists, rcounts = ix.linear_search(qs, k)
         assert ix.tensor_core_batches == before + 1
         assert_bit_exact(ids, dists, counts, rids, rdists, rcounts, what="%s k=%d" % (case, k))
+    # ... and what the C restatement of the reference's linearSearch returns, directly (so that a bug shared by both device
+    # paths cannot hide): bit for bit where the arithmetic is exact, within the float tolerance otherwise
+    ix.set_tensor_core(True)
+    before = ix.tensor_core_batches
+    ids, dists, counts = ix.linear_search(qs, 10)
+    assert ix.tensor_core_batches == before + 1
+    sub = 40
+    pobj = po.pad_objects(base, ot)
+    pq = po.pad_queries(np.asarray(qs[:sub], np.float32 if ot == po.FLOAT else np.uint8), ot)
+    rids, rdists, rcounts = port.linear_search(dt, ot, pobj, pq, 10)
+    if case in ("sift_l2_exact_bf16", "sift_u8_l2", "sift_hamming", "sift_l2_forced_stream"):
+        assert_bit_exact(ids[:sub], dists[:sub], counts[:sub], rids, rdists, rcounts, what=case + " vs the C restatement")
+    else:
+        assert_float_parity(ids[:sub], dists[:sub], counts[:sub], rids, rdists, rcounts, what=case + " vs the C restatement")
     # kNN-graph construction: stored rows as queries, the row itself dropped
     ix.set_tensor_core(True)
     gi, gd, gc = build.knn_graph(ix, 16, batch=8192)
