@@ -154,8 +154,10 @@ int ngtgpu_index_set_onchip_tiers(ngtgpu_index *index, int tiers);
  * kernel with the same results; 0 sends it through the general kernel as well (default 1). */
 int ngtgpu_index_set_fast_kernel(ngtgpu_index *index, int enabled);
 /* Shape of the lean kernel's on-chip tiers: warps per query -- 0 (default): 2 whenever a round fits 64 threads (<= 64
- * edges and seeds; 16 CTAs per SM, twice the queries in flight: rounds are latency-bound), else 4; 2 / 4 as asked -- and
- * a cap on resident CTAs per SM (0: what fits). Same results either way. */
+ * edges and seeds; 16 CTAs per SM, twice the queries in flight: rounds are latency-bound), else 4; 4 as asked; 2 as asked
+ * also for rounds of up to 128 edges (two per thread; measured slower than 4 on 512-byte rows); 1 as asked for rows of
+ * <= 128 bytes and rounds of <= 64 edges (32 CTAs per SM, first tier only; measured slower than 2) -- and a cap on
+ * resident CTAs per SM (0: what fits). Same results either way. */
 int ngtgpu_index_set_fast_shape(ngtgpu_index *index, int warps_per_query, int ctas_per_sm);
 /* Searches without a seed list take the nearest pivots of the seed table. 1: the lean traversal kernel selects them itself
  * (no separate selection launch: +1.4 % queries/s on the 1M x 128 set, but the traversal launch then also carries the
