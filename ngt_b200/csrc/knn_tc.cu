@@ -27,8 +27,12 @@
 // warp; group g owns accumulator g, i.e. the even / the odd row tiles, with buffers and thresholds of its own, so the
 // two groups never share state), warp 8 producer (cp.async.bulk of pre-swizzled 16 KB operand tiles, mbarrier
 // complete_tx), warp 9 MMA issuer (one elected thread; M=128, N=128, K=16 per instruction, SWIZZLE_128B K-major
-// descriptors). The query operand stays resident in shared memory, row tiles stream through a ring of up to six
-// stages, and the two 128-column accumulators in TMEM alternate, so each epilogue group has two tile times per tile.
+// descriptors). A CTA owns 256 queries (two query tiles; every row tile feeds both). Short K axes (<= 6 chunks of 64
+// elements): the query operand stays resident in shared memory and row tiles stream through a ring of up to ten 16 KB
+// stages. Long K axes (960-d data: 46 chunks as split floats): one k-chunk of both query tiles travels with every row
+// chunk through a ring of four 48 KB stages, and the grid is ordered so that a wave is a few query-tile pairs times all
+// row splits (the re-read query operand of a wave stays in L2). The two sets of 128-column accumulators in TMEM
+// alternate, so each epilogue group has two tile times per tile.
 #include <algorithm>
 #include <cfloat>
 #include <cstdlib>
