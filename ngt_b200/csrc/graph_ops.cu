@@ -23,6 +23,8 @@
 //            (the lowest undecided id never waits, so this terminates).
 // The result is the reference's graph bit for bit (tests/golden/adjust_paths.npz pins it).
 #include <cub/cub.cuh>
+#include <mutex>
+#include <vector>
 
 #include "ngtgpu_internal.cuh"
 
@@ -215,24 +217,111 @@ __global__ void keep_mask_kernel(const uint8_t *__restrict__ status, uint64_t nn
     keep[i] = status[i] == 1 ? 1 : 0;
 }
 
-struct DeviceBuffers {   // frees what it allocated, whichever way the function returns
-  std::vector<void *> ptrs;
+// Temporary device buffers of one call: handed back, whichever way the function returns, to a small per-device cache of
+// blocks instead of cudaFree -- the construction loop calls these functions once per batch of 200 objects, and a dozen
+// cudaMalloc / cudaFree pairs per call (each a driver round trip with an implicit device synchronisation) were most of
+// its time (19 ms per batch of which ~2 ms on the GPU). A block goes back to the cache only after the device is idle,
+// which is the guarantee cudaFree gave.
+struct BlockCache {
+  struct Block {
+    void *p;
+    size_t bytes;
+    int dev;
+  };
+  std::mutex mu;
+  std::vector<Block> free_blocks;
+  size_t cached_bytes = 0;
+  static constexpr size_t kMaxCachedBytes = (size_t)8 << 30;
+  static constexpr size_t kMaxBlocks = 96;
+  void *take(size_t bytes, int dev, size_t *got) {
+    std::lock_guard<std::mutex> lock(mu);
+    int best = -1;
+    for (size_t i = 0; i < free_blocks.size(); i++) {
+      const Block &b = free_blocks[i];
+      if (b.dev != dev || b.bytes < bytes || b.bytes > 2 * bytes + ((size_t)1 << 20)) continue;
+      if (best < 0 || b.bytes < free_blocks[best].bytes) best = (int)i;
+    }
+    if (best < 0) return nullptr;
+    Block b = free_blocks[best];
+    free_blocks.erase(free_blocks.begin() + best);
+    cached_bytes -= b.bytes;
+    *got = b.bytes;
+    return b.p;
+  }
+  void give(void *p, size_t bytes, int dev) {
+    std::lock_guard<std::mutex> lock(mu);
+    free_blocks.push_back(Block{p, bytes, dev});
+    cached_bytes += bytes;
+    while (!free_blocks.empty() && (cached_bytes > kMaxCachedBytes || free_blocks.size() > kMaxBlocks)) {   // oldest first
+      cudaFree(free_blocks.front().p);
+      cached_bytes -= free_blocks.front().bytes;
+      free_blocks.erase(free_blocks.begin());
+    }
+  }
+  // everything back to the driver (a failed cudaMalloc retries after this)
+  void trim() {
+    std::lock_guard<std::mutex> lock(mu);
+    for (Block &b : free_blocks) cudaFree(b.p);
+    free_blocks.clear();
+    cached_bytes = 0;
+  }
+};
+BlockCache &block_cache() {
+  static BlockCache *c = new BlockCache();   // leaked on purpose: no cudaFree after the driver has shut down
+  return *c;
+}
+
+struct DeviceBuffers {
+  struct Held {
+    void *p;
+    size_t bytes;
+  };
+  std::vector<Held> held;
+  int dev = -1;
+  cudaStream_t stream;   // the caller's stream: blocks are zeroed on it before they are handed out
+  explicit DeviceBuffers(cudaStream_t s) : stream(s) {}
   ~DeviceBuffers() {
-    for (void *p : ptrs) cudaFree(p);
+    if (held.empty()) return;
+    cudaDeviceSynchronize();
+    for (Held &h : held) block_cache().give(h.p, h.bytes, dev);
   }
   template <typename T>
   cudaError_t alloc(T **out, size_t count) {
-    void *p = nullptr;
-    cudaError_t e = cudaMalloc(&p, count ? count * sizeof(T) : sizeof(T));
-    if (e == cudaSuccess) ptrs.push_back(p);
+    if (dev < 0 && cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    size_t bytes = (count ? count * sizeof(T) : sizeof(T));
+    bytes = (bytes + 511) & ~(size_t)511;
+    size_t got = 0;
+    void *p = block_cache().take(bytes, dev, &got);
+    cudaError_t e = cudaSuccess;
+    if (!p) {
+      got = bytes;
+      e = cudaMalloc(&p, bytes);
+      if (e != cudaSuccess) {   // the cache may be what fills the device
+        cudaGetLastError();
+        cudaDeviceSynchronize();
+        block_cache().trim();
+        e = cudaMalloc(&p, bytes);
+      }
+    }
+    if (e == cudaSuccess) {
+      held.push_back(Held{p, got});
+      // (development: NGTGPU_POISON=1 fills with 0xff instead, which shows every dependence on that)
+      static const bool poison = getenv("NGTGPU_POISON") != nullptr;
+      // a block of the cache holds what its last user left, and a fresh one is zero only by the driver's habit: every
+      // block starts zeroed (the callers' counters and sparse tables count on it)
+      e = cudaMemsetAsync(p, poison ? 0xff : 0, got, stream);
+    } else {
+      p = nullptr;
+    }
     *out = static_cast<T *>(p);
     return e;
   }
   void release(void *p) {
-    for (size_t i = 0; i < ptrs.size(); i++)
-      if (ptrs[i] == p) {
-        cudaFree(p);
-        ptrs.erase(ptrs.begin() + i);
+    for (size_t i = 0; i < held.size(); i++)
+      if (held[i].p == p) {
+        cudaDeviceSynchronize();
+        block_cache().give(p, held[i].bytes, dev);
+        held.erase(held.begin() + i);
         return;
       }
   }
@@ -257,7 +346,7 @@ extern "C" int ngtgpu_graph_adjust_paths(uint64_t n, const uint64_t *d_row_ptr, 
     NGTGPU_FAIL(NGTGPU_ERR_INVALID, "ngtgpu_graph_adjust_paths: more than 2^31 edges are not supported");
   const unsigned grid = (unsigned)sms * 8;
   uint64_t launches = 0;
-  DeviceBuffers mem;
+  DeviceBuffers mem(stream);
 
   // ---- edge -> (source, rank); degree histogram (for the number of active nodes per sweep)
   const uint32_t hist_cap = 1u << 20;
@@ -560,7 +649,7 @@ extern "C" int ngtgpu_graph_reconstruct(uint64_t n, const uint64_t *d_row_ptr, c
   if (nnz == 0) return NGTGPU_OK;
   if (!d_col || !d_dist || !d_out_col || !d_out_dist) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "ngtgpu_graph_reconstruct: null buffer");
   if (n >= 0xfffffffeull) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "ngtgpu_graph_reconstruct: too many nodes");
-  DeviceBuffers mem;
+  DeviceBuffers mem(stream);
   uint32_t *src_a, *src_b;
   uint64_t *key_a, *key_b;
   unsigned long long *counter;
@@ -655,7 +744,7 @@ extern "C" int ngtgpu_graph_from_knn_table(uint64_t n, const uint32_t *d_ids, co
   *out_nnz = 0;
   CUDA_TRY(cudaMemsetAsync(d_out_row_ptr, 0, (n + 2) * sizeof(uint64_t), stream));
   if (n == 0 || k == 0) return NGTGPU_OK;
-  DeviceBuffers mem;
+  DeviceBuffers mem(stream);
   const uint64_t m_max = (uint64_t)n * k * (symmetric ? 2 : 1);
   uint32_t *src_a, *src_b;
   uint64_t *key_a, *key_b;
@@ -725,7 +814,7 @@ extern "C" int ngtgpu_graph_select_edges(uint64_t n, const uint64_t *d_row_ptr, 
   CUDA_TRY(cudaGetDevice(&dev));
   CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   const unsigned grid = (unsigned)sms * 8;
-  DeviceBuffers mem;
+  DeviceBuffers mem(stream);
   uint32_t *deg;
   CUDA_TRY(mem.alloc(&deg, n + 2));
   CUDA_TRY(cudaMemsetAsync(d_out_row_ptr, 0, 8, stream));
@@ -761,7 +850,7 @@ extern "C" int ngtgpu_index_refine_anng(ngtgpu_index *ix, float epsilon, int32_t
   uint64_t nnz = 0;
   CUDA_TRY(cudaMemcpyAsync(&nnz, d_row_ptr + n + 1, 8, cudaMemcpyDeviceToHost, stream));
   CUDA_TRY(cudaStreamSynchronize(stream));
-  DeviceBuffers mem;
+  DeviceBuffers mem(stream);
   uint32_t *r_ids, *r_counts, *t_col;
   float *r_dists, *t_dist;
   uint64_t *t_ptr;
@@ -968,7 +1057,7 @@ extern "C" int ngtgpu_index_insert_batch(ngtgpu_index *ix, uint32_t first_id, ui
   uint64_t nnz = 0;
   CUDA_TRY(cudaMemcpyAsync(&nnz, d_row_ptr + n + 1, 8, cudaMemcpyDeviceToHost, stream));
   CUDA_TRY(cudaStreamSynchronize(stream));
-  DeviceBuffers mem;
+  DeviceBuffers mem(stream);
   uint32_t *r_ids = nullptr, *r_counts = nullptr, *o_ids, *o_counts;
   float *r_dists = nullptr, *o_dists;
   CUDA_TRY(mem.alloc(&o_ids, (size_t)count * e));
@@ -979,7 +1068,8 @@ extern "C" int ngtgpu_index_insert_batch(ngtgpu_index *ix, uint32_t first_id, ui
     CUDA_TRY(mem.alloc(&r_ids, (size_t)count * e));
     CUDA_TRY(mem.alloc(&r_dists, (size_t)count * e));
     CUDA_TRY(mem.alloc(&r_counts, count));
-    NGTGPU_TRY(ngtgpu_index_set_graph(ix, d_row_ptr, d_col, 1));
+    // (the previous batch left exactly this graph on the index: same caller buffers, same edge count)
+    if (!(ix->graph_source == d_row_ptr && ix->nnz == nnz)) NGTGPU_TRY(ngtgpu_index_set_graph(ix, d_row_ptr, d_col, 1));
     if (n_pivots == 0) {   // SeedTypeFixedNodes (Index.h:1122-1127): ids 1..min(seedSize, nodes in the graph)
       std::vector<uint32_t> fixed(std::min<uint32_t>(n_seeds, first_id - 1));
       for (uint32_t i = 0; i < fixed.size(); i++) fixed[i] = i + 1;
@@ -1081,6 +1171,7 @@ extern "C" int ngtgpu_index_insert_batch(ngtgpu_index *ix, uint32_t first_id, ui
     nnz = out_nnz;
   }
   NGTGPU_TRY(ngtgpu_index_set_graph(ix, d_row_ptr, d_col, 1));
+  ix->graph_source = d_row_ptr;
   *nnz_out = nnz;
   return NGTGPU_OK;
 }
@@ -1108,7 +1199,7 @@ extern "C" int ngtgpu_index_build_onng(ngtgpu_index *ix, uint32_t knn, uint32_t 
     cudaEvent_t *e;
     ~EvGuard() { for (int i = 0; i < 4; i++) cudaEventDestroy(e[i]); }
   } guard{ev};
-  DeviceBuffers mem;
+  DeviceBuffers mem(stream);
   uint32_t *t_ids, *t_counts;
   float *t_dists;
   CUDA_TRY(mem.alloc(&t_ids, n * k));
@@ -1248,7 +1339,7 @@ extern "C" int ngtgpu_index_pairwise_distances(ngtgpu_index *ix, const uint32_t 
   for (uint32_t i = 0; i < m; i++)
     if (ids[i] == 0 || ids[i] > ix->n) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "ngtgpu_index_pairwise_distances: id out of range");
   cudaStream_t stream = ix->stream;
-  DeviceBuffers mem;
+  DeviceBuffers mem(stream);
   uint32_t *d_ids;
   float *d_out;
   CUDA_TRY(mem.alloc(&d_ids, m));

@@ -166,6 +166,8 @@ static void free_graph(ngtgpu_index *ix) {
   ix->d_row_ptr = nullptr;
   ix->d_col = nullptr;
   ix->nnz = 0;
+  ix->row_ptr_cap = ix->col_cap = ix->head_cap = 0;
+  ix->graph_source = nullptr;
 }
 static void free_tc(ngtgpu_index *ix) {
   if (ix->d_tc_tiles) cudaFree(ix->d_tc_tiles);
@@ -180,6 +182,7 @@ static void free_pivots(ngtgpu_index *ix) {
   ix->d_pivot_rows = nullptr;
   ix->d_pivot_ids = nullptr;
   ix->n_pivots = 0;
+  ix->pivot_cap = 0;
 }
 
 extern "C" int ngtgpu_index_destroy(ngtgpu_index *ix) {
@@ -421,7 +424,7 @@ extern "C" int ngtgpu_index_set_graph(ngtgpu_index *ix, const uint64_t *row_ptr,
   if (!ix->d_objects) NGTGPU_FAIL(NGTGPU_ERR_STATE, "ngtgpu_index_set_graph: objects are not set");
   if (!row_ptr) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "ngtgpu_index_set_graph: null row_ptr");
   CUDA_TRY(cudaStreamSynchronize(ix->stream));
-  free_graph(ix);
+  ix->graph_source = nullptr;
   uint64_t nnz = 0;
   cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
   if (on_device) {
@@ -434,12 +437,30 @@ extern "C" int ngtgpu_index_set_graph(ngtgpu_index *ix, const uint64_t *row_ptr,
       if (col[j] == 0 || col[j] > ix->n) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "ngtgpu_index_set_graph: edge to an id out of range");
   }
   if (nnz && !col) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "ngtgpu_index_set_graph: null col");
-  CUDA_TRY(cudaMalloc(&ix->d_row_ptr, (ix->n + 2) * sizeof(uint64_t)));
-  CUDA_TRY(cudaMalloc(&ix->d_col, (nnz ? nnz : 1) * sizeof(uint32_t)));
+  // the buffers of the previous graph are reused when they are large enough (the edge list grows by half when it is not)
+  if (ix->row_ptr_cap < ix->n + 2) {
+    if (ix->d_row_ptr) cudaFree(ix->d_row_ptr);
+    ix->d_row_ptr = nullptr, ix->row_ptr_cap = 0;
+    CUDA_TRY(cudaMalloc(&ix->d_row_ptr, (ix->n + 2) * sizeof(uint64_t)));
+    ix->row_ptr_cap = ix->n + 2;
+  }
+  if (ix->col_cap < (nnz ? nnz : 1)) {
+    if (ix->d_col) cudaFree(ix->d_col);
+    ix->d_col = nullptr;
+    const uint64_t want = ix->col_cap ? nnz + nnz / 2 : (nnz ? nnz : 1);
+    ix->col_cap = 0;
+    CUDA_TRY(cudaMalloc(&ix->d_col, want * sizeof(uint32_t)));
+    ix->col_cap = want;
+  }
   CUDA_TRY(cudaMemcpy(ix->d_row_ptr, row_ptr, (ix->n + 2) * sizeof(uint64_t), kind));
   if (nnz) CUDA_TRY(cudaMemcpy(ix->d_col, col, nnz * sizeof(uint32_t), kind));
   ix->nnz = nnz;
-  CUDA_TRY(cudaMalloc(&ix->d_head, (ix->n + 1) * NGTGPU_HEAD_WIDTH * sizeof(uint32_t)));
+  if (ix->head_cap < (ix->n + 1) * NGTGPU_HEAD_WIDTH) {
+    if (ix->d_head) cudaFree(ix->d_head);
+    ix->d_head = nullptr, ix->head_cap = 0;
+    CUDA_TRY(cudaMalloc(&ix->d_head, (ix->n + 1) * NGTGPU_HEAD_WIDTH * sizeof(uint32_t)));
+    ix->head_cap = (ix->n + 1) * NGTGPU_HEAD_WIDTH;
+  }
   build_head_kernel<<<ix->sm_count * 8, 256, 0, ix->stream>>>(ix->d_row_ptr, ix->d_col, ix->n, ix->d_head);
   ix->launches++;
   CUDA_TRY(cudaGetLastError());
@@ -555,8 +576,12 @@ static inline uint64_t splitmix64(uint64_t &x) {
 
 static int install_pivots(ngtgpu_index *ix, const std::vector<uint32_t> &ids) {
   const uint32_t n_pivots = (uint32_t)ids.size();
-  CUDA_TRY(cudaMalloc(&ix->d_pivot_ids, n_pivots * sizeof(uint32_t)));
-  CUDA_TRY(cudaMalloc(&ix->d_pivot_rows, (size_t)n_pivots * ix->row_bytes));
+  if (ix->pivot_cap < n_pivots) {
+    free_pivots(ix);
+    CUDA_TRY(cudaMalloc(&ix->d_pivot_ids, n_pivots * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc(&ix->d_pivot_rows, (size_t)n_pivots * ix->row_bytes));
+    ix->pivot_cap = n_pivots;
+  }
   CUDA_TRY(cudaMemcpy(ix->d_pivot_ids, ids.data(), n_pivots * sizeof(uint32_t), cudaMemcpyHostToDevice));
   gather_pivots_kernel<<<ix->sm_count * 4, 256, 0, ix->stream>>>(ix->d_objects, ix->row_bytes, ix->d_pivot_ids,
                                                                  n_pivots, ix->d_pivot_rows);
@@ -577,8 +602,11 @@ extern "C" int ngtgpu_index_build_seed_table_range(ngtgpu_index *ix, uint32_t n_
   NGTGPU_TRY(ngtgpu_check_device(ix));
   if (!ix->d_objects || ix->n == 0) NGTGPU_FAIL(NGTGPU_ERR_STATE, "ngtgpu_index_build_seed_table: objects are not set");
   CUDA_TRY(cudaStreamSynchronize(ix->stream));
-  free_pivots(ix);
-  if (n_pivots == 0) return NGTGPU_OK;
+  ix->n_pivots = 0;   // (the buffers stay: install_pivots reuses them)
+  if (n_pivots == 0) {
+    free_pivots(ix);
+    return NGTGPU_OK;
+  }
   const uint64_t range = (limit == 0 || limit > ix->n) ? ix->n : limit;
   if (n_pivots > range) n_pivots = (uint32_t)range;
   // evenly strided sample with a random phase per stride: distinct ids, spread over the id range
@@ -616,7 +644,7 @@ extern "C" int ngtgpu_index_set_seed_table_ids(ngtgpu_index *ix, const uint32_t 
     if (pivot_ids[i] == 0 || pivot_ids[i] > ix->n)
       NGTGPU_FAIL(NGTGPU_ERR_INVALID, "ngtgpu_index_set_seed_table_ids: id " + std::to_string(pivot_ids[i]) + " out of range");
   CUDA_TRY(cudaStreamSynchronize(ix->stream));
-  free_pivots(ix);
+  ix->n_pivots = 0;
   return install_pivots(ix, std::vector<uint32_t>(pivot_ids, pivot_ids + n_pivots));
 }
 

@@ -106,6 +106,10 @@ struct ngtgpu_index {
   int fast_ctas_per_sm = 0;            // cap on resident CTAs per SM of its first tier (0: what fits)
   bool fast_kernel = true;             // first tier of the common case on search_fast_kernel (off: tests of the general kernel)
   std::atomic<uint64_t> last_overflows{0};   // queries of the last call that fell to the global-memory tier
+  // capacities of the graph / pivot buffers (elements): ngtgpu_index_set_graph and the seed table builders reuse them --
+  // the construction loop sets a graph and a seed table once per batch of 200 objects
+  uint64_t row_ptr_cap = 0, col_cap = 0, head_cap = 0, pivot_cap = 0;
+  const void *graph_source = nullptr;   // caller's device row_ptr the graph was last set from (ngtgpu_index_insert_batch)
   // scratch
   void *d_scratch[SCR_COUNT] = {nullptr};
   size_t scratch_bytes[SCR_COUNT] = {0};
