@@ -138,6 +138,52 @@ __global__ void tc_pack_kernel(const uint8_t *__restrict__ rows, int kind, uint3
   }
 }
 
+// Integer kinds on tcgen05 kind::i8 (u8 x u8 -> s32, exact): one K element per byte (uint8 L2) or per bit (Hamming, 0 / 1),
+// 128 elements per 128-byte swizzle row -- half the bytes of the bf16 image, and an MMA covers K = 32. Products of
+// unsigned bytes only add up, so the row norm rides along as h = (M - ||x||^2) >> 1 >= 0 (M: a bound of all row norms)
+// in a few extra K slots: h = 255 t + r is spread as bytes over `wslots` slots that meet 255 on the query side and one
+// slot that meets 1. The accumulator is then q.x + h, and ||q||^2 + ||x||^2 - 2 q.x = ||q||^2 + M - 2 acc - (parity of
+// M - ||x||^2): one subtraction per thread and a max tree per eight columns decide "nothing here", like the float path.
+// Padding / empty rows: zero bytes, h = 0, integer norm 0x3f000000 (they never become candidates).
+__global__ void tc_pack_i8_kernel(const uint8_t *__restrict__ rows, int kind, uint32_t row_bytes, uint64_t n_rows, uint64_t n_pad,
+                                  uint32_t kdim, uint32_t kchunks, int side, int m_bound, uint32_t wslots,
+                                  const float *__restrict__ norms, int32_t *__restrict__ norms_i, uint8_t *__restrict__ tiles) {
+  const uint64_t units_per_row = (uint64_t)kchunks * 8;
+  const uint64_t total = n_pad * units_per_row;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t row = i / units_per_row;
+    const uint32_t U = (uint32_t)(i % units_per_row);
+    const float nrm = norms[row];
+    const bool live = row < n_rows && nrm < 1.0e9f;
+    const int rn = live ? (int)nrm : 0x3f000000;
+    const uint32_t h = live ? (uint32_t)(m_bound - rn) >> 1 : 0u;
+    const uint32_t t = h / 255u, r = h % 255u;
+    uint8_t v[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      const uint32_t d = U * 16 + j;
+      uint32_t x = 0;
+      if (d < kdim) {
+        if (row < n_rows) {
+          const uint8_t *rp = rows + row * (uint64_t)row_bytes;
+          x = kind == 1 ? rp[d] : ((rp[d >> 3] >> (d & 7)) & 1u);
+        }
+      } else if (d < kdim + wslots) {
+        const uint32_t s = d - kdim;
+        x = side == 0 ? 255u : (t > 255u * s ? (t - 255u * s < 255u ? t - 255u * s : 255u) : 0u);
+      } else if (d == kdim + wslots) {
+        x = side == 0 ? 1u : r;
+      }
+      v[j] = (uint8_t)x;
+    }
+    if (U == 0 && norms_i) norms_i[row] = rn;
+    const uint64_t tile = row / TC_TILE;
+    const uint32_t rr = (uint32_t)(row % TC_TILE), c = U / 8, u = U % 8;
+    uint8_t *dst = tiles + (tile * kchunks + c) * (uint64_t)TC_TILE_BYTES + rr * 128 + ((u ^ (rr & 7)) * 16);
+    *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<const uint4 *>(v);
+  }
+}
+
 // largest finite squared norm of the rows (bounds the filter's error margin per query)
 __global__ void tc_max_norm_kernel(const float *__restrict__ norms, uint64_t n, float *out) {
   float m = 0.f;
@@ -230,6 +276,16 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, ui
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // SWIZZLE_128B, K-major operand tile (rows of 128 bytes, 8-row groups 1024 bytes apart): cute::UMMA::SmemDescriptor
 __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr) {
   uint64_t d = 0;
@@ -284,7 +340,7 @@ struct TcArgs {
   uint64_t n_rows;
   uint32_t kchunks;
   uint32_t k;
-  int mode;                 // 0 L2, 1 dot (normalised kinds), 2 cosine
+  int mode;                 // 0 L2, 1 dot (normalised kinds), 2 cosine, 3 integer L2 / Hamming on kind::i8 (accumulator = q.x, exact)
   float rel_margin;         // error bound of the bf16 product, relative to ||q||^2+||x||^2 (L2) or absolute (similarities)
   float max_row_norm;       // MODE 0: largest ||x||^2, the margin of a query is 2 * rel_margin * (||q||^2 + max_row_norm)
   uint32_t stages;          // ring depth (2..TC_STAGES)
@@ -295,6 +351,8 @@ struct TcArgs {
   uint64_t tiles_per_split;
   uint32_t qgroups;         // query tiles per CTA: 2 (256 queries share every row tile) or 1 when two query operands do not fit
   int stream;               // 1: the query operand does not fit shared memory and streams through the ring with the rows (long K axis)
+  const int32_t *b_norms_i; // MODE 3 (kind::i8): integer squared norms / popcounts of the rows
+  int i8_m;                 // ... and their bound M (see tc_pack_i8_kernel)
   int debug_skip;           // development: 1 = the epilogue only releases the accumulators (timing of the MMA side alone)
   uint32_t cap;             // entries of one (query, split) buffer: a multiple of 32, <= TC_CAND_MAX
   uint2 *cand;              // [nq][nsplit][cap] (score bits, row index 0-based)
@@ -362,9 +420,27 @@ __device__ __noinline__ uint32_t tc_compact(uint2 *buf, uint32_t cnt, uint32_t K
 // instruction-fetch bound: 58 % I-cache hit rate, 6 "no instruction" stall cycles per issue).
 template <int MODE>
 __device__ __noinline__ uint32_t tc_append8(uint4 lo, uint4 hi, float thr, float margin, float qn, uint32_t rbase,
-                                             const float *__restrict__ b_norms, uint2 *buf, uint32_t cnt) {
+                                             const float *__restrict__ b_norms, uint2 *buf, uint32_t cnt, int m_bound) {
   const uint32_t v[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-  if (MODE == 0) {
+  if (MODE == 3) {
+    // v[] are q.x + h (exact integers, h = (M - ||x||^2) >> 1): with the rows' integer norms (`b_norms` carries them here;
+    // `qn` the bits of ||q||^2 as an integer, `margin` unchanged, M in the sign-free upper half of `rbase`'s partner `m_bound`)
+    const float lim = thr + margin;
+    const int4 *rn4 = reinterpret_cast<const int4 *>(reinterpret_cast<const int32_t *>(b_norms) + rbase);
+    const int4 r0 = __ldg(rn4), r1 = __ldg(rn4 + 1);
+    const int rn[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+    const int qn_i = __float_as_int(qn);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const int h = (m_bound - rn[j]) >> 1;
+      const float sc = __int2float_rn((rn[j] + qn_i) - 2 * ((int)v[j] - h));
+      if (rn[j] >= 0x3f000000) continue;   // padding / empty row
+      if (sc <= lim) {
+        __stcg(buf + cnt, make_uint2(__float_as_uint(sc), rbase + j));
+        cnt++;
+      }
+    }
+  } else if (MODE == 0) {
     const float lim = thr + margin;   // the accumulator already is ||q||^2 + ||x||^2 - 2 q.x
 #pragma unroll
     for (int j = 0; j < 8; j++)
@@ -468,7 +544,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_filter_kernel(const TcAr
     // ===================== MMA issuer =====================
     if (ntiles && tc_elect_one()) {
       // kind::f16, A = B = BF16, D = F32, K-major both, N = 128, M = 128 (cute::UMMA::InstrDescriptor)
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+      // (MODE 3: kind::i8, A = B = unsigned 8-bit, D = S32, K = 32 per instruction: the same four 32-byte steps per chunk)
+      const uint32_t idesc = MODE == 3 ? (2u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24)
+                                       : (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
       const uint64_t descA0 = tc_smem_desc(smem_u32(sA)), descB0 = tc_smem_desc(smem_u32(sB));
       if (!a.stream) {
         tc_mbar_wait(&bar_a, 0);
@@ -489,7 +567,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_filter_kernel(const TcAr
               const uint32_t a_at = a.stream ? st * stage_bytes + qg * TC_TILE_BYTES : (qg * a.kchunks + c) * TC_TILE_BYTES;
               const uint64_t da = descA0 + (uint64_t)((a_at + s * 32) >> 4);
               const uint64_t db = descB0 + (uint64_t)((st * stage_bytes + b_off + s * 32) >> 4);
-              tc_mma_bf16(tmem_base + (acc * 2 + qg) * 128, da, db, idesc, (c | s) != 0 ? 1u : 0u);
+              if (MODE == 3) tc_mma_i8(tmem_base + (acc * 2 + qg) * 128, da, db, idesc, (c | s) != 0 ? 1u : 0u);
+              else tc_mma_bf16(tmem_base + (acc * 2 + qg) * 128, da, db, idesc, (c | s) != 0 ? 1u : 0u);
             }
           }
           tc_commit(&bar_empty[st]);   // frees the ring slot when these MMAs have read it
@@ -514,7 +593,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_filter_kernel(const TcAr
     const size_t list = (size_t)(q_ok ? q : 0u) * a.nsplit + split;
     uint2 *mybuf = a.cand + list * a.cap;
     const float m2 = 2.0f * a.rel_margin;
-    const float margin = MODE == 0 ? m2 * (qn + a.max_row_norm) : m2;   // MODE 0: per-query bound of twice the error
+    const float margin = (MODE == 0 || MODE == 3) ? m2 * (qn + a.max_row_norm) : m2;   // L2: per-query bound of twice the error
+    const int qn_i = MODE == 3 ? __float2int_rn(qn) : 0;
+    const int t_i = qn_i + a.i8_m - 1;
     const uint32_t room = a.cap - TC_TILE;            // one tile can add 128 entries
     for (uint64_t t = 0; t < ntiles && g < a.qgroups; t++) {
       const uint32_t acc = (uint32_t)(t & 1);
@@ -537,12 +618,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_filter_kernel(const TcAr
           tc_tmem_wait_ld();
           if (cb + 1 < 4) tc_tmem_ld32(taddr + (cb + 1) * 32, v[(h + 1) & 1]);   // next 32 columns in flight under this block
           const uint32_t(&blk)[32] = v[h];
-          // Most groups of eight columns hold nothing for any of the warp's 32 queries: a min (max) tree and one vote
-          // decide that in a dozen instructions. The threshold is a snapshot (it only shrinks): the tests admit a superset.
+          // Most blocks of 32 columns, and most groups of eight inside the others, hold nothing for any of the warp's 32
+          // queries: a min (max) tree and one vote decide that (the tree over 32 values has the instruction-level
+          // parallelism the four dependent group tests lack). The threshold is a snapshot (it only shrinks): the tests
+          // admit a superset.
+          if (MODE == 0) {
+            if (!__any_sync(0xffffffffu, tc_min32(blk) <= thr + margin)) continue;
+          } else if (MODE == 1) {
+            if (!__any_sync(0xffffffffu, -tc_max32(blk) - margin <= thr)) continue;
+          } else if (MODE == 3) {
+            int m16[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) m16[i] = max((int)blk[2 * i], (int)blk[2 * i + 1]);
+#pragma unroll
+            for (int wd = 8; wd > 0; wd >>= 1)
+#pragma unroll
+              for (int i = 0; i < wd; i++) m16[i] = max(m16[i], m16[i + wd]);
+            if (!__any_sync(0xffffffffu, __int2float_rn(t_i - 2 * m16[0]) <= thr + margin)) continue;
+          }
 #pragma unroll
           for (int c8 = 0; c8 < 4; c8++) {
             bool maybe = true;   // cosine scales every column by its row norm: no cheap bound
-            if (MODE == 0) {
+            uint32_t w[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) w[j] = blk[c8 * 8 + j];
+            if (MODE == 3) {
+              // acc = q.x + h: the score of a column is >= ||q||^2 + M - 1 - 2 acc, so the largest of eight accumulators decides
+              const int mx = max(max(max((int)w[0], (int)w[1]), max((int)w[2], (int)w[3])),
+                                 max(max((int)w[4], (int)w[5]), max((int)w[6], (int)w[7])));
+              maybe = __any_sync(0xffffffffu, __int2float_rn(t_i - 2 * mx) <= thr + margin);
+            } else if (MODE == 0) {
               const float m = fminf(fminf(fminf(__uint_as_float(blk[c8 * 8]), __uint_as_float(blk[c8 * 8 + 1])),
                                           fminf(__uint_as_float(blk[c8 * 8 + 2]), __uint_as_float(blk[c8 * 8 + 3]))),
                                     fminf(fminf(__uint_as_float(blk[c8 * 8 + 4]), __uint_as_float(blk[c8 * 8 + 5])),
@@ -556,9 +661,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_filter_kernel(const TcAr
               maybe = __any_sync(0xffffffffu, -m - margin <= thr);   // score = -dot
             }
             if (maybe)
-              cnt = tc_append8<MODE>(make_uint4(blk[c8 * 8], blk[c8 * 8 + 1], blk[c8 * 8 + 2], blk[c8 * 8 + 3]),
-                                     make_uint4(blk[c8 * 8 + 4], blk[c8 * 8 + 5], blk[c8 * 8 + 6], blk[c8 * 8 + 7]), thr, margin, qn,
-                                     (uint32_t)(row0 + cb * 32 + c8 * 8), a.b_norms, mybuf, cnt);
+              cnt = tc_append8<MODE>(make_uint4(w[0], w[1], w[2], w[3]), make_uint4(w[4], w[5], w[6], w[7]), thr, margin,
+                                     MODE == 3 ? __int_as_float(qn_i) : qn, (uint32_t)(row0 + cb * 32 + c8 * 8),
+                                     MODE == 3 ? reinterpret_cast<const float *>(a.b_norms_i) : a.b_norms, mybuf, cnt, a.i8_m);
           }
         }
       }
@@ -703,17 +808,26 @@ static uint32_t tc_kdim(const ngtgpu_index *ix) {   // K elements per stored row
 static uint32_t tc_kchunks(const ngtgpu_index *ix, uint32_t nseg, int fold) {
   return (nseg * tc_kdim(ix) + TC_KCHUNK - 1) / TC_KCHUNK + (fold ? 1 : 0);
 }
+// kind::i8: one byte per element, + the slots that carry (M - norm) / 2 (tc_pack_i8_kernel): wslots of weight 255, one of weight 1
+static uint32_t tc_i8_wslots(int m_bound) { return (uint32_t)(((uint64_t)(m_bound / 2) / 255 + 254) / 255); }
+static uint32_t tc_kchunks_i8(const ngtgpu_index *ix, uint32_t wslots) { return (tc_kdim(ix) + wslots + 1 + 127) / 128; }
 
 // rows are padded (zeros, norm +inf) to a multiple of `pad_rows`
 static int tc_pack(ngtgpu_index *ix, const uint8_t *d_rows, uint64_t n_rows, uint32_t pad_rows, int side, uint32_t nseg, int fold,
-                   uint32_t first_id, const uint8_t *d_valid, uint8_t *tiles, float *norms, cudaStream_t stream) {
-  const uint32_t kchunks = tc_kchunks(ix, nseg, fold);
+                   uint32_t first_id, const uint8_t *d_valid, uint8_t *tiles, float *norms, cudaStream_t stream,
+                   int i8 = 0, int32_t *norms_i = nullptr, bool norms_done = false) {
+  const uint32_t kchunks = i8 ? tc_kchunks_i8(ix, (uint32_t)ix->tc_i8_w) : tc_kchunks(ix, nseg, fold);
   const uint64_t n_pad = (n_rows + pad_rows - 1) / pad_rows * pad_rows;
   uint64_t total = n_pad * kchunks * 8;
   unsigned blocks = (unsigned)((total + 255) / 256 > (uint64_t)ix->sm_count * 64 ? (uint64_t)ix->sm_count * 64 : (total + 255) / 256);
-  tc_norms_kernel<<<ix->sm_count * 8, 256, 0, stream>>>(d_rows, tc_kind(ix), ix->row_bytes, n_rows, n_pad, tc_kdim(ix), first_id, d_valid, norms);
+  if (!norms_done)
+    tc_norms_kernel<<<ix->sm_count * 8, 256, 0, stream>>>(d_rows, tc_kind(ix), ix->row_bytes, n_rows, n_pad, tc_kdim(ix), first_id, d_valid, norms);
   CUDA_TRY(cudaGetLastError());
-  tc_pack_kernel<<<blocks, 256, 0, stream>>>(d_rows, tc_kind(ix), ix->row_bytes, n_rows, n_pad, tc_kdim(ix), side, nseg, kchunks, fold, norms, tiles);
+  if (i8)
+    tc_pack_i8_kernel<<<blocks, 256, 0, stream>>>(d_rows, tc_kind(ix), ix->row_bytes, n_rows, n_pad, tc_kdim(ix), kchunks, side, ix->tc_i8_m,
+                                                  (uint32_t)ix->tc_i8_w, norms, norms_i, tiles);
+  else
+    tc_pack_kernel<<<blocks, 256, 0, stream>>>(d_rows, tc_kind(ix), ix->row_bytes, n_rows, n_pad, tc_kdim(ix), side, nseg, kchunks, fold, norms, tiles);
   CUDA_TRY(cudaGetLastError());
   ix->launches += 2;
   return NGTGPU_OK;
@@ -754,25 +868,46 @@ int ngtgpu_scan_topk_tc(ngtgpu_index *ix, const ScanParams &p, cudaStream_t stre
     bool exact = integer_kind || all_bf16_exact(ix, reinterpret_cast<const float *>(rows), p.n_rows * ix->padded_dim, d_flag, stream, &rc);
     if (rc != NGTGPU_OK) return rc;
     uint32_t nseg = exact ? 1 : 3;
-    const int fold = (ix->acc_kind == ACC_F_L2 || integer_kind) ? 1 : 0;   // L2 (and Hamming = L2 of bits): norms ride in the GEMM
-    const uint32_t kchunks = tc_kchunks(ix, nseg, fold);
+    // integer kinds: u8 x u8 -> s32 on tcgen05 kind::i8 (NGTGPU_TC_I8=0: the bf16 image instead, for comparison)
+    const char *i8_env = getenv("NGTGPU_TC_I8");
+    const int i8 = integer_kind && !(i8_env && atoi(i8_env) == 0) ? 1 : 0;
+    const int fold = i8 ? 0 : (ix->acc_kind == ACC_F_L2 || integer_kind) ? 1 : 0;   // L2 (and Hamming = L2 of bits): norms ride in the GEMM
     const uint64_t n_tiles = (p.n_rows + TC_TILE - 1) / TC_TILE;
     if (ix->d_tc_tiles) cudaFree(ix->d_tc_tiles);
     if (ix->d_tc_norms) cudaFree(ix->d_tc_norms);
     ix->d_tc_tiles = nullptr;
     ix->d_tc_norms = nullptr;
-    CUDA_TRY(cudaMalloc(&ix->d_tc_tiles, n_tiles * kchunks * (size_t)TC_TILE_BYTES));
-    CUDA_TRY(cudaMalloc(&ix->d_tc_norms, (n_tiles * TC_TILE + 64) * sizeof(float)));
-    NGTGPU_TRY(tc_pack(ix, rows, p.n_rows, TC_TILE, 1, nseg, fold, p.first_row_id, p.d_valid, ix->d_tc_tiles, ix->d_tc_norms, stream));
+    // float norms, the largest of them, and (kind::i8) the integer norms behind
+    CUDA_TRY(cudaMalloc(&ix->d_tc_norms, (n_tiles * TC_TILE + 64) * sizeof(float) + (i8 ? n_tiles * TC_TILE * sizeof(int32_t) : 0)));
     float *d_max = ix->d_tc_norms + n_tiles * TC_TILE;
-    CUDA_TRY(cudaMemsetAsync(d_max, 0, sizeof(float), stream));
-    tc_max_norm_kernel<<<ix->sm_count * 4, 256, 0, stream>>>(ix->d_tc_norms, n_tiles * TC_TILE, d_max);
-    ix->launches++;
-    CUDA_TRY(cudaMemcpyAsync(&ix->tc_max_norm, d_max, sizeof(float), cudaMemcpyDeviceToHost, stream));
+    if (i8) {
+      // the norms and their bound come first: the bound decides how many K slots the rows' images carry
+      tc_norms_kernel<<<ix->sm_count * 8, 256, 0, stream>>>(rows, tc_kind(ix), ix->row_bytes, p.n_rows, n_tiles * TC_TILE, tc_kdim(ix),
+                                                            p.first_row_id, p.d_valid, ix->d_tc_norms);
+      CUDA_TRY(cudaMemsetAsync(d_max, 0, sizeof(float), stream));
+      tc_max_norm_kernel<<<ix->sm_count * 4, 256, 0, stream>>>(ix->d_tc_norms, n_tiles * TC_TILE, d_max);
+      ix->launches += 2;
+      CUDA_TRY(cudaMemcpyAsync(&ix->tc_max_norm, d_max, sizeof(float), cudaMemcpyDeviceToHost, stream));
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      if (!(ix->tc_max_norm < 1.0e9f)) return NGTGPU_OK;   // (norms beyond 2^30: the CUDA-core scan)
+      ix->tc_i8_m = (int)ix->tc_max_norm + 2;              // >= every truncated norm
+      ix->tc_i8_w = (int)tc_i8_wslots(ix->tc_i8_m);
+    }
+    const uint32_t kchunks = i8 ? tc_kchunks_i8(ix, (uint32_t)ix->tc_i8_w) : tc_kchunks(ix, nseg, fold);
+    CUDA_TRY(cudaMalloc(&ix->d_tc_tiles, n_tiles * kchunks * (size_t)TC_TILE_BYTES));
+    NGTGPU_TRY(tc_pack(ix, rows, p.n_rows, TC_TILE, 1, nseg, fold, p.first_row_id, p.d_valid, ix->d_tc_tiles, ix->d_tc_norms, stream, i8,
+                       i8 ? reinterpret_cast<int32_t *>(ix->d_tc_norms + n_tiles * TC_TILE + 64) : nullptr, i8 != 0));
+    if (!i8) {
+      CUDA_TRY(cudaMemsetAsync(d_max, 0, sizeof(float), stream));
+      tc_max_norm_kernel<<<ix->sm_count * 4, 256, 0, stream>>>(ix->d_tc_norms, n_tiles * TC_TILE, d_max);
+      ix->launches++;
+      CUDA_TRY(cudaMemcpyAsync(&ix->tc_max_norm, d_max, sizeof(float), cudaMemcpyDeviceToHost, stream));
+    }
     CUDA_TRY(cudaStreamSynchronize(stream));
     ix->tc_nseg = nseg;
     ix->tc_kchunks = kchunks;
     ix->tc_fold = fold;
+    ix->tc_i8 = i8;
     ix->tc_rows_valid = true;
   }
   uint32_t nseg = ix->tc_nseg;
@@ -794,10 +929,11 @@ int ngtgpu_scan_topk_tc(ngtgpu_index *ix, const ScanParams &p, cudaStream_t stre
   const uint32_t qtiles = qtiles128 / qgroups;                                                   // CTAs per split
   uint8_t *a_tiles = nullptr;
   float *a_norms = nullptr;
-  NGTGPU_TRY(ngtgpu_scratch(ix, SCR_TC_QUERY, (size_t)qtiles128 * kchunks * TC_TILE_BYTES + (size_t)qtiles128 * TC_TILE * 4, (void **)&a_tiles));
+  NGTGPU_TRY(ngtgpu_scratch(ix, SCR_TC_QUERY, (size_t)qtiles128 * kchunks * TC_TILE_BYTES + (size_t)qtiles128 * TC_TILE * 8, (void **)&a_tiles));
   a_norms = reinterpret_cast<float *>(a_tiles + (size_t)qtiles128 * kchunks * TC_TILE_BYTES);
-  NGTGPU_TRY(tc_pack(ix, qrows, p.nq, TC_TILE * qgroups, 0, nseg, ix->tc_fold, 0, nullptr, a_tiles, a_norms, stream));
+  NGTGPU_TRY(tc_pack(ix, qrows, p.nq, TC_TILE * qgroups, 0, nseg, ix->tc_fold, 0, nullptr, a_tiles, a_norms, stream, ix->tc_i8, nullptr));
 
+  const uint64_t total_tiles_for_norms = (p.n_rows + TC_TILE - 1) / TC_TILE;
   TcArgs a;
   memset(&a, 0, sizeof(a));
   a.a_tiles = a_tiles;
@@ -808,7 +944,9 @@ int ngtgpu_scan_topk_tc(ngtgpu_index *ix, const ScanParams &p, cudaStream_t stre
   a.n_rows = p.n_rows;
   a.kchunks = kchunks;
   a.k = p.k;
-  a.mode = (ix->acc_kind == ACC_F_L2 || integer_kind) ? 0 : ix->acc_kind == ACC_F_DOT ? 1 : 2;
+  a.mode = ix->tc_i8 ? 3 : (ix->acc_kind == ACC_F_L2 || integer_kind) ? 0 : ix->acc_kind == ACC_F_DOT ? 1 : 2;
+  a.b_norms_i = ix->tc_i8 ? reinterpret_cast<const int32_t *>(ix->d_tc_norms + total_tiles_for_norms * TC_TILE + 64) : nullptr;
+  a.i8_m = ix->tc_i8_m;
   // split floats: the dropped lo x lo products (2^-16) and the bf16 rounding of the lo parts, plus fp32 accumulation over
   // the K axis, which grows with its length
   a.rel_margin = nseg == 1 ? 4.0e-6f : std::max(1.0e-4f, 6.0e-8f * (float)(kchunks * TC_KCHUNK));
@@ -850,7 +988,10 @@ int ngtgpu_scan_topk_tc(ngtgpu_index *ix, const ScanParams &p, cudaStream_t stre
   if (fixed_smem + (size_t)stages * stage_bytes > 225 * 1024) return NGTGPU_OK;
   a.stages = stages;
   const size_t smem = fixed_smem + (size_t)stages * stage_bytes;
-  if (a.mode == 0) {
+  if (a.mode == 3) {
+    CUDA_TRY(cudaFuncSetAttribute(knn_tc_filter_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    knn_tc_filter_kernel<3><<<qtiles * a.nsplit, TC_THREADS, smem, stream>>>(a);
+  } else if (a.mode == 0) {
     CUDA_TRY(cudaFuncSetAttribute(knn_tc_filter_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     knn_tc_filter_kernel<0><<<qtiles * a.nsplit, TC_THREADS, smem, stream>>>(a);
   } else if (a.mode == 1) {

@@ -127,6 +127,8 @@ struct ngtgpu_index {
   float *d_tc_norms = nullptr;
   uint32_t tc_nseg = 0, tc_kchunks = 0;
   int tc_fold = 0;                     // L2: squared norms folded into the GEMM as an extra k-chunk
+  int tc_i8 = 0;                       // integer kinds: u8 x u8 -> s32 operands (tcgen05 kind::i8)
+  int tc_i8_m = 0, tc_i8_w = 0;        // ... bound of the integer row norms, and the K slots that carry (bound - norm) / 2
   float tc_max_norm = 0.f;
   uint64_t tc_batches = 0;             // batches answered by the tensor-core path
   uint32_t *d_prof = nullptr;          // development aid: per-phase cycle counters of the traversal kernel
