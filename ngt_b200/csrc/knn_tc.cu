@@ -8,7 +8,8 @@
 // fp32 operands are split into bf16 parts, x = hi + lo, and the three products that matter are obtained from
 // ONE bf16 GEMM over a concatenated K axis:  A' = [q_hi | q_hi | q_lo],  B' = [x_hi | x_lo | x_hi]
 // (q_lo.x_lo, relative 2^-16, is dropped). When every value is exactly a bf16 number (SIFT-like integer
-// data) a single segment is used and the products are exact.
+// data) a single segment is used and the products are exact. uint8 and Hamming objects go through kind::i8 as bytes
+// (u8 x u8 -> s32, exact; tc_pack_i8_kernel for how the norms ride along).
 //
 // The tensor cores only FILTER. Each epilogue thread owns one query (one TMEM lane) and a buffer of (score, row) pairs
 // in global memory (L2-resident): a row whose approximate score is within an error margin of the query's running
