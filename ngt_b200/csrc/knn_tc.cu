@@ -47,7 +47,17 @@
 #define TC_TILE_BYTES (TC_TILE * TC_KCHUNK * 2)   // 16 KB: one operand tile of one k-chunk
 #define TC_STAGES 10
 #define TC_MAX_K 128
-#define TC_EPI_WARPS 8          // two groups of four: group g takes the tiles whose accumulator is g
+// Epilogue warps: four (one per 32 TMEM lanes) per query tile and per column half. TC_HALVES = 1: a thread owns one query
+// and all 128 columns of a row tile. TC_HALVES = 2 (a thread owns 64 columns, with a candidate buffer and a threshold of
+// its own; sixteen epilogue warps) was measured SLOWER on every shape -- uint8 1M 0.434 -> 0.487 s, float 128-d 0.544 ->
+// 0.649 s, 960-d 0.54 -> 0.67 s: two thresholds per query admit more candidates, and the accumulator read-back was not
+// waiting for warps.
+#ifndef TC_HALVES
+#define TC_HALVES 1
+#endif
+#define TC_EPI_WARPS (8 * TC_HALVES)
+#define TC_COLS (128 / TC_HALVES)              // accumulator columns per epilogue thread and row tile
+#define TC_BLK (TC_HALVES == 1 ? 32 : 16)      // columns per tcgen05.ld
 #define TC_THREADS ((TC_EPI_WARPS + 2) * 32)
 #define TC_CAND_MAX 512        // largest (score, row) buffer per (query, split): 16 entries per lane during a compaction
 
@@ -308,29 +318,51 @@ __device__ __forceinline__ void tc_tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) 
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
 }
-__device__ __forceinline__ void tc_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// min / max of 32 values as a tree (five dependent levels instead of a chain of 32)
-__device__ __forceinline__ float tc_min32(const uint32_t (&v)[32]) {
-  float m[16];
+__device__ __forceinline__ void tc_tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_tmem_ld(uint32_t taddr, uint32_t (&v)[32]) { tc_tmem_ld32(taddr, v); }
+__device__ __forceinline__ void tc_tmem_ld(uint32_t taddr, uint32_t (&v)[16]) { tc_tmem_ld16(taddr, v); }
+// extremes of a block of N values as trees (log depth instead of a chain)
+template <int N>
+__device__ __forceinline__ float tc_fmin(const uint32_t (&v)[N]) {
+  float m[N / 2];
 #pragma unroll
-  for (int i = 0; i < 16; i++) m[i] = fminf(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+  for (int i = 0; i < N / 2; i++) m[i] = fminf(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
 #pragma unroll
-  for (int w = 8; w > 0; w >>= 1)
+  for (int w = N / 4; w > 0; w >>= 1)
 #pragma unroll
     for (int i = 0; i < w; i++) m[i] = fminf(m[i], m[i + w]);
   return m[0];
 }
-__device__ __forceinline__ float tc_max32(const uint32_t (&v)[32]) {
-  float m[16];
+template <int N>
+__device__ __forceinline__ float tc_fmax(const uint32_t (&v)[N]) {
+  float m[N / 2];
 #pragma unroll
-  for (int i = 0; i < 16; i++) m[i] = fmaxf(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+  for (int i = 0; i < N / 2; i++) m[i] = fmaxf(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
 #pragma unroll
-  for (int w = 8; w > 0; w >>= 1)
+  for (int w = N / 4; w > 0; w >>= 1)
 #pragma unroll
     for (int i = 0; i < w; i++) m[i] = fmaxf(m[i], m[i + w]);
   return m[0];
 }
-
+template <int N>
+__device__ __forceinline__ int tc_imax(const uint32_t (&v)[N]) {
+  int m[N / 2];
+#pragma unroll
+  for (int i = 0; i < N / 2; i++) m[i] = max((int)v[2 * i], (int)v[2 * i + 1]);
+#pragma unroll
+  for (int w = N / 4; w > 0; w >>= 1)
+#pragma unroll
+    for (int i = 0; i < w; i++) m[i] = max(m[i], m[i + w]);
+  return m[0];
+}
+__device__ __forceinline__ void tc_tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // ---- the filter kernel ------------------------------------------------------------------------------------
 struct TcArgs {
   const uint8_t *a_tiles;   // packed query operand  [q_tiles][kchunks][16 KB]
@@ -503,7 +535,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_filter_kernel(const TcAr
     tc_mbar_init(&bar_a, 1);
     for (int i = 0; i < 2; i++) {
       tc_mbar_init(&bar_tfull[i], 1);
-      tc_mbar_init(&bar_tempty[i], 128 * a.qgroups);
+      tc_mbar_init(&bar_tempty[i], 128 * TC_HALVES * a.qgroups);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -579,8 +611,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_filter_kernel(const TcAr
     }
   } else {
     // ===================== epilogue: one query per thread =====================
-    const uint32_t g = (uint32_t)warp >> 2;            // query group: warps 0-3 the CTA's first query tile, 4-7 its second
-    const uint32_t qlane = (uint32_t)tid & 127u;       // TMEM lane == query of the tile
+    const uint32_t g = ((uint32_t)warp >> 2) & 1u;     // query group: the CTA's first / second query tile
+    const uint32_t half = (uint32_t)warp >> 3;         // which TC_COLS columns of every row tile
+    const uint32_t qlane = (uint32_t)tid & 127u;       // TMEM lane == query of the tile (warp w reads lanes 32 (w % 4) ..)
     const uint32_t q = (qtile * a.qgroups + g) * TC_TILE + qlane;
     const bool q_ok = q < a.nq && g < a.qgroups;
     const float qn = g < a.qgroups ? a.a_norms[(size_t)(qtile * a.qgroups + g) * TC_TILE + qlane] : 0.f;
@@ -591,13 +624,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_filter_kernel(const TcAr
     float thr = q_ok ? 1.0e37f : -__int_as_float(0x7f800000);
     uint32_t cnt = 0;
     bool bad = false;
-    const size_t list = (size_t)(q_ok ? q : 0u) * a.nsplit + split;
+    const size_t list = ((size_t)(q_ok ? q : 0u) * a.nsplit + split) * TC_HALVES + half;
     uint2 *mybuf = a.cand + list * a.cap;
     const float m2 = 2.0f * a.rel_margin;
     const float margin = (MODE == 0 || MODE == 3) ? m2 * (qn + a.max_row_norm) : m2;   // L2: per-query bound of twice the error
     const int qn_i = MODE == 3 ? __float2int_rn(qn) : 0;
     const int t_i = qn_i + a.i8_m - 1;
-    const uint32_t room = a.cap - TC_TILE;            // one tile can add 128 entries
+    const uint32_t room = a.cap - TC_COLS;            // one tile can add TC_COLS entries
     for (uint64_t t = 0; t < ntiles && g < a.qgroups; t++) {
       const uint32_t acc = (uint32_t)(t & 1);
       tc_mbar_wait(&bar_tfull[acc], (uint32_t)((t >> 1) & 1));
@@ -607,38 +640,31 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_filter_kernel(const TcAr
         tc_mbar_arrive(&bar_tempty[acc]);
         continue;
       }
-      const uint64_t row0 = (t_begin + t) * TC_TILE;
-      const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (acc * 2 + g) * 128;
-      uint32_t v[2][32];
-      tc_tmem_ld32(taddr, v[0]);
+      const uint64_t row0 = (t_begin + t) * TC_TILE + half * TC_COLS;
+      const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (acc * 2 + g) * 128 + half * TC_COLS;
+      uint32_t v[2][TC_BLK];
+      tc_tmem_ld(taddr, v[0]);
 #pragma unroll 1
       for (uint32_t cbp = 0; cbp < 2; cbp++) {
 #pragma unroll
         for (int h = 0; h < 2; h++) {
           const uint32_t cb = cbp * 2 + h;
           tc_tmem_wait_ld();
-          if (cb + 1 < 4) tc_tmem_ld32(taddr + (cb + 1) * 32, v[(h + 1) & 1]);   // next 32 columns in flight under this block
-          const uint32_t(&blk)[32] = v[h];
+          if (cb + 1 < 4) tc_tmem_ld(taddr + (cb + 1) * TC_BLK, v[(h + 1) & 1]);   // the next block in flight under this one
+          const uint32_t(&blk)[TC_BLK] = v[h];
           // Most blocks of 32 columns, and most groups of eight inside the others, hold nothing for any of the warp's 32
           // queries: a min (max) tree and one vote decide that (the tree over 32 values has the instruction-level
           // parallelism the four dependent group tests lack). The threshold is a snapshot (it only shrinks): the tests
           // admit a superset.
           if (MODE == 0) {
-            if (!__any_sync(0xffffffffu, tc_min32(blk) <= thr + margin)) continue;
+            if (!__any_sync(0xffffffffu, tc_fmin<TC_BLK>(blk) <= thr + margin)) continue;
           } else if (MODE == 1) {
-            if (!__any_sync(0xffffffffu, -tc_max32(blk) - margin <= thr)) continue;
+            if (!__any_sync(0xffffffffu, -tc_fmax<TC_BLK>(blk) - margin <= thr)) continue;
           } else if (MODE == 3) {
-            int m16[16];
-#pragma unroll
-            for (int i = 0; i < 16; i++) m16[i] = max((int)blk[2 * i], (int)blk[2 * i + 1]);
-#pragma unroll
-            for (int wd = 8; wd > 0; wd >>= 1)
-#pragma unroll
-              for (int i = 0; i < wd; i++) m16[i] = max(m16[i], m16[i + wd]);
-            if (!__any_sync(0xffffffffu, __int2float_rn(t_i - 2 * m16[0]) <= thr + margin)) continue;
+            if (!__any_sync(0xffffffffu, __int2float_rn(t_i - 2 * tc_imax<TC_BLK>(blk)) <= thr + margin)) continue;
           }
 #pragma unroll
-          for (int c8 = 0; c8 < 4; c8++) {
+          for (int c8 = 0; c8 < TC_BLK / 8; c8++) {
             bool maybe = true;   // cosine scales every column by its row norm: no cheap bound
             uint32_t w[8];
 #pragma unroll
@@ -663,7 +689,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) knn_tc_filter_kernel(const TcAr
             }
             if (maybe)
               cnt = tc_append8<MODE>(make_uint4(w[0], w[1], w[2], w[3]), make_uint4(w[4], w[5], w[6], w[7]), thr, margin,
-                                     MODE == 3 ? __int_as_float(qn_i) : qn, (uint32_t)(row0 + cb * 32 + c8 * 8),
+                                     MODE == 3 ? __int_as_float(qn_i) : qn, (uint32_t)(row0 + cb * TC_BLK + c8 * 8),
                                      MODE == 3 ? reinterpret_cast<const float *>(a.b_norms_i) : a.b_norms, mybuf, cnt, a.i8_m);
           }
         }
@@ -967,12 +993,12 @@ int ngtgpu_scan_topk_tc(ngtgpu_index *ix, const ScanParams &p, cudaStream_t stre
   a.nsplit = (uint32_t)((total_tiles + a.tiles_per_split - 1) / a.tiles_per_split);
   // (score, row) buffers: room for K entries, the rows inside the margin and one more block of 32 columns
   const uint32_t K = p.k + (p.exclude_self ? 1u : 0u);
-  uint32_t cap = (K + TC_TILE + 96 + 31u) & ~31u;
+  uint32_t cap = (K + TC_COLS + 96 + 31u) & ~31u;
   if (cap > TC_CAND_MAX) cap = TC_CAND_MAX;
   a.cap = cap;
   a.debug_skip = getenv("NGTGPU_TC_SKIP_EPILOGUE") ? 1 : 0;
   uint8_t *cand_raw = nullptr;
-  const size_t n_lists = (size_t)p.nq * a.nsplit;
+  const size_t n_lists = (size_t)p.nq * a.nsplit * TC_HALVES;
   const size_t list_bytes = n_lists * cap * sizeof(uint2);
   NGTGPU_TRY(ngtgpu_scratch(ix, SCR_TC_CAND, list_bytes + (n_lists + 4) * 4, (void **)&cand_raw));
   a.cand = reinterpret_cast<uint2 *>(cand_raw);
@@ -1013,7 +1039,7 @@ int ngtgpu_scan_topk_tc(ngtgpu_index *ix, const ScanParams &p, cudaStream_t stre
   r.chunks = ix->chunks;
   r.nq = p.nq;
   r.k = p.k;
-  r.nsplit = a.nsplit;
+  r.nsplit = a.nsplit * TC_HALVES;
   r.first_row_id = p.first_row_id;
   r.id_map = nullptr;
   r.radius = p.radius;
