@@ -506,6 +506,8 @@ def run_workload(spec, a, dev, rank, world, lib):
                      "n_dist_per_query_rank0": round(float(st[:, 0].mean()), 1), "n_edge_per_query_rank0": round(float(st[:, 1].mean()), 1)},
         "knn_pass": {"k": spec["knn"], "seconds_max_over_ranks": round(knn_s, 2), "useful_tflops_per_gpu": round(tf, 1),
                      "frac_of_bf16_sustained": round(tf / bf_sus, 4), "bf16_tflops_sustained": bf_sus,
+                     "operands": ("u8 x u8 -> s32 on tcgen05 kind::i8 (its dense rate is twice the bf16 one the fraction is quoted against)"
+                                  if spec["kind"] in ("u8", "ham") else "bf16 (split floats: three segments) on tcgen05 kind::f16"),
                      "tensor_core_batches_rank0": "%d of %d" % (tc_batches, n_batches)},
         "setup_s_max_over_ranks": {"objects": round(float(red[7]), 2), "knn_pass": round(knn_s, 2), "onng": round(float(red[6]), 2)},
         "epsilon_sweep": curve,
