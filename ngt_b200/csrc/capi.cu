@@ -131,6 +131,7 @@ struct CapiIndex {
   ngtgpu_sharded *sharded = nullptr;   // opened over several GPUs (NGTGPU_DEVICES / ngt_open_index_sharded): read-only
   size_t pending = 0;              // appended since the last build
   size_t raw_from = 0;             // first id whose row is not normalised yet (Normalized* types)
+  uint64_t num_dist = 0;           // distance computations of the single-query searches so far (SearchContainer::distanceComputationCount)
   size_t record_bytes() const { return (size_t)prop.dimension * (prop.object_type == NGTGPU_OBJECT_UINT8 ? 1 : 4); }
   size_t n() const { return present.empty() ? 0 : present.size() - 1; }
 };
@@ -616,7 +617,11 @@ void search_one(CapiIndex &ix, const float *q, int32_t dim, size_t size, float e
   uint32_t seeds = (uint32_t)prf_long(ix, "SeedSize", 10);
   if (seeds == 0) seeds = 10;
   if (ix.sharded) check(ngtgpu_sharded_search(ix.sharded, q, NGTGPU_OBJECT_FLOAT, 1, &p, seeds, ids.data(), ds.data(), cnt.data()));
-  else check(ngtgpu_search(ix.gpu, q, NGTGPU_OBJECT_FLOAT, 1, &p, nullptr, seeds, ids.data(), ds.data(), cnt.data(), nullptr));
+  else {
+    uint32_t stats[3] = {0, 0, 0};   // {distance computations, adjacency entries, expansions}: Graph.cpp:592,604
+    check(ngtgpu_search(ix.gpu, q, NGTGPU_OBJECT_FLOAT, 1, &p, nullptr, seeds, ids.data(), ds.data(), cnt.data(), stats));
+    __atomic_fetch_add(&ix.num_dist, (uint64_t)stats[0], __ATOMIC_RELAXED);   // searches may run concurrently on one index
+  }
   fill_results(results, ids.data(), ds.data(), cnt[0]);
 }
 
@@ -852,6 +857,8 @@ SET_DISTANCE(ngt_set_property_distance_type_jaccard, 7)
 SET_DISTANCE(ngt_set_property_distance_type_cosine, NGTGPU_DISTANCE_COSINE)
 SET_DISTANCE(ngt_set_property_distance_type_normalized_angle, NGTGPU_DISTANCE_NORMALIZED_ANGLE)
 SET_DISTANCE(ngt_set_property_distance_type_normalized_cosine, NGTGPU_DISTANCE_NORMALIZED_COSINE)
+// additive (include/ngt_capi_ext.h): Capi.h:86-104 has no setter for DistanceTypeNormalizedL2, ngtpy.create takes it
+SET_DISTANCE(ngt_set_property_distance_type_normalized_l2, NGTGPU_DISTANCE_NORMALIZED_L2)
 
 // ---- index life cycle, Capi.cpp:40-111, 694-711 ------------------------------------------------------------
 NGTIndex ngt_open_index(const char *index_path, NGTError error) {
@@ -1535,6 +1542,26 @@ bool ngt_optimizer_set_processing_modes(NGTOptimizer optimizer, bool searchParam
   return true;
 }
 void ngt_destroy_optimizer(NGTOptimizer optimizer) { delete static_cast<CapiOptimizer *>(optimizer); }
+
+// ---- additive, for the ngtpy module (csrc/ngtpy.cpp; declared in include/ngt_capi_ext.h) -----------------------
+// GraphOptimizer::shortcutReduction (GraphOptimizer.h:73, set through setProcessingModes :640-650): Capi.h's
+// ngt_optimizer_set_processing_modes carries the three tuning flags only, ngtpy's set_processing_modes has this one too.
+bool ngt_optimizer_set_shortcut_reduction(NGTOptimizer optimizer, bool shortcutReduction, NGTError error) {
+  OPT_CHECK(false)
+  static_cast<CapiOptimizer *>(optimizer)->shortcut_reduction = shortcutReduction;
+  return true;
+}
+// Sum of SearchContainer::distanceComputationCount (Graph.cpp:592) over the single-query searches this handle served:
+// what ngtpy.Index.get_num_of_distance_computations accumulates (python/src/ngtpy.cpp:181,349).
+uint64_t ngt_get_number_of_distance_computations(NGTIndex index, NGTError error) {
+  if (index == NULL) {
+    std::stringstream ss;
+    ss << "Capi : " << __FUNCTION__ << "() : parametor error: index = " << index;
+    operate_error_string(ss, error);
+    return 0;
+  }
+  return __atomic_load_n(&static_cast<CapiIndex *>(index)->num_dist, __ATOMIC_RELAXED);
+}
 
 // Capi.cpp:1043-1058: the defaults of GraphOptimizer::ANNGEdgeOptimizationParameter (GraphOptimizer.h:28-36)
 NGTAnngEdgeOptimizationParameter ngt_get_anng_edge_optimization_parameter() {

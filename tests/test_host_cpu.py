@@ -31,6 +31,55 @@ def test_c_abi_exports_every_declared_symbol():
         assert name in _lib.SYMBOLS and name in declared
 
 
+def test_additive_capi_header_symbols_are_exported():
+    """include/ngt_capi_ext.h: the `ngt_*` entry points the library adds to lib/NGT/Capi.h's 67."""
+    from ngt_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "ngt_capi_ext.h")).read()
+    declared = set(re.findall(r"^(?:bool|NGTIndex|uint64_t)\s+(ngt_[a-z0-9_]+)\(", header, re.M))
+    assert len(declared) == 8, sorted(declared)
+    lib = C.CDLL(_lib.SO_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), "libngtgpu.so does not export %s" % name
+
+
+def test_ngtpy_module_has_the_reference_surface():
+    """ngt_b200/ngtpy.*.so (csrc/ngtpy.cpp): every function and method of the reference's pybind11 module
+    (python/src/ngtpy.cpp:500-607) is there with the same signature line -- names, keyword arguments, defaults --
+    recorded from the reference's own build (tests/golden/ngtpy_surface.json, make_golden_ngtpy.py). QuantizedIndex
+    (NGTQG, outside the hot path) exists and refuses loudly. No compute here: this container has no GPU."""
+    import json
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    sys.path.insert(0, os.path.join(ROOT, "ngt_b200"))
+    try:
+        import ngtpy
+        from make_golden_ngtpy import surface
+    finally:
+        del sys.path[:2]
+    assert ngtpy.__file__.startswith(os.path.join(ROOT, "ngt_b200"))
+    ours = surface(ngtpy)
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "ngtpy_surface.json")))
+    checked = 0
+    for name, line in ref.items():
+        if name.startswith("QuantizedIndex.") and name != "QuantizedIndex.__init__":
+            continue
+        assert ours.get(name) == line, name
+        checked += 1
+    assert checked == 24
+    assert "Index.batch_search" in ours and "Index.batch_linear_search" in ours          # additive (SURVEY.md section 8b)
+    with pytest.raises(RuntimeError, match="PropertySet::load: Cannot load the property file /nonexistent/idx/prf."):
+        ngtpy.Index("/nonexistent/idx")
+    with pytest.raises(RuntimeError, match="outside the hot path"):
+        ngtpy.QuantizedIndex("/nonexistent/idx")
+    with pytest.raises(RuntimeError, match="invalid distance type"):
+        ngtpy.create("/tmp/ngtpy-never-made", 8, distance_type="Chebyshev")
+    o = ngtpy.Optimizer(log_disabled=True)
+    o.set(num_of_outgoings=5, num_of_incomings=20)
+    o.set_processing_modes(shortcut_reduction=False)
+    with pytest.raises(RuntimeError, match="outside the hot path"):
+        o.optimize_search_parameters("/nonexistent/idx")
+
+
 def test_no_device_is_an_error_not_a_fallback():
     """Without a CUDA device every entry point fails loudly (this container has no GPU)."""
     import torch
