@@ -3,6 +3,7 @@
 oracle/Makefile into oracle/_ref/ngtpy/):
   ngtpy_surface.json   the pybind11 signature line of every function and method (names, keyword arguments, defaults)
   ngtpy_scenario.json  what tests/ngtpy_scenario.py returns when it runs on the reference's module
+  ngtpy_sample.txt     what the reference's own python/sample/sample.py prints on the reference's module
     python tests/golden/make_golden_ngtpy.py
 """
 import json
@@ -49,5 +50,13 @@ if __name__ == "__main__":
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
     json.dump(rec, open(os.path.join(OUT, "ngtpy_scenario.json"), "w"))
+    tmp = tempfile.mkdtemp(prefix="ngt-golden-ngtpy-")
+    try:
+        done = ngtpy_scenario.run_reference_sample(os.path.join(ROOT, "oracle", "_ref", "ngtpy"), OUT, tmp,
+                                                   os.path.join(ROOT, "oracle", "_ref", "python", "sample", "sample.py"))
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    assert done.returncode == 0, done.stderr
+    open(os.path.join(OUT, "ngtpy_sample.txt"), "w").write(done.stdout)
     print({k: (list(v) if isinstance(v, dict) else v) for k, v in rec.items()})
     print(os.path.getsize(os.path.join(OUT, "ngtpy_scenario.json")), "bytes")

@@ -115,3 +115,21 @@ def run(ngtpy, golden_dir, tmp, read_graph):
     out["refined"] = {"graph": [_pairs(ix.search(q, size=5, epsilon=0.3)) for q in queries]}
     ix.close()
     return out
+
+
+def run_reference_sample(module_dir, golden_dir, tmp, sample_py):
+    """python/sample/sample.py of the reference, UNMODIFIED (`sample_py`: the copy oracle/Makefile puts under oracle/_ref/),
+    as a separate interpreter with `module_dir` first on the module path so that its `import ngtpy` finds the module under
+    test; the two data files it reads (../../data/sift-*.tsv) are written from tests/golden/sift5k.npz. -> CompletedProcess"""
+    import subprocess
+    import sys
+    z = np.load(os.path.join(golden_dir, "sift5k.npz"))
+    os.makedirs(os.path.join(tmp, "data"))
+    cwd = os.path.join(tmp, "python", "sample")
+    os.makedirs(cwd)
+    for name, arr in (("sift-dataset-5k.tsv", z["data"]), ("sift-query-3.tsv", z["queries"])):
+        with open(os.path.join(tmp, "data", name), "w") as f:
+            for row in arr:
+                f.write("\t".join(str(int(v)) for v in row) + "\n")
+    env = dict(os.environ, PYTHONPATH=module_dir + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    return subprocess.run([sys.executable, sample_py], cwd=cwd, env=env, capture_output=True, text=True, timeout=600)

@@ -119,3 +119,24 @@ def test_batch_entry_points_and_counters(ngtpy, sift5k):
     ix.close()
     with pytest.raises(RuntimeError, match="closed"):
         ix.search(qs[0])
+
+
+def test_the_reference_sample_script_runs_unmodified(tmp_path):
+    """python/sample/sample.py of the reference (create, batch_insert of rows given as strings, save, reopen, search,
+    get_object, 5 000 single inserts, build_index, remove, save) executed as it is, `import ngtpy` resolving to the repo's
+    module: the result tables it prints are the ones the reference's module printed (tests/golden/ngtpy_sample.txt; top-5/6
+    of a 5k / 10k index at the default epsilon 0.1 -- both find the exact neighbours); the distance-computation counters
+    differ (other seeds, other graph) and are only required to be there and to grow."""
+    import ngtpy_scenario
+    sample = os.path.join(ROOT, "oracle", "_ref", "python", "sample", "sample.py")
+    if not os.path.exists(sample):
+        pytest.skip("no copy of the reference's python/sample/sample.py on this box")
+    done = ngtpy_scenario.run_reference_sample(os.path.join(ROOT, "ngt_b200"), GOLDEN, str(tmp_path), sample)
+    assert done.returncode == 0, done.stderr[-3000:]
+    want = open(os.path.join(GOLDEN, "ngtpy_sample.txt")).read().splitlines()
+    have = done.stdout.splitlines()
+    key = "# of distance computations="
+    assert [l for l in have if not l.startswith(key)] == [l for l in want if not l.startswith(key)]
+    counts = [int(l[len(key):]) for l in have if l.startswith(key)]
+    assert len(counts) == 4 and counts[0] > 0 and counts[1] > counts[0]           # accumulated until the next insertion
+    assert counts[2] > 0 and counts[3] > counts[2]
