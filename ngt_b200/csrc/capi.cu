@@ -1318,6 +1318,7 @@ struct DeviceGraph {   // a CSR with distances in device buffers of `cap` entrie
       throw std::runtime_error("cudaMalloc failed (graph buffers)");
     }
     cudaMemset(rp, 0, (n + 2) * 8);
+    cudaStreamSynchronize(cudaStreamLegacy);   // (the fill runs on the legacy stream; the users' streams are not ordered with it)
   }
   DeviceGraph(const DeviceGraph &) = delete;
   ~DeviceGraph() { release(); }

@@ -1279,12 +1279,16 @@ extern "C" int ngtgpu_index_build_onng(ngtgpu_index *ix, uint32_t knn, uint32_t 
       CUDA_TRY(cudaMemcpy(graph_out->col, g_col, nnz * 4, cudaMemcpyDeviceToDevice));
       CUDA_TRY(cudaMemcpy(graph_out->dist, g_dist, nnz * 4, cudaMemcpyDeviceToDevice));
     }
+    CUDA_TRY(cudaStreamSynchronize(cudaStreamLegacy));   // (device-to-device copies do not wait on the host)
   }
   return NGTGPU_OK;
 }
 
 extern "C" int ngtgpu_device_copy(void *dst, const void *src, uint64_t bytes) {
-  if (bytes) CUDA_TRY(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToDevice));
+  if (bytes) {
+    CUDA_TRY(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToDevice));
+    CUDA_TRY(cudaStreamSynchronize(cudaStreamLegacy));   // (device-to-device copies do not wait on the host)
+  }
   return NGTGPU_OK;
 }
 

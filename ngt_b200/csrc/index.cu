@@ -452,8 +452,12 @@ extern "C" int ngtgpu_index_set_graph(ngtgpu_index *ix, const uint64_t *row_ptr,
     CUDA_TRY(cudaMalloc(&ix->d_col, want * sizeof(uint32_t)));
     ix->col_cap = want;
   }
-  CUDA_TRY(cudaMemcpy(ix->d_row_ptr, row_ptr, (ix->n + 2) * sizeof(uint64_t), kind));
-  if (nnz) CUDA_TRY(cudaMemcpy(ix->d_col, col, nnz * sizeof(uint32_t), kind));
+  // On the index's stream, in order with the head-table kernel below: a synchronous cudaMemcpy between two device
+  // buffers does NOT wait on the host and runs on the legacy default stream, which the (non-blocking) stream of the index
+  // is not ordered with -- the kernel could read the previous graph's edges (seen as refineANNG runs on 100k objects
+  // that differed from one call to the next).
+  CUDA_TRY(cudaMemcpyAsync(ix->d_row_ptr, row_ptr, (ix->n + 2) * sizeof(uint64_t), kind, ix->stream));
+  if (nnz) CUDA_TRY(cudaMemcpyAsync(ix->d_col, col, nnz * sizeof(uint32_t), kind, ix->stream));
   ix->nnz = nnz;
   if (ix->head_cap < (ix->n + 1) * NGTGPU_HEAD_WIDTH) {
     if (ix->d_head) cudaFree(ix->d_head);

@@ -197,9 +197,9 @@ int ngtgpu_traverse(ngtgpu_index *ix, const uint8_t *d_queries, uint32_t nq, con
     a.query_list_count = t == 0 ? nullptr : ws + 2 * (t - 1) + 1;
     size_t smem = extra + (size_t)a.queue_cap * 8;
     // the on-chip tiers of the common case run the lean kernel: rows of 5..32 chunks, head-table adjacency, set semantics
-    // (epsilon >= 0), results in one warp's registers, a seed list that is one round
+    // (epsilon >= 0), results in one warp's registers (k <= 128), a seed list that is one round
     const bool fast = ix->fast_kernel && ix->chunks >= FAST_MIN_CHUNKS && ix->chunks <= 32 && cap <= NGTGPU_HEAD_WIDTH &&
-                      a.coef >= 1.0f && k <= 32 && n_seeds <= 32 * FAST_WARPS && cap <= 32 * FAST_WARPS &&   // one edge per thread
+                      a.coef >= 1.0f && k <= 32 * FAST_KL_MAX && n_seeds <= 32 * FAST_WARPS && cap <= 32 * FAST_WARPS &&   // one edge per thread
                       (ix->n + 1) * (uint64_t)ix->row_bytes < (1ull << 36);   // 32-bit row offsets in 16-byte units
     const int fast_ch = ix->chunks <= 8 ? 1 : ix->chunks <= 16 ? 2 : 4;
     // two warps per query (16 CTAs per SM) for narrow rows whose rounds fit 64 threads (edge cap and seeds <= 64)
@@ -210,7 +210,8 @@ int ngtgpu_traverse(ngtgpu_index *ix, const uint8_t *d_queries, uint32_t nq, con
     const bool one_fit = two_fit && fast_ch == 1 && t == 0 && ix->fast_warps == 1;
     // (two warps also take rounds of up to 128 edges, two per thread, when asked for)
     const bool two_asked = ix->fast_warps == 2 && cap <= 128 && n_seeds <= 128;
-    const int fast_w = one_fit ? 1 : (two_fit && ix->fast_warps != 4) || two_asked ? 2 : FAST_WARPS;
+    // (result lists of more than 32 keys -- construction and refinement searches -- come with four warps only)
+    const int fast_w = k > 32 ? FAST_WARPS : one_fit ? 1 : (two_fit && ix->fast_warps != 4) || two_asked ? 2 : FAST_WARPS;
     if (fast) smem = (size_t)fast_w * fast_stage_per_warp(fast_ch, fast_w) + (fast_w == 1 ? 0 : (size_t)a.queue_cap * 8);
     if (smem > 200 * 1024)
       NGTGPU_FAIL(NGTGPU_ERR_INVALID, "search: working set does not fit shared memory; lower queue_cap/size");

@@ -5,7 +5,7 @@
 // few hundred instructions instead of a few thousand (ncu source attribution of the general kernel: 5.4k
 // warp-instructions per expansion, a third of them address arithmetic around the row copies):
 //
-//   rows of <= 512 bytes (<= 32 chunks), edge cap <= 128 (head table), epsilon >= 0 (set semantics), k <= 32,
+//   rows of <= 512 bytes (<= 32 chunks), edge cap <= 128 (head table), epsilon >= 0 (set semantics), k <= 128,
 //   <= 128 seeds, visited hash in a slab of global memory (both on-chip tiers). Everything else runs search_kernel.
 //
 // One CTA (4 warps) per query, persistent grid. Per round:
@@ -31,6 +31,7 @@
 // offered for rows of <= 128 bytes with <= 64 edges and seeds per round, where a round moves a quarter of the bytes and
 // its latency chain, not the bandwidth, sets the pace. 3 warps x 10 CTAs/SM measured the same as 4 x 8 on 512-byte rows.
 #define FAST_WARPS 4
+#define FAST_KL_MAX 4     // result keys per lane of the control warp when k > 32 (k <= 128)
 #define FAST_STAGE_PER_WARP 4096u
 #ifndef FAST_INT_LD
 #define FAST_INT_LD 4u    // lanes per row for integer rows of <= 128 bytes in a distance step (8 rows per step)
@@ -115,12 +116,43 @@ __device__ __forceinline__ void cp_async_wait_group() {
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// ---- result list of the control warp: KL keys per lane, sorted; position p lives on lane p / KL, slot p % KL -----------
+// KL == 1 serves k <= 32 (one key per lane: every headline search); KL == 4 serves k <= 128 -- the searches of the
+// construction loop and of refineANNG, whose k is the edge count (Index.h:815-837, GraphReconstructor.h:852).
+template <int KL>
+__device__ __forceinline__ uint64_t res_kth(const uint64_t (&res)[KL], uint32_t idx) {
+  uint64_t v = res[0];
+  if (KL > 1) {
+    const uint32_t j = idx % KL;
+#pragma unroll
+    for (int m = 1; m < KL; m++)
+      if (j == (uint32_t)m) v = res[m];
+  }
+  return shfl_u64(v, (int)(idx / KL));
+}
+// insert a key that is not in the list; entries past position k - 1 fall off
+template <int KL>
+__device__ __forceinline__ void res_insert(uint64_t (&res)[KL], uint64_t kk, uint32_t k, int lane) {
+  uint32_t pos = 0;
+#pragma unroll
+  for (int m = 0; m < KL; m++) pos += __popc(__ballot_sync(0xffffffffu, res[m] < kk));
+  const uint64_t up = shfl_up_u64(res[KL - 1], 1);
+#pragma unroll
+  for (int m = KL - 1; m >= 0; m--) {
+    const uint32_t idx = (uint32_t)lane * KL + m;
+    const uint64_t prev = m > 0 ? res[m > 0 ? m - 1 : 0] : up;
+    if (idx == pos) res[m] = kk;
+    else if (idx > pos) res[m] = prev;
+    if (idx >= k) res[m] = KEY_NONE;
+  }
+}
+
 // W == 1 (opt-in, ngtgpu_index_set_fast_shape): the whole round runs in one warp (32 CTAs per SM, nobody waiting at a
 // barrier behind the control chain): a round of up to 64 edges is filtered in two passes whose bucket reads are issued
 // together, CTA barriers become warp barriers, and the unsorted back of the unchecked set lives in a per-CTA slab of
 // global memory next to the visited hash so that 32 CTAs fit the SM's shared memory. Measured slower than W == 2 on
 // 128-byte rows (3.6 vs 3.2 ms per 10k batch, 3.0 vs 2.9 ms per 10k at batch 40k): twice the slabs fall out of L2.
-template <int ACC, int CH, int W>
+template <int ACC, int CH, int W, int KL>
 __global__ void __launch_bounds__(W * 32, 32 / W) search_fast_kernel(const SearchArgs a) {
   constexpr int P = W <= 2 ? 2 : 1;                            // filter passes = edges per thread and round (the second
                                                                // one only when the round has more than 32 * W edges)
@@ -158,7 +190,7 @@ __global__ void __launch_bounds__(W * 32, 32 / W) search_fast_kernel(const Searc
   __shared__ float s_er;
   // control-warp state between rounds: it lives here while the rows are copied and evaluated, so that the row loop
   // has the register file to itself (lane constants stay in registers instead of being recomputed every step)
-  __shared__ uint64_t s_res[32], s_front[32];
+  __shared__ uint64_t s_res[32 * KL], s_front[32];   // s_res[32 * m + lane]: slot m of the lane
   __shared__ uint64_t s_T;
   __shared__ uint32_t s_ctl[12];   // fn, qsize, res_n, visited_n, st_dist, st_edge, st_exp, pref_id, buf, flags, radius, er
 
@@ -317,7 +349,8 @@ __global__ void __launch_bounds__(W * 32, 32 / W) search_fast_kernel(const Searc
 
     // ---- control-warp state (kept in shared memory between rounds)
     if (warp == 0) {
-      s_res[lane] = KEY_NONE;     // result list: lane i holds the i-th smallest key (k <= 32)
+#pragma unroll
+      for (int m = 0; m < KL; m++) s_res[32 * m + lane] = KEY_NONE;     // result list: lane i holds the keys of positions i * KL .. (k <= 32 * KL)
       s_front[lane] = KEY_NONE;
       if (lane == 0) s_T = KEY_NONE;
       if (lane < 10) s_ctl[lane] = lane == 9 ? 1u : 0u;   // flags: bit 0 seeding, bit 1 seeds taken, bit 2 head round, bit 3 a round ran
@@ -344,7 +377,9 @@ __global__ void __launch_bounds__(W * 32, 32 / W) search_fast_kernel(const Searc
       }
       // ================= control (warp 0) =================
       if (warp == 0) {
-        uint64_t res = s_res[lane];
+        uint64_t res[KL];
+#pragma unroll
+        for (int m = 0; m < KL; m++) res[m] = s_res[32 * m + lane];
         Unchecked U;
         U.front = s_front[lane];
         U.T = s_T;
@@ -381,13 +416,9 @@ __global__ void __launch_bounds__(W * 32, 32 / W) search_fast_kernel(const Searc
               m &= m - 1;
               const uint64_t kk = shfl_u64(key, src);
               if (key_dist(kk) > radius) continue;   // the radius shrank meanwhile
-              const uint32_t pos = __popc(__ballot_sync(0xffffffffu, res < kk));
-              const uint64_t up = shfl_up_u64(res, 1);
-              if ((uint32_t)lane == pos) res = kk;
-              else if ((uint32_t)lane > pos) res = up;
-              if ((uint32_t)lane >= a.k) res = KEY_NONE;
+              res_insert<KL>(res, kk, a.k, lane);
               if (res_n < a.k) res_n++;
-              if (!seeding && res_n >= a.k) radius = key_dist(shfl_u64(res, (int)a.k - 1));
+              if (!seeding && res_n >= a.k) radius = key_dist(res_kth<KL>(res, a.k - 1));
             }
           }
           if (!seeding) er = a.coef * radius;
@@ -433,7 +464,7 @@ __global__ void __launch_bounds__(W * 32, 32 / W) search_fast_kernel(const Searc
             if (seeding) {
               // setupSeeds: radius from the seeds once k of them are within it (Graph.cpp:349-351)
               seeding = false;
-              if (res_n >= a.k) radius = key_dist(shfl_u64(res, (int)a.k - 1));
+              if (res_n >= a.k) radius = key_dist(res_kth<KL>(res, a.k - 1));
               er = a.coef * radius;
             }
             if (U.fn == 0 && U.qsize != 0 && key_dist(U.T) <= er) {
@@ -470,7 +501,8 @@ __global__ void __launch_bounds__(W * 32, 32 / W) search_fast_kernel(const Searc
           }
           if (!finished && visited_n + take > a.hash_limit) overflow = true;
         }
-        s_res[lane] = res;
+#pragma unroll
+        for (int m = 0; m < KL; m++) s_res[32 * m + lane] = res[m];
         s_front[lane] = U.front;
         if (lane == 0) {
           s_T = U.T;
@@ -708,15 +740,19 @@ __global__ void __launch_bounds__(W * 32, 32 / W) search_fast_kernel(const Searc
     const int state = s_state;
     if (warp == 0) {
       if (state == 1) {
-        const uint64_t res = s_res[lane];
         const uint32_t res_n = s_ctl[2];
-        if ((uint32_t)lane < a.k) {
-          const bool ok = (uint32_t)lane < res_n;
-          if (a.keys_out) {
-            a.keys_out[(size_t)q * a.k + lane] = ok ? res + a.id_offset : KEY_NONE;
-          } else {
-            a.ids[(size_t)q * a.k + lane] = ok ? key_id(res) : 0u;
-            a.dists[(size_t)q * a.k + lane] = ok ? key_dist(res) : 0.f;
+#pragma unroll
+        for (int m = 0; m < KL; m++) {
+          const uint32_t p = (uint32_t)lane + 32u * m;   // position p: lane p / KL, slot p % KL (coalesced stores)
+          if (p < a.k) {
+            const uint64_t res = s_res[32 * (p % KL) + p / KL];
+            const bool ok = p < res_n;
+            if (a.keys_out) {
+              a.keys_out[(size_t)q * a.k + p] = ok ? res + a.id_offset : KEY_NONE;
+            } else {
+              a.ids[(size_t)q * a.k + p] = ok ? key_id(res) : 0u;
+              a.dists[(size_t)q * a.k + p] = ok ? key_dist(res) : 0.f;
+            }
           }
         }
         if (lane == 0) {
@@ -844,21 +880,30 @@ cudaError_t seed_select_dispatch(const SeedArgs &a, cudaStream_t stream) {
 }
 
 // op == 0: launch, op == 1: occupancy query
-template <int ACC, int CH, int W>
+template <int ACC, int CH, int W, int KL = 1>
 static cudaError_t fast_one(const SearchArgs &a, unsigned grid, size_t smem, cudaStream_t stream, int op, int *blocks) {
-  cudaError_t e = cudaFuncSetAttribute(search_fast_kernel<ACC, CH, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(search_fast_kernel<ACC, CH, W, KL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(search_fast_kernel<ACC, CH, W>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  e = cudaFuncSetAttribute(search_fast_kernel<ACC, CH, W, KL>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   if (e != cudaSuccess) return e;
-  if (op == 1) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, search_fast_kernel<ACC, CH, W>, W * 32, smem);
-  search_fast_kernel<ACC, CH, W><<<grid, W * 32, smem, stream>>>(a);
+  if (op == 1) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks, search_fast_kernel<ACC, CH, W, KL>, W * 32, smem);
+  search_fast_kernel<ACC, CH, W, KL><<<grid, W * 32, smem, stream>>>(a);
   return cudaGetLastError();
 }
 
-// ch: chunks per lane of a row's eight lanes (1, 2, 4); warps per query: 4 or 2
+// ch: chunks per lane of a row's eight lanes (1, 2, 4); warps per query: 4 or 2 (1 when asked for); result lists of
+// 33..128 keys (four per lane of the control warp) come with four warps per query
 template <int ACC>
 cudaError_t search_fast_dispatch(const SearchArgs &a, int ch, int warps, unsigned grid, size_t smem, cudaStream_t stream, int op,
                                  int *blocks) {
+  if (a.k > 32u * FAST_KL_MAX) return cudaErrorInvalidValue;
+  if (a.k > 32u) {
+    if (warps != FAST_WARPS) return cudaErrorInvalidValue;
+    if (ch == 1) return fast_one<ACC, 1, 4, FAST_KL_MAX>(a, grid, smem, stream, op, blocks);
+    if (ch == 2) return fast_one<ACC, 2, 4, FAST_KL_MAX>(a, grid, smem, stream, op, blocks);
+    if (ch == 4) return fast_one<ACC, 4, 4, FAST_KL_MAX>(a, grid, smem, stream, op, blocks);
+    return cudaErrorInvalidValue;
+  }
   if (ch == 1 && warps == 1) return fast_one<ACC, 1, 1>(a, grid, smem, stream, op, blocks);
   if (ch == 1 && warps == 2) return fast_one<ACC, 1, 2>(a, grid, smem, stream, op, blocks);
   if (ch == 2 && warps == 2) return fast_one<ACC, 2, 2>(a, grid, smem, stream, op, blocks);

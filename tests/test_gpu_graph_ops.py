@@ -237,3 +237,30 @@ def test_refine_anng_equals_the_reference(eng, tag):
     got = _lists(out[0].cpu().numpy(), out[1].cpu().numpy().astype(np.uint32), out[2].cpu().numpy())
     assert got == _lists(zr[tag + "_row_ptr"], zr[tag + "_col"], zr[tag + "_dist"])[:n + 1]
     ix.close()
+
+
+def test_refine_anng_is_reproducible_at_size(eng):
+    """100k objects, result lists of 40 keys (four per lane of the lean kernel's control warp): refineANNG gives the same
+    graph call after call and on both traversal kernels. Guards the ordering of ngtgpu_index_set_graph's device-to-device
+    copies with its head-table kernel: on the legacy stream they were not ordered with the index's stream, and at this
+    size the head table of one batch could hold edges of the batch before (one call in three differed)."""
+    import torch
+    from ngt_b200 import build, synth
+    dev = torch.device("cuda", 0)
+    base = synth.make_device("sift", 100000, 1, dev)
+    ix = eng.GpuIndex(po.FLOAT, po.L2, base.shape[1])
+    ix.set_objects(base)
+    g = ix.build_onng(64, 10, 64, True, want_graph=True)
+    ix.build_seed_table(256, 1)
+    rp, col, dist = g["graph"]
+    runs = []
+    for fast in (True, True, True, False):
+        ix.set_fast_kernel(fast)
+        ix.set_graph(rp, col)
+        runs.append(build.refine_anng(ix, rp, col, dist, 0.1, 0, -1, 10000, 40, 10))
+    for r in runs[1:]:
+        for x, y in zip(r, runs[0]):
+            assert x.shape == y.shape and torch.equal(x, y)
+    assert runs[0][1].numel() > col.numel()
+    ix.set_fast_kernel(True)
+    ix.close()

@@ -276,6 +276,77 @@ def test_fast_kernel_equals_general_kernel(eng, port, kind):
     ix.close()
 
 
+@pytest.mark.parametrize("kind", ["f32l2_128", "f32cos_100", "f32l2_48", "u8l2_128", "f32ncos_32", "u8ham_256"])
+def test_fast_kernel_wide_result_lists(eng, port, kind):
+    """search_fast_kernel<.., KL = 4>: result lists of 33..128 keys, four per lane of the control warp -- the searches of
+    the construction loop and of refineANNG, whose k is the edge count (Index.h:815-837, GraphReconstructor.h:852).
+    Ids, distance bits, counts and work counters equal the general kernel's (sorted array in shared memory) for every
+    row width class; integer-valued kinds also equal the C restatement of the reference. Covered: k not a multiple of
+    four, lists that stay shorter than k (radius), repeated seeds, queries that overflow the first tier."""
+    from ngt_b200 import synth
+    rng = np.random.default_rng(13)
+    name, dim = kind.split("_")
+    dim = int(dim)
+    n, nq = 20000, 200
+    base = synth.make("sift", n, 1)[:, :min(dim, 128)]
+    qs = synth.make("sift", nq, 2)[:, :min(dim, 128)]
+    normalize = False
+    if name == "f32l2":
+        otype, dtype, objs, q = po.FLOAT, po.L2, base, qs
+    elif name == "u8l2":
+        otype, dtype, objs, q = po.UINT8, po.L2, base.astype(np.uint8), qs
+    elif name == "u8ham":
+        otype, dtype = po.UINT8, po.HAMMING   # 1024 bits = eight 16-byte chunks per object
+        wide, wq = np.concatenate([base, base[:, ::-1]], 1), np.concatenate([qs, qs[:, ::-1]], 1)
+        objs = np.concatenate([synth.hamming_from(wide, t) for t in (40.0, 56.0, 72.0, 88.0)], 1)
+        q = np.concatenate([synth.hamming_from(wq, t) for t in (40.0, 56.0, 72.0, 88.0)], 1).astype(np.float32)
+    elif name == "f32cos":
+        otype, dtype = po.FLOAT, po.COSINE
+        objs, q = (base - 64.0).astype(np.float32) / 40.0, (qs - 64.0).astype(np.float32) / 40.0
+    else:
+        otype, dtype, normalize = po.FLOAT, po.NORMALIZED_COSINE, True
+        objs, q = (base - 64.0).astype(np.float32) / 40.0, (qs - 64.0).astype(np.float32) / 40.0
+    ix = eng.GpuIndex(otype, dtype, objs.shape[1])
+    ix.set_objects(objs, normalize=normalize)
+    gids, gd, gcounts = ix.linear_search(objs.astype(np.float32), 25)
+    row_ptr, col = _knn_csr(gids, gcounts)
+    ix.set_graph(row_ptr, col)
+    seeds = np.stack([rng.choice(n, 10, replace=False) + 1 for _ in range(nq)]).astype(np.uint32)
+    seeds_rep = seeds.copy()
+    seeds_rep[::3, 5] = seeds_rep[::3, 1]
+    exact = name in ("f32l2", "u8l2", "u8ham")
+    rad = float(np.median(gd[:, 20]))   # lists that end below k: about twenty objects lie this close to a base row
+    for eps, cap, kk, radius in ((0.1, 16, 33, -1.0), (0.1, 100, 64, -1.0), (0.0, 24, 100, -1.0), (0.2, 128, 128, -1.0),
+                                 (0.1, 40, 50, rad), (0.1, 30, 127, -1.0)):
+        what = "%s eps=%g cap=%d k=%d radius=%g" % (kind, eps, cap, kk, radius)
+        for sd in (seeds_rep, seeds):   # (a repeated seed is evaluated once by both kernels)
+            out = {}
+            for fast in (True, False):
+                ix.set_fast_kernel(fast)
+                out[fast] = ix.search(q, kk, eps, radius=radius, edge_size=cap, seeds=sd, with_stats=True)
+            for a, b in zip(out[True], out[False]):
+                assert (np.asarray(a).view(np.uint32) == np.asarray(b).view(np.uint32)).all(), what
+        if radius >= 0:
+            assert (np.asarray(out[True][2]) < kk).any(), what + ": no short list in this case"
+        if exact:
+            pobj, pq = po.pad_objects(objs, otype), po.pad_queries(q, otype)
+            rids, rdists, rcounts, rstats = port.graph_search(dtype, otype, pobj, row_ptr, col, pq, seeds, kk, eps,
+                                                              edge_size=cap, radius=radius)
+            assert_bit_exact(out[True][0], out[True][1], out[True][2], rids, rdists, rcounts, what=what)
+            assert (out[True][3].astype(np.uint64) == rstats).all(), what
+    # queries that outgrow the first tier: the second tier is the same kernel with larger slabs, then the general one
+    ix.set_fast_kernel(False)
+    ref = ix.search(q, 64, 0.3, edge_size=100, seeds=seeds)
+    ix.set_fast_kernel(True)
+    for tiers in (2, 1):
+        ix.set_search_workspace(hash_bits=9, queue_cap=64, onchip_tiers=tiers)
+        got = ix.search(q, 64, 0.3, edge_size=100, seeds=seeds)
+        assert ix.last_overflows > 0
+        for a, b in zip(got, ref):
+            assert (np.asarray(a).view(np.uint32) == np.asarray(b).view(np.uint32)).all(), kind + " overflow, %d tiers" % tiers
+    ix.close()
+
+
 @pytest.mark.parametrize("kind", ["u8l2_128", "f32l2_32", "u8l2_128_wide"])
 def test_one_warp_per_query_shape(eng, port, kind):
     """search_fast_kernel<.., W = 1>: rounds of 33..64 edges and seed lists of 40 (two filter passes per round, a seed id
