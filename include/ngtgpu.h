@@ -285,6 +285,10 @@ int ngtgpu_index_build_onng(ngtgpu_index *index, uint32_t knn, uint32_t outgoing
                             uint32_t min_edges, ngtgpu_graph_buffers *graph_out, double *seconds);
 int ngtgpu_device_free(void *device_pointer);
 int ngtgpu_device_copy(void *dst, const void *src, uint64_t bytes); /* device to device, synchronous */
+/* Counters of the construction path since the library was loaded (evidence for tools/anng_probe.py):
+ * [0] batches merged into the sorted lists, [1] batches that took the full sort, [2] temporary blocks that had to come
+ * from cudaMalloc, [3] temporary blocks served by the per-device cache. */
+int ngtgpu_construction_counters(uint64_t out[4]);
 
 /* The sub-graph of the edges with keep[e] != 0, order inside the lists preserved (compaction after
  * ngtgpu_graph_adjust_paths). DEVICE buffers; *out_nnz is a host word. */

@@ -24,6 +24,7 @@
 // The result is the reference's graph bit for bit (tests/golden/adjust_paths.npz pins it).
 #include <cub/cub.cuh>
 #include <mutex>
+#include <atomic>
 #include <vector>
 
 #include "ngtgpu_internal.cuh"
@@ -222,6 +223,8 @@ __global__ void keep_mask_kernel(const uint8_t *__restrict__ status, uint64_t nn
 // cudaMalloc / cudaFree pairs per call (each a driver round trip with an implicit device synchronisation) were most of
 // its time (19 ms per batch of which ~2 ms on the GPU). A block goes back to the cache only after the device is idle,
 // which is the guarantee cudaFree gave.
+std::atomic<uint64_t> g_batches_merged{0}, g_batches_sorted{0}, g_blocks_malloc{0}, g_blocks_cached{0};
+
 struct BlockCache {
   struct Block {
     void *p;
@@ -293,6 +296,8 @@ struct DeviceBuffers {
     size_t got = 0;
     void *p = block_cache().take(bytes, dev, &got);
     cudaError_t e = cudaSuccess;
+    if (p) g_blocks_cached++;
+    else g_blocks_malloc++;
     if (!p) {
       got = bytes;
       e = cudaMalloc(&p, bytes);
@@ -1039,6 +1044,82 @@ __global__ void pick_retry_counts_kernel(uint32_t count, uint32_t e, uint32_t *c
 
 }  // namespace
 
+// ---- a batch's edge triples merged into the sorted lists of the graph ----------------------------------------
+// The lists of the CSR are in (distance, target) order already and a batch touches a few thousand of them: instead of
+// sorting every edge of the graph again (11 ms per batch of 200 at 1M objects), only the NEW triples are sorted by
+// (source, distance, target); then one pass moves every list to its new place, a warp per list, and a list that gains
+// edges is merged with its run of new triples by rank: an old entry moves up by the number of new keys below it, a new
+// entry lands behind the old entries not above it (binary searches; hub lists of thousands of entries stay parallel).
+// The full sort also drops an entry whose target equals the entry before it. That cannot happen when new nodes are
+// inserted, but a caller may insert an id the graph already links: any such neighbourhood (and any list that does not
+// come strictly ascending) raises a flag and the batch takes the full sort, which handles both.
+namespace {
+
+__global__ void list_degree_kernel(const uint64_t *__restrict__ row_ptr, uint64_t n, uint32_t *__restrict__ deg) {
+  for (uint64_t id = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; id <= n; id += (uint64_t)gridDim.x * blockDim.x)
+    deg[id] = (uint32_t)(row_ptr[id + 1] - row_ptr[id]);
+}
+
+// src sorted: every triple adds one to its source's degree, the first of a run records where the run starts
+__global__ void run_degree_kernel(const uint32_t *__restrict__ src, uint64_t m, uint32_t *__restrict__ deg,
+                                  uint32_t *__restrict__ run_start) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < m; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t s = src[i];
+    atomicAdd(&deg[s], 1u);
+    if (i == 0 || src[i - 1] != s) run_start[s] = (uint32_t)i;
+  }
+}
+
+__device__ __forceinline__ uint64_t edge_key(const uint32_t *col, const float *dist, uint64_t e) {
+  return ((uint64_t)ord_of_float(dist[e]) << 32) | col[e];
+}
+
+__global__ void merge_lists_kernel(const uint64_t *__restrict__ row_ptr, const uint64_t *__restrict__ new_ptr, uint64_t n,
+                                   const uint32_t *__restrict__ col, const float *__restrict__ dist,
+                                   const uint64_t *__restrict__ key, const uint32_t *__restrict__ run_start,
+                                   uint32_t *__restrict__ out_col, float *__restrict__ out_dist, uint32_t *__restrict__ redo) {
+  const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+  for (uint64_t id = warp; id <= n; id += warps) {
+    const uint64_t ob = row_ptr[id], nb = new_ptr[id], d = row_ptr[id + 1] - ob;
+    const uint64_t lb = (new_ptr[id + 1] - nb) - d;   // new triples of this list
+    const uint64_t rs = lb ? run_start[id] : 0;
+    for (uint64_t i = lane; i < d; i += 32) {
+      const uint32_t t = col[ob + i];
+      const float x = dist[ob + i];
+      const uint64_t ka = ((uint64_t)ord_of_float(x) << 32) | t;
+      if (i + 1 < d) {
+        const uint32_t t1 = col[ob + i + 1];
+        if (edge_key(col, dist, ob + i + 1) <= ka || t1 == t) *redo = 1u;
+      }
+      uint64_t lo = 0, hi = lb;   // new keys below this one
+      while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (key[rs + mid] < ka) lo = mid + 1;
+        else hi = mid;
+      }
+      out_col[nb + i + lo] = t;
+      out_dist[nb + i + lo] = x;
+    }
+    for (uint64_t j = lane; j < lb; j += 32) {
+      const uint64_t kb = key[rs + j];
+      const uint32_t t = (uint32_t)kb;
+      uint64_t lo = 0, hi = d;    // old keys not above this one
+      while (lo < hi) {
+        const uint64_t mid = (lo + hi) >> 1;
+        if (edge_key(col, dist, ob + mid) <= kb) lo = mid + 1;
+        else hi = mid;
+      }
+      out_col[nb + j + lo] = t;
+      out_dist[nb + j + lo] = float_of_ord((uint32_t)(kb >> 32));
+      if ((lo > 0 && col[ob + lo - 1] == t) || (lo < d && col[ob + lo] == t) || (j > 0 && (uint32_t)key[rs + j - 1] == t)) *redo = 1u;
+    }
+  }
+}
+
+}  // namespace
+
 extern "C" int ngtgpu_index_insert_batch(ngtgpu_index *ix, uint32_t first_id, uint32_t count, uint32_t edge_size_for_creation,
                                          float epsilon, int64_t edge_size, uint32_t n_seeds, uint32_t n_pivots,
                                          uint64_t pivot_seed, uint64_t capacity, uint64_t *d_row_ptr, uint32_t *d_col,
@@ -1135,15 +1216,84 @@ extern "C" int ngtgpu_index_insert_batch(ngtgpu_index *ix, uint32_t first_id, ui
   }
   if (ce != cudaSuccess) NGTGPU_FAIL(NGTGPU_ERR_CUDA, std::string("in-batch distance kernel launch: ") + cudaGetErrorString(ce));
   ix->launches++;
-  // old edges + (new node -> listed node) + (listed node -> new node)
-  const uint64_t m_max = nnz + 2ull * count * e;
+  // (new node -> listed node) + (listed node -> new node) merged into the lists of the graph
+  static const bool merge_off = getenv("NGTGPU_INSERT_MERGE") != nullptr && atoi(getenv("NGTGPU_INSERT_MERGE")) == 0;
+  bool merged = false;
+  if (nnz && !merge_off) {
+    const uint64_t m_new_max = 2ull * count * e;
+    uint32_t *ns_a, *ns_b, *deg, *unsorted;
+    uint64_t *nk_a, *nk_b, *t_ptr;
+    unsigned long long *cnt;
+    CUDA_TRY(mem.alloc(&ns_a, m_new_max));
+    CUDA_TRY(mem.alloc(&ns_b, m_new_max));
+    CUDA_TRY(mem.alloc(&nk_a, m_new_max));
+    CUDA_TRY(mem.alloc(&nk_b, m_new_max));
+    CUDA_TRY(mem.alloc(&cnt, 2));
+    CUDA_TRY(mem.alloc(&unsorted, 4));
+    CUDA_TRY(cudaMemsetAsync(cnt, 0, 16, stream));
+    CUDA_TRY(cudaMemsetAsync(unsorted, 0, 16, stream));
+    refine_emit_kernel<<<grid, 256, 0, stream>>>(o_ids, o_dists, o_counts, first_id, count, e, ix->d_valid, 1, ns_a, nk_a, cnt);
+    ix->launches++;
+    unsigned long long m_new = 0;
+    CUDA_TRY(cudaMemcpyAsync(&m_new, cnt, 8, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    if (m_new == 0) {
+      merged = true;   // nothing to add: the graph stays as it is
+    } else {
+      const uint64_t out_nnz = nnz + m_new;
+      if (out_nnz > capacity)
+        NGTGPU_FAIL(NGTGPU_ERR_INVALID, "ngtgpu_index_insert_batch: graph capacity " + std::to_string(capacity) + " < " +
+                                            std::to_string(out_nnz) + " edges");
+      int hi_bits = 1;
+      while (hi_bits < 32 && (n >> hi_bits) != 0) hi_bits++;
+      size_t t1 = 0, t2 = 0, t3 = 0;
+      uint32_t *run_start, *t_col;
+      float *t_dist;
+      CUDA_TRY(mem.alloc(&deg, n + 2));
+      CUDA_TRY(mem.alloc(&run_start, n + 2));
+      CUDA_TRY(mem.alloc(&t_ptr, n + 2));
+      // (the caller's capacity, not this batch's edge count: the same size in every batch of a loop, so the block cache
+      // serves it -- a size that grows by a few KB per batch would miss it every time)
+      CUDA_TRY(mem.alloc(&t_col, (size_t)capacity));
+      CUDA_TRY(mem.alloc(&t_dist, (size_t)capacity));
+      CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, t1, nk_a, nk_b, ns_a, ns_b, (int64_t)m_new_max, 0, 64, stream));
+      CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, t2, ns_b, ns_a, nk_b, nk_a, (int64_t)m_new_max, 0, hi_bits, stream));
+      CUDA_TRY(cub::DeviceScan::InclusiveScan(nullptr, t3, deg, t_ptr + 1, cub::Sum(), (int64_t)n + 1, stream));
+      uint8_t *tmp;
+      CUDA_TRY(mem.alloc(&tmp, std::max(t1, std::max(t2, t3))));   // (sized for the largest batch: constant as well)
+      CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, t1, nk_a, nk_b, ns_a, ns_b, (int64_t)m_new, 0, 64, stream));       // by (distance, target)
+      CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, t2, ns_b, ns_a, nk_b, nk_a, (int64_t)m_new, 0, hi_bits, stream));  // then, stably, by source
+      list_degree_kernel<<<grid, 256, 0, stream>>>(d_row_ptr, n, deg);
+      run_degree_kernel<<<grid, 256, 0, stream>>>(ns_a, m_new, deg, run_start);
+      CUDA_TRY(cub::DeviceScan::InclusiveScan(tmp, t3, deg, t_ptr + 1, cub::Sum(), (int64_t)n + 1, stream));   // (t_ptr[0] is zero: a fresh block)
+      merge_lists_kernel<<<grid, 256, 0, stream>>>(d_row_ptr, t_ptr, n, d_col, d_dist, nk_a, run_start, t_col, t_dist, unsorted);
+      ix->launches += 3;
+      uint32_t bad = 0;
+      CUDA_TRY(cudaMemcpyAsync(&bad, unsorted, 4, cudaMemcpyDeviceToHost, stream));
+      CUDA_TRY(cudaStreamSynchronize(stream));
+      CUDA_TRY(cudaGetLastError());
+      if (!bad) {
+        CUDA_TRY(cudaMemcpyAsync(d_row_ptr, t_ptr, (n + 2) * 8, cudaMemcpyDeviceToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(d_col, t_col, out_nnz * 4, cudaMemcpyDeviceToDevice, stream));
+        CUDA_TRY(cudaMemcpyAsync(d_dist, t_dist, out_nnz * 4, cudaMemcpyDeviceToDevice, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        nnz = out_nnz;
+        merged = true;
+      }
+    }
+    if (merged) g_batches_merged++;
+  }
+  if (!merged) {
+  g_batches_sorted++;
+  // the full sort: old edges + new triples (an empty graph, or lists that did not come in (distance, target) order)
   uint32_t *src_a, *src_b;
   uint64_t *key_a, *key_b;
   unsigned long long *counter;
-  CUDA_TRY(mem.alloc(&src_a, m_max));
-  CUDA_TRY(mem.alloc(&src_b, m_max));
-  CUDA_TRY(mem.alloc(&key_a, m_max));
-  CUDA_TRY(mem.alloc(&key_b, m_max));
+  const uint64_t m_alloc = std::max<uint64_t>(capacity, nnz) + 2ull * count * e;   // the same in every batch of a loop (block cache)
+  CUDA_TRY(mem.alloc(&src_a, m_alloc));
+  CUDA_TRY(mem.alloc(&src_b, m_alloc));
+  CUDA_TRY(mem.alloc(&key_a, m_alloc));
+  CUDA_TRY(mem.alloc(&key_b, m_alloc));
   CUDA_TRY(mem.alloc(&counter, 2));
   CUDA_TRY(cudaMemsetAsync(counter, 0, 16, stream));
   if (nnz) emit_edges_kernel<<<grid, 256, 0, stream>>>(d_row_ptr, d_col, d_dist, n, 0xffffffffu, 0u, src_a, key_a, counter);
@@ -1169,6 +1319,7 @@ extern "C" int ngtgpu_index_insert_batch(ngtgpu_index *ix, uint32_t first_id, ui
     CUDA_TRY(cudaMemcpyAsync(d_dist, t_dist, out_nnz * 4, cudaMemcpyDeviceToDevice, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
     nnz = out_nnz;
+  }
   }
   NGTGPU_TRY(ngtgpu_index_set_graph(ix, d_row_ptr, d_col, 1));
   ix->graph_source = d_row_ptr;
@@ -1281,6 +1432,12 @@ extern "C" int ngtgpu_index_build_onng(ngtgpu_index *ix, uint32_t knn, uint32_t 
     }
     CUDA_TRY(cudaStreamSynchronize(cudaStreamLegacy));   // (device-to-device copies do not wait on the host)
   }
+  return NGTGPU_OK;
+}
+
+extern "C" int ngtgpu_construction_counters(uint64_t out[4]) {
+  if (!out) NGTGPU_FAIL(NGTGPU_ERR_INVALID, "ngtgpu_construction_counters: null buffer");
+  out[0] = g_batches_merged, out[1] = g_batches_sorted, out[2] = g_blocks_malloc, out[3] = g_blocks_cached;
   return NGTGPU_OK;
 }
 

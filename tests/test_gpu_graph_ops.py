@@ -264,3 +264,31 @@ def test_refine_anng_is_reproducible_at_size(eng):
     assert runs[0][1].numel() > col.numel()
     ix.set_fast_kernel(True)
     ix.close()
+
+
+def test_insert_batch_merge_equals_the_full_sort(eng):
+    """ngtgpu_index_insert_batch merges a batch's sorted edge triples into the lists of the graph; lists that do not come
+    in (distance, target) order send the batch through the full sort of every edge instead, which repairs them. Both
+    routes must leave the same graph: the same second half inserted into a graph given sorted (merge from the first
+    batch on) and given with every list reversed (full sort first; no edge cap, so the searches see the same sets)."""
+    import torch
+    from ngt_b200 import build, synth
+    n, half = 3000, 2000
+    base = synth.make("sift", n, 21)
+    ix = eng.GpuIndex(po.FLOAT, po.L2, base.shape[1])
+    ix.set_objects(base)
+    g1 = build.insert_objects(ix, 1, half, None, 8, 0.1, 0, 200, 10, 0)
+    ref = build.insert_objects(ix, half + 1, n - half, g1, 8, 0.1, 0, 200, 10, 0)
+    rp, col, dist = [t.cpu().numpy() for t in g1]
+    rcol, rdist = col.copy(), dist.copy()
+    for i in range(len(rp) - 1):
+        b, e = int(rp[i]), int(rp[i + 1])
+        rcol[b:e], rdist[b:e] = col[b:e][::-1], dist[b:e][::-1]
+    assert (rcol != col).any()
+    dev = g1[1].device
+    g1r = (g1[0], torch.from_numpy(rcol).to(dev), torch.from_numpy(rdist).to(dev))
+    got = build.insert_objects(ix, half + 1, n - half, g1r, 8, 0.1, 0, 200, 10, 0)
+    for x, y in zip(got, ref):
+        assert x.shape == y.shape and torch.equal(x, y)
+    assert ref[1].numel() > col.size
+    ix.close()

@@ -21,6 +21,7 @@ ap.add_argument("--n", type=int, default=200000)
 ap.add_argument("--edges", type=int, default=10)
 ap.add_argument("--batch", type=int, default=200)
 ap.add_argument("--eps-create", type=float, default=0.1)
+ap.add_argument("--loop-only", action="store_true")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 base = make_rows("sift", "f32", a.n, 1, dev)
@@ -53,6 +54,14 @@ rp, col, dist = build.insert_objects(ix, 1, a.n, None, a.edges, a.eps_create, -1
 torch.cuda.synchronize()
 out["insert_loop_s"] = round(time.time() - t, 2)
 out["insert_loop_edges"] = int(col.numel())
+import ctypes as C
+cnt = (C.c_uint64 * 4)()
+_lib.check(_lib.load().ngtgpu_construction_counters(cnt))
+out["batches_merged"], out["batches_full_sort"], out["blocks_from_cudaMalloc"], out["blocks_from_cache"] = [int(v) for v in cnt]
+out["insert_merge"] = os.environ.get("NGTGPU_INSERT_MERGE", "1")
+if a.loop_only:
+    print(json.dumps(out), flush=True)
+    sys.exit(0)
 ix.set_graph(rp, col)
 sweep(ix, "insert_loop")
 ix.close()
