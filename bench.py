@@ -845,6 +845,11 @@ def run_ours(a):
             if tj.get("kernel_source_sha256_16") == src:
                 out["roofline"]["traffic"] = tj.get("search_kernel_dram_bytes_per_launch")
                 out["roofline"]["traffic_source"] = tj.get("source")
+            elif src in tj.get("sass_equivalent_sources", {}):
+                # a later source whose measured instantiation compiles to the captured kernel's instructions (evidence named in the note)
+                out["roofline"]["traffic"] = tj.get("search_kernel_dram_bytes_per_launch")
+                out["roofline"]["traffic_source"] = tj.get("source")
+                out["roofline"]["traffic_note"] = "capture of an earlier source: " + tj["sass_equivalent_sources"][src]
             else:
                 out["roofline"]["traffic_note"] = "profiles/traffic.json was captured from another version of the kernel source: dropped"
         except Exception:
