@@ -1,0 +1,133 @@
+"""Size-independent properties of the path, checked on the CPU (no device): they tie the oracle's graph search to its
+own exhaustive search, and the host twins of the multi-GPU key format to plain numpy, on randomised inputs.
+
+* exhaustive search (ObjectSpaceRepository::linearSearch, lib/NGT/ObjectSpaceRepository.h:466-502) == numpy's sort of
+  the exact integer distances (uint8 L2, Hamming);
+* graph search (NeighborhoodGraph::search, lib/NGT/Graph.cpp:398-495) on a COMPLETE graph visits every object whatever
+  epsilon is, so it equals the exhaustive search; on any graph its results are a subset of the objects reachable from
+  the seeds, ascending, without repeats, and no object's distance is computed twice;
+* 64-bit keys (ordered distance bits << 32 | id): unsigned order == (distance, id) order of ObjectDistance::operator<
+  (lib/NGT/Common.h:1946-1952); pack -> unpack is the identity; the k-way merge of per-shard lists == the k smallest of
+  the union."""
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+from oracle import pyoracle as po
+
+
+def _complete_graph(n):
+    row_ptr = np.zeros(n + 2, np.uint64)
+    row_ptr[2:] = np.cumsum(np.full(n, n - 1, np.uint64))
+    col = np.concatenate([np.delete(np.arange(1, n + 1, dtype=np.uint32), i) for i in range(n)])
+    return row_ptr, col
+
+
+def _knn_graph(port, dtype, otype, pobj, k):
+    ids, _, counts = port.linear_search(dtype, otype, pobj, pobj[1:], k + 1)
+    n = pobj.shape[0] - 1
+    lists = [[int(t) for t in ids[i, :counts[i]] if int(t) != i + 1][:k] for i in range(n)]
+    row_ptr = np.zeros(n + 2, np.uint64)
+    row_ptr[2:] = np.cumsum(np.array([len(x) for x in lists], np.uint64))
+    return row_ptr, np.array([t for x in lists for t in x], np.uint32), lists
+
+
+@settings(max_examples=12, deadline=None, derandomize=True)
+@given(st.integers(0, 2 ** 31 - 1), st.sampled_from(["u8l2", "ham"]), st.integers(1, 40))
+def test_linear_search_is_the_sorted_exact_distance(port, seed, kind, k):
+    rng = np.random.default_rng(seed)
+    n, nq, dim = 300, 8, 32
+    objs = rng.integers(0, 256, (n, dim), dtype=np.uint8)
+    q = rng.integers(0, 256, (nq, dim), dtype=np.uint8)
+    dtype = po.L2 if kind == "u8l2" else po.HAMMING
+    pobj, pq = po.pad_objects(objs, po.UINT8), po.pad_queries(q.astype(np.float32), po.UINT8)
+    ids, dists, counts = port.linear_search(dtype, po.UINT8, pobj, pq, k)
+    for i in range(nq):
+        if kind == "u8l2":
+            exact = ((objs.astype(np.int64) - q[i].astype(np.int64)) ** 2).sum(1)
+            want_d = np.sqrt(exact.astype(np.float64)).astype(np.float32)
+        else:
+            exact = np.unpackbits(objs ^ q[i], axis=1).sum(1).astype(np.int64)
+            want_d = exact.astype(np.float32)
+        order = np.lexsort((np.arange(1, n + 1), exact))[:k]     # ascending (distance, id)
+        assert counts[i] == min(k, n)
+        assert (ids[i, :counts[i]] == order + 1).all()
+        assert (dists[i, :counts[i]].view(np.uint32) == want_d[order].view(np.uint32)).all()
+
+
+@settings(max_examples=8, deadline=None, derandomize=True)
+@given(st.integers(0, 2 ** 31 - 1), st.sampled_from([0.0, 0.1, 0.5]), st.integers(1, 20))
+def test_graph_search_on_a_complete_graph_is_exhaustive(port, seed, eps, k):
+    rng = np.random.default_rng(seed)
+    n, nq, dim = 60, 6, 16
+    objs = rng.integers(0, 256, (n, dim), dtype=np.uint8)
+    q = rng.integers(0, 256, (nq, dim)).astype(np.float32)
+    pobj, pq = po.pad_objects(objs, po.UINT8), po.pad_queries(q, po.UINT8)
+    row_ptr, col = _complete_graph(n)
+    seeds = np.stack([rng.choice(n, 3, replace=False) + 1 for _ in range(nq)]).astype(np.uint32)
+    ids, dists, counts, stats = port.graph_search(po.L2, po.UINT8, pobj, row_ptr, col, pq, seeds, k, eps)
+    rids, rdists, rcounts = port.linear_search(po.L2, po.UINT8, pobj, pq, k)
+    assert (counts == rcounts).all() and (ids == rids).all()
+    assert (dists.view(np.uint32) == rdists.view(np.uint32)).all()
+    assert (stats[:, 0] == n).all()          # every object's distance is computed exactly once
+
+
+@settings(max_examples=8, deadline=None, derandomize=True)
+@given(st.integers(0, 2 ** 31 - 1))
+def test_graph_search_results_are_reachable_sorted_and_unique(port, seed):
+    rng = np.random.default_rng(seed)
+    n, nq, dim, k = 400, 10, 24, 10
+    objs = rng.integers(0, 256, (n, dim), dtype=np.uint8)
+    q = rng.integers(0, 256, (nq, dim)).astype(np.float32)
+    pobj, pq = po.pad_objects(objs, po.UINT8), po.pad_queries(q, po.UINT8)
+    row_ptr, col, lists = _knn_graph(port, po.L2, po.UINT8, pobj, 6)
+    seeds = np.stack([rng.choice(n, 4, replace=False) + 1 for _ in range(nq)]).astype(np.uint32)
+    for eps in (0.0, 0.1, 0.3, 1.0):
+        ids, dists, counts, stats = port.graph_search(po.L2, po.UINT8, pobj, row_ptr, col, pq, seeds, k, eps)
+        for i in range(nq):
+            c = int(counts[i])
+            got = ids[i, :c]
+            assert len(set(got.tolist())) == c
+            keys = [(float(dists[i, j]), int(ids[i, j])) for j in range(c)]
+            assert keys == sorted(keys)
+            reach, todo = set(int(s) for s in seeds[i]), [int(s) for s in seeds[i]]
+            while todo:
+                for t in lists[todo.pop() - 1]:
+                    if t not in reach:
+                        reach.add(t)
+                        todo.append(t)
+            assert set(got.tolist()) <= reach
+            assert stats[i, 0] <= len(reach)     # distance computations: at most one per reachable object
+
+
+@settings(max_examples=25, deadline=None, derandomize=True)
+@given(st.integers(0, 2 ** 31 - 1), st.integers(1, 6), st.integers(1, 12))
+def test_key_format_round_trip_and_merge_is_the_union(seed, world, k):
+    from ngt_b200 import sharded
+    rng = np.random.default_rng(seed)
+    nq, n_local = 5, 50
+    per, union = [], [[] for _ in range(nq)]
+    for r in range(world):
+        counts = rng.integers(0, k + 1, nq).astype(np.uint32)
+        ids = np.zeros((nq, k), np.uint32)
+        d = np.zeros((nq, k), np.float32)
+        for qi in range(nq):
+            c = int(counts[qi])
+            # few distinct distance values: ties across shards are the rule, and are broken by the global id
+            rows = sorted(zip(rng.integers(0, 4, c).astype(np.float32).tolist(), rng.choice(n_local, c, replace=False) + 1))
+            for j, (dd, t) in enumerate(rows):
+                ids[qi, j], d[qi, j] = t, dd
+                union[qi].append((dd, int(t) + r * n_local))
+        keys = sharded.pack_keys_host(ids, d, counts, r * n_local)
+        ui, ud, valid = sharded.unpack_keys_host(keys)
+        assert (valid.sum(1) == counts).all()
+        for qi in range(nq):
+            c = int(counts[qi])
+            assert (ui[qi, :c] == ids[qi, :c] + r * n_local).all() and (ud[qi, :c] == d[qi, :c]).all()
+            assert (np.diff(keys[qi, :c].astype(np.uint64)) > 0).all() if c > 1 else True   # key order == (distance, id) order
+        per.append(keys)
+    mi, md, mc = sharded.merge_keys_host(np.stack(per), k)
+    for qi in range(nq):
+        want = sorted(union[qi])[:k]
+        assert int(mc[qi]) == len(want)
+        assert [(float(md[qi, j]), int(mi[qi, j])) for j in range(len(want))] == want
