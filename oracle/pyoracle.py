@@ -503,3 +503,39 @@ def remove_edges_reliably_loop(port, dtype, otype, pobj, lists, node_id):
         if i + 1 != minj:
             order[i + 1], order[minj] = order[minj], order[i + 1]
     lists[node_id] = []
+
+
+def full_sort_lists(old, new):
+    """What insertANNGNode's reverse-edge insertion converges to for ONE node's list as the engine's full sort states it
+    (csr_from_triples, ngt_b200/csrc/graph_ops.cu; lib/NGT/Graph.h:845-886 inserts by lower_bound on (distance, id) and
+    rejects an id that is already there): the keys of the old list and of the batch's new edges sorted ascending, an
+    entry dropped when its target (low 32 bits of the key) equals the entry before it. Test infrastructure."""
+    out, prev = [], None
+    for k in sorted(list(old) + list(new)):
+        if prev is None or (k & 0xFFFFFFFF) != (prev & 0xFFFFFFFF):
+            out.append(k)
+        prev = k
+    return out
+
+
+def merge_lists_by_rank(old, new):
+    """The rank merge of merge_lists_kernel (ngt_b200/csrc/graph_ops.cu), restated: an old key moves up by the number of
+    new keys below it, a new key lands behind the old keys not above it; `redo` is raised for a list that is not
+    strictly ascending / repeats a target in neighbouring entries, or when a new key's target equals the old entry on
+    either side of its place or the new key before it -- the cases in which the full sort (above) is taken instead.
+    old, new: ascending lists of 64-bit keys (ordered distance bits << 32 | target). -> (merged keys, redo)."""
+    import bisect
+    redo = False
+    out = [None] * (len(old) + len(new))
+    for i, ka in enumerate(old):
+        if i + 1 < len(old) and (old[i + 1] <= ka or (old[i + 1] & 0xFFFFFFFF) == (ka & 0xFFFFFFFF)):
+            redo = True
+        out[i + bisect.bisect_left(new, ka)] = ka
+    for j, kb in enumerate(new):
+        lo = bisect.bisect_right(old, kb)
+        t = kb & 0xFFFFFFFF
+        out[j + lo] = kb
+        if (lo > 0 and (old[lo - 1] & 0xFFFFFFFF) == t) or (lo < len(old) and (old[lo] & 0xFFFFFFFF) == t) or \
+                (j > 0 and (new[j - 1] & 0xFFFFFFFF) == t):
+            redo = True
+    return out, redo

@@ -130,3 +130,33 @@ def test_key_format_round_trip_and_merge_is_the_union(seed, world, k):
         want = sorted(union[qi])[:k]
         assert int(mc[qi]) == len(want)
         assert [(float(md[qi, j]), int(mi[qi, j])) for j in range(len(want))] == want
+
+
+@settings(max_examples=300, deadline=None, derandomize=True)
+@given(st.integers(0, 2 ** 31 - 1), st.integers(0, 40), st.integers(0, 12), st.booleans())
+def test_rank_merge_of_the_construction_loop_equals_the_full_sort(seed, n_old, n_new, allow_repeats):
+    """ngtgpu_index_insert_batch merges a batch's new edges into a node's sorted list by rank (merge_lists_kernel) and
+    takes the full sort when the kernel raises its flag. Restated in oracle/pyoracle.py: whenever the flag stays down the
+    rank merge IS the full sort's list (which drops an entry whose target equals the entry before it), and the flag is
+    up whenever the full sort would have dropped anything."""
+    rng = np.random.default_rng(seed)
+    targets = rng.choice(60, n_old + n_new, replace=allow_repeats) + 1      # few distances: ties are the rule
+    keys = [(int(rng.integers(0, 5)) << 32) | int(t) for t in targets]
+    if allow_repeats and n_old and n_new and rng.random() < 0.5:
+        keys[n_old] = keys[int(rng.integers(0, n_old))]                   # the same edge again (an id inserted twice)
+    old = sorted(set(keys[:n_old]))
+    if not allow_repeats or rng.random() < 0.5:
+        seen, uniq = set(), []
+        for k in old:                                                     # a list as the engine keeps it: one entry per target
+            if k & 0xFFFFFFFF not in seen:
+                uniq.append(k)
+                seen.add(k & 0xFFFFFFFF)
+        old = uniq
+    new = sorted(keys[n_old:])
+    want = po.full_sort_lists(old, new)
+    got, redo = po.merge_lists_by_rank(old, new)
+    if len(want) != len(old) + len(new):
+        assert redo                      # something was dropped: the batch must take the full sort
+    if not redo:
+        assert got == want
+        assert all(b > a for a, b in zip(got, got[1:]))
