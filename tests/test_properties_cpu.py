@@ -160,3 +160,44 @@ def test_rank_merge_of_the_construction_loop_equals_the_full_sort(seed, n_old, n
     if not redo:
         assert got == want
         assert all(b > a for a, b in zip(got, got[1:]))
+
+
+KEY_NONE = 0xFFFFFFFFFFFFFFFF
+
+
+def _res_insert(res, kk, k, kl):
+    """search_fast.cuh res_insert<KL>, lane by lane: res[lane][slot], position p on lane p // KL, slot p % KL."""
+    pos = sum(1 for lane in range(32) for m in range(kl) if res[lane][m] < kk)            # KL ballots + popc
+    up = [res[lane - 1][kl - 1] if lane > 0 else res[0][kl - 1] for lane in range(32)]    # shfl_up of the last slot
+    for lane in range(32):
+        for m in range(kl - 1, -1, -1):
+            idx = lane * kl + m
+            prev = res[lane][m - 1] if m > 0 else up[lane]
+            if idx == pos:
+                res[lane][m] = kk
+            elif idx > pos:
+                res[lane][m] = prev
+            if idx >= k:
+                res[lane][m] = KEY_NONE
+
+
+@settings(max_examples=60, deadline=None, derandomize=True)
+@given(st.integers(0, 2 ** 31 - 1), st.sampled_from([1, 4]), st.integers(1, 128), st.integers(0, 300))
+def test_result_list_of_the_lean_kernel_is_the_k_smallest(seed, kl, k, n_keys):
+    """The control warp's result list (search_fast.cuh: KL keys per lane, k <= 32 * KL) after any sequence of distinct
+    keys holds the k smallest in ascending positions, and res_kth reads position k - 1 -- ResultSet + the pop of the
+    extras in NeighborhoodGraph::search (lib/NGT/Graph.cpp:467-479), restated lane by lane."""
+    k = min(k, 32 * kl)
+    rng = np.random.default_rng(seed)
+    keys = [(int(d) << 32) | int(t) for d, t in zip(rng.integers(0, 50, n_keys), rng.permutation(n_keys) + 1)]
+    res = [[KEY_NONE] * kl for _ in range(32)]
+    seen = []
+    for kk in keys:
+        _res_insert(res, kk, k, kl)
+        seen.append(kk)
+        want = sorted(seen)[:k]
+        flat = [res[p // kl][p % kl] for p in range(32 * kl)]
+        assert flat[:len(want)] == want
+        assert all(v == KEY_NONE for v in flat[len(want):])
+        kth = res[(k - 1) // kl][(k - 1) % kl]                                          # res_kth<KL>(res, k - 1)
+        assert kth == (want[k - 1] if len(want) == k else KEY_NONE)
