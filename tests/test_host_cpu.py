@@ -31,6 +31,18 @@ def test_c_abi_exports_every_declared_symbol():
         assert name in _lib.SYMBOLS and name in declared
 
 
+def test_public_headers_are_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/*.h compile as pedantic C99 and as C++11 (plain pointers and sizes, no
+    C++ or torch types in any signature), so a cgo / JNI / ctypes / C++ host can bind them."""
+    src = tmp_path / "hdr.c"
+    src.write_text('#include "ngtgpu.h"\n#include "ngt_capi_ext.h"\nint main(void) { return 0; }\n')
+    inc = os.path.join(ROOT, "include")
+    for cmd in (["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-I" + inc, str(src)],
+                ["g++", "-std=c++11", "-Wall", "-Werror", "-fsyntax-only", "-I" + inc, "-x", "c++", str(src)]):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, " ".join(cmd) + "\n" + r.stderr
+
+
 def test_additive_capi_header_symbols_are_exported():
     """include/ngt_capi_ext.h: the `ngt_*` entry points the library adds to lib/NGT/Capi.h's 67."""
     from ngt_b200 import _lib
